@@ -1,0 +1,247 @@
+"""ctypes bindings of the CPU oracle (oracle/_build/liblocus_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never by locus_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblocus_oracle.so")
+
+
+def build(force=False):
+    srcs = ["kdtree.c", "bfgs_oracle.c", "gicp_oracle.c", "voxel_oracle.c", "lb_oracle.h"]
+    if not force and os.path.exists(_SO):
+        mt = os.path.getmtime(_SO)
+        if all(os.path.getmtime(os.path.join(_HERE, s)) <= mt for s in srcs):
+            return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+class GicpParams(C.Structure):
+    _fields_ = [
+        ("k_correspondences", C.c_int), ("gicp_epsilon", C.c_double),
+        ("rotation_epsilon", C.c_double), ("transformation_epsilon", C.c_double),
+        ("corr_dist_threshold", C.c_double), ("max_iterations", C.c_int),
+        ("max_inner_iterations", C.c_int), ("num_threads", C.c_int),
+        ("source_cov_from_normals", C.c_int), ("target_cov_from_normals", C.c_int),
+        ("optimizer", C.c_int),
+    ]
+
+
+class GicpResult(C.Structure):
+    _fields_ = [
+        ("final_transformation", C.c_float * 16), ("nr_iterations", C.c_int),
+        ("converged", C.c_int), ("n_correspondences", C.c_int), ("delta", C.c_double),
+        ("n_fdf_evals", C.c_long), ("n_inner_iterations", C.c_long),
+        ("t_covariances_s", C.c_double), ("t_iterations_s", C.c_double), ("t_total_s", C.c_double),
+        ("t_lookups_s", C.c_double), ("t_optimization_s", C.c_double), ("status", C.c_int),
+    ]
+
+
+class VoxelParams(C.Structure):
+    _fields_ = [
+        ("leaf", C.c_float * 3), ("filter_field_offset", C.c_int),
+        ("filter_limit_min", C.c_double), ("filter_limit_max", C.c_double),
+        ("filter_limit_negative", C.c_int), ("min_points_per_voxel", C.c_int),
+        ("downsample_all_data", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.og_gicp_default_params.argtypes = [C.POINTER(GicpParams)]
+        L.og_gicp_align.restype = C.c_int
+        L.og_gicp_align.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+            C.POINTER(GicpParams), C.c_void_p, C.POINTER(GicpResult), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_gicp_covariances.restype = C.c_int
+        L.og_gicp_covariances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        L.og_gicp_fitness.restype = C.c_double
+        L.og_gicp_fitness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_double, C.c_int]
+        L.og_gicp_fdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_gicp_apply_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.og_kdtree_build.restype = C.c_void_p
+        L.og_kdtree_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.og_kdtree_free.argtypes = [C.c_void_p]
+        L.og_kdtree_knn.restype = C.c_int
+        L.og_kdtree_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.og_kdtree_nn_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.og_bfgs_minimize_quadratic.restype = C.c_int
+        L.og_bfgs_minimize_quadratic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double]
+        L.og_voxel_filter.restype = C.c_int
+        L.og_voxel_filter.argtypes = [
+            C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+            C.c_void_p, C.c_int, C.POINTER(VoxelParams), C.c_void_p, C.POINTER(C.c_size_t),
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_normalize_pcloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.og_compute_ap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_params(**kw):
+    p = GicpParams()
+    lib().og_gicp_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _as_cloud(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def gicp_align(src, tgt, params=None, guess=None, src_normal_off=-1, tgt_normal_off=-1,
+               want_cov=False, want_aligned=False):
+    """src/tgt: (n, stride) float32 arrays with xyz in columns 0..2."""
+    src = _as_cloud(src); tgt = _as_cloud(tgt)
+    params = params or default_params()
+    res = GicpResult()
+    g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+    sc = np.zeros((src.shape[0], 9)) if want_cov else None
+    tc = np.zeros((tgt.shape[0], 9)) if want_cov else None
+    al = np.zeros((src.shape[0], 3), dtype=np.float32) if want_aligned else None
+    rc = lib().og_gicp_align(_p(src), src.shape[0], src.shape[1], src_normal_off,
+                             _p(tgt), tgt.shape[0], tgt.shape[1], tgt_normal_off,
+                             C.byref(params), _p(g), C.byref(res), _p(sc), _p(tc), _p(al))
+    out = {
+        "status": rc,
+        "T": np.array(res.final_transformation, dtype=np.float32).reshape(4, 4),
+        "iterations": res.nr_iterations, "converged": bool(res.converged),
+        "n_corr": res.n_correspondences, "delta": res.delta,
+        "n_evals": res.n_fdf_evals, "n_inner": res.n_inner_iterations,
+        "t_cov": res.t_covariances_s, "t_iter": res.t_iterations_s, "t_total": res.t_total_s,
+        "t_lookups": res.t_lookups_s, "t_opt": res.t_optimization_s,
+    }
+    if want_cov:
+        out["src_cov"] = sc.reshape(-1, 3, 3); out["tgt_cov"] = tc.reshape(-1, 3, 3)
+    if want_aligned:
+        out["aligned"] = al
+    return out
+
+
+def covariances(pts, k=20, eps=1e-3, num_threads=1):
+    pts = _as_cloud(pts)
+    out = np.zeros((pts.shape[0], 9))
+    rc = lib().og_gicp_covariances(_p(pts), pts.shape[0], pts.shape[1], k, eps, num_threads, _p(out))
+    if rc:
+        raise RuntimeError("og_gicp_covariances rc=%d" % rc)
+    return out.reshape(-1, 3, 3)
+
+
+def fitness(src, tgt, T, max_range=float(np.finfo(np.float64).max), num_threads=1):
+    src = _as_cloud(src); tgt = _as_cloud(tgt)
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+    return lib().og_gicp_fitness(_p(src), src.shape[0], src.shape[1], _p(tgt), tgt.shape[0], tgt.shape[1],
+                                 _p(T), max_range, num_threads)
+
+
+def fdf(src4, tgt4, M, x):
+    src4 = np.ascontiguousarray(src4, dtype=np.float32); tgt4 = np.ascontiguousarray(tgt4, dtype=np.float32)
+    M = np.ascontiguousarray(M, dtype=np.float64).reshape(-1, 9)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    f = C.c_double(); g = np.zeros(6)
+    lib().og_gicp_fdf(_p(src4), _p(tgt4), _p(M), src4.shape[0], _p(x), C.byref(f), _p(g))
+    return f.value, g
+
+
+def apply_state(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    T = np.zeros(16, dtype=np.float32)
+    lib().og_gicp_apply_state(_p(x), _p(T))
+    return T.reshape(4, 4)
+
+
+class KdTree:
+    def __init__(self, pts):
+        self.pts = _as_cloud(pts)
+        self.h = lib().og_kdtree_build(_p(self.pts), self.pts.shape[0], self.pts.shape[1])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().og_kdtree_free(self.h); self.h = None
+
+    def knn(self, q, k):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        idx = np.zeros(k, dtype=np.int32); d2 = np.zeros(k, dtype=np.float32)
+        c = lib().og_kdtree_knn(self.h, _p(q), k, _p(idx), _p(d2))
+        return idx[:c], d2[:c]
+
+    def nn_batch(self, q, num_threads=1):
+        q = _as_cloud(q)
+        idx = np.zeros(q.shape[0], dtype=np.int32); d2 = np.zeros(q.shape[0], dtype=np.float32)
+        lib().og_kdtree_nn_batch(self.h, _p(q), q.shape[0], q.shape[1], _p(idx), _p(d2), num_threads)
+        return idx, d2
+
+
+def bfgs_quadratic(A, b, x0, max_iters=100, grad_tol=1e-8):
+    A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64)
+    it = lib().og_bfgs_minimize_quadratic(_p(A), _p(b), A.shape[0], _p(x), max_iters, grad_tol)
+    return x, it
+
+
+def voxel_filter(blob, point_step, leaf, x_off=0, y_off=4, z_off=8, float_fields=None,
+                 filter_field_offset=-1, limit_min=-3.4028234663852886e38, limit_max=3.4028234663852886e38,
+                 negative=False, min_points_per_voxel=0, downsample_all_data=True):
+    """blob: uint8 array of n*point_step bytes.  Returns dict(out, voxel_idx, first_pt, count, min_b, div_b, rc)."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
+    n = blob.size // point_step
+    if float_fields is None:
+        float_fields = [x_off, y_off, z_off]
+    ffo = np.array(float_fields, dtype=np.uint32)
+    P = VoxelParams()
+    if np.isscalar(leaf):
+        leaf = (leaf, leaf, leaf)
+    P.leaf[0], P.leaf[1], P.leaf[2] = [np.float32(v) for v in leaf]
+    P.filter_field_offset = filter_field_offset
+    P.filter_limit_min = limit_min; P.filter_limit_max = limit_max
+    P.filter_limit_negative = int(negative); P.min_points_per_voxel = min_points_per_voxel
+    P.downsample_all_data = int(downsample_all_data)
+    out = np.zeros(max(n, 1) * point_step, dtype=np.uint8)
+    vidx = np.zeros(max(n, 1), dtype=np.int32); first = np.zeros(max(n, 1), dtype=np.int32)
+    cnt = np.zeros(max(n, 1), dtype=np.int32)
+    min_b = np.zeros(3, dtype=np.int32); div_b = np.zeros(3, dtype=np.int32)
+    n_out = C.c_size_t(0)
+    rc = lib().og_voxel_filter(_p(blob), n, point_step, x_off, y_off, z_off, _p(ffo), len(ffo), C.byref(P),
+                               _p(out), C.byref(n_out), _p(vidx), _p(first), _p(cnt), _p(min_b), _p(div_b))
+    m = n_out.value
+    return {"rc": rc, "out": out[: m * point_step].reshape(m, point_step), "voxel_idx": vidx[:m],
+            "first_pt": first[:m], "count": cnt[:m], "min_b": min_b, "div_b": div_b}
+
+
+def normalize_pcloud(xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros_like(xyz)
+    lib().og_normalize_pcloud(_p(xyz), xyz.shape[0], _p(out))
+    return out
+
+
+def compute_ap(query_xyz, ref_normals, correspondences):
+    q = np.ascontiguousarray(query_xyz, dtype=np.float32).reshape(-1, 3)
+    nr = np.ascontiguousarray(ref_normals, dtype=np.float32).reshape(-1, 3)
+    co = np.ascontiguousarray(correspondences, dtype=np.int64)
+    Ap = np.zeros(36)
+    lib().og_compute_ap(_p(q), q.shape[0], _p(nr), _p(co), _p(Ap))
+    return Ap.reshape(6, 6)
