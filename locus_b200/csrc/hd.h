@@ -1,0 +1,365 @@
+// hd.h -- scalar math shared by every kernel of the GICP / VoxelGrid path.
+//
+// Everything here is `__host__ __device__` so that the per-point logic the
+// kernels run can also be compiled by g++ into the CPU test harness
+// (tests/hd_harness.cpp) and checked against the oracle without a GPU.  The
+// product library only ever calls these from CUDA kernels and from the small
+// host-side driver; there is no CPU compute path in the product.
+//
+// Precision contract (mirrors the reference, see DESIGN.md "Numerics"):
+//   * points are float32; T*p is evaluated in float32 with the association
+//     ((c0*x + c1*y) + c2*z) + c3 and NO fused multiply-add
+//     (reference: Matrix4f * Vector4f, gicp.hpp:307,341,382,469);
+//   * residuals, covariances, Mahalanobis matrices and all sums are double
+//     (gicp.hpp:310-314, 484-493);
+//   * the whole library is compiled with -fmad=false so float/double products
+//     and sums round exactly like the reference's x86-64 build.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LB_HD __host__ __device__ __forceinline__
+#define LB_D __device__ __forceinline__
+#else
+#define LB_HD inline
+#define LB_D inline
+#endif
+
+namespace lb {
+
+struct f4 { float x, y, z, w; };  // same layout as CUDA float4
+
+LB_HD float bits_to_float(int32_t i) { union { int32_t i; float f; } u; u.i = i; return u.f; }
+LB_HD int32_t float_to_bits(float f) { union { int32_t i; float f; } u; u.f = f; return u.i; }
+
+// ---------------------------------------------------------------- rigid transform
+// Row-major 3x4 float [R|t].  ((r0*x + r1*y) + r2*z) + t  (Eigen coefficient order).
+LB_HD void xform(const float* T, float x, float y, float z, float& ox, float& oy, float& oz) {
+  float v;
+  v = T[0] * x; v = v + T[1] * y; v = v + T[2] * z; ox = v + T[3];
+  v = T[4] * x; v = v + T[5] * y; v = v + T[6] * z; oy = v + T[7];
+  v = T[8] * x; v = v + T[9] * y; v = v + T[10] * z; oz = v + T[11];
+}
+// pcl::transformPointCloud (PCL 1.10 Transformer::se3): p0 + (p1 + (p2 + t)).
+LB_HD void xform_pcl(const float* T, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = T[0] * x + (T[1] * y + (T[2] * z + T[3]));
+  oy = T[4] * x + (T[5] * y + (T[6] * z + T[7]));
+  oz = T[8] * x + (T[9] * y + (T[10] * z + T[11]));
+}
+
+// applyState on identity (gicp.hpp:619-634): R = Rz(x5) Ry(x4) Rx(x3) built in
+// float32 through Eigen's AngleAxisf -> Quaternionf products -> toRotationMatrix.
+// sin/cos of the half angles are taken in double and rounded to float: that is
+// the correctly rounded float result on host and device alike (glibc sinf/cosf
+// used by the reference are correctly rounded in all but vanishingly few cases).
+LB_HD void apply_state(const double* x, float* T /*12: row-major 3x4*/) {
+  float az = (float)x[5], ay = (float)x[4], ax = (float)x[3];
+  float hz = 0.5f * az, hy = 0.5f * ay, hx = 0.5f * ax;
+  float cz = (float)cos((double)hz), sz = (float)sin((double)hz);
+  float cy = (float)cos((double)hy), sy = (float)sin((double)hy);
+  float cx = (float)cos((double)hx), sx = (float)sin((double)hx);
+  float w1 = cz * cy, x1 = -(sz * sy), y1 = cz * sy, z1 = sz * cy;
+  float qw = w1 * cx - x1 * sx;
+  float qx = w1 * sx + x1 * cx;
+  float qy = y1 * cx + z1 * sx;
+  float qz = z1 * cx - y1 * sx;
+  float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+  float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  T[0] = 1.0f - (tyy + tzz); T[1] = txy - twz;          T[2] = txz + twy;           T[3] = (float)x[0];
+  T[4] = txy + twz;          T[5] = 1.0f - (txx + tzz); T[6] = tyz - twx;           T[7] = (float)x[1];
+  T[8] = txz - twy;          T[9] = tyz + twx;          T[10] = 1.0f - (txx + tyy); T[11] = (float)x[2];
+}
+
+// State from a transform (gicp.hpp:235-241), float entries promoted to double.
+LB_HD void state_from_transform(const float* T, double* x) {
+  x[0] = T[3]; x[1] = T[7]; x[2] = T[11];
+  x[3] = atan2((double)T[9], (double)T[10]);
+  x[4] = asin(-(double)T[8]);
+  x[5] = atan2((double)T[4], (double)T[0]);
+}
+
+// dR/d(phi,theta,psi) closed forms (gicp.hpp:175-209), row-major 3x3 each.
+LB_HD void r_derivatives(const double* x, double* dP, double* dT, double* dS) {
+  double phi = x[3], theta = x[4], psi = x[5];
+  double cphi = cos(phi), sphi = sin(phi);
+  double ctheta = cos(theta), stheta = sin(theta);
+  double cpsi = cos(psi), spsi = sin(psi);
+  dP[0] = 0.; dP[3] = 0.; dP[6] = 0.;
+  dP[1] = sphi * spsi + cphi * cpsi * stheta;
+  dP[4] = -cpsi * sphi + cphi * spsi * stheta;
+  dP[7] = cphi * ctheta;
+  dP[2] = cphi * spsi - cpsi * sphi * stheta;
+  dP[5] = -cphi * cpsi - sphi * spsi * stheta;
+  dP[8] = -ctheta * sphi;
+
+  dT[0] = -cpsi * stheta; dT[3] = -spsi * stheta; dT[6] = -ctheta;
+  dT[1] = cpsi * ctheta * sphi; dT[4] = ctheta * sphi * spsi; dT[7] = -sphi * stheta;
+  dT[2] = cphi * cpsi * ctheta; dT[5] = cphi * ctheta * spsi; dT[8] = -cphi * stheta;
+
+  dS[0] = -ctheta * spsi; dS[3] = cpsi * ctheta; dS[6] = 0.;
+  dS[1] = -cphi * cpsi - sphi * spsi * stheta;
+  dS[4] = -cphi * spsi + cpsi * sphi * stheta;
+  dS[7] = 0.;
+  dS[2] = cpsi * sphi - cphi * spsi * stheta;
+  dS[5] = sphi * spsi + cphi * cpsi * stheta;
+  dS[8] = 0.;
+}
+
+// g[3..5] = tr(dR_k * Rhat)  (computeRDerivative + matricesInnerProd, gicp.hpp:211-213, gicp.h:361-370)
+LB_HD void rotation_gradient(const double* x, const double* Rhat /*row-major 3x3*/, double* g) {
+  double dP[9], dT[9], dS[9];
+  r_derivatives(x, dP, dT, dS);
+  double r0 = 0., r1 = 0., r2 = 0.;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      r0 += dP[j * 3 + i] * Rhat[i * 3 + j];
+      r1 += dT[j * 3 + i] * Rhat[i * 3 + j];
+      r2 += dS[j * 3 + i] * Rhat[i * 3 + j];
+    }
+  g[3] = r0; g[4] = r1; g[5] = r2;
+}
+
+// ---------------------------------------------------------------- symmetric 3x3
+// Symmetric matrices are stored as 6 doubles: [xx, xy, xz, yy, yz, zz].
+enum { SXX = 0, SXY = 1, SXZ = 2, SYY = 3, SYZ = 4, SZZ = 5 };
+
+template <int P, int Q, int R>
+LB_HD void jacobi_rotate(double (&A)[3][3], double (&V)[3][3], int sweep) {
+  double apq = A[P][Q];
+  if (apq == 0.0) return;
+  double g = 100.0 * fabs(apq);
+  if (sweep > 3 && fabs(A[P][P]) + g == fabs(A[P][P]) && fabs(A[Q][Q]) + g == fabs(A[Q][Q])) {
+    A[P][Q] = A[Q][P] = 0.0;
+    return;
+  }
+  double h = A[Q][Q] - A[P][P];
+  double t;
+  if (fabs(h) + g == fabs(h)) {
+    t = apq / h;
+  } else {
+    double theta = 0.5 * h / apq;
+    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+    if (theta < 0.0) t = -t;
+  }
+  double c = 1.0 / sqrt(1.0 + t * t);
+  double s = t * c;
+  double tau = s / (1.0 + c);
+  double hh = t * apq;
+  A[P][P] -= hh;
+  A[Q][Q] += hh;
+  A[P][Q] = A[Q][P] = 0.0;
+  double arp = A[R][P], arq = A[R][Q];
+  A[R][P] = A[P][R] = arp - s * (arq + arp * tau);
+  A[R][Q] = A[Q][R] = arq + s * (arp - arq * tau);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double vkp = V[k][P], vkq = V[k][Q];
+    V[k][P] = vkp - s * (vkq + vkp * tau);
+    V[k][Q] = vkq + s * (vkp - vkq * tau);
+  }
+}
+
+// GICP covariance regularisation (gicp.hpp:139-153): SVD of the symmetric
+// sample covariance, singular values replaced by (1, 1, eps).  cov is the full
+// symmetric 3x3; out is [xx xy xz yy yz zz] of  sum_k v_k u_k u_k'.
+LB_HD void regularise_cov(double (&A)[3][3], double eps, double* out6) {
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 12; sweep++) {
+    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off == 0.0) break;
+    jacobi_rotate<0, 1, 2>(A, V, sweep);
+    jacobi_rotate<0, 2, 1>(A, V, sweep);
+    jacobi_rotate<1, 2, 0>(A, V, sweep);
+  }
+  double d0 = fabs(A[0][0]), d1 = fabs(A[1][1]), d2 = fabs(A[2][2]);
+  // stable descending order of |d|: find order (o0,o1,o2)
+  int o0 = 0, o1 = 1, o2 = 2;
+  // insertion sort, identical tie behaviour to the oracle (strict '<' moves)
+  if (d0 < d1) { int t = o0; o0 = o1; o1 = t; double td = d0; d0 = d1; d1 = td; }
+  if (d1 < d2) {
+    int t = o1; o1 = o2; o2 = t; double td = d1; d1 = d2; d2 = td;
+    if (d0 < d1) { t = o0; o0 = o1; o1 = t; td = d0; d0 = d1; d1 = td; }
+  }
+  double u0[3], u1[3], u2[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    u0[r] = (o0 == 0) ? V[r][0] : ((o0 == 1) ? V[r][1] : V[r][2]);
+    u1[r] = (o1 == 0) ? V[r][0] : ((o1 == 1) ? V[r][1] : V[r][2]);
+    u2[r] = (o2 == 0) ? V[r][0] : ((o2 == 1) ? V[r][1] : V[r][2]);
+  }
+  // out(r,c) = ((0 + (1*u0r)*u0c) + (1*u1r)*u1c) + (eps*u2r)*u2c   for r <= c
+  const int RR[6] = {0, 0, 0, 1, 1, 2};
+  const int CC[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int e = 0; e < 6; e++) {
+    int r = RR[e], c = CC[e];
+    double acc = 0.0;
+    acc += (1.0 * u0[r]) * u0[c];
+    acc += (1.0 * u1[r]) * u1[c];
+    acc += (eps * u2[r]) * u2[c];
+    out6[e] = acc;
+  }
+}
+
+// Sample covariance from accumulated moments (gicp.hpp:129-137), then regularise.
+// mean[3] = sum p ; m2 = [xx, yx, yy, zx, zy, zz] sums of float products.
+LB_HD void cov_from_moments(const double* sum, const double* m2, int k, double eps, double* out6) {
+  double kk = (double)k;
+  double mx = sum[0] / kk, my = sum[1] / kk, mz = sum[2] / kk;
+  double A[3][3];
+  A[0][0] = m2[0] / kk - mx * mx;
+  A[1][0] = m2[1] / kk - my * mx;
+  A[1][1] = m2[2] / kk - my * my;
+  A[2][0] = m2[3] / kk - mz * mx;
+  A[2][1] = m2[4] / kk - mz * my;
+  A[2][2] = m2[5] / kk - mz * mz;
+  A[0][1] = A[1][0]; A[0][2] = A[2][0]; A[1][2] = A[2][1];
+  regularise_cov(A, eps, out6);
+}
+
+// From-normals covariance (gicp.hpp:81-82; external CalculateCovarianceFromNormals,
+// parity unpinned): C = I - (1-eps) n n'.
+LB_HD void cov_from_normal(float nx, float ny, float nz, double eps, double* out6) {
+  double n[3] = {(double)nx, (double)ny, (double)nz};
+  double s = 1.0 - eps;
+  out6[SXX] = 1.0 - s * n[0] * n[0];
+  out6[SXY] = 0.0 - s * n[0] * n[1];
+  out6[SXZ] = 0.0 - s * n[0] * n[2];
+  out6[SYY] = 1.0 - s * n[1] * n[1];
+  out6[SYZ] = 0.0 - s * n[1] * n[2];
+  out6[SZZ] = 1.0 - s * n[2] * n[2];
+}
+
+// Mahalanobis matrix M = (R C1 R' + C2)^-1  (gicp.hpp:484-493).  R row-major
+// 3x3 double; C1, C2, M symmetric-6.  Products follow the reference order
+// (R*C1 first, then *R'), inverse by cofactors / determinant like
+// Eigen::Matrix3d::inverse().
+LB_HD void mahalanobis(const double* R, const double* C1, const double* C2, double* M) {
+  double c[3][3] = {{C1[SXX], C1[SXY], C1[SXZ]}, {C1[SXY], C1[SYY], C1[SYZ]}, {C1[SXZ], C1[SYZ], C1[SZZ]}};
+  double rc[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) rc[i][j] = (R[i * 3 + 0] * c[0][j] + R[i * 3 + 1] * c[1][j]) + R[i * 3 + 2] * c[2][j];
+  double t[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++)
+      t[i][j] = (rc[i][0] * R[j * 3 + 0] + rc[i][1] * R[j * 3 + 1]) + rc[i][2] * R[j * 3 + 2];
+  double a = t[0][0] + C2[SXX], b = t[0][1] + C2[SXY], cc = t[0][2] + C2[SXZ];
+  double d = t[1][1] + C2[SYY], e = t[1][2] + C2[SYZ], f = t[2][2] + C2[SZZ];
+  // symmetric matrix [[a b cc],[b d e],[cc e f]]
+  double k00 = d * f - e * e;
+  double k01 = e * cc - b * f;   // cofactor(1,0) = m(2,1)m(0,2) - m(2,2)m(0,1)
+  double k02 = b * e - cc * d;   // cofactor(2,0) = m(0,1)m(1,2) - m(0,2)m(1,1)
+  double det = (k00 * a + k01 * b) + k02 * cc;
+  double inv = 1.0 / det;
+  M[SXX] = k00 * inv;
+  M[SXY] = k01 * inv;
+  M[SXZ] = k02 * inv;
+  M[SYY] = (f * a - cc * cc) * inv;
+  M[SYZ] = (cc * b - e * a) * inv;  // cofactor(2,1) = m(0,2)m(1,0) - m(0,0)m(1,2)
+  M[SZZ] = (a * d - b * b) * inv;
+}
+
+// ---------------------------------------------------------------- objective
+// Per-correspondence contribution to the 13 sums of the GICP objective
+// (gicp.hpp:373-397): f += r'Mr ; gt += Mr ; Rhat += p (Mr)'.
+// T: row-major 3x4 float; p: source point (already guess-transformed);
+// q: matched target point; M symmetric-6 (all-zero M => exact zero contribution).
+LB_HD void objective_terms(const float* T, float px, float py, float pz, float qx, float qy, float qz,
+                           const double* M, double* acc /*13*/) {
+  float tx, ty, tz;
+  xform(T, px, py, pz, tx, ty, tz);
+  double r0 = (double)(tx - qx), r1 = (double)(ty - qy), r2 = (double)(tz - qz);
+  double t0 = (M[SXX] * r0 + M[SXY] * r1) + M[SXZ] * r2;
+  double t1 = (M[SXY] * r0 + M[SYY] * r1) + M[SYZ] * r2;
+  double t2 = (M[SXZ] * r0 + M[SYZ] * r1) + M[SZZ] * r2;
+  acc[0] += (r0 * t0 + r1 * t1) + r2 * t2;
+  acc[1] += t0; acc[2] += t1; acc[3] += t2;
+  double dx = (double)px, dy = (double)py, dz = (double)pz;
+  acc[4] += dx * t0; acc[5] += dx * t1; acc[6] += dx * t2;
+  acc[7] += dy * t0; acc[8] += dy * t1; acc[9] += dy * t2;
+  acc[10] += dz * t0; acc[11] += dz * t1; acc[12] += dz * t2;
+}
+
+// Turn the 13 reduced sums into f and the 6-gradient (gicp.hpp:398-401).
+LB_HD void objective_finish(const double* sums /*13*/, int m, const double* x, double* f, double* g /*6*/) {
+  *f = sums[0] / (double)m;
+  double sc = 2.0 / m;
+  g[0] = sums[1] * sc; g[1] = sums[2] * sc; g[2] = sums[3] * sc;
+  double Rhat[9];
+  for (int i = 0; i < 9; i++) Rhat[i] = sums[4 + i] * sc;
+  rotation_gradient(x, Rhat, g);
+}
+
+// Gauss-Newton terms (not in the reference): J = [I | dP p, dT p, dS p],
+// H += J'MJ (21 upper-tri), b += J'Mr (6), f += r'Mr.  acc: 28 doubles [f, b0..5, H00,H01,..H55 upper].
+LB_HD void gn_terms(const float* T, const double* dP, const double* dT, const double* dS,
+                    float px, float py, float pz, float qx, float qy, float qz,
+                    const double* M, double* acc /*28*/) {
+  float tx, ty, tz;
+  xform(T, px, py, pz, tx, ty, tz);
+  double r[3] = {(double)(tx - qx), (double)(ty - qy), (double)(tz - qz)};
+  double p[3] = {(double)px, (double)py, (double)pz};
+  double J[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    J[i][0] = (i == 0); J[i][1] = (i == 1); J[i][2] = (i == 2);
+    J[i][3] = dP[i * 3 + 0] * p[0] + dP[i * 3 + 1] * p[1] + dP[i * 3 + 2] * p[2];
+    J[i][4] = dT[i * 3 + 0] * p[0] + dT[i * 3 + 1] * p[1] + dT[i * 3 + 2] * p[2];
+    J[i][5] = dS[i * 3 + 0] * p[0] + dS[i * 3 + 1] * p[1] + dS[i * 3 + 2] * p[2];
+  }
+  double Mm[3][3] = {{M[SXX], M[SXY], M[SXZ]}, {M[SXY], M[SYY], M[SYZ]}, {M[SXZ], M[SYZ], M[SZZ]}};
+  double Mr[3], MJ[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Mr[i] = Mm[i][0] * r[0] + Mm[i][1] * r[1] + Mm[i][2] * r[2];
+#pragma unroll
+    for (int a = 0; a < 6; a++) MJ[i][a] = Mm[i][0] * J[0][a] + Mm[i][1] * J[1][a] + Mm[i][2] * J[2][a];
+  }
+  acc[0] += r[0] * Mr[0] + r[1] * Mr[1] + r[2] * Mr[2];
+  int e = 7;
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    acc[1 + a] += J[0][a] * Mr[0] + J[1][a] * Mr[1] + J[2][a] * Mr[2];
+#pragma unroll
+    for (int b = a; b < 6; b++) {
+      acc[e] += J[0][a] * MJ[0][b] + J[1][a] * MJ[1][b] + J[2][a] * MJ[2][b];
+      e++;
+    }
+  }
+}
+
+// Solve the 6x6 SPD system H d = -b (H given as 21 upper-tri row-major).  Gaussian
+// elimination with partial pivoting in double; returns 0 on success.
+LB_HD int solve6_neg(const double* Hu, const double* b, double* d) {
+  double A[6][7];
+  int e = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) { A[i][j] = Hu[e]; A[j][i] = Hu[e]; e++; }
+  for (int i = 0; i < 6; i++) A[i][6] = -b[i];
+  for (int c = 0; c < 6; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 6; r++) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (fabs(A[piv][c]) < 1e-300) return -1;
+    if (piv != c) for (int j = 0; j < 7; j++) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+    for (int r = c + 1; r < 6; r++) {
+      double f = A[r][c] / A[c][c];
+      for (int j = c; j < 7; j++) A[r][j] -= f * A[c][j];
+    }
+  }
+  for (int i = 5; i >= 0; i--) {
+    double s = A[i][6];
+    for (int j = i + 1; j < 6; j++) s -= A[i][j] * d[j];
+    d[i] = s / A[i][i];
+  }
+  return 0;
+}
+
+}  // namespace lb

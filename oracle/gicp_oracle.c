@@ -450,7 +450,7 @@ static int gn_solve(functor_ctx* c, double x[6], int max_inner, long* n_inner) {
     if (solve6(H, nb, dx) != 0) return -1;
     double mx = 0;
     for (int a = 0; a < 6; a++) { x[a] += dx[a]; if (fabs(dx[a]) > mx) mx = fabs(dx[a]); }
-    if (mx < 1e-10) break;
+    if (mx < 1e-6) break; /* below the float32 resolution of T(x) */
   }
   return 0;
 }
