@@ -1,0 +1,216 @@
+/*
+ * locus_b200.h -- C ABI of the B200-native GICP scan matcher and VoxelGrid
+ * front-end that drops in behind LOCUS's registration and filter seams.
+ *
+ * Plain C, plain pointers and sizes; no C++/torch/PCL types cross this
+ * boundary and no exception ever does: every function returns an lb_status
+ * (0 = OK, < 0 = error; lb_last_error_string() gives the text).  On any error
+ * the handle keeps its previous state (the last good pose stays valid), which
+ * is how the reference behaves on solver failure (gicp.hpp:542-547).
+ *
+ * Reference interfaces each entry point replaces (paths relative to the
+ * LOCUS repository):
+ *
+ *   lb_gicp_create/destroy        make_shared<MultithreadedGeneralizedIterativeClosestPoint>
+ *                                 point_cloud_odometry/src/PointCloudOdometry.cc:142-146
+ *                                 point_cloud_localization/src/PointCloudLocalization.cc:229-232
+ *   lb_gicp_set_params            setTransformationEpsilon / setMaxCorrespondenceDistance /
+ *                                 setMaximumIterations / setRANSACIterations /
+ *                                 setMaximumOptimizerIterations / setNumThreads /
+ *                                 enableTimingOutput / RecomputeTarget|SourceCovariance /
+ *                                 setEuclideanFitnessEpsilon
+ *                                 PointCloudOdometry.cc:147-155, PointCloudLocalization.cc:234-245,
+ *                                 multithreaded_gicp/include/multithreaded_gicp/gicp.h:111-143,264-298
+ *   lb_gicp_set_source            icp_->setInputSource()   PointCloudOdometry.cc:265,
+ *                                 PointCloudLocalization.cc:306 (gicp.h:162-179)
+ *   lb_gicp_set_target            icp_->setInputTarget()   PointCloudOdometry.cc:266,
+ *                                 PointCloudLocalization.cc:307 (gicp.h:196-200)
+ *   lb_gicp_align                 icp_->align() + getFinalTransformation() + hasConverged()
+ *                                 PointCloudOdometry.cc:267-269, PointCloudLocalization.cc:309-313
+ *                                 (computeTransformation, gicp.hpp:405-617)
+ *   lb_gicp_transform_source      the `output` cloud of align() (gicp.hpp:586) and
+ *                                 pcl::transformPointCloudWithNormals, PointCloudLocalization.cc:325
+ *   lb_gicp_nn_target             icp_->getSearchMethodTarget()->nearestKSearch(pt, 1, ..)
+ *                                 PointCloudLocalization.cc:327-336
+ *   lb_gicp_fitness               icp_->getFitnessScore()
+ *                                 point_cloud_odometry/test/test_point_cloud_odometry.cpp:298
+ *   lb_voxel_create/destroy       pcl::VoxelGrid<pcl::PCLPointCloud2> impl_
+ *                                 point_cloud_filter/include/point_cloud_filter/custom_voxel_grid.h:25
+ *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
+ *   lb_voxel_set_filter_limits    impl_.setFilterFieldName/Limits/LimitsNegative  custom_voxel_grid.cc:103-134
+ *   lb_voxel_filter               impl_.setInputCloud + setIndices + filter()     custom_voxel_grid.cc:76-87
+ *
+ * Threading: a handle is used from one thread at a time (the reference calls
+ * the seam from the dedicated lidar spinner thread, locus/src/Locus.cc:63-69,
+ * and CustomVoxelGrid::filter holds mutex_, custom_voxel_grid.cc:79).  One
+ * handle owns one CUDA stream; independent scan streams use independent
+ * handles (one per GPU in the multi-GPU mode).
+ *
+ * Ownership: input buffers are borrowed for the duration of the call only;
+ * the library owns all device memory.  `mem` says where a buffer lives.
+ */
+#ifndef LOCUS_B200_H_
+#define LOCUS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_VERSION 100
+
+typedef enum lb_status {
+  LB_OK = 0,
+  LB_ERR_INVALID_ARG = -1,
+  LB_ERR_CUDA = -2,
+  LB_ERR_NO_DEVICE = -3,
+  LB_ERR_EMPTY_SOURCE = -4,       /* gicp.h:164-171: empty source cloud -> error, state untouched */
+  LB_ERR_NO_TARGET = -5,
+  LB_ERR_TOO_FEW_POINTS = -6,     /* gicp.hpp:72-79: k_correspondences > cloud size */
+  LB_ERR_VOXEL_OVERFLOW = -7,     /* leaf size too small: int32 voxel index would overflow */
+  LB_ERR_CAPACITY = -8,           /* output buffer too small */
+  LB_ERR_UNSUPPORTED = -9,
+  LB_ERR_NO_ALIGN = -10           /* result requested before any successful align() */
+} lb_status;
+
+typedef enum lb_mem { LB_MEM_HOST = 0, LB_MEM_DEVICE = 1 } lb_mem;
+typedef enum lb_optimizer { LB_OPT_BFGS = 0, LB_OPT_GAUSS_NEWTON = 1 } lb_optimizer;
+typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1 } lb_execution;
+
+#define LB_NO_NORMALS ((ptrdiff_t)-1)
+
+int lb_version(void);
+const char* lb_last_error_string(void);
+const char* lb_status_string(int status);
+int lb_device_count(int* n);
+
+/* ------------------------------------------------------------------ GICP */
+typedef struct lb_gicp lb_gicp;
+
+typedef struct lb_gicp_params {
+  /* values and defaults: gicp.h:111-127 */
+  int k_correspondences;                /* 20   setCorrespondenceRandomness */
+  double gicp_epsilon;                  /* 1e-3 */
+  double rotation_epsilon;              /* 2e-3 setRotationEpsilon */
+  double transformation_epsilon;        /* 5e-4 setTransformationEpsilon */
+  double max_correspondence_distance;   /* 5.0  setMaxCorrespondenceDistance */
+  int max_iterations;                   /* 200  setMaximumIterations */
+  int max_optimizer_iterations;         /* 20   setMaximumOptimizerIterations */
+  /* 1: k-NN + SVD covariances (gicp.hpp:85-154).  0: from normals
+   * (gicp.hpp:81-82) -- needs normals in the cloud, else falls back to k-NN. */
+  int recompute_source_covariance;      /* reference default 0; here 1 (normals are optional) */
+  int recompute_target_covariance;
+  int optimizer;                        /* lb_optimizer; LB_OPT_BFGS = reference-exact */
+  int execution;                        /* lb_execution; persistent cooperative kernel by default */
+  /* accepted for interface compatibility, no effect on the GPU path */
+  double euclidean_fitness_epsilon;     /* setEuclideanFitnessEpsilon (unused by gicp.hpp too) */
+  int ransac_iterations;                /* setRANSACIterations(0) */
+  int num_threads;                      /* setNumThreads */
+  int enable_timing_output;             /* enableTimingOutput: spans are always in lb_gicp_result */
+  float index_cell_size;                /* voxel-hash cell size in metres; 0 = automatic */
+} lb_gicp_params;
+
+typedef struct lb_gicp_result {
+  float final_transformation[16];  /* row-major 4x4 = previous_transformation_ * guess (gicp.hpp:583) */
+  int converged;                   /* hasConverged(): delta < 1 OR iteration cap (gicp.hpp:566-568) */
+  int iterations;                  /* nr_iterations_ */
+  int n_correspondences;           /* of the last outer iteration */
+  double delta;                    /* last convergence ratio (gicp.hpp:526-541) */
+  int n_objective_evals;           /* fused f+gradient passes */
+  int n_inner_iterations;
+  /* CUDA-event spans, same three spans the reference times (gicp.hpp:588-616) */
+  float t_covariances_ms;
+  float t_iterations_ms;
+  float t_total_ms;
+  int status;
+} lb_gicp_result;
+
+int lb_gicp_default_params(lb_gicp_params* p);
+int lb_gicp_create(int device, lb_gicp** h);
+/* same, but work is enqueued on the caller's cudaStream_t (so the caller can
+ * bracket it with its own CUDA events) */
+int lb_gicp_create_on_stream(int device, void* cuda_stream, lb_gicp** h);
+int lb_gicp_destroy(lb_gicp* h);
+int lb_gicp_set_params(lb_gicp* h, const lb_gicp_params* p);
+int lb_gicp_get_params(lb_gicp* h, lb_gicp_params* p);
+
+/* pts: n points, `stride` bytes apart; float32 x,y,z at byte offset xyz_off;
+ * float32 normal_x,y,z at normal_off (LB_NO_NORMALS if absent).
+ * Builds the voxel-hash index of the cloud and (lazily, in align) its
+ * covariances.  Invalidates previous covariances like gicp.h:177-178,196-200. */
+int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off,
+                       ptrdiff_t normal_off, int mem);
+int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off,
+                       ptrdiff_t normal_off, int mem, uint64_t* generation /* nullable */);
+/* scan-to-scan odometry (PointCloudOdometry.cc:243-244 copies the last scan into
+ * reference_): re-use the current source's index and covariances as the next
+ * target instead of rebuilding them. */
+int lb_gicp_promote_source_to_target(lb_gicp* h);
+
+/* guess: row-major 4x4 float, NULL = identity (the callers pass none). */
+int lb_gicp_align(lb_gicp* h, const float* guess, lb_gicp_result* out);
+
+/* out_pts[i] = T * source[i] (and rotated normals if normal_off >= 0), in the
+ * source's original order and layout.  T NULL = final transformation. */
+int lb_gicp_transform_source(lb_gicp* h, const float* T, void* out_pts, size_t stride, size_t xyz_off,
+                             ptrdiff_t normal_off, int mem);
+/* exact 1-NN of n query points in the current target: original target index
+ * and float32 squared distance. */
+int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int32_t* idx, float* d2, int mem);
+/* pcl::Registration::getFitnessScore(max_range) for transform T (NULL = final). */
+int lb_gicp_fitness(lb_gicp* h, const float* T, double max_range, double* score);
+/* covariances used by the last align, n x 9 doubles row-major, original point order. which: 0 source, 1 target */
+int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points);
+/* number of points currently indexed. which: 0 source, 1 target */
+int lb_gicp_cloud_size(lb_gicp* h, int which, size_t* n);
+/* kernels launched by this handle since creation (bench.py reports it) */
+int lb_gicp_launch_count(lb_gicp* h, uint64_t* n);
+/* CUDA-event duration (ms, averaged per launch) of a named kernel class since the last reset:
+ * "nn_corr", "objective", "knn_cov", "align_persistent", "index_build". */
+int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches);
+int lb_gicp_reset_kernel_times(lb_gicp* h, int enable_timing);
+
+/* ------------------------------------------------------------- VoxelGrid */
+typedef struct lb_voxel lb_voxel;
+
+/* sensor_msgs/PointField datatypes */
+enum { LB_INT8 = 1, LB_UINT8 = 2, LB_INT16 = 3, LB_UINT16 = 4, LB_INT32 = 5, LB_UINT32 = 6,
+       LB_FLOAT32 = 7, LB_FLOAT64 = 8 };
+
+typedef struct lb_field {
+  char name[32];
+  uint32_t offset;
+  uint8_t datatype;
+  uint32_t count;
+} lb_field;
+
+int lb_voxel_create(int device, lb_voxel** h);
+int lb_voxel_create_on_stream(int device, void* cuda_stream, lb_voxel** h);
+int lb_voxel_destroy(lb_voxel* h);
+int lb_voxel_set_leaf_size(lb_voxel* h, float lx, float ly, float lz);
+int lb_voxel_get_leaf_size(lb_voxel* h, float* leaf3);
+/* field_name NULL or "" = no filter field.  Defaults: none, [-FLT_MAX, FLT_MAX], not negative. */
+int lb_voxel_set_filter_limits(lb_voxel* h, const char* field_name, double limit_min, double limit_max, int negative);
+int lb_voxel_set_min_points_per_voxel(lb_voxel* h, int min_points);
+int lb_voxel_set_downsample_all_data(lb_voxel* h, int all);
+
+/* data: n_pts points of point_step bytes described by `fields` (must contain
+ * FLOAT32 x, y, z).  indices: accepted for signature compatibility with
+ * pcl_ros::Filter::filter(); pcl::VoxelGrid<PCLPointCloud2> ignores them and
+ * so does this call.  out: capacity out_capacity_pts points of point_step
+ * bytes; *n_out = number of voxels written (ascending voxel index).
+ * out_voxel_idx (nullable, host or device like out): int32 PCL leaf index of
+ * each output point. */
+int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t point_step,
+                    const lb_field* fields, int n_fields, const int32_t* indices, size_t n_indices,
+                    uint8_t* out, size_t out_capacity_pts, size_t* n_out, int32_t* out_voxel_idx,
+                    int mem_in, int mem_out);
+int lb_voxel_launch_count(lb_voxel* h, uint64_t* n);
+int lb_voxel_kernel_time(lb_voxel* h, float* ms_total_last_call);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCUS_B200_H_ */

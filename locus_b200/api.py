@@ -1,0 +1,382 @@
+"""ctypes binding of liblocus_b200.so + host-side mirror of the reference interface.
+
+GicpB200 mirrors the surface of pcl::MultithreadedGeneralizedIterativeClosestPoint
+that LOCUS's callers use (multithreaded_gicp/include/multithreaded_gicp/gicp.h:134-298,
+PointCloudOdometry.cc:147-155,265-269, PointCloudLocalization.cc:234-245,306-336):
+same method names (setInputSource, setInputTarget, align, getFinalTransformation,
+hasConverged, getFitnessScore, setMaximumIterations, ...), same argument meaning, same
+error behaviour (empty source -> error + state untouched; failure -> last pose kept).
+VoxelGridB200 mirrors point_cloud_filter::CustomVoxelGrid::filter and the setters its
+config_callback drives (custom_voxel_grid.cc:62-149).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblocus_b200.so")
+
+LB_MEM_HOST, LB_MEM_DEVICE = 0, 1
+LB_OPT_BFGS, LB_OPT_GAUSS_NEWTON = 0, 1
+LB_EXEC_PERSISTENT, LB_EXEC_HOST_DRIVEN = 0, 1
+LB_FLOAT32 = 7
+
+
+class LocusB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("locus_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class GicpParams(C.Structure):
+    _fields_ = [
+        ("k_correspondences", C.c_int), ("gicp_epsilon", C.c_double), ("rotation_epsilon", C.c_double),
+        ("transformation_epsilon", C.c_double), ("max_correspondence_distance", C.c_double),
+        ("max_iterations", C.c_int), ("max_optimizer_iterations", C.c_int),
+        ("recompute_source_covariance", C.c_int), ("recompute_target_covariance", C.c_int),
+        ("optimizer", C.c_int), ("execution", C.c_int), ("euclidean_fitness_epsilon", C.c_double),
+        ("ransac_iterations", C.c_int), ("num_threads", C.c_int), ("enable_timing_output", C.c_int),
+        ("index_cell_size", C.c_float),
+    ]
+
+
+class GicpResult(C.Structure):
+    _fields_ = [
+        ("final_transformation", C.c_float * 16), ("converged", C.c_int), ("iterations", C.c_int),
+        ("n_correspondences", C.c_int), ("delta", C.c_double), ("n_objective_evals", C.c_int),
+        ("n_inner_iterations", C.c_int), ("t_covariances_ms", C.c_float), ("t_iterations_ms", C.c_float),
+        ("t_total_ms", C.c_float), ("status", C.c_int),
+    ]
+
+
+class Field(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
+
+
+# every symbol include/locus_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "lb_version", "lb_last_error_string", "lb_status_string", "lb_device_count",
+    "lb_gicp_default_params", "lb_gicp_create", "lb_gicp_create_on_stream", "lb_gicp_destroy",
+    "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
+    "lb_gicp_promote_source_to_target", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
+    "lb_gicp_fitness", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
+    "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
+    "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
+    "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
+    "lb_voxel_set_downsample_all_data", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
+]
+
+
+def lib_path():
+    return _SO
+
+
+def build(force=False, verbose=False):
+    """Compile liblocus_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j4"] + (["-B"] if force else [])
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or out.returncode:
+        print(out.stdout)
+    if out.returncode:
+        raise RuntimeError("building liblocus_b200.so failed")
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly when it is missing: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise LocusB200Error(-3, "liblocus_b200.so not built (run __graft_entry__.build()); "
+                                 "locus_b200 has no CPU fallback")
+    L = C.CDLL(_SO)
+    vp, sz, i32, u64p = C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)
+    L.lb_last_error_string.restype = C.c_char_p
+    L.lb_status_string.restype = C.c_char_p
+    L.lb_status_string.argtypes = [i32]
+    L.lb_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.lb_gicp_default_params.argtypes = [C.POINTER(GicpParams)]
+    L.lb_gicp_create.argtypes = [i32, C.POINTER(vp)]
+    L.lb_gicp_create_on_stream.argtypes = [i32, vp, C.POINTER(vp)]
+    L.lb_gicp_destroy.argtypes = [vp]
+    L.lb_gicp_set_params.argtypes = [vp, C.POINTER(GicpParams)]
+    L.lb_gicp_get_params.argtypes = [vp, C.POINTER(GicpParams)]
+    L.lb_gicp_set_source.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32]
+    L.lb_gicp_set_target.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32, u64p]
+    L.lb_gicp_promote_source_to_target.argtypes = [vp]
+    L.lb_gicp_align.argtypes = [vp, vp, C.POINTER(GicpResult)]
+    L.lb_gicp_transform_source.argtypes = [vp, vp, vp, sz, sz, C.c_ssize_t, i32]
+    L.lb_gicp_nn_target.argtypes = [vp, vp, sz, sz, vp, vp, i32]
+    L.lb_gicp_fitness.argtypes = [vp, vp, C.c_double, C.POINTER(C.c_double)]
+    L.lb_gicp_get_covariances.argtypes = [vp, i32, vp, sz]
+    L.lb_gicp_cloud_size.argtypes = [vp, i32, C.POINTER(sz)]
+    L.lb_gicp_launch_count.argtypes = [vp, u64p]
+    L.lb_gicp_kernel_time.argtypes = [vp, C.c_char_p, C.POINTER(C.c_float), u64p]
+    L.lb_gicp_reset_kernel_times.argtypes = [vp, i32]
+    L.lb_voxel_create.argtypes = [i32, C.POINTER(vp)]
+    L.lb_voxel_create_on_stream.argtypes = [i32, vp, C.POINTER(vp)]
+    L.lb_voxel_destroy.argtypes = [vp]
+    L.lb_voxel_set_leaf_size.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    L.lb_voxel_get_leaf_size.argtypes = [vp, vp]
+    L.lb_voxel_set_filter_limits.argtypes = [vp, C.c_char_p, C.c_double, C.c_double, i32]
+    L.lb_voxel_set_min_points_per_voxel.argtypes = [vp, i32]
+    L.lb_voxel_set_downsample_all_data.argtypes = [vp, i32]
+    L.lb_voxel_filter.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, vp, sz, vp, sz,
+                                  C.POINTER(sz), vp, i32, i32]
+    L.lb_voxel_launch_count.argtypes = [vp, u64p]
+    L.lb_voxel_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        raise LocusB200Error(status, lib().lb_last_error_string().decode(errors="replace"))
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().lb_device_count(C.byref(n))
+    return n.value
+
+
+def _ptr(a):
+    """host numpy array -> (void*, LB_MEM_HOST); int -> raw device pointer."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def xyzi_fields():
+    """PointField list of pcl::PointXYZI as it leaves BodyFilter (body_filter.cc:36-39)."""
+    return [("x", 0, LB_FLOAT32, 1), ("y", 4, LB_FLOAT32, 1), ("z", 8, LB_FLOAT32, 1), ("intensity", 16, LB_FLOAT32, 1)]
+
+
+class GicpB200:
+    """Mirror of the pcl::Registration surface LOCUS calls (see module docstring)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        L = lib()
+        if stream is None:
+            _check(L.lb_gicp_create(device, C.byref(self._h)))
+        else:
+            _check(L.lb_gicp_create_on_stream(device, C.c_void_p(int(stream)), C.byref(self._h)))
+        self._p = GicpParams()
+        L.lb_gicp_default_params(C.byref(self._p))
+        self._res = None
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lb_gicp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # ---- configuration (gicp.h:134-143,264-298 + pcl::Registration setters)
+    def _apply(self):
+        _check(lib().lb_gicp_set_params(self._h, C.byref(self._p)))
+
+    def setTransformationEpsilon(self, v): self._p.transformation_epsilon = v; self._apply()
+    def setMaxCorrespondenceDistance(self, v): self._p.max_correspondence_distance = v; self._apply()
+    def setMaximumIterations(self, v): self._p.max_iterations = int(v); self._apply()
+    def setRANSACIterations(self, v): self._p.ransac_iterations = int(v); self._apply()
+    def setMaximumOptimizerIterations(self, v): self._p.max_optimizer_iterations = int(v); self._apply()
+    def setNumThreads(self, v): self._p.num_threads = int(v); self._apply()
+    def enableTimingOutput(self, v): self._p.enable_timing_output = int(bool(v)); self._apply()
+    def RecomputeTargetCovariance(self, v): self._p.recompute_target_covariance = int(bool(v)); self._apply()
+    def RecomputeSourceCovariance(self, v): self._p.recompute_source_covariance = int(bool(v)); self._apply()
+    def setEuclideanFitnessEpsilon(self, v): self._p.euclidean_fitness_epsilon = v; self._apply()
+    def setRotationEpsilon(self, v): self._p.rotation_epsilon = v; self._apply()
+    def setCorrespondenceRandomness(self, k): self._p.k_correspondences = int(k); self._apply()
+    def setOptimizer(self, v): self._p.optimizer = int(v); self._apply()
+    def setExecution(self, v): self._p.execution = int(v); self._apply()
+    def setIndexCellSize(self, v): self._p.index_cell_size = float(v); self._apply()
+    def getMaximumIterations(self): return self._p.max_iterations
+    def getMaxCorrespondenceDistance(self): return self._p.max_correspondence_distance
+    def getTransformationEpsilon(self): return self._p.transformation_epsilon
+    def getRotationEpsilon(self): return self._p.rotation_epsilon
+    def getCorrespondenceRandomness(self): return self._p.k_correspondences
+    def getMaximumOptimizerIterations(self): return self._p.max_optimizer_iterations
+
+    # ---- clouds.  cloud: (n, stride/4) float32 host array (xyz in columns xyz_col..+2), or
+    # a raw device pointer with n/stride given explicitly.
+    def _cloud_args(self, cloud, n, stride, xyz_off, normal_off):
+        if isinstance(cloud, np.ndarray):
+            a = np.ascontiguousarray(cloud, dtype=np.float32)
+            assert a.ndim == 2 and a.shape[1] >= 3
+            return a, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1] * 4, xyz_off, normal_off, LB_MEM_HOST
+        return None, C.c_void_p(int(cloud)), int(n), int(stride), xyz_off, normal_off, LB_MEM_DEVICE
+
+    def setInputSource(self, cloud, n=None, stride=None, xyz_off=0, normal_off=-1):
+        keep, p, n_, st, xo, no, mem = self._cloud_args(cloud, n, stride, xyz_off, normal_off)
+        _check(lib().lb_gicp_set_source(self._h, p, n_, st, xo, no, mem))
+        self._keep["src"] = keep
+
+    def setInputTarget(self, cloud, n=None, stride=None, xyz_off=0, normal_off=-1):
+        keep, p, n_, st, xo, no, mem = self._cloud_args(cloud, n, stride, xyz_off, normal_off)
+        gen = C.c_uint64(0)
+        _check(lib().lb_gicp_set_target(self._h, p, n_, st, xo, no, mem, C.byref(gen)))
+        self._keep["tgt"] = keep
+        return gen.value
+
+    def promoteSourceToTarget(self):
+        _check(lib().lb_gicp_promote_source_to_target(self._h))
+
+    def align(self, guess=None):
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        res = GicpResult()
+        st = lib().lb_gicp_align(self._h, _ptr(g), C.byref(res))
+        self._res = res
+        _check(st)
+        return res
+
+    def getFinalTransformation(self):
+        if self._res is None:
+            return np.eye(4, dtype=np.float32)
+        return np.array(self._res.final_transformation, dtype=np.float32).reshape(4, 4)
+
+    def hasConverged(self):
+        return bool(self._res.converged) if self._res is not None else False
+
+    def getFitnessScore(self, max_range=1.7976931348623157e308):
+        s = C.c_double(0)
+        _check(lib().lb_gicp_fitness(self._h, None, max_range, C.byref(s)))
+        return s.value
+
+    def transformSource(self, T=None, with_normals=False):
+        """The `output` cloud of align(): (n,3) float32 [, (n,3) normals]."""
+        n = self.cloudSize(0)
+        cols = 6 if with_normals else 3
+        out = np.zeros((n, cols), dtype=np.float32)
+        t = None if T is None else np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        _check(lib().lb_gicp_transform_source(self._h, _ptr(t), _ptr(out), cols * 4, 0, 12 if with_normals else -1, LB_MEM_HOST))
+        return out
+
+    def nearestTarget(self, xyz):
+        """getSearchMethodTarget()->nearestKSearch(pt, 1) for a batch: (idx int32, d2 float32)."""
+        q = np.ascontiguousarray(xyz, dtype=np.float32)
+        idx = np.zeros(q.shape[0], dtype=np.int32); d2 = np.zeros(q.shape[0], dtype=np.float32)
+        _check(lib().lb_gicp_nn_target(self._h, _ptr(q), q.shape[0], q.shape[1] * 4, _ptr(idx), _ptr(d2), LB_MEM_HOST))
+        return idx, d2
+
+    def covariances(self, which):
+        n = self.cloudSize(which)
+        out = np.zeros((n, 9))
+        _check(lib().lb_gicp_get_covariances(self._h, which, _ptr(out), n))
+        return out.reshape(n, 3, 3)
+
+    def cloudSize(self, which):
+        n = C.c_size_t(0)
+        _check(lib().lb_gicp_cloud_size(self._h, which, C.byref(n)))
+        return n.value
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        lib().lb_gicp_launch_count(self._h, C.byref(n))
+        return n.value
+
+    def resetKernelTimes(self, enable=True):
+        _check(lib().lb_gicp_reset_kernel_times(self._h, int(enable)))
+
+    def kernelTime(self, name):
+        ms = C.c_float(0); n = C.c_uint64(0)
+        lib().lb_gicp_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+
+class VoxelGridB200:
+    """Mirror of point_cloud_filter::CustomVoxelGrid's impl_ (pcl::VoxelGrid<PCLPointCloud2>)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        if stream is None:
+            _check(lib().lb_voxel_create(device, C.byref(self._h)))
+        else:
+            _check(lib().lb_voxel_create_on_stream(device, C.c_void_p(int(stream)), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lb_voxel_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def setLeafSize(self, lx, ly=None, lz=None):
+        ly = lx if ly is None else ly
+        lz = lx if lz is None else lz
+        _check(lib().lb_voxel_set_leaf_size(self._h, np.float32(lx), np.float32(ly), np.float32(lz)))
+
+    def getLeafSize(self):
+        a = np.zeros(3, dtype=np.float32)
+        _check(lib().lb_voxel_get_leaf_size(self._h, _ptr(a)))
+        return a
+
+    def setFilterFieldName(self, name): self._ff = name; self._push_limits()
+    def setFilterLimits(self, lo, hi): self._lo, self._hi = lo, hi; self._push_limits()
+    def setFilterLimitsNegative(self, neg): self._neg = bool(neg); self._push_limits()
+
+    def _push_limits(self):
+        name = getattr(self, "_ff", "")
+        lo = getattr(self, "_lo", -3.4028234663852886e38); hi = getattr(self, "_hi", 3.4028234663852886e38)
+        _check(lib().lb_voxel_set_filter_limits(self._h, name.encode() if name else None, lo, hi, int(getattr(self, "_neg", False))))
+
+    def setMinimumPointsNumberPerVoxel(self, m): _check(lib().lb_voxel_set_min_points_per_voxel(self._h, int(m)))
+    def setDownsampleAllData(self, a): _check(lib().lb_voxel_set_downsample_all_data(self._h, int(bool(a))))
+
+    @staticmethod
+    def _fields(fields):
+        arr = (Field * len(fields))()
+        for i, (name, off, dt, cnt) in enumerate(fields):
+            arr[i].name = name.encode(); arr[i].offset = off; arr[i].datatype = dt; arr[i].count = cnt
+        return arr
+
+    def filter(self, blob, point_step, fields, want_voxel_idx=False):
+        """blob: uint8 host array (n*point_step).  returns (out (m, point_step) uint8[, voxel_idx int32])."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
+        n = blob.size // point_step
+        out = np.zeros(max(n, 1) * point_step, dtype=np.uint8)
+        vidx = np.zeros(max(n, 1), dtype=np.int32) if want_voxel_idx else None
+        n_out = C.c_size_t(0)
+        fa = self._fields(fields)
+        _check(lib().lb_voxel_filter(self._h, _ptr(blob), n, point_step, fa, len(fields), None, 0, _ptr(out), n,
+                                     C.byref(n_out), _ptr(vidx), LB_MEM_HOST, LB_MEM_HOST))
+        m = n_out.value
+        o = out[: m * point_step].reshape(m, point_step)
+        return (o, vidx[:m]) if want_voxel_idx else o
+
+    def filter_device(self, d_in, n, point_step, fields, d_out, capacity, d_vidx=None):
+        """device pointers in/out; returns number of voxels."""
+        n_out = C.c_size_t(0)
+        fa = self._fields(fields)
+        _check(lib().lb_voxel_filter(self._h, C.c_void_p(int(d_in)), n, point_step, fa, len(fields), None, 0,
+                                     C.c_void_p(int(d_out)), capacity, C.byref(n_out),
+                                     C.c_void_p(int(d_vidx)) if d_vidx else None, LB_MEM_DEVICE, LB_MEM_DEVICE))
+        return n_out.value
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        lib().lb_voxel_launch_count(self._h, C.byref(n))
+        return n.value
+
+    def lastCallMs(self):
+        ms = C.c_float(0)
+        lib().lb_voxel_kernel_time(self._h, C.byref(ms))
+        return ms.value

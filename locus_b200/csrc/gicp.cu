@@ -1,0 +1,686 @@
+// gicp.cu -- host side of the B200 GICP scan matcher and its C ABI.
+//
+// One lb_gicp handle = one CUDA stream + the device-resident state of a
+// registration object (the role pcl::Registration<PointF,PointF>::Ptr icp_
+// plays in PointCloudOdometry.h:154 / PointCloudLocalization.h:228):
+//   source / target clouds as cell-sorted float4 + voxel-hash CSR + covariances,
+//   correspondence arrays, reduction scratch, last result.
+// All compute runs in the kernels of gicp_kernels.cuh; the host only sequences
+// launches (host-driven mode) or launches ONE cooperative kernel per align()
+// (persistent mode).  There is no CPU compute path: without a CUDA device every
+// entry point fails with LB_ERR_NO_DEVICE.
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "gicp_kernels.cuh"
+
+namespace lb {
+const char* last_error();
+
+struct Cloud {
+  size_t n = 0;
+  bool valid = false;
+  bool has_normals = false;
+  bool cov_valid = false;
+  DBuf<f4> raw;                // original order (x,y,z,1)
+  DBuf<f4> nrm;                // original order normals
+  DBuf<f4> pts;                // cell-sorted, w = original index
+  DBuf<uint32_t> cell_start;   // ncells + 1
+  DBuf<double> cov;            // sorted order, 6 per point
+  GridGeom geom{};
+  size_t ncells = 0;
+  uint64_t generation = 0;
+
+  GridView view() const {
+    GridView v;
+    v.pts = pts.p; v.cell_start = cell_start.p;
+    v.ox = geom.ox; v.oy = geom.oy; v.oz = geom.oz; v.inv_h = geom.inv_h; v.h = geom.h;
+    v.nx = geom.nx; v.ny = geom.ny; v.nz = geom.nz; v.n = (int)n;
+    return v;
+  }
+  void release() { raw.release(); nrm.release(); pts.release(); cell_start.release(); cov.release(); }
+};
+
+struct KTimer {          // CUDA-event timing of one kernel class
+  std::string name;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  double total_ms = 0;
+  uint64_t launches = 0;
+};
+
+}  // namespace lb
+
+using namespace lb;
+
+struct lb_gicp {
+  Ctx c;
+  lb_gicp_params P;
+  Cloud src, tgt;
+  uint64_t gen_counter = 0;
+  // staging / scratch
+  DBuf<uint8_t> stage;           // H2D staging of caller clouds
+  DBuf<uint32_t> keys, cell_cnt;
+  SortWork sort;
+  ScanWork scan;
+  BBoxAcc* d_acc = nullptr; BBoxAcc* h_acc = nullptr;
+  uint32_t* d_u32 = nullptr; uint32_t* h_u32 = nullptr;     // small counters [8]
+  // align state
+  DBuf<f4> src_work, corr;
+  DBuf<double> M, partials;
+  unsigned* d_barrier = nullptr;      // [2]: barrier, ticket
+  int* d_m = nullptr;
+  double* h_sums = nullptr; double* d_sums = nullptr;        // mapped pinned [32]
+  int* h_m = nullptr;                                         // pinned
+  OuterResult* d_result = nullptr; OuterResult* h_result = nullptr;
+  int align_blocks = 0;
+  bool have_result = false;
+  float final_T[16];
+  DBuf<uint8_t> io;              // transform/nn output staging
+  DBuf<int32_t> io_idx; DBuf<float> io_d2;
+  std::vector<uint8_t> h_io;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timing = false;
+  std::vector<KTimer> timers;
+};
+
+namespace {
+
+KTimer* timer_for(lb_gicp* h, const char* name) {
+  for (auto& t : h->timers) if (t.name == name) return &t;
+  h->timers.push_back(KTimer());
+  h->timers.back().name = name;
+  return &h->timers.back();
+}
+
+struct ScopedKernelTime {
+  lb_gicp* h; KTimer* t; size_t slot;
+  ScopedKernelTime(lb_gicp* h_, const char* name) : h(h_), t(nullptr), slot(0) {
+    if (!h->timing) return;
+    t = timer_for(h, name);
+    if (t->used + 2 > t->ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      t->ev.push_back(a); t->ev.push_back(b);
+    }
+    slot = t->used; t->used += 2;
+    cudaEventRecord(t->ev[slot], h->c.stream);
+  }
+  ~ScopedKernelTime() {
+    if (!t) return;
+    cudaEventRecord(t->ev[slot + 1], h->c.stream);
+    t->launches++;
+  }
+};
+
+void timers_collect(lb_gicp* h) {   // call after a stream sync
+  for (auto& t : h->timers) {
+    for (size_t i = 0; i + 1 < t.used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ms;
+    }
+    t.used = 0;
+  }
+}
+
+void mat16_to_34(const float* T16, Mat34& m) { for (int i = 0; i < 12; i++) m.m[i] = T16[i]; }
+
+// smallest float g with (d2 < g) <=> ((double)d2 < D) for every float d2
+float float_gate(double D) {
+  float g = (float)D;
+  if ((double)g < D) g = nextafterf(g, INFINITY);
+  return g;
+}
+
+int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
+  if (!out) { set_error("lb_gicp_create: null handle pointer"); return LB_ERR_INVALID_ARG; }
+  lb_gicp* h = new lb_gicp;
+  int s = ctx_init(h->c, device, stream, ext);
+  if (s != LB_OK) { delete h; return s; }
+  lb_gicp_default_params(&h->P);
+  bool ok = cudaMalloc((void**)&h->d_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_barrier, 2 * sizeof(unsigned)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_m, sizeof(int)) == cudaSuccess &&
+            cudaHostAlloc((void**)&h->h_sums, 32 * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&h->d_sums, h->h_sums, 0) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_m, sizeof(int)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_result, sizeof(OuterResult)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_result, sizeof(OuterResult)) == cudaSuccess;
+  for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+  if (ok) ok = cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned)) == cudaSuccess;
+  if (!ok) {
+    set_error("lb_gicp_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return LB_ERR_CUDA;
+  }
+  // persistent kernel: one CTA per SM, co-resident (cooperative launch)
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel, AL_THREADS, 0);
+  h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
+  if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
+  for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  *out = h;
+  return LB_OK;
+}
+
+// Upload a caller cloud and build its voxel-hash index (K2).
+int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off,
+                int mem, const char* what) {
+  Ctx& c = h->c;
+  if (!pts) { set_error("%s: null cloud", what); return LB_ERR_INVALID_ARG; }
+  if (n > 0x7ffffff0ull) { set_error("%s: too many points", what); return LB_ERR_INVALID_ARG; }
+  if ((stride & 3u) || (xyz_off & 3u) || xyz_off + 12 > stride || (normal_off >= 0 && ((normal_off & 3) || (size_t)normal_off + 12 > stride))) {
+    set_error("%s: stride/offsets must be 4-byte aligned and inside the point", what);
+    return LB_ERR_INVALID_ARG;
+  }
+  LB_CUDA(cudaSetDevice(c.device));
+  ScopedKernelTime kt(h, "index_build");
+  const uint32_t N = (uint32_t)n;
+  const uint8_t* d_src = (const uint8_t*)pts;
+  if (mem == LB_MEM_HOST) {
+    LB_TRY(h->stage.ensure(n * stride));
+    LB_CUDA(cudaMemcpyAsync(h->stage.p, pts, n * stride, cudaMemcpyHostToDevice, c.stream));
+    d_src = h->stage.p;
+  }
+  LB_TRY(cl.raw.ensure(n)); LB_TRY(cl.pts.ensure(n));
+  if (normal_off >= 0) LB_TRY(cl.nrm.ensure(n));
+  gather_cloud_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_src, N, (uint32_t)stride, (uint32_t)xyz_off, (int)normal_off,
+                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr);
+  bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
+  bbox_kernel<<<min(cdiv(N, 256), c.sm_count * 8), 256, 0, c.stream>>>((const uint8_t*)cl.raw.p, N, 16, 0, -1, 0.f, 0.f, 0, h->d_acc);
+  c.launches += 3;
+  LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  if (h->h_acc->count != N) {
+    set_error("%s: cloud holds %u non-finite points; GICP inputs must be dense (PCL kd-tree precondition)", what, N - h->h_acc->count);
+    return LB_ERR_INVALID_ARG;
+  }
+  float mn[3], mx[3];
+  for (int d = 0; d < 3; d++) { mn[d] = ord2f(h->h_acc->mn[d]); mx[d] = ord2f(h->h_acc->mx[d]); }
+  float ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+
+  auto make_geom = [&](float cell) {
+    GridGeom g;
+    const int MAXDIM = 16384;
+    const double MAXCELLS = 64.0 * 1024 * 1024;
+    for (;;) {
+      g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+      g.h = cell; g.inv_h = 1.0f / cell;
+      double fx = floor((double)(ext[0] * g.inv_h)) + 1, fy = floor((double)(ext[1] * g.inv_h)) + 1, fz = floor((double)(ext[2] * g.inv_h)) + 1;
+      if (fx <= MAXDIM && fy <= MAXDIM && fz <= MAXDIM && fx * fy * fz <= MAXCELLS) {
+        g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz;
+        return g;
+      }
+      cell *= 1.5f;
+    }
+  };
+
+  LB_TRY(h->keys.ensure(n));
+  GridGeom g;
+  float cell = h->P.index_cell_size;
+  if (cell > 0.f) {
+    g = make_geom(cell);
+  } else {
+    // automatic: aim at ~6 points per occupied cell (h ~ 2.5 x point spacing on a surface, so the
+    // 20-NN radius is about one cell and a 1-NN probe rarely leaves the 3x3x3 block)
+    double area = 2.0 * ((double)ext[0] * ext[1] + (double)ext[1] * ext[2] + (double)ext[0] * ext[2]);
+    double diag = sqrt((double)ext[0] * ext[0] + (double)ext[1] * ext[1] + (double)ext[2] * ext[2]);
+    if (!(area > 0)) area = diag * diag;
+    double spacing = sqrt(area / (double)(N ? N : 1));
+    cell = (float)(2.5 * spacing);
+    if (!(cell > 0.f)) cell = 1.0f;
+    const double target = 6.0;
+    for (int round = 0; round < 4; round++) {
+      g = make_geom(cell);
+      size_t nc = (size_t)g.nx * g.ny * g.nz;
+      LB_TRY(h->cell_cnt.ensure(nc + 1));
+      LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (nc + 1) * sizeof(uint32_t), c.stream));
+      LB_CUDA(cudaMemsetAsync(h->d_u32, 0, sizeof(uint32_t), c.stream));
+      grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p);
+      grid_occupancy_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->keys.p, N, h->cell_cnt.p, h->d_u32);
+      c.launches += 2;
+      LB_CUDA(cudaMemcpyAsync(h->h_u32, h->d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+      LB_CUDA(cudaStreamSynchronize(c.stream));
+      double occ = (double)N / (double)(h->h_u32[0] ? h->h_u32[0] : 1);
+      if (occ >= target / 2 && occ <= target * 2) break;
+      if (N <= 8 || h->h_u32[0] <= 1) break;
+      double scale = sqrt(target / occ);
+      if (scale > 4) scale = 4;
+      if (scale < 0.25) scale = 0.25;
+      cell = g.h * (float)scale;
+    }
+  }
+  cl.geom = g;
+  cl.ncells = (size_t)g.nx * g.ny * g.nz;
+  int key_bits = 1;
+  while (key_bits < 32 && (1ull << key_bits) < (uint64_t)cl.ncells) key_bits++;
+  LB_TRY(h->cell_cnt.ensure(cl.ncells + 1));
+  LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
+  LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
+  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p);
+  c.launches++;
+  uint32_t *sk = nullptr, *sv = nullptr;
+  LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));
+  grid_reorder_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, sk, sv, N, cl.pts.p, h->cell_cnt.p);
+  c.launches++;
+  LB_TRY(exclusive_scan_u32(c, h->scan, h->cell_cnt.p, cl.cell_start.p, cl.ncells + 1, nullptr));
+  LB_CUDA(cudaGetLastError());
+  cl.n = n;
+  cl.valid = true;
+  cl.has_normals = normal_off >= 0;
+  cl.cov_valid = false;
+  cl.generation = ++h->gen_counter;
+  return LB_OK;
+}
+
+int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
+  Ctx& c = h->c;
+  const uint32_t N = (uint32_t)cl.n;
+  LB_TRY(cl.cov.ensure(6 * cl.n));
+  ScopedKernelTime kt(h, "knn_cov");
+  if (!recompute && cl.has_normals) {
+    normal_cov_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.pts.p, cl.nrm.p, N, h->P.gicp_epsilon, cl.cov.p);
+  } else {
+    int k = h->P.k_correspondences;
+    GridView v = cl.view();
+    if (k <= 20) knn_cov_kernel<20><<<cdiv(N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    else knn_cov_kernel<32><<<cdiv(N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+  }
+  c.launches++;
+  LB_CUDA(cudaGetLastError());
+  cl.cov_valid = true;
+  return LB_OK;
+}
+
+// ---- host-driven backend: the Backend concept of bfgs.h implemented with kernel launches ----
+struct HostBackend {
+  lb_gicp* h;
+  CorrArgs ca;
+  int m = 0;
+  int status = LB_OK;
+
+  int correspond(const float* T, const double* R) {
+    Ctx& c = h->c;
+    Mat34 t; Mat33d r;
+    for (int i = 0; i < 12; i++) t.m[i] = T[i];
+    for (int i = 0; i < 9; i++) r.m[i] = R[i];
+    cudaMemsetAsync(h->d_m, 0, sizeof(int), c.stream);
+    {
+      ScopedKernelTime kt(h, "nn_corr");
+      nn_corr_kernel<<<cdiv(ca.n_src, 128), 128, 0, c.stream>>>(ca, t, r, h->d_m);
+      c.launches++;
+    }
+    cudaMemcpyAsync(h->h_m, h->d_m, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) { status = LB_ERR_CUDA; return 0; }
+    m = *h->h_m;
+    return m;
+  }
+  template <int NV>
+  bool run_objective(const double* x) {
+    Ctx& c = h->c;
+    ObjArgs oa{ca.src, ca.corr, ca.M, ca.n_src};
+    Vec6d xv;
+    for (int i = 0; i < 6; i++) xv.v[i] = x[i];
+    {
+      ScopedKernelTime kt(h, "objective");
+      objective_kernel<NV><<<h->align_blocks, AL_THREADS, 0, c.stream>>>(oa, xv, h->partials.p, h->d_barrier + 1, h->d_sums);
+      c.launches++;
+    }
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) { status = LB_ERR_CUDA; return false; }
+    return true;
+  }
+  void fdf(const double* x, double* f, double* g) {
+    if (!run_objective<13>(x)) { *f = 0; for (int i = 0; i < 6; i++) g[i] = 0; return; }
+    objective_finish(h->h_sums, m, x, f, g);
+  }
+  int gn(const double* x, double* f, double* b, double* H) {
+    if (!run_objective<28>(x)) return -1;
+    *f = h->h_sums[0] / (double)m;
+    for (int e = 0; e < 6; e++) b[e] = h->h_sums[1 + e];
+    for (int e = 0; e < 21; e++) H[e] = h->h_sums[7 + e];
+    return 0;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int lb_version(void) { return LB_VERSION; }
+const char* lb_last_error_string(void) { return lb::last_error(); }
+const char* lb_status_string(int s) {
+  switch (s) {
+    case LB_OK: return "ok";
+    case LB_ERR_INVALID_ARG: return "invalid argument";
+    case LB_ERR_CUDA: return "CUDA error";
+    case LB_ERR_NO_DEVICE: return "no CUDA device (the product path has no CPU fallback)";
+    case LB_ERR_EMPTY_SOURCE: return "empty source cloud";
+    case LB_ERR_NO_TARGET: return "no target cloud";
+    case LB_ERR_TOO_FEW_POINTS: return "fewer points than k_correspondences";
+    case LB_ERR_VOXEL_OVERFLOW: return "voxel index overflow (leaf too small)";
+    case LB_ERR_CAPACITY: return "output capacity too small";
+    case LB_ERR_UNSUPPORTED: return "unsupported";
+    case LB_ERR_NO_ALIGN: return "no align() result yet";
+    default: return "unknown status";
+  }
+}
+int lb_device_count(int* n) {
+  if (!n) return LB_ERR_INVALID_ARG;
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { *n = 0; cudaGetLastError(); return LB_OK; }
+  *n = c;
+  return LB_OK;
+}
+
+int lb_gicp_default_params(lb_gicp_params* p) {
+  if (!p) return LB_ERR_INVALID_ARG;
+  memset(p, 0, sizeof(*p));
+  p->k_correspondences = 20;              // gicp.h:112
+  p->gicp_epsilon = 0.001;                // gicp.h:118
+  p->rotation_epsilon = 2e-3;             // gicp.h:119
+  p->transformation_epsilon = 5e-4;       // gicp.h:126
+  p->max_correspondence_distance = 5.0;   // gicp.h:127
+  p->max_iterations = 200;                // gicp.h:125
+  p->max_optimizer_iterations = 20;       // gicp.h:121
+  p->recompute_source_covariance = 1;
+  p->recompute_target_covariance = 1;
+  p->optimizer = LB_OPT_BFGS;
+  p->execution = LB_EXEC_PERSISTENT;
+  p->euclidean_fitness_epsilon = 0.0;
+  p->ransac_iterations = 0;
+  p->num_threads = 1;
+  p->enable_timing_output = 0;
+  p->index_cell_size = 0.f;
+  return LB_OK;
+}
+
+int lb_gicp_create(int device, lb_gicp** h) { return gicp_create_impl(device, nullptr, false, h); }
+int lb_gicp_create_on_stream(int device, void* stream, lb_gicp** h) { return gicp_create_impl(device, stream, true, h); }
+
+int lb_gicp_destroy(lb_gicp* h) {
+  if (!h) return LB_OK;
+  cudaSetDevice(h->c.device);
+  cudaStreamSynchronize(h->c.stream);
+  h->src.release(); h->tgt.release();
+  h->stage.release(); h->keys.release(); h->cell_cnt.release();
+  h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
+  h->sort.scan.sums.release(); h->scan.sums.release();
+  h->src_work.release(); h->corr.release(); h->M.release(); h->partials.release();
+  h->io.release(); h->io_idx.release(); h->io_d2.release();
+  if (h->d_acc) cudaFree(h->d_acc);
+  if (h->h_acc) cudaFreeHost(h->h_acc);
+  if (h->d_u32) cudaFree(h->d_u32);
+  if (h->h_u32) cudaFreeHost(h->h_u32);
+  if (h->d_barrier) cudaFree(h->d_barrier);
+  if (h->d_m) cudaFree(h->d_m);
+  if (h->h_sums) cudaFreeHost(h->h_sums);
+  if (h->h_m) cudaFreeHost(h->h_m);
+  if (h->d_result) cudaFree(h->d_result);
+  if (h->h_result) cudaFreeHost(h->h_result);
+  for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (auto& t : h->timers) for (auto e : t.ev) cudaEventDestroy(e);
+  ctx_destroy(h->c);
+  delete h;
+  return LB_OK;
+}
+
+int lb_gicp_set_params(lb_gicp* h, const lb_gicp_params* p) {
+  if (!h || !p) { set_error("lb_gicp_set_params: null argument"); return LB_ERR_INVALID_ARG; }
+  if (p->k_correspondences < 1 || p->k_correspondences > 32) { set_error("k_correspondences must be in [1, 32]"); return LB_ERR_UNSUPPORTED; }
+  if (!(p->gicp_epsilon > 0) || !(p->rotation_epsilon > 0) || !(p->transformation_epsilon > 0) ||
+      !(p->max_correspondence_distance > 0) || p->max_iterations < 1 || p->max_optimizer_iterations < 1) {
+    set_error("lb_gicp_set_params: epsilons / distance / iteration caps must be positive");
+    return LB_ERR_INVALID_ARG;
+  }
+  bool cov_change = p->k_correspondences != h->P.k_correspondences || p->gicp_epsilon != h->P.gicp_epsilon ||
+                    p->recompute_source_covariance != h->P.recompute_source_covariance ||
+                    p->recompute_target_covariance != h->P.recompute_target_covariance;
+  h->P = *p;
+  if (cov_change) { h->src.cov_valid = false; h->tgt.cov_valid = false; }
+  return LB_OK;
+}
+int lb_gicp_get_params(lb_gicp* h, lb_gicp_params* p) { if (!h || !p) return LB_ERR_INVALID_ARG; *p = h->P; return LB_OK; }
+
+int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem) {
+  if (!h) { set_error("lb_gicp_set_source: null handle"); return LB_ERR_INVALID_ARG; }
+  if (n == 0) {
+    // gicp.h:164-171: "Invalid or empty point cloud dataset given!" -> return, previous input kept
+    set_error("lb_gicp_set_source: invalid or empty point cloud dataset given");
+    return LB_ERR_EMPTY_SOURCE;
+  }
+  return build_cloud(h, h->src, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
+}
+
+int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem,
+                       uint64_t* generation) {
+  if (!h) { set_error("lb_gicp_set_target: null handle"); return LB_ERR_INVALID_ARG; }
+  if (n == 0) { set_error("lb_gicp_set_target: empty target cloud"); return LB_ERR_NO_TARGET; }
+  int s = build_cloud(h, h->tgt, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
+  if (s == LB_OK && generation) *generation = h->tgt.generation;
+  return s;
+}
+
+int lb_gicp_promote_source_to_target(lb_gicp* h) {
+  if (!h) return LB_ERR_INVALID_ARG;
+  if (!h->src.valid) { set_error("lb_gicp_promote_source_to_target: no source set"); return LB_ERR_EMPTY_SOURCE; }
+  std::swap(h->src, h->tgt);
+  h->src.valid = false; h->src.cov_valid = false; h->src.n = 0;
+  h->tgt.generation = ++h->gen_counter;
+  return LB_OK;
+}
+
+int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
+  if (!h || !out) { set_error("lb_gicp_align: null argument"); return LB_ERR_INVALID_ARG; }
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < 16; i++) out->final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
+  if (!h->src.valid || h->src.n == 0) { set_error("lb_gicp_align: no source cloud"); out->status = LB_ERR_EMPTY_SOURCE; return LB_ERR_EMPTY_SOURCE; }
+  if (!h->tgt.valid || h->tgt.n == 0) { set_error("lb_gicp_align: no target cloud"); out->status = LB_ERR_NO_TARGET; return LB_ERR_NO_TARGET; }
+  const int k = h->P.k_correspondences;
+  bool src_knn = h->P.recompute_source_covariance || !h->src.has_normals;
+  bool tgt_knn = h->P.recompute_target_covariance || !h->tgt.has_normals;
+  // gicp.hpp:72-79 applies the k > size check in both covariance modes
+  if ((size_t)k > h->src.n || (size_t)k > h->tgt.n) {
+    set_error("lb_gicp_align: number of points in cloud (%zu / %zu) is less than k_correspondences (%d)", h->src.n, h->tgt.n, k);
+    out->status = LB_ERR_TOO_FEW_POINTS;
+    return LB_ERR_TOO_FEW_POINTS;
+  }
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  float guess[16];
+  for (int i = 0; i < 16; i++) guess[i] = guess_in ? guess_in[i] : ((i % 5 == 0) ? 1.f : 0.f);
+
+  LB_CUDA(cudaEventRecord(h->ev[0], c.stream));
+  if (!h->tgt.cov_valid) LB_TRY(compute_covariances(h, h->tgt, tgt_knn));   // target first, gicp.hpp:420-432
+  if (!h->src.cov_valid) LB_TRY(compute_covariances(h, h->src, src_knn));
+  LB_CUDA(cudaEventRecord(h->ev[1], c.stream));
+
+  const uint32_t N = (uint32_t)h->src.n;
+  LB_TRY(h->src_work.ensure(N)); LB_TRY(h->corr.ensure(N)); LB_TRY(h->M.ensure(6 * (size_t)N));
+  LB_TRY(h->partials.ensure((size_t)2 * h->align_blocks * AL_PSTRIDE));
+  Mat34 G; mat16_to_34(guess, G);
+  prep_source_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.pts.p, N, G, h->src_work.p);   // gicp.hpp:440
+  c.launches++;
+
+  CorrArgs ca;
+  ca.tgt = h->tgt.view(); ca.tgt_cov = h->tgt.cov.p; ca.src = h->src_work.p; ca.src_cov = h->src.cov.p;
+  ca.n_src = (int)N; ca.max_d2 = float_gate(h->P.max_correspondence_distance * h->P.max_correspondence_distance);
+  ca.corr = h->corr.p; ca.M = h->M.p;
+  OuterParams OP;
+  OP.rotation_epsilon = h->P.rotation_epsilon; OP.transformation_epsilon = h->P.transformation_epsilon;
+  OP.max_iterations = h->P.max_iterations; OP.max_inner_iterations = h->P.max_optimizer_iterations;
+  OP.optimizer = h->P.optimizer == LB_OPT_GAUSS_NEWTON ? 1 : 0;
+
+  OuterResult R;
+  if (h->P.execution == LB_EXEC_HOST_DRIVEN) {
+    HostBackend be; be.h = h; be.ca = ca;
+    gicp_outer_loop(be, OP, guess, R);
+    if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
+  } else {
+    AlignArgs aa;
+    aa.c = ca; aa.partials = h->partials.p; aa.barrier = h->d_barrier; aa.P = OP; aa.result = h->d_result;
+    for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
+    LB_CUDA(cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned), c.stream));
+    void* args[] = {&aa};
+    {
+      ScopedKernelTime kt(h, "align_persistent");
+      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(h->align_blocks), dim3(AL_THREADS), args, 0, c.stream));
+      c.launches++;
+    }
+    LB_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(OuterResult), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+    R = *h->h_result;
+  }
+  LB_CUDA(cudaEventRecord(h->ev[2], c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  timers_collect(h);
+  for (int i = 0; i < 16; i++) { out->final_transformation[i] = R.final_T[i]; h->final_T[i] = R.final_T[i]; }
+  h->have_result = true;
+  out->converged = R.converged;
+  out->iterations = R.nr_iterations;
+  out->n_correspondences = R.n_corr;
+  out->delta = R.delta;
+  out->n_objective_evals = R.st.n_evals;
+  out->n_inner_iterations = R.st.n_inner;
+  cudaEventElapsedTime(&out->t_covariances_ms, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&out->t_iterations_ms, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&out->t_total_ms, h->ev[0], h->ev[2]);
+  out->status = LB_OK;
+  return LB_OK;
+}
+
+int lb_gicp_transform_source(lb_gicp* h, const float* T_in, void* out_pts, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem) {
+  if (!h || !out_pts) { set_error("lb_gicp_transform_source: null argument"); return LB_ERR_INVALID_ARG; }
+  if (!h->src.valid) { set_error("lb_gicp_transform_source: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
+  if (!T_in && !h->have_result) { set_error("lb_gicp_transform_source: no align() result yet"); return LB_ERR_NO_ALIGN; }
+  if ((stride & 3u) || (xyz_off & 3u) || xyz_off + 12 > stride) { set_error("lb_gicp_transform_source: bad stride/offset"); return LB_ERR_INVALID_ARG; }
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  const uint32_t N = (uint32_t)h->src.n;
+  Mat34 T; mat16_to_34(T_in ? T_in : h->final_T, T);
+  bool nrm = normal_off >= 0 && h->src.has_normals;
+  if (mem == LB_MEM_DEVICE) {
+    transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.raw.p, nrm ? h->src.nrm.p : nullptr, N, T, (uint8_t*)out_pts,
+                                                         (uint32_t)stride, (uint32_t)xyz_off, nrm ? (int)normal_off : -1);
+    c.launches++;
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+    return LB_OK;
+  }
+  // host output: packed (xyz | normal) rows on the device, one D2H, scatter into the caller's layout
+  const uint32_t row = nrm ? 24 : 12;
+  LB_TRY(h->io.ensure((size_t)N * row));
+  transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.raw.p, nrm ? h->src.nrm.p : nullptr, N, T, h->io.p, row, 0, nrm ? 12 : -1);
+  c.launches++;
+  h->h_io.resize((size_t)N * row);
+  LB_CUDA(cudaMemcpyAsync(h->h_io.data(), h->io.p, (size_t)N * row, cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  uint8_t* o = (uint8_t*)out_pts;
+  for (uint32_t i = 0; i < N; i++) {
+    memcpy(o + (size_t)i * stride + xyz_off, h->h_io.data() + (size_t)i * row, 12);
+    if (nrm) memcpy(o + (size_t)i * stride + normal_off, h->h_io.data() + (size_t)i * row + 12, 12);
+  }
+  return LB_OK;
+}
+
+int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int32_t* idx, float* d2, int mem) {
+  if (!h || !xyz || !idx || !d2) { set_error("lb_gicp_nn_target: null argument"); return LB_ERR_INVALID_ARG; }
+  if (!h->tgt.valid) { set_error("lb_gicp_nn_target: no target cloud"); return LB_ERR_NO_TARGET; }
+  if (n == 0) return LB_OK;
+  if ((stride & 3u) || stride < 12) { set_error("lb_gicp_nn_target: bad stride"); return LB_ERR_INVALID_ARG; }
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  const uint32_t N = (uint32_t)n;
+  const uint8_t* dq = (const uint8_t*)xyz; int32_t* di = idx; float* dd = d2;
+  if (mem == LB_MEM_HOST) {
+    LB_TRY(h->stage.ensure(n * stride)); LB_TRY(h->io_idx.ensure(n)); LB_TRY(h->io_d2.ensure(n));
+    LB_CUDA(cudaMemcpyAsync(h->stage.p, xyz, n * stride, cudaMemcpyHostToDevice, c.stream));
+    dq = h->stage.p; di = h->io_idx.p; dd = h->io_d2.p;
+  }
+  nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd);
+  c.launches++;
+  if (mem == LB_MEM_HOST) {
+    LB_CUDA(cudaMemcpyAsync(idx, di, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaMemcpyAsync(d2, dd, n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  }
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  LB_CUDA(cudaGetLastError());
+  return LB_OK;
+}
+
+int lb_gicp_fitness(lb_gicp* h, const float* T_in, double max_range, double* score) {
+  if (!h || !score) { set_error("lb_gicp_fitness: null argument"); return LB_ERR_INVALID_ARG; }
+  if (!h->src.valid) { set_error("lb_gicp_fitness: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
+  if (!h->tgt.valid) { set_error("lb_gicp_fitness: no target cloud"); return LB_ERR_NO_TARGET; }
+  if (!T_in && !h->have_result) { set_error("lb_gicp_fitness: no align() result yet"); return LB_ERR_NO_ALIGN; }
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  const uint32_t N = (uint32_t)h->src.n;
+  int nb = cdiv(N, 128);
+  LB_TRY(h->io.ensure((size_t)nb * 2 * sizeof(double)));
+  Mat34 T; mat16_to_34(T_in ? T_in : h->final_T, T);
+  fitness_kernel<<<nb, 128, 0, c.stream>>>(h->tgt.view(), h->src.raw.p, N, T, max_range, (double*)h->io.p);
+  c.launches++;
+  std::vector<double> part((size_t)nb * 2);
+  LB_CUDA(cudaMemcpyAsync(part.data(), h->io.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  double sum = 0, cnt = 0;
+  for (int b = 0; b < nb; b++) { sum += part[2 * (size_t)b]; cnt += part[2 * (size_t)b + 1]; }
+  *score = cnt > 0 ? sum / cnt : 1.7976931348623157e308;   // PCL returns numeric_limits<double>::max()
+  return LB_OK;
+}
+
+int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points) {
+  if (!h || !out9) return LB_ERR_INVALID_ARG;
+  Cloud& cl = which ? h->tgt : h->src;
+  if (!cl.valid || !cl.cov_valid) { set_error("lb_gicp_get_covariances: covariances not computed (run align first)"); return LB_ERR_NO_ALIGN; }
+  if (capacity_points < cl.n) { set_error("lb_gicp_get_covariances: capacity too small"); return LB_ERR_CAPACITY; }
+  LB_CUDA(cudaSetDevice(h->c.device));
+  std::vector<double> c6(6 * cl.n);
+  std::vector<f4> pts(cl.n);
+  LB_CUDA(cudaMemcpyAsync(c6.data(), cl.cov.p, c6.size() * sizeof(double), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaMemcpyAsync(pts.data(), cl.pts.p, pts.size() * sizeof(f4), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaStreamSynchronize(h->c.stream));
+  for (size_t s = 0; s < cl.n; s++) {
+    size_t i = (size_t)float_to_bits(pts[s].w);
+    const double* m = &c6[6 * s];
+    double* o = &out9[9 * i];
+    o[0] = m[SXX]; o[1] = m[SXY]; o[2] = m[SXZ];
+    o[3] = m[SXY]; o[4] = m[SYY]; o[5] = m[SYZ];
+    o[6] = m[SXZ]; o[7] = m[SYZ]; o[8] = m[SZZ];
+  }
+  return LB_OK;
+}
+
+int lb_gicp_cloud_size(lb_gicp* h, int which, size_t* n) {
+  if (!h || !n) return LB_ERR_INVALID_ARG;
+  Cloud& cl = which ? h->tgt : h->src;
+  *n = cl.valid ? cl.n : 0;
+  return LB_OK;
+}
+int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) { if (!h || !n) return LB_ERR_INVALID_ARG; *n = h->c.launches; return LB_OK; }
+
+int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches) {
+  if (!h || !name || !ms_avg) return LB_ERR_INVALID_ARG;
+  *ms_avg = 0.f; if (launches) *launches = 0;
+  for (auto& t : h->timers) {
+    if (t.name == name) {
+      if (t.launches) *ms_avg = (float)(t.total_ms / (double)t.launches);
+      if (launches) *launches = t.launches;
+    }
+  }
+  return LB_OK;
+}
+int lb_gicp_reset_kernel_times(lb_gicp* h, int enable) {
+  if (!h) return LB_ERR_INVALID_ARG;
+  cudaStreamSynchronize(h->c.stream);
+  timers_collect(h);
+  for (auto& t : h->timers) { t.total_ms = 0; t.launches = 0; t.used = 0; }
+  h->timing = enable != 0;
+  return LB_OK;
+}
+
+}  // extern "C"

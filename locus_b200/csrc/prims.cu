@@ -1,0 +1,280 @@
+// prims.cu -- implementations of the device-wide primitives (see prims.cuh).
+#include <stdarg.h>
+
+#include "prims.cuh"
+
+namespace lb {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int ctx_init(Ctx& c, int device, void* external_stream, bool use_external) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s): the product path has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return LB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return LB_ERR_INVALID_ARG; }
+  LB_CUDA(cudaSetDevice(device));
+  c.device = device;
+  if (use_external) {
+    c.stream = (cudaStream_t)external_stream;
+    c.own_stream = false;
+  } else {
+    LB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.own_stream = true;
+  }
+  cudaDeviceProp prop;
+  LB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.sm_count = prop.multiProcessorCount;
+  c.launches = 0;
+  return LB_OK;
+}
+
+void ctx_destroy(Ctx& c) {
+  if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+}
+
+// ------------------------------------------------------------------ bbox
+__global__ void bbox_init_kernel(BBoxAcc* acc) {
+  if (threadIdx.x < 3) { acc->mn[threadIdx.x] = 0xffffffffu; acc->mx[threadIdx.x] = 0u; }
+  if (threadIdx.x == 3) { acc->count = 0; acc->pad = 0; }
+}
+
+__global__ void __launch_bounds__(256)
+bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off,
+            int ff_off, float fmin, float fmax, int negative, BBoxAcc* acc) {
+  uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0, mx1 = 0, mx2 = 0, cnt = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t* p = base + (size_t)i * stride;
+    if (ff_off >= 0) {
+      float v = *reinterpret_cast<const float*>(p + ff_off);
+      bool drop = negative ? (v < fmax && v > fmin) : (v > fmax || v < fmin);
+      if (drop) continue;
+    }
+    const float* q = reinterpret_cast<const float*>(p + xyz_off);
+    float x = q[0], y = q[1], z = q[2];
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+    uint32_t ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+    mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+    mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+    cnt++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
+    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+    mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    atomicMin(&acc->mn[0], mn0); atomicMin(&acc->mn[1], mn1); atomicMin(&acc->mn[2], mn2);
+    atomicMax(&acc->mx[0], mx0); atomicMax(&acc->mx[1], mx1); atomicMax(&acc->mx[2], mx2);
+    atomicAdd(&acc->count, cnt);
+  }
+}
+
+// ------------------------------------------------------------------ scan
+constexpr int SC_T = 256, SC_I = 8, SC_TILE = SC_T * SC_I;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across the block; returns exclusive prefix, total in *total
+template <int T>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* smem /*T/32+1*/) {
+  uint32_t incl = warp_incl_scan(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (l < T / 32) ? smem[l] : 0;
+    uint32_t si = warp_incl_scan(s);
+    if (l < T / 32) smem[l] = si - s;
+    if (l == T / 32 - 1) smem[T / 32] = si;
+  }
+  __syncthreads();
+  uint32_t r = smem[w] + incl - v;
+  *total = smem[T / 32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SC_T) scan_reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* sums) {
+  __shared__ uint32_t sm[SC_T / 32 + 1];
+  size_t base = (size_t)blockIdx.x * SC_TILE + (size_t)threadIdx.x * SC_I;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < SC_I; j++) if (base + j < n) s += in[base + j];
+  uint32_t tot;
+  block_excl_scan<SC_T>(s, &tot, sm);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) scan_spine_kernel(uint32_t* sums, size_t nb, uint32_t* total) {
+  __shared__ uint32_t sm[1024 / 32 + 1];
+  uint32_t carry = 0;
+  for (size_t start = 0; start < nb; start += 1024 * 8) {
+    size_t base = start + (size_t)threadIdx.x * 8;
+    uint32_t v[8]; uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = (base + j < nb) ? sums[base + j] : 0; s += v[j]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<1024>(s, &tot, sm) + carry;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { if (base + j < nb) sums[base + j] = ex; ex += v[j]; }
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(SC_T)
+scan_down_kernel(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t sm[SC_T / 32 + 1];
+  size_t base = (size_t)blockIdx.x * SC_TILE + (size_t)threadIdx.x * SC_I;
+  uint32_t v[SC_I]; uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < SC_I; j++) { v[j] = (base + j < n) ? in[base + j] : 0; s += v[j]; }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan<SC_T>(s, &tot, sm) + sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SC_I; j++) { if (base + j < n) out[base + j] = ex; ex += v[j]; }
+}
+
+int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev) {
+  if (n == 0) {
+    if (total_dev) LB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), c.stream));
+    return LB_OK;
+  }
+  size_t nb = (n + SC_TILE - 1) / SC_TILE;
+  LB_TRY(w.sums.ensure(nb));
+  scan_reduce_kernel<<<(unsigned)nb, SC_T, 0, c.stream>>>(in, n, w.sums.p);
+  scan_spine_kernel<<<1, 1024, 0, c.stream>>>(w.sums.p, nb, total_dev);
+  scan_down_kernel<<<(unsigned)nb, SC_T, 0, c.stream>>>(in, out, n, w.sums.p);
+  c.launches += 3;
+  LB_CUDA(cudaGetLastError());
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------ radix sort
+constexpr int RS_WARPS = 8, RS_ITEMS = 8, RS_TILE = RS_WARPS * 32 * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist, uint32_t nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = base + j * (RS_WARPS * 32) + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  block_hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                  const uint32_t* __restrict__ offsets, uint32_t nblocks) {
+  __shared__ uint32_t whist[RS_WARPS][256];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_WARPS * 32) (&whist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t warp_base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt_mask = (1u << l) - 1u;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = warp_base + j * 32 + l;
+    bool valid = i < n;
+    key[j] = valid ? keys_in[i] : 0xffffffffu;
+    val[j] = valid ? (vals_in ? vals_in[i] : i) : 0u;
+    uint32_t d = valid ? ((key[j] >> shift) & 255u) : 256u;
+    uint32_t mask = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(mask) - 1;
+    uint32_t old = 0;
+    if (l == leader && d < 256u) {
+      old = whist[w][d];
+      whist[w][d] = old + __popc(mask);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[j] = old + __popc(mask & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over the warps of this block, seeded with the global offset
+  {
+    uint32_t d = threadIdx.x;  // RS_WARPS*32 == 256 threads
+    uint32_t run = offsets[d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      uint32_t cnt = whist[ww][d];
+      whist[ww][d] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = warp_base + j * 32 + l;
+    if (i < n) {
+      uint32_t d = (key[j] >> shift) & 255u;
+      uint32_t pos = whist[w][d] + rank[j];
+      keys_out[pos] = key[j];
+      vals_out[pos] = val[j];
+    }
+  }
+}
+
+static_assert(RS_WARPS * 32 == 256, "digit scan assumes 256 threads per block");
+
+int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
+                     uint32_t** keys_out, uint32_t** vals_out) {
+  if (n > 0xfffffff0ull) { set_error("radix_sort_pairs: n too large"); return LB_ERR_INVALID_ARG; }
+  LB_TRY(w.ka.ensure(n ? n : 1)); LB_TRY(w.kb.ensure(n ? n : 1));
+  LB_TRY(w.va.ensure(n ? n : 1)); LB_TRY(w.vb.ensure(n ? n : 1));
+  uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+  if (nblocks == 0) nblocks = 1;
+  LB_TRY(w.hist.ensure((size_t)256 * nblocks));
+  int passes = (key_bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  const uint32_t* kin = keys_in; const uint32_t* vin = vals_in;
+  uint32_t* kout = w.ka.p; uint32_t* vout = w.va.p;
+  for (int p = 0; p < passes; p++) {
+    int shift = 8 * p;
+    rs_hist_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, nblocks);
+    c.launches++;
+    LB_TRY(exclusive_scan_u32(c, w.scan, w.hist.p, w.hist.p, (size_t)256 * nblocks, nullptr));
+    rs_scatter_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
+    c.launches++;
+    kin = kout; vin = vout;
+    if (kout == w.ka.p) { kout = w.kb.p; vout = w.vb.p; } else { kout = w.ka.p; vout = w.va.p; }
+  }
+  LB_CUDA(cudaGetLastError());
+  *keys_out = const_cast<uint32_t*>(kin);
+  *vals_out = const_cast<uint32_t*>(vin);
+  return LB_OK;
+}
+
+}  // namespace lb

@@ -1,0 +1,109 @@
+// prims.cuh -- device-wide primitives shared by the VoxelGrid and GICP paths:
+// stream context + growable device buffers, bounding-box reduction, stable LSD
+// radix sort of (key, value) pairs, exclusive scan.  All hand-written for
+// sm_100a; no CUB/Thrust on the product path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/locus_b200.h"
+#include "hd.h"
+
+namespace lb {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+
+#define LB_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      lb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return LB_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define LB_TRY(call)            \
+  do {                          \
+    int s__ = (call);           \
+    if (s__ != LB_OK) return s__; \
+  } while (0)
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t launches = 0;
+  int sm_count = 148;
+};
+
+int ctx_init(Ctx& c, int device, void* external_stream, bool use_external);
+void ctx_destroy(Ctx& c);
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return LB_OK;
+    size_t nc = cap ? cap : 1024;
+    while (nc < n) nc = nc + nc / 2 + 1024;
+    if (p) LB_CUDA(cudaFree(p));
+    p = nullptr; cap = 0;
+    LB_CUDA(cudaMalloc((void**)&p, nc * sizeof(T)));
+    cap = nc;
+    return LB_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ bbox
+// ordered-uint encoding of float so that unsigned min/max == float min/max
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+struct BBoxAcc {          // device-resident accumulator, 8 words
+  uint32_t mn[3], mx[3];
+  uint32_t count, pad;
+};
+
+__global__ void bbox_init_kernel(BBoxAcc* acc);
+
+// Finite-point bounding box of a strided cloud (x,y,z float32 at xyz_off).
+// Optional limit filter (VoxelGrid getMinMax3D): field value v at ff_off is
+// dropped if  negative ? (v < fmax && v > fmin) : (v > fmax || v < fmin), float compare.
+__global__ void bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off,
+                            int ff_off, float fmin, float fmax, int negative, BBoxAcc* acc);
+
+// ------------------------------------------------------------------ scan
+// Exclusive scan of n uint32 (in may alias out).  total (nullable, device) receives the grand total.
+struct ScanWork { DBuf<uint32_t> sums; };
+int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);
+
+// ------------------------------------------------------------------ sort
+// Stable LSD radix sort of (key, val) pairs on the low `key_bits` bits.
+// vals_in == nullptr means val = element index.  Result ends in *keys_out/*vals_out
+// (pointers into the ping-pong buffers a/b).
+struct SortWork {
+  DBuf<uint32_t> ka, kb, va, vb, hist;
+  ScanWork scan;
+};
+int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
+                     uint32_t** keys_out, uint32_t** vals_out);
+
+}  // namespace lb

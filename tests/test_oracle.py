@@ -1,0 +1,95 @@
+"""Pin the CPU oracle against every fixture the reference's own tests hold for this path
+(SURVEY.md section 8c).  CPU only."""
+import numpy as np
+
+import fixtures as F
+
+
+def test_hollow_cube_shift(oracle):
+    """point_cloud_odometry/test/test_point_cloud_odometry.cpp:280-305: 360-pt hollow cube vs a copy
+    shifted (+0.05, +0.05, 0); converged, fitness < 0.1, inverse translation within 1e-2."""
+    box = F.hollow_cube()
+    assert box.shape == (360, 3)
+    moved = box.copy(); moved[:, 0] += np.float32(0.05); moved[:, 1] += np.float32(0.05)
+    # odometry settings: point_cloud_odometry/config/parameters.yaml (tf_eps 1e-3, corr 1.0, 20 iterations)
+    p = oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=20)
+    r = oracle.gicp_align(moved, box, p)     # source = new scan, target = previous scan (PCO.cc:265-266)
+    assert r["status"] == 0 and r["converged"]
+    assert oracle.fitness(moved, box, r["T"]) < 0.1
+    Tinv = np.linalg.inv(r["T"].astype(np.float64))
+    assert abs(Tinv[0, 3] - 0.05) < 1e-2 and abs(Tinv[1, 3] - 0.05) < 1e-2 and abs(Tinv[2, 3]) < 1e-2
+
+
+def test_ap_known_answers(oracle):
+    """test_point_cloud_localization.cpp:337-339,391-393,501-506: Ap(0,0)=Ap(1,1)=56.7753, Ap(5,5)=100."""
+    xyz, nrm = F.plane()
+    assert xyz.shape == (100, 3)
+    Ap = oracle.compute_ap(oracle.normalize_pcloud(xyz), nrm, np.arange(100))
+    assert abs(Ap[0, 0] - 56.7753) < 1e-4 and abs(Ap[1, 1] - 56.7753) < 1e-4 and abs(Ap[5, 5] - 100) < 1e-4
+    ev = np.sort(np.linalg.eigvalsh(Ap))
+    assert np.allclose(ev, [0, 0, 0, 56.7753, 56.7753, 100], atol=1e-4)
+
+
+def test_garage_thread_invariance(oracle):
+    """multithreaded_gicp/test/test_same_output_different_num_threads.cpp:51-85: T and fitness bit-equal
+    for 1..8 threads (tf_eps 1e-10, corr 0.2, 20 iterations, 50 inner)."""
+    q, ref = F.garage()
+    assert q.shape == (811, 4) and ref.shape == (8112, 4)
+    base = None
+    for nt in range(1, 9):
+        p = oracle.default_params(transformation_epsilon=1e-10, corr_dist_threshold=0.2, max_iterations=20,
+                                  max_inner_iterations=50, num_threads=nt)
+        r = oracle.gicp_align(q, ref, p)
+        fit = oracle.fitness(q, ref, r["T"], num_threads=nt)
+        assert r["status"] == 0 and r["converged"]
+        if base is None:
+            base = (r["T"].copy(), fit)
+        else:
+            assert np.array_equal(r["T"], base[0]) and fit == base[1]
+
+
+def test_kdtree_vs_scipy(oracle):
+    from scipy.spatial import cKDTree
+    pts = F.random_scene(5000, 7)
+    q = (pts[:500] + np.random.default_rng(1).normal(0, 0.2, (500, 3))).astype(np.float32)
+    kt = oracle.KdTree(pts)
+    idx, d2 = kt.nn_batch(q)
+    dd, ii = cKDTree(pts.astype(np.float64)).query(q.astype(np.float64))
+    # scipy works in double; compare distances (ties / float rounding excepted)
+    assert np.allclose(np.sqrt(d2), dd, rtol=1e-5, atol=1e-6)
+    assert (idx == ii).mean() > 0.99
+
+
+def test_bfgs_quadratic(oracle):
+    A = np.array([[3, 1, 0.5], [1, 2, 0.2], [0.5, 0.2, 1.0]]); b = np.array([1., -2, 0.5])
+    x, it = oracle.bfgs_quadratic(A, b, np.zeros(3))
+    assert np.allclose(x, np.linalg.solve(A, b), atol=1e-6)
+
+
+def test_voxel_oracle_vs_numpy(oracle):
+    """independent numpy restatement of the PCL index arithmetic."""
+    from tools import gen_lidar as G
+    scene = G.make_scene(3)
+    blob = G.scan(scene, np.eye(4), 5, beams=16, az=512)
+    leaf = np.float32(0.4)
+    r = oracle.voxel_filter(blob, 32, leaf, float_fields=G.FLOAT_FIELDS, filter_field_offset=8,
+                            limit_min=-100, limit_max=100)
+    xyz = G.blob_xyz(blob)
+    ok = np.isfinite(xyz).all(1) & (xyz[:, 2] <= 100) & (xyz[:, 2] >= -100)
+    p = xyz[ok]
+    inv = np.float32(1.0) / leaf
+    mn = np.floor(p.min(0) * inv).astype(np.int32); mx = np.floor(p.max(0) * inv).astype(np.int32)
+    div = mx - mn + 1
+    ijk = (np.floor(p * inv) - mn.astype(np.float32)).astype(np.int32)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    u, cnt = np.unique(idx, return_counts=True)
+    assert np.array_equal(u, r["voxel_idx"]) and np.array_equal(cnt, r["count"])
+    # centroid of one multi-point voxel, summed in ascending input order in float32
+    k = int(np.argmax(cnt))
+    members = np.nonzero(idx == u[k])[0]
+    acc = p[members[0]].copy()
+    for m in members[1:]:
+        acc = acc + p[m]
+    acc = acc / np.float32(len(members))
+    got = r["out"][k].view(np.float32)[:3]
+    assert np.array_equal(got, acc)
