@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on its own config.
+
+Workload (N=1: BASELINE.json configs[1], "scan-to-scan odometry"): a synthetic 64-beam stream,
+131072 rays/scan (tools/gen_lidar.py), each step = ONE scan through the hot path:
+    VoxelGrid (130k -> ~30k)  ->  setInputSource(new) + setInputTarget(previous filtered) + align()
+with the odometry settings of SURVEY.md 8d/C2: 50 outer iterations max, 20 inner, corr 1.0 m,
+tf_eps 1e-3, k-NN(20) covariances.  Source AND target index + covariances are rebuilt every step,
+exactly like the reference's callers (PointCloudOdometry.cc:265-267).
+
+  value : scans/s, inputs already resident in HBM when the timed region starts (device pointers
+          through the C ABI), CUDA events on the launching stream, L2 flushed between steps.
+  e2e   : same metric through the reference-facing C ABI with HOST buffers (pinned): H2D of the raw
+          scan, D2H of the filtered cloud (the VoxelGrid nodelet hands it back to the host), H2D of
+          source/target, D2H of the pose -- all inside the timed region.
+  --impl reference : the CPU arm = oracle/ (C port of the reference; the reference itself needs
+          PCL/ROS and cannot be built here), all host threads, one scan per step.
+
+N>1 (torchrun): one independent scan stream per GPU (weak scaling, no data-path collective);
+barrier + device sync on both sides, max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tools import gen_lidar as G  # noqa: E402
+
+POINT_STEP = 32
+TARGET_VOXELS = 30000
+N_STREAM = 6            # distinct scans per rank, cycled
+GICP_CFG = dict(max_iterations=50, max_inner=20, corr_dist=1.0, tf_eps=1e-3, k=20)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def seq(i):
+    """ping-pong over the stream so that consecutive steps are always neighbouring poses"""
+    p = 2 * (N_STREAM - 1)
+    r = i % p
+    return r if r < N_STREAM else p - r
+
+
+def make_stream(rank):
+    seed = 2 + 8 * rank
+    scene, poses, blobs = G.stream(seed, N_STREAM)
+    return poses, blobs
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_scan_step(O, prev_filtered, blob, leaf, threads):
+    r = O.voxel_filter(blob, POINT_STEP, leaf, float_fields=G.FLOAT_FIELDS, filter_field_offset=G.Z_OFF,
+                       limit_min=-100.0, limit_max=100.0)
+    cur = np.ascontiguousarray(r["out"]).view(np.float32).reshape(-1, 8)
+    res = None
+    if prev_filtered is not None:
+        p = O.default_params(transformation_epsilon=GICP_CFG["tf_eps"], corr_dist_threshold=GICP_CFG["corr_dist"],
+                             max_iterations=GICP_CFG["max_iterations"], max_inner_iterations=GICP_CFG["max_inner"],
+                             k_correspondences=GICP_CFG["k"], num_threads=threads)
+        res = O.gicp_align(cur, prev_filtered, p)
+    return cur, res
+
+
+def run_cpu_arm(args, leaf, blobs, budget_s=None, max_steps=None):
+    """Times the oracle (C port of the reference, OpenMP like the reference: covariances + NN look-ups
+    parallel, objective serial) on the same stream.  returns (scans_per_s, n_scans, poses, cores)."""
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    prev, _ = cpu_scan_step(O, None, blobs[seq(0)], leaf, cores)
+    n, t_total, poses = 0, 0.0, {}
+    i = 1
+    while True:
+        t0 = time.perf_counter()
+        cur, res = cpu_scan_step(O, prev, blobs[seq(i)], leaf, cores)
+        t_total += time.perf_counter() - t0
+        poses[(seq(i - 1), seq(i))] = res["T"]
+        prev = cur
+        n += 1; i += 1
+        if max_steps is not None and n >= max_steps:
+            break
+        if budget_s is not None and (t_total >= budget_s or n >= 4 * len(blobs)):
+            break
+    return n / t_total, n, poses, cores
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    workload = {"workload": "C2 scan-to-scan odometry: 131072-ray synthetic 64-beam scan -> VoxelGrid ~30k -> "
+                            "GICP (<=50 outer, 20 inner BFGS, corr 1.0 m, tf_eps 1e-3, kNN(20) covariances)",
+                "raw_points_per_scan": 64 * 2048, "streams": world, "parallelism": "stream-per-gpu x%d" % world,
+                "l2": "flushed between steps (256 MiB write)", "optimizer": "bfgs (reference-exact)",
+                "execution": "persistent cooperative kernel", "index": "source and target rebuilt every step"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        leaf = pick_leaf_cpu(make_stream(0)[1][0])
+        poses, blobs = make_stream(0)
+        # warm-up
+        run_cpu_arm(args, leaf, blobs, max_steps=max(1, min(args.warmup, 2)))
+        sps, n, _, cores = run_cpu_arm(args, leaf, blobs, max_steps=max(1, args.steps))
+        line = {"impl": "reference", "metric": "gicp_scans_per_sec", "value": sps, "unit": "scans/s", "n_gpus": args.gpus,
+                "steps": n, "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 points / f64 accumulation", "data": "synthetic",
+                "config": workload,
+                "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
+                                 "sample": "%d scans of the same stream (oracle/: C port of multithreaded_gicp + "
+                                           "PCL VoxelGrid; the reference itself needs PCL/ROS, unbuildable here)" % n},
+                "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import locus_b200
+    from locus_b200 import api
+
+    if locus_b200.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; locus_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    poses, blobs = make_stream(rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    L = locus_b200.lib()
+    fields = locus_b200.xyzi_fields()
+    vg = locus_b200.VoxelGridB200(local_rank, stream=stream.cuda_stream)
+    gicp = locus_b200.GicpB200(local_rank, stream=stream.cuda_stream)
+    gicp.setMaximumIterations(GICP_CFG["max_iterations"]); gicp.setMaximumOptimizerIterations(GICP_CFG["max_inner"])
+    gicp.setMaxCorrespondenceDistance(GICP_CFG["corr_dist"]); gicp.setTransformationEpsilon(GICP_CFG["tf_eps"])
+    gicp.setCorrespondenceRandomness(GICP_CFG["k"]); gicp.setRANSACIterations(0)
+    gicp.setOptimizer(locus_b200.LB_OPT_BFGS); gicp.setExecution(locus_b200.LB_EXEC_PERSISTENT)
+
+    # leaf by bisection so that the filter output is ~30000 points, on the GPU filter itself
+    vg.setFilterFieldName("z"); vg.setFilterLimits(-100.0, 100.0)
+    lo, hi = 0.02, 2.0
+    for _ in range(18):
+        mid = 0.5 * (lo + hi)
+        vg.setLeafSize(mid)
+        n = vg.filter(blobs[0], POINT_STEP, fields).shape[0]
+        if n > TARGET_VOXELS:
+            lo = mid
+        else:
+            hi = mid
+    leaf = float(np.float32(0.5 * (lo + hi)))
+    vg.setLeafSize(leaf)
+    workload["leaf_m"] = leaf
+
+    nraw = blobs[0].size // POINT_STEP
+    with torch.cuda.stream(stream):
+        d_scans = [torch.from_numpy(b).cuda(non_blocking=False) for b in blobs]
+        d_filt = [torch.empty(nraw * POINT_STEP, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.int32, device="cuda")
+    h_scans = [torch.from_numpy(b).pin_memory() for b in blobs]
+    h_filt = [torch.empty(nraw * POINT_STEP, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    fa = api.VoxelGridB200._fields(fields)
+    n_out = C.c_size_t(0)
+    res = api.GicpResult()
+    state = {"n_prev": 0, "poses": []}
+
+    def check(s):
+        if s != 0:
+            raise RuntimeError("locus_b200 status %d: %s" % (s, L.lb_last_error_string().decode()))
+
+    def step_device(i, record=False):
+        """one scan, inputs resident in HBM"""
+        cur, prv = d_filt[i & 1], d_filt[(i + 1) & 1]
+        check(L.lb_voxel_filter(vg._h, C.c_void_p(d_scans[seq(i)].data_ptr()), nraw, POINT_STEP, fa, len(fields),
+                                None, 0, C.c_void_p(cur.data_ptr()), nraw, C.byref(n_out), None, 1, 1))
+        n_cur = n_out.value
+        if state["n_prev"]:
+            check(L.lb_gicp_set_source(gicp._h, C.c_void_p(cur.data_ptr()), n_cur, POINT_STEP, 0, -1, 1))
+            check(L.lb_gicp_set_target(gicp._h, C.c_void_p(prv.data_ptr()), state["n_prev"], POINT_STEP, 0, -1, 1, None))
+            check(L.lb_gicp_align(gicp._h, None, C.byref(res)))
+            if record:
+                state["poses"].append(((seq(i - 1), seq(i)), np.array(res.final_transformation, dtype=np.float32).reshape(4, 4)))
+                state["iters"].append(res.iterations); state["evals"].append(res.n_objective_evals)
+                state["ncorr"].append(res.n_correspondences); state["nsrc"].append(n_cur)
+        state["n_prev"] = n_cur
+
+    def step_host(i):
+        """one scan through the C ABI with HOST (pinned) buffers"""
+        cur, prv = h_filt[i & 1], h_filt[(i + 1) & 1]
+        check(L.lb_voxel_filter(vg._h, C.c_void_p(h_scans[seq(i)].data_ptr()), nraw, POINT_STEP, fa, len(fields),
+                                None, 0, C.c_void_p(cur.data_ptr()), nraw, C.byref(n_out), None, 0, 0))
+        n_cur = n_out.value
+        if state["n_prev"]:
+            check(L.lb_gicp_set_source(gicp._h, C.c_void_p(cur.data_ptr()), n_cur, POINT_STEP, 0, -1, 0))
+            check(L.lb_gicp_set_target(gicp._h, C.c_void_p(prv.data_ptr()), state["n_prev"], POINT_STEP, 0, -1, 0, None))
+            check(L.lb_gicp_align(gicp._h, None, C.byref(res)))
+            state["h2d"] = nraw * POINT_STEP + (n_cur + state["n_prev"]) * POINT_STEP
+            state["d2h"] = n_cur * POINT_STEP + 64
+        state["n_prev"] = n_cur
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(step_fn, steps, warmup, record=False):
+        state["n_prev"] = 0
+        state["poses"], state["iters"], state["evals"], state["ncorr"], state["nsrc"] = [], [], [], [], []
+        step_fn(0)                                   # prime the "previous scan"
+        for w in range(warmup):
+            step_fn(1 + w)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l_start = gicp.launchCount() + vg.launchCount()
+        t_wall0 = time.perf_counter()
+        for k in range(steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(k)                       # L2 flush: 256 MiB write, outside the event pair
+                ev[k][0].record(stream)
+            if record:
+                step_fn(1 + warmup + k, True)
+            else:
+                step_fn(1 + warmup + k)
+            ev[k][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        state["launches"] = gicp.launchCount() + vg.launchCount() - l_start
+        return dev_ms, wall
+
+    # ---- device-resident arm (value) with per-kernel timers and launch counting
+    sampler = ClockSampler(local_rank)
+    gicp.resetKernelTimes(True)
+    sampler.start()
+    dev_ms, wall = timed_run(lambda i, rec=False: step_device(i, rec), args.steps, args.warmup, record=True)
+    clocks = sampler.stop()
+    launches_timed = int(state["launches"])
+    k_ms, k_n = gicp.kernelTime("align_persistent")
+    cov_ms, cov_n = gicp.kernelTime("knn_cov")
+    idx_ms, idx_n = gicp.kernelTime("index_build")
+    gicp.resetKernelTimes(False)
+    gpu_poses = list(state["poses"])
+    iters = np.array(state["iters"], dtype=np.float64); evals = np.array(state["evals"], dtype=np.float64)
+    ncorr = np.array(state["ncorr"], dtype=np.float64); nsrc = np.array(state["nsrc"], dtype=np.float64)
+
+    # ---- host-buffer arm (e2e)
+    e2e_ms, e2e_wall = timed_run(step_host, args.steps, args.warmup)
+
+    # max over ranks (device time), whole-job aggregate
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_scans = args.steps * world
+    value = total_scans / (dev_ms_max / 1e3)
+    e2e_value = total_scans / (e2e_ms_max / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (persistent align: K4 correspondences + K5 objective resident on device).
+    # algorithmic bytes per launch: It * (88*Ns + E * 80*m), It = outer iterations, E = evals per outer.
+    peak, peak_src = measured_peak_hbm()
+    bytes_per_launch = float(np.mean(iters * 88.0 * nsrc + evals * 80.0 * ncorr)) if len(iters) else 0.0
+    achieved = (bytes_per_launch / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "align_persistent_kernel (K4 NN-correspondence + K5 objective + BFGS, resident)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": k_ms, "launches_timed": int(k_n),
+                "note": "working set (<= 5 MB) is L2-resident: this kernel is bound by grid-barrier/launch latency, "
+                        "not HBM (SURVEY H3); fraction reported for information"}
+
+    line = {"metric": "gicp_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 points / f64 accumulation", "data": "synthetic", "config": workload,
+            "clocks": clocks, "gpu_launches": launches_timed,
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(state.get("h2d", 0)),
+                    "d2h_bytes_per_step": int(state.get("d2h", 0)), "ms_per_step": e2e_ms_max / args.steps},
+            "roofline": roofline,
+            "per_scan": {"outer_iterations_mean": float(iters.mean()) if len(iters) else None,
+                         "objective_evals_mean": float(evals.mean()) if len(evals) else None,
+                         "correspondences_mean": float(ncorr.mean()) if len(ncorr) else None,
+                         "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
+                         "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms,
+                         "wall_s_timed_region": wall}}
+
+    if world == 1 and not args.no_cpu_baseline:
+        # CPU baseline on a bounded sample of the same stream, and pose delta GPU vs CPU on those scans
+        sps, n, cpu_poses, cores = run_cpu_arm(args, leaf, blobs, budget_s=args.cpu_baseline_seconds)
+        line["cpu_baseline"] = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
+                                "sample": "%d scans of the same stream, same leaf (oracle/: C port of "
+                                          "multithreaded_gicp + PCL VoxelGrid)" % n}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import fixtures as F
+        dts, drs = [], []
+        for key, Tg in gpu_poses:          # same (previous scan, scan) pair on both arms
+            if key in cpu_poses:
+                dt, dr = F.pose_delta(cpu_poses[key], Tg)
+                dts.append(dt); drs.append(dr)
+        if dts:
+            line["pose_delta_vs_cpu"] = {"max_dt_m": float(max(dts)), "max_dr_rad": float(max(drs)), "pairs": len(dts)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def pick_leaf_cpu(blob):
+    """leaf for ~30000 voxels using the oracle's voxel filter (CPU arm only)."""
+    from oracle import oracle as O
+    lo, hi = 0.02, 2.0
+    for _ in range(18):
+        mid = 0.5 * (lo + hi)
+        n = O.voxel_filter(blob, POINT_STEP, mid, float_fields=G.FLOAT_FIELDS, filter_field_offset=G.Z_OFF,
+                           limit_min=-100.0, limit_max=100.0)["out"].shape[0]
+        if n > TARGET_VOXELS:
+            lo = mid
+        else:
+            hi = mid
+    return float(np.float32(0.5 * (lo + hi)))
+
+
+if __name__ == "__main__":
+    main()
