@@ -32,6 +32,9 @@ struct Cloud {
   GridGeom geom{};
   size_t ncells = 0;
   uint64_t generation = 0;
+  float auto_cell = 0.f;       // cell size found by the last occupancy probe for this slot
+  size_t auto_n = 0;
+  float auto_diag = 0.f;
 
   GridView view() const {
     GridView v;
@@ -70,7 +73,8 @@ struct lb_gicp {
   // align state
   DBuf<f4> src_work, corr;
   DBuf<double> M, partials;
-  unsigned* d_barrier = nullptr;      // [2]: barrier, ticket
+  unsigned* d_barrier = nullptr;      // [2]: (unused), ticket of the host-driven objective kernel
+  unsigned* d_flags = nullptr;        // [2][align_blocks] epoch flags of the persistent kernel
   int* d_m = nullptr;
   double* h_sums = nullptr; double* d_sums = nullptr;        // mapped pinned [32]
   int* h_m = nullptr;                                         // pinned
@@ -163,6 +167,11 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel, AL_THREADS, 0);
   h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
   if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
+  if (cudaMalloc((void**)&h->d_flags, 2 * (size_t)h->align_blocks * sizeof(unsigned)) != cudaSuccess) {
+    set_error("lb_gicp_create: allocation failed");
+    delete h;
+    return LB_ERR_CUDA;
+  }
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   *out = h;
   return LB_OK;
@@ -235,7 +244,12 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
     cell = (float)(2.5 * spacing);
     if (!(cell > 0.f)) cell = 1.0f;
     const double target = 6.0;
-    for (int round = 0; round < 4; round++) {
+    // consecutive clouds of one stream look alike: re-use the probed cell size while the point count
+    // and extent stay within +-30 % (the probe costs two launches and a host sync per round)
+    bool reuse = cl.auto_cell > 0.f && (double)N > 0.7 * (double)cl.auto_n && (double)N < 1.3 * (double)cl.auto_n &&
+                 diag > 0.7 * cl.auto_diag && diag < 1.3 * cl.auto_diag;
+    if (reuse) { cell = cl.auto_cell; g = make_geom(cell); }
+    for (int round = 0; round < 4 && !reuse; round++) {
       g = make_geom(cell);
       size_t nc = (size_t)g.nx * g.ny * g.nz;
       LB_TRY(h->cell_cnt.ensure(nc + 1));
@@ -254,6 +268,7 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
       if (scale < 0.25) scale = 0.25;
       cell = g.h * (float)scale;
     }
+    cl.auto_cell = g.h; cl.auto_n = N; cl.auto_diag = (float)diag;
   }
   cl.geom = g;
   cl.ncells = (size_t)g.nx * g.ny * g.nz;
@@ -288,8 +303,8 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    if (k <= 20) knn_cov_kernel<20><<<cdiv(N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
-    else knn_cov_kernel<32><<<cdiv(N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    else knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
   }
   c.launches++;
   LB_CUDA(cudaGetLastError());
@@ -417,6 +432,7 @@ int lb_gicp_destroy(lb_gicp* h) {
   if (h->d_u32) cudaFree(h->d_u32);
   if (h->h_u32) cudaFreeHost(h->h_u32);
   if (h->d_barrier) cudaFree(h->d_barrier);
+  if (h->d_flags) cudaFree(h->d_flags);
   if (h->d_m) cudaFree(h->d_m);
   if (h->h_sums) cudaFreeHost(h->h_sums);
   if (h->h_m) cudaFreeHost(h->h_m);
@@ -522,9 +538,9 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
   } else {
     AlignArgs aa;
-    aa.c = ca; aa.partials = h->partials.p; aa.barrier = h->d_barrier; aa.P = OP; aa.result = h->d_result;
+    aa.c = ca; aa.partials = h->partials.p; aa.flags = h->d_flags; aa.P = OP; aa.result = h->d_result;
     for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
-    LB_CUDA(cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned), c.stream));
+    LB_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * (size_t)h->align_blocks * sizeof(unsigned), c.stream));
     void* args[] = {&aa};
     {
       ScopedKernelTime kt(h, "align_persistent");

@@ -108,6 +108,115 @@ knn_cov_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
   for (int e = 0; e < 6; e++) d[e] = out[e];
 }
 
+// K3, quad-per-query variant (default): the 4 lanes of a quad scan every cell run of the probe block
+// cooperatively (lane q takes points s+q, s+q+4, ... of each contiguous run: 64-byte coalesced reads),
+// each keeping its own sorted top-K; a quad-wide K-round merge (shuffle min on (d2, index)) yields the
+// exact union top-K in ascending order and accumulates the moments in that order -- the same order the
+// one-thread kernel and the oracle use, so results are bit-identical.  4x the resident warps of the
+// thread-per-point kernel and a quarter of the insertion work per lane.
+template <int K>
+struct QuadList {
+  float d2[K];
+  int oi[K];
+  int si[K];
+  int cnt;
+  __device__ __forceinline__ void init() { cnt = 0; }
+  __device__ __forceinline__ void push(float d, int o, int s) {
+    if (cnt == K) {
+      if (!better(d, o, d2[K - 1], oi[K - 1])) return;
+    } else {
+      cnt++;
+    }
+    int j = cnt - 1;
+    while (j > 0 && better(d, o, d2[j - 1], oi[j - 1])) {
+      d2[j] = d2[j - 1]; oi[j] = oi[j - 1]; si[j] = si[j - 1];
+      j--;
+    }
+    d2[j] = d; oi[j] = o; si[j] = s;
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int cy, int cz, int r, float qx, float qy,
+                                                float qz, int sub, QuadList<K>& L) {
+  int z0 = imax_(cz - r, 0), z1 = imin_(cz + r, g.nz - 1);
+  int y0 = imax_(cy - r, 0), y1 = imin_(cy + r, g.ny - 1);
+  for (int z = z0; z <= z1; z++) {
+    bool zface = (iabs_(z - cz) == r);
+    for (int y = y0; y <= y1; y++) {
+      bool face = zface || (iabs_(y - cy) == r);
+      int base = (z * g.ny + y) * g.nx;
+      int nseg = face ? 1 : 2;
+      for (int k = 0; k < nseg; k++) {
+        int xa, xb;
+        if (face) { xa = imax_(cx - r, 0); xb = imin_(cx + r, g.nx - 1); }
+        else { xa = xb = (k == 0) ? cx - r : cx + r; if (xa < 0 || xa >= g.nx) continue; }
+        if (xa > xb) continue;
+        uint32_t s = g.cell_start[base + xa], e = g.cell_start[base + xb + 1];
+        for (uint32_t i = s + sub; i < e; i += 4) {
+          f4 p = g.pts[i];
+          L.push(dist2(qx, qy, qz, p.x, p.y, p.z), float_to_bits(p.w), (int)i);
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t s = t >> 2;
+  const int sub = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+  if (s >= (uint32_t)g.n) return;   // whole quads exit together (n is checked per quad)
+  f4 q = g.pts[s];
+  QuadList<K> L;
+  L.init();
+  int cx, cy, cz; float minfrac;
+  query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
+  int r0, r1;
+  ring_range(g, cx, cy, cz, r0, r1);
+  double sum[3], m2[6];
+  for (int r = r0; r <= r1; r++) {
+    quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L);
+    // K-round merge of the four sorted lists
+    int p = 0, found = 0;
+    float kth = 3.0e38f;
+    sum[0] = sum[1] = sum[2] = 0.0;
+    m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+    for (int round = 0; round < k; round++) {
+      float hd = (p < L.cnt) ? L.d2[p] : 3.0e38f;
+      int ho = (p < L.cnt) ? L.oi[p] : 0x7fffffff;
+      int hs = (p < L.cnt) ? L.si[p] : -1;
+      float bd = hd; int bo = ho; int bs = hs;
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        float od = __shfl_xor_sync(qmask, bd, o);
+        int oo = __shfl_xor_sync(qmask, bo, o);
+        int os = __shfl_xor_sync(qmask, bs, o);
+        if (better(od, oo, bd, bo)) { bd = od; bo = oo; bs = os; }
+      }
+      if (bs < 0) break;          // fewer than k points in everything scanned so far
+      if (bo == ho && hs >= 0) p++;
+      found++;
+      kth = bd;
+      f4 pt = g.pts[bs];
+      sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
+      m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
+      m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+    }
+    if (found == k && kth < ring_bound2(g, r, minfrac)) break;
+  }
+  double out[6];
+  cov_from_moments(sum, m2, k, eps, out);
+  if (sub == 0) {
+    double* d = cov + 6 * (size_t)s;
+#pragma unroll
+    for (int e = 0; e < 6; e++) d[e] = out[e];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 normal_cov_kernel(const f4* __restrict__ pts, const f4* __restrict__ nrm, uint32_t n, double eps, double* __restrict__ cov) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,139 +431,206 @@ objective_kernel(ObjArgs a, Vec6d x, double* __restrict__ partials, unsigned* __
 }
 
 // ------------------------------------------------------------------ persistent align
+// One cooperative launch per align(): the whole computeTransformation loop (gicp.hpp:445-583) stays on
+// the device.  Per CTA, warp 0 is the LEADER: its 32 lanes run the scalar outer-loop / BFGS code of
+// bfgs.h convergently (state in registers / a few hundred bytes of L1-resident local memory); the other
+// warps are WORKERS parked on the CTA barrier until the leader posts a command (correspond / objective /
+// Gauss-Newton terms / exit) in shared memory.  Every data-parallel command ends in a grid-wide
+// deterministic all-reduce: CTA partials + an epoch flag are published to a slot (st.release), every CTA
+// polls the flags of all slots (ld.acquire) and sums the slots in a fixed order -- no atomics, and every
+// CTA obtains bitwise identical totals, so all leaders take identical decisions.
 struct AlignArgs {
   CorrArgs c;
-  double* partials;       // 2 buffers x gridDim.x x AL_PSTRIDE doubles
-  unsigned* barrier;      // zeroed before launch
+  double* partials;       // [2][gridDim.x][AL_PSTRIDE] doubles
+  unsigned* flags;        // [2][gridDim.x] epoch flags, zeroed before launch
   OuterParams P;
   float guess[16];
   OuterResult* result;
 };
 
-struct DeviceBackend {
-  const AlignArgs& a;
-  double* red;            // shared: [AL_THREADS/32][AL_MAXV]
-  double* bc;             // shared: broadcast slots [AL_MAXV + 8]
+enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4 };
+
+struct AlignShared {
+  int op;
+  int m;
+  float T[12];
+  double R[9];
+  double D[27];
+  double red[(AL_THREADS / 32) * AL_MAXV];
+  double bc[AL_MAXV + 4];
+};
+
+struct Collective {   // per-thread copy; advances in lockstep in every thread of the grid
   unsigned epoch;
   int flip;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid-wide deterministic sum of NV doubles per thread; totals land in sh.bc[0..NV-1] (all threads, after return)
+template <int NV>
+__device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared& sh, Collective& co, double* acc) {
+  block_reduce<NV, AL_THREADS>(acc, sh.red);
+  co.epoch++;
+  const int ncta = gridDim.x;
+  double* buf = a.partials + (size_t)co.flip * ncta * AL_PSTRIDE;
+  unsigned* flg = a.flags + (size_t)co.flip * ncta;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int e = 0; e < NV; e++) __stcg(&buf[(size_t)blockIdx.x * AL_PSTRIDE + e], acc[e]);
+    st_release_u32(&flg[blockIdx.x], co.epoch);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = warp; e < NV; e += AL_THREADS / 32) {
+    double x = 0.0;
+    for (int b = lane; b < ncta; b += 32) {
+      while (ld_acquire_u32(&flg[b]) < co.epoch) {}
+      x += __ldcg(&buf[(size_t)b * AL_PSTRIDE + e]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sh.bc[e] = x;
+  }
+  co.flip ^= 1;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co) {
+  float T[12]; double R[9];
+#pragma unroll
+  for (int i = 0; i < 12; i++) T[i] = sh.T[i];
+#pragma unroll
+  for (int i = 0; i < 9; i++) R[i] = sh.R[i];
+  double cnt[1] = {0.0};
+  for (int s = blockIdx.x * AL_THREADS + threadIdx.x; s < a.c.n_src; s += gridDim.x * AL_THREADS)
+    cnt[0] += (double)correspond_point(a.c, T, R, s);
+  // the correspondence arrays written above are read by other CTAs?  No: every CTA re-reads only the
+  // points of its own grid-stride slice in do_objective, written by the same threads.
+  grid_all_reduce<1>(a, sh, co, cnt);
+}
+
+template <int NV>
+__device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh, Collective& co) {
+  float T[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) T[i] = sh.T[i];
+  double acc[NV];
+#pragma unroll
+  for (int e = 0; e < NV; e++) acc[e] = 0.0;
+  ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
+  objective_accumulate<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, blockIdx.x * AL_THREADS + threadIdx.x,
+                           gridDim.x * AL_THREADS, acc);
+  grid_all_reduce<NV>(a, sh, co, acc);
+}
+
+// Backend of bfgs.h for the leader warp (all 32 lanes call every method together).
+struct DeviceBackend {
+  const AlignArgs& a;
+  AlignShared& sh;
+  Collective& co;
   int m;
 
-  __device__ DeviceBackend(const AlignArgs& a_, double* red_, double* bc_) : a(a_), red(red_), bc(bc_), epoch(0), flip(0), m(0) {}
+  __device__ DeviceBackend(const AlignArgs& a_, AlignShared& sh_, Collective& co_) : a(a_), sh(sh_), co(co_), m(0) {}
 
-  __device__ __forceinline__ void grid_barrier() {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      epoch++;
-      unsigned target = epoch * gridDim.x;
-      __threadfence();
-      atomicAdd(a.barrier, 1u);
-      while (true) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
-        if (v >= target) break;
-      }
-      __threadfence();
+  // the 12 trigonometric values of a state, one per lane, broadcast to the warp
+  __device__ __forceinline__ void warp_trig(const double* x, Trig& t) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane % 3;
+    double v = 0.0;
+    if (lane < 6) {                      // half angles, float-rounded argument
+      double h = (double)half_angle(x, k);
+      v = (lane < 3) ? cos(h) : sin(h);
+    } else if (lane < 12) {
+      double ang = x[3 + k];
+      v = (lane < 9) ? cos(ang) : sin(ang);
     }
-    __syncthreads();
-  }
-
-  // grid-wide deterministic sum of NV doubles per thread; totals land in bc[0..NV-1] for every thread
-  template <int NV>
-  __device__ __forceinline__ void grid_reduce(double* acc) {
-    block_reduce<NV, AL_THREADS>(acc, red);
-    double* buf = a.partials + (size_t)flip * gridDim.x * AL_PSTRIDE;
-    if (threadIdx.x == 0) {
 #pragma unroll
-      for (int e = 0; e < NV; e++) __stcg(&buf[(size_t)blockIdx.x * AL_PSTRIDE + e], acc[e]);
+    for (int i = 0; i < 3; i++) {
+      t.ch[i] = (float)__shfl_sync(0xffffffffu, v, i);
+      t.sh[i] = (float)__shfl_sync(0xffffffffu, v, 3 + i);
+      t.c[i] = __shfl_sync(0xffffffffu, v, 6 + i);
+      t.s[i] = __shfl_sync(0xffffffffu, v, 9 + i);
     }
-    grid_barrier();
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = warp; e < NV; e += AL_THREADS / 32) {
-      double x = reduce_slots(buf, gridDim.x, e, lane);
-      if (lane == 0) bc[e] = x;
-    }
-    flip ^= 1;
-    __syncthreads();
   }
 
   __device__ int correspond(const float* T, const double* R) {
-    double cnt[1] = {0.0};
-    for (int s = blockIdx.x * AL_THREADS + threadIdx.x; s < a.c.n_src; s += gridDim.x * AL_THREADS)
-      cnt[0] += (double)correspond_point(a.c, T, R, s);
-    grid_reduce<1>(cnt);
-    m = (int)bc[0];
+    const int lane = threadIdx.x & 31;
+    if (lane < 12) sh.T[lane] = T[lane];
+    if (lane < 9) sh.R[lane] = R[lane];
+    if (lane == 0) sh.op = OP_CORR;
     __syncthreads();
+    do_correspond(a, sh, co);
+    m = (int)sh.bc[0];
     return m;
   }
 
   __device__ void fdf(const double* x, double* f, double* g) {
+    const int lane = threadIdx.x & 31;
+    Trig t;
+    warp_trig(x, t);
     float T[12];
-    if (threadIdx.x == 0) {
-      float t[12];
-      apply_state(x, t);
-      float* sT = reinterpret_cast<float*>(bc + AL_MAXV);
-#pragma unroll
-      for (int i = 0; i < 12; i++) sT[i] = t[i];
-    }
+    apply_state_trig(x, t, T);
+    if (lane < 12) sh.T[lane] = T[lane];
+    if (lane == 0) sh.op = OP_FDF;
     __syncthreads();
-    {
-      const float* sT = reinterpret_cast<const float*>(bc + AL_MAXV);
+    do_objective<13>(a, sh, co);
+    double sums[13];
 #pragma unroll
-      for (int i = 0; i < 12; i++) T[i] = sT[i];
-    }
-    double acc[13];
-#pragma unroll
-    for (int e = 0; e < 13; e++) acc[e] = 0.0;
-    ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
-    objective_accumulate<13>(oa, T, nullptr, nullptr, nullptr, blockIdx.x * AL_THREADS + threadIdx.x,
-                             gridDim.x * AL_THREADS, acc);
-    grid_reduce<13>(acc);
-    if (threadIdx.x == 0) {
-      double sums[13], ff, gg[6];
-#pragma unroll
-      for (int e = 0; e < 13; e++) sums[e] = bc[e];
-      objective_finish(sums, m, x, &ff, gg);
-      bc[16] = ff;
-#pragma unroll
-      for (int e = 0; e < 6; e++) bc[17 + e] = gg[e];
-    }
-    __syncthreads();
-    *f = bc[16];
-#pragma unroll
-    for (int e = 0; e < 6; e++) g[e] = bc[17 + e];
-    __syncthreads();
+    for (int e = 0; e < 13; e++) sums[e] = sh.bc[e];
+    objective_finish_trig(sums, m, t, f, g);
   }
 
   __device__ int gn(const double* x, double* f, double* b, double* H) {
-    // derivative matrices and T are cheap: every thread builds them (identical inputs -> identical bits)
+    const int lane = threadIdx.x & 31;
+    Trig t;
+    warp_trig(x, t);
     float T[12];
-    double dP[9], dT[9], dS[9];
-    apply_state(x, T);
-    r_derivatives(x, dP, dT, dS);
-    double acc[28];
-#pragma unroll
-    for (int e = 0; e < 28; e++) acc[e] = 0.0;
-    ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
-    objective_accumulate<28>(oa, T, dP, dT, dS, blockIdx.x * AL_THREADS + threadIdx.x, gridDim.x * AL_THREADS, acc);
-    grid_reduce<28>(acc);
-    *f = bc[0] / (double)m;
-#pragma unroll
-    for (int e = 0; e < 6; e++) b[e] = bc[1 + e];
-#pragma unroll
-    for (int e = 0; e < 21; e++) H[e] = bc[7 + e];
+    double D[27];
+    apply_state_trig(x, t, T);
+    r_derivatives_trig(t, D, D + 9, D + 18);
+    if (lane < 12) sh.T[lane] = T[lane];
+    if (lane < 27) sh.D[lane] = D[lane];
+    if (lane == 0) sh.op = OP_GN;
     __syncthreads();
+    do_objective<28>(a, sh, co);
+    *f = sh.bc[0] / (double)m;
+#pragma unroll
+    for (int e = 0; e < 6; e++) b[e] = sh.bc[1 + e];
+#pragma unroll
+    for (int e = 0; e < 21; e++) H[e] = sh.bc[7 + e];
     return 0;
   }
 };
 
 __global__ void __launch_bounds__(AL_THREADS, 1)
 align_persistent_kernel(const __grid_constant__ AlignArgs a) {
-  __shared__ double red[(AL_THREADS / 32) * AL_MAXV];
-  __shared__ double bc[AL_MAXV + 8];
-  DeviceBackend be(a, red, bc);
-  OuterResult r;
-  gicp_outer_loop(be, a.P, a.guess, r);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.result = r;
+  __shared__ AlignShared sh;
+  Collective co;
+  co.epoch = 0; co.flip = 0;
+  if (threadIdx.x < 32) {
+    DeviceBackend be(a, sh, co);
+    OuterResult r;
+    gicp_outer_loop(be, a.P, a.guess, r);
+    if (threadIdx.x == 0) sh.op = OP_EXIT;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.result = r;
+  } else {
+    for (;;) {
+      __syncthreads();
+      const int op = sh.op;
+      if (op == OP_EXIT) break;
+      if (op == OP_CORR) do_correspond(a, sh, co);
+      else if (op == OP_FDF) do_objective<13>(a, sh, co);
+      else do_objective<28>(a, sh, co);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ fitness (a9)

@@ -49,17 +49,32 @@ LB_HD void xform_pcl(const float* T, float x, float y, float z, float& ox, float
   oz = T[8] * x + (T[9] * y + (T[10] * z + T[11]));
 }
 
+// Trigonometry of one optimiser state x: half-angle cos/sin (float, for applyState) and
+// full-angle cos/sin (double, for the rotation derivatives).  Kept separate from its users so the
+// persistent kernel can evaluate the 12 values on 12 lanes of the leader warp in parallel.
+// index 0,1,2 = roll(x3), pitch(x4), yaw(x5).
+struct Trig {
+  float ch[3], sh[3];
+  double c[3], s[3];
+};
+LB_HD float half_angle(const double* x, int k) { return 0.5f * (float)x[3 + k]; }
+// sin/cos of the half angles are taken in double and rounded to float: that is the correctly
+// rounded float result on host and device alike (glibc sinf/cosf used by the reference are
+// correctly rounded in all but vanishingly few cases).
+LB_HD void trig_compute(const double* x, Trig& t) {
+  for (int k = 0; k < 3; k++) {
+    double h = (double)half_angle(x, k);
+    t.ch[k] = (float)cos(h); t.sh[k] = (float)sin(h);
+    t.c[k] = cos(x[3 + k]); t.s[k] = sin(x[3 + k]);
+  }
+}
+
 // applyState on identity (gicp.hpp:619-634): R = Rz(x5) Ry(x4) Rx(x3) built in
 // float32 through Eigen's AngleAxisf -> Quaternionf products -> toRotationMatrix.
-// sin/cos of the half angles are taken in double and rounded to float: that is
-// the correctly rounded float result on host and device alike (glibc sinf/cosf
-// used by the reference are correctly rounded in all but vanishingly few cases).
-LB_HD void apply_state(const double* x, float* T /*12: row-major 3x4*/) {
-  float az = (float)x[5], ay = (float)x[4], ax = (float)x[3];
-  float hz = 0.5f * az, hy = 0.5f * ay, hx = 0.5f * ax;
-  float cz = (float)cos((double)hz), sz = (float)sin((double)hz);
-  float cy = (float)cos((double)hy), sy = (float)sin((double)hy);
-  float cx = (float)cos((double)hx), sx = (float)sin((double)hx);
+LB_HD void apply_state_trig(const double* x, const Trig& t, float* T /*12: row-major 3x4*/) {
+  float cz = t.ch[2], sz = t.sh[2];
+  float cy = t.ch[1], sy = t.sh[1];
+  float cx = t.ch[0], sx = t.sh[0];
   float w1 = cz * cy, x1 = -(sz * sy), y1 = cz * sy, z1 = sz * cy;
   float qw = w1 * cx - x1 * sx;
   float qx = w1 * sx + x1 * cx;
@@ -73,6 +88,11 @@ LB_HD void apply_state(const double* x, float* T /*12: row-major 3x4*/) {
   T[4] = txy + twz;          T[5] = 1.0f - (txx + tzz); T[6] = tyz - twx;           T[7] = (float)x[1];
   T[8] = txz - twy;          T[9] = tyz + twx;          T[10] = 1.0f - (txx + tyy); T[11] = (float)x[2];
 }
+LB_HD void apply_state(const double* x, float* T) {
+  Trig t;
+  trig_compute(x, t);
+  apply_state_trig(x, t, T);
+}
 
 // State from a transform (gicp.hpp:235-241), float entries promoted to double.
 LB_HD void state_from_transform(const float* T, double* x) {
@@ -83,11 +103,10 @@ LB_HD void state_from_transform(const float* T, double* x) {
 }
 
 // dR/d(phi,theta,psi) closed forms (gicp.hpp:175-209), row-major 3x3 each.
-LB_HD void r_derivatives(const double* x, double* dP, double* dT, double* dS) {
-  double phi = x[3], theta = x[4], psi = x[5];
-  double cphi = cos(phi), sphi = sin(phi);
-  double ctheta = cos(theta), stheta = sin(theta);
-  double cpsi = cos(psi), spsi = sin(psi);
+LB_HD void r_derivatives_trig(const Trig& t, double* dP, double* dT, double* dS) {
+  double cphi = t.c[0], sphi = t.s[0];
+  double ctheta = t.c[1], stheta = t.s[1];
+  double cpsi = t.c[2], spsi = t.s[2];
   dP[0] = 0.; dP[3] = 0.; dP[6] = 0.;
   dP[1] = sphi * spsi + cphi * cpsi * stheta;
   dP[4] = -cpsi * sphi + cphi * spsi * stheta;
@@ -109,10 +128,16 @@ LB_HD void r_derivatives(const double* x, double* dP, double* dT, double* dS) {
   dS[8] = 0.;
 }
 
+LB_HD void r_derivatives(const double* x, double* dP, double* dT, double* dS) {
+  Trig t;
+  trig_compute(x, t);
+  r_derivatives_trig(t, dP, dT, dS);
+}
+
 // g[3..5] = tr(dR_k * Rhat)  (computeRDerivative + matricesInnerProd, gicp.hpp:211-213, gicp.h:361-370)
-LB_HD void rotation_gradient(const double* x, const double* Rhat /*row-major 3x3*/, double* g) {
+LB_HD void rotation_gradient_trig(const Trig& t, const double* Rhat /*row-major 3x3*/, double* g) {
   double dP[9], dT[9], dS[9];
-  r_derivatives(x, dP, dT, dS);
+  r_derivatives_trig(t, dP, dT, dS);
   double r0 = 0., r1 = 0., r2 = 0.;
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
@@ -121,6 +146,11 @@ LB_HD void rotation_gradient(const double* x, const double* Rhat /*row-major 3x3
       r2 += dS[j * 3 + i] * Rhat[i * 3 + j];
     }
   g[3] = r0; g[4] = r1; g[5] = r2;
+}
+LB_HD void rotation_gradient(const double* x, const double* Rhat, double* g) {
+  Trig t;
+  trig_compute(x, t);
+  rotation_gradient_trig(t, Rhat, g);
 }
 
 // ---------------------------------------------------------------- symmetric 3x3
@@ -289,13 +319,18 @@ LB_HD void objective_terms(const float* T, float px, float py, float pz, float q
 }
 
 // Turn the 13 reduced sums into f and the 6-gradient (gicp.hpp:398-401).
-LB_HD void objective_finish(const double* sums /*13*/, int m, const double* x, double* f, double* g /*6*/) {
+LB_HD void objective_finish_trig(const double* sums /*13*/, int m, const Trig& t, double* f, double* g /*6*/) {
   *f = sums[0] / (double)m;
   double sc = 2.0 / m;
   g[0] = sums[1] * sc; g[1] = sums[2] * sc; g[2] = sums[3] * sc;
   double Rhat[9];
   for (int i = 0; i < 9; i++) Rhat[i] = sums[4 + i] * sc;
-  rotation_gradient(x, Rhat, g);
+  rotation_gradient_trig(t, Rhat, g);
+}
+LB_HD void objective_finish(const double* sums /*13*/, int m, const double* x, double* f, double* g /*6*/) {
+  Trig t;
+  trig_compute(x, t);
+  objective_finish_trig(sums, m, t, f, g);
 }
 
 // Gauss-Newton terms (not in the reference): J = [I | dP p, dT p, dS p],

@@ -88,40 +88,60 @@ vg_keep_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ s
   keep[s] = ((int)(e - a) >= min_points) ? 1u : 0u;
 }
 
+// Gather the averaged FLOAT32 fields of every point into voxel-sorted order (one thread per sorted
+// position: scattered 4-byte reads with full memory-level parallelism, coalesced writes), so that the
+// per-voxel sequential sums below stream over contiguous memory.
+__global__ void __launch_bounds__(256)
+vg_gather_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ vals, uint32_t n,
+                 VoxelFieldsDev F, float* __restrict__ sorted_f) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint8_t* p = in + (size_t)vals[s] * stride;
+  float* d = sorted_f + (size_t)s * F.n_ff;
+  for (int f = 0; f < F.n_ff; f++) d[f] = *reinterpret_cast<const float*>(p + F.ff_off[f]);
+}
+
+// One thread per voxel: float32 sum of its points in ascending input order (the order the stable sort
+// produced), divide by the count (centroid /= float(n), PCL), write the output point.
 __global__ void __launch_bounds__(128)
 vg_centroid_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ keys,
-                   const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_start,
-                   const uint32_t* n_seg_dev, const uint32_t* __restrict__ slot /*nullable*/,
-                   const uint32_t* __restrict__ keep /*nullable*/, uint32_t n, VoxelFieldsDev F, uint32_t capacity,
-                   uint8_t* __restrict__ out, int32_t* __restrict__ out_voxel_idx) {
+                   const uint32_t* __restrict__ vals, const float* __restrict__ sorted_f,
+                   const uint32_t* __restrict__ seg_start, const uint32_t* n_seg_dev,
+                   const uint32_t* __restrict__ slot /*nullable*/, const uint32_t* __restrict__ keep /*nullable*/,
+                   uint32_t n, VoxelFieldsDev F, uint32_t capacity, uint8_t* __restrict__ out,
+                   int32_t* __restrict__ out_voxel_idx) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= *n_seg_dev) return;
+  const uint32_t n_seg = *n_seg_dev;
+  if (s >= n_seg) return;
   if (keep && !keep[s]) return;
   uint32_t o = slot ? slot[s] : s;
   if (o >= capacity) return;
   uint32_t a = seg_start[s];
   uint32_t k = keys[a];
+  // segment end: next segment's start, or the first sentinel key after the last voxel
+  uint32_t e;
+  if (s + 1 < n_seg) e = seg_start[s + 1];
+  else { e = a + 1; while (e < n && keys[e] == k) e++; }
   float acc[VG_MAX_FIELDS];
-  const uint8_t* first = in + (size_t)vals[a] * stride;
+  const int nf = F.n_ff;
+  const float* src = sorted_f + (size_t)a * nf;
 #pragma unroll
-  for (int f = 0; f < VG_MAX_FIELDS; f++)
-    acc[f] = (f < F.n_ff) ? *reinterpret_cast<const float*>(first + F.ff_off[f]) : 0.f;
-  uint32_t e = a + 1;
-  while (e < n && keys[e] == k) {
-    const uint8_t* p = in + (size_t)vals[e] * stride;
+  for (int f = 0; f < VG_MAX_FIELDS; f++) acc[f] = (f < nf) ? src[f] : 0.f;
+  for (uint32_t j = a + 1; j < e; j++) {
+    src += nf;
 #pragma unroll
     for (int f = 0; f < VG_MAX_FIELDS; f++)
-      if (f < F.n_ff) acc[f] = acc[f] + *reinterpret_cast<const float*>(p + F.ff_off[f]);
-    e++;
+      if (f < nf) acc[f] = acc[f] + src[f];
   }
   float cnt = (float)(e - a);
+  const uint8_t* first = in + (size_t)vals[a] * stride;
   uint8_t* dst = out + (size_t)o * stride;
   // bytes not covered by an averaged field come from the voxel's first point
   for (uint32_t w = 0; w < stride / 4; w++)
     reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(first)[w];
 #pragma unroll
   for (int f = 0; f < VG_MAX_FIELDS; f++)
-    if (f < F.n_ff) *reinterpret_cast<float*>(dst + F.ff_off[f]) = acc[f] / cnt;
+    if (f < nf) *reinterpret_cast<float*>(dst + F.ff_off[f]) = acc[f] / cnt;
   if (out_voxel_idx) out_voxel_idx[o] = (int32_t)k;
 }
 
@@ -140,6 +160,7 @@ struct lb_voxel {
   DBuf<uint8_t> d_in, d_out;
   DBuf<int32_t> d_vidx;
   DBuf<uint32_t> keys, flags, seg_start, keep, slot;
+  DBuf<float> sorted_f;
   BBoxAcc* d_acc = nullptr;     // device
   uint32_t* d_tot = nullptr;    // device [2]
   BBoxAcc* h_acc = nullptr;     // pinned
@@ -178,7 +199,7 @@ int lb_voxel_destroy(lb_voxel* h) {
   cudaSetDevice(h->c.device);
   cudaStreamSynchronize(h->c.stream);
   h->d_in.release(); h->d_out.release(); h->d_vidx.release(); h->keys.release(); h->flags.release();
-  h->seg_start.release(); h->keep.release(); h->slot.release();
+  h->seg_start.release(); h->keep.release(); h->slot.release(); h->sorted_f.release();
   h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
   h->sort.scan.sums.release(); h->scan.sums.release();
   if (h->d_acc) cudaFree(h->d_acc);
@@ -256,6 +277,8 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     F.n_ff = 3; F.ff_off[0] = xo; F.ff_off[1] = yo; F.ff_off[2] = zo;
   }
 
+  // x,y,z must be contiguous for bbox_kernel's 3-float read (true for every PCL point type)
+  if (yo != xo + 4 || zo != xo + 8) { set_error("lb_voxel_filter: x,y,z must be consecutive FLOAT32 fields"); return LB_ERR_UNSUPPORTED; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
   const uint32_t n = (uint32_t)n_pts;
@@ -273,8 +296,6 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, ffo, (float)h->lim_min,
                                                 (float)h->lim_max, h->negative, h->d_acc);
   c.launches += 2;
-  // x,y,z must be contiguous for bbox_kernel's 3-float read
-  if (yo != xo + 4 || zo != xo + 8) { set_error("lb_voxel_filter: x,y,z must be consecutive FLOAT32 fields"); return LB_ERR_UNSUPPORTED; }
   LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
   if (h->h_acc->count == 0) { *n_out = 0; return LB_OK; }
@@ -327,9 +348,11 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     d_out = h->d_out.p; capacity = n;
     if (out_voxel_idx) { LB_TRY(h->d_vidx.ensure(n)); d_vidx = h->d_vidx.p; }
   }
-  vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, h->seg_start.p, &h->d_tot[0], slot,
-                                                          keep, n, F, capacity, d_out, d_vidx);
-  c.launches++;
+  LB_TRY(h->sorted_f.ensure((size_t)n * F.n_ff));
+  vg_gather_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, point_step, sv, n, F, h->sorted_f.p);
+  vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, h->sorted_f.p, h->seg_start.p,
+                                                          &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
+  c.launches += 2;
   LB_CUDA(cudaGetLastError());
   LB_CUDA(cudaMemcpyAsync(h->h_tot, n_final_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
