@@ -239,6 +239,12 @@ def main():
     gicp.setMaxCorrespondenceDistance(GICP_CFG["corr_dist"]); gicp.setTransformationEpsilon(GICP_CFG["tf_eps"])
     gicp.setCorrespondenceRandomness(GICP_CFG["k"]); gicp.setRANSACIterations(0)
     gicp.setOptimizer(locus_b200.LB_OPT_BFGS); gicp.setExecution(locus_b200.LB_EXEC_PERSISTENT)
+    if os.environ.get("LB_CELL"):            # tuning aid: fixed voxel-hash cell size instead of the automatic one
+        gicp.setIndexCellSize(float(os.environ["LB_CELL"]))
+        workload["index_cell_size"] = float(os.environ["LB_CELL"])
+    if os.environ.get("LB_EXEC"):
+        gicp.setExecution(int(os.environ["LB_EXEC"]))
+        workload["execution"] = "host-driven" if int(os.environ["LB_EXEC"]) else workload["execution"]
 
     # leaf by bisection so that the filter output is ~30000 points, on the GPU filter itself
     vg.setFilterFieldName("z"); vg.setFilterLimits(-100.0, 100.0)
@@ -341,6 +347,7 @@ def main():
     k_ms, k_n = gicp.kernelTime("align_persistent")
     cov_ms, cov_n = gicp.kernelTime("knn_cov")
     idx_ms, idx_n = gicp.kernelTime("index_build")
+    dbg = [gicp.kernelTime("debug%d" % i)[0] for i in range(4)]
     gicp.resetKernelTimes(False)
     gpu_poses = list(state["poses"])
     iters = np.array(state["iters"], dtype=np.float64); evals = np.array(state["evals"], dtype=np.float64)
@@ -387,6 +394,8 @@ def main():
                          "correspondences_mean": float(ncorr.mean()) if len(ncorr) else None,
                          "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
                          "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms,
+                         "align_last_launch_cycles": {"total": dbg[0], "block_reduce_publish": dbg[1],
+                                                      "slot_wait_sum": dbg[2], "collectives": dbg[3]},
                          "wall_s_timed_region": wall}}
 
     if world == 1 and not args.no_cpu_baseline:

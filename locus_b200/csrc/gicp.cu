@@ -72,9 +72,11 @@ struct lb_gicp {
   uint32_t* d_u32 = nullptr; uint32_t* h_u32 = nullptr;     // small counters [8]
   // align state
   DBuf<f4> src_work, corr;
-  DBuf<double> M, partials;
+  DBuf<double> M;
+  DBuf<SlotWord> slots;
+  unsigned long long epoch_base = 1ull << 20;
+  long long* d_debug = nullptr; long long* h_debug = nullptr;
   unsigned* d_barrier = nullptr;      // [2]: (unused), ticket of the host-driven objective kernel
-  unsigned* d_flags = nullptr;        // [2][align_blocks] epoch flags of the persistent kernel
   int* d_m = nullptr;
   double* h_sums = nullptr; double* d_sums = nullptr;        // mapped pinned [32]
   int* h_m = nullptr;                                         // pinned
@@ -167,11 +169,15 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel, AL_THREADS, 0);
   h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
   if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
-  if (cudaMalloc((void**)&h->d_flags, 2 * (size_t)h->align_blocks * sizeof(unsigned)) != cudaSuccess) {
+  if (h->slots.ensure((size_t)2 * h->c.sm_count * AL_PSTRIDE) != LB_OK ||
+      cudaMemset(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_debug, 8 * sizeof(long long)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_debug, 8 * sizeof(long long)) != cudaSuccess) {
     set_error("lb_gicp_create: allocation failed");
     delete h;
     return LB_ERR_CUDA;
   }
+  memset(h->h_debug, 0, 8 * sizeof(long long));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   *out = h;
   return LB_OK;
@@ -312,6 +318,15 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
   return LB_OK;
 }
 
+// CTAs of the align kernels: one thread per source point, at least 8 and at most one CTA per SM.
+// Both execution modes use the same grid so their reductions have the same shape (identical bits).
+int grid_for(lb_gicp* h, int n_src) {
+  int g = cdiv(n_src, AL_THREADS);
+  if (g < 8) g = 8;
+  if (g > h->align_blocks) g = h->align_blocks;
+  return g;
+}
+
 // ---- host-driven backend: the Backend concept of bfgs.h implemented with kernel launches ----
 struct HostBackend {
   lb_gicp* h;
@@ -343,7 +358,7 @@ struct HostBackend {
     for (int i = 0; i < 6; i++) xv.v[i] = x[i];
     {
       ScopedKernelTime kt(h, "objective");
-      objective_kernel<NV><<<h->align_blocks, AL_THREADS, 0, c.stream>>>(oa, xv, h->partials.p, h->d_barrier + 1, h->d_sums);
+      objective_kernel<NV><<<grid_for(h, ca.n_src), AL_THREADS, 0, c.stream>>>(oa, xv, h->slots.p, h->d_barrier + 1, h->d_sums);
       c.launches++;
     }
     if (cudaStreamSynchronize(c.stream) != cudaSuccess) { status = LB_ERR_CUDA; return false; }
@@ -425,14 +440,15 @@ int lb_gicp_destroy(lb_gicp* h) {
   h->stage.release(); h->keys.release(); h->cell_cnt.release();
   h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
   h->sort.scan.sums.release(); h->scan.sums.release();
-  h->src_work.release(); h->corr.release(); h->M.release(); h->partials.release();
+  h->src_work.release(); h->corr.release(); h->M.release(); h->slots.release();
   h->io.release(); h->io_idx.release(); h->io_d2.release();
   if (h->d_acc) cudaFree(h->d_acc);
   if (h->h_acc) cudaFreeHost(h->h_acc);
   if (h->d_u32) cudaFree(h->d_u32);
   if (h->h_u32) cudaFreeHost(h->h_u32);
   if (h->d_barrier) cudaFree(h->d_barrier);
-  if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_debug) cudaFree(h->d_debug);
+  if (h->h_debug) cudaFreeHost(h->h_debug);
   if (h->d_m) cudaFree(h->d_m);
   if (h->h_sums) cudaFreeHost(h->h_sums);
   if (h->h_m) cudaFreeHost(h->h_m);
@@ -517,7 +533,6 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
 
   const uint32_t N = (uint32_t)h->src.n;
   LB_TRY(h->src_work.ensure(N)); LB_TRY(h->corr.ensure(N)); LB_TRY(h->M.ensure(6 * (size_t)N));
-  LB_TRY(h->partials.ensure((size_t)2 * h->align_blocks * AL_PSTRIDE));
   Mat34 G; mat16_to_34(guess, G);
   prep_source_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.pts.p, N, G, h->src_work.p);   // gicp.hpp:440
   c.launches++;
@@ -538,15 +553,17 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
   } else {
     AlignArgs aa;
-    aa.c = ca; aa.partials = h->partials.p; aa.flags = h->d_flags; aa.P = OP; aa.result = h->d_result;
+    aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
+    aa.epoch_base = h->epoch_base; h->epoch_base += 1ull << 20;      // > collectives per align
+    aa.debug = h->timing ? h->d_debug : nullptr;
     for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
-    LB_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * (size_t)h->align_blocks * sizeof(unsigned), c.stream));
     void* args[] = {&aa};
     {
       ScopedKernelTime kt(h, "align_persistent");
-      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(h->align_blocks), dim3(AL_THREADS), args, 0, c.stream));
+      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid_for(h, ca.n_src)), dim3(AL_THREADS), args, 0, c.stream));
       c.launches++;
     }
+    if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, 8 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
     LB_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(OuterResult), cudaMemcpyDeviceToHost, c.stream));
     LB_CUDA(cudaStreamSynchronize(c.stream));
     R = *h->h_result;
@@ -682,6 +699,10 @@ int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) { if (!h || !n) return LB_ERR_
 int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches) {
   if (!h || !name || !ms_avg) return LB_ERR_INVALID_ARG;
   *ms_avg = 0.f; if (launches) *launches = 0;
+  if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '7') {   // cycle counters of the last persistent align
+    *ms_avg = (float)h->h_debug[name[5] - '0'];
+    return LB_OK;
+  }
   for (auto& t : h->timers) {
     if (t.name == name) {
       if (t.launches) *ms_avg = (float)(t.total_ms / (double)t.launches);

@@ -280,10 +280,11 @@ nn_query_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t 
 
 // ------------------------------------------------------------------ block / grid reductions
 // Fixed-shape, bitwise run-to-run deterministic reduction of NV doubles per thread:
-// warp shuffle tree -> per-warp slots in shared memory -> warp 0 tree.  Result valid in
-// thread 0 (red[0..NV-1] in shared memory after the trailing barrier).
+// warp shuffle tree -> per-warp slots in shared memory -> lane e of warp 0 adds the THREADS/32 slots of
+// value e in warp order.  After the call lane e (< NV) of warp 0 holds total e in its return value; every
+// other thread gets 0.  (NV <= 32.)
 template <int NV, int THREADS>
-__device__ __forceinline__ void block_reduce(double* v, double* red /*[THREADS/32][NV]*/) {
+__device__ __forceinline__ double block_reduce(double* v, double* red /*[THREADS/32][NV]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int e = 0; e < NV; e++) {
@@ -293,27 +294,30 @@ __device__ __forceinline__ void block_reduce(double* v, double* red /*[THREADS/3
     if (lane == 0) red[warp * NV + e] = x;
   }
   __syncthreads();
-  if (warp == 0) {
+  double tot = 0.0;
+  if (warp == 0 && lane < NV) {
     constexpr int NW = THREADS / 32;
 #pragma unroll
-    for (int e = 0; e < NV; e++) {
-      double x = (lane < NW) ? red[lane * NV + e] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      if (lane == 0) v[e] = x;
-    }
+    for (int w = 0; w < NW; w++) tot += red[w * NV + lane];
   }
   __syncthreads();
+  return tot;
 }
 
-// Sum NV values over `nb` CTA slots of the partials buffer in a fixed order.  Called by one full warp
-// per value group; result returned in lane 0.
-__device__ __forceinline__ double reduce_slots(const double* __restrict__ partials, int nb, int e, int lane) {
-  double x = 0.0;
-  for (int b = lane; b < nb; b += 32) x += __ldcg(&partials[(size_t)b * AL_PSTRIDE + e]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-  return x;
+// One (value, epoch) word of a CTA slot: written and read as a single aligned 16-byte L2 transaction
+// (st/ld.global.cg.v2.u64), the CUB decoupled-look-back idiom -- no fences, no L1 invalidation.
+struct __align__(16) SlotWord { double v; unsigned long long epoch; };
+
+__device__ __forceinline__ void slot_store(SlotWord* p, double v, unsigned long long epoch) {
+  asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+}
+__device__ __forceinline__ double slot_wait(const SlotWord* p, unsigned long long epoch) {
+  unsigned long long v, e;
+  for (;;) {
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(p) : "memory");
+    if (e == epoch) break;
+  }
+  return __longlong_as_double((long long)v);
 }
 
 // ------------------------------------------------------------------ K4 correspondences
@@ -389,11 +393,12 @@ __device__ __forceinline__ void objective_accumulate(const ObjArgs& a, const flo
 
 struct Vec6d { double v[6]; };
 
-// Host-driven objective: every CTA reduces its slice into partials[cta]; the last CTA to
-// finish sums the slots in fixed order and writes the NV totals to `out` (mapped pinned memory).
+// Host-driven objective: every CTA reduces its slice into its slot; the last CTA to finish sums the slots
+// in fixed order and writes the NV totals to `out` (mapped pinned memory).  Same block_reduce and the same
+// slot summation order as the persistent kernel, so both execution modes produce identical bits.
 template <int NV>
 __global__ void __launch_bounds__(AL_THREADS)
-objective_kernel(ObjArgs a, Vec6d x, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out) {
+objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __restrict__ ticket, double* __restrict__ out) {
   __shared__ double red[(AL_THREADS / 32) * NV];
   __shared__ float sT[12];
   __shared__ double sD[27];
@@ -410,11 +415,11 @@ objective_kernel(ObjArgs a, Vec6d x, double* __restrict__ partials, unsigned* __
 #pragma unroll
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
   objective_accumulate<NV>(a, T, sD, sD + 9, sD + 18, blockIdx.x * AL_THREADS + threadIdx.x, gridDim.x * AL_THREADS, acc);
-  block_reduce<NV, AL_THREADS>(acc, red);
+  double tot = block_reduce<NV, AL_THREADS>(acc, red);
+  if (threadIdx.x < NV) slot_store(&slots[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, 1ull);
+  __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int e = 0; e < NV; e++) __stcg(&partials[(size_t)blockIdx.x * AL_PSTRIDE + e], acc[e]);
-    __threadfence();
     unsigned t = atomicAdd(ticket, 1u);
     last = (t == gridDim.x - 1);
   }
@@ -423,9 +428,16 @@ objective_kernel(ObjArgs a, Vec6d x, double* __restrict__ partials, unsigned* __
     __threadfence();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = warp; e < NV; e += AL_THREADS / 32) {
-      double x = reduce_slots(partials, gridDim.x, e, lane);
-      if (lane == 0) out[e] = x;
+      double xs = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) xs += slot_wait(&slots[(size_t)b * AL_PSTRIDE + e], 1ull);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) xs += __shfl_down_sync(0xffffffffu, xs, o);
+      if (lane == 0) out[e] = xs;
     }
+    __syncthreads();
+    // reset the slots' epochs and the ticket for the next launch
+    for (int i = threadIdx.x; i < (int)gridDim.x * NV; i += AL_THREADS)
+      slot_store(&slots[(size_t)(i / NV) * AL_PSTRIDE + (i % NV)], 0.0, 0ull);
     if (threadIdx.x == 0) *ticket = 0;
   }
 }
@@ -436,13 +448,15 @@ objective_kernel(ObjArgs a, Vec6d x, double* __restrict__ partials, unsigned* __
 // bfgs.h convergently (state in registers / a few hundred bytes of L1-resident local memory); the other
 // warps are WORKERS parked on the CTA barrier until the leader posts a command (correspond / objective /
 // Gauss-Newton terms / exit) in shared memory.  Every data-parallel command ends in a grid-wide
-// deterministic all-reduce: CTA partials + an epoch flag are published to a slot (st.release), every CTA
-// polls the flags of all slots (ld.acquire) and sums the slots in a fixed order -- no atomics, and every
-// CTA obtains bitwise identical totals, so all leaders take identical decisions.
+// deterministic all-reduce: each CTA publishes its partials as (value, epoch) words in its slot with
+// single 16-byte L2 stores; every CTA polls the words of all slots and sums them in a fixed order -- no
+// atomics, no fences (so L1 is never invalidated), and every CTA obtains bitwise identical totals, so all
+// leaders take identical decisions.  Slots are double-buffered; epochs are unique across launches.
 struct AlignArgs {
   CorrArgs c;
-  double* partials;       // [2][gridDim.x][AL_PSTRIDE] doubles
-  unsigned* flags;        // [2][gridDim.x] epoch flags, zeroed before launch
+  SlotWord* slots;        // [2][gridDim.x][AL_PSTRIDE] (value, epoch) words
+  unsigned long long epoch_base;   // unique per launch, so stale epochs of earlier launches never match
+  long long* debug;       // nullable: [8] cycle counters written by CTA 0 (profiling aid)
   OuterParams P;
   float guess[16];
   OuterResult* result;
@@ -453,6 +467,7 @@ enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4 };
 struct AlignShared {
   int op;
   int m;
+  long long t_reduce, t_wait, n_coll;   // CTA 0 / thread 0 cycle counters
   float T[12];
   double R[9];
   double D[27];
@@ -461,45 +476,38 @@ struct AlignShared {
 };
 
 struct Collective {   // per-thread copy; advances in lockstep in every thread of the grid
-  unsigned epoch;
+  unsigned long long epoch;
   int flip;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // grid-wide deterministic sum of NV doubles per thread; totals land in sh.bc[0..NV-1] (all threads, after return)
 template <int NV>
 __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared& sh, Collective& co, double* acc) {
-  block_reduce<NV, AL_THREADS>(acc, sh.red);
+  const bool prof = (blockIdx.x == 0 && threadIdx.x == 0);
+  long long t0 = prof ? clock64() : 0;
+  double tot = block_reduce<NV, AL_THREADS>(acc, sh.red);
   co.epoch++;
   const int ncta = gridDim.x;
-  double* buf = a.partials + (size_t)co.flip * ncta * AL_PSTRIDE;
-  unsigned* flg = a.flags + (size_t)co.flip * ncta;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int e = 0; e < NV; e++) __stcg(&buf[(size_t)blockIdx.x * AL_PSTRIDE + e], acc[e]);
-    st_release_u32(&flg[blockIdx.x], co.epoch);
-  }
+  SlotWord* buf = a.slots + (size_t)co.flip * ncta * AL_PSTRIDE;
+  if (threadIdx.x < NV) slot_store(&buf[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, co.epoch);
+  long long t1 = prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = warp; e < NV; e += AL_THREADS / 32) {
     double x = 0.0;
-    for (int b = lane; b < ncta; b += 32) {
-      while (ld_acquire_u32(&flg[b]) < co.epoch) {}
-      x += __ldcg(&buf[(size_t)b * AL_PSTRIDE + e]);
-    }
+    for (int b = lane; b < ncta; b += 32) x += slot_wait(&buf[(size_t)b * AL_PSTRIDE + e], co.epoch);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
     if (lane == 0) sh.bc[e] = x;
   }
   co.flip ^= 1;
   __syncthreads();
+  if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; }
 }
 
 __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co) {
@@ -613,14 +621,21 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
 align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   __shared__ AlignShared sh;
   Collective co;
-  co.epoch = 0; co.flip = 0;
+  co.epoch = a.epoch_base; co.flip = 0;
+  const long long t_begin = clock64();
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; }
   if (threadIdx.x < 32) {
     DeviceBackend be(a, sh, co);
     OuterResult r;
     gicp_outer_loop(be, a.P, a.guess, r);
     if (threadIdx.x == 0) sh.op = OP_EXIT;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.result = r;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *a.result = r;
+      if (a.debug) {
+        a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_reduce; a.debug[2] = sh.t_wait; a.debug[3] = sh.n_coll;
+      }
+    }
   } else {
     for (;;) {
       __syncthreads();
@@ -649,8 +664,8 @@ fitness_kernel(GridView g, const f4* __restrict__ raw, uint32_t n, Mat34 T, doub
     int s = nn1(g, x, y, z, 3.0e38f, bo, bd);
     if (s >= 0 && (double)bd <= max_range) { acc[0] = (double)bd; acc[1] = 1.0; }
   }
-  block_reduce<2, 128>(acc, red);
-  if (threadIdx.x == 0) { partials[2 * (size_t)blockIdx.x] = acc[0]; partials[2 * (size_t)blockIdx.x + 1] = acc[1]; }
+  double tot = block_reduce<2, 128>(acc, red);
+  if (threadIdx.x < 2) partials[2 * (size_t)blockIdx.x + threadIdx.x] = tot;
 }
 
 }  // namespace lb
