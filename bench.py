@@ -119,10 +119,25 @@ def seq(i):
     return r if r < N_STREAM else p - r
 
 
-def make_stream(rank):
-    seed = 2 + 8 * rank
-    scene, poses, blobs = G.stream(seed, N_STREAM)
+def stream_seed(rank):
+    """scan stream s -> GPU s: independent streams, one per rank; rank 0 is the N=1 workload"""
+    return 2 + 8 * rank
+
+
+def make_stream(rank, n_scans=N_STREAM, beams=64, az=2048):
+    scene, poses, blobs = G.stream(stream_seed(rank), n_scans, beams, az)
     return poses, blobs
+
+
+def aggregate(dist, device, times_ms, steps, world):
+    """max over ranks of the per-rank device times; whole-job throughput = all ranks' scans / that time"""
+    import torch
+    t = torch.tensor(list(times_ms), dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tmax = [float(x) for x in t]
+    total = steps * world
+    return tmax, [total / (x / 1e3) for x in tmax]
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -357,13 +372,7 @@ def main():
     e2e_ms, e2e_wall = timed_run(step_host, args.steps, args.warmup)
 
     # max over ranks (device time), whole-job aggregate
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    total_scans = args.steps * world
-    value = total_scans / (dev_ms_max / 1e3)
-    e2e_value = total_scans / (e2e_ms_max / 1e3)
+    (dev_ms_max, e2e_ms_max), (value, e2e_value) = aggregate(dist, "cuda", [dev_ms, e2e_ms], args.steps, world)
 
     if rank != 0:
         if dist is not None:

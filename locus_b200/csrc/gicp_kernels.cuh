@@ -304,19 +304,24 @@ __device__ __forceinline__ double block_reduce(double* v, double* red /*[THREADS
   return tot;
 }
 
-// One (value, epoch) word of a CTA slot: written and read as a single aligned 16-byte L2 transaction
-// (st/ld.global.cg.v2.u64), the CUB decoupled-look-back idiom -- no fences, no L1 invalidation.
+// One (value, epoch) word of a CTA slot.  The writer publishes both halves with ONE aligned 16-byte L2
+// store (STG.E.128.STRONG.GPU).  The reader polls the epoch half with a strong (L1-bypassing) 8-byte load
+// and only then loads the value half, through an address that depends on the observed epoch, so the value
+// read can never be ordered before the epoch read.  No fences anywhere: a gpu-scope fence would invalidate
+// L1 (CCTL.IVALL), where the leader warp keeps its BFGS state.
 struct __align__(16) SlotWord { double v; unsigned long long epoch; };
 
 __device__ __forceinline__ void slot_store(SlotWord* p, double v, unsigned long long epoch) {
-  asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
 }
 __device__ __forceinline__ double slot_wait(const SlotWord* p, unsigned long long epoch) {
-  unsigned long long v, e;
-  for (;;) {
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(p) : "memory");
-    if (e == epoch) break;
-  }
+  const unsigned long long* pe = &p->epoch;
+  unsigned long long e, v;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(pe) : "memory");
+  } while (e != epoch);
+  const char* pv = reinterpret_cast<const char*>(p) + (e ^ epoch);   // == p; carries the dependency
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(pv) : "memory");
   return __longlong_as_double((long long)v);
 }
 
