@@ -402,7 +402,7 @@ def main():
                          "objective_evals_mean": float(evals.mean()) if len(evals) else None,
                          "correspondences_mean": float(ncorr.mean()) if len(ncorr) else None,
                          "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
-                         "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms,
+                         "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms, "voxel_last_call_ms": vg.lastCallMs(),
                          "align_last_launch_cycles": {"total": dbg[0], "block_reduce_publish": dbg[1],
                                                       "slot_wait_sum": dbg[2], "collectives": dbg[3]},
                          "wall_s_timed_region": wall}}

@@ -159,6 +159,7 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
             cudaMallocHost((void**)&h->h_result, sizeof(OuterResult)) == cudaSuccess;
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned)) == cudaSuccess;
+  if (ok) { bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_acc); ok = cudaStreamSynchronize(h->c.stream) == cudaSuccess; }
   if (!ok) {
     set_error("lb_gicp_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -205,13 +206,12 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
   LB_TRY(cl.raw.ensure(n)); LB_TRY(cl.pts.ensure(n));
   if (normal_off >= 0) LB_TRY(cl.nrm.ensure(n));
   gather_cloud_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_src, N, (uint32_t)stride, (uint32_t)xyz_off, (int)normal_off,
-                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr);
-  bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
-  bbox_kernel<<<min(cdiv(N, 256), c.sm_count * 8), 256, 0, c.stream>>>((const uint8_t*)cl.raw.p, N, 16, 0, -1, 0.f, 0.f, 0, h->d_acc);
-  c.launches += 3;
+                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr, h->d_acc);
+  c.launches += 1;
   LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
   if (h->h_acc->count != N) {
+    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);   // leave the accumulator clean for the next build
     set_error("%s: cloud holds %u non-finite points; GICP inputs must be dense (PCL kd-tree precondition)", what, N - h->h_acc->count);
     return LB_ERR_INVALID_ARG;
   }
@@ -261,7 +261,7 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
       LB_TRY(h->cell_cnt.ensure(nc + 1));
       LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (nc + 1) * sizeof(uint32_t), c.stream));
       LB_CUDA(cudaMemsetAsync(h->d_u32, 0, sizeof(uint32_t), c.stream));
-      grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p);
+      grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p, nullptr);
       grid_occupancy_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->keys.p, N, h->cell_cnt.p, h->d_u32);
       c.launches += 2;
       LB_CUDA(cudaMemcpyAsync(h->h_u32, h->d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
@@ -283,7 +283,7 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
   LB_TRY(h->cell_cnt.ensure(cl.ncells + 1));
   LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
   LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
-  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p);
+  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p, h->d_acc);
   c.launches++;
   uint32_t *sk = nullptr, *sv = nullptr;
   LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));
@@ -321,7 +321,7 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
 // CTAs of the align kernels: one thread per source point, at least 8 and at most one CTA per SM.
 // Both execution modes use the same grid so their reductions have the same shape (identical bits).
 int grid_for(lb_gicp* h, int n_src) {
-  int g = cdiv(n_src, AL_THREADS);
+  int g = cdiv(n_src, AL_PPC);
   if (g < 8) g = 8;
   if (g > h->align_blocks) g = h->align_blocks;
   return g;
@@ -554,6 +554,11 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   } else {
     AlignArgs aa;
     aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
+    // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
+    if ((h->epoch_base >> 32) != ((h->epoch_base + (1ull << 20)) >> 32) || (h->epoch_base & 0xffffffffull) == 0) {
+      LB_CUDA(cudaMemsetAsync(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord), c.stream));
+      h->epoch_base = ((h->epoch_base >> 32) + 1) << 32 | (1ull << 20);
+    }
     aa.epoch_base = h->epoch_base; h->epoch_base += 1ull << 20;      // > collectives per align
     aa.debug = h->timing ? h->d_debug : nullptr;
     for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];

@@ -18,23 +18,33 @@
 
 namespace lb {
 
-constexpr int AL_THREADS = 512;      // threads per CTA of the align kernels
+constexpr int AL_THREADS = 256;      // threads per CTA of the align kernels (255 registers for the leader warp)
+constexpr int AL_ACC_WARPS = 4;      // warps that accumulate objective terms (shuffle throughput bounds the reduce)
+constexpr int AL_ACC = AL_ACC_WARPS * 32;
+constexpr int AL_PPC = 512;          // source points per CTA (4 per accumulating lane)
 constexpr int AL_MAXV = 28;          // widest reduction (Gauss-Newton)
-constexpr int AL_PSTRIDE = 32;       // doubles per CTA slot in the partials buffer
+constexpr int AL_PSTRIDE = 32;       // words per CTA slot
+constexpr int AL_MAXB = 8;           // slots per polling lane: supports up to 256 CTAs
 
 // ------------------------------------------------------------------ cloud upload
 __global__ void __launch_bounds__(256)
 gather_cloud_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, int normal_off,
-                    f4* __restrict__ raw, f4* __restrict__ nrm) {
+                    f4* __restrict__ raw, f4* __restrict__ nrm, BBoxAcc* __restrict__ acc) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t* p = base + (size_t)i * stride;
-  const float* q = reinterpret_cast<const float*>(p + xyz_off);
-  raw[i] = f4{q[0], q[1], q[2], 1.0f};
-  if (normal_off >= 0) {
-    const float* m = reinterpret_cast<const float*>(p + normal_off);
-    nrm[i] = f4{m[0], m[1], m[2], 0.0f};
+  bool ok = false;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (i < n) {
+    const uint8_t* p = base + (size_t)i * stride;
+    const float* q = reinterpret_cast<const float*>(p + xyz_off);
+    x = q[0]; y = q[1]; z = q[2];
+    raw[i] = f4{x, y, z, 1.0f};
+    if (normal_off >= 0) {
+      const float* m = reinterpret_cast<const float*>(p + normal_off);
+      nrm[i] = f4{m[0], m[1], m[2], 0.0f};
+    }
+    ok = isfinite(x) && isfinite(y) && isfinite(z);
   }
+  bbox_warp_accumulate(ok, x, y, z, acc);   // finite-point bounding box + count (accumulator was reset by the previous build)
 }
 
 // ------------------------------------------------------------------ K2 index build
@@ -52,8 +62,9 @@ __device__ __forceinline__ uint32_t cell_of(const GridGeom& g, float x, float y,
 }
 
 __global__ void __launch_bounds__(256)
-grid_keys_kernel(const f4* __restrict__ raw, uint32_t n, GridGeom g, uint32_t* __restrict__ keys) {
+grid_keys_kernel(const f4* __restrict__ raw, uint32_t n, GridGeom g, uint32_t* __restrict__ keys, BBoxAcc* acc_to_reset) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && acc_to_reset) bbox_reset(acc_to_reset);   // the host has consumed it: ready for the next build
   if (i >= n) return;
   f4 p = raw[i];
   keys[i] = cell_of(g, p.x, p.y, p.z);
@@ -279,50 +290,78 @@ nn_query_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t 
 }
 
 // ------------------------------------------------------------------ block / grid reductions
-// Fixed-shape, bitwise run-to-run deterministic reduction of NV doubles per thread:
-// warp shuffle tree -> per-warp slots in shared memory -> lane e of warp 0 adds the THREADS/32 slots of
-// value e in warp order.  After the call lane e (< NV) of warp 0 holds total e in its return value; every
-// other thread gets 0.  (NV <= 32.)
-template <int NV, int THREADS>
-__device__ __forceinline__ double block_reduce(double* v, double* red /*[THREADS/32][NV]*/) {
+// Fixed-shape, bitwise run-to-run deterministic reduction of NV doubles held by the threads of the first
+// NWARPS warps: warp shuffle tree -> per-warp slots in shared memory -> lane e of warp 0 adds the NWARPS
+// slots of value e in warp order.  Lane e (< NV) of warp 0 returns total e; every other thread gets 0.
+// (Only NWARPS warps shuffle: SHFL issues at one warp-instruction per cycle per SM, so the cost is
+// NWARPS * NV * 10 cycles.)  All threads of the CTA must call it (two CTA barriers inside).
+template <int NV, int NWARPS>
+__device__ __forceinline__ double block_reduce(double* v, double* red /*[NWARPS][NV]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < NWARPS) {
 #pragma unroll
-  for (int e = 0; e < NV; e++) {
-    double x = v[e];
+    for (int e = 0; e < NV; e++) {
+      double x = v[e];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) red[warp * NV + e] = x;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) red[warp * NV + e] = x;
+    }
   }
   __syncthreads();
   double tot = 0.0;
   if (warp == 0 && lane < NV) {
-    constexpr int NW = THREADS / 32;
 #pragma unroll
-    for (int w = 0; w < NW; w++) tot += red[w * NV + lane];
+    for (int w = 0; w < NWARPS; w++) tot += red[w * NV + lane];
   }
   __syncthreads();
   return tot;
 }
 
-// One (value, epoch) word of a CTA slot.  The writer publishes both halves with ONE aligned 16-byte L2
-// store (STG.E.128.STRONG.GPU).  The reader polls the epoch half with a strong (L1-bypassing) 8-byte load
-// and only then loads the value half, through an address that depends on the observed epoch, so the value
-// read can never be ordered before the epoch read.  No fences anywhere: a gpu-scope fence would invalidate
-// L1 (CCTL.IVALL), where the leader warp keeps its BFGS state.
-struct __align__(16) SlotWord { double v; unsigned long long epoch; };
+// One published value of a CTA slot: the double is split in two 32-bit halves, each packed with the low 32
+// bits of the collective's epoch into an 8-byte word (8-byte accesses are single L2 transactions).  A reader
+// loads both words at once and retries until both tags match: ONE round trip, no fences (a gpu-scope fence
+// would invalidate L1, where the leader warp keeps its BFGS state), no reliance on 16-byte atomicity.
+struct __align__(16) SlotWord { unsigned long long lo, hi; };
 
 __device__ __forceinline__ void slot_store(SlotWord* p, double v, unsigned long long epoch) {
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+  unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  unsigned long long tag = (epoch & 0xffffffffull) << 32;
+  unsigned long long lo = tag | (bits & 0xffffffffull), hi = tag | (bits >> 32);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ double slot_wait(const SlotWord* p, unsigned long long epoch) {
-  const unsigned long long* pe = &p->epoch;
-  unsigned long long e, v;
-  do {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(pe) : "memory");
-  } while (e != epoch);
-  const char* pv = reinterpret_cast<const char*>(p) + (e ^ epoch);   // == p; carries the dependency
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(pv) : "memory");
-  return __longlong_as_double((long long)v);
+__device__ __forceinline__ bool slot_try(const SlotWord* p, unsigned long long epoch, double& v) {
+  unsigned long long lo, hi;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  unsigned long long tag = epoch & 0xffffffffull;
+  if ((lo >> 32) != tag || (hi >> 32) != tag) return false;
+  v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  return true;
+}
+// Sum value e over the slots of all CTAs in a fixed order (lane b, b+32, ... then shuffle tree); all the
+// lane's loads are issued together and only the missing ones are re-polled.  Result in lane 0.
+__device__ __forceinline__ double slots_sum(const SlotWord* buf, int ncta, int e, unsigned long long epoch) {
+  const int lane = threadIdx.x & 31;
+  double val[AL_MAXB];
+  unsigned pending = 0;
+#pragma unroll
+  for (int k = 0; k < AL_MAXB; k++) {
+    val[k] = 0.0;
+    if (lane + 32 * k < ncta) pending |= 1u << k;
+  }
+  while (pending) {
+#pragma unroll
+    for (int k = 0; k < AL_MAXB; k++)
+      if (pending & (1u << k)) {
+        double v;
+        if (slot_try(&buf[(size_t)(lane + 32 * k) * AL_PSTRIDE + e], epoch, v)) { val[k] = v; pending &= ~(1u << k); }
+      }
+  }
+  double x = 0.0;
+#pragma unroll
+  for (int k = 0; k < AL_MAXB; k++) x += val[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  return x;
 }
 
 // ------------------------------------------------------------------ K4 correspondences
@@ -380,10 +419,17 @@ struct ObjArgs {
 };
 
 // accumulate the NV sums of this thread's points.  NV = 13: BFGS objective; 28: Gauss-Newton.
+// CTA c owns the contiguous chunk [c*chunk, (c+1)*chunk) of the (cell-sorted) source
+__device__ __forceinline__ void cta_chunk(int n, int& begin, int& end) {
+  int chunk = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  begin = min(n, (int)blockIdx.x * chunk);
+  end = min(n, begin + chunk);
+}
+
 template <int NV>
 __device__ __forceinline__ void objective_accumulate(const ObjArgs& a, const float* T, const double* dP, const double* dT,
-                                                     const double* dS, int first, int step, double* acc) {
-  for (int s = first; s < a.n_src; s += step) {
+                                                     const double* dS, int first, int end, int step, double* acc) {
+  for (int s = first; s < end; s += step) {
     f4 c = a.corr[s];
     if (float_to_bits(c.w) < 0) continue;
     f4 p = a.src[s];
@@ -398,13 +444,13 @@ __device__ __forceinline__ void objective_accumulate(const ObjArgs& a, const flo
 
 struct Vec6d { double v[6]; };
 
-// Host-driven objective: every CTA reduces its slice into its slot; the last CTA to finish sums the slots
-// in fixed order and writes the NV totals to `out` (mapped pinned memory).  Same block_reduce and the same
+// Host-driven objective: every CTA reduces its chunk into its slot; the last CTA to finish sums the slots
+// in fixed order and writes the NV totals to `out` (mapped pinned memory).  Same chunking, block_reduce and
 // slot summation order as the persistent kernel, so both execution modes produce identical bits.
 template <int NV>
 __global__ void __launch_bounds__(AL_THREADS)
 objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __restrict__ ticket, double* __restrict__ out) {
-  __shared__ double red[(AL_THREADS / 32) * NV];
+  __shared__ double red[AL_ACC_WARPS * NV];
   __shared__ float sT[12];
   __shared__ double sD[27];
   __shared__ bool last;
@@ -419,8 +465,10 @@ objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __r
   double acc[NV];
 #pragma unroll
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
-  objective_accumulate<NV>(a, T, sD, sD + 9, sD + 18, blockIdx.x * AL_THREADS + threadIdx.x, gridDim.x * AL_THREADS, acc);
-  double tot = block_reduce<NV, AL_THREADS>(acc, red);
+  int begin, end;
+  cta_chunk(a.n_src, begin, end);
+  if (threadIdx.x < AL_ACC) objective_accumulate<NV>(a, T, sD, sD + 9, sD + 18, begin + threadIdx.x, end, AL_ACC, acc);
+  double tot = block_reduce<NV, AL_ACC_WARPS>(acc, red);
   if (threadIdx.x < NV) slot_store(&slots[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, 1ull);
   __threadfence();
   __syncthreads();
@@ -433,14 +481,11 @@ objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __r
     __threadfence();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = warp; e < NV; e += AL_THREADS / 32) {
-      double xs = 0.0;
-      for (int b = lane; b < (int)gridDim.x; b += 32) xs += slot_wait(&slots[(size_t)b * AL_PSTRIDE + e], 1ull);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) xs += __shfl_down_sync(0xffffffffu, xs, o);
+      double xs = slots_sum(slots, gridDim.x, e, 1ull);
       if (lane == 0) out[e] = xs;
     }
     __syncthreads();
-    // reset the slots' epochs and the ticket for the next launch
+    // reset the tags and the ticket for the next launch
     for (int i = threadIdx.x; i < (int)gridDim.x * NV; i += AL_THREADS)
       slot_store(&slots[(size_t)(i / NV) * AL_PSTRIDE + (i % NV)], 0.0, 0ull);
     if (threadIdx.x == 0) *ticket = 0;
@@ -476,7 +521,7 @@ struct AlignShared {
   float T[12];
   double R[9];
   double D[27];
-  double red[(AL_THREADS / 32) * AL_MAXV];
+  double red[AL_ACC_WARPS * AL_MAXV];
   double bc[AL_MAXV + 4];
 };
 
@@ -491,12 +536,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// grid-wide deterministic sum of NV doubles per thread; totals land in sh.bc[0..NV-1] (all threads, after return)
+// grid-wide deterministic sum of the NV doubles held by the accumulating lanes; totals land in
+// sh.bc[0..NV-1] (visible to all threads after return)
 template <int NV>
 __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared& sh, Collective& co, double* acc) {
   const bool prof = (blockIdx.x == 0 && threadIdx.x == 0);
   long long t0 = prof ? clock64() : 0;
-  double tot = block_reduce<NV, AL_THREADS>(acc, sh.red);
+  double tot = block_reduce<NV, AL_ACC_WARPS>(acc, sh.red);
   co.epoch++;
   const int ncta = gridDim.x;
   SlotWord* buf = a.slots + (size_t)co.flip * ncta * AL_PSTRIDE;
@@ -504,10 +550,7 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   long long t1 = prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = warp; e < NV; e += AL_THREADS / 32) {
-    double x = 0.0;
-    for (int b = lane; b < ncta; b += 32) x += slot_wait(&buf[(size_t)b * AL_PSTRIDE + e], co.epoch);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    double x = slots_sum(buf, ncta, e, co.epoch);
     if (lane == 0) sh.bc[e] = x;
   }
   co.flip ^= 1;
@@ -521,11 +564,22 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
 #pragma unroll
   for (int i = 0; i < 9; i++) R[i] = sh.R[i];
+  int begin, end;
+  cta_chunk(a.c.n_src, begin, end);
+  int hits = 0;
+  for (int s = begin + threadIdx.x; s < end; s += AL_THREADS) hits += correspond_point(a.c, T, R, s);
+  // fold the 8 warps' counts onto the accumulating lanes: the correspondence arrays written above are only
+  // ever re-read by this CTA (do_objective uses the same chunk), after the CTA barriers below.
+  __shared__ int s_hits[AL_THREADS];
+  s_hits[threadIdx.x] = hits;
+  __syncthreads();
   double cnt[1] = {0.0};
-  for (int s = blockIdx.x * AL_THREADS + threadIdx.x; s < a.c.n_src; s += gridDim.x * AL_THREADS)
-    cnt[0] += (double)correspond_point(a.c, T, R, s);
-  // the correspondence arrays written above are read by other CTAs?  No: every CTA re-reads only the
-  // points of its own grid-stride slice in do_objective, written by the same threads.
+  if (threadIdx.x < AL_ACC) {
+    int h = 0;
+#pragma unroll
+    for (int k = 0; k < AL_THREADS / AL_ACC; k++) h += s_hits[threadIdx.x + k * AL_ACC];
+    cnt[0] = (double)h;
+  }
   grid_all_reduce<1>(a, sh, co, cnt);
 }
 
@@ -538,8 +592,9 @@ __device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh
 #pragma unroll
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
   ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
-  objective_accumulate<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, blockIdx.x * AL_THREADS + threadIdx.x,
-                           gridDim.x * AL_THREADS, acc);
+  int begin, end;
+  cta_chunk(a.c.n_src, begin, end);
+  if (threadIdx.x < AL_ACC) objective_accumulate<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, begin + threadIdx.x, end, AL_ACC, acc);
   grid_all_reduce<NV>(a, sh, co, acc);
 }
 
@@ -669,7 +724,7 @@ fitness_kernel(GridView g, const f4* __restrict__ raw, uint32_t n, Mat34 T, doub
     int s = nn1(g, x, y, z, 3.0e38f, bo, bd);
     if (s >= 0 && (double)bd <= max_range) { acc[0] = (double)bd; acc[1] = 1.0; }
   }
-  double tot = block_reduce<2, 128>(acc, red);
+  double tot = block_reduce<2, 4>(acc, red);
   if (threadIdx.x < 2) partials[2 * (size_t)blockIdx.x + threadIdx.x] = tot;
 }
 

@@ -160,9 +160,33 @@ scan_down_kernel(const uint32_t* in, uint32_t* out, size_t n, const uint32_t* __
   for (int j = 0; j < SC_I; j++) { if (base + j < n) out[base + j] = ex; ex += v[j]; }
 }
 
+// whole scan in one CTA (n up to a few 10^4: launch latency, not bandwidth, is what matters there)
+__global__ void __launch_bounds__(1024) scan_single_kernel(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total) {
+  __shared__ uint32_t sm[1024 / 32 + 1];
+  uint32_t carry = 0;
+  for (size_t start = 0; start < n; start += 1024 * 8) {
+    size_t base = start + (size_t)threadIdx.x * 8;
+    uint32_t v[8]; uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = (base + j < n) ? in[base + j] : 0; s += v[j]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<1024>(s, &tot, sm) + carry;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { if (base + j < n) out[base + j] = ex; ex += v[j]; }
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
 int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev) {
   if (n == 0) {
     if (total_dev) LB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), c.stream));
+    return LB_OK;
+  }
+  if (n <= 65536) {
+    scan_single_kernel<<<1, 1024, 0, c.stream>>>(in, out, n, total_dev);
+    c.launches += 1;
+    LB_CUDA(cudaGetLastError());
     return LB_OK;
   }
   size_t nb = (n + SC_TILE - 1) / SC_TILE;

@@ -84,6 +84,32 @@ struct BBoxAcc {          // device-resident accumulator, 8 words
 
 __global__ void bbox_init_kernel(BBoxAcc* acc);
 
+// accumulate one point into warp-level then global bounding box (call with all 32 lanes; valid = lane has a point)
+__device__ __forceinline__ void bbox_warp_accumulate(bool valid, float x, float y, float z, BBoxAcc* acc) {
+  uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0, mx1 = 0, mx2 = 0, cnt = 0;
+  if (valid) { mn0 = mx0 = f2ord(x); mn1 = mx1 = f2ord(y); mn2 = mx2 = f2ord(z); cnt = 1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o));
+    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+    mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    atomicMin(&acc->mn[0], mn0); atomicMin(&acc->mn[1], mn1); atomicMin(&acc->mn[2], mn2);
+    atomicMax(&acc->mx[0], mx0); atomicMax(&acc->mx[1], mx1); atomicMax(&acc->mx[2], mx2);
+    atomicAdd(&acc->count, cnt);
+  }
+}
+__device__ __forceinline__ void bbox_reset(BBoxAcc* acc) {
+  acc->mn[0] = acc->mn[1] = acc->mn[2] = 0xffffffffu;
+  acc->mx[0] = acc->mx[1] = acc->mx[2] = 0u;
+  acc->count = 0; acc->pad = 0;
+}
+
 // Finite-point bounding box of a strided cloud (x,y,z float32 at xyz_off).
 // Optional limit filter (VoxelGrid getMinMax3D): field value v at ff_off is
 // dropped if  negative ? (v < fmax && v > fmin) : (v > fmax || v < fmin), float compare.

@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(256)
 vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t x_off, uint32_t y_off,
                uint32_t z_off, int ff_off, double lim_min, double lim_max, int negative, float inv0, float inv1,
                float inv2, int min_b0, int min_b1, int min_b2, int mul1, int mul2, uint32_t sentinel,
-               uint32_t* __restrict__ keys) {
+               uint32_t* __restrict__ keys, BBoxAcc* acc_to_reset) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) bbox_reset(acc_to_reset);   // the host has consumed the bounding box: ready for the next call
   if (i >= n) return;
   const uint8_t* p = base + (size_t)i * stride;
   bool ok = true;
@@ -185,6 +186,8 @@ static int voxel_create_impl(int device, void* stream, bool ext, lb_voxel** out)
     delete h;
     return LB_ERR_CUDA;
   }
+  bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_acc);
+  cudaStreamSynchronize(h->c.stream);
   *out = h;
   return LB_OK;
 }
@@ -291,20 +294,24 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     d_in = h->d_in.p;
   }
   // ---- bounding box of the surviving points (pcl::getMinMax3D with float limits)
-  bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
   int bb_blocks = min(cdiv(n, 256), c.sm_count * 8);
   bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, ffo, (float)h->lim_min,
                                                 (float)h->lim_max, h->negative, h->d_acc);
-  c.launches += 2;
+  c.launches += 1;
   LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
-  if (h->h_acc->count == 0) { *n_out = 0; return LB_OK; }
+  if (h->h_acc->count == 0) {
+    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
+    *n_out = 0;
+    return LB_OK;
+  }
   float min_p[3], max_p[3], inv[3];
   for (int d = 0; d < 3; d++) { min_p[d] = ord2f(h->h_acc->mn[d]); max_p[d] = ord2f(h->h_acc->mx[d]); inv[d] = 1.0f / h->leaf[d]; }
   int64_t dx = (int64_t)((max_p[0] - min_p[0]) * inv[0]) + 1;
   int64_t dy = (int64_t)((max_p[1] - min_p[1]) * inv[1]) + 1;
   int64_t dz = (int64_t)((max_p[2] - min_p[2]) * inv[2]) + 1;
   if (dx * dy * dz > (int64_t)INT32_MAX) {
+    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
     set_error("lb_voxel_filter: leaf size too small for the input dataset, integer indices would overflow");
     return LB_ERR_VOXEL_OVERFLOW;
   }
@@ -315,7 +322,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     div_b[d] = max_b[d] - min_b[d] + 1;
   }
   int64_t ncells64 = (int64_t)div_b[0] * div_b[1] * div_b[2];
-  if (ncells64 > (int64_t)INT32_MAX) { set_error("lb_voxel_filter: voxel index overflow"); return LB_ERR_VOXEL_OVERFLOW; }
+  if (ncells64 > (int64_t)INT32_MAX) { bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc); set_error("lb_voxel_filter: voxel index overflow"); return LB_ERR_VOXEL_OVERFLOW; }
   uint32_t sentinel = (uint32_t)ncells64;
   int key_bits = 1;
   while (key_bits < 32 && (1ull << key_bits) <= (uint64_t)sentinel) key_bits++;
@@ -323,7 +330,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   LB_TRY(h->keys.ensure(n)); LB_TRY(h->flags.ensure(n)); LB_TRY(h->seg_start.ensure(n));
   vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, n, point_step, xo, yo, zo, ffo, h->lim_min, h->lim_max,
                                                      h->negative, inv[0], inv[1], inv[2], min_b[0], min_b[1], min_b[2],
-                                                     div_b[0], div_b[0] * div_b[1], sentinel, h->keys.p);
+                                                     div_b[0], div_b[0] * div_b[1], sentinel, h->keys.p, h->d_acc);
   c.launches++;
   uint32_t *sk = nullptr, *sv = nullptr;
   LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));
