@@ -309,8 +309,19 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
-    else knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    // quad-per-query up to ring 2, then a warp per query for the sparse tail (worklist through h->keys / d_u32[1])
+    const int ring_cap = 2;
+    LB_TRY(h->keys.ensure(cl.n));
+    LB_CUDA(cudaMemsetAsync(h->d_u32 + 1, 0, sizeof(uint32_t), c.stream));
+    int tail_blocks = c.sm_count * 4;
+    if (k <= 20) {
+      knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, ring_cap, h->keys.p, h->d_u32 + 1);
+      knn_cov_tail_kernel<20><<<tail_blocks, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, h->keys.p, h->d_u32 + 1);
+    } else {
+      knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, ring_cap, h->keys.p, h->d_u32 + 1);
+      knn_cov_tail_kernel<32><<<tail_blocks, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, h->keys.p, h->d_u32 + 1);
+    }
+    c.launches++;
   }
   c.launches++;
   LB_CUDA(cudaGetLastError());
@@ -324,6 +335,7 @@ int grid_for(lb_gicp* h, int n_src) {
   int g = cdiv(n_src, AL_PPC);
   if (g < 8) g = 8;
   if (g > h->align_blocks) g = h->align_blocks;
+  if (g > AL_MAXCTA) g = AL_MAXCTA;
   return g;
 }
 

@@ -175,7 +175,8 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
 
 template <int K>
 __global__ void __launch_bounds__(128)
-knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
+knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int ring_cap,
+                    uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t s = t >> 2;
   const int sub = threadIdx.x & 3;
@@ -189,6 +190,8 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
   int r0, r1;
   ring_range(g, cx, cy, cz, r0, r1);
   double sum[3], m2[6];
+  bool done = false;
+  if (r1 > ring_cap) r1 = ring_cap;   // sparse neighbourhoods are finished by knn_cov_tail_kernel (a warp per query)
   for (int r = r0; r <= r1; r++) {
     quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L);
     // K-round merge of the four sorted lists
@@ -217,7 +220,17 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
       m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
       m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
     }
-    if (found == k && kth < ring_bound2(g, r, minfrac)) break;
+    if (found == k && kth < ring_bound2(g, r, minfrac)) { done = true; break; }
+  }
+  // the whole grid was covered (r1 not capped): the union top-k is final even without the bound test
+  {
+    int rr0, rr1;
+    ring_range(g, cx, cy, cz, rr0, rr1);
+    if (rr1 <= ring_cap) done = true;
+  }
+  if (!done) {
+    if (sub == 0) worklist[atomicAdd(wl_count, 1u)] = s;
+    return;
   }
   double out[6];
   cov_from_moments(sum, m2, k, eps, out);
@@ -225,6 +238,95 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
     double* d = cov + 6 * (size_t)s;
 #pragma unroll
     for (int e = 0; e < 6; e++) d[e] = out[e];
+  }
+}
+
+// K3 tail: one WARP per query for the sparse neighbourhoods the quad kernel gave up on.  The rows of each
+// shell are spread over the 32 lanes (a shell of radius r has (2r+1)^2 rows, most of them empty: the cost is
+// the dependent cell_start -> points loads, which now overlap 32-wide); a 32-way merge on packed
+// (d2, index) keys yields the exact top-k in ascending order.
+template <int K>
+__global__ void __launch_bounds__(128)
+knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, const uint32_t* __restrict__ worklist,
+                    const uint32_t* __restrict__ wl_count) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t count = *wl_count;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += nwarps) {
+    const uint32_t s = worklist[w];
+    f4 q = g.pts[s];
+    QuadList<K> L;
+    L.init();
+    int cx, cy, cz; float minfrac;
+    query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
+    int r0, r1;
+    ring_range(g, cx, cy, cz, r0, r1);
+    double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
+    for (int r = r0; r <= r1; r++) {
+      // rows of the shell, lane-strided
+      const int side = 2 * r + 1;
+      for (int j = lane; j < side * side; j += 32) {
+        int dz = j / side - r, dy = j % side - r;
+        int z = cz + dz, y = cy + dy;
+        if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+        bool face = (iabs_(dz) == r) || (iabs_(dy) == r);
+        int base = (z * g.ny + y) * g.nx;
+        int nseg = face ? 1 : 2;
+        for (int sgm = 0; sgm < nseg; sgm++) {
+          int xa, xb;
+          if (face) { xa = imax_(cx - r, 0); xb = imin_(cx + r, g.nx - 1); }
+          else { xa = xb = (sgm == 0) ? cx - r : cx + r; if (xa < 0 || xa >= g.nx) continue; }
+          if (xa > xb) continue;
+          uint32_t a = g.cell_start[base + xa], e = g.cell_start[base + xb + 1];
+          for (uint32_t i = a; i < e; i++) {
+            f4 p = g.pts[i];
+            L.push(dist2(q.x, q.y, q.z, p.x, p.y, p.z), float_to_bits(p.w), (int)i);
+          }
+        }
+      }
+      __syncwarp();
+      // enough candidates in total?  (cheap test before the 32-way merge)
+      int total = L.cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (total < k && r < r1) continue;
+      // k-round merge on packed keys: (float bits of d2 (non-negative: order preserving) << 32) | original index
+      int p = 0, found = 0;
+      float kth = 3.0e38f;
+      sum[0] = sum[1] = sum[2] = 0.0;
+      m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+      for (int round = 0; round < k; round++) {
+        unsigned long long key = (p < L.cnt)
+            ? (((unsigned long long)__float_as_uint(L.d2[p]) << 32) | (unsigned)L.oi[p])
+            : 0xffffffffffffffffull;
+        unsigned long long best = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other < best ? other : best;
+        }
+        if (best == 0xffffffffffffffffull) break;
+        unsigned owner = __ballot_sync(0xffffffffu, key == best);
+        int src_lane = __ffs(owner) - 1;
+        int bs = __shfl_sync(0xffffffffu, (p < L.cnt) ? L.si[p] : -1, src_lane);
+        if (lane == src_lane) p++;
+        found++;
+        kth = __uint_as_float((unsigned)(best >> 32));
+        f4 pt = g.pts[bs];
+        sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
+        m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
+        m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+      }
+      if (found == k && kth < ring_bound2(g, r, minfrac)) break;
+    }
+    double out[6];
+    cov_from_moments(sum, m2, k, eps, out);
+    if (lane == 0) {
+      double* d = cov + 6 * (size_t)s;
+#pragma unroll
+      for (int e = 0; e < 6; e++) d[e] = out[e];
+    }
+    __syncwarp();
   }
 }
 
@@ -337,31 +439,40 @@ __device__ __forceinline__ bool slot_try(const SlotWord* p, unsigned long long e
   v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
   return true;
 }
-// Sum value e over the slots of all CTAs in a fixed order (lane b, b+32, ... then shuffle tree); all the
-// lane's loads are issued together and only the missing ones are re-polled.  Result in lane 0.
-__device__ __forceinline__ double slots_sum(const SlotWord* buf, int ncta, int e, unsigned long long epoch) {
-  const int lane = threadIdx.x & 31;
-  double val[AL_MAXB];
+// Gather the NV published words of all `ncta` slots and sum each value over the slots in a fixed order.
+// Every (slot, value) pair is polled by exactly one thread of the CTA, all pairs in flight at once (one L2
+// round trip when nobody is late); the values land in a shared matrix and warp w then sums rows e = w,
+// w + nwarps, ... lane-strided + shuffle tree.  out[e] (shared) valid after the trailing CTA barrier.
+constexpr int AL_MAXCTA = 160;
+template <int NV, int THREADS>
+__device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, unsigned long long epoch,
+                                              double* mat /*[NV][AL_MAXCTA] shared*/, double* out /*shared [NV]*/) {
+  const int npairs = ncta * NV;
+  constexpr int MAXP = (AL_MAXCTA * NV + THREADS - 1) / THREADS;
   unsigned pending = 0;
 #pragma unroll
-  for (int k = 0; k < AL_MAXB; k++) {
-    val[k] = 0.0;
-    if (lane + 32 * k < ncta) pending |= 1u << k;
-  }
+  for (int k = 0; k < MAXP; k++)
+    if ((int)threadIdx.x + k * THREADS < npairs) pending |= 1u << k;
   while (pending) {
 #pragma unroll
-    for (int k = 0; k < AL_MAXB; k++)
+    for (int k = 0; k < MAXP; k++)
       if (pending & (1u << k)) {
+        int pr = threadIdx.x + k * THREADS;
+        int b = pr / NV, e = pr - b * NV;
         double v;
-        if (slot_try(&buf[(size_t)(lane + 32 * k) * AL_PSTRIDE + e], epoch, v)) { val[k] = v; pending &= ~(1u << k); }
+        if (slot_try(&buf[(size_t)b * AL_PSTRIDE + e], epoch, v)) { mat[e * AL_MAXCTA + b] = v; pending &= ~(1u << k); }
       }
   }
-  double x = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = warp; e < NV; e += THREADS / 32) {
+    double x = 0.0;
+    for (int b = lane; b < ncta; b += 32) x += mat[e * AL_MAXCTA + b];
 #pragma unroll
-  for (int k = 0; k < AL_MAXB; k++) x += val[k];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-  return x;
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) out[e] = x;
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------ K4 correspondences
@@ -451,6 +562,8 @@ template <int NV>
 __global__ void __launch_bounds__(AL_THREADS)
 objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __restrict__ ticket, double* __restrict__ out) {
   __shared__ double red[AL_ACC_WARPS * NV];
+  __shared__ double mat[NV * AL_MAXCTA];
+  __shared__ double tot_s[NV];
   __shared__ float sT[12];
   __shared__ double sD[27];
   __shared__ bool last;
@@ -479,12 +592,8 @@ objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __r
   __syncthreads();
   if (last) {
     __threadfence();
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = warp; e < NV; e += AL_THREADS / 32) {
-      double xs = slots_sum(slots, gridDim.x, e, 1ull);
-      if (lane == 0) out[e] = xs;
-    }
-    __syncthreads();
+    slots_all_sum<NV, AL_THREADS>(slots, gridDim.x, 1ull, mat, tot_s);
+    if (threadIdx.x < NV) out[threadIdx.x] = tot_s[threadIdx.x];
     // reset the tags and the ticket for the next launch
     for (int i = threadIdx.x; i < (int)gridDim.x * NV; i += AL_THREADS)
       slot_store(&slots[(size_t)(i / NV) * AL_PSTRIDE + (i % NV)], 0.0, 0ull);
@@ -523,6 +632,7 @@ struct AlignShared {
   double D[27];
   double red[AL_ACC_WARPS * AL_MAXV];
   double bc[AL_MAXV + 4];
+  double mat[AL_MAXV * AL_MAXCTA];
 };
 
 struct Collective {   // per-thread copy; advances in lockstep in every thread of the grid
@@ -548,13 +658,8 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   SlotWord* buf = a.slots + (size_t)co.flip * ncta * AL_PSTRIDE;
   if (threadIdx.x < NV) slot_store(&buf[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, co.epoch);
   long long t1 = prof ? clock64() : 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e = warp; e < NV; e += AL_THREADS / 32) {
-    double x = slots_sum(buf, ncta, e, co.epoch);
-    if (lane == 0) sh.bc[e] = x;
-  }
+  slots_all_sum<NV, AL_THREADS>(buf, ncta, co.epoch, sh.mat, sh.bc);
   co.flip ^= 1;
-  __syncthreads();
   if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; }
 }
 
@@ -611,20 +716,18 @@ struct DeviceBackend {
   __device__ __forceinline__ void warp_trig(const double* x, Trig& t) {
     const int lane = threadIdx.x & 31;
     const int k = lane % 3;
-    double v = 0.0;
-    if (lane < 6) {                      // half angles, float-rounded argument
-      double h = (double)half_angle(x, k);
-      v = (lane < 3) ? cos(h) : sin(h);
-    } else if (lane < 12) {
-      double ang = x[3 + k];
-      v = (lane < 9) ? cos(ang) : sin(ang);
+    double sv = 0.0, cv = 0.0;
+    if (lane < 6) {                      // lanes 0-2: half angles (float-rounded argument), lanes 3-5: full angles
+      double ang = (lane < 3) ? (double)half_angle(x, k) : x[3 + k];
+      sv = sin(ang);
+      cv = cos(ang);
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      t.ch[i] = (float)__shfl_sync(0xffffffffu, v, i);
-      t.sh[i] = (float)__shfl_sync(0xffffffffu, v, 3 + i);
-      t.c[i] = __shfl_sync(0xffffffffu, v, 6 + i);
-      t.s[i] = __shfl_sync(0xffffffffu, v, 9 + i);
+      t.ch[i] = (float)__shfl_sync(0xffffffffu, cv, i);
+      t.sh[i] = (float)__shfl_sync(0xffffffffu, sv, i);
+      t.c[i] = __shfl_sync(0xffffffffu, cv, 3 + i);
+      t.s[i] = __shfl_sync(0xffffffffu, sv, 3 + i);
     }
   }
 
