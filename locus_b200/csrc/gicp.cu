@@ -10,6 +10,7 @@
 // (persistent mode).  There is no CPU compute path: without a CUDA device every
 // entry point fails with LB_ERR_NO_DEVICE.
 #include <math.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -332,7 +333,9 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
 // CTAs of the align kernels: one thread per source point, at least 8 and at most one CTA per SM.
 // Both execution modes use the same grid so their reductions have the same shape (identical bits).
 int grid_for(lb_gicp* h, int n_src) {
-  int g = cdiv(n_src, AL_PPC);
+  static int ppc = 0;   // tuning aid: LB_PPC overrides the source points per CTA
+  if (!ppc) { const char* e = getenv("LB_PPC"); ppc = e ? atoi(e) : AL_PPC; if (ppc < AL_ACC) ppc = AL_ACC; }
+  int g = cdiv(n_src, ppc);
   if (g < 8) g = 8;
   if (g > h->align_blocks) g = h->align_blocks;
   if (g > AL_MAXCTA) g = AL_MAXCTA;

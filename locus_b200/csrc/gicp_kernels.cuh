@@ -393,20 +393,20 @@ nn_query_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t 
 
 // ------------------------------------------------------------------ block / grid reductions
 // Fixed-shape, bitwise run-to-run deterministic reduction of NV doubles held by the threads of the first
-// NWARPS warps: warp shuffle tree -> per-warp slots in shared memory -> lane e of warp 0 adds the NWARPS
+// NWARPS warps [W0, W0+NWARPS): warp shuffle tree -> per-warp slots in shared memory -> lane e of warp 0 adds the NWARPS
 // slots of value e in warp order.  Lane e (< NV) of warp 0 returns total e; every other thread gets 0.
 // (Only NWARPS warps shuffle: SHFL issues at one warp-instruction per cycle per SM, so the cost is
 // NWARPS * NV * 10 cycles.)  All threads of the CTA must call it (two CTA barriers inside).
-template <int NV, int NWARPS>
+template <int NV, int NWARPS, int W0 = 0>
 __device__ __forceinline__ double block_reduce(double* v, double* red /*[NWARPS][NV]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp < NWARPS) {
+  if (warp >= W0 && warp < W0 + NWARPS) {
 #pragma unroll
     for (int e = 0; e < NV; e++) {
       double x = v[e];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      if (lane == 0) red[warp * NV + e] = x;
+      if (lane == 0) red[(warp - W0) * NV + e] = x;
     }
   }
   __syncthreads();
@@ -530,24 +530,67 @@ struct ObjArgs {
 };
 
 // accumulate the NV sums of this thread's points.  NV = 13: BFGS objective; 28: Gauss-Newton.
-// CTA c owns the contiguous chunk [c*chunk, (c+1)*chunk) of the (cell-sorted) source
+// CTA c owns the contiguous chunk [c*chunk, (c+1)*chunk) of the (cell-sorted) source.  The objective terms are
+// accumulated by the 128 lanes of warps 1..4 (warp 0 is the leader of the persistent kernel): lane t takes points
+// begin + t + 128*j, j = 0, 1, ...  in that order.
+constexpr int AL_ACC_W0 = 1;                 // first accumulating warp
+constexpr int AL_PPL = AL_PPC / AL_ACC;      // points per accumulating lane held in registers (4)
+
 __device__ __forceinline__ void cta_chunk(int n, int& begin, int& end) {
   int chunk = (n + (int)gridDim.x - 1) / (int)gridDim.x;
   begin = min(n, (int)blockIdx.x * chunk);
   end = min(n, begin + chunk);
 }
+__device__ __forceinline__ int acc_lane() { return (int)threadIdx.x - 32 * AL_ACC_W0; }   // 0..127 for accumulating lanes
+
+// A lane's correspondences, register-resident across all objective evaluations of one outer iteration
+// (the correspondences are fixed during the inner solve, gicp.hpp:518-524): zero memory traffic per evaluation.
+struct PointCache {
+  float px[AL_PPL], py[AL_PPL], pz[AL_PPL], qx[AL_PPL], qy[AL_PPL], qz[AL_PPL];
+  double M[AL_PPL][6];
+};
+
+__device__ __forceinline__ void cache_load(const ObjArgs& a, int begin, int end, PointCache& pc) {
+  const int t = acc_lane();
+#pragma unroll
+  for (int j = 0; j < AL_PPL; j++) {
+    int s = begin + t + AL_ACC * j;
+    bool ok = (t >= 0 && t < AL_ACC && s < end);
+    f4 c = ok ? a.corr[s] : f4{0.f, 0.f, 0.f, bits_to_float(-1)};
+    ok = ok && float_to_bits(c.w) >= 0;
+    f4 p = ok ? a.src[s] : f4{0.f, 0.f, 0.f, 0.f};
+    pc.px[j] = p.x; pc.py[j] = p.y; pc.pz[j] = p.z;
+    pc.qx[j] = c.x; pc.qy[j] = c.y; pc.qz[j] = c.z;
+#pragma unroll
+    for (int e = 0; e < 6; e++) pc.M[j][e] = ok ? a.M[6 * (size_t)s + e] : 0.0;   // M = 0: exact zero contribution
+  }
+}
 
 template <int NV>
-__device__ __forceinline__ void objective_accumulate(const ObjArgs& a, const float* T, const double* dP, const double* dT,
-                                                     const double* dS, int first, int end, int step, double* acc) {
-  for (int s = first; s < end; s += step) {
+__device__ __forceinline__ void objective_from_cache(const PointCache& pc, const float* T, const double* dP, const double* dT,
+                                                     const double* dS, double* acc) {
+#pragma unroll
+  for (int j = 0; j < AL_PPL; j++) {
+    if constexpr (NV == 13) objective_terms(T, pc.px[j], pc.py[j], pc.pz[j], pc.qx[j], pc.qy[j], pc.qz[j], pc.M[j], acc);
+    else gn_terms(T, dP, dT, dS, pc.px[j], pc.py[j], pc.pz[j], pc.qx[j], pc.qy[j], pc.qz[j], pc.M[j], acc);
+  }
+}
+
+// same lane -> points mapping and order, straight from global memory (chunks larger than AL_PPC, and the
+// host-driven kernel).  Unmatched points carry M = 0 and add exact zeros, like the padded cache entries.
+template <int NV>
+__device__ __forceinline__ void objective_from_global(const ObjArgs& a, const float* T, const double* dP, const double* dT,
+                                                      const double* dS, int begin, int end, double* acc) {
+  const int t = acc_lane();
+  if (t < 0 || t >= AL_ACC) return;
+  for (int s = begin + t; s < end; s += AL_ACC) {
     f4 c = a.corr[s];
-    if (float_to_bits(c.w) < 0) continue;
     f4 p = a.src[s];
     double M[6];
     const double* m = a.M + 6 * (size_t)s;
 #pragma unroll
     for (int e = 0; e < 6; e++) M[e] = m[e];
+    if (float_to_bits(c.w) < 0) { c = f4{0.f, 0.f, 0.f, 0.f}; p = c; }
     if constexpr (NV == 13) objective_terms(T, p.x, p.y, p.z, c.x, c.y, c.z, M, acc);
     else gn_terms(T, dP, dT, dS, p.x, p.y, p.z, c.x, c.y, c.z, M, acc);
   }
@@ -580,8 +623,8 @@ objective_kernel(ObjArgs a, Vec6d x, SlotWord* __restrict__ slots, unsigned* __r
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
   int begin, end;
   cta_chunk(a.n_src, begin, end);
-  if (threadIdx.x < AL_ACC) objective_accumulate<NV>(a, T, sD, sD + 9, sD + 18, begin + threadIdx.x, end, AL_ACC, acc);
-  double tot = block_reduce<NV, AL_ACC_WARPS>(acc, red);
+  objective_from_global<NV>(a, T, sD, sD + 9, sD + 18, begin, end, acc);
+  double tot = block_reduce<NV, AL_ACC_WARPS, AL_ACC_W0>(acc, red);
   if (threadIdx.x < NV) slot_store(&slots[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, 1ull);
   __threadfence();
   __syncthreads();
@@ -652,7 +695,7 @@ template <int NV>
 __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared& sh, Collective& co, double* acc) {
   const bool prof = (blockIdx.x == 0 && threadIdx.x == 0);
   long long t0 = prof ? clock64() : 0;
-  double tot = block_reduce<NV, AL_ACC_WARPS>(acc, sh.red);
+  double tot = block_reduce<NV, AL_ACC_WARPS, AL_ACC_W0>(acc, sh.red);
   co.epoch++;
   const int ncta = gridDim.x;
   SlotWord* buf = a.slots + (size_t)co.flip * ncta * AL_PSTRIDE;
@@ -663,7 +706,7 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; }
 }
 
-__device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co) {
+__device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co, PointCache& pc) {
   float T[12]; double R[9];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
@@ -673,33 +716,42 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
   cta_chunk(a.c.n_src, begin, end);
   int hits = 0;
   for (int s = begin + threadIdx.x; s < end; s += AL_THREADS) hits += correspond_point(a.c, T, R, s);
-  // fold the 8 warps' counts onto the accumulating lanes: the correspondence arrays written above are only
-  // ever re-read by this CTA (do_objective uses the same chunk), after the CTA barriers below.
+  // The correspondence arrays written above are only ever re-read by this CTA, after the CTA barrier below.
   __shared__ int s_hits[AL_THREADS];
   s_hits[threadIdx.x] = hits;
   __syncthreads();
   double cnt[1] = {0.0};
-  if (threadIdx.x < AL_ACC) {
+  const int t = acc_lane();
+  if (t >= 0 && t < AL_ACC) {
     int h = 0;
 #pragma unroll
-    for (int k = 0; k < AL_THREADS / AL_ACC; k++) h += s_hits[threadIdx.x + k * AL_ACC];
+    for (int k = 0; k < AL_THREADS / AL_ACC; k++) h += s_hits[t + k * AL_ACC];
     cnt[0] = (double)h;
+  }
+  if (end - begin <= AL_PPC && t >= 0 && t < AL_ACC) {
+    ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
+    cache_load(oa, begin, end, pc);
   }
   grid_all_reduce<1>(a, sh, co, cnt);
 }
 
 template <int NV>
-__device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh, Collective& co) {
+__device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh, Collective& co, const PointCache& pc) {
   float T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
   double acc[NV];
 #pragma unroll
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
-  ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
   int begin, end;
   cta_chunk(a.c.n_src, begin, end);
-  if (threadIdx.x < AL_ACC) objective_accumulate<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, begin + threadIdx.x, end, AL_ACC, acc);
+  const int t = acc_lane();
+  if (end - begin <= AL_PPC) {
+    if (t >= 0 && t < AL_ACC) objective_from_cache<NV>(pc, T, sh.D, sh.D + 9, sh.D + 18, acc);
+  } else {
+    ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
+    objective_from_global<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, begin, end, acc);
+  }
   grid_all_reduce<NV>(a, sh, co, acc);
 }
 
@@ -708,9 +760,11 @@ struct DeviceBackend {
   const AlignArgs& a;
   AlignShared& sh;
   Collective& co;
+  PointCache& pc;     // warp 0 never accumulates: its cache is never read
   int m;
 
-  __device__ DeviceBackend(const AlignArgs& a_, AlignShared& sh_, Collective& co_) : a(a_), sh(sh_), co(co_), m(0) {}
+  __device__ DeviceBackend(const AlignArgs& a_, AlignShared& sh_, Collective& co_, PointCache& pc_)
+      : a(a_), sh(sh_), co(co_), pc(pc_), m(0) {}
 
   // the 12 trigonometric values of a state, one per lane, broadcast to the warp
   __device__ __forceinline__ void warp_trig(const double* x, Trig& t) {
@@ -737,7 +791,7 @@ struct DeviceBackend {
     if (lane < 9) sh.R[lane] = R[lane];
     if (lane == 0) sh.op = OP_CORR;
     __syncthreads();
-    do_correspond(a, sh, co);
+    do_correspond(a, sh, co, pc);
     m = (int)sh.bc[0];
     return m;
   }
@@ -751,7 +805,7 @@ struct DeviceBackend {
     if (lane < 12) sh.T[lane] = T[lane];
     if (lane == 0) sh.op = OP_FDF;
     __syncthreads();
-    do_objective<13>(a, sh, co);
+    do_objective<13>(a, sh, co, pc);
     double sums[13];
 #pragma unroll
     for (int e = 0; e < 13; e++) sums[e] = sh.bc[e];
@@ -770,7 +824,7 @@ struct DeviceBackend {
     if (lane < 27) sh.D[lane] = D[lane];
     if (lane == 0) sh.op = OP_GN;
     __syncthreads();
-    do_objective<28>(a, sh, co);
+    do_objective<28>(a, sh, co, pc);
     *f = sh.bc[0] / (double)m;
 #pragma unroll
     for (int e = 0; e < 6; e++) b[e] = sh.bc[1 + e];
@@ -788,7 +842,8 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   const long long t_begin = clock64();
   if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; }
   if (threadIdx.x < 32) {
-    DeviceBackend be(a, sh, co);
+    PointCache pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
+    DeviceBackend be(a, sh, co, pc_unused);
     OuterResult r;
     gicp_outer_loop(be, a.P, a.guess, r);
     if (threadIdx.x == 0) sh.op = OP_EXIT;
@@ -800,13 +855,14 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       }
     }
   } else {
+    PointCache pc;
     for (;;) {
       __syncthreads();
       const int op = sh.op;
       if (op == OP_EXIT) break;
-      if (op == OP_CORR) do_correspond(a, sh, co);
-      else if (op == OP_FDF) do_objective<13>(a, sh, co);
-      else do_objective<28>(a, sh, co);
+      if (op == OP_CORR) do_correspond(a, sh, co, pc);
+      else if (op == OP_FDF) do_objective<13>(a, sh, co, pc);
+      else do_objective<28>(a, sh, co, pc);
     }
   }
 }
@@ -827,7 +883,7 @@ fitness_kernel(GridView g, const f4* __restrict__ raw, uint32_t n, Mat34 T, doub
     int s = nn1(g, x, y, z, 3.0e38f, bo, bd);
     if (s >= 0 && (double)bd <= max_range) { acc[0] = (double)bd; acc[1] = 1.0; }
   }
-  double tot = block_reduce<2, 4>(acc, red);
+  double tot = block_reduce<2, 4, 0>(acc, red);
   if (threadIdx.x < 2) partials[2 * (size_t)blockIdx.x + threadIdx.x] = tot;
 }
 
