@@ -180,6 +180,11 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
     return LB_ERR_CUDA;
   }
   memset(h->h_debug, 0, 8 * sizeof(long long));
+  if (cudaFuncSetAttribute(knn_cov_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnWarpSmem)) != cudaSuccess) {
+    set_error("lb_gicp_create: cannot reserve %zu bytes of shared memory", sizeof(KnnWarpSmem));
+    delete h;
+    return LB_ERR_CUDA;
+  }
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   *out = h;
   return LB_OK;
@@ -310,19 +315,11 @@ int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    // quad-per-query up to ring 2, then a warp per query for the sparse tail (worklist through h->keys / d_u32[1])
-    const int ring_cap = 2;
-    LB_TRY(h->keys.ensure(cl.n));
-    LB_CUDA(cudaMemsetAsync(h->d_u32 + 1, 0, sizeof(uint32_t), c.stream));
-    int tail_blocks = c.sm_count * 4;
-    if (k <= 20) {
-      knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, ring_cap, h->keys.p, h->d_u32 + 1);
-      knn_cov_tail_kernel<20><<<tail_blocks, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, h->keys.p, h->d_u32 + 1);
-    } else {
-      knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, ring_cap, h->keys.p, h->d_u32 + 1);
-      knn_cov_tail_kernel<32><<<tail_blocks, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, h->keys.p, h->d_u32 + 1);
-    }
-    c.launches++;
+    // warp-per-query k-NN (candidates staged in shared memory, exact top-k by k rounds of warp-min)
+    int blocks = cdiv(N, KW_WARPS);
+    int max_blocks = c.sm_count * 4;
+    if (blocks > max_blocks) blocks = max_blocks;
+    knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
   }
   c.launches++;
   LB_CUDA(cudaGetLastError());
