@@ -330,61 +330,69 @@ knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, con
   }
 }
 
-// K3, warp-per-query variant (default).  A warp owns one query: the rows of every shell are spread over the
-// lanes (all cell_start look-ups of a shell in flight at once), the candidates of the probed block are staged
-// in the warp's shared-memory buffer as packed (d2 bits << 32 | original index) keys, and the exact top-k is
-// extracted by k rounds of "smallest key greater than the previous one" (lane-strided scan + warp min).
-// The moments are accumulated in that ascending (d2, index) order -- the order of the oracle -- so the
-// covariances are bit-identical to the thread-per-point kernels.  After an unsuccessful bound test only the
-// k best are kept, so the buffer never holds more than k + one shell.
+// K3, warp-per-query variant (default).  A warp owns one query:
+//   * the rows of every shell are spread over the lanes (all cell_start look-ups of a shell in flight at once),
+//     then the candidate points of those rows are fetched FLATTENED -- lane l takes candidates l, l+32, ... of
+//     the concatenated runs -- so every load instruction has 32 independent addresses in flight;
+//   * candidates are staged in the warp's shared-memory buffer (packed key = d2 bits << 32 | original index,
+//     plus x, y, z);
+//   * the exact top-k is found by RANKING: every lane counts, for each candidate it owns, how many keys are
+//     smaller (one shared-memory broadcast read per compare) -- no dependent selection rounds; candidates
+//     with rank < k drop into slot `rank` of the selection buffer, which is therefore sorted ascending;
+//   * the moments are accumulated from that buffer in ascending (d2, index) order -- the order of the oracle --
+//     so the covariances are bit-identical to the thread-per-point kernels.
+// After an unsuccessful bound test only the k best are kept, so the buffer holds at most k + one batch.
 constexpr int KW_WARPS = 8;       // warps (= queries in flight) per CTA
-constexpr int KW_CAP = 512;       // candidate slots per warp
+constexpr int KW_CAP = 320;       // candidate slots per warp
+constexpr int KW_T = KW_CAP / 32; // candidates owned per lane
 
 struct KnnWarpSmem {
   long long key[KW_WARPS][KW_CAP];
-  int si[KW_WARPS][KW_CAP];
+  float x[KW_WARPS][KW_CAP], y[KW_WARPS][KW_CAP], z[KW_WARPS][KW_CAP];
   long long sel_key[KW_WARPS][32];
-  int sel_si[KW_WARPS][32];
+  float sel_x[KW_WARPS][32], sel_y[KW_WARPS][32], sel_z[KW_WARPS][32];
+  uint32_t row_a0[KW_WARPS][32], row_a1[KW_WARPS][32];
+  int row_n0[KW_WARPS][32], row_off[KW_WARPS][33];
 };
 
-// select the k smallest keys of key[0..cnt) in ascending order; accumulates the moments of the selected
-// points in that order; returns the number found and the k-th key.  All lanes return identical values.
-__device__ __forceinline__ int warp_select_k(const GridView& g, const long long* key, const int* si, int cnt, int k,
-                                             long long* sel_key, int* sel_si, double* sum, double* m2, long long& kth) {
+struct KnnWarpView {   // this warp's slices of the shared buffers
+  long long* key; float *x, *y, *z;
+  long long* sel_key; float *sel_x, *sel_y, *sel_z;
+  uint32_t *row_a0, *row_a1; int *row_n0, *row_off;
+};
+
+// rank-select the k smallest of key[0..cnt) into sel_*[0..found) (ascending).  returns found = min(cnt, k).
+__device__ __forceinline__ int warp_rank_select(const KnnWarpView& w, int cnt, int k) {
   const int lane = threadIdx.x & 31;
-  long long prev = -1;
-  int found = 0;
-  sum[0] = sum[1] = sum[2] = 0.0;
-  m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
-  for (int round = 0; round < k; round++) {
-    long long best = 0x7fffffffffffffffll;
-    int bi = -1;
-    for (int i = lane; i < cnt; i += 32) {
-      long long kk = key[i];
-      if (kk > prev && kk < best) { best = kk; bi = i; }
-    }
-    long long wbest = best;
+  long long mine[KW_T];
+  int rank[KW_T];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
-      wbest = other < wbest ? other : wbest;
-    }
-    if (wbest == 0x7fffffffffffffffll) break;
-    unsigned owner = __ballot_sync(0xffffffffu, best == wbest);
-    int src_lane = __ffs(owner) - 1;
-    int wbi = __shfl_sync(0xffffffffu, bi, src_lane);
-    int s = si[wbi];
-    if (lane == 0) { sel_key[found] = wbest; sel_si[found] = s; }
-    prev = wbest;
-    found++;
-    f4 pt = g.pts[s];
-    sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
-    m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
-    m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+  for (int t = 0; t < KW_T; t++) {
+    int i = lane + 32 * t;
+    mine[t] = (i < cnt) ? w.key[i] : 0x7fffffffffffffffll;
+    rank[t] = 0;
   }
-  kth = prev;
+  for (int j = 0; j < cnt; j++) {
+    long long kj = w.key[j];
+#pragma unroll
+    for (int t = 0; t < KW_T; t++) rank[t] += (kj < mine[t]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int t = 0; t < KW_T; t++) {
+    int i = lane + 32 * t;
+    if (i < cnt && rank[t] < k) {
+      int r = rank[t];
+      w.sel_key[r] = mine[t]; w.sel_x[r] = w.x[i]; w.sel_y[r] = w.y[i]; w.sel_z[r] = w.z[i];
+    }
+  }
   __syncwarp();
-  return found;
+  return cnt < k ? cnt : k;
+}
+
+__device__ __forceinline__ void warp_compact_to_selection(const KnnWarpView& w, int found) {
+  const int lane = threadIdx.x & 31;
+  if (lane < found) { w.key[lane] = w.sel_key[lane]; w.x[lane] = w.sel_x[lane]; w.y[lane] = w.sel_y[lane]; w.z[lane] = w.sel_z[lane]; }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(KW_WARPS * 32)
@@ -392,10 +400,8 @@ knn_cov_warp_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
   extern __shared__ __align__(16) unsigned char kw_smem_raw[];
   KnnWarpSmem& sm = *reinterpret_cast<KnnWarpSmem*>(kw_smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  long long* key = sm.key[wib];
-  int* si = sm.si[wib];
-  long long* sel_key = sm.sel_key[wib];
-  int* sel_si = sm.sel_si[wib];
+  KnnWarpView w{sm.key[wib], sm.x[wib], sm.y[wib], sm.z[wib], sm.sel_key[wib], sm.sel_x[wib], sm.sel_y[wib], sm.sel_z[wib],
+                sm.row_a0[wib], sm.row_a1[wib], sm.row_n0[wib], sm.row_off[wib]};
   const uint32_t nwarps = gridDim.x * KW_WARPS;
   for (uint32_t s = blockIdx.x * KW_WARPS + wib; s < (uint32_t)g.n; s += nwarps) {
     const f4 q = g.pts[s];
@@ -403,14 +409,13 @@ knn_cov_warp_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
     query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
     int r0, r1;
     ring_range(g, cx, cy, cz, r0, r1);
-    int cnt = 0;
-    double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
+    int cnt = 0, found = 0;
     for (int r = r0; r <= r1; r++) {
       const int side = 2 * r + 1;
       const int nrows = side * side;
       for (int rowbase = 0; rowbase < nrows; rowbase += 32) {
-        // this lane's row of the shell: up to two runs [a0,e0) [a1,e1)
-        uint32_t a0 = 0, e0 = 0, a1 = 0, e1 = 0;
+        // this lane's row of the shell: up to two runs [a0, a0+n0) and [a1, a1+n1)
+        uint32_t a0 = 0, a1 = 0; int n0 = 0, n1 = 0;
         int j = rowbase + lane;
         if (j < nrows) {
           int dz = j / side - r, dy = j - (j / side) * side - r;
@@ -420,88 +425,67 @@ knn_cov_warp_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
             bool face = (iabs_(dz) == r) || (iabs_(dy) == r);
             if (face) {
               int xa = imax_(cx - r, 0), xb = imin_(cx + r, g.nx - 1);
-              if (xa <= xb) { a0 = g.cell_start[base + xa]; e0 = g.cell_start[base + xb + 1]; }
+              if (xa <= xb) { a0 = g.cell_start[base + xa]; n0 = (int)(g.cell_start[base + xb + 1] - a0); }
             } else {
               int x0 = cx - r, x1 = cx + r;
-              if (x0 >= 0 && x0 < g.nx) { a0 = g.cell_start[base + x0]; e0 = g.cell_start[base + x0 + 1]; }
-              if (x1 >= 0 && x1 < g.nx) { a1 = g.cell_start[base + x1]; e1 = g.cell_start[base + x1 + 1]; }
+              if (x0 >= 0 && x0 < g.nx) { a0 = g.cell_start[base + x0]; n0 = (int)(g.cell_start[base + x0 + 1] - a0); }
+              if (x1 >= 0 && x1 < g.nx) { a1 = g.cell_start[base + x1]; n1 = (int)(g.cell_start[base + x1 + 1] - a1); }
             }
           }
         }
-        int len = (int)(e0 - a0) + (int)(e1 - a1);
-        // exclusive scan of the row lengths -> slot of this lane's candidates
+        int len = n0 + n1;
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           int t = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += t;
         }
-        int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (cnt + total > KW_CAP) {
-          // make room: reduce what we have to its k best (exact: top-k(A u B) = top-k(top-k(A) u B))
-          if (cnt > k) {
-            long long kth;
-            int found = warp_select_k(g, key, si, cnt, k, sel_key, sel_si, sum, m2, kth);
-            if (lane < found) { key[lane] = sel_key[lane]; si[lane] = sel_si[lane]; }
-            cnt = found;
-            __syncwarp();
-          }
-        }
-        if (cnt + total <= KW_CAP) {
-          int off = cnt + incl - len;
-          for (uint32_t i = a0; i < e0; i++) {
-            f4 p = g.pts[i];
-            key[off] = ((long long)__float_as_uint(dist2(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | (unsigned)float_to_bits(p.w);
-            si[off] = (int)i; off++;
-          }
-          for (uint32_t i = a1; i < e1; i++) {
-            f4 p = g.pts[i];
-            key[off] = ((long long)__float_as_uint(dist2(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | (unsigned)float_to_bits(p.w);
-            si[off] = (int)i; off++;
-          }
-          cnt += total;
-        } else {
-          // a single batch of rows larger than the buffer (very dense cells): stream it, one lane's rows at a
-          // time, keeping the buffer reduced to the k best whenever it fills up
-          for (int l = 0; l < 32; l++) {
-            uint32_t ba0 = __shfl_sync(0xffffffffu, a0, l), be0 = __shfl_sync(0xffffffffu, e0, l);
-            uint32_t ba1 = __shfl_sync(0xffffffffu, a1, l), be1 = __shfl_sync(0xffffffffu, e1, l);
-            for (int seg = 0; seg < 2; seg++) {
-              uint32_t sa = seg ? ba1 : ba0, se = seg ? be1 : be0;
-              for (uint32_t i0 = sa; i0 < se; i0 += 32) {
-                if (cnt + 32 > KW_CAP) {
-                  long long kth;
-                  int found = warp_select_k(g, key, si, cnt, k, sel_key, sel_si, sum, m2, kth);
-                  if (lane < found) { key[lane] = sel_key[lane]; si[lane] = sel_si[lane]; }
-                  cnt = found;
-                  __syncwarp();
-                }
-                uint32_t i = i0 + lane;
-                bool ok = i < se;
-                unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                  f4 p = g.pts[i];
-                  int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                  key[pos] = ((long long)__float_as_uint(dist2(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | (unsigned)float_to_bits(p.w);
-                  si[pos] = (int)i;
-                }
-                cnt += __popc(m);
-                __syncwarp();
-              }
-            }
-          }
-        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        w.row_a0[lane] = a0; w.row_a1[lane] = a1; w.row_n0[lane] = n0; w.row_off[lane] = incl - len;
+        if (lane == 31) w.row_off[32] = total;
         __syncwarp();
+        // flattened fetch of the `total` candidates of this batch of rows, in chunks that fit the buffer
+        int done = 0;
+        while (done < total) {
+          int room = KW_CAP - cnt;
+          if (room < 32 && cnt > k) {              // make room: top-k(A u B) = top-k(top-k(A) u B)
+            found = warp_rank_select(w, cnt, k);
+            warp_compact_to_selection(w, found);
+            cnt = found;
+            room = KW_CAP - cnt;
+          }
+          int take = total - done < room ? total - done : room;
+          int cur = 0;
+          for (int idx = done + lane; idx < done + take; idx += 32) {
+            while (idx >= w.row_off[cur + 1]) cur++;
+            int local = idx - w.row_off[cur];
+            int nn0 = w.row_n0[cur];
+            uint32_t pi = (local < nn0) ? (w.row_a0[cur] + (uint32_t)local) : (w.row_a1[cur] + (uint32_t)(local - nn0));
+            f4 p = g.pts[pi];
+            int slot = cnt + (idx - done);
+            w.key[slot] = ((long long)__float_as_uint(dist2(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | (unsigned)float_to_bits(p.w);
+            w.x[slot] = p.x; w.y[slot] = p.y; w.z[slot] = p.z;
+          }
+          cnt += take;
+          done += take;
+          __syncwarp();
+        }
       }
       if (cnt < k && r < r1) continue;     // not even k candidates yet: next shell
-      long long kth;
-      int found = warp_select_k(g, key, si, cnt, k, sel_key, sel_si, sum, m2, kth);
+      found = warp_rank_select(w, cnt, k);
+      long long kth = w.sel_key[found - 1];
       float kth_d2 = __uint_as_float((unsigned)((unsigned long long)kth >> 32));
       if (found == k && kth_d2 < ring_bound2(g, r, minfrac)) break;
-      // keep only the k best before adding the next shell
-      if (lane < found) { key[lane] = sel_key[lane]; si[lane] = sel_si[lane]; }
+      warp_compact_to_selection(w, found);  // keep only the k best before adding the next shell
       cnt = found;
-      __syncwarp();
+    }
+    // moments in ascending (d2, index) order (float products accumulated in double, gicp.hpp:112-127)
+    double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
+    for (int i = 0; i < found; i++) {
+      float px = w.sel_x[i], py = w.sel_y[i], pz = w.sel_z[i];
+      sum[0] += px; sum[1] += py; sum[2] += pz;
+      m2[0] += px * px; m2[1] += py * px; m2[2] += py * py;
+      m2[3] += pz * px; m2[4] += pz * py; m2[5] += pz * pz;
     }
     double out[6];
     cov_from_moments(sum, m2, k, eps, out);

@@ -183,7 +183,7 @@ int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, s
     if (total_dev) LB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), c.stream));
     return LB_OK;
   }
-  if (n <= 65536) {
+  if (n <= 16384) {
     scan_single_kernel<<<1, 1024, 0, c.stream>>>(in, out, n, total_dev);
     c.launches += 1;
     LB_CUDA(cudaGetLastError());
