@@ -363,6 +363,10 @@ def main():
     cov_ms, cov_n = gicp.kernelTime("knn_cov")
     idx_ms, idx_n = gicp.kernelTime("index_build")
     dbg = [gicp.kernelTime("debug%d" % i)[0] for i in range(4)]
+    snapP = [gicp.kernelTime("snapP%d" % i)[0] for i in range(64)]
+    snapC = [gicp.kernelTime("snapC%d" % i)[0] for i in range(64)]
+    if os.environ.get("LB_SNAP"):
+        sys.stderr.write("SNAP publish ns: %s\nSNAP complete ns: %s\n" % (snapP, snapC))
     gicp.resetKernelTimes(False)
     gpu_poses = list(state["poses"])
     iters = np.array(state["iters"], dtype=np.float64); evals = np.array(state["evals"], dtype=np.float64)

@@ -173,13 +173,14 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
   if (h->slots.ensure((size_t)2 * h->c.sm_count * AL_PSTRIDE) != LB_OK ||
       cudaMemset(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord)) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_debug, 8 * sizeof(long long)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_debug, 8 * sizeof(long long)) != cudaSuccess) {
+      cudaMalloc((void**)&h->d_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long)) != cudaSuccess) {
     set_error("lb_gicp_create: allocation failed");
     delete h;
     return LB_ERR_CUDA;
   }
-  memset(h->h_debug, 0, 8 * sizeof(long long));
+  memset(h->h_debug, 0, (16 + 2 * AL_MAXCTA) * sizeof(long long));
+  cudaMemset(h->d_debug, 0, (16 + 2 * AL_MAXCTA) * sizeof(long long));
   if (cudaFuncSetAttribute(knn_cov_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnWarpSmem)) != cudaSuccess) {
     set_error("lb_gicp_create: cannot reserve %zu bytes of shared memory", sizeof(KnnWarpSmem));
     delete h;
@@ -580,7 +581,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid_for(h, ca.n_src)), dim3(AL_THREADS), args, 0, c.stream));
       c.launches++;
     }
-    if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, 8 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
     LB_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(OuterResult), cudaMemcpyDeviceToHost, c.stream));
     LB_CUDA(cudaStreamSynchronize(c.stream));
     R = *h->h_result;
@@ -718,6 +719,13 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
   *ms_avg = 0.f; if (launches) *launches = 0;
   if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '7') {   // cycle counters of the last persistent align
     *ms_avg = (float)h->h_debug[name[5] - '0'];
+    return LB_OK;
+  }
+  if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100
+    int i = atoi(name + 5);
+    if (i < 0 || i >= AL_MAXCTA) return LB_ERR_INVALID_ARG;
+    long long base = h->h_debug[16];
+    *ms_avg = (float)(h->h_debug[16 + (name[4] == 'C' ? AL_MAXCTA : 0) + i] - base);
     return LB_OK;
   }
   for (auto& t : h->timers) {

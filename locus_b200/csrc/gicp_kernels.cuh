@@ -361,32 +361,43 @@ struct KnnWarpView {   // this warp's slices of the shared buffers
   uint32_t *row_a0, *row_a1; int *row_n0, *row_off;
 };
 
-// rank-select the k smallest of key[0..cnt) into sel_*[0..found) (ascending).  returns found = min(cnt, k).
+// select the k smallest of key[0..cnt) into sel_*[0..found) (ascending): each lane keeps the keys it owns
+// (slots lane, lane+32, ...) in registers; round i takes the smallest key greater than the previous winner
+// (per-lane scan of its registers + 64-bit warp min), and the owner copies the point into slot i.
+// returns found = min(cnt, k).
 __device__ __forceinline__ int warp_rank_select(const KnnWarpView& w, int cnt, int k) {
   const int lane = threadIdx.x & 31;
   long long mine[KW_T];
-  int rank[KW_T];
 #pragma unroll
   for (int t = 0; t < KW_T; t++) {
     int i = lane + 32 * t;
     mine[t] = (i < cnt) ? w.key[i] : 0x7fffffffffffffffll;
-    rank[t] = 0;
   }
-  for (int j = 0; j < cnt; j++) {
-    long long kj = w.key[j];
+  const int nt = (cnt + 31) >> 5;   // slots per lane actually in use
+  long long prev = -1;
+  int found = 0;
+  for (int round = 0; round < k; round++) {
+    long long best = 0x7fffffffffffffffll;
+    int bt = 0;
 #pragma unroll
-    for (int t = 0; t < KW_T; t++) rank[t] += (kj < mine[t]) ? 1 : 0;
-  }
+    for (int t = 0; t < KW_T; t++)
+      if (t < nt && mine[t] > prev && mine[t] < best) { best = mine[t]; bt = t; }
+    long long wbest = best;
 #pragma unroll
-  for (int t = 0; t < KW_T; t++) {
-    int i = lane + 32 * t;
-    if (i < cnt && rank[t] < k) {
-      int r = rank[t];
-      w.sel_key[r] = mine[t]; w.sel_x[r] = w.x[i]; w.sel_y[r] = w.y[i]; w.sel_z[r] = w.z[i];
+    for (int o = 16; o > 0; o >>= 1) {
+      long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
+      wbest = other < wbest ? other : wbest;
     }
+    if (wbest == 0x7fffffffffffffffll) break;
+    if (best == wbest) {          // unique owner (keys are unique)
+      int i = lane + 32 * bt;
+      w.sel_key[found] = wbest; w.sel_x[found] = w.x[i]; w.sel_y[found] = w.y[i]; w.sel_z[found] = w.z[i];
+    }
+    prev = wbest;
+    found++;
   }
   __syncwarp();
-  return cnt < k ? cnt : k;
+  return found;
 }
 
 __device__ __forceinline__ void warp_compact_to_selection(const KnnWarpView& w, int found) {
@@ -869,7 +880,10 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   SlotWord* buf = a.slots + (size_t)co.flip * ncta * AL_PSTRIDE;
   if (threadIdx.x < NV) slot_store(&buf[(size_t)blockIdx.x * AL_PSTRIDE + threadIdx.x], tot, co.epoch);
   long long t1 = prof ? clock64() : 0;
+  const bool snap = a.debug && threadIdx.x == 0 && (co.epoch - a.epoch_base) == 100;   // one collective, all CTAs
+  if (snap) a.debug[16 + blockIdx.x] = (long long)globaltimer_ns();
   slots_all_sum<NV, AL_THREADS>(buf, ncta, co.epoch, sh.mat, sh.bc);
+  if (snap) a.debug[16 + AL_MAXCTA + blockIdx.x] = (long long)globaltimer_ns();
   co.flip ^= 1;
   if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; }
 }

@@ -80,10 +80,22 @@ bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint3
     mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0 && cnt > 0) {
-    atomicMin(&acc->mn[0], mn0); atomicMin(&acc->mn[1], mn1); atomicMin(&acc->mn[2], mn2);
-    atomicMax(&acc->mx[0], mx0); atomicMax(&acc->mx[1], mx1); atomicMax(&acc->mx[2], mx2);
-    atomicAdd(&acc->count, cnt);
+  // one set of atomics per CTA (same-address atomics serialise in L2)
+  __shared__ uint32_t sm[8][7];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[w][0] = mn0; sm[w][1] = mn1; sm[w][2] = mn2; sm[w][3] = mx0; sm[w][4] = mx1; sm[w][5] = mx2; sm[w][6] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) {
+      mn0 = min(mn0, sm[i][0]); mn1 = min(mn1, sm[i][1]); mn2 = min(mn2, sm[i][2]);
+      mx0 = max(mx0, sm[i][3]); mx1 = max(mx1, sm[i][4]); mx2 = max(mx2, sm[i][5]);
+      cnt += sm[i][6];
+    }
+    if (cnt > 0) {
+      atomicMin(&acc->mn[0], mn0); atomicMin(&acc->mn[1], mn1); atomicMin(&acc->mn[2], mn2);
+      atomicMax(&acc->mx[0], mx0); atomicMax(&acc->mx[1], mx1); atomicMax(&acc->mx[2], mx2);
+      atomicAdd(&acc->count, cnt);
+    }
   }
 }
 
@@ -183,7 +195,7 @@ int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, s
     if (total_dev) LB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), c.stream));
     return LB_OK;
   }
-  if (n <= 16384) {
+  if (n <= 8192) {
     scan_single_kernel<<<1, 1024, 0, c.stream>>>(in, out, n, total_dev);
     c.launches += 1;
     LB_CUDA(cudaGetLastError());
