@@ -608,7 +608,10 @@ __device__ __forceinline__ void slot_store(SlotWord* p, double v, unsigned long 
   unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   unsigned long long tag = (epoch & 0xffffffffull) << 32;
   unsigned long long lo = tag | (bits & 0xffffffffull), hi = tag | (bits >> 32);
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+  // published with atomic exchanges: atomics are performed at L2 immediately, whereas a plain store can sit in
+  // the SM's write path for microseconds when no fence pushes it out (measured: 2.1-2.6 us publish-to-visible)
+  atomicExch(&p->lo, lo);
+  atomicExch(&p->hi, hi);
 }
 __device__ __forceinline__ bool slot_try(const SlotWord* p, unsigned long long epoch, double& v) {
   unsigned long long lo, hi;
