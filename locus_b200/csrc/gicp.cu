@@ -33,6 +33,7 @@ struct Cloud {
   GridGeom geom{};
   size_t ncells = 0;
   uint64_t generation = 0;
+  bool index_dirty = false;    // uploaded + geometry chosen, CSR index not built yet (built lazily in align)
   float auto_cell = 0.f;       // cell size found by the last occupancy probe for this slot
   size_t auto_n = 0;
   float auto_diag = 0.f;
@@ -45,6 +46,26 @@ struct Cloud {
     return v;
   }
   void release() { raw.release(); nrm.release(); pts.release(); cell_start.release(); cov.release(); }
+};
+
+// per-slot scratch so that the source and target pipelines can run concurrently on two streams
+struct Scratch {
+  Ctx c;                         // copy of the handle context with this slot's stream
+  DBuf<uint8_t> stage;           // H2D staging of the caller cloud
+  DBuf<uint32_t> keys, cell_cnt;
+  SortWork sort;
+  ScanWork scan;
+  BBoxAcc* d_acc = nullptr; BBoxAcc* h_acc = nullptr;
+  uint32_t* d_u32 = nullptr; uint32_t* h_u32 = nullptr;
+  void release() {
+    stage.release(); keys.release(); cell_cnt.release();
+    sort.ka.release(); sort.kb.release(); sort.va.release(); sort.vb.release(); sort.hist.release();
+    sort.scan.sums.release(); scan.sums.release();
+    if (d_acc) cudaFree(d_acc);
+    if (h_acc) cudaFreeHost(h_acc);
+    if (d_u32) cudaFree(d_u32);
+    if (h_u32) cudaFreeHost(h_u32);
+  }
 };
 
 struct KTimer {          // CUDA-event timing of one kernel class
@@ -64,13 +85,10 @@ struct lb_gicp {
   lb_gicp_params P;
   Cloud src, tgt;
   uint64_t gen_counter = 0;
-  // staging / scratch
-  DBuf<uint8_t> stage;           // H2D staging of caller clouds
-  DBuf<uint32_t> keys, cell_cnt;
-  SortWork sort;
-  ScanWork scan;
-  BBoxAcc* d_acc = nullptr; BBoxAcc* h_acc = nullptr;
-  uint32_t* d_u32 = nullptr; uint32_t* h_u32 = nullptr;     // small counters [8]
+  // staging / scratch: slot 0 = source pipeline (handle stream), slot 1 = target pipeline (second stream)
+  Scratch sc[2];
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // align state
   DBuf<f4> src_work, corr;
   DBuf<double> M;
@@ -147,11 +165,19 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   int s = ctx_init(h->c, device, stream, ext);
   if (s != LB_OK) { delete h; return s; }
   lb_gicp_default_params(&h->P);
-  bool ok = cudaMalloc((void**)&h->d_acc, sizeof(BBoxAcc)) == cudaSuccess &&
-            cudaMallocHost((void**)&h->h_acc, sizeof(BBoxAcc)) == cudaSuccess &&
-            cudaMalloc((void**)&h->d_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMallocHost((void**)&h->h_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMalloc((void**)&h->d_barrier, 2 * sizeof(unsigned)) == cudaSuccess &&
+  bool ok = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; ok && k < 2; k++) {
+    Scratch& S = h->sc[k];
+    S.c = h->c; S.c.own_stream = false; S.c.launches = 0;
+    if (k == 1) S.c.stream = h->stream2;
+    ok = cudaMalloc((void**)&S.d_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+         cudaMallocHost((void**)&S.h_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+         cudaMalloc((void**)&S.d_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMallocHost((void**)&S.h_u32, 8 * sizeof(uint32_t)) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc((void**)&h->d_barrier, 2 * sizeof(unsigned)) == cudaSuccess &&
             cudaMalloc((void**)&h->d_m, sizeof(int)) == cudaSuccess &&
             cudaHostAlloc((void**)&h->h_sums, 32 * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
             cudaHostGetDevicePointer((void**)&h->d_sums, h->h_sums, 0) == cudaSuccess &&
@@ -160,7 +186,10 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
             cudaMallocHost((void**)&h->h_result, sizeof(OuterResult)) == cudaSuccess;
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned)) == cudaSuccess;
-  if (ok) { bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_acc); ok = cudaStreamSynchronize(h->c.stream) == cudaSuccess; }
+  if (ok) {
+    for (int k = 0; k < 2; k++) bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->sc[k].d_acc);
+    ok = cudaStreamSynchronize(h->c.stream) == cudaSuccess;
+  }
   if (!ok) {
     set_error("lb_gicp_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -191,10 +220,12 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   return LB_OK;
 }
 
-// Upload a caller cloud and build its voxel-hash index (K2).
-int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off,
-                int mem, const char* what) {
-  Ctx& c = h->c;
+// Phase 1 (inside set_source / set_target, synchronous because the caller's buffer is only borrowed for the
+// duration of the call): upload, gather into packed float4 + bounding box in one kernel, choose the grid.
+int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, size_t stride, size_t xyz_off,
+                 ptrdiff_t normal_off, int mem, const char* what) {
+  Scratch& S = h->sc[slot];
+  Ctx& c = S.c;
   if (!pts) { set_error("%s: null cloud", what); return LB_ERR_INVALID_ARG; }
   if (n > 0x7ffffff0ull) { set_error("%s: too many points", what); return LB_ERR_INVALID_ARG; }
   if ((stride & 3u) || (xyz_off & 3u) || xyz_off + 12 > stride || (normal_off >= 0 && ((normal_off & 3) || (size_t)normal_off + 12 > stride))) {
@@ -204,26 +235,28 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
   LB_CUDA(cudaSetDevice(c.device));
   ScopedKernelTime kt(h, "index_build");
   const uint32_t N = (uint32_t)n;
+  cl.valid = false; cl.cov_valid = false; cl.index_dirty = false;
   const uint8_t* d_src = (const uint8_t*)pts;
   if (mem == LB_MEM_HOST) {
-    LB_TRY(h->stage.ensure(n * stride));
-    LB_CUDA(cudaMemcpyAsync(h->stage.p, pts, n * stride, cudaMemcpyHostToDevice, c.stream));
-    d_src = h->stage.p;
+    LB_TRY(S.stage.ensure(n * stride));
+    LB_CUDA(cudaMemcpyAsync(S.stage.p, pts, n * stride, cudaMemcpyHostToDevice, c.stream));
+    d_src = S.stage.p;
   }
   LB_TRY(cl.raw.ensure(n)); LB_TRY(cl.pts.ensure(n));
   if (normal_off >= 0) LB_TRY(cl.nrm.ensure(n));
   gather_cloud_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_src, N, (uint32_t)stride, (uint32_t)xyz_off, (int)normal_off,
-                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr, h->d_acc);
+                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr, S.d_acc);
   c.launches += 1;
-  LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaMemcpyAsync(S.h_acc, S.d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
+  bbox_init_kernel<<<1, 32, 0, c.stream>>>(S.d_acc);   // accumulator clean for the next upload
+  c.launches += 1;
   LB_CUDA(cudaStreamSynchronize(c.stream));
-  if (h->h_acc->count != N) {
-    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);   // leave the accumulator clean for the next build
-    set_error("%s: cloud holds %u non-finite points; GICP inputs must be dense (PCL kd-tree precondition)", what, N - h->h_acc->count);
+  if (S.h_acc->count != N) {
+    set_error("%s: cloud holds %u non-finite points; GICP inputs must be dense (PCL kd-tree precondition)", what, N - S.h_acc->count);
     return LB_ERR_INVALID_ARG;
   }
   float mn[3], mx[3];
-  for (int d = 0; d < 3; d++) { mn[d] = ord2f(h->h_acc->mn[d]); mx[d] = ord2f(h->h_acc->mx[d]); }
+  for (int d = 0; d < 3; d++) { mn[d] = ord2f(S.h_acc->mn[d]); mx[d] = ord2f(S.h_acc->mx[d]); }
   float ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
 
   auto make_geom = [&](float cell) {
@@ -242,7 +275,6 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
     }
   };
 
-  LB_TRY(h->keys.ensure(n));
   GridGeom g;
   float cell = h->P.index_cell_size;
   if (cell > 0.f) {
@@ -262,20 +294,21 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
     bool reuse = cl.auto_cell > 0.f && (double)N > 0.7 * (double)cl.auto_n && (double)N < 1.3 * (double)cl.auto_n &&
                  diag > 0.7 * cl.auto_diag && diag < 1.3 * cl.auto_diag;
     if (reuse) { cell = cl.auto_cell; g = make_geom(cell); }
+    LB_TRY(S.keys.ensure(n));
     for (int round = 0; round < 4 && !reuse; round++) {
       g = make_geom(cell);
       size_t nc = (size_t)g.nx * g.ny * g.nz;
-      LB_TRY(h->cell_cnt.ensure(nc + 1));
-      LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (nc + 1) * sizeof(uint32_t), c.stream));
-      LB_CUDA(cudaMemsetAsync(h->d_u32, 0, sizeof(uint32_t), c.stream));
-      grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p, nullptr);
-      grid_occupancy_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->keys.p, N, h->cell_cnt.p, h->d_u32);
+      LB_TRY(S.cell_cnt.ensure(nc + 1));
+      LB_CUDA(cudaMemsetAsync(S.cell_cnt.p, 0, (nc + 1) * sizeof(uint32_t), c.stream));
+      LB_CUDA(cudaMemsetAsync(S.d_u32, 0, sizeof(uint32_t), c.stream));
+      grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, S.keys.p, nullptr);
+      grid_occupancy_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(S.keys.p, N, S.cell_cnt.p, S.d_u32);
       c.launches += 2;
-      LB_CUDA(cudaMemcpyAsync(h->h_u32, h->d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+      LB_CUDA(cudaMemcpyAsync(S.h_u32, S.d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
       LB_CUDA(cudaStreamSynchronize(c.stream));
-      double occ = (double)N / (double)(h->h_u32[0] ? h->h_u32[0] : 1);
+      double occ = (double)N / (double)(S.h_u32[0] ? S.h_u32[0] : 1);
       if (occ >= target / 2 && occ <= target * 2) break;
-      if (N <= 8 || h->h_u32[0] <= 1) break;
+      if (N <= 8 || S.h_u32[0] <= 1) break;
       double scale = sqrt(target / occ);
       if (scale > 4) scale = 4;
       if (scale < 0.25) scale = 0.25;
@@ -285,46 +318,91 @@ int build_cloud(lb_gicp* h, Cloud& cl, const void* pts, size_t n, size_t stride,
   }
   cl.geom = g;
   cl.ncells = (size_t)g.nx * g.ny * g.nz;
-  int key_bits = 1;
-  while (key_bits < 32 && (1ull << key_bits) < (uint64_t)cl.ncells) key_bits++;
-  LB_TRY(h->cell_cnt.ensure(cl.ncells + 1));
-  LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
-  LB_CUDA(cudaMemsetAsync(h->cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
-  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, g, h->keys.p, h->d_acc);
-  c.launches++;
-  uint32_t *sk = nullptr, *sv = nullptr;
-  LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));
-  grid_reorder_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, sk, sv, N, cl.pts.p, h->cell_cnt.p);
-  c.launches++;
-  LB_TRY(exclusive_scan_u32(c, h->scan, h->cell_cnt.p, cl.cell_start.p, cl.ncells + 1, nullptr));
-  LB_CUDA(cudaGetLastError());
   cl.n = n;
   cl.valid = true;
   cl.has_normals = normal_off >= 0;
   cl.cov_valid = false;
+  cl.index_dirty = true;
   cl.generation = ++h->gen_counter;
   return LB_OK;
 }
 
-int compute_covariances(lb_gicp* h, Cloud& cl, bool recompute) {
-  Ctx& c = h->c;
+// Phase 2 (asynchronous, on the slot's stream): cell keys, stable sort, cell-contiguous copy, CSR offsets.
+int finish_index(lb_gicp* h, Cloud& cl, int slot) {
+  if (!cl.index_dirty) return LB_OK;
+  Scratch& S = h->sc[slot];
+  Ctx& c = S.c;
+  const uint32_t N = (uint32_t)cl.n;
+  int key_bits = 1;
+  while (key_bits < 32 && (1ull << key_bits) < (uint64_t)cl.ncells) key_bits++;
+  LB_TRY(S.keys.ensure(cl.n));
+  LB_TRY(S.cell_cnt.ensure(cl.ncells + 1));
+  LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
+  LB_CUDA(cudaMemsetAsync(S.cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
+  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, cl.geom, S.keys.p, nullptr);
+  c.launches++;
+  uint32_t *sk = nullptr, *sv = nullptr;
+  LB_TRY(radix_sort_pairs(c, S.sort, S.keys.p, nullptr, cl.n, key_bits, &sk, &sv));
+  grid_reorder_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, sk, sv, N, cl.pts.p, S.cell_cnt.p);
+  c.launches++;
+  LB_TRY(exclusive_scan_u32(c, S.scan, S.cell_cnt.p, cl.cell_start.p, cl.ncells + 1, nullptr));
+  LB_CUDA(cudaGetLastError());
+  cl.index_dirty = false;
+  return LB_OK;
+}
+
+// Build whatever is missing (indices, covariances) for both clouds: the target pipeline runs on the second
+// stream, concurrently with the source pipeline on the handle's stream (fork / join with events).
+int prepare_clouds(lb_gicp* h, bool need_cov, bool src_knn, bool tgt_knn);
+
+int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
+  Ctx& c = h->sc[slot].c;
   const uint32_t N = (uint32_t)cl.n;
   LB_TRY(cl.cov.ensure(6 * cl.n));
-  ScopedKernelTime kt(h, "knn_cov");
   if (!recompute && cl.has_normals) {
     normal_cov_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.pts.p, cl.nrm.p, N, h->P.gicp_epsilon, cl.cov.p);
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    // warp-per-query k-NN (candidates staged in shared memory, exact top-k by k rounds of warp-min)
-    int blocks = cdiv(N, KW_WARPS);
-    int max_blocks = c.sm_count * 4;
-    if (blocks > max_blocks) blocks = max_blocks;
-    knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    static int variant = -1;   // tuning aid: LB_KNN=warp selects the warp-per-query kernel (default: quad-per-query)
+    if (variant < 0) { const char* e = getenv("LB_KNN"); variant = (e && !strcmp(e, "warp")) ? 1 : 0; }
+    if (variant == 1) {
+      int blocks = cdiv(N, KW_WARPS);
+      int max_blocks = c.sm_count * 4;
+      if (blocks > max_blocks) blocks = max_blocks;
+      knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
+    } else {
+      const int no_cap = 1 << 30;
+      if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr);
+      else knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr);
+    }
   }
   c.launches++;
   LB_CUDA(cudaGetLastError());
   cl.cov_valid = true;
+  return LB_OK;
+}
+
+int prepare_clouds(lb_gicp* h, bool need_cov, bool src_knn, bool tgt_knn) {
+  Ctx& c = h->c;
+  bool tgt_work = h->tgt.valid && (h->tgt.index_dirty || (need_cov && !h->tgt.cov_valid));
+  bool src_work = h->src.valid && (h->src.index_dirty || (need_cov && !h->src.cov_valid));
+  if (!tgt_work && !src_work) return LB_OK;
+  ScopedKernelTime kt(h, "knn_cov");
+  if (tgt_work) {
+    LB_CUDA(cudaEventRecord(h->ev_fork, c.stream));
+    LB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    LB_TRY(finish_index(h, h->tgt, 1));
+    if (need_cov && !h->tgt.cov_valid) LB_TRY(compute_covariances(h, h->tgt, 1, tgt_knn));   // target first, gicp.hpp:420-432
+  }
+  if (src_work) {
+    LB_TRY(finish_index(h, h->src, 0));
+    if (need_cov && !h->src.cov_valid) LB_TRY(compute_covariances(h, h->src, 0, src_knn));
+  }
+  if (tgt_work) {
+    LB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+    LB_CUDA(cudaStreamWaitEvent(c.stream, h->ev_join, 0));
+  }
   return LB_OK;
 }
 
@@ -450,15 +528,13 @@ int lb_gicp_destroy(lb_gicp* h) {
   cudaSetDevice(h->c.device);
   cudaStreamSynchronize(h->c.stream);
   h->src.release(); h->tgt.release();
-  h->stage.release(); h->keys.release(); h->cell_cnt.release();
-  h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
-  h->sort.scan.sums.release(); h->scan.sums.release();
+  cudaStreamSynchronize(h->stream2);
+  h->sc[0].release(); h->sc[1].release();
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   h->src_work.release(); h->corr.release(); h->M.release(); h->slots.release();
   h->io.release(); h->io_idx.release(); h->io_d2.release();
-  if (h->d_acc) cudaFree(h->d_acc);
-  if (h->h_acc) cudaFreeHost(h->h_acc);
-  if (h->d_u32) cudaFree(h->d_u32);
-  if (h->h_u32) cudaFreeHost(h->h_u32);
   if (h->d_barrier) cudaFree(h->d_barrier);
   if (h->d_debug) cudaFree(h->d_debug);
   if (h->h_debug) cudaFreeHost(h->h_debug);
@@ -498,14 +574,14 @@ int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
     set_error("lb_gicp_set_source: invalid or empty point cloud dataset given");
     return LB_ERR_EMPTY_SOURCE;
   }
-  return build_cloud(h, h->src, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
+  return upload_cloud(h, h->src, 0, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
 }
 
 int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem,
                        uint64_t* generation) {
   if (!h) { set_error("lb_gicp_set_target: null handle"); return LB_ERR_INVALID_ARG; }
   if (n == 0) { set_error("lb_gicp_set_target: empty target cloud"); return LB_ERR_NO_TARGET; }
-  int s = build_cloud(h, h->tgt, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
+  int s = upload_cloud(h, h->tgt, 1, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
   if (s == LB_OK && generation) *generation = h->tgt.generation;
   return s;
 }
@@ -540,8 +616,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   for (int i = 0; i < 16; i++) guess[i] = guess_in ? guess_in[i] : ((i % 5 == 0) ? 1.f : 0.f);
 
   LB_CUDA(cudaEventRecord(h->ev[0], c.stream));
-  if (!h->tgt.cov_valid) LB_TRY(compute_covariances(h, h->tgt, tgt_knn));   // target first, gicp.hpp:420-432
-  if (!h->src.cov_valid) LB_TRY(compute_covariances(h, h->src, src_knn));
+  LB_TRY(prepare_clouds(h, true, src_knn, tgt_knn));
   LB_CUDA(cudaEventRecord(h->ev[1], c.stream));
 
   const uint32_t N = (uint32_t)h->src.n;
@@ -644,12 +719,13 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
   if ((stride & 3u) || stride < 12) { set_error("lb_gicp_nn_target: bad stride"); return LB_ERR_INVALID_ARG; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
+  LB_TRY(prepare_clouds(h, false, false, false));
   const uint32_t N = (uint32_t)n;
   const uint8_t* dq = (const uint8_t*)xyz; int32_t* di = idx; float* dd = d2;
   if (mem == LB_MEM_HOST) {
-    LB_TRY(h->stage.ensure(n * stride)); LB_TRY(h->io_idx.ensure(n)); LB_TRY(h->io_d2.ensure(n));
-    LB_CUDA(cudaMemcpyAsync(h->stage.p, xyz, n * stride, cudaMemcpyHostToDevice, c.stream));
-    dq = h->stage.p; di = h->io_idx.p; dd = h->io_d2.p;
+    LB_TRY(h->io.ensure(n * stride)); LB_TRY(h->io_idx.ensure(n)); LB_TRY(h->io_d2.ensure(n));
+    LB_CUDA(cudaMemcpyAsync(h->io.p, xyz, n * stride, cudaMemcpyHostToDevice, c.stream));
+    dq = h->io.p; di = h->io_idx.p; dd = h->io_d2.p;
   }
   nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd);
   c.launches++;
@@ -669,6 +745,7 @@ int lb_gicp_fitness(lb_gicp* h, const float* T_in, double max_range, double* sco
   if (!T_in && !h->have_result) { set_error("lb_gicp_fitness: no align() result yet"); return LB_ERR_NO_ALIGN; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
+  LB_TRY(prepare_clouds(h, false, false, false));
   const uint32_t N = (uint32_t)h->src.n;
   int nb = cdiv(N, 128);
   LB_TRY(h->io.ensure((size_t)nb * 2 * sizeof(double)));
@@ -712,7 +789,11 @@ int lb_gicp_cloud_size(lb_gicp* h, int which, size_t* n) {
   *n = cl.valid ? cl.n : 0;
   return LB_OK;
 }
-int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) { if (!h || !n) return LB_ERR_INVALID_ARG; *n = h->c.launches; return LB_OK; }
+int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) {
+  if (!h || !n) return LB_ERR_INVALID_ARG;
+  *n = h->c.launches + h->sc[0].c.launches + h->sc[1].c.launches;
+  return LB_OK;
+}
 
 int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches) {
   if (!h || !name || !ms_avg) return LB_ERR_INVALID_ARG;
