@@ -152,9 +152,15 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
                                                 float qz, int sub, QuadList<K>& L) {
   int z0 = imax_(cz - r, 0), z1 = imin_(cz + r, g.nz - 1);
   int y0 = imax_(cy - r, 0), y1 = imin_(cy + r, g.ny - 1);
+  // r <= 1: the 4 lanes split the POINTS of every run (64-byte coalesced reads of dense cells);
+  // r >= 2: the lanes split the ROWS (shells of sparse neighbourhoods are mostly empty rows, whose cost is the
+  //         dependent cell_start look-ups: four of them now overlap)
+  const bool split_rows = r >= 2;
+  int row = 0;
   for (int z = z0; z <= z1; z++) {
     bool zface = (iabs_(z - cz) == r);
-    for (int y = y0; y <= y1; y++) {
+    for (int y = y0; y <= y1; y++, row++) {
+      if (split_rows && (row & 3) != sub) continue;
       bool face = zface || (iabs_(y - cy) == r);
       int base = (z * g.ny + y) * g.nx;
       int nseg = face ? 1 : 2;
@@ -164,7 +170,7 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
         else { xa = xb = (k == 0) ? cx - r : cx + r; if (xa < 0 || xa >= g.nx) continue; }
         if (xa > xb) continue;
         uint32_t s = g.cell_start[base + xa], e = g.cell_start[base + xb + 1];
-        for (uint32_t i = s + sub; i < e; i += 4) {
+        for (uint32_t i = s + (split_rows ? 0 : sub); i < e; i += (split_rows ? 1 : 4)) {
           f4 p = g.pts[i];
           L.push(dist2(qx, qy, qz, p.x, p.y, p.z), float_to_bits(p.w), (int)i);
         }
@@ -194,6 +200,12 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
   if (r1 > ring_cap) r1 = ring_cap;   // sparse neighbourhoods are finished by knn_cov_tail_kernel (a warp per query)
   for (int r = r0; r <= r1; r++) {
     quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L);
+    {
+      int total = L.cnt;
+      total += __shfl_xor_sync(qmask, total, 1);
+      total += __shfl_xor_sync(qmask, total, 2);
+      if (total < k && r < r1) continue;   // not even k candidates yet: next shell
+    }
     // K-round merge of the four sorted lists
     int p = 0, found = 0;
     float kth = 3.0e38f;
@@ -626,11 +638,18 @@ __device__ __forceinline__ bool slot_try(const SlotWord* p, unsigned long long e
 // round trip when nobody is late); the values land in a shared matrix and warp w then sums rows e = w,
 // w + nwarps, ... lane-strided + shuffle tree.  out[e] (shared) valid after the trailing CTA barrier.
 constexpr int AL_MAXCTA = 160;
+constexpr long long AL_POLL_DELAY = 700;   // cycles
 template <int NV, int THREADS>
 __device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, unsigned long long epoch,
                                               double* mat /*[NV][AL_MAXCTA] shared*/, double* out /*shared [NV]*/) {
   const int npairs = ncta * NV;
   constexpr int MAXP = (AL_MAXCTA * NV + THREADS - 1) / THREADS;
+  // every CTA publishes at about the same time and a publication needs ~0.5 us to land in L2: polling at once
+  // wastes a full ~1 us round trip on words that are not there yet, so hold the first poll back a little
+  {
+    const long long t_start = clock64();
+    while (clock64() - t_start < AL_POLL_DELAY) {}
+  }
   unsigned pending = 0;
 #pragma unroll
   for (int k = 0; k < MAXP; k++)
