@@ -373,8 +373,14 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
       knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
     } else {
       const int no_cap = 1 << 30;
-      if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr);
-      else knn_cov_quad_kernel<32><<<cdiv(4ll * N, 128), 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr);
+      static int split_from = -1, lazy_merge = -1, qthreads = 128;
+      if (split_from < 0) {
+        const char* e = getenv("LB_QSPLIT"); split_from = e ? atoi(e) : 2;
+        e = getenv("LB_QMERGE"); lazy_merge = e ? atoi(e) : 1;
+        e = getenv("LB_QTHREADS"); qthreads = e ? atoi(e) : 128;
+      }
+      if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
+      else knn_cov_quad_kernel<32><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
     }
   }
   c.launches++;
@@ -727,8 +733,18 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
     LB_CUDA(cudaMemcpyAsync(h->io.p, xyz, n * stride, cudaMemcpyHostToDevice, c.stream));
     dq = h->io.p; di = h->io_idx.p; dd = h->io_d2.p;
   }
-  nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd);
-  c.launches++;
+  {
+    ScopedKernelTime kt(h, "nn_query");
+    nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+    c.launches++;
+  }
+  if (h->timing) {   // profiling aid: mean number of target points visited per query -> h_debug[4], h_debug[5]
+    LB_CUDA(cudaMemsetAsync(h->d_debug + 4, 0, sizeof(long long), c.stream));
+    nn_count_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, 3.0e38f,
+                                                        (unsigned long long*)(h->d_debug + 4));
+    LB_CUDA(cudaMemcpyAsync(h->h_debug + 4, h->d_debug + 4, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    h->h_debug[5] = (long long)N;
+  }
   if (mem == LB_MEM_HOST) {
     LB_CUDA(cudaMemcpyAsync(idx, di, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
     LB_CUDA(cudaMemcpyAsync(d2, dd, n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));

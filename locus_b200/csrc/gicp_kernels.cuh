@@ -149,13 +149,13 @@ struct QuadList {
 
 template <int K>
 __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int cy, int cz, int r, float qx, float qy,
-                                                float qz, int sub, QuadList<K>& L) {
+                                                float qz, int sub, QuadList<K>& L, int split_from) {
   int z0 = imax_(cz - r, 0), z1 = imin_(cz + r, g.nz - 1);
   int y0 = imax_(cy - r, 0), y1 = imin_(cy + r, g.ny - 1);
   // r <= 1: the 4 lanes split the POINTS of every run (64-byte coalesced reads of dense cells);
   // r >= 2: the lanes split the ROWS (shells of sparse neighbourhoods are mostly empty rows, whose cost is the
   //         dependent cell_start look-ups: four of them now overlap)
-  const bool split_rows = r >= 2;
+  const bool split_rows = r >= split_from;
   int row = 0;
   for (int z = z0; z <= z1; z++) {
     bool zface = (iabs_(z - cz) == r);
@@ -182,7 +182,7 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
 template <int K>
 __global__ void __launch_bounds__(128)
 knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int ring_cap,
-                    uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count) {
+                    uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count, int split_from, int lazy_merge) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t s = t >> 2;
   const int sub = threadIdx.x & 3;
@@ -199,8 +199,8 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
   bool done = false;
   if (r1 > ring_cap) r1 = ring_cap;   // sparse neighbourhoods are finished by knn_cov_tail_kernel (a warp per query)
   for (int r = r0; r <= r1; r++) {
-    quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L);
-    {
+    quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L, split_from);
+    if (lazy_merge) {
       int total = L.cnt;
       total += __shfl_xor_sync(qmask, total, 1);
       total += __shfl_xor_sync(qmask, total, 2);
@@ -572,14 +572,48 @@ transform_kernel(const f4* __restrict__ raw, const f4* __restrict__ nrm, uint32_
 // exact 1-NN of arbitrary queries in a grid (PointCloudLocalization.cc:327-336)
 __global__ void __launch_bounds__(128)
 nn_query_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, int32_t* __restrict__ idx,
-                float* __restrict__ d2) {
+                float* __restrict__ d2, float max_d2) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride);
   int bo; float bd;
-  int s = nn1(g, p[0], p[1], p[2], 3.0e38f, bo, bd);
+  int s = nn1(g, p[0], p[1], p[2], max_d2, bo, bd);
   idx[i] = (s >= 0) ? bo : -1;
   d2[i] = bd;
+}
+
+// candidate-scan statistics of the same search (profiling aid for the NN roofline, SURVEY 8d: B_nn = Nq (16 + 16 c + 8)):
+// counts the target points a query visits.
+__global__ void __launch_bounds__(128)
+nn_count_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, float max_d2,
+                unsigned long long* __restrict__ total) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned cnt = 0;
+  if (i < n) {
+    const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride);
+    float qx = p[0], qy = p[1], qz = p[2];
+    int cx, cy, cz; float minfrac;
+    query_cell(g, qx, qy, qz, cx, cy, cz, minfrac);
+    int r0, r1;
+    ring_range(g, cx, cy, cz, r0, r1);
+    float bd2 = max_d2; bool found = false; int bi = 0x7fffffff;
+    for (int r = r0; r <= r1; r++) {
+      if (r > r0 || r0 > 0) {
+        float lb2 = ring_bound2(g, r - 1, minfrac);
+        if (lb2 >= max_d2) break;
+        if (found && bd2 < lb2) break;
+      }
+      visit_shell(g, cx, cy, cz, r, [&](float x, float y, float z, int oi, int si) {
+        cnt++;
+        float d = dist2(qx, qy, qz, x, y, z);
+        if (!found) { if (d < max_d2) { found = true; bd2 = d; bi = oi; } }
+        else if (better(d, oi, bd2, bi)) { bd2 = d; bi = oi; }
+      });
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
 }
 
 // ------------------------------------------------------------------ block / grid reductions
