@@ -375,7 +375,7 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
       const int no_cap = 1 << 30;
       static int split_from = -1, lazy_merge = -1, qthreads = 128;
       if (split_from < 0) {
-        const char* e = getenv("LB_QSPLIT"); split_from = e ? atoi(e) : 2;
+        const char* e = getenv("LB_QSPLIT"); split_from = e ? atoi(e) : 99;
         e = getenv("LB_QMERGE"); lazy_merge = e ? atoi(e) : 1;
         e = getenv("LB_QTHREADS"); qthreads = e ? atoi(e) : 128;
       }

@@ -174,3 +174,63 @@ def test_full_size_c2_pipeline(oracle):
     dt, dr = F.pose_delta(gt, g.getFinalTransformation())
     assert dt < 0.02 and dr < 0.005
     assert g.getFitnessScore() < oracle.fitness(f1, f0, np.eye(4))
+
+
+def _submap(n, seed):
+    """voxel-merged-submap-like cloud: n surface points of a 60 x 45 x 9 m hall + clutter"""
+    return F.random_scene(n, seed, extent=(30.0, 22.5, 4.5))
+
+
+def test_full_size_c3_scan_to_submap(oracle):
+    """BASELINE config 3 at full size: 30 k-point scan vs 500 k-point submap, localization settings
+    (corr 0.2... here 0.5 m, tf_eps 1e-5, 50 inner): GPU pose vs the oracle, and vs the known offset."""
+    tgt = _submap(500_000, 31)
+    rng = np.random.default_rng(3)
+    sub = tgt[rng.choice(len(tgt), 30_000, replace=False)] + rng.normal(0, 0.01, (30_000, 3)).astype(np.float32)
+    Tg = F.se3([0.08, -0.05, 0.02], [0.004, -0.006, 0.01])
+    src = ((sub.astype(np.float64) - Tg[:3, 3]) @ Tg[:3, :3]).astype(np.float32)      # src = Tg^-1 * sub
+    prm = oracle.default_params(transformation_epsilon=1e-5, corr_dist_threshold=0.5, max_iterations=50,
+                                max_inner_iterations=50, num_threads=16)
+    r = oracle.gicp_align(src, tgt, prm)
+    g = _mk(prm, 0)
+    g.setInputSource(src); g.setInputTarget(tgt)
+    res = g.align()
+    dt, dr = F.pose_delta(r["T"], g.getFinalTransformation())
+    assert dt <= TOL_T and dr <= TOL_R, (dt, dr)
+    assert res.iterations == r["iterations"] and res.n_correspondences == r["n_corr"]
+    dt, dr = F.pose_delta(Tg, g.getFinalTransformation())
+    assert dt < 5e-3 and dr < 2e-3
+    # the submap index is reused by the next scan (only the source changes): same answer
+    g.setInputSource(src)
+    g.align()
+    assert np.array_equal(np.array(res.final_transformation, dtype=np.float32).reshape(4, 4), g.getFinalTransformation())
+
+
+def test_full_size_c5_dense_properties():
+    """BASELINE config 5 shape: 200 k-point scan vs 10 M-point map.  The oracle cannot finish this in seconds, so
+    size-independent properties: exact 1-NN against brute force on sampled queries, recovered pose close to the
+    known offset, fitness decreases, result independent of the execution mode."""
+    import locus_b200
+    tgt = F.random_scene(10_000_000, 5, extent=(100.0, 75.0, 15.0))
+    rng = np.random.default_rng(11)
+    sub = tgt[rng.choice(len(tgt), 200_000, replace=False)] + rng.normal(0, 0.005, (200_000, 3)).astype(np.float32)
+    Tg = F.se3([0.05, 0.03, -0.01], [0.002, 0.003, -0.004])
+    src = ((sub.astype(np.float64) - Tg[:3, 3]) @ Tg[:3, :3]).astype(np.float32)
+    g = locus_b200.GicpB200()
+    g.setTransformationEpsilon(1e-5); g.setMaxCorrespondenceDistance(0.3); g.setMaximumIterations(50)
+    g.setMaximumOptimizerIterations(50)
+    g.setInputSource(src); g.setInputTarget(tgt)
+    q = sub[:64]
+    idx, d2 = g.nearestTarget(q)
+    for i in range(0, 64, 8):
+        dd = (tgt - q[i]) ** 2
+        d = (dd[:, 0] + dd[:, 1]) + dd[:, 2]
+        assert d2[i] == d.min() and idx[i] == int(np.flatnonzero(d == d.min())[0])
+    res = g.align()
+    assert res.converged
+    dt, dr = F.pose_delta(Tg, g.getFinalTransformation())
+    assert dt < 5e-3 and dr < 1e-3, (dt, dr)
+    T_p = g.getFinalTransformation().copy()
+    g.setExecution(1)
+    g.align()
+    assert np.array_equal(T_p, g.getFinalTransformation())

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""NN-search kernel on the HBM-resident configuration (BASELINE.json config 5 shape): 200 k queries against a
+10 M-point map.  Reports the achieved candidate-scan bandwidth  B_nn = Nq * (16 + 16*c + 8)  bytes  (SURVEY.md
+8d; c = mean number of target points a query visits, counted on the device) over the CUDA-event duration of
+nn_query_kernel, as a fraction of the measured HBM copy peak (MEASURED_PEAKS.json).
+
+    python tools/nn_roofline.py [--map 10000000] [--queries 200000] [--reps 5]
+
+Run it under ncu for dram__bytes:  ncu --set full -k regex:nn_query_kernel -c 2 -o gpurun_out/prof_nn python tools/nn_roofline.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--map", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=200_000)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sorted-queries", type=int, default=1, help="1: queries in spatial (cell) order like a cell-sorted source")
+    a = ap.parse_args()
+    import locus_b200
+    import fixtures as F
+    t0 = time.time()
+    # surface-like map: 10 M points on the walls of a 200 x 150 x 30 m hall (about the density of a voxel-merged submap)
+    tgt = F.random_scene(a.map, 5, extent=(100.0, 75.0, 15.0))
+    rng = np.random.default_rng(7)
+    q = (tgt[rng.integers(0, a.map, a.queries)] + rng.normal(0, 0.05, (a.queries, 3))).astype(np.float32)
+    if a.sorted_queries:
+        key = np.lexsort((np.floor(q[:, 0] / 0.5), np.floor(q[:, 1] / 0.5), np.floor(q[:, 2] / 0.5)))
+        q = np.ascontiguousarray(q[key])
+    t_gen = time.time() - t0
+    g = locus_b200.GicpB200(0)
+    t0 = time.time()
+    g.setInputTarget(tgt)
+    idx, d2 = g.nearestTarget(q)            # first call builds the index lazily
+    t_build = time.time() - t0
+    g.resetKernelTimes(True)
+    for _ in range(a.reps):
+        idx, d2 = g.nearestTarget(q)
+    ms, n = g.kernelTime("nn_query")
+    cand_total = g.kernelTime("debug4")[0]
+    c = cand_total / float(a.queries)
+    g.resetKernelTimes(False)
+    bytes_nn = a.queries * (16.0 + 16.0 * c + 8.0)
+    peak = 6650.0; src = "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); src = "measured"
+    except Exception:
+        pass
+    ach = bytes_nn / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    # exactness spot check against brute force on a few queries
+    chk = rng.integers(0, a.queries, 16)
+    ok = True
+    for i in chk:
+        dd = ((tgt - q[i]) ** 2)
+        d = (dd[:, 0] + dd[:, 1]) + dd[:, 2]
+        j = int(np.argmin(d))
+        ok = ok and (d2[i] == d[j])
+    print(json.dumps({"workload": "C5-shaped NN search", "map_points": a.map, "queries": a.queries,
+                      "sorted_queries": bool(a.sorted_queries), "kernel_ms": ms, "launches": int(n),
+                      "candidates_per_query": c, "algorithmic_bytes": bytes_nn, "achieved_gbs": ach,
+                      "peak_gbs": peak, "peak_source": src, "frac": ach / peak, "queries_per_s": a.queries / (ms * 1e-3) if ms else 0,
+                      "index_build_incl_upload_s": t_build, "gen_s": t_gen, "brute_force_spot_check_ok": bool(ok)}))
+
+
+if __name__ == "__main__":
+    main()
