@@ -257,6 +257,9 @@ def main():
     if os.environ.get("LB_CELL"):            # tuning aid: fixed voxel-hash cell size instead of the automatic one
         gicp.setIndexCellSize(float(os.environ["LB_CELL"]))
         workload["index_cell_size"] = float(os.environ["LB_CELL"])
+    if os.environ.get("LB_OPT"):             # tuning aid: 1 = Gauss-Newton inner solve (north_star's 6x6 solve; not reference-exact)
+        gicp.setOptimizer(int(os.environ["LB_OPT"]))
+        workload["optimizer"] = "gauss-newton" if int(os.environ["LB_OPT"]) else workload["optimizer"]
     if os.environ.get("LB_EXEC"):
         gicp.setExecution(int(os.environ["LB_EXEC"]))
         workload["execution"] = "host-driven" if int(os.environ["LB_EXEC"]) else workload["execution"]

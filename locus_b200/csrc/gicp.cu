@@ -814,6 +814,8 @@ int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) {
 int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches) {
   if (!h || !name || !ms_avg) return LB_ERR_INVALID_ARG;
   *ms_avg = 0.f; if (launches) *launches = 0;
+  cudaStreamSynchronize(h->c.stream);
+  timers_collect(h);
   if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '7') {   // cycle counters of the last persistent align
     *ms_avg = (float)h->h_debug[name[5] - '0'];
     return LB_OK;
