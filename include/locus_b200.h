@@ -77,7 +77,10 @@ typedef enum lb_status {
 
 typedef enum lb_mem { LB_MEM_HOST = 0, LB_MEM_DEVICE = 1 } lb_mem;
 typedef enum lb_optimizer { LB_OPT_BFGS = 0, LB_OPT_GAUSS_NEWTON = 1 } lb_optimizer;
-typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1 } lb_execution;
+/* PERSISTENT: one kernel per align() -- a 16-CTA thread-block cluster runs the inner solve through distributed
+ * shared memory when the source has <= 32768 points, else the all-SM kernel; PERSISTENT_GRID forces the all-SM
+ * kernel; HOST_DRIVEN sequences one launch per objective evaluation from the host. */
+typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_GRID = 2 } lb_execution;
 
 #define LB_NO_NORMALS ((ptrdiff_t)-1)
 

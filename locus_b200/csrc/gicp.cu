@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "align_cluster.cuh"
 #include "gicp_kernels.cuh"
 
 namespace lb {
@@ -95,6 +96,9 @@ struct lb_gicp {
   DBuf<SlotWord> slots;
   unsigned long long epoch_base = 1ull << 20;
   long long* d_debug = nullptr; long long* h_debug = nullptr;
+  DBuf<SlotWord> cslots;           // cluster kernel: [CL_MAX_CTAS] hit-count words + [CL_CMD_WORDS] command words
+  bool cluster_ok = false;
+  int cluster_count = 0;           // clusters per launch (solver cluster + helpers)
   unsigned* d_barrier = nullptr;      // [2]: (unused), ticket of the host-driven objective kernel
   int* d_m = nullptr;
   double* h_sums = nullptr; double* d_sums = nullptr;        // mapped pinned [32]
@@ -210,6 +214,29 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   }
   memset(h->h_debug, 0, (16 + 2 * AL_MAXCTA) * sizeof(long long));
   cudaMemset(h->d_debug, 0, (16 + 2 * AL_MAXCTA) * sizeof(long long));
+  // thread-block-cluster variant of the persistent kernel: needs a non-portable cluster of 16 CTAs with
+  // 147 KB of dynamic shared memory each; fall back to the all-SM kernel when the device cannot host it
+  {
+    bool okc = cudaFuncSetAttribute(align_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+               cudaFuncSetAttribute(align_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterCache)) == cudaSuccess;
+    int ncl = 0;
+    if (okc) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CL_SIZE * 8); cfg.blockDim = dim3(AL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterCache);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      okc = cudaOccupancyMaxActiveClusters(&ncl, align_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1;
+    }
+    cudaGetLastError();
+    const char* e = getenv("LB_CLUSTER");
+    if (e && atoi(e) == 0) okc = false;
+    h->cluster_ok = okc;
+    h->cluster_count = okc ? (ncl > 9 ? 9 : ncl) : 0;
+    if (okc && (h->cslots.ensure(CL_MAX_CTAS + CL_CMD_WORDS) != LB_OK ||
+                cudaMemset(h->cslots.p, 0, (CL_MAX_CTAS + CL_CMD_WORDS) * sizeof(SlotWord)) != cudaSuccess))
+      h->cluster_ok = false;
+  }
   if (cudaFuncSetAttribute(knn_cov_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnWarpSmem)) != cudaSuccess) {
     set_error("lb_gicp_create: cannot reserve %zu bytes of shared memory", sizeof(KnnWarpSmem));
     delete h;
@@ -539,7 +566,7 @@ int lb_gicp_destroy(lb_gicp* h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  h->src_work.release(); h->corr.release(); h->M.release(); h->slots.release();
+  h->src_work.release(); h->corr.release(); h->M.release(); h->slots.release(); h->cslots.release();
   h->io.release(); h->io_idx.release(); h->io_d2.release();
   if (h->d_barrier) cudaFree(h->d_barrier);
   if (h->d_debug) cudaFree(h->d_debug);
@@ -646,18 +673,44 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     gicp_outer_loop(be, OP, guess, R);
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
   } else {
-    AlignArgs aa;
-    aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
     // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
     if ((h->epoch_base >> 32) != ((h->epoch_base + (1ull << 20)) >> 32) || (h->epoch_base & 0xffffffffull) == 0) {
       LB_CUDA(cudaMemsetAsync(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord), c.stream));
+      if (h->cslots.p) LB_CUDA(cudaMemsetAsync(h->cslots.p, 0, (CL_MAX_CTAS + CL_CMD_WORDS) * sizeof(SlotWord), c.stream));
       h->epoch_base = ((h->epoch_base >> 32) + 1) << 32 | (1ull << 20);
     }
-    aa.epoch_base = h->epoch_base; h->epoch_base += 1ull << 20;      // > collectives per align
-    aa.debug = h->timing ? h->d_debug : nullptr;
-    for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
-    void* args[] = {&aa};
-    {
+    const unsigned long long epoch_base = h->epoch_base;
+    h->epoch_base += 1ull << 20;      // > collectives per align
+    bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT && N <= (uint32_t)(CL_SIZE * CL_CAP);
+    bool launched = false;
+    if (use_cluster) {
+      ClusterArgs ka;
+      ka.c = ca; ka.gslots = h->cslots.p; ka.gcmd = h->cslots.p + CL_MAX_CTAS; ka.epoch_base = epoch_base;
+      ka.P = OP; ka.result = h->d_result; ka.debug = h->timing ? h->d_debug : nullptr;
+      for (int i = 0; i < 16; i++) ka.guess[i] = guess[i];
+      // helpers only pay off when there is enough NN work for them
+      int clusters = cdiv(N, CL_SIZE * 256);
+      if (clusters < 1) clusters = 1;
+      if (clusters > h->cluster_count) clusters = h->cluster_count;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CL_SIZE * clusters); cfg.blockDim = dim3(AL_THREADS);
+      cfg.dynamicSmemBytes = sizeof(ClusterCache); cfg.stream = c.stream;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+      cfg.attrs = at; cfg.numAttrs = 2;
+      ScopedKernelTime kt(h, "align_persistent");
+      cudaError_t e = cudaLaunchKernelEx(&cfg, align_cluster_kernel, ka);
+      if (e == cudaSuccess) { launched = true; c.launches++; }
+      else { cudaGetLastError(); h->cluster_ok = false; }   // e.g. cooperative + cluster launch refused: use the all-SM kernel from now on
+    }
+    if (!launched) {
+      AlignArgs aa;
+      aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
+      aa.epoch_base = epoch_base;
+      aa.debug = h->timing ? h->d_debug : nullptr;
+      for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
+      void* args[] = {&aa};
       ScopedKernelTime kt(h, "align_persistent");
       LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid_for(h, ca.n_src)), dim3(AL_THREADS), args, 0, c.stream));
       c.launches++;
@@ -735,7 +788,15 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
   }
   {
     ScopedKernelTime kt(h, "nn_query");
-    nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+    static int nnv = -1;   // tuning aid: LB_NN=thread selects the thread-per-query kernel
+    if (nnv < 0) { const char* e = getenv("LB_NN"); nnv = (e && !strcmp(e, "thread")) ? 0 : 1; }
+    if (nnv == 0) {
+      nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+    } else {
+      int blocks = cdiv(N, 8);
+      if (blocks > c.sm_count * 8) blocks = c.sm_count * 8;
+      nn_query_warp_kernel<<<blocks, 256, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+    }
     c.launches++;
   }
   if (h->timing) {   // profiling aid: mean number of target points visited per query -> h_debug[4], h_debug[5]

@@ -582,6 +582,112 @@ nn_query_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t 
   d2[i] = bd;
 }
 
+// Exact 1-NN, warp-per-query (the HBM-resident regime: big maps, many queries).  The rows of the probe block are
+// looked up by different lanes at once, then the candidate points of all rows are fetched FLATTENED: lane l takes
+// candidates l, l+32, ... of the concatenated runs, so every load instruction moves 32 independent 16-byte points
+// (512 contiguous bytes where the runs are dense).  Each lane keeps its best packed key (d2 bits << 32 | original
+// index); one 64-bit warp-min per shell decides.  First step = the whole 3x3x3 block (nine 3-cell runs).
+struct NnWarpSmem { uint32_t a0[32], a1[32]; int n0[32], off[33]; };
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other < v ? other : v;
+  }
+  return v;
+}
+
+// returns the best packed key (all lanes), 0xffff... when nothing is within max_d2
+__device__ __forceinline__ unsigned long long nn1_warp(const GridView& g, float qx, float qy, float qz, float max_d2,
+                                                      NnWarpSmem& w) {
+  const int lane = threadIdx.x & 31;
+  int cx, cy, cz; float minfrac;
+  query_cell(g, qx, qy, qz, cx, cy, cz, minfrac);
+  int r0, r1;
+  ring_range(g, cx, cy, cz, r0, r1);
+  unsigned long long best = 0xffffffffffffffffull;
+  const unsigned long long gate = ((unsigned long long)__float_as_uint(max_d2)) << 32;   // keys >= gate fail d2 < max_d2
+  bool first = true;
+  if (r0 > 1 && ring_bound2(g, r0 - 1, minfrac) >= max_d2) return 0xffffffffffffffffull;   // query far outside the grid
+  for (int r = (r0 <= 1 ? 1 : r0); r <= (r1 < 1 ? 1 : r1); r++) {
+    // rows of this step: the full (2r+1)^2 block when it is the first step with r == 1, else the shell of radius r;
+    // only rows that intersect the grid are enumerated
+    const bool block = first && r == 1;
+    first = false;
+    const int z0 = imax_(cz - r, 0), z1 = imin_(cz + r, g.nz - 1);
+    const int y0 = imax_(cy - r, 0), y1 = imin_(cy + r, g.ny - 1);
+    const int ny_c = y1 - y0 + 1;
+    const int nrows = (z1 >= z0 && y1 >= y0) ? (z1 - z0 + 1) * ny_c : 0;
+    for (int rowbase = 0; rowbase < nrows; rowbase += 32) {
+      uint32_t a0 = 0, a1 = 0; int n0 = 0, n1 = 0;
+      int j = rowbase + lane;
+      if (j < nrows) {
+        int z = z0 + j / ny_c, y = y0 + j % ny_c;
+        int base = (z * g.ny + y) * g.nx;
+        bool face = block || (iabs_(z - cz) == r) || (iabs_(y - cy) == r);
+        if (face) {
+          int xa = imax_(cx - r, 0), xb = imin_(cx + r, g.nx - 1);
+          if (xa <= xb) { a0 = g.cell_start[base + xa]; n0 = (int)(g.cell_start[base + xb + 1] - a0); }
+        } else {
+          int x0 = cx - r, x1 = cx + r;
+          if (x0 >= 0 && x0 < g.nx) { a0 = g.cell_start[base + x0]; n0 = (int)(g.cell_start[base + x0 + 1] - a0); }
+          if (x1 >= 0 && x1 < g.nx) { a1 = g.cell_start[base + x1]; n1 = (int)(g.cell_start[base + x1 + 1] - a1); }
+        }
+      }
+      int len = n0 + n1;
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) continue;
+      __syncwarp();
+      w.a0[lane] = a0; w.a1[lane] = a1; w.n0[lane] = n0; w.off[lane] = incl - len;
+      if (lane == 31) w.off[32] = total;
+      __syncwarp();
+      int cur = 0;
+      for (int idx = lane; idx < total; idx += 32) {
+        while (idx >= w.off[cur + 1]) cur++;
+        int local = idx - w.off[cur];
+        int nn0 = w.n0[cur];
+        uint32_t pi = (local < nn0) ? (w.a0[cur] + (uint32_t)local) : (w.a1[cur] + (uint32_t)(local - nn0));
+        f4 p = g.pts[pi];
+        unsigned long long key = ((unsigned long long)__float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z)) << 32) |
+                                 (unsigned)float_to_bits(p.w);
+        best = key < best ? key : best;
+      }
+    }
+    unsigned long long wbest = warp_min_u64(best);
+    float lb2 = ring_bound2(g, r, minfrac);
+    if (lb2 >= max_d2) { best = wbest; break; }
+    if (wbest < gate && __uint_as_float((unsigned)(wbest >> 32)) < lb2) { best = wbest; break; }
+    if (r == (r1 < 1 ? 1 : r1)) best = wbest;
+  }
+  best = warp_min_u64(best);
+  return best < gate ? best : 0xffffffffffffffffull;
+}
+
+__global__ void __launch_bounds__(256)
+nn_query_warp_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, int32_t* __restrict__ idx,
+                     float* __restrict__ d2, float max_d2) {
+  __shared__ NnWarpSmem sm[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * 8;
+  for (uint32_t i = blockIdx.x * 8 + wib; i < n; i += nwarps) {
+    const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride);
+    float qx = p[0], qy = p[1], qz = p[2];
+    unsigned long long best = nn1_warp(g, qx, qy, qz, max_d2, sm[wib]);
+    if (lane == 0) {
+      bool ok = best != 0xffffffffffffffffull;
+      idx[i] = ok ? (int32_t)(unsigned)(best & 0xffffffffull) : -1;
+      d2[i] = ok ? __uint_as_float((unsigned)(best >> 32)) : max_d2;
+    }
+  }
+}
+
 // candidate-scan statistics of the same search (profiling aid for the NN roofline, SURVEY 8d: B_nn = Nq (16 + 16 c + 8)):
 // counts the target points a query visits.
 __global__ void __launch_bounds__(128)
