@@ -49,6 +49,7 @@ struct ClusterShared {                 // static shared memory
   double mat[AL_MAXV * CL_SIZE];
   double cmd[CL_CMD_WORDS];
   double counts[CL_MAX_CTAS];
+  long long t_acc, t_sync, t_gather, n_coll;   // CTA 0 / thread 0 cycle counters (profiling aid)
 };
 
 struct ClusterArgs {
@@ -130,6 +131,8 @@ __device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const Cluster
   double acc[NV];
 #pragma unroll
   for (int e = 0; e < NV; e++) acc[e] = 0.0;
+  const bool prof = (blockIdx.x == 0 && threadIdx.x == 0);
+  const long long t0 = prof ? clock64() : 0;
   const int t = (int)threadIdx.x - 32;
   if (t >= 0 && t < CL_ACC) {
     const int cnt = sh.cnt;
@@ -143,7 +146,9 @@ __device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const Cluster
   }
   double tot = block_reduce<NV, CL_ACC_WARPS, 1>(acc, sh.red);
   if (threadIdx.x < NV) sh.xs[flip][threadIdx.x] = tot;
+  const long long t1 = prof ? clock64() : 0;
   cluster.sync();                                  // hardware cluster barrier: every CTA's partials are visible
+  const long long t2 = prof ? clock64() : 0;
   for (int pr = threadIdx.x; pr < CL_SIZE * NV; pr += blockDim.x) {
     const int r = pr / NV, e = pr - r * NV;
     const double* remote = cluster.map_shared_rank(&sh.xs[flip][e], r);
@@ -158,6 +163,7 @@ __device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const Cluster
   }
   flip ^= 1;
   __syncthreads();
+  if (prof) { const long long t3 = clock64(); sh.t_acc += t1 - t0; sh.t_sync += t2 - t1; sh.t_gather += t3 - t2; sh.n_coll++; }
 }
 
 // Backend of bfgs.h for the leader warp of a solver CTA (all 32 lanes call every method together).
@@ -300,6 +306,7 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
   }
 
   // ---- solver CTA
+  if (threadIdx.x == 0) { sh.t_acc = 0; sh.t_sync = 0; sh.t_gather = 0; sh.n_coll = 0; }
   if (threadIdx.x < 32) {
     ClusterBackend be(a, sh, cache, cluster, cmd_epoch, flip, rank);
     OuterResult r;
@@ -310,7 +317,10 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       *a.result = r;
-      if (a.debug) a.debug[0] = clock64() - t_begin;
+      if (a.debug) {
+        a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_acc; a.debug[2] = sh.t_sync; a.debug[3] = sh.n_coll;
+        a.debug[6] = sh.t_gather;
+      }
     }
   } else {
     for (;;) {
