@@ -412,7 +412,7 @@ def main():
                          "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
                          "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms, "voxel_last_call_ms": vg.lastCallMs(),
                          "align_last_launch_cycles": {"total": dbg[0], "block_reduce_publish": dbg[1],
-                                                      "slot_wait_sum": dbg[2], "collectives": dbg[3], "gather": dbg6},
+                                                      "slot_wait_sum": dbg[2], "collectives": dbg[3], "leader_scalar_before_fdf": dbg6},
                          "wall_s_timed_region": wall}}
 
     if world == 1 and not args.no_cpu_baseline:

@@ -77,10 +77,11 @@ typedef enum lb_status {
 
 typedef enum lb_mem { LB_MEM_HOST = 0, LB_MEM_DEVICE = 1 } lb_mem;
 typedef enum lb_optimizer { LB_OPT_BFGS = 0, LB_OPT_GAUSS_NEWTON = 1 } lb_optimizer;
-/* PERSISTENT: one kernel per align() -- a 16-CTA thread-block cluster runs the inner solve through distributed
- * shared memory when the source has <= 32768 points, else the all-SM kernel; PERSISTENT_GRID forces the all-SM
- * kernel; HOST_DRIVEN sequences one launch per objective evaluation from the host. */
-typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_GRID = 2 } lb_execution;
+/* PERSISTENT: one cooperative kernel per align() (leader warp + worker warps per CTA, grid-wide all-reduce through
+ * L2); HOST_DRIVEN sequences one launch per objective evaluation from the host; PERSISTENT_CLUSTER runs the inner
+ * solve inside one 16-CTA thread-block cluster (all-reduce through distributed shared memory; sources <= 32768
+ * points, falls back to PERSISTENT otherwise) -- measured slower than PERSISTENT on B200, kept as an option. */
+typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_CLUSTER = 2 } lb_execution;
 
 #define LB_NO_NORMALS ((ptrdiff_t)-1)
 

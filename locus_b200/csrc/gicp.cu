@@ -681,7 +681,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     }
     const unsigned long long epoch_base = h->epoch_base;
     h->epoch_base += 1ull << 20;      // > collectives per align
-    bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT && N <= (uint32_t)(CL_SIZE * CL_CAP);
+    bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT_CLUSTER && N <= (uint32_t)(CL_SIZE * CL_CAP);
     bool launched = false;
     if (use_cluster) {
       ClusterArgs ka;

@@ -1010,7 +1010,7 @@ enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4 };
 struct AlignShared {
   int op;
   int m;
-  long long t_reduce, t_wait, n_coll;   // CTA 0 / thread 0 cycle counters
+  long long t_reduce, t_wait, n_coll, t_scalar, t_mark;   // CTA 0 / thread 0 cycle counters
   float T[12];
   double R[9];
   double D[27];
@@ -1047,7 +1047,7 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   slots_all_sum<NV, AL_THREADS>(buf, ncta, co.epoch, sh.mat, sh.bc);
   if (snap) a.debug[16 + AL_MAXCTA + blockIdx.x] = (long long)globaltimer_ns();
   co.flip ^= 1;
-  if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; }
+  if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; sh.t_mark = t2; }
 }
 
 __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co, PointCache& pc) {
@@ -1148,6 +1148,7 @@ struct DeviceBackend {
     apply_state_trig(x, t, T);
     if (lane < 12) sh.T[lane] = T[lane];
     if (lane == 0) sh.op = OP_FDF;
+    if (blockIdx.x == 0 && threadIdx.x == 0) sh.t_scalar += clock64() - sh.t_mark;   // leader time since the last collective
     __syncthreads();
     do_objective<13>(a, sh, co, pc);
     double sums[13];
@@ -1184,7 +1185,7 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   Collective co;
   co.epoch = a.epoch_base; co.flip = 0;
   const long long t_begin = clock64();
-  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; }
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_mark = clock64(); }
   if (threadIdx.x < 32) {
     PointCache pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
     DeviceBackend be(a, sh, co, pc_unused);
@@ -1196,6 +1197,7 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       *a.result = r;
       if (a.debug) {
         a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_reduce; a.debug[2] = sh.t_wait; a.debug[3] = sh.n_coll;
+        a.debug[6] = sh.t_scalar;
       }
     }
   } else {
