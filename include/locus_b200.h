@@ -34,6 +34,8 @@
  *                                 PointCloudLocalization.cc:327-336
  *   lb_gicp_fitness               icp_->getFitnessScore()
  *                                 point_cloud_odometry/test/test_point_cloud_odometry.cpp:298
+ *   lb_gicp_point2plane_information   normalizePCloud + ComputeAp_ForPoint2PlaneICP
+ *                                 point_cloud_localization/src/utils.cc:106-128, PointCloudLocalization.cc:694-750
  *   lb_voxel_create/destroy       pcl::VoxelGrid<pcl::PCLPointCloud2> impl_
  *                                 point_cloud_filter/include/point_cloud_filter/custom_voxel_grid.h:25
  *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
@@ -165,6 +167,15 @@ int lb_gicp_transform_source(lb_gicp* h, const float* T, void* out_pts, size_t s
 int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int32_t* idx, float* d2, int mem);
 /* pcl::Registration::getFitnessScore(max_range) for transform T (NULL = final). */
 int lb_gicp_fitness(lb_gicp* h, const float* T, double max_range, double* score);
+/* SURVEY 8f row f1 -- the step right after align() in PointCloudLocalization::MeasurementUpdate:
+ * normalizePCloud (point_cloud_localization/src/utils.cc:106-128) followed by ComputeAp_ForPoint2PlaneICP
+ * (PointCloudLocalization.cc:694-750): Ap = sum_i H_i' H_i, H_i = [a_i x n_i, n_i], a_i = (normalised) query point,
+ * n_i = normal of reference point correspondences[i] (rotated by T's rotation when T != NULL), NaN rows skipped.
+ * query: n points (xyz at q_xyz_off); reference: n_ref points (normal at r_normal_off); correspondences: n int32
+ * indices into reference.  Ap36: 36 doubles row-major (host).  All buffers host or all device (`mem`). */
+int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, size_t q_stride, size_t q_xyz_off,
+                                    const void* reference, size_t n_ref, size_t r_stride, size_t r_normal_off,
+                                    const int32_t* correspondences, const float* T, int normalize, double* Ap36, int mem);
 /* covariances used by the last align, n x 9 doubles row-major, original point order. which: 0 source, 1 target */
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points);
 /* number of points currently indexed. which: 0 source, 1 target */

@@ -61,7 +61,7 @@ SYMBOLS = [
     "lb_gicp_default_params", "lb_gicp_create", "lb_gicp_create_on_stream", "lb_gicp_destroy",
     "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
     "lb_gicp_promote_source_to_target", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
-    "lb_gicp_fitness", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
+    "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
@@ -114,6 +114,7 @@ def lib():
     L.lb_gicp_transform_source.argtypes = [vp, vp, vp, sz, sz, C.c_ssize_t, i32]
     L.lb_gicp_nn_target.argtypes = [vp, vp, sz, sz, vp, vp, i32]
     L.lb_gicp_fitness.argtypes = [vp, vp, C.c_double, C.POINTER(C.c_double)]
+    L.lb_gicp_point2plane_information.argtypes = [vp, vp, sz, sz, sz, vp, sz, sz, sz, vp, vp, i32, vp, i32]
     L.lb_gicp_get_covariances.argtypes = [vp, i32, vp, sz]
     L.lb_gicp_cloud_size.argtypes = [vp, i32, C.POINTER(sz)]
     L.lb_gicp_launch_count.argtypes = [vp, u64p]
@@ -272,6 +273,17 @@ class GicpB200:
         idx = np.zeros(q.shape[0], dtype=np.int32); d2 = np.zeros(q.shape[0], dtype=np.float32)
         _check(lib().lb_gicp_nn_target(self._h, _ptr(q), q.shape[0], q.shape[1] * 4, _ptr(idx), _ptr(d2), LB_MEM_HOST))
         return idx, d2
+
+    def point2planeInformation(self, query_xyz, ref_normals, correspondences, T=None, normalize=True):
+        """normalizePCloud + ComputeAp_ForPoint2PlaneICP (PointCloudLocalization.cc:694-750): 6x6 Ap."""
+        q = np.ascontiguousarray(query_xyz, dtype=np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(ref_normals, dtype=np.float32).reshape(-1, 3)
+        co = np.ascontiguousarray(correspondences, dtype=np.int32)
+        t = None if T is None else np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        Ap = np.zeros(36)
+        _check(lib().lb_gicp_point2plane_information(self._h, _ptr(q), q.shape[0], 12, 0, _ptr(r), r.shape[0], 12, 0,
+                                                     _ptr(co), _ptr(t), int(normalize), _ptr(Ap), LB_MEM_HOST))
+        return Ap.reshape(6, 6)
 
     def covariances(self, which):
         n = self.cloudSize(which)

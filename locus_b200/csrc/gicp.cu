@@ -838,6 +838,70 @@ int lb_gicp_fitness(lb_gicp* h, const float* T_in, double max_range, double* sco
   return LB_OK;
 }
 
+int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, size_t q_stride, size_t q_xyz_off,
+                                    const void* reference, size_t n_ref, size_t r_stride, size_t r_normal_off,
+                                    const int32_t* correspondences, const float* T, int normalize, double* Ap36, int mem) {
+  if (!h || !query || !reference || !correspondences || !Ap36) { set_error("lb_gicp_point2plane_information: null argument"); return LB_ERR_INVALID_ARG; }
+  if ((q_stride & 3u) || (q_xyz_off & 3u) || q_xyz_off + 12 > q_stride || (r_stride & 3u) || (r_normal_off & 3u) || r_normal_off + 12 > r_stride) {
+    set_error("lb_gicp_point2plane_information: bad stride/offset");
+    return LB_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < 36; i++) Ap36[i] = 0.0;
+  if (n == 0) return LB_OK;
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  const uint32_t N = (uint32_t)n;
+  const uint8_t *dq = (const uint8_t*)query, *dr = (const uint8_t*)reference;
+  const int32_t* dc = correspondences;
+  if (mem == LB_MEM_HOST) {
+    size_t bq = n * q_stride, br = n_ref * r_stride, bc = n * sizeof(int32_t);
+    size_t o1 = (bq + 255) & ~(size_t)255, o2 = o1 + ((br + 255) & ~(size_t)255);
+    LB_TRY(h->io.ensure(o2 + bc));
+    LB_CUDA(cudaMemcpyAsync(h->io.p, query, bq, cudaMemcpyHostToDevice, c.stream));
+    LB_CUDA(cudaMemcpyAsync(h->io.p + o1, reference, br, cudaMemcpyHostToDevice, c.stream));
+    LB_CUDA(cudaMemcpyAsync(h->io.p + o2, correspondences, bc, cudaMemcpyHostToDevice, c.stream));
+    dq = h->io.p; dr = h->io.p + o1; dc = (const int32_t*)(h->io.p + o2);
+  }
+  int nb = cdiv(N, 256);
+  if (nb > c.sm_count * 4) nb = c.sm_count * 4;
+  DBuf<double>& scratch = h->M;   // not in use outside align()
+  LB_TRY(scratch.ensure((size_t)nb * 21));
+  std::vector<double> part((size_t)nb * 21);
+  ApArgs a;
+  a.q = dq; a.n = N; a.q_stride = (uint32_t)q_stride; a.q_xyz_off = (uint32_t)q_xyz_off;
+  a.ref = dr; a.n_ref = (uint32_t)n_ref; a.r_stride = (uint32_t)r_stride; a.r_normal_off = (uint32_t)r_normal_off;
+  a.corr = dc; a.factor = 1.f; a.tx = a.ty = a.tz = 0.f; a.use_R = T ? 1 : 0;
+  for (int i = 0; i < 9; i++) a.R[i] = T ? (double)T[(i / 3) * 4 + (i % 3)] : ((i % 4 == 0) ? 1.0 : 0.0);
+  if (normalize) {
+    // normalizePCloud: centroid, mean distance to it, a = factor * (p - centroid) with factor = n / sum |p - c|
+    ap_sum_kernel<<<nb, 256, 0, c.stream>>>(dq, N, (uint32_t)q_stride, (uint32_t)q_xyz_off, 0.f, 0.f, 0.f, 0, scratch.p);
+    c.launches++;
+    LB_CUDA(cudaMemcpyAsync(part.data(), scratch.p, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+    double sx = 0, sy = 0, sz = 0;
+    for (int b = 0; b < nb; b++) { sx += part[3 * (size_t)b]; sy += part[3 * (size_t)b + 1]; sz += part[3 * (size_t)b + 2]; }
+    float cx = (float)(sx / (double)n), cy = (float)(sy / (double)n), cz = (float)(sz / (double)n);
+    ap_sum_kernel<<<nb, 256, 0, c.stream>>>(dq, N, (uint32_t)q_stride, (uint32_t)q_xyz_off, cx, cy, cz, 1, scratch.p);
+    c.launches++;
+    LB_CUDA(cudaMemcpyAsync(part.data(), scratch.p, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+    double dist = 0;
+    for (int b = 0; b < nb; b++) dist += part[3 * (size_t)b];
+    float factor = (float)n / (float)dist;
+    a.factor = factor; a.tx = -factor * cx; a.ty = -factor * cy; a.tz = -factor * cz;
+  }
+  ap_accumulate_kernel<<<nb, 256, 0, c.stream>>>(a, scratch.p);
+  c.launches++;
+  LB_CUDA(cudaMemcpyAsync(part.data(), scratch.p, (size_t)nb * 21 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  LB_CUDA(cudaGetLastError());
+  double up[21] = {0};
+  for (int b = 0; b < nb; b++) for (int e = 0; e < 21; e++) up[e] += part[21 * (size_t)b + e];
+  int e = 0;
+  for (int r = 0; r < 6; r++) for (int cc = r; cc < 6; cc++) { Ap36[r * 6 + cc] = up[e]; Ap36[cc * 6 + r] = up[e]; e++; }
+  return LB_OK;
+}
+
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points) {
   if (!h || !out9) return LB_ERR_INVALID_ARG;
   Cloud& cl = which ? h->tgt : h->src;

@@ -1213,6 +1213,66 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ row f1: point-to-plane information matrix
+// PointCloudLocalization.cc:694-750 (ComputeAp_ForPoint2PlaneICP) after src/utils.cc:106-128 (normalizePCloud).
+// Three small reductions (double, fixed-shape block trees; per-CTA partials are summed on the host in CTA order).
+__global__ void __launch_bounds__(256)
+ap_sum_kernel(const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, uint32_t xyz_off, float cx, float cy, float cz,
+              int mode /*0: sum xyz, 1: sum |p - c|*/, double* __restrict__ partials /*[grid][3]*/) {
+  __shared__ double red[8 * 3];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride + xyz_off);
+    if (mode == 0) { acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; }
+    else {
+      float dx = p[0] - cx, dy = p[1] - cy, dz = p[2] - cz;
+      acc[0] += (double)sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+  }
+  double tot = block_reduce<3, 8, 0>(acc, red);
+  if (threadIdx.x < 3) partials[3 * (size_t)blockIdx.x + threadIdx.x] = tot;
+}
+
+struct ApArgs {
+  const uint8_t* q; uint32_t n, q_stride, q_xyz_off;
+  const uint8_t* ref; uint32_t n_ref, r_stride, r_normal_off;
+  const int32_t* corr;
+  float factor, tx, ty, tz;      // normalisation a = factor * p + t  (identity: 1, 0, 0, 0)
+  double R[9]; int use_R;        // PointNormal variant rotates the reference normal by R (PointCloudLocalization.cc:715-718)
+};
+
+__global__ void __launch_bounds__(256)
+ap_accumulate_kernel(ApArgs a, double* __restrict__ partials /*[grid][21]*/) {
+  __shared__ double red[8 * 21];
+  double acc[21];
+#pragma unroll
+  for (int e = 0; e < 21; e++) acc[e] = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(a.q + (size_t)i * a.q_stride + a.q_xyz_off);
+    int j = a.corr[i];
+    if (j < 0 || (uint32_t)j >= a.n_ref) continue;
+    const float* nr = reinterpret_cast<const float*>(a.ref + (size_t)j * a.r_stride + a.r_normal_off);
+    double ai[3] = {(double)(a.factor * p[0] + a.tx), (double)(a.factor * p[1] + a.ty), (double)(a.factor * p[2] + a.tz)};
+    double ni[3] = {(double)nr[0], (double)nr[1], (double)nr[2]};
+    if (isnan(ai[0]) || isnan(ai[1]) || isnan(ai[2]) || isnan(ni[0]) || isnan(ni[1]) || isnan(ni[2])) continue;
+    if (a.use_R) {
+      double r0 = a.R[0] * ni[0] + a.R[1] * ni[1] + a.R[2] * ni[2];
+      double r1 = a.R[3] * ni[0] + a.R[4] * ni[1] + a.R[5] * ni[2];
+      double r2 = a.R[6] * ni[0] + a.R[7] * ni[1] + a.R[8] * ni[2];
+      ni[0] = r0; ni[1] = r1; ni[2] = r2;
+    }
+    double H[6] = {ai[1] * ni[2] - ai[2] * ni[1], ai[2] * ni[0] - ai[0] * ni[2], ai[0] * ni[1] - ai[1] * ni[0],
+                   ni[0], ni[1], ni[2]};
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = r; c < 6; c++) acc[e++] += H[r] * H[c];
+  }
+  double tot = block_reduce<21, 8, 0>(acc, red);
+  if (threadIdx.x < 21) partials[21 * (size_t)blockIdx.x + threadIdx.x] = tot;
+}
+
 // ------------------------------------------------------------------ fitness (a9)
 // pcl::Registration::getFitnessScore: mean of squared 1-NN distances <= max_range.
 __global__ void __launch_bounds__(128)

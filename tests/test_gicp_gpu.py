@@ -237,3 +237,29 @@ def test_full_size_c5_dense_properties():
     g.setExecution(1)
     g.align()
     assert np.array_equal(T_p, g.getFinalTransformation())
+
+
+def test_point2plane_information_known_answers(oracle):
+    """SURVEY 8f row f1.  test_point_cloud_localization.cpp:337-339,391-393: Ap(0,0) = Ap(1,1) = 56.7753,
+    Ap(5,5) = 100 (+-1e-4) on the 10 x 10 plane; plus the oracle on a random cloud, NaN rows skipped, rotated normals."""
+    import locus_b200
+    g = locus_b200.GicpB200()
+    xyz, nrm = F.plane()
+    Ap = g.point2planeInformation(xyz, nrm, np.arange(100))
+    assert abs(Ap[0, 0] - 56.7753) < 1e-4 and abs(Ap[1, 1] - 56.7753) < 1e-4 and abs(Ap[5, 5] - 100) < 1e-4
+    ref = oracle.compute_ap(oracle.normalize_pcloud(xyz), nrm, np.arange(100))
+    assert np.allclose(Ap, ref, rtol=1e-6, atol=1e-6)
+    rng = np.random.default_rng(0)
+    q = rng.normal(0, 3, (5000, 3)).astype(np.float32)
+    n = rng.normal(0, 1, (800, 3)).astype(np.float32); n /= np.linalg.norm(n, axis=1, keepdims=True)
+    co = rng.integers(0, 800, 5000)
+    q[17] = np.nan; n[5, 1] = np.nan
+    Ap = g.point2planeInformation(q, n, co, normalize=False)
+    ref = oracle.compute_ap(q, n, co)
+    assert np.allclose(Ap, ref, rtol=1e-9, atol=1e-9)
+    T = F.se3([0, 0, 0], [0.1, -0.2, 0.3]).astype(np.float32)
+    Ap = g.point2planeInformation(q, n, co, T=T, normalize=False)
+    nr = (n.astype(np.float64) @ T[:3, :3].astype(np.float64).T).astype(np.float64)
+    ok = ~(np.isnan(q).any(1) | np.isnan(nr[co]).any(1))
+    H = np.concatenate([np.cross(q[ok].astype(np.float64), nr[co][ok]), nr[co][ok]], axis=1)
+    assert np.allclose(Ap, H.T @ H, rtol=1e-9, atol=1e-7)

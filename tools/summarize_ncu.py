@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+  python tools/summarize_ncu.py launches <launches.csv> <out.md>      # per-kernel time shares of ONE bench step
+  python tools/summarize_ncu.py full <report.ncu-rep> <out.md>         # key metrics of every captured launch
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_elapsed.max"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    seq = []
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("lb::", "").replace("void ", "")
+        seq.append((name, v))
+    idx = [i for i, s in enumerate(seq) if "align_" in s[0]]
+    with open(out, "w") as f:
+        f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none): one bench step\n\n")
+        f.write("Source: `%s` (%d launches captured); the step between the last two align kernels.\n" % (path, len(seq)))
+        f.write("Durations under ncu are serialised (and cold-cache unless --cache-control none): compare SHARES.\n\n")
+        if len(idx) >= 2:
+            step = seq[idx[-2] + 1: idx[-1] + 1]
+            agg = collections.OrderedDict()
+            for n, v in step:
+                a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
+            tot = sum(a[1] for a in agg.values())
+            f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+            for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+                f.write("| %s | %d | %.1f | %.1f %% |\n" % (k, n, t, 100 * t / tot))
+            f.write("| **sum** | %d | %.1f | |\n" % (sum(a[0] for a in agg.values()), tot))
+    print("wrote", out)
+
+
+def full(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w") as f:
+        f.write("# ncu --set full summary of `%s`\n\n" % rep)
+        for r in rows[2:]:
+            f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % r[ix["Kernel Name"]])
+            for k in KEYS:
+                if k in ix:
+                    f.write("| %s | %s | %s |\n" % (k, r[ix[k]], units[ix[k]]))
+            f.write("\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
