@@ -367,6 +367,7 @@ def main():
     idx_ms, idx_n = gicp.kernelTime("index_build")
     dbg = [gicp.kernelTime("debug%d" % i)[0] for i in range(4)]
     dbg6 = gicp.kernelTime("debug6")[0]
+    dbg7 = gicp.kernelTime("debug7")[0]; dbg8 = gicp.kernelTime("debug8")[0]
     snapP = [gicp.kernelTime("snapP%d" % i)[0] for i in range(64)]
     snapC = [gicp.kernelTime("snapC%d" % i)[0] for i in range(64)]
     if os.environ.get("LB_SNAP"):
@@ -412,7 +413,8 @@ def main():
                          "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
                          "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms, "voxel_last_call_ms": vg.lastCallMs(),
                          "align_last_launch_cycles": {"total": dbg[0], "block_reduce_publish": dbg[1],
-                                                      "slot_wait_sum": dbg[2], "collectives": dbg[3], "leader_scalar_before_fdf": dbg6},
+                                                      "slot_wait_sum": dbg[2], "collectives": dbg[3], "leader_scalar_before_fdf": dbg6, "poll_rounds_thread0": dbg7,
+                                                      "poll_publish_to_done_thread0": dbg8},
                          "wall_s_timed_region": wall}}
 
     if world == 1 and not args.no_cpu_baseline:

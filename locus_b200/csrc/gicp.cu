@@ -708,6 +708,9 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       AlignArgs aa;
       aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
       aa.epoch_base = epoch_base;
+      static int poll_delay = -1;   // tuning aid
+      if (poll_delay < 0) { const char* e = getenv("LB_POLL_DELAY"); poll_delay = e ? atoi(e) : (int)AL_POLL_DELAY; }
+      aa.poll_delay = poll_delay;
       aa.debug = h->timing ? h->d_debug : nullptr;
       for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
       void* args[] = {&aa};
@@ -941,7 +944,7 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
   *ms_avg = 0.f; if (launches) *launches = 0;
   cudaStreamSynchronize(h->c.stream);
   timers_collect(h);
-  if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '7') {   // cycle counters of the last persistent align
+  if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '9') {   // cycle counters of the last persistent align
     *ms_avg = (float)h->h_debug[name[5] - '0'];
     return LB_OK;
   }

@@ -781,20 +781,23 @@ constexpr int AL_MAXCTA = 160;
 constexpr long long AL_POLL_DELAY = 700;   // cycles
 template <int NV, int THREADS>
 __device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, unsigned long long epoch,
-                                              double* mat /*[NV][AL_MAXCTA] shared*/, double* out /*shared [NV]*/) {
+                                              double* mat /*[NV][AL_MAXCTA] shared*/, double* out /*shared [NV]*/,
+                                              long long* prof_rounds = nullptr, long long poll_delay = AL_POLL_DELAY) {
   const int npairs = ncta * NV;
   constexpr int MAXP = (AL_MAXCTA * NV + THREADS - 1) / THREADS;
   // every CTA publishes at about the same time and a publication needs ~0.5 us to land in L2: polling at once
   // wastes a full ~1 us round trip on words that are not there yet, so hold the first poll back a little
   {
     const long long t_start = clock64();
-    while (clock64() - t_start < AL_POLL_DELAY) {}
+    while (clock64() - t_start < poll_delay) {}
   }
   unsigned pending = 0;
 #pragma unroll
   for (int k = 0; k < MAXP; k++)
     if ((int)threadIdx.x + k * THREADS < npairs) pending |= 1u << k;
+  int rounds = 0;
   while (pending) {
+    rounds++;
 #pragma unroll
     for (int k = 0; k < MAXP; k++)
       if (pending & (1u << k)) {
@@ -804,6 +807,7 @@ __device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, uns
         if (slot_try(&buf[(size_t)b * AL_PSTRIDE + e], epoch, v)) { mat[e * AL_MAXCTA + b] = v; pending &= ~(1u << k); }
       }
   }
+  if (prof_rounds) { prof_rounds[0] += rounds; prof_rounds[1] += clock64(); }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = warp; e < NV; e += THREADS / 32) {
@@ -999,6 +1003,7 @@ struct AlignArgs {
   CorrArgs c;
   SlotWord* slots;        // [2][gridDim.x][AL_PSTRIDE] (value, epoch) words
   unsigned long long epoch_base;   // unique per launch, so stale epochs of earlier launches never match
+  int poll_delay;                  // cycles to hold back the first poll of a collective
   long long* debug;       // nullable: [8] cycle counters written by CTA 0 (profiling aid)
   OuterParams P;
   float guess[16];
@@ -1011,6 +1016,7 @@ struct AlignShared {
   int op;
   int m;
   long long t_reduce, t_wait, n_coll, t_scalar, t_mark;   // CTA 0 / thread 0 cycle counters
+  long long poll[2];                                       // poll rounds of thread 0, sum of clock at poll completion
   float T[12];
   double R[9];
   double D[27];
@@ -1044,7 +1050,8 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   long long t1 = prof ? clock64() : 0;
   const bool snap = a.debug && threadIdx.x == 0 && (co.epoch - a.epoch_base) == 100;   // one collective, all CTAs
   if (snap) a.debug[16 + blockIdx.x] = (long long)globaltimer_ns();
-  slots_all_sum<NV, AL_THREADS>(buf, ncta, co.epoch, sh.mat, sh.bc);
+  slots_all_sum<NV, AL_THREADS>(buf, ncta, co.epoch, sh.mat, sh.bc, prof ? sh.poll : nullptr, (long long)a.poll_delay);
+  if (prof) sh.poll[1] -= t1;   // accumulates (poll completion - publish) for thread 0
   if (snap) a.debug[16 + AL_MAXCTA + blockIdx.x] = (long long)globaltimer_ns();
   co.flip ^= 1;
   if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; sh.t_mark = t2; }
@@ -1185,7 +1192,7 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   Collective co;
   co.epoch = a.epoch_base; co.flip = 0;
   const long long t_begin = clock64();
-  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_mark = clock64(); }
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
   if (threadIdx.x < 32) {
     PointCache pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
     DeviceBackend be(a, sh, co, pc_unused);
@@ -1197,7 +1204,7 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       *a.result = r;
       if (a.debug) {
         a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_reduce; a.debug[2] = sh.t_wait; a.debug[3] = sh.n_coll;
-        a.debug[6] = sh.t_scalar;
+        a.debug[6] = sh.t_scalar; a.debug[7] = sh.poll[0]; a.debug[8] = sh.poll[1];
       }
     }
   } else {
