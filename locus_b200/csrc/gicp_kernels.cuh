@@ -798,13 +798,26 @@ __device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, uns
   int rounds = 0;
   while (pending) {
     rounds++;
+    // issue every pending load first, then look at the tags: the loads of one round overlap (one L2 round trip)
+    unsigned long long lo[MAXP], hi[MAXP];
 #pragma unroll
-    for (int k = 0; k < MAXP; k++)
+    for (int k = 0; k < MAXP; k++) {
+      lo[k] = 0; hi[k] = 0;
       if (pending & (1u << k)) {
         int pr = threadIdx.x + k * THREADS;
         int b = pr / NV, e = pr - b * NV;
-        double v;
-        if (slot_try(&buf[(size_t)b * AL_PSTRIDE + e], epoch, v)) { mat[e * AL_MAXCTA + b] = v; pending &= ~(1u << k); }
+        const SlotWord* p = &buf[(size_t)b * AL_PSTRIDE + e];
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[k]), "=l"(hi[k]) : "l"(p));
+      }
+    }
+    const unsigned long long tag = epoch & 0xffffffffull;
+#pragma unroll
+    for (int k = 0; k < MAXP; k++)
+      if ((pending & (1u << k)) && (lo[k] >> 32) == tag && (hi[k] >> 32) == tag) {
+        int pr = threadIdx.x + k * THREADS;
+        int b = pr / NV, e = pr - b * NV;
+        mat[e * AL_MAXCTA + b] = __longlong_as_double((long long)((hi[k] << 32) | (lo[k] & 0xffffffffull)));
+        pending &= ~(1u << k);
       }
   }
   if (prof_rounds) { prof_rounds[0] += rounds; prof_rounds[1] += clock64(); }
