@@ -778,7 +778,7 @@ __device__ __forceinline__ bool slot_try(const SlotWord* p, unsigned long long e
 // round trip when nobody is late); the values land in a shared matrix and warp w then sums rows e = w,
 // w + nwarps, ... lane-strided + shuffle tree.  out[e] (shared) valid after the trailing CTA barrier.
 constexpr int AL_MAXCTA = 160;
-constexpr long long AL_POLL_DELAY = 700;   // cycles
+constexpr long long AL_POLL_DELAY = 400;   // cycles (sweep 0..1000 on B200: flat minimum around 300-600)
 template <int NV, int THREADS>
 __device__ __forceinline__ void slots_all_sum(const SlotWord* buf, int ncta, unsigned long long epoch,
                                               double* mat /*[NV][AL_MAXCTA] shared*/, double* out /*shared [NV]*/,
