@@ -156,6 +156,32 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
   // r >= 2: the lanes split the ROWS (shells of sparse neighbourhoods are mostly empty rows, whose cost is the
   //         dependent cell_start look-ups: four of them now overlap)
   const bool split_rows = r >= split_from;
+  if (r == 1 && !split_rows) {
+    // nearest rows first (centre row, then the four face-adjacent rows, then the four corner rows): the k-th
+    // best distance tightens early, so fewer of the later candidates have to be inserted into the sorted lists
+    const int DZ[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+    const int DY[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+#pragma unroll 1
+    for (int j = 0; j < 9; j++) {
+      int z = cz + DZ[j], y = cy + DY[j];
+      if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+      int base = (z * g.ny + y) * g.nx;
+      bool face = (j != 0);
+      int nseg = face ? 1 : 2;
+      for (int k = 0; k < nseg; k++) {
+        int xa, xb;
+        if (face) { xa = imax_(cx - 1, 0); xb = imin_(cx + 1, g.nx - 1); }
+        else { xa = xb = (k == 0) ? cx - 1 : cx + 1; if (xa < 0 || xa >= g.nx) continue; }
+        if (xa > xb) continue;
+        uint32_t s = g.cell_start[base + xa], e = g.cell_start[base + xb + 1];
+        for (uint32_t i = s + sub; i < e; i += 4) {
+          f4 p = g.pts[i];
+          L.push(dist2(qx, qy, qz, p.x, p.y, p.z), float_to_bits(p.w), (int)i);
+        }
+      }
+    }
+    return;
+  }
   int row = 0;
   for (int z = z0; z <= z1; z++) {
     bool zface = (iabs_(z - cz) == r);
