@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--leaf", type=float, default=0.0, help="fixed VoxelGrid leaf (skips the bisection; profiling aid)")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling aid for ncu: device-resident arm only (no e2e arm, no CPU baseline, no variants)")
     return ap.parse_args()
 
 
@@ -267,7 +270,7 @@ def main():
     # leaf by bisection so that the filter output is ~30000 points, on the GPU filter itself
     vg.setFilterFieldName("z"); vg.setFilterLimits(-100.0, 100.0)
     lo, hi = 0.02, 2.0
-    for _ in range(18):
+    for _ in range(0 if args.leaf > 0 else 18):
         mid = 0.5 * (lo + hi)
         vg.setLeafSize(mid)
         n = vg.filter(blobs[0], POINT_STEP, fields).shape[0]
@@ -275,7 +278,7 @@ def main():
             lo = mid
         else:
             hi = mid
-    leaf = float(np.float32(0.5 * (lo + hi)))
+    leaf = float(np.float32(args.leaf if args.leaf > 0 else 0.5 * (lo + hi)))
     vg.setLeafSize(leaf)
     workload["leaf_m"] = leaf
 
@@ -378,7 +381,21 @@ def main():
     ncorr = np.array(state["ncorr"], dtype=np.float64); nsrc = np.array(state["nsrc"], dtype=np.float64)
 
     # ---- host-buffer arm (e2e)
-    e2e_ms, e2e_wall = timed_run(step_host, args.steps, args.warmup)
+    if args.profile:
+        e2e_ms, e2e_wall = dev_ms, wall
+    else:
+        e2e_ms, e2e_wall = timed_run(step_host, args.steps, args.warmup)
+
+    # ---- variant (information only, N = 1): north_star's Gauss-Newton inner solve instead of the reference's BFGS
+    variants = {}
+    if world == 1 and not args.profile and not os.environ.get("LB_OPT"):
+        gicp.setOptimizer(locus_b200.LB_OPT_GAUSS_NEWTON)
+        gn_ms, _ = timed_run(lambda i, rec=False: step_device(i, rec), args.steps, args.warmup, record=True)
+        gicp.setOptimizer(locus_b200.LB_OPT_BFGS)
+        variants["gauss_newton"] = {"value": args.steps / (gn_ms * 1e-3), "unit": "scans/s",
+                                    "poses": list(state["poses"]),
+                                    "note": "6x6 Gauss-Newton inner solve (BASELINE north_star wording); NOT the headline: "
+                                            "its pose differs from the reference's BFGS result by more than the 1e-4 bar"}
 
     # max over ranks (device time), whole-job aggregate
     (dev_ms_max, e2e_ms_max), (value, e2e_value) = aggregate(dist, "cuda", [dev_ms, e2e_ms], args.steps, world)
@@ -395,7 +412,7 @@ def main():
     achieved = (bytes_per_launch / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "align_persistent_kernel (K4 NN-correspondence + K5 objective + BFGS, resident)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": ncu_traffic("align_persistent_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms, "launches_timed": int(k_n),
                 "note": "working set (<= 5 MB) is L2-resident: this kernel is bound by grid-barrier/launch latency, "
                         "not HBM (SURVEY H3); fraction reported for information"}
@@ -417,7 +434,9 @@ def main():
                                                       "poll_publish_to_done_thread0": dbg8},
                          "wall_s_timed_region": wall}}
 
-    if world == 1 and not args.no_cpu_baseline:
+    if args.profile:
+        line["profile_run"] = True
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
         # CPU baseline on a bounded sample of the same stream, and pose delta GPU vs CPU on those scans
         sps, n, cpu_poses, cores = run_cpu_arm(args, leaf, blobs, budget_s=args.cpu_baseline_seconds)
         line["cpu_baseline"] = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
@@ -432,9 +451,29 @@ def main():
                 dts.append(dt); drs.append(dr)
         if dts:
             line["pose_delta_vs_cpu"] = {"max_dt_m": float(max(dts)), "max_dr_rad": float(max(drs)), "pairs": len(dts)}
+        for v in variants.values():
+            d = [F.pose_delta(cpu_poses[key], Tg) for key, Tg in v["poses"] if key in cpu_poses]
+            if d:
+                v["pose_delta_vs_cpu"] = {"max_dt_m": float(max(x[0] for x in d)), "max_dr_rad": float(max(x[1] for x in d)),
+                                          "pairs": len(d)}
+    for v in variants.values():
+        v.pop("poses", None)
+    if variants:
+        line["variants"] = variants
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py traffic); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t[kernel]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def pick_leaf_cpu(blob):

@@ -3,6 +3,7 @@
 
   python tools/summarize_ncu.py launches <launches.csv> <out.md>      # per-kernel time shares of ONE bench step
   python tools/summarize_ncu.py full <report.ncu-rep> <out.md>         # key metrics of every captured launch
+  python tools/summarize_ncu.py traffic <report.ncu-rep> <out.json>    # mean DRAM bytes per launch, per kernel
 """
 import collections
 import csv
@@ -68,5 +69,30 @@ def full(rep, out):
     print("wrote", out)
 
 
+def traffic(rep, out):
+    """profiles/traffic.json: what bench.py reports as roofline.traffic (dram read + write bytes per launch)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"],
+                         stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("lb::", "").replace("void ", "")
+        name = re.sub(r"<.*", "", name)
+        rd = float(r[ix["dram__bytes_read.sum"]].replace(",", ""))
+        wr = float(r[ix["dram__bytes_write.sum"]].replace(",", ""))
+        dur = float(r[ix["gpu__time_duration.sum"]].replace(",", ""))
+        a = acc.setdefault(name, [0, 0.0, 0.0, 0.0]); a[0] += 1; a[1] += rd; a[2] += wr; a[3] += dur
+    res = {k: {"launches_captured": n, "dram_bytes_read_per_launch": rd / n, "dram_bytes_write_per_launch": wr / n,
+               "dram_bytes_per_launch": (rd + wr) / n, "ncu_duration_ns_per_launch": d / n}
+           for k, (n, rd, wr, d) in acc.items()}
+    res["_source"] = "ncu --set full --clock-control none capture %s" % rep
+    with open(out, "w") as f:
+        json.dump(res, f, indent=1)
+    print("wrote", out)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
