@@ -41,6 +41,10 @@
  *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
  *   lb_voxel_set_filter_limits    impl_.setFilterFieldName/Limits/LimitsNegative  custom_voxel_grid.cc:103-134
  *   lb_voxel_filter               impl_.setInputCloud + setIndices + filter()     custom_voxel_grid.cc:76-87
+ *   lb_odometry_submit/next       the per-scan chain of the lidar callback: filtered scan -> odometry_.SetLidar()
+ *                                 -> odometry_.UpdateEstimate()   locus/src/Locus.cc:451-453,
+ *                                 PointCloudOdometry.cc:221-230 (SetLidar), 237-247 (UpdateEstimate: first scan
+ *                                 only stored; afterwards reference_ = previous query_), 249-274 (UpdateICP)
  *
  * Threading: a handle is used from one thread at a time (the reference calls
  * the seam from the dedicated lidar spinner thread, locus/src/Locus.cc:63-69,
@@ -224,6 +228,55 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
                     int mem_in, int mem_out);
 int lb_voxel_launch_count(lb_voxel* h, uint64_t* n);
 int lb_voxel_kernel_time(lb_voxel* h, float* ms_total_last_call);
+
+/* ------------------------------------------------- scan-to-scan odometry pipeline
+ * One robot's lidar stream, scans submitted in order: VoxelGrid(scan k) -> GICP(source = filtered k, target =
+ * filtered k-1), i.e. what Locus.cc:451-453 + PointCloudOdometry::UpdateEstimate do per scan.  Results are
+ * identical to calling lb_voxel_filter / lb_gicp_set_source / lb_gicp_set_target / lb_gicp_align per scan; what
+ * the pipeline adds is overlap: a voxel stage (one host thread, one CUDA stream) and `depth` registration workers
+ * (one host thread, one lb_gicp handle and stream each).  Scan k+1 is filtered and indexed while scan k is still in
+ * its align kernel -- a latency-bound persistent kernel that occupies ~60 of the 148 SMs -- and up to `depth`
+ * aligns are in flight at once.  Registration k does not depend on the pose of registration k-1 (the caller's
+ * prior, if any, comes from IMU/odometry: PointCloudOdometry.cc:252-262), so the overlap changes no result.
+ * In the reference the voxel filter already runs in its own nodelet thread ahead of the odometry thread.
+ *
+ * Threading: submit/next/drain are called from one thread (the lidar callback).  A submitted scan buffer (and the
+ * optional filtered_out buffer) must stay valid until its result has been returned by lb_odometry_next. */
+typedef struct lb_odometry lb_odometry;
+
+typedef struct lb_odometry_result {
+  uint64_t ticket;          /* 0-based submission number */
+  int status;               /* lb_status of the stages of this scan */
+  int has_pose;             /* 0 for the first scan (UpdateEstimate only stores it) or when a stage failed */
+  size_t n_filtered;        /* points after VoxelGrid */
+  lb_gicp_result gicp;      /* as lb_gicp_align (valid when has_pose) */
+  char error[160];          /* message when status != LB_OK */
+} lb_odometry_result;
+
+/* depth: registration workers (1..8).  max_points / max_point_step size the ring of filtered clouds. */
+int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_point_step, lb_odometry** out);
+int lb_odometry_destroy(lb_odometry* h);
+/* the pipeline's VoxelGrid handle: configure leaf / limits on it before the first submit */
+lb_voxel* lb_odometry_voxel(lb_odometry* h);
+/* registration worker i's handle (0 <= i < depth): read-only use for counters / kernel times while idle */
+lb_gicp* lb_odometry_gicp(lb_odometry* h, int i);
+int lb_odometry_depth(lb_odometry* h);
+/* applied to every worker's lb_gicp handle (call while the pipeline is idle) */
+int lb_odometry_set_gicp_params(lb_odometry* h, const lb_gicp_params* p);
+/* scan: n_pts points of point_step bytes described by fields (as lb_voxel_filter); xyz must be FLOAT32 fields.
+ * guess: row-major 4x4 prior handed to align() (NULL = identity).  filtered_out (nullable): host (LB_MEM_HOST) or
+ * device buffer of at least n_pts * point_step bytes that receives the filtered cloud.  Blocks while 2*depth+2 scans
+ * are already in flight.  *ticket (nullable) = the submission number. */
+int lb_odometry_submit(lb_odometry* h, const uint8_t* scan, size_t n_pts, uint32_t point_step, const lb_field* fields,
+                       int n_fields, int mem, const float* guess, uint8_t* filtered_out, int mem_filtered,
+                       uint64_t* ticket);
+/* next result in submission order.  block != 0: wait for it; block == 0: returns 1 when it is not ready yet.
+ * Returns LB_ERR_NO_ALIGN when every submitted scan has already been returned. */
+int lb_odometry_next(lb_odometry* h, lb_odometry_result* r, int block);
+/* scans submitted but not yet returned by lb_odometry_next */
+int lb_odometry_pending(lb_odometry* h, size_t* n);
+/* kernels launched by all stages since creation */
+int lb_odometry_launch_count(lb_odometry* h, uint64_t* n);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,11 @@ class GicpResult(C.Structure):
     ]
 
 
+class OdometryResult(C.Structure):
+    _fields_ = [("ticket", C.c_uint64), ("status", C.c_int), ("has_pose", C.c_int), ("n_filtered", C.c_size_t),
+                ("gicp", GicpResult), ("error", C.c_char * 160)]
+
+
 class Field(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
 
@@ -66,6 +71,9 @@ SYMBOLS = [
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
     "lb_voxel_set_downsample_all_data", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
+    "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
+    "lb_odometry_set_gicp_params", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
+    "lb_odometry_launch_count",
 ]
 
 
@@ -132,6 +140,16 @@ def lib():
                                   C.POINTER(sz), vp, i32, i32]
     L.lb_voxel_launch_count.argtypes = [vp, u64p]
     L.lb_voxel_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lb_odometry_create.argtypes = [i32, i32, sz, C.c_uint32, C.POINTER(vp)]
+    L.lb_odometry_destroy.argtypes = [vp]
+    L.lb_odometry_voxel.argtypes = [vp]; L.lb_odometry_voxel.restype = vp
+    L.lb_odometry_gicp.argtypes = [vp, i32]; L.lb_odometry_gicp.restype = vp
+    L.lb_odometry_depth.argtypes = [vp]
+    L.lb_odometry_set_gicp_params.argtypes = [vp, C.POINTER(GicpParams)]
+    L.lb_odometry_submit.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, i32, vp, vp, i32, u64p]
+    L.lb_odometry_next.argtypes = [vp, C.POINTER(OdometryResult), i32]
+    L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
+    L.lb_odometry_launch_count.argtypes = [vp, u64p]
     _lib = L
     return L
 
@@ -183,6 +201,8 @@ class GicpB200:
             pass
 
     def close(self):
+        if getattr(self, "_borrowed", False):
+            return
         if getattr(self, "_h", None) and self._h.value:
             lib().lb_gicp_destroy(self._h)
             self._h = C.c_void_p()
@@ -327,6 +347,8 @@ class VoxelGridB200:
             pass
 
     def close(self):
+        if getattr(self, "_borrowed", False):
+            return
         if getattr(self, "_h", None) and self._h.value:
             lib().lb_voxel_destroy(self._h)
             self._h = C.c_void_p()
@@ -392,3 +414,80 @@ class VoxelGridB200:
         ms = C.c_float(0)
         lib().lb_voxel_kernel_time(self._h, C.byref(ms))
         return ms.value
+
+
+class OdometryB200:
+    """Mirror of the per-scan chain of the reference's lidar callback (locus/src/Locus.cc:451-453:
+    odometry_.SetLidar(filtered) + odometry_.UpdateEstimate(), PointCloudOdometry.cc:221-274) as the library's
+    two-stage pipeline: VoxelGrid of scan k+1 overlaps the registration of scan k, `depth` registrations in flight."""
+
+    def __init__(self, device=0, depth=3, max_points=1 << 18, max_point_step=32):
+        self._h = C.c_void_p()
+        _check(lib().lb_odometry_create(device, depth, max_points, max_point_step, C.byref(self._h)))
+        self.depth = depth
+        self.voxel = VoxelGridB200.__new__(VoxelGridB200)          # borrowed handles: never destroyed from here
+        self.voxel._h = C.c_void_p(lib().lb_odometry_voxel(self._h)); self.voxel._borrowed = True
+        self._g = []
+        for i in range(depth):
+            g = GicpB200.__new__(GicpB200)
+            g._h = C.c_void_p(lib().lb_odometry_gicp(self._h, i)); g._borrowed = True
+            g._p = GicpParams(); lib().lb_gicp_get_params(g._h, C.byref(g._p)); g._res = None; g._keep = {}
+            self._g.append(g)
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lb_odometry_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def gicp(self, i):
+        return self._g[i]
+
+    def setGicpParams(self, **kw):
+        """keyword = lb_gicp_params field name; applied to every registration worker."""
+        p = GicpParams()
+        lib().lb_gicp_get_params(self._g[0]._h, C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        _check(lib().lb_odometry_set_gicp_params(self._h, C.byref(p)))
+        for g in self._g:
+            lib().lb_gicp_get_params(g._h, C.byref(g._p))
+
+    def submit(self, scan, n_pts, point_step, fields, mem=LB_MEM_HOST, guess=None, filtered_out=None,
+               mem_filtered=LB_MEM_HOST):
+        """scan / filtered_out: host uint8 numpy arrays or raw pointers (int).  Returns the ticket."""
+        fa = fields if not isinstance(fields, (list, tuple)) else VoxelGridB200._fields(fields)
+        t = C.c_uint64(0)
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        _check(lib().lb_odometry_submit(self._h, _ptr(scan), n_pts, point_step, fa, len(fa), mem, _ptr(g),
+                                        _ptr(filtered_out), mem_filtered, C.byref(t)))
+        self._keep[t.value] = (scan, fa, g, filtered_out)        # buffers stay alive until the result is returned
+        return t.value
+
+    def next(self, block=True):
+        """next result in submission order, or None when block=False and it is not ready."""
+        r = OdometryResult()
+        s = lib().lb_odometry_next(self._h, C.byref(r), int(bool(block)))
+        if s == 1:
+            return None
+        _check(s)
+        self._keep.pop(r.ticket, None)
+        return r
+
+    def pending(self):
+        n = C.c_size_t(0)
+        _check(lib().lb_odometry_pending(self._h, C.byref(n)))
+        return n.value
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        lib().lb_odometry_launch_count(self._h, C.byref(n))
+        return n.value

@@ -400,12 +400,15 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
       knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
     } else {
       const int no_cap = 1 << 30;
-      static int split_from = -1, lazy_merge = -1, qthreads = 128;
-      if (split_from < 0) {
-        const char* e = getenv("LB_QSPLIT"); split_from = e ? atoi(e) : 99;
-        e = getenv("LB_QMERGE"); lazy_merge = e ? atoi(e) : 1;
-        e = getenv("LB_QTHREADS"); qthreads = e ? atoi(e) : 128;
-      }
+      struct QuadTune { int split_from, lazy_merge, qthreads; };   // tuning aids; magic static: initialised once, thread-safe
+      static const QuadTune qt = [] {
+        QuadTune t;
+        const char* e = getenv("LB_QSPLIT"); t.split_from = e ? atoi(e) : 99;
+        e = getenv("LB_QMERGE"); t.lazy_merge = e ? atoi(e) : 1;
+        e = getenv("LB_QTHREADS"); t.qthreads = e ? atoi(e) : 128;
+        return t;
+      }();
+      const int split_from = qt.split_from, lazy_merge = qt.lazy_merge, qthreads = qt.qthreads;
       if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
       else knn_cov_quad_kernel<32><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
     }
