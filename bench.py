@@ -50,8 +50,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("LB_DEPTH", "4")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("LB_DEPTH", "6")),
                     help="registration workers of the odometry pipeline (aligns in flight)")
+    ap.add_argument("--pipeline-ppc", type=int, default=int(os.environ.get("LB_PIPE_PPC", "1024")),
+                    help="align_points_per_cta of the pipeline's registration workers (sequential arm: library default 512)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -377,6 +379,7 @@ def main():
     k_ms, k_n = gicp.kernelTime("align_persistent")
     cov_ms, cov_n = gicp.kernelTime("knn_cov")
     idx_ms, idx_n = gicp.kernelTime("index_build")
+    probe_rounds = gicp.kernelTime("probe_rounds")[0]
     dbg = [gicp.kernelTime("debug%d" % i)[0] for i in range(4)]
     dbg6 = gicp.kernelTime("debug6")[0]
     dbg7 = gicp.kernelTime("debug7")[0]; dbg8 = gicp.kernelTime("debug8")[0]
@@ -401,7 +404,9 @@ def main():
     workload["input_pool"] = {"buffers": n_pool, "bytes": n_pool * scan_bytes, "l2_bytes": l2_bytes}
     odo = locus_b200.OdometryB200(local_rank, depth=args.depth, max_points=nraw, max_point_step=POINT_STEP)
     odo.voxel.setFilterFieldName("z"); odo.voxel.setFilterLimits(-100.0, 100.0); odo.voxel.setLeafSize(leaf)
-    odo.setGicpParams(**{k: getattr(gicp._p, k) for k, _ in api.GicpParams._fields_})
+    odo.setGicpParams(**dict({k: getattr(gicp._p, k) for k, _ in api.GicpParams._fields_},
+                             align_points_per_cta=args.pipeline_ppc))
+    workload["pipeline"] += ", %d source points per align CTA" % args.pipeline_ppc
     d_pool = [d_scans[seq(j)].clone() for j in range(n_pool)]
     h_pool = h_scans
     h_fout = [torch.empty(nraw * POINT_STEP, dtype=torch.uint8).pin_memory() for _ in range(2 * args.depth + 4)]
@@ -418,6 +423,7 @@ def main():
 
     def pipelined_run(submit_fn, steps, warmup):
         """K scans of one stream through the pipeline; returns (device ms, results of the timed scans, launches)"""
+        warmup = max(warmup, 3 * args.depth)     # every registration worker sizes its buffers before the timed region
         for i in range(1 + warmup):
             submit_fn(i)
         while odo.pending():
@@ -518,7 +524,7 @@ def main():
                          "objective_evals_mean": float(evals.mean()) if len(evals) else None,
                          "correspondences_mean": float(ncorr.mean()) if len(ncorr) else None,
                          "source_points_mean": float(nsrc.mean()) if len(nsrc) else None,
-                         "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms, "voxel_last_call_ms": vg.lastCallMs(),
+                         "knn_cov_kernel_ms": cov_ms, "index_build_ms": idx_ms, "cell_probe_rounds_total": probe_rounds, "voxel_last_call_ms": vg.lastCallMs(),
                          "align_last_launch_cycles": {"total": dbg[0], "block_reduce_publish": dbg[1],
                                                       "slot_wait_sum": dbg[2], "collectives": dbg[3], "leader_scalar_before_fdf": dbg6, "poll_rounds_thread0": dbg7,
                                                       "poll_publish_to_done_thread0": dbg8},

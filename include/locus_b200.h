@@ -119,7 +119,12 @@ typedef struct lb_gicp_params {
   int ransac_iterations;                /* setRANSACIterations(0) */
   int num_threads;                      /* setNumThreads */
   int enable_timing_output;             /* enableTimingOutput: spans are always in lb_gicp_result */
-  float index_cell_size;                /* voxel-hash cell size in metres; 0 = automatic */
+  float index_cell_size;                /* voxel-hash cell size in metres; 0 = automatic (a pure function of the cloud) */
+  int align_points_per_cta;             /* source points per CTA of the persistent align kernel; 0 = 512 (lowest latency
+                                           of one align: ~60 SMs for a 30k-point scan).  Larger values (1024, 2048) use
+                                           fewer SMs per align for longer: more aligns fit on the GPU at once, which is
+                                           what lb_odometry's workers want.  Changes the shape of the reduction, i.e. the
+                                           last bits of the pose, not the algorithm. */
 } lb_gicp_params;
 
 typedef struct lb_gicp_result {

@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "liblocus_b200.so")
+_SO = os.environ.get("LOCUS_B200_LIB") or os.path.join(_HERE, "liblocus_b200.so")   # env: experiments with variant builds
 
 LB_MEM_HOST, LB_MEM_DEVICE = 0, 1
 LB_OPT_BFGS, LB_OPT_GAUSS_NEWTON = 0, 1
@@ -38,7 +38,7 @@ class GicpParams(C.Structure):
         ("recompute_source_covariance", C.c_int), ("recompute_target_covariance", C.c_int),
         ("optimizer", C.c_int), ("execution", C.c_int), ("euclidean_fitness_epsilon", C.c_double),
         ("ransac_iterations", C.c_int), ("num_threads", C.c_int), ("enable_timing_output", C.c_int),
-        ("index_cell_size", C.c_float),
+        ("index_cell_size", C.c_float), ("align_points_per_cta", C.c_int),
     ]
 
 
@@ -226,6 +226,7 @@ class GicpB200:
     def setOptimizer(self, v): self._p.optimizer = int(v); self._apply()
     def setExecution(self, v): self._p.execution = int(v); self._apply()
     def setIndexCellSize(self, v): self._p.index_cell_size = float(v); self._apply()
+    def setAlignPointsPerCta(self, v): self._p.align_points_per_cta = int(v); self._apply()
     def getMaximumIterations(self): return self._p.max_iterations
     def getMaxCorrespondenceDistance(self): return self._p.max_correspondence_distance
     def getTransformationEpsilon(self): return self._p.transformation_epsilon

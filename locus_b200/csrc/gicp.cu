@@ -13,6 +13,8 @@
 #include <stdlib.h>
 
 #include <string>
+#include <condition_variable>
+#include <mutex>
 #include <vector>
 
 #include "align_cluster.cuh"
@@ -35,9 +37,8 @@ struct Cloud {
   size_t ncells = 0;
   uint64_t generation = 0;
   bool index_dirty = false;    // uploaded + geometry chosen, CSR index not built yet (built lazily in align)
-  float auto_cell = 0.f;       // cell size found by the last occupancy probe for this slot
-  size_t auto_n = 0;
-  float auto_diag = 0.f;
+  int keys_slot = -1;          // >= 0: that slot's scratch holds this cloud's cell keys and per-cell counts for `geom`
+                               // (left there by the accepted round of the occupancy probe)
 
   GridView view() const {
     GridView v;
@@ -113,9 +114,40 @@ struct lb_gicp {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timing = false;
   std::vector<KTimer> timers;
+  uint64_t probe_rounds = 0;       // occupancy-probe rounds since creation (diagnostic)
 };
 
 namespace {
+
+// One align() kernel occupies its SMs exclusively (255 registers x 256 threads = the whole register file) and its
+// CTAs spin on each other, so the persistent kernels of concurrently used handles (lb_odometry workers, or a
+// caller's own threads) must fit on the device TOGETHER: more CTAs than SMs would leave a cooperative grid waiting
+// for SMs held by other spinning grids.  Per device, launches take their CTA count from this budget and give it
+// back after the stream sync; a few SMs stay reserved for the short kernels (VoxelGrid, index, k-NN) of the other
+// pipeline stages.  A lone align always runs.
+constexpr int LB_MAX_DEVICES = 64;
+struct SmBudget {
+  std::mutex mu;
+  std::condition_variable cv;
+  int in_use = 0;
+};
+SmBudget g_sm_budget[LB_MAX_DEVICES];
+
+struct SmLease {
+  SmBudget* b = nullptr; int n = 0;
+  void acquire(int device, int ctas, int capacity) {
+    if (device < 0 || device >= LB_MAX_DEVICES) return;
+    b = &g_sm_budget[device]; n = ctas;
+    std::unique_lock<std::mutex> lk(b->mu);
+    b->cv.wait(lk, [&] { return b->in_use == 0 || b->in_use + n <= capacity; });
+    b->in_use += n;
+  }
+  ~SmLease() {
+    if (!b) return;
+    { std::lock_guard<std::mutex> lk(b->mu); b->in_use -= n; }
+    b->cv.notify_all();
+  }
+};
 
 KTimer* timer_for(lb_gicp* h, const char* name) {
   for (auto& t : h->timers) if (t.name == name) return &t;
@@ -262,7 +294,7 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
   LB_CUDA(cudaSetDevice(c.device));
   ScopedKernelTime kt(h, "index_build");
   const uint32_t N = (uint32_t)n;
-  cl.valid = false; cl.cov_valid = false; cl.index_dirty = false;
+  cl.valid = false; cl.cov_valid = false; cl.index_dirty = false; cl.keys_slot = -1;
   const uint8_t* d_src = (const uint8_t*)pts;
   if (mem == LB_MEM_HOST) {
     LB_TRY(S.stage.ensure(n * stride));
@@ -313,16 +345,15 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
     double diag = sqrt((double)ext[0] * ext[0] + (double)ext[1] * ext[1] + (double)ext[2] * ext[2]);
     if (!(area > 0)) area = diag * diag;
     double spacing = sqrt(area / (double)(N ? N : 1));
-    cell = (float)(2.5 * spacing);
+    cell = (float)(1.3 * spacing);     // first guess; lidar scans concentrate their points, so the bbox-surface spacing
+                                       // overestimates: 1.3x lands inside the accepted occupancy band in one round
     if (!(cell > 0.f)) cell = 1.0f;
     const double target = 6.0;
-    // consecutive clouds of one stream look alike: re-use the probed cell size while the point count
-    // and extent stay within +-30 % (the probe costs two launches and a host sync per round)
-    bool reuse = cl.auto_cell > 0.f && (double)N > 0.7 * (double)cl.auto_n && (double)N < 1.3 * (double)cl.auto_n &&
-                 diag > 0.7 * cl.auto_diag && diag < 1.3 * cl.auto_diag;
-    if (reuse) { cell = cl.auto_cell; g = make_geom(cell); }
+    // The cell size is a pure function of the cloud (no memory of earlier clouds): the same cloud gives the same
+    // grid, hence the same summation order in the align kernel and bit-identical poses, whichever handle or
+    // pipeline worker sees it.  The accepted round's keys and per-cell counts are what finish_index needs.
     LB_TRY(S.keys.ensure(n));
-    for (int round = 0; round < 4 && !reuse; round++) {
+    for (int round = 0; round < 4; round++) {
       g = make_geom(cell);
       size_t nc = (size_t)g.nx * g.ny * g.nz;
       LB_TRY(S.cell_cnt.ensure(nc + 1));
@@ -333,6 +364,7 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
       c.launches += 2;
       LB_CUDA(cudaMemcpyAsync(S.h_u32, S.d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
       LB_CUDA(cudaStreamSynchronize(c.stream));
+      h->probe_rounds++;
       double occ = (double)N / (double)(S.h_u32[0] ? S.h_u32[0] : 1);
       if (occ >= target / 2 && occ <= target * 2) break;
       if (N <= 8 || S.h_u32[0] <= 1) break;
@@ -341,7 +373,7 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
       if (scale < 0.25) scale = 0.25;
       cell = g.h * (float)scale;
     }
-    cl.auto_cell = g.h; cl.auto_n = N; cl.auto_diag = (float)diag;
+    cl.keys_slot = slot;
   }
   cl.geom = g;
   cl.ncells = (size_t)g.nx * g.ny * g.nz;
@@ -362,15 +394,19 @@ int finish_index(lb_gicp* h, Cloud& cl, int slot) {
   const uint32_t N = (uint32_t)cl.n;
   int key_bits = 1;
   while (key_bits < 32 && (1ull << key_bits) < (uint64_t)cl.ncells) key_bits++;
-  LB_TRY(S.keys.ensure(cl.n));
-  LB_TRY(S.cell_cnt.ensure(cl.ncells + 1));
+  const bool have_keys = cl.keys_slot == slot;     // the occupancy probe left keys + per-cell counts in this slot
+  cl.keys_slot = -1;
   LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
-  LB_CUDA(cudaMemsetAsync(S.cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
-  grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, cl.geom, S.keys.p, nullptr);
-  c.launches++;
+  if (!have_keys) {
+    LB_TRY(S.keys.ensure(cl.n));
+    LB_TRY(S.cell_cnt.ensure(cl.ncells + 1));
+    LB_CUDA(cudaMemsetAsync(S.cell_cnt.p, 0, (cl.ncells + 1) * sizeof(uint32_t), c.stream));
+    grid_keys_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, N, cl.geom, S.keys.p, nullptr);
+    c.launches++;
+  }
   uint32_t *sk = nullptr, *sv = nullptr;
   LB_TRY(radix_sort_pairs(c, S.sort, S.keys.p, nullptr, cl.n, key_bits, &sk, &sv));
-  grid_reorder_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, sk, sv, N, cl.pts.p, S.cell_cnt.p);
+  grid_reorder_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.raw.p, sk, sv, N, cl.pts.p, have_keys ? nullptr : S.cell_cnt.p);
   c.launches++;
   LB_TRY(exclusive_scan_u32(c, S.scan, S.cell_cnt.p, cl.cell_start.p, cl.ncells + 1, nullptr));
   LB_CUDA(cudaGetLastError());
@@ -391,8 +427,9 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    static int variant = -1;   // tuning aid: LB_KNN=warp selects the warp-per-query kernel (default: quad-per-query)
-    if (variant < 0) { const char* e = getenv("LB_KNN"); variant = (e && !strcmp(e, "warp")) ? 1 : 0; }
+    // tuning aid: LB_KNN=warp selects the warp-per-query kernel, LB_KNN=quadlocal the quad kernel with
+    // local-memory lists (default: quad-per-query with register-resident lists)
+    static const int variant = [] { const char* e = getenv("LB_KNN"); return (e && !strcmp(e, "warp")) ? 1 : (e && !strcmp(e, "quadlocal")) ? 2 : 0; }();
     if (variant == 1) {
       int blocks = cdiv(N, KW_WARPS);
       int max_blocks = c.sm_count * 4;
@@ -409,7 +446,8 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
         return t;
       }();
       const int split_from = qt.split_from, lazy_merge = qt.lazy_merge, qthreads = qt.qthreads;
-      if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
+      if (k <= 20 && variant == 0) knn_cov_quadreg_kernel<20><<<cdiv(4ll * N, KQ_THREADS), KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from);
+      else if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
       else knn_cov_quad_kernel<32><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
     }
   }
@@ -445,8 +483,9 @@ int prepare_clouds(lb_gicp* h, bool need_cov, bool src_knn, bool tgt_knn) {
 // CTAs of the align kernels: one thread per source point, at least 8 and at most one CTA per SM.
 // Both execution modes use the same grid so their reductions have the same shape (identical bits).
 int grid_for(lb_gicp* h, int n_src) {
-  static int ppc = 0;   // tuning aid: LB_PPC overrides the source points per CTA
-  if (!ppc) { const char* e = getenv("LB_PPC"); ppc = e ? atoi(e) : AL_PPC; if (ppc < AL_ACC) ppc = AL_ACC; }
+  static const int env_ppc = [] { const char* e = getenv("LB_PPC"); return e ? atoi(e) : 0; }();   // tuning aid
+  int ppc = h->P.align_points_per_cta > 0 ? h->P.align_points_per_cta : (env_ppc > 0 ? env_ppc : AL_PPC);
+  if (ppc < AL_ACC) ppc = AL_ACC;
   int g = cdiv(n_src, ppc);
   if (g < 8) g = 8;
   if (g > h->align_blocks) g = h->align_blocks;
@@ -553,6 +592,7 @@ int lb_gicp_default_params(lb_gicp_params* p) {
   p->num_threads = 1;
   p->enable_timing_output = 0;
   p->index_cell_size = 0.f;
+  p->align_points_per_cta = 0;
   return LB_OK;
 }
 
@@ -686,6 +726,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     h->epoch_base += 1ull << 20;      // > collectives per align
     bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT_CLUSTER && N <= (uint32_t)(CL_SIZE * CL_CAP);
     bool launched = false;
+    SmLease lease;     // released when this block ends, i.e. after the stream sync below
     if (use_cluster) {
       ClusterArgs ka;
       ka.c = ca; ka.gslots = h->cslots.p; ka.gcmd = h->cslots.p + CL_MAX_CTAS; ka.epoch_base = epoch_base;
@@ -717,8 +758,11 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       aa.debug = h->timing ? h->d_debug : nullptr;
       for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
       void* args[] = {&aa};
+      const int grid = grid_for(h, ca.n_src);
+      static const int reserve = [] { const char* e = getenv("LB_SM_RESERVE"); return e ? atoi(e) : 16; }();
+      lease.acquire(c.device, grid, h->align_blocks - reserve);
       ScopedKernelTime kt(h, "align_persistent");
-      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid_for(h, ca.n_src)), dim3(AL_THREADS), args, 0, c.stream));
+      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid), dim3(AL_THREADS), args, 0, c.stream));
       c.launches++;
     }
     if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
@@ -951,6 +995,7 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
     *ms_avg = (float)h->h_debug[name[5] - '0'];
     return LB_OK;
   }
+  if (!strcmp(name, "probe_rounds")) { *ms_avg = (float)h->probe_rounds; return LB_OK; }
   if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100
     int i = atoi(name + 5);
     if (i < 0 || i >= AL_MAXCTA) return LB_ERR_INVALID_ARG;

@@ -89,7 +89,7 @@ grid_reorder_kernel(const f4* __restrict__ raw, const uint32_t* __restrict__ sor
   uint32_t i = sorted_vals[s];
   f4 p = raw[i];
   pts[s] = f4{p.x, p.y, p.z, bits_to_float((int32_t)i)};
-  atomicAdd(&cell_cnt[sorted_keys[s]], 1u);
+  if (cell_cnt) atomicAdd(&cell_cnt[sorted_keys[s]], 1u);   // null: the occupancy probe already counted
 }
 
 // ------------------------------------------------------------------ K3 covariances
@@ -147,9 +147,29 @@ struct QuadList {
   }
 };
 
+// per-row hook of quad_scan_shell: lists without a shared gate do nothing
 template <int K>
+__device__ __forceinline__ void quad_row_done(QuadList<K>&, unsigned) {}
+// RegList: tighten the rejection gate to the quad-wide maximum of the lanes' (K/4)-th best keys.  The union of the
+// four lists then holds at least K >= k candidates that are not worse than the gate, so a candidate beyond it
+// can never be one of the k nearest.  Lanes hold disjoint quarters of the candidates, so the single-lane
+// threshold key[K-1] alone prunes 4x less than one list over all candidates would.
+template <int K>
+__device__ __forceinline__ void quad_row_done(RegList<K>& L, unsigned qmask) {
+  unsigned long long t = L.key[K / 4 - 1];
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    unsigned hi = __shfl_xor_sync(qmask, (unsigned)(t >> 32), o);
+    unsigned lo = __shfl_xor_sync(qmask, (unsigned)t, o);
+    unsigned long long u = ((unsigned long long)hi << 32) | lo;
+    t = u > t ? u : t;
+  }
+  L.gate = t;
+}
+
+template <int K, class List>
 __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int cy, int cz, int r, float qx, float qy,
-                                                float qz, int sub, QuadList<K>& L, int split_from) {
+                                                float qz, int sub, List& L, int split_from, unsigned qmask = 0u) {
   int z0 = imax_(cz - r, 0), z1 = imin_(cz + r, g.nz - 1);
   int y0 = imax_(cy - r, 0), y1 = imin_(cy + r, g.ny - 1);
   // r <= 1: the 4 lanes split the POINTS of every run (64-byte coalesced reads of dense cells);
@@ -179,6 +199,7 @@ __device__ __forceinline__ void quad_scan_shell(const GridView& g, int cx, int c
           L.push(dist2(qx, qy, qz, p.x, p.y, p.z), float_to_bits(p.w), (int)i);
         }
       }
+      if (qmask) quad_row_done(L, qmask);
     }
     return;
   }
@@ -270,6 +291,84 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
     if (sub == 0) worklist[atomicAdd(wl_count, 1u)] = s;
     return;
   }
+  double out[6];
+  cov_from_moments(sum, m2, k, eps, out);
+  if (sub == 0) {
+    double* d = cov + 6 * (size_t)s;
+#pragma unroll
+    for (int e = 0; e < 6; e++) d[e] = out[e];
+  }
+}
+
+// K3, register-resident variant (the default for k <= 20).  Same quad-per-query scan, same (d2, index) order and
+// same summation order as knn_cov_quad_kernel, hence the same bits; what changes is where the candidate lists
+// live.  Each lane's sorted list is a RegList (static indexing, fully unrolled: ~60 registers), so an insertion is
+// ~100 independent select instructions instead of a chain of dependent local-memory loads and stores -- the
+// long-scoreboard stalls that held the old kernel at ~16 % of the issue rate.  The 4-way merge needs a moving
+// head per lane, i.e. dynamic indexing: the lists are copied once per merge into shared memory ([entry][thread]
+// layout, conflict-free) and popped from there.  Lists hold keys only; the k selected points are re-read through
+// their original index (`raw`, the original-order copy of the cloud: same coordinates as the sorted copy).
+constexpr int KQ_THREADS = 128;
+#ifndef KQ_MINB
+#define KQ_MINB 4
+#endif
+template <int K>
+__global__ void __launch_bounds__(KQ_THREADS, KQ_MINB)
+knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps, double* __restrict__ cov, int split_from) {
+  __shared__ uint32_t m_d[(K + 1) * KQ_THREADS];
+  __shared__ uint32_t m_o[(K + 1) * KQ_THREADS];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t s = t >> 2;
+  const int sub = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+  if (s >= (uint32_t)g.n) return;   // whole quads exit together
+  const int tid = threadIdx.x;
+  m_d[K * KQ_THREADS + tid] = 0xffffffffu; m_o[K * KQ_THREADS + tid] = 0xffffffffu;   // sentinel behind every list
+  f4 q = g.pts[s];
+  RegList<K> L;
+  L.init();
+  int cx, cy, cz; float minfrac;
+  query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
+  int r0, r1;
+  ring_range(g, cx, cy, cz, r0, r1);
+  double sum[3], m2[6];
+  for (int r = r0; r <= r1; r++) {
+    quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L, split_from, qmask);
+    quad_row_done(L, qmask);
+    int total = L.cnt;
+    total += __shfl_xor_sync(qmask, total, 1);
+    total += __shfl_xor_sync(qmask, total, 2);
+    if (total < k && r < r1) continue;   // not even k candidates yet: next shell
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      m_d[j * KQ_THREADS + tid] = (uint32_t)(L.key[j] >> 32);
+      m_o[j * KQ_THREADS + tid] = (uint32_t)L.key[j];
+    }
+    int p = 0, found = 0;
+    float kth = 3.0e38f;
+    sum[0] = sum[1] = sum[2] = 0.0;
+    m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+    for (int round = 0; round < k; round++) {
+      const uint32_t hd = m_d[p * KQ_THREADS + tid], ho = m_o[p * KQ_THREADS + tid];
+      uint32_t bd = hd, bo = ho;
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        uint32_t od = __shfl_xor_sync(qmask, bd, o);
+        uint32_t oo = __shfl_xor_sync(qmask, bo, o);
+        if (od < bd || (od == bd && oo < bo)) { bd = od; bo = oo; }
+      }
+      if (bd == 0xffffffffu && bo == 0xffffffffu) break;   // fewer than k points in everything scanned so far
+      if (bd == hd && bo == ho) p++;                       // original indices are unique: exactly one lane pops
+      found++;
+      kth = bits_to_float((int32_t)bd);
+      f4 pt = raw[bo];
+      sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
+      m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
+      m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+    }
+    if (found == k && kth < ring_bound2(g, r, minfrac)) break;
+  }
+  // either the bound proved the top-k final, or the whole grid was scanned (r1 = last ring): final both ways
   double out[6];
   cov_from_moments(sum, m2, k, eps, out);
   if (sub == 0) {
@@ -1225,7 +1324,10 @@ struct DeviceBackend {
   }
 };
 
-__global__ void __launch_bounds__(AL_THREADS, 1)
+#ifndef AL_MINB
+#define AL_MINB 1
+#endif
+__global__ void __launch_bounds__(AL_THREADS, AL_MINB)
 align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   __shared__ AlignShared sh;
   Collective co;

@@ -179,6 +179,41 @@ struct KnnList {
   }
 };
 
+// Sorted candidate list with STATIC indexing only, so that a fully unrolled build keeps it in registers (a list
+// indexed by a loop-carried position lives in local memory and every insertion becomes a chain of dependent
+// loads and stores).  Order = better(): ascending (d2, original index), packed into one 64-bit key -- d2 >= 0, so
+// its float bits are monotone as an unsigned integer.  Unfilled entries hold the all-ones sentinel.  Only the key
+// is kept: the point itself is fetched again through its original index when it is needed.
+// `gate`: an extra rejection threshold the caller may tighten (see knn_cov_quadreg_kernel); candidates with
+// key >= gate are known not to belong to the result.
+template <int K>
+struct RegList {
+  unsigned long long key[K];
+  unsigned long long gate;
+  int cnt;
+  LB_HD static unsigned long long make_key(float d2, int orig) {
+    return ((unsigned long long)(uint32_t)float_to_bits(d2) << 32) | (uint32_t)orig;
+  }
+  LB_HD void init() {
+    cnt = 0; gate = ~0ull;
+#pragma unroll
+    for (int i = 0; i < K; i++) key[i] = ~0ull;
+  }
+  LB_HD void push(float d2, int orig, int /*sorted position: not kept*/ = 0) {
+    const unsigned long long k = make_key(d2, orig);
+    if (k >= key[K - 1] || k >= gate) return;
+    cnt += (cnt < K) ? 1 : 0;
+    bool here = true;                       // k < (old) key[j]
+#pragma unroll
+    for (int j = K - 1; j > 0; j--) {
+      const bool up = k < key[j - 1];       // the new entry belongs below j: slot j takes its lower neighbour
+      key[j] = up ? key[j - 1] : (here ? k : key[j]);
+      here = up;
+    }
+    if (here) key[0] = k;
+  }
+};
+
 template <int KMAX>
 LB_HD int knn(const GridView& g, float qx, float qy, float qz, int k, KnnList<KMAX>& L) {
   L.init(k);

@@ -25,6 +25,22 @@ struct HGrid {
 };
 
 extern "C" {
+// RegList (the register-resident candidate list of knn_cov_quadreg_kernel): after n pushes of (d2, orig) it must
+// hold the K best in ascending (d2, orig) order.  gate_d2 >= 0: candidates not better than (gate_d2, gate_orig)
+// are rejected on top of that.  out_*: K entries (-1 when unfilled).
+void hh_reglist_topk(const float* d2, const int* orig, int n, float gate_d2, int gate_orig, int* out_orig, float* out_d2, int* out_cnt) {
+  RegList<20> L;
+  L.init();
+  if (gate_d2 >= 0.f) L.gate = RegList<20>::make_key(gate_d2, gate_orig);
+  for (int i = 0; i < n; i++) L.push(d2[i], orig[i]);
+  for (int j = 0; j < 20; j++) {
+    bool filled = L.key[j] != ~0ull;
+    out_orig[j] = filled ? (int)(uint32_t)L.key[j] : -1;
+    out_d2[j] = filled ? bits_to_float((int32_t)(L.key[j] >> 32)) : -1.0f;
+  }
+  *out_cnt = L.cnt;
+}
+
 
 // CPU stand-in for the GPU index build (min/max, keys, stable sort, CSR).
 void* hh_grid_build(const float* xyz, int n, int stride_f, float h) {

@@ -97,3 +97,25 @@ def test_gauss_newton_matches_oracle(harness, oracle):
         r = oracle.gicp_align(s, t, prm)
         T, info, d = _hh_align(harness, s, t, h, prm, opt=1)
         assert np.array_equal(r["T"], T), name
+
+
+@pytest.mark.parametrize("n", [0, 5, 20, 21, 300])
+@pytest.mark.parametrize("gated", [False, True])
+def test_reglist_keeps_topk_sorted(harness, n, gated):
+    """RegList<20>.push == stable top-20 by (d2, original index), ties and duplicates included; with a gate,
+    only candidates strictly better than the gate key are eligible"""
+    rng = np.random.default_rng(n)
+    d2 = rng.choice(np.array([0.0, 0.25, 0.5, 1.0, 1e-30, 3e30], np.float32), n) if n else np.zeros(0, np.float32)
+    d2 = np.where(rng.random(n) < 0.5, d2, rng.random(n).astype(np.float32)).astype(np.float32)
+    orig = rng.permutation(max(n, 1) * 3)[:n].astype(np.int32)
+    oo = np.zeros(20, np.int32); od = np.zeros(20, np.float32); cnt = C.c_int(0)
+    gd, go = (np.float32(0.5), 7) if gated else (np.float32(-1.0), 0)
+    harness.hh_reglist_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    harness.hh_reglist_topk(_p(d2), _p(orig), n, gd, go, _p(oo), _p(od), C.byref(cnt))
+    ok = np.ones(n, bool) if not gated else ((d2 < gd) | ((d2 == gd) & (orig < go)))
+    idx = np.flatnonzero(ok)
+    order = idx[np.lexsort((orig[idx], d2[idx]))][:20]
+    m = len(order)
+    assert cnt.value == m
+    assert np.array_equal(oo[:m], orig[order]) and np.array_equal(od[:m], d2[order])
+    assert (oo[m:] == -1).all()
