@@ -20,7 +20,11 @@
 #include <thread>
 #include <vector>
 
+#ifdef LB_ODOMETRY_STUB          // TEST-ONLY build without CUDA: tests/odometry_harness.cpp supplies fake stages
+#include "odometry_stub.h"
+#else
 #include "prims.cuh"
+#endif
 
 using namespace lb;
 
