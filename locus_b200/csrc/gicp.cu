@@ -54,13 +54,13 @@ struct Cloud {
 struct Scratch {
   Ctx c;                         // copy of the handle context with this slot's stream
   DBuf<uint8_t> stage;           // H2D staging of the caller cloud
-  DBuf<uint32_t> keys, cell_cnt;
+  DBuf<uint32_t> keys, cell_cnt, worklist;   // worklist: queries the quad k-NN kernel hands to the tail kernel
   SortWork sort;
   ScanWork scan;
   BBoxAcc* d_acc = nullptr; BBoxAcc* h_acc = nullptr;
   uint32_t* d_u32 = nullptr; uint32_t* h_u32 = nullptr;
   void release() {
-    stage.release(); keys.release(); cell_cnt.release();
+    stage.release(); keys.release(); cell_cnt.release(); worklist.release();
     sort.ka.release(); sort.kb.release(); sort.va.release(); sort.vb.release(); sort.hist.release();
     sort.scan.sums.release(); scan.sums.release();
     if (d_acc) cudaFree(d_acc);
@@ -446,7 +446,18 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
         return t;
       }();
       const int split_from = qt.split_from, lazy_merge = qt.lazy_merge, qthreads = qt.qthreads;
-      if (k <= 20 && variant == 0) knn_cov_quadreg_kernel<20><<<cdiv(4ll * N, KQ_THREADS), KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from);
+      if (k <= 20 && variant == 0) {
+        static const int ring_cap = [] { const char* e = getenv("LB_RING_CAP"); return e ? atoi(e) : 6; }();   // tuning aid (sweep on B200: 4-6 best for a 500k-point submap, >= 6 free for a 30k scan)
+        Scratch& S = h->sc[slot];
+        LB_TRY(S.worklist.ensure(N));
+        uint32_t* d_wl = S.d_u32 + 4;      // [0] is the occupancy probe's counter
+        LB_CUDA(cudaMemsetAsync(d_wl, 0, sizeof(uint32_t), c.stream));
+        knn_cov_quadreg_kernel<20><<<cdiv(4ll * N, KQ_THREADS), KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from,
+                                                                                        ring_cap, S.worklist.p, d_wl);
+        // queries of sparse neighbourhoods (count read on the device: no host sync; a few resident warps when empty)
+        knn_cov_tail_kernel<20><<<c.sm_count * 2, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, S.worklist.p, d_wl);
+        c.launches++;
+      }
       else if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
       else knn_cov_quad_kernel<32><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
     }

@@ -314,7 +314,8 @@ constexpr int KQ_THREADS = 128;
 #endif
 template <int K>
 __global__ void __launch_bounds__(KQ_THREADS, KQ_MINB)
-knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps, double* __restrict__ cov, int split_from) {
+knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps, double* __restrict__ cov, int split_from,
+                       int ring_cap, uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count) {
   __shared__ uint32_t m_d[(K + 1) * KQ_THREADS];
   __shared__ uint32_t m_o[(K + 1) * KQ_THREADS];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,13 +333,18 @@ knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps
   int r0, r1;
   ring_range(g, cx, cy, cz, r0, r1);
   double sum[3], m2[6];
-  for (int r = r0; r <= r1; r++) {
+  // Shell r of a query in a sparse corner of the grid is (2r+1)^2 mostly empty rows of dependent look-ups: past
+  // ring_cap the query goes to knn_cov_tail_kernel, where a whole warp shares the rows of each shell.
+  bool done = r1 <= ring_cap;          // the whole grid gets scanned below: final even without the bound test
+  const int r_last = r1 < ring_cap ? r1 : ring_cap;
+  for (int r = r0; r <= r_last; r++) {
     quad_scan_shell<K>(g, cx, cy, cz, r, q.x, q.y, q.z, sub, L, split_from, qmask);
     quad_row_done(L, qmask);
     int total = L.cnt;
     total += __shfl_xor_sync(qmask, total, 1);
     total += __shfl_xor_sync(qmask, total, 2);
-    if (total < k && r < r1) continue;   // not even k candidates yet: next shell
+    if (total < k && r < r_last) continue;   // not even k candidates yet: next shell
+    if (total < k && !done) break;           // capped and still short of k: the tail kernel finishes this query
 #pragma unroll
     for (int j = 0; j < K; j++) {
       m_d[j * KQ_THREADS + tid] = (uint32_t)(L.key[j] >> 32);
@@ -366,9 +372,12 @@ knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps
       m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
       m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
     }
-    if (found == k && kth < ring_bound2(g, r, minfrac)) break;
+    if (found == k && kth < ring_bound2(g, r, minfrac)) { done = true; break; }
   }
-  // either the bound proved the top-k final, or the whole grid was scanned (r1 = last ring): final both ways
+  if (!done) {
+    if (sub == 0) worklist[atomicAdd(wl_count, 1u)] = s;
+    return;
+  }
   double out[6];
   cov_from_moments(sum, m2, k, eps, out);
   if (sub == 0) {
