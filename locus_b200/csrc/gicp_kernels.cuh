@@ -19,9 +19,12 @@
 namespace lb {
 
 constexpr int AL_THREADS = 256;      // threads per CTA of the align kernels (255 registers for the leader warp)
-constexpr int AL_ACC_WARPS = 4;      // warps that accumulate objective terms (shuffle throughput bounds the reduce)
+#ifndef AL_ACC_WARPS_CFG
+#define AL_ACC_WARPS_CFG 4
+#endif
+constexpr int AL_ACC_WARPS = AL_ACC_WARPS_CFG;   // warps that accumulate objective terms (shuffle throughput bounds the reduce)
 constexpr int AL_ACC = AL_ACC_WARPS * 32;
-constexpr int AL_PPC = 512;          // source points per CTA (4 per accumulating lane)
+constexpr int AL_PPC = AL_ACC * 4;   // source points per CTA (4 per accumulating lane, register-resident)
 constexpr int AL_MAXV = 28;          // widest reduction (Gauss-Newton)
 constexpr int AL_PSTRIDE = 32;       // words per CTA slot
 constexpr int AL_MAXB = 8;           // slots per polling lane: supports up to 256 CTAs
@@ -1253,8 +1256,7 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
   const int t = acc_lane();
   if (t >= 0 && t < AL_ACC) {
     int h = 0;
-#pragma unroll
-    for (int k = 0; k < AL_THREADS / AL_ACC; k++) h += s_hits[t + k * AL_ACC];
+    for (int k = t; k < AL_THREADS; k += AL_ACC) h += s_hits[k];
     cnt[0] = (double)h;
   }
   if (end - begin <= AL_PPC && t >= 0 && t < AL_ACC) {
