@@ -505,10 +505,15 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "traffic": ncu_traffic("align_persistent_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms, "launches_timed": int(k_n), "avg_launch_ms_sequential": k_seq_ms,
+                "kernel_share_of_sequential_step": (k_seq_ms / (seq_ms_max / args.steps)) if seq_ms_max else None,
+                "aligns_in_flight_mean": (k_ms / (dev_ms_max / args.steps)) if dev_ms_max else None,
                 "note": "working set (<= 5 MB) is L2-resident: this kernel is bound by the latency of its grid-wide "
                         "all-reduces, not by HBM (SURVEY H3); fraction reported for information.  avg_launch_ms is "
                         "measured inside the pipelined timed region (several aligns + the next scans' kernels share the "
-                        "GPU), avg_launch_ms_sequential with the kernel alone on the GPU"}
+                        "GPU), avg_launch_ms_sequential with the kernel alone on the GPU: kernel_share_of_sequential_step is "
+                        "the share the ncu launch list of the sequential calls shows (profiles/r1_launches*.md); in the "
+                        "pipelined region kernels of different scans overlap, so avg_launch_ms / ms_per_step = the mean "
+                        "number of aligns in flight, not a share"}
 
     line = {"metric": "gicp_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
