@@ -233,7 +233,7 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   }
   // persistent kernel: one CTA per SM, co-resident (cooperative launch)
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel, AL_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel<AL_PPL>, AL_THREADS, 0);
   h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
   if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
   if (h->slots.ensure((size_t)2 * h->c.sm_count * AL_PSTRIDE) != LB_OK ||
@@ -773,7 +773,10 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       static const int reserve = [] { const char* e = getenv("LB_SM_RESERVE"); return e ? atoi(e) : 16; }();
       lease.acquire(c.device, grid, h->align_blocks - reserve);
       ScopedKernelTime kt(h, "align_persistent");
-      LB_CUDA(cudaLaunchCooperativeKernel((void*)align_persistent_kernel, dim3(grid), dim3(AL_THREADS), args, 0, c.stream));
+      // points per CTA up to 512: 4 per accumulating lane in registers; up to 1024: 8 (beyond: read back from L2)
+      const int chunk = cdiv(ca.n_src, grid);
+      void* kfn = chunk <= AL_PPC ? (void*)align_persistent_kernel<AL_PPL> : (void*)align_persistent_kernel<2 * AL_PPL>;
+      LB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(AL_THREADS), args, 0, c.stream));
       c.launches++;
     }
     if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));

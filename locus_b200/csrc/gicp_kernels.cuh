@@ -1071,15 +1071,18 @@ __device__ __forceinline__ int acc_lane() { return (int)threadIdx.x - 32 * AL_AC
 
 // A lane's correspondences, register-resident across all objective evaluations of one outer iteration
 // (the correspondences are fixed during the inner solve, gicp.hpp:518-524): zero memory traffic per evaluation.
-struct PointCache {
-  float px[AL_PPL], py[AL_PPL], pz[AL_PPL], qx[AL_PPL], qy[AL_PPL], qz[AL_PPL];
-  double M[AL_PPL][6];
+template <int PPL>
+struct PointCacheT {
+  float px[PPL], py[PPL], pz[PPL], qx[PPL], qy[PPL], qz[PPL];
+  double M[PPL][6];
 };
+using PointCache = PointCacheT<AL_PPL>;
 
-__device__ __forceinline__ void cache_load(const ObjArgs& a, int begin, int end, PointCache& pc) {
+template <int PPL>
+__device__ __forceinline__ void cache_load(const ObjArgs& a, int begin, int end, PointCacheT<PPL>& pc) {
   const int t = acc_lane();
 #pragma unroll
-  for (int j = 0; j < AL_PPL; j++) {
+  for (int j = 0; j < PPL; j++) {
     int s = begin + t + AL_ACC * j;
     bool ok = (t >= 0 && t < AL_ACC && s < end);
     f4 c = ok ? a.corr[s] : f4{0.f, 0.f, 0.f, bits_to_float(-1)};
@@ -1092,11 +1095,11 @@ __device__ __forceinline__ void cache_load(const ObjArgs& a, int begin, int end,
   }
 }
 
-template <int NV>
-__device__ __forceinline__ void objective_from_cache(const PointCache& pc, const float* T, const double* dP, const double* dT,
+template <int NV, int PPL>
+__device__ __forceinline__ void objective_from_cache(const PointCacheT<PPL>& pc, const float* T, const double* dP, const double* dT,
                                                      const double* dS, double* acc) {
 #pragma unroll
-  for (int j = 0; j < AL_PPL; j++) {
+  for (int j = 0; j < PPL; j++) {
     if constexpr (NV == 13) objective_terms(T, pc.px[j], pc.py[j], pc.pz[j], pc.qx[j], pc.qy[j], pc.qz[j], pc.M[j], acc);
     else gn_terms(T, dP, dT, dS, pc.px[j], pc.py[j], pc.pz[j], pc.qx[j], pc.qy[j], pc.qz[j], pc.M[j], acc);
   }
@@ -1238,7 +1241,8 @@ __device__ __forceinline__ void grid_all_reduce(const AlignArgs& a, AlignShared&
   if (prof) { long long t2 = clock64(); sh.t_reduce += t1 - t0; sh.t_wait += t2 - t1; sh.n_coll++; sh.t_mark = t2; }
 }
 
-__device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co, PointCache& pc) {
+template <int PPL>
+__device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& sh, Collective& co, PointCacheT<PPL>& pc) {
   float T[12]; double R[9];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
@@ -1259,15 +1263,15 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
     for (int k = t; k < AL_THREADS; k += AL_ACC) h += s_hits[k];
     cnt[0] = (double)h;
   }
-  if (end - begin <= AL_PPC && t >= 0 && t < AL_ACC) {
+  if (end - begin <= PPL * AL_ACC && t >= 0 && t < AL_ACC) {
     ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
-    cache_load(oa, begin, end, pc);
+    cache_load<PPL>(oa, begin, end, pc);
   }
   grid_all_reduce<1>(a, sh, co, cnt);
 }
 
-template <int NV>
-__device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh, Collective& co, const PointCache& pc) {
+template <int NV, int PPL>
+__device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh, Collective& co, const PointCacheT<PPL>& pc) {
   float T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
@@ -1277,8 +1281,8 @@ __device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh
   int begin, end;
   cta_chunk(a.c.n_src, begin, end);
   const int t = acc_lane();
-  if (end - begin <= AL_PPC) {
-    if (t >= 0 && t < AL_ACC) objective_from_cache<NV>(pc, T, sh.D, sh.D + 9, sh.D + 18, acc);
+  if (end - begin <= PPL * AL_ACC) {
+    if (t >= 0 && t < AL_ACC) objective_from_cache<NV, PPL>(pc, T, sh.D, sh.D + 9, sh.D + 18, acc);
   } else {
     ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
     objective_from_global<NV>(oa, T, sh.D, sh.D + 9, sh.D + 18, begin, end, acc);
@@ -1287,14 +1291,15 @@ __device__ __forceinline__ void do_objective(const AlignArgs& a, AlignShared& sh
 }
 
 // Backend of bfgs.h for the leader warp (all 32 lanes call every method together).
-struct DeviceBackend {
+template <int PPL>
+struct DeviceBackendT {
   const AlignArgs& a;
   AlignShared& sh;
   Collective& co;
-  PointCache& pc;     // warp 0 never accumulates: its cache is never read
+  PointCacheT<PPL>& pc;     // warp 0 never accumulates: its cache is never read
   int m;
 
-  __device__ DeviceBackend(const AlignArgs& a_, AlignShared& sh_, Collective& co_, PointCache& pc_)
+  __device__ DeviceBackendT(const AlignArgs& a_, AlignShared& sh_, Collective& co_, PointCacheT<PPL>& pc_)
       : a(a_), sh(sh_), co(co_), pc(pc_), m(0) {}
 
   // the 12 trigonometric values of a state, one per lane, broadcast to the warp
@@ -1322,7 +1327,7 @@ struct DeviceBackend {
     if (lane < 9) sh.R[lane] = R[lane];
     if (lane == 0) sh.op = OP_CORR;
     __syncthreads();
-    do_correspond(a, sh, co, pc);
+    do_correspond<PPL>(a, sh, co, pc);
     m = (int)sh.bc[0];
     return m;
   }
@@ -1337,7 +1342,7 @@ struct DeviceBackend {
     if (lane == 0) sh.op = OP_FDF;
     if (blockIdx.x == 0 && threadIdx.x == 0) sh.t_scalar += clock64() - sh.t_mark;   // leader time since the last collective
     __syncthreads();
-    do_objective<13>(a, sh, co, pc);
+    do_objective<13, PPL>(a, sh, co, pc);
     double sums[13];
 #pragma unroll
     for (int e = 0; e < 13; e++) sums[e] = sh.bc[e];
@@ -1356,7 +1361,7 @@ struct DeviceBackend {
     if (lane < 27) sh.D[lane] = D[lane];
     if (lane == 0) sh.op = OP_GN;
     __syncthreads();
-    do_objective<28>(a, sh, co, pc);
+    do_objective<28, PPL>(a, sh, co, pc);
     *f = sh.bc[0] / (double)m;
 #pragma unroll
     for (int e = 0; e < 6; e++) b[e] = sh.bc[1 + e];
@@ -1369,6 +1374,9 @@ struct DeviceBackend {
 #ifndef AL_MINB
 #define AL_MINB 1
 #endif
+// PPL = source points per accumulating lane kept in registers: 4 (512 points per CTA: lowest latency) or 8 (1024
+// points per CTA: half the SMs per align, what the odometry pipeline's workers use)
+template <int PPL>
 __global__ void __launch_bounds__(AL_THREADS, AL_MINB)
 align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   __shared__ AlignShared sh;
@@ -1377,8 +1385,8 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   const long long t_begin = clock64();
   if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
   if (threadIdx.x < 32) {
-    PointCache pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
-    DeviceBackend be(a, sh, co, pc_unused);
+    PointCacheT<PPL> pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
+    DeviceBackendT<PPL> be(a, sh, co, pc_unused);
     OuterResult r;
     gicp_outer_loop(be, a.P, a.guess, r);
     if (threadIdx.x == 0) sh.op = OP_EXIT;
@@ -1391,14 +1399,14 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       }
     }
   } else {
-    PointCache pc;
+    PointCacheT<PPL> pc;
     for (;;) {
       __syncthreads();
       const int op = sh.op;
       if (op == OP_EXIT) break;
-      if (op == OP_CORR) do_correspond(a, sh, co, pc);
-      else if (op == OP_FDF) do_objective<13>(a, sh, co, pc);
-      else do_objective<28>(a, sh, co, pc);
+      if (op == OP_CORR) do_correspond<PPL>(a, sh, co, pc);
+      else if (op == OP_FDF) do_objective<13, PPL>(a, sh, co, pc);
+      else do_objective<28, PPL>(a, sh, co, pc);
     }
   }
 }

@@ -285,6 +285,99 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
 
 static_assert(RS_WARPS * 32 == 256, "digit scan assumes 256 threads per block");
 
+// Small inputs (<= RS_FUSED_MAX_BLOCKS tiles): no separate scan launches.  The histogram kernel writes block-major
+// counts (coalesced), and every scatter block derives its own 256 offsets from the whole table -- a few coalesced
+// 1 KB reads per tile, L2-resident -- instead of three scan kernels per pass between histogram and scatter.
+constexpr uint32_t RS_FUSED_MAX_BLOCKS = 128;
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rs_hist_bm_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = base + j * (RS_WARPS * 32) + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  block_hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rs_scatter_fused_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                        uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                        const uint32_t* __restrict__ block_hist /*[nblocks][256]*/, uint32_t nblocks) {
+  __shared__ uint32_t whist[RS_WARPS][256];
+  __shared__ uint32_t scan_sm[RS_WARPS + 1];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_WARPS * 32) (&whist[0][0])[i] = 0;
+  // global offset of (digit d = threadIdx.x, this tile): digits below d in all tiles + digit d in the tiles before
+  uint32_t before = 0, total = 0;
+  {
+    const uint32_t d = threadIdx.x;
+    uint32_t b = 0;
+    for (; b + 4 <= nblocks; b += 4) {
+      uint32_t c0 = block_hist[(b + 0) * 256 + d], c1 = block_hist[(b + 1) * 256 + d];
+      uint32_t c2 = block_hist[(b + 2) * 256 + d], c3 = block_hist[(b + 3) * 256 + d];
+      total += (c0 + c1) + (c2 + c3);
+      before += (b + 0 < blockIdx.x ? c0 : 0u) + (b + 1 < blockIdx.x ? c1 : 0u) + (b + 2 < blockIdx.x ? c2 : 0u) +
+                (b + 3 < blockIdx.x ? c3 : 0u);
+    }
+    for (; b < nblocks; b++) {
+      uint32_t c = block_hist[b * 256 + d];
+      total += c;
+      before += (b < blockIdx.x) ? c : 0u;
+    }
+  }
+  uint32_t all;
+  const uint32_t digit_base = block_excl_scan<RS_WARPS * 32>(total, &all, scan_sm);   // (syncs: whist is zeroed)
+  const uint32_t warp_base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt_mask = (1u << l) - 1u;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = warp_base + j * 32 + l;
+    bool valid = i < n;
+    key[j] = valid ? keys_in[i] : 0xffffffffu;
+    val[j] = valid ? (vals_in ? vals_in[i] : i) : 0u;
+    uint32_t d = valid ? ((key[j] >> shift) & 255u) : 256u;
+    uint32_t mask = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(mask) - 1;
+    uint32_t old = 0;
+    if (l == leader && d < 256u) {
+      old = whist[w][d];
+      whist[w][d] = old + __popc(mask);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[j] = old + __popc(mask & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    uint32_t d = threadIdx.x;
+    uint32_t run = digit_base + before;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      uint32_t cnt = whist[ww][d];
+      whist[ww][d] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    uint32_t i = warp_base + j * 32 + l;
+    if (i < n) {
+      uint32_t d = (key[j] >> shift) & 255u;
+      uint32_t pos = whist[w][d] + rank[j];
+      keys_out[pos] = key[j];
+      vals_out[pos] = val[j];
+    }
+  }
+}
+
 int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
                      uint32_t** keys_out, uint32_t** vals_out) {
   if (n > 0xfffffff0ull) { set_error("radix_sort_pairs: n too large"); return LB_ERR_INVALID_ARG; }
@@ -297,13 +390,20 @@ int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_
   if (passes < 1) passes = 1;
   const uint32_t* kin = keys_in; const uint32_t* vin = vals_in;
   uint32_t* kout = w.ka.p; uint32_t* vout = w.va.p;
+  const bool fused = nblocks <= RS_FUSED_MAX_BLOCKS;
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
-    rs_hist_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, nblocks);
-    c.launches++;
-    LB_TRY(exclusive_scan_u32(c, w.scan, w.hist.p, w.hist.p, (size_t)256 * nblocks, nullptr));
-    rs_scatter_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
-    c.launches++;
+    if (fused) {
+      rs_hist_bm_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p);
+      rs_scatter_fused_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
+      c.launches += 2;
+    } else {
+      rs_hist_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, nblocks);
+      c.launches++;
+      LB_TRY(exclusive_scan_u32(c, w.scan, w.hist.p, w.hist.p, (size_t)256 * nblocks, nullptr));
+      rs_scatter_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
+      c.launches++;
+    }
     kin = kout; vin = vout;
     if (kout == w.ka.p) { kout = w.kb.p; vout = w.vb.p; } else { kout = w.ka.p; vout = w.va.p; }
   }

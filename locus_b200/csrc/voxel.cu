@@ -102,6 +102,81 @@ vg_gather_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t
   for (int f = 0; f < F.n_ff; f++) d[f] = *reinterpret_cast<const float*>(p + F.ff_off[f]);
 }
 
+// The common record layout (x, y, z, intensity averaged: 16-byte records).  A warp owns 32 consecutive voxels, i.e.
+// ONE contiguous range of the voxel-sorted records: the warp copies that range through shared memory with
+// coalesced 16-byte loads, and every lane then adds up its own voxel's records from shared memory in ascending
+// input order (the order defines the float32 rounding) -- no per-lane chains of dependent global loads, which is
+// what made the thread-per-voxel kernel below take 50 us for 30 k voxels.
+constexpr int VG4_TILE = 256;       // records per warp tile (4 KB)
+__global__ void __launch_bounds__(128)
+vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ keys,
+                    const uint32_t* __restrict__ vals, const float4* __restrict__ rec,
+                    const uint32_t* __restrict__ seg_start, const uint32_t* n_seg_dev,
+                    const uint32_t* __restrict__ slot /*nullable*/, const uint32_t* __restrict__ keep /*nullable*/,
+                    uint32_t n, VoxelFieldsDev F, uint32_t capacity, uint8_t* __restrict__ out,
+                    int32_t* __restrict__ out_voxel_idx) {
+  __shared__ float4 tile[4][VG4_TILE];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t n_seg = *n_seg_dev;
+  const uint32_t s0 = (blockIdx.x * 4 + wib) * 32;
+  if (s0 >= n_seg) return;                                  // whole warp
+  const uint32_t s = s0 + lane;
+  const bool seg = s < n_seg;
+  uint32_t a = 0, e = 0, k = 0;
+  if (seg) {
+    a = seg_start[s];
+    k = keys[a];
+    // segment end: next segment's start, or the first sentinel key after the last voxel
+    if (s + 1 < n_seg) e = seg_start[s + 1];
+    else { e = a + 1; while (e < n && keys[e] == k) e++; }
+  }
+  const uint32_t n_act = min(32u, n_seg - s0);
+  const uint32_t r0 = __shfl_sync(0xffffffffu, a, 0);
+  const uint32_t r1 = __shfl_sync(0xffffffffu, e, (int)n_act - 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t t0 = r0; t0 < r1; t0 += VG4_TILE) {
+    const uint32_t t1 = min(r1, t0 + (uint32_t)VG4_TILE);
+    for (uint32_t i = t0 + lane; i < t1; i += 32) tile[wib][i - t0] = rec[i];
+    __syncwarp();
+    if (seg) {
+      uint32_t lo = max(a, t0), hi = min(e, t1);
+      if (lo < hi && lo == a) { acc = tile[wib][lo - t0]; lo++; }      // the sum starts from the first record itself
+      for (; lo + 4 <= hi; lo += 4) {
+        const float4 v0 = tile[wib][lo - t0], v1 = tile[wib][lo + 1 - t0], v2 = tile[wib][lo + 2 - t0], v3 = tile[wib][lo + 3 - t0];
+        acc.x = acc.x + v0.x; acc.y = acc.y + v0.y; acc.z = acc.z + v0.z; acc.w = acc.w + v0.w;
+        acc.x = acc.x + v1.x; acc.y = acc.y + v1.y; acc.z = acc.z + v1.z; acc.w = acc.w + v1.w;
+        acc.x = acc.x + v2.x; acc.y = acc.y + v2.y; acc.z = acc.z + v2.z; acc.w = acc.w + v2.w;
+        acc.x = acc.x + v3.x; acc.y = acc.y + v3.y; acc.z = acc.z + v3.z; acc.w = acc.w + v3.w;
+      }
+      for (; lo < hi; lo++) {
+        const float4 v = tile[wib][lo - t0];
+        acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
+      }
+    }
+    __syncwarp();
+  }
+  if (!seg) return;
+  if (keep && !keep[s]) return;
+  const uint32_t o = slot ? slot[s] : s;
+  if (o >= capacity) return;
+  const float cnt = (float)(e - a);
+  const uint8_t* first = in + (size_t)vals[a] * stride;
+  uint8_t* dst = out + (size_t)o * stride;
+  // bytes not covered by an averaged field come from the voxel's first point
+  if (stride == 32 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    const uint4 w0 = reinterpret_cast<const uint4*>(first)[0], w1 = reinterpret_cast<const uint4*>(first)[1];
+    reinterpret_cast<uint4*>(dst)[0] = w0; reinterpret_cast<uint4*>(dst)[1] = w1;
+  } else {
+    for (uint32_t w = 0; w < stride / 4; w++)
+      reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(first)[w];
+  }
+  *reinterpret_cast<float*>(dst + F.ff_off[0]) = acc.x / cnt;
+  *reinterpret_cast<float*>(dst + F.ff_off[1]) = acc.y / cnt;
+  *reinterpret_cast<float*>(dst + F.ff_off[2]) = acc.z / cnt;
+  *reinterpret_cast<float*>(dst + F.ff_off[3]) = acc.w / cnt;
+  if (out_voxel_idx) out_voxel_idx[o] = (int32_t)k;
+}
+
 // One thread per voxel: float32 sum of its points in ascending input order (the order the stable sort
 // produced), divide by the count (centroid /= float(n), PCL), write the output point.
 __global__ void __launch_bounds__(128)
@@ -372,8 +447,12 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   }
   LB_TRY(h->sorted_f.ensure((size_t)n * F.n_ff));
   vg_gather_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, point_step, sv, n, F, h->sorted_f.p);
-  vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, h->sorted_f.p, h->seg_start.p,
-                                                          &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
+  if (F.n_ff == 4)
+    vg_centroid4_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, reinterpret_cast<const float4*>(h->sorted_f.p),
+                                                             h->seg_start.p, &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
+  else
+    vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, h->sorted_f.p, h->seg_start.p,
+                                                            &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
   c.launches += 2;
   LB_CUDA(cudaGetLastError());
   LB_CUDA(cudaMemcpyAsync(h->h_tot, n_final_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
