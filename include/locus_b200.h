@@ -258,7 +258,7 @@ typedef struct lb_odometry_result {
   char error[160];          /* message when status != LB_OK */
 } lb_odometry_result;
 
-/* depth: registration workers (1..8).  max_points / max_point_step size the ring of filtered clouds. */
+/* depth: registration workers (1..16).  max_points / max_point_step size the ring of filtered clouds. */
 int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_point_step, lb_odometry** out);
 int lb_odometry_destroy(lb_odometry* h);
 /* the pipeline's VoxelGrid handle: configure leaf / limits on it before the first submit */

@@ -106,6 +106,7 @@ struct lb_gicp {
   int* h_m = nullptr;                                         // pinned
   OuterResult* d_result = nullptr; OuterResult* h_result = nullptr;
   int align_blocks = 0;
+  int knn_resident_blocks = 0;    // CTAs of knn_cov_quadreg_kernel that are resident at once on this device
   bool have_result = false;
   float final_T[16];
   DBuf<uint8_t> io;              // transform/nn output staging
@@ -234,6 +235,11 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   // persistent kernel: one CTA per SM, co-resident (cooperative launch)
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel<AL_PPL>, AL_THREADS, 0);
+  {
+    int knn_per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&knn_per_sm, knn_cov_quadreg_kernel<20>, KQ_THREADS, 0);
+    h->knn_resident_blocks = h->c.sm_count * (knn_per_sm > 0 ? knn_per_sm : 1);
+  }
   h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
   if (h->align_blocks <= 0) h->align_blocks = h->c.sm_count;
   if (h->slots.ensure((size_t)2 * h->c.sm_count * AL_PSTRIDE) != LB_OK ||
@@ -451,9 +457,15 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
         Scratch& S = h->sc[slot];
         LB_TRY(S.worklist.ensure(N));
         uint32_t* d_wl = S.d_u32 + 4;      // [0] is the occupancy probe's counter
-        LB_CUDA(cudaMemsetAsync(d_wl, 0, sizeof(uint32_t), c.stream));
-        knn_cov_quadreg_kernel<20><<<cdiv(4ll * N, KQ_THREADS), KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from,
-                                                                                        ring_cap, S.worklist.p, d_wl);
+        LB_CUDA(cudaMemsetAsync(d_wl, 0, 2 * sizeof(uint32_t), c.stream));     // [0] worklist count, [1] next query batch
+        // tuning aid LB_KNN_DYN=1: a resident grid pulls 8-query batches from a counter (measured on B200: 3-7 % slower
+        // than the static grid at 30 k and 500 k points, so off by default)
+        static const int dyn = [] { const char* e = getenv("LB_KNN_DYN"); return e ? atoi(e) : 0; }();
+        int blocks = cdiv(4ll * N, KQ_THREADS);
+        const bool use_dyn = dyn && h->knn_resident_blocks > 0 && blocks > h->knn_resident_blocks;    // more than one wave
+        if (use_dyn) blocks = h->knn_resident_blocks;
+        knn_cov_quadreg_kernel<20><<<blocks, KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from,
+                                                                      ring_cap, S.worklist.p, d_wl, use_dyn ? d_wl + 1 : nullptr);
         // queries of sparse neighbourhoods (count read on the device: no host sync; a few resident warps when empty)
         knn_cov_tail_kernel<20><<<c.sm_count * 2, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, S.worklist.p, d_wl);
         c.launches++;

@@ -312,22 +312,50 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
 // layout, conflict-free) and popped from there.  Lists hold keys only; the k selected points are re-read through
 // their original index (`raw`, the original-order copy of the cloud: same coordinates as the sorted copy).
 constexpr int KQ_THREADS = 128;
+template <int K>
+__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, double eps,
+                                               double* __restrict__ cov, int split_from, int ring_cap,
+                                               uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count, uint32_t s,
+                                               int sub, unsigned qmask, int tid, uint32_t* m_d, uint32_t* m_o);
 #ifndef KQ_MINB
 #define KQ_MINB 4
 #endif
 template <int K>
 __global__ void __launch_bounds__(KQ_THREADS, KQ_MINB)
 knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps, double* __restrict__ cov, int split_from,
-                       int ring_cap, uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count) {
+                       int ring_cap, uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count,
+                       uint32_t* __restrict__ next_query /*nullable: dynamic distribution of 8-query batches*/) {
   __shared__ uint32_t m_d[(K + 1) * KQ_THREADS];
   __shared__ uint32_t m_o[(K + 1) * KQ_THREADS];
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t s = t >> 2;
   const int sub = threadIdx.x & 3;
-  const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
-  if (s >= (uint32_t)g.n) return;   // whole quads exit together
+  const int lane = threadIdx.x & 31;
+  const unsigned qmask = 0xFu << (lane & ~3);
   const int tid = threadIdx.x;
   m_d[K * KQ_THREADS + tid] = 0xffffffffu; m_o[K * KQ_THREADS + tid] = 0xffffffffu;   // sentinel behind every list
+  // Static mode (next_query == nullptr): one batch per warp, taken from the thread index.  Dynamic mode: a
+  // resident grid whose warps pull batches of 8 consecutive queries from a counter until the cloud is done -- the
+  // per-query cost varies a lot (rings scanned), and a static grid of ~1.6 waves ends with a long, mostly idle tail.
+  uint32_t wbase = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8;
+  for (;; ) {
+    if (next_query) {
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(next_query, 8u);
+      wbase = __shfl_sync(0xffffffffu, b, 0);
+    }
+    if (wbase >= (uint32_t)g.n) return;
+    knn_quad_query<K>(g, raw, k, eps, cov, split_from, ring_cap, worklist, wl_count, wbase + (uint32_t)(lane >> 2), sub, qmask,
+                      tid, m_d, m_o);
+    if (!next_query) return;
+    __syncwarp();
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, double eps,
+                                               double* __restrict__ cov, int split_from, int ring_cap,
+                                               uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count, uint32_t s,
+                                               int sub, unsigned qmask, int tid, uint32_t* m_d, uint32_t* m_o) {
+  if (s >= (uint32_t)g.n) return;   // whole quads exit together
   f4 q = g.pts[s];
   RegList<K> L;
   L.init();

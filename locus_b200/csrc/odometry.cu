@@ -190,8 +190,8 @@ void align_stage(lb_odometry* h, int w) {
 extern "C" {
 
 int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_point_step, lb_odometry** out) {
-  if (!out || depth < 1 || depth > 8 || max_points == 0 || max_point_step < 12) {
-    set_error("lb_odometry_create: need depth in 1..8, max_points > 0, max_point_step >= 12");
+  if (!out || depth < 1 || depth > 16 || max_points == 0 || max_point_step < 12) {
+    set_error("lb_odometry_create: need depth in 1..16, max_points > 0, max_point_step >= 12");
     return LB_ERR_INVALID_ARG;
   }
   lb_odometry* h = new lb_odometry;

@@ -103,7 +103,7 @@ def test_pipeline_error_propagation_and_limits(oh):
     oh.oh_reset(50)
     h = C.c_void_p()
     assert oh.lb_odometry_create(0, 0, 8, STEP, C.byref(h)) == -1
-    assert oh.lb_odometry_create(0, 9, 8, STEP, C.byref(h)) == -1
+    assert oh.lb_odometry_create(0, 17, 8, STEP, C.byref(h)) == -1
     assert oh.lb_odometry_create(0, 2, 8, STEP, C.byref(h)) == 0
     fa = _fields()
     t = C.c_uint64(0)

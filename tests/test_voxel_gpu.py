@@ -118,3 +118,15 @@ def test_voxel_full_size_c2():
     # filtering the output again with the same leaf keeps every voxel (idempotent voxel set)
     out2 = vg.filter(out.reshape(-1), 32, _fields())
     assert out2.shape[0] == out.shape[0]
+
+
+@pytest.mark.parametrize("n_scans,leaf", [(3, 0.5), (3, 0.06), (1, 2.5)])
+def test_voxel_large_inputs_and_long_segments(n_scans, leaf):
+    """393 k points (above the 262 144-point limit of the scan-free radix-sort path -> the scan path) and a coarse
+    leaf whose voxels hold thousands of points (the centroid kernel's multi-tile path): bit-exact vs the oracle."""
+    scene = G.make_scene(4)
+    poses = G.trajectory(4, n_scans, t_step=0.05, r_step_deg=0.5)
+    blob = np.concatenate([G.scan(scene, poses[i], 90 + i, beams=64, az=2048) for i in range(n_scans)])
+    out, vidx, r, _ = _run(blob, leaf)
+    _check(out, vidx, r)
+    assert int(r["count"].max()) > (2000 if leaf > 1 else 1)
