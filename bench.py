@@ -432,6 +432,7 @@ def main():
                 raise RuntimeError("lb_odometry: status %d: %s" % (r.status, r.error.decode(errors="replace")))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        st0 = odo.stageTimes()
         l0 = odo.launchCount()
         ev0.record(stream)
         out = []
@@ -449,6 +450,12 @@ def main():
         for r in out:
             if r.status != 0 or not r.has_pose:
                 raise RuntimeError("lb_odometry: ticket %d status %d: %s" % (r.ticket, r.status, r.error.decode(errors="replace")))
+        st1 = odo.stageTimes()
+        nf = max(1, st1["filtered"] - st0["filtered"]); nr = max(1, st1["registered"] - st0["registered"])
+        state["stages"] = {"voxel_stage_busy_ms_per_scan": 1e3 * (st1["voxel_busy_s"] - st0["voxel_busy_s"]) / nf,
+                           "voxel_stage_wait_ms_per_scan": 1e3 * (st1["voxel_wait_s"] - st0["voxel_wait_s"]) / nf,
+                           "worker_busy_ms_per_scan": 1e3 * (st1["workers_busy_s"] - st0["workers_busy_s"]) / nr,
+                           "worker_wait_ms_per_scan": 1e3 * (st1["workers_wait_s"] - st0["workers_wait_s"]) / nr}
         return ev0.elapsed_time(ev1), out, odo.launchCount() - l0
 
     sampler = ClockSampler(local_rank)
@@ -457,6 +464,7 @@ def main():
         g.resetKernelTimes(True)
     dev_ms, p_out, launches_timed = pipelined_run(submit_device, args.steps, args.warmup)
     clocks = sampler.stop()
+    stages_device = dict(state["stages"])
     kt = [odo.gicp(i).kernelTime("align_persistent") for i in range(args.depth)]
     for g in (odo.gicp(i) for i in range(args.depth)):
         g.resetKernelTimes(False)
@@ -525,6 +533,8 @@ def main():
             "sequential": {"value": seq_value, "unit": "scans/s", "ms_per_scan": seq_ms_max / args.steps,
                            "note": "per-scan C-ABI calls, one scan at a time (latency view), L2 flushed between scans"},
             "pipeline_equals_sequential": bool(pipe_same),
+            "pipeline_stages": dict(stages_device, note="host wall clock per scan inside the timed region (value arm): the "
+                                    "VoxelGrid stage is serial, the registration workers run %d-wide" % args.depth),
             "per_scan": {"outer_iterations_mean": float(iters.mean()) if len(iters) else None,
                          "objective_evals_mean": float(evals.mean()) if len(evals) else None,
                          "correspondences_mean": float(ncorr.mean()) if len(ncorr) else None,

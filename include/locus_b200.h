@@ -282,6 +282,10 @@ int lb_odometry_next(lb_odometry* h, lb_odometry_result* r, int block);
 int lb_odometry_pending(lb_odometry* h, size_t* n);
 /* kernels launched by all stages since creation */
 int lb_odometry_launch_count(lb_odometry* h, uint64_t* n);
+/* host wall-clock accounting since creation, to see which stage bounds the throughput:
+ * out6 = { scans filtered, VoxelGrid stage busy s, its wait s (for a scan or a free ring slot),
+ *          scans registered, registration workers busy s (summed over workers), their wait s (for a filtered scan) } */
+int lb_odometry_stage_times(lb_odometry* h, double* out6);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,7 @@ SYMBOLS = [
     "lb_voxel_set_downsample_all_data", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
     "lb_odometry_set_gicp_params", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
-    "lb_odometry_launch_count",
+    "lb_odometry_launch_count", "lb_odometry_stage_times",
 ]
 
 
@@ -151,6 +151,7 @@ def lib():
         L.lb_odometry_next.argtypes = [vp, C.POINTER(OdometryResult), i32]
         L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
         L.lb_odometry_launch_count.argtypes = [vp, u64p]
+        L.lb_odometry_stage_times.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -493,3 +494,10 @@ class OdometryB200:
         n = C.c_uint64(0)
         lib().lb_odometry_launch_count(self._h, C.byref(n))
         return n.value
+
+    def stageTimes(self):
+        """host wall-clock accounting since creation (see lb_odometry_stage_times)"""
+        a = (C.c_double * 6)()
+        _check(lib().lb_odometry_stage_times(self._h, a))
+        return {"filtered": int(a[0]), "voxel_busy_s": a[1], "voxel_wait_s": a[2], "registered": int(a[3]),
+                "workers_busy_s": a[4], "workers_wait_s": a[5]}

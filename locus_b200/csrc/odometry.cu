@@ -12,8 +12,10 @@
 // exists because one align() is a latency-bound persistent kernel on ~60 of 148 SMs: the rest of the GPU filters
 // and indexes the following scans, and several aligns (each on its own CTAs) are in flight at once.  Results are
 // those of the sequential calls: registration k reads only filtered clouds k and k-1 and its caller-given prior.
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -71,6 +73,7 @@ struct lb_odometry {
   std::vector<lb_gicp*> gicp;
   std::vector<Slot> ring;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t voxel_stream = nullptr;
 
   std::mutex mu;
   std::condition_variable cv;          // one condition variable for every state change (few threads, short waits)
@@ -81,6 +84,9 @@ struct lb_odometry {
   uint64_t next_return = 0;            // next ticket lb_odometry_next returns
   uint64_t done_floor = 0;             // every ticket < done_floor has finished stage G
   bool stop = false;
+  // stage accounting (seconds, host wall clock; mu held when updated): which stage bounds the throughput
+  double t_voxel_busy = 0, t_voxel_wait = 0, t_worker_busy = 0, t_worker_wait = 0;
+  uint64_t n_filtered = 0, n_registered = 0;
   std::thread vthread;
   std::vector<std::thread> gthreads;
 
@@ -110,6 +116,7 @@ void voxel_stage(lb_odometry* h) {
   for (;;) {
     Entry* e = nullptr;
     uint64_t t = 0;
+    const auto tw0 = std::chrono::steady_clock::now();
     {
       std::unique_lock<std::mutex> lk(h->mu);
       // slot t % R was last read by registrations t-R (source) and t-R+1 (target): both must have finished
@@ -120,6 +127,7 @@ void voxel_stage(lb_odometry* h) {
       t = h->next_filter;
       e = h->entry(t);
     }
+    const auto tb0 = std::chrono::steady_clock::now();
     Slot& s = h->ring[t % R];
     const Job& j = e->job;
     size_t n_out = 0;
@@ -142,6 +150,9 @@ void voxel_stage(lb_odometry* h) {
       e->filtered = true;
       e->res.n_filtered = s.n;
       h->next_filter = t + 1;
+      h->t_voxel_wait += std::chrono::duration<double>(tb0 - tw0).count();
+      h->t_voxel_busy += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
+      h->n_filtered++;
     }
     h->cv.notify_all();
   }
@@ -154,6 +165,7 @@ void align_stage(lb_odometry* h, int w) {
   for (;;) {
     Entry* e = nullptr;
     uint64_t t = 0;
+    const auto tw0 = std::chrono::steady_clock::now();
     {
       std::unique_lock<std::mutex> lk(h->mu);
       h->cv.wait(lk, [&] { return h->stop || h->next_align < h->next_filter; });
@@ -161,6 +173,7 @@ void align_stage(lb_odometry* h, int w) {
       t = h->next_align++;
       e = h->entry(t);
     }
+    const auto tb0 = std::chrono::steady_clock::now();
     lb_odometry_result& r = e->res;
     const Slot& cur = h->ring[t % R];
     r.status = cur.status;
@@ -180,6 +193,9 @@ void align_stage(lb_odometry* h, int w) {
       std::lock_guard<std::mutex> lk(h->mu);
       e->done = true;
       advance_done_floor(h);
+      h->t_worker_wait += std::chrono::duration<double>(tb0 - tw0).count();
+      h->t_worker_busy += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
+      h->n_registered++;
     }
     h->cv.notify_all();
   }
@@ -196,7 +212,19 @@ int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_po
   }
   lb_odometry* h = new lb_odometry;
   h->device = device; h->depth = depth; h->max_points = max_points; h->max_step = max_point_step;
-  int st = lb_voxel_create(device, &h->vg);
+  // The VoxelGrid stage is the one serial stage of the pipeline and a chain of ~12 short dependent kernels: on its
+  // own high-priority stream its CTAs are placed before the pending CTAs of the workers' k-NN / index kernels.
+  int st = LB_OK;
+  {
+    int lo = 0, hi = 0;
+    const char* e = getenv("LB_VOXEL_PRIO");
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->voxel_stream, cudaStreamNonBlocking, (e && atoi(e) == 0) ? lo : hi) != cudaSuccess) {
+      set_error("lb_odometry_create: stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      st = LB_ERR_CUDA;
+    }
+  }
+  if (st == LB_OK) st = lb_voxel_create_on_stream(device, h->voxel_stream, &h->vg);
   for (int i = 0; st == LB_OK && i < depth; i++) {
     lb_gicp* g = nullptr;
     st = lb_gicp_create(device, &g);
@@ -220,6 +248,7 @@ int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_po
     for (auto& s : h->ring) if (s.d) cudaFree(s.d);
     for (auto g : h->gicp) lb_gicp_destroy(g);
     if (h->vg) lb_voxel_destroy(h->vg);
+    if (h->voxel_stream) cudaStreamDestroy(h->voxel_stream);
     delete h;
     return st;
   }
@@ -243,6 +272,7 @@ int lb_odometry_destroy(lb_odometry* h) {
   lb_voxel_destroy(h->vg);
   for (auto& s : h->ring) if (s.d) cudaFree(s.d);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->voxel_stream) cudaStreamDestroy(h->voxel_stream);
   for (auto e : h->inflight) delete e;
   delete h;
   return LB_OK;
@@ -319,6 +349,14 @@ int lb_odometry_pending(lb_odometry* h, size_t* n) {
   if (!h || !n) return LB_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   *n = (size_t)(h->next_ticket - h->next_return);
+  return LB_OK;
+}
+
+int lb_odometry_stage_times(lb_odometry* h, double* out6) {
+  if (!h || !out6) return LB_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  out6[0] = (double)h->n_filtered; out6[1] = h->t_voxel_busy; out6[2] = h->t_voxel_wait;
+  out6[3] = (double)h->n_registered; out6[4] = h->t_worker_busy; out6[5] = h->t_worker_wait;
   return LB_OK;
 }
 

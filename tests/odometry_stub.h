@@ -26,6 +26,8 @@ inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, int, int) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "stub"; }
@@ -55,6 +57,7 @@ inline void nap(uint64_t seed) {
 extern "C" {
 inline const char* lb_last_error_string(void) { return lb::err_buf(); }
 inline int lb_voxel_create(int, lb_voxel** h) { *h = new lb_voxel; return LB_OK; }
+inline int lb_voxel_create_on_stream(int, void*, lb_voxel** h) { *h = new lb_voxel; return LB_OK; }
 inline int lb_voxel_destroy(lb_voxel* h) { delete h; return LB_OK; }
 inline int lb_voxel_launch_count(lb_voxel* h, uint64_t* n) { *n = h->launches; return LB_OK; }
 // scan layout of the fakes: [0..7] id, [8..11] flags (bit 0: make the filter fail)
