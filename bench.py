@@ -65,16 +65,46 @@ def parse():
 
 # ------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in a thread (a few microseconds per
+    query) when nvidia_ml_py is importable; otherwise an `nvidia-smi -lms` subprocess.  (Eight nvidia-smi pollers on
+    an 8-GPU box visibly slowed the arm they ran next to, so the in-process NVML path is preferred.)"""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.01):
         self.index = index
+        self.period = period_s
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], None, set()
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                return None          # UUID list: let the nvidia-smi path deal with it
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self._visible_index()
+            if idx is None:
+                raise RuntimeError("no integer device index")
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,11 +114,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        N = self.nvml
+        names = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
+        masks = [(n, getattr(N, a, 0)) for n, a in names]
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for n, m in masks:
+                    if m and (r & m):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.proc.terminate()
@@ -110,7 +161,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_hbm():
@@ -256,6 +307,7 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     poses, blobs = make_stream(rank)
