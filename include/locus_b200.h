@@ -194,6 +194,8 @@ int lb_gicp_launch_count(lb_gicp* h, uint64_t* n);
 /* CUDA-event duration (ms, averaged per launch) of a named kernel class since the last reset:
  * "nn_corr", "objective", "knn_cov", "align_persistent", "index_build". */
 int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches);
+/* enable_timing: 0 off; 1 event timers of every kernel class plus the align kernel's cycle counters;
+ * 2 only the event pair around the align kernel (cheap enough for a throughput run) */
 int lb_gicp_reset_kernel_times(lb_gicp* h, int enable_timing);
 
 /* ------------------------------------------------------------- VoxelGrid */

@@ -325,6 +325,7 @@ class GicpB200:
         return n.value
 
     def resetKernelTimes(self, enable=True):
+        """False/0: off; True/1: all kernel classes + cycle counters; 2: only the align kernel's event pair"""
         _check(lib().lb_gicp_reset_kernel_times(self._h, int(enable)))
 
     def kernelTime(self, name):
