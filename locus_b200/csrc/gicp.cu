@@ -276,11 +276,6 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
                 cudaMemset(h->cslots.p, 0, (CL_MAX_CTAS + CL_CMD_WORDS) * sizeof(SlotWord)) != cudaSuccess))
       h->cluster_ok = false;
   }
-  if (cudaFuncSetAttribute(knn_cov_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnWarpSmem)) != cudaSuccess) {
-    set_error("lb_gicp_create: cannot reserve %zu bytes of shared memory", sizeof(KnnWarpSmem));
-    delete h;
-    return LB_ERR_CUDA;
-  }
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   *out = h;
   return LB_OK;
@@ -434,15 +429,11 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
   } else {
     int k = h->P.k_correspondences;
     GridView v = cl.view();
-    // tuning aid: LB_KNN=warp selects the warp-per-query kernel, LB_KNN=quadlocal the quad kernel with
-    // local-memory lists (default: quad-per-query with register-resident lists)
-    static const int variant = [] { const char* e = getenv("LB_KNN"); return (e && !strcmp(e, "warp")) ? 1 : (e && !strcmp(e, "quadlocal")) ? 2 : 0; }();
-    if (variant == 1) {
-      int blocks = cdiv(N, KW_WARPS);
-      int max_blocks = c.sm_count * 4;
-      if (blocks > max_blocks) blocks = max_blocks;
-      knn_cov_warp_kernel<<<blocks, KW_WARPS * 32, sizeof(KnnWarpSmem), c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p);
-    } else {
+    // tuning aid: LB_KNN=quadlocal selects the quad kernel with local-memory lists (default: quad-per-query with
+    // register-resident lists; a warp-per-query and a thread-per-query kernel were tried in round 1 and removed:
+    // issue-bound at 5x the instructions, resp. 10/32 active lanes)
+    static const int variant = [] { const char* e = getenv("LB_KNN"); return (e && !strcmp(e, "quadlocal")) ? 2 : 0; }();
+    {
       const int no_cap = 1 << 30;
       struct QuadTune { int split_from, lazy_merge, qthreads; };   // tuning aids; magic static: initialised once, thread-safe
       static const QuadTune qt = [] {

@@ -3,7 +3,8 @@
 //   gather_cloud_kernel      strided caller cloud -> packed float4 (+ normals)
 //   grid_keys_kernel         K2: cell key per point
 //   grid_reorder_kernel      K2: cell-contiguous float4 copy + cell histogram
-//   knn_cov_kernel<K>        K3: k-NN(20) -> moments -> Jacobi -> regularised covariance
+//   knn_cov_quadreg_kernel   K3: k-NN(20) -> moments -> Jacobi -> regularised covariance (+ knn_cov_tail_kernel,
+//                            knn_cov_quad_kernel for k > 20)
 //   normal_cov_kernel        K3': covariance from normals (reference default mode)
 //   prep_source_kernel       K6: output = guess * input (gicp.hpp:440)
 //   nn_corr_kernel           K4: transform, exact 1-NN in the voxel hash, gate, Mahalanobis
@@ -96,33 +97,7 @@ grid_reorder_kernel(const f4* __restrict__ raw, const uint32_t* __restrict__ sor
 }
 
 // ------------------------------------------------------------------ K3 covariances
-template <int KMAX>
-__global__ void __launch_bounds__(128)
-knn_cov_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= (uint32_t)g.n) return;
-  f4 q = g.pts[s];
-  KnnList<KMAX> L;
-  knn<KMAX>(g, q.x, q.y, q.z, k, L);
-  double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
-#pragma unroll
-  for (int j = 0; j < KMAX; j++) {
-    if (j < L.cnt) {
-      f4 p = g.pts[L.si[j]];
-      // pt.x * pt.x is a float product accumulated into double (gicp.hpp:115-126)
-      sum[0] += p.x; sum[1] += p.y; sum[2] += p.z;
-      m2[0] += p.x * p.x; m2[1] += p.y * p.x; m2[2] += p.y * p.y;
-      m2[3] += p.z * p.x; m2[4] += p.z * p.y; m2[5] += p.z * p.z;
-    }
-  }
-  double out[6];
-  cov_from_moments(sum, m2, k, eps, out);
-  double* d = cov + 6 * (size_t)s;
-#pragma unroll
-  for (int e = 0; e < 6; e++) d[e] = out[e];
-}
-
-// K3, quad-per-query variant (default): the 4 lanes of a quad scan every cell run of the probe block
+// K3, quad-per-query variant with local-memory lists (k > 20, and the A/B baseline behind LB_KNN=quadlocal): the 4 lanes of a quad scan every cell run of the probe block
 // cooperatively (lane q takes points s+q, s+q+4, ... of each contiguous run: 64-byte coalesced reads),
 // each keeping its own sorted top-K; a quad-wide K-round merge (shuffle min on (d2, index)) yields the
 // exact union top-K in ascending order and accumulates the moments in that order -- the same order the
@@ -507,185 +482,7 @@ knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, con
   }
 }
 
-// K3, warp-per-query variant (default).  A warp owns one query:
-//   * the rows of every shell are spread over the lanes (all cell_start look-ups of a shell in flight at once),
-//     then the candidate points of those rows are fetched FLATTENED -- lane l takes candidates l, l+32, ... of
-//     the concatenated runs -- so every load instruction has 32 independent addresses in flight;
-//   * candidates are staged in the warp's shared-memory buffer (packed key = d2 bits << 32 | original index,
-//     plus x, y, z);
-//   * the exact top-k is found by RANKING: every lane counts, for each candidate it owns, how many keys are
-//     smaller (one shared-memory broadcast read per compare) -- no dependent selection rounds; candidates
-//     with rank < k drop into slot `rank` of the selection buffer, which is therefore sorted ascending;
-//   * the moments are accumulated from that buffer in ascending (d2, index) order -- the order of the oracle --
-//     so the covariances are bit-identical to the thread-per-point kernels.
-// After an unsuccessful bound test only the k best are kept, so the buffer holds at most k + one batch.
-constexpr int KW_WARPS = 8;       // warps (= queries in flight) per CTA
-constexpr int KW_CAP = 320;       // candidate slots per warp
-constexpr int KW_T = KW_CAP / 32; // candidates owned per lane
-
-struct KnnWarpSmem {
-  long long key[KW_WARPS][KW_CAP];
-  float x[KW_WARPS][KW_CAP], y[KW_WARPS][KW_CAP], z[KW_WARPS][KW_CAP];
-  long long sel_key[KW_WARPS][32];
-  float sel_x[KW_WARPS][32], sel_y[KW_WARPS][32], sel_z[KW_WARPS][32];
-  uint32_t row_a0[KW_WARPS][32], row_a1[KW_WARPS][32];
-  int row_n0[KW_WARPS][32], row_off[KW_WARPS][33];
-};
-
-struct KnnWarpView {   // this warp's slices of the shared buffers
-  long long* key; float *x, *y, *z;
-  long long* sel_key; float *sel_x, *sel_y, *sel_z;
-  uint32_t *row_a0, *row_a1; int *row_n0, *row_off;
-};
-
-// select the k smallest of key[0..cnt) into sel_*[0..found) (ascending): each lane keeps the keys it owns
-// (slots lane, lane+32, ...) in registers; round i takes the smallest key greater than the previous winner
-// (per-lane scan of its registers + 64-bit warp min), and the owner copies the point into slot i.
-// returns found = min(cnt, k).
-__device__ __forceinline__ int warp_rank_select(const KnnWarpView& w, int cnt, int k) {
-  const int lane = threadIdx.x & 31;
-  long long mine[KW_T];
-#pragma unroll
-  for (int t = 0; t < KW_T; t++) {
-    int i = lane + 32 * t;
-    mine[t] = (i < cnt) ? w.key[i] : 0x7fffffffffffffffll;
-  }
-  const int nt = (cnt + 31) >> 5;   // slots per lane actually in use
-  long long prev = -1;
-  int found = 0;
-  for (int round = 0; round < k; round++) {
-    long long best = 0x7fffffffffffffffll;
-    int bt = 0;
-#pragma unroll
-    for (int t = 0; t < KW_T; t++)
-      if (t < nt && mine[t] > prev && mine[t] < best) { best = mine[t]; bt = t; }
-    long long wbest = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
-      wbest = other < wbest ? other : wbest;
-    }
-    if (wbest == 0x7fffffffffffffffll) break;
-    if (best == wbest) {          // unique owner (keys are unique)
-      int i = lane + 32 * bt;
-      w.sel_key[found] = wbest; w.sel_x[found] = w.x[i]; w.sel_y[found] = w.y[i]; w.sel_z[found] = w.z[i];
-    }
-    prev = wbest;
-    found++;
-  }
-  __syncwarp();
-  return found;
-}
-
-__device__ __forceinline__ void warp_compact_to_selection(const KnnWarpView& w, int found) {
-  const int lane = threadIdx.x & 31;
-  if (lane < found) { w.key[lane] = w.sel_key[lane]; w.x[lane] = w.sel_x[lane]; w.y[lane] = w.sel_y[lane]; w.z[lane] = w.sel_z[lane]; }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(KW_WARPS * 32)
-knn_cov_warp_kernel(GridView g, int k, double eps, double* __restrict__ cov) {
-  extern __shared__ __align__(16) unsigned char kw_smem_raw[];
-  KnnWarpSmem& sm = *reinterpret_cast<KnnWarpSmem*>(kw_smem_raw);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  KnnWarpView w{sm.key[wib], sm.x[wib], sm.y[wib], sm.z[wib], sm.sel_key[wib], sm.sel_x[wib], sm.sel_y[wib], sm.sel_z[wib],
-                sm.row_a0[wib], sm.row_a1[wib], sm.row_n0[wib], sm.row_off[wib]};
-  const uint32_t nwarps = gridDim.x * KW_WARPS;
-  for (uint32_t s = blockIdx.x * KW_WARPS + wib; s < (uint32_t)g.n; s += nwarps) {
-    const f4 q = g.pts[s];
-    int cx, cy, cz; float minfrac;
-    query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
-    int r0, r1;
-    ring_range(g, cx, cy, cz, r0, r1);
-    int cnt = 0, found = 0;
-    for (int r = r0; r <= r1; r++) {
-      const int side = 2 * r + 1;
-      const int nrows = side * side;
-      for (int rowbase = 0; rowbase < nrows; rowbase += 32) {
-        // this lane's row of the shell: up to two runs [a0, a0+n0) and [a1, a1+n1)
-        uint32_t a0 = 0, a1 = 0; int n0 = 0, n1 = 0;
-        int j = rowbase + lane;
-        if (j < nrows) {
-          int dz = j / side - r, dy = j - (j / side) * side - r;
-          int z = cz + dz, y = cy + dy;
-          if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-            int base = (z * g.ny + y) * g.nx;
-            bool face = (iabs_(dz) == r) || (iabs_(dy) == r);
-            if (face) {
-              int xa = imax_(cx - r, 0), xb = imin_(cx + r, g.nx - 1);
-              if (xa <= xb) { a0 = g.cell_start[base + xa]; n0 = (int)(g.cell_start[base + xb + 1] - a0); }
-            } else {
-              int x0 = cx - r, x1 = cx + r;
-              if (x0 >= 0 && x0 < g.nx) { a0 = g.cell_start[base + x0]; n0 = (int)(g.cell_start[base + x0 + 1] - a0); }
-              if (x1 >= 0 && x1 < g.nx) { a1 = g.cell_start[base + x1]; n1 = (int)(g.cell_start[base + x1 + 1] - a1); }
-            }
-          }
-        }
-        int len = n0 + n1;
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        w.row_a0[lane] = a0; w.row_a1[lane] = a1; w.row_n0[lane] = n0; w.row_off[lane] = incl - len;
-        if (lane == 31) w.row_off[32] = total;
-        __syncwarp();
-        // flattened fetch of the `total` candidates of this batch of rows, in chunks that fit the buffer
-        int done = 0;
-        while (done < total) {
-          int room = KW_CAP - cnt;
-          if (room < 32 && cnt > k) {              // make room: top-k(A u B) = top-k(top-k(A) u B)
-            found = warp_rank_select(w, cnt, k);
-            warp_compact_to_selection(w, found);
-            cnt = found;
-            room = KW_CAP - cnt;
-          }
-          int take = total - done < room ? total - done : room;
-          int cur = 0;
-          for (int idx = done + lane; idx < done + take; idx += 32) {
-            while (idx >= w.row_off[cur + 1]) cur++;
-            int local = idx - w.row_off[cur];
-            int nn0 = w.row_n0[cur];
-            uint32_t pi = (local < nn0) ? (w.row_a0[cur] + (uint32_t)local) : (w.row_a1[cur] + (uint32_t)(local - nn0));
-            f4 p = g.pts[pi];
-            int slot = cnt + (idx - done);
-            w.key[slot] = ((long long)__float_as_uint(dist2(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | (unsigned)float_to_bits(p.w);
-            w.x[slot] = p.x; w.y[slot] = p.y; w.z[slot] = p.z;
-          }
-          cnt += take;
-          done += take;
-          __syncwarp();
-        }
-      }
-      if (cnt < k && r < r1) continue;     // not even k candidates yet: next shell
-      found = warp_rank_select(w, cnt, k);
-      long long kth = w.sel_key[found - 1];
-      float kth_d2 = __uint_as_float((unsigned)((unsigned long long)kth >> 32));
-      if (found == k && kth_d2 < ring_bound2(g, r, minfrac)) break;
-      warp_compact_to_selection(w, found);  // keep only the k best before adding the next shell
-      cnt = found;
-    }
-    // moments in ascending (d2, index) order (float products accumulated in double, gicp.hpp:112-127)
-    double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
-    for (int i = 0; i < found; i++) {
-      float px = w.sel_x[i], py = w.sel_y[i], pz = w.sel_z[i];
-      sum[0] += px; sum[1] += py; sum[2] += pz;
-      m2[0] += px * px; m2[1] += py * px; m2[2] += py * py;
-      m2[3] += pz * px; m2[4] += pz * py; m2[5] += pz * pz;
-    }
-    double out[6];
-    cov_from_moments(sum, m2, k, eps, out);
-    if (lane == 0) {
-      double* d = cov + 6 * (size_t)s;
-#pragma unroll
-      for (int e = 0; e < 6; e++) d[e] = out[e];
-    }
-    __syncwarp();
-  }
-}
-
+// K3': covariance from a stored normal (the reference's default mode when normals are present)
 __global__ void __launch_bounds__(256)
 normal_cov_kernel(const f4* __restrict__ pts, const f4* __restrict__ nrm, uint32_t n, double eps, double* __restrict__ cov) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
