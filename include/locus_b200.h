@@ -36,6 +36,8 @@
  *                                 point_cloud_odometry/test/test_point_cloud_odometry.cpp:298
  *   lb_gicp_point2plane_information   normalizePCloud + ComputeAp_ForPoint2PlaneICP
  *                                 point_cloud_localization/src/utils.cc:106-128, PointCloudLocalization.cc:694-750
+ *   lb_gicp_compute_normals       NormalComputation::filter, k-NN mode (pcl::NormalEstimationOMP)
+ *                                 point_cloud_filter/src/normal_computation.cc:26-59
  *   lb_voxel_create/destroy       pcl::VoxelGrid<pcl::PCLPointCloud2> impl_
  *                                 point_cloud_filter/include/point_cloud_filter/custom_voxel_grid.h:25
  *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
@@ -185,6 +187,15 @@ int lb_gicp_fitness(lb_gicp* h, const float* T, double max_range, double* score)
 int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, size_t q_stride, size_t q_xyz_off,
                                     const void* reference, size_t n_ref, size_t r_stride, size_t r_normal_off,
                                     const int32_t* correspondences, const float* T, int normalize, double* Ap36, int mem);
+/* SURVEY 8f row f2 -- the step right before the path: point_cloud_filter::NormalComputation::filter in its k-NN
+ * mode (point_cloud_filter/src/normal_computation.cc:26-59; norm_est_ = pcl::NormalEstimationOMP<PointXYZI, Normal>,
+ * normal_computation.h:38; k = normal_search_knn, cfg/NormalComputation.cfg:15).  Per point of the cloud currently set
+ * as source (which = 0) or target (which = 1): the k nearest neighbours (itself included) -> PCL's float32
+ * mean/covariance -> eigenvector of the smallest eigenvalue (PCL eigen33) -> flipped towards `viewpoint` (NULL = the
+ * origin, what fromROSMsg leaves in sensor_origin_).  out4: n x (normal_x, normal_y, normal_z, curvature) float32 in
+ * the caller's point order, host or device.  3 <= k <= 20.  The radius mode of the nodelet is not implemented
+ * (LB_ERR_UNSUPPORTED is never returned silently: there is no such entry point). */
+int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint, float* out4, int mem);
 /* covariances used by the last align, n x 9 doubles row-major, original point order. which: 0 source, 1 target */
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points);
 /* number of points currently indexed. which: 0 source, 1 target */

@@ -66,7 +66,7 @@ SYMBOLS = [
     "lb_gicp_default_params", "lb_gicp_create", "lb_gicp_create_on_stream", "lb_gicp_destroy",
     "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
     "lb_gicp_promote_source_to_target", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
-    "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
+    "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_compute_normals", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
@@ -124,6 +124,8 @@ def lib():
     L.lb_gicp_fitness.argtypes = [vp, vp, C.c_double, C.POINTER(C.c_double)]
     L.lb_gicp_point2plane_information.argtypes = [vp, vp, sz, sz, sz, vp, sz, sz, sz, vp, vp, i32, vp, i32]
     L.lb_gicp_get_covariances.argtypes = [vp, i32, vp, sz]
+    if hasattr(L, "lb_gicp_compute_normals"):
+        L.lb_gicp_compute_normals.argtypes = [vp, i32, i32, vp, vp, i32]
     L.lb_gicp_cloud_size.argtypes = [vp, i32, C.POINTER(sz)]
     L.lb_gicp_launch_count.argtypes = [vp, u64p]
     L.lb_gicp_kernel_time.argtypes = [vp, C.c_char_p, C.POINTER(C.c_float), u64p]
@@ -318,6 +320,16 @@ class GicpB200:
         n = C.c_size_t(0)
         _check(lib().lb_gicp_cloud_size(self._h, which, C.byref(n)))
         return n.value
+
+    def computeNormals(self, which=0, k=20, viewpoint=None):
+        """NormalComputation nodelet, k-NN mode: (n, 4) float32 = normal_x, normal_y, normal_z, curvature of the cloud
+        currently set as source (which=0) or target (which=1), in the caller's point order."""
+        n = C.c_size_t(0)
+        _check(lib().lb_gicp_cloud_size(self._h, which, C.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        vp_ = None if viewpoint is None else np.ascontiguousarray(viewpoint, dtype=np.float32)
+        _check(lib().lb_gicp_compute_normals(self._h, which, int(k), _ptr(vp_), _ptr(out), LB_MEM_HOST))
+        return out
 
     def launchCount(self):
         n = C.c_uint64(0)

@@ -238,7 +238,7 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel<AL_PPL>, AL_THREADS, 0);
   {
     int knn_per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&knn_per_sm, knn_cov_quadreg_kernel<20>, KQ_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&knn_per_sm, knn_cov_quadreg_kernel<20, CovFin>, KQ_THREADS, 0);
     h->knn_resident_blocks = h->c.sm_count * (knn_per_sm > 0 ? knn_per_sm : 1);
   }
   h->align_blocks = h->c.sm_count * (per_sm >= 1 ? 1 : 0);
@@ -456,10 +456,12 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
         int blocks = cdiv(4ll * N, KQ_THREADS);
         const bool use_dyn = dyn && h->knn_resident_blocks > 0 && blocks > h->knn_resident_blocks;    // more than one wave
         if (use_dyn) blocks = h->knn_resident_blocks;
-        knn_cov_quadreg_kernel<20><<<blocks, KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, h->P.gicp_epsilon, cl.cov.p, split_from,
-                                                                      ring_cap, S.worklist.p, d_wl, use_dyn ? d_wl + 1 : nullptr);
+        CovFin fin;
+        fin.eps = h->P.gicp_epsilon; fin.cov = cl.cov.p;
+        knn_cov_quadreg_kernel<20, CovFin><<<blocks, KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, fin, split_from, ring_cap, S.worklist.p,
+                                                                              d_wl, use_dyn ? d_wl + 1 : nullptr);
         // queries of sparse neighbourhoods (count read on the device: no host sync; a few resident warps when empty)
-        knn_cov_tail_kernel<20><<<c.sm_count * 2, 128, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, S.worklist.p, d_wl);
+        knn_cov_tail_kernel<20, CovFin><<<c.sm_count * 2, 128, 0, c.stream>>>(v, k, fin, S.worklist.p, d_wl);
         c.launches++;
       }
       else if (k <= 20) knn_cov_quad_kernel<20><<<cdiv(4ll * N, qthreads), qthreads, 0, c.stream>>>(v, k, h->P.gicp_epsilon, cl.cov.p, no_cap, nullptr, nullptr, split_from, lazy_merge);
@@ -967,6 +969,38 @@ int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, siz
   for (int b = 0; b < nb; b++) for (int e = 0; e < 21; e++) up[e] += part[21 * (size_t)b + e];
   int e = 0;
   for (int r = 0; r < 6; r++) for (int cc = r; cc < 6; cc++) { Ap36[r * 6 + cc] = up[e]; Ap36[cc * 6 + r] = up[e]; e++; }
+  return LB_OK;
+}
+
+// point_cloud_filter::NormalComputation::filter in k-NN mode (normal_computation.cc:26-59).
+int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint, float* out4, int mem) {
+  if (!h || !out4 || (which != 0 && which != 1)) { set_error("lb_gicp_compute_normals: bad argument"); return LB_ERR_INVALID_ARG; }
+  Cloud& cl = which == 0 ? h->src : h->tgt;
+  if (!cl.valid) { set_error("lb_gicp_compute_normals: no %s cloud", which == 0 ? "source" : "target"); return which == 0 ? LB_ERR_EMPTY_SOURCE : LB_ERR_NO_TARGET; }
+  if (k < 3 || k > 20) { set_error("lb_gicp_compute_normals: k must be in [3, 20] (PCL yields NaN normals below 3)"); return LB_ERR_UNSUPPORTED; }
+  if ((size_t)k > cl.n) { set_error("lb_gicp_compute_normals: cloud has %zu points, fewer than k = %d", cl.n, k); return LB_ERR_TOO_FEW_POINTS; }
+  Scratch& S = h->sc[which];
+  Ctx& c = S.c;
+  LB_CUDA(cudaSetDevice(c.device));
+  LB_TRY(finish_index(h, cl, which));
+  const uint32_t N = (uint32_t)cl.n;
+  f4* d_out = reinterpret_cast<f4*>(out4);
+  if (mem == LB_MEM_HOST) { LB_TRY(h->io.ensure((size_t)N * sizeof(f4))); d_out = reinterpret_cast<f4*>(h->io.p); }
+  LB_TRY(S.worklist.ensure(N));
+  uint32_t* d_wl = S.d_u32 + 4;
+  LB_CUDA(cudaMemsetAsync(d_wl, 0, 2 * sizeof(uint32_t), c.stream));
+  NormalFin fin;
+  fin.vp[0] = viewpoint ? viewpoint[0] : 0.f; fin.vp[1] = viewpoint ? viewpoint[1] : 0.f; fin.vp[2] = viewpoint ? viewpoint[2] : 0.f;
+  fin.out = d_out;
+  GridView v = cl.view();
+  static const int ring_cap = [] { const char* e = getenv("LB_RING_CAP"); return e ? atoi(e) : 6; }();
+  knn_cov_quadreg_kernel<20, NormalFin><<<cdiv(4ll * N, KQ_THREADS), KQ_THREADS, 0, c.stream>>>(v, cl.raw.p, k, fin, 99, ring_cap,
+                                                                                        S.worklist.p, d_wl, nullptr);
+  knn_cov_tail_kernel<20, NormalFin><<<c.sm_count * 2, 128, 0, c.stream>>>(v, k, fin, S.worklist.p, d_wl);
+  c.launches += 2;
+  LB_CUDA(cudaGetLastError());
+  if (mem == LB_MEM_HOST) LB_CUDA(cudaMemcpyAsync(out4, d_out, (size_t)N * sizeof(f4), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
   return LB_OK;
 }
 

@@ -278,6 +278,47 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
   }
 }
 
+// What a k-NN kernel does with the k neighbours of a query, visited in ascending (d2, index) order:
+// CovFin  -> GICP covariance (gicp.hpp:85-154): double moments -> Jacobi -> regularised, written in sorted order;
+// NormalFin -> PCL NormalEstimation (hd.h): nine float accumulators -> eigen33 -> flipped normal +
+//              curvature, written at the point's ORIGINAL index.
+struct CovFin {
+  double eps;
+  double* cov;
+  double sum[3], m2[6];
+  __device__ __forceinline__ void reset() {
+    sum[0] = sum[1] = sum[2] = 0.0;
+    m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+  }
+  __device__ __forceinline__ void add(const f4& pt) {
+    sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
+    m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
+    m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+  }
+  __device__ __forceinline__ void finish(uint32_t s, const f4&, int k, bool writer) {
+    double out[6];
+    cov_from_moments(sum, m2, k, eps, out);
+    if (writer) {
+      double* d = cov + 6 * (size_t)s;
+#pragma unroll
+      for (int e = 0; e < 6; e++) d[e] = out[e];
+    }
+  }
+};
+
+struct NormalFin {
+  float vp[3];
+  f4* out;            // original order: (nx, ny, nz, curvature)
+  NormalAccum acc;
+  __device__ __forceinline__ void reset() { acc.reset(); }
+  __device__ __forceinline__ void add(const f4& pt) { acc.add(pt.x, pt.y, pt.z); }
+  __device__ __forceinline__ void finish(uint32_t, const f4& q, int k, bool writer) {
+    float o[4];
+    pcl_normal_from_accum(acc, k, q.x, q.y, q.z, vp, o);
+    if (writer) out[float_to_bits(q.w)] = f4{o[0], o[1], o[2], o[3]};
+  }
+};
+
 // K3, register-resident variant (the default for k <= 20).  Same quad-per-query scan, same (d2, index) order and
 // same summation order as knn_cov_quad_kernel, hence the same bits; what changes is where the candidate lists
 // live.  Each lane's sorted list is a RegList (static indexing, fully unrolled: ~60 registers), so an insertion is
@@ -287,17 +328,17 @@ knn_cov_quad_kernel(GridView g, int k, double eps, double* __restrict__ cov, int
 // layout, conflict-free) and popped from there.  Lists hold keys only; the k selected points are re-read through
 // their original index (`raw`, the original-order copy of the cloud: same coordinates as the sorted copy).
 constexpr int KQ_THREADS = 128;
-template <int K>
-__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, double eps,
-                                               double* __restrict__ cov, int split_from, int ring_cap,
-                                               uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count, uint32_t s,
-                                               int sub, unsigned qmask, int tid, uint32_t* m_d, uint32_t* m_o);
+template <int K, class Fin>
+__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, Fin& fin, int split_from,
+                                               int ring_cap, uint32_t* __restrict__ worklist,
+                                               uint32_t* __restrict__ wl_count, uint32_t s, int sub, unsigned qmask, int tid,
+                                               uint32_t* m_d, uint32_t* m_o);
 #ifndef KQ_MINB
 #define KQ_MINB 4
 #endif
-template <int K>
+template <int K, class Fin>
 __global__ void __launch_bounds__(KQ_THREADS, KQ_MINB)
-knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps, double* __restrict__ cov, int split_from,
+knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, Fin fin, int split_from,
                        int ring_cap, uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count,
                        uint32_t* __restrict__ next_query /*nullable: dynamic distribution of 8-query batches*/) {
   __shared__ uint32_t m_d[(K + 1) * KQ_THREADS];
@@ -318,18 +359,18 @@ knn_cov_quadreg_kernel(GridView g, const f4* __restrict__ raw, int k, double eps
       wbase = __shfl_sync(0xffffffffu, b, 0);
     }
     if (wbase >= (uint32_t)g.n) return;
-    knn_quad_query<K>(g, raw, k, eps, cov, split_from, ring_cap, worklist, wl_count, wbase + (uint32_t)(lane >> 2), sub, qmask,
+    knn_quad_query<K>(g, raw, k, fin, split_from, ring_cap, worklist, wl_count, wbase + (uint32_t)(lane >> 2), sub, qmask,
                       tid, m_d, m_o);
     if (!next_query) return;
     __syncwarp();
   }
 }
 
-template <int K>
-__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, double eps,
-                                               double* __restrict__ cov, int split_from, int ring_cap,
-                                               uint32_t* __restrict__ worklist, uint32_t* __restrict__ wl_count, uint32_t s,
-                                               int sub, unsigned qmask, int tid, uint32_t* m_d, uint32_t* m_o) {
+template <int K, class Fin>
+__device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __restrict__ raw, int k, Fin& fin, int split_from,
+                                               int ring_cap, uint32_t* __restrict__ worklist,
+                                               uint32_t* __restrict__ wl_count, uint32_t s, int sub, unsigned qmask, int tid,
+                                               uint32_t* m_d, uint32_t* m_o) {
   if (s >= (uint32_t)g.n) return;   // whole quads exit together
   f4 q = g.pts[s];
   RegList<K> L;
@@ -338,7 +379,6 @@ __device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __re
   query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
   int r0, r1;
   ring_range(g, cx, cy, cz, r0, r1);
-  double sum[3], m2[6];
   // Shell r of a query in a sparse corner of the grid is (2r+1)^2 mostly empty rows of dependent look-ups: past
   // ring_cap the query goes to knn_cov_tail_kernel, where a whole warp shares the rows of each shell.
   bool done = r1 <= ring_cap;          // the whole grid gets scanned below: final even without the bound test
@@ -358,8 +398,7 @@ __device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __re
     }
     int p = 0, found = 0;
     float kth = 3.0e38f;
-    sum[0] = sum[1] = sum[2] = 0.0;
-    m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+    fin.reset();
     for (int round = 0; round < k; round++) {
       const uint32_t hd = m_d[p * KQ_THREADS + tid], ho = m_o[p * KQ_THREADS + tid];
       uint32_t bd = hd, bo = ho;
@@ -373,10 +412,7 @@ __device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __re
       if (bd == hd && bo == ho) p++;                       // original indices are unique: exactly one lane pops
       found++;
       kth = bits_to_float((int32_t)bd);
-      f4 pt = raw[bo];
-      sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
-      m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
-      m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+      fin.add(raw[bo]);
     }
     if (found == k && kth < ring_bound2(g, r, minfrac)) { done = true; break; }
   }
@@ -384,22 +420,16 @@ __device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __re
     if (sub == 0) worklist[atomicAdd(wl_count, 1u)] = s;
     return;
   }
-  double out[6];
-  cov_from_moments(sum, m2, k, eps, out);
-  if (sub == 0) {
-    double* d = cov + 6 * (size_t)s;
-#pragma unroll
-    for (int e = 0; e < 6; e++) d[e] = out[e];
-  }
+  fin.finish(s, q, k, sub == 0);
 }
 
 // K3 tail: one WARP per query for the sparse neighbourhoods the quad kernel gave up on.  The rows of each
 // shell are spread over the 32 lanes (a shell of radius r has (2r+1)^2 rows, most of them empty: the cost is
 // the dependent cell_start -> points loads, which now overlap 32-wide); a 32-way merge on packed
 // (d2, index) keys yields the exact top-k in ascending order.
-template <int K>
+template <int K, class Fin>
 __global__ void __launch_bounds__(128)
-knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, const uint32_t* __restrict__ worklist,
+knn_cov_tail_kernel(GridView g, int k, Fin fin, const uint32_t* __restrict__ worklist,
                     const uint32_t* __restrict__ wl_count) {
   const int lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -413,7 +443,6 @@ knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, con
     query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
     int r0, r1;
     ring_range(g, cx, cy, cz, r0, r1);
-    double sum[3] = {0., 0., 0.}, m2[6] = {0., 0., 0., 0., 0., 0.};
     for (int r = r0; r <= r1; r++) {
       // rows of the shell, lane-strided
       const int side = 2 * r + 1;
@@ -445,8 +474,7 @@ knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, con
       // k-round merge on packed keys: (float bits of d2 (non-negative: order preserving) << 32) | original index
       int p = 0, found = 0;
       float kth = 3.0e38f;
-      sum[0] = sum[1] = sum[2] = 0.0;
-      m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+      fin.reset();
       for (int round = 0; round < k; round++) {
         unsigned long long key = (p < L.cnt)
             ? (((unsigned long long)__float_as_uint(L.d2[p]) << 32) | (unsigned)L.oi[p])
@@ -464,20 +492,11 @@ knn_cov_tail_kernel(GridView g, int k, double eps, double* __restrict__ cov, con
         if (lane == src_lane) p++;
         found++;
         kth = __uint_as_float((unsigned)(best >> 32));
-        f4 pt = g.pts[bs];
-        sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
-        m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
-        m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+        fin.add(g.pts[bs]);
       }
       if (found == k && kth < ring_bound2(g, r, minfrac)) break;
     }
-    double out[6];
-    cov_from_moments(sum, m2, k, eps, out);
-    if (lane == 0) {
-      double* d = cov + 6 * (size_t)s;
-#pragma unroll
-      for (int e = 0; e < 6; e++) d[e] = out[e];
-    }
+    fin.finish(s, q, k, lane == 0);
     __syncwarp();
   }
 }

@@ -264,6 +264,116 @@ LB_HD void cov_from_normal(float nx, float ny, float nz, double eps, double* out
   out6[SZZ] = 1.0 - s * n[2] * n[2];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// per-point surface normal the way point_cloud_filter::NormalComputation obtains it
+// (normal_computation.cc:26-59 -> pcl::NormalEstimationOMP<PointXYZI, Normal>, k-NN mode).  PCL is not in the
+// reference tree; this restates PCL 1.10's published algorithm in float32 like PCL runs it:
+//   computeMeanAndCovarianceMatrix (common/impl/centroid.hpp, dense branch): nine float accumulators over the
+//     neighbours in search order, divided by the count, covariance = E[xx'] - mu mu';
+//   solvePlaneParameters (features/impl/feature.hpp) -> eigen33 (common/impl/eigen.hpp): smallest eigenvalue by the
+//     closed-form cubic (computeRoots / computeRoots2), eigenvector = largest of the three row cross products of
+//     (A - lambda I), curvature = |lambda / trace|;
+//   flipNormalTowardsViewpoint (features/normal_3d.h): negate when (vp - p) . n < 0.
+// Parity unpinned in the last bits (atan2f / cosf / sinf of the platform's libm); everything else is IEEE-exact.
+struct NormalAccum {       // accu[0..8] of computeMeanAndCovarianceMatrix
+  float a[9];
+  LB_HD void reset() { for (int i = 0; i < 9; i++) a[i] = 0.f; }
+  LB_HD void add(float x, float y, float z) {
+    a[0] = a[0] + x * x; a[1] = a[1] + x * y; a[2] = a[2] + x * z;
+    a[3] = a[3] + y * y; a[4] = a[4] + y * z; a[5] = a[5] + z * z;
+    a[6] = a[6] + x; a[7] = a[7] + y; a[8] = a[8] + z;
+  }
+};
+
+LB_HD void pcl_compute_roots2(float b, float c, float* roots) {
+  roots[0] = 0.f;
+  float d = b * b - 4.0f * c;
+  if (d < 0.0f) d = 0.0f;
+  float sd = sqrtf(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+LB_HD void pcl_compute_roots(const float m[3][3], float* roots) {
+  // characteristic polynomial det(x I - A) = x^3 - c2 x^2 + c1 x - c0
+  float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+             m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+             m[1][2] * m[1][2];
+  float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (fabsf(c0) < 1.1920929e-07f) {          // std::numeric_limits<float>::epsilon(): one root is 0
+    pcl_compute_roots2(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = 1.0f / 3.0f;
+  const float s_sqrt3 = sqrtf(3.0f);
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  float rho = sqrtf(-a_over_3);
+  float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+  float cos_theta = cosf(theta);
+  float sin_theta = sinf(theta);
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) { float t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+  if (roots[1] >= roots[2]) {
+    float t = roots[1]; roots[1] = roots[2]; roots[2] = t;
+    if (roots[0] >= roots[1]) { float u = roots[0]; roots[0] = roots[1]; roots[1] = u; }
+  }
+  if (roots[0] <= 0.0f) pcl_compute_roots2(c2, c1, roots);   // a PSD matrix has no negative eigenvalue: drop to the quadratic
+}
+
+// out4 = (nx, ny, nz, curvature) of the neighbourhood accumulated in `acc` (count points), flipped towards `vp`
+// as seen from the query point (px, py, pz).
+LB_HD void pcl_normal_from_accum(const NormalAccum& acc, int count, float px, float py, float pz, const float* vp,
+                                 float* out4) {
+  float a[9];
+  const float cnt = (float)count;
+  for (int i = 0; i < 9; i++) a[i] = acc.a[i] / cnt;
+  float C[3][3];
+  C[0][0] = a[0] - a[6] * a[6];
+  C[0][1] = a[1] - a[6] * a[7];
+  C[0][2] = a[2] - a[6] * a[8];
+  C[1][1] = a[3] - a[7] * a[7];
+  C[1][2] = a[4] - a[7] * a[8];
+  C[2][2] = a[5] - a[8] * a[8];
+  C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
+  // eigen33: scale to [-1, 1]
+  float scale = 0.f;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) { float v = fabsf(C[r][c]); if (v > scale) scale = v; }
+  if (scale <= 1.17549435e-38f) scale = 1.0f;           // std::numeric_limits<float>::min()
+  float S[3][3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) S[r][c] = C[r][c] / scale;
+  float roots[3];
+  pcl_compute_roots(S, roots);
+  const float eigenvalue = roots[0] * scale;
+  S[0][0] = S[0][0] - roots[0]; S[1][1] = S[1][1] - roots[0]; S[2][2] = S[2][2] - roots[0];
+  float v1[3] = {S[0][1] * S[1][2] - S[0][2] * S[1][1], S[0][2] * S[1][0] - S[0][0] * S[1][2], S[0][0] * S[1][1] - S[0][1] * S[1][0]};
+  float v2[3] = {S[0][1] * S[2][2] - S[0][2] * S[2][1], S[0][2] * S[2][0] - S[0][0] * S[2][2], S[0][0] * S[2][1] - S[0][1] * S[2][0]};
+  float v3[3] = {S[1][1] * S[2][2] - S[1][2] * S[2][1], S[1][2] * S[2][0] - S[1][0] * S[2][2], S[1][0] * S[2][1] - S[1][1] * S[2][0]};
+  float l1 = (v1[0] * v1[0] + v1[1] * v1[1]) + v1[2] * v1[2];
+  float l2 = (v2[0] * v2[0] + v2[1] * v2[1]) + v2[2] * v2[2];
+  float l3 = (v3[0] * v3[0] + v3[1] * v3[1]) + v3[2] * v3[2];
+  float n[3];
+  if (l1 >= l2 && l1 >= l3) { float s = sqrtf(l1); n[0] = v1[0] / s; n[1] = v1[1] / s; n[2] = v1[2] / s; }
+  else if (l2 >= l1 && l2 >= l3) { float s = sqrtf(l2); n[0] = v2[0] / s; n[1] = v2[1] / s; n[2] = v2[2] / s; }
+  else { float s = sqrtf(l3); n[0] = v3[0] / s; n[1] = v3[1] / s; n[2] = v3[2] / s; }
+  const float eig_sum = (C[0][0] + C[1][1]) + C[2][2];
+  float curvature = (eig_sum != 0.f) ? fabsf(eigenvalue / eig_sum) : 0.f;
+  // flipNormalTowardsViewpoint
+  float dx = vp[0] - px, dy = vp[1] - py, dz = vp[2] - pz;
+  float cos_theta = (dx * n[0] + dy * n[1]) + dz * n[2];
+  if (cos_theta < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  out4[0] = n[0]; out4[1] = n[1]; out4[2] = n[2]; out4[3] = curvature;
+}
+
 // Mahalanobis matrix M = (R C1 R' + C2)^-1  (gicp.hpp:484-493).  R row-major
 // 3x3 double; C1, C2, M symmetric-6.  Products follow the reference order
 // (R*C1 first, then *R'), inverse by cofactors / determinant like

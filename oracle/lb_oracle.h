@@ -191,6 +191,10 @@ void og_normalize_pcloud(const float* xyz, int n, float* out_xyz);
 void og_compute_ap(const float* query_xyz, int n, const float* ref_normals_xyz,
                    const int64_t* correspondences, double* Ap);
 
+/* point_cloud_filter::NormalComputation (k-NN mode) = pcl::NormalEstimationOMP, restated (normals_oracle.c).
+ * out4: n x (nx, ny, nz, curvature). */
+int og_normals_knn(const float* pts, int n, int stride_f, int k, const float vp[3], float* out4, int num_threads);
+
 #ifdef __cplusplus
 }
 #endif

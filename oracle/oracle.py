@@ -245,3 +245,16 @@ def compute_ap(query_xyz, ref_normals, correspondences):
     Ap = np.zeros(36)
     lib().og_compute_ap(_p(q), q.shape[0], _p(nr), _p(co), _p(Ap))
     return Ap.reshape(6, 6)
+
+
+def normals_knn(pts, k=20, viewpoint=(0.0, 0.0, 0.0), num_threads=8):
+    """point_cloud_filter::NormalComputation, k-NN mode (normals_oracle.c).  pts: (n, >=3) float32.
+    Returns (n, 4) float32: nx, ny, nz, curvature."""
+    p = _as_cloud(pts)
+    vp = np.ascontiguousarray(viewpoint, dtype=np.float32)
+    out = np.zeros((p.shape[0], 4), dtype=np.float32)
+    lib().og_normals_knn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    rc = lib().og_normals_knn(_p(p), p.shape[0], p.shape[1], int(k), _p(vp), _p(out), int(num_threads))
+    if rc != 0:
+        raise ValueError("og_normals_knn: need 3 <= k <= n")
+    return out

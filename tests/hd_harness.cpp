@@ -106,6 +106,24 @@ void hh_knn_batch(void* g, const float* q, int nq, int stride_f, int k, int* idx
 }
 
 // k-NN covariances exactly as the cov kernel does per thread; out: n x 6 (sym) in ORIGINAL order
+// Row f2: the product's NormalAccum / pcl_normal_from_accum (hd.h) driven by the product's exact k-NN (grid.h),
+// original point order.  Same libm as the oracle on this machine -> bit-identical to og_normals_knn.
+void hh_normals_knn(void* g, int k, const float* vp, float* out4) {
+  HGrid* G = (HGrid*)g;
+  for (int s = 0; s < G->v.n; s++) {
+    f4 q = G->pts[s];
+    KnnList<32> L;
+    int c = knn<32>(G->v, q.x, q.y, q.z, k, L);
+    NormalAccum acc;
+    acc.reset();
+    for (int j = 0; j < c; j++) {
+      f4 p = G->pts[L.si[j]];
+      acc.add(p.x, p.y, p.z);
+    }
+    pcl_normal_from_accum(acc, c, q.x, q.y, q.z, vp, &out4[4 * (size_t)float_to_bits(q.w)]);
+  }
+}
+
 void hh_cov_knn(void* g, int k, double eps, double* out6) {
   HGrid* G = (HGrid*)g;
   for (int s = 0; s < G->v.n; s++) {

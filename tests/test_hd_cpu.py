@@ -119,3 +119,22 @@ def test_reglist_keeps_topk_sorted(harness, n, gated):
     assert cnt.value == m
     assert np.array_equal(oo[:m], orig[order]) and np.array_equal(od[:m], d2[order])
     assert (oo[m:] == -1).all()
+
+
+@pytest.mark.parametrize("name", list(CLOUDS))
+@pytest.mark.parametrize("k", [5, 20])
+def test_normals_bit_exact_vs_oracle(harness, oracle, name, k):
+    """row f2: hd.h's PCL-style normal estimation == the oracle's independent restatement, bit for bit (same libm)"""
+    pts = np.ascontiguousarray(CLOUDS[name](), dtype=np.float32)[:3000]
+    g = harness.hh_grid_build(_p(pts), len(pts), 3, 0.4)
+    vp = np.array([0.5, -1.0, 2.0], np.float32)
+    out = np.zeros((len(pts), 4), np.float32)
+    harness.hh_normals_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    harness.hh_normals_knn(g, k, _p(vp), _p(out))
+    ref = oracle.normals_knn(pts, k, viewpoint=vp)
+    harness.hh_grid_free(g)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    nrm = np.linalg.norm(ref[:, :3].astype(np.float64), axis=1)
+    ok = np.isfinite(nrm)
+    assert np.abs(nrm[ok] - 1).max() < 1e-5
+    assert (((vp - pts[ok]).astype(np.float64) * ref[ok, :3]).sum(1) >= -1e-6).all()      # flipped towards the viewpoint
