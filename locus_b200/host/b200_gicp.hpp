@@ -99,6 +99,18 @@ class B200Gicp {
   bool nearestKSearchTarget(const PointF* pts, size_t n, int32_t* idx, float* d2) {
     return lb_gicp_nn_target(h_, pts, n, sizeof(PointF), idx, d2, LB_MEM_HOST) == LB_OK;
   }
+  // point_cloud_filter::NormalComputation::filter, k-NN mode (normal_computation.cc:26-59): writes normal_x/y/z of
+  // every point of `cloud` (the curvature field is left alone, as the nodelet does).  3 <= k <= 20.
+  bool computeNormals(PointF* cloud, size_t n, int k = 20) {
+    if (lb_gicp_set_source(h_, cloud, n, sizeof(PointF), 0, LB_NO_NORMALS, LB_MEM_HOST) != LB_OK) return false;
+    n_src_ = n;
+    std::vector<float> nrm(4 * n);
+    if (lb_gicp_compute_normals(h_, 0, k, nullptr, nrm.data(), LB_MEM_HOST) != LB_OK) return false;
+    for (size_t i = 0; i < n; i++) {
+      cloud[i].normal_x = nrm[4 * i]; cloud[i].normal_y = nrm[4 * i + 1]; cloud[i].normal_z = nrm[4 * i + 2];
+    }
+    return true;
+  }
   const lb_gicp_result& result() const { return r_; }
   lb_gicp* handle() { return h_; }
 
@@ -154,6 +166,42 @@ class B200VoxelGrid {
   std::string field_;
   double lo_ = -3.4028234663852886e38, hi_ = 3.4028234663852886e38;
   bool neg_ = false;
+};
+
+// The per-scan chain of the lidar callback (locus/src/Locus.cc:451-453: odometry_.SetLidar(filtered) +
+// odometry_.UpdateEstimate(); PointCloudOdometry.cc:221-274) as the library's pipeline: submit raw PointCloud2 blobs
+// in order, take results in order; scan k+1 is filtered while scan k is registered, `depth` registrations in flight.
+class B200Odometry {
+ public:
+  B200Odometry(int device, int depth, size_t max_points, uint32_t max_point_step) {
+    if (lb_odometry_create(device, depth, max_points, max_point_step, &h_) != LB_OK) throw std::runtime_error(lb_last_error_string());
+    lb_gicp_default_params(&p_);
+  }
+  ~B200Odometry() { lb_odometry_destroy(h_); }
+  B200Odometry(const B200Odometry&) = delete;
+  B200Odometry& operator=(const B200Odometry&) = delete;
+
+  void setLeafSize(float l) { lb_voxel_set_leaf_size(lb_odometry_voxel(h_), l, l, l); }
+  void setFilterLimits(const std::string& field, double lo, double hi) {
+    lb_voxel_set_filter_limits(lb_odometry_voxel(h_), field.c_str(), lo, hi, 0);
+  }
+  lb_gicp_params& params() { return p_; }                       // edit, then applyParams() while the pipeline is idle
+  bool applyParams() { return lb_odometry_set_gicp_params(h_, &p_) == LB_OK; }
+
+  // scan (and filtered_out, if given) must stay valid until next() has returned this ticket
+  bool submit(const uint8_t* scan, size_t n_pts, uint32_t point_step, const std::vector<lb_field>& fields,
+              const Matrix4f* prior = nullptr, uint8_t* filtered_out = nullptr, uint64_t* ticket = nullptr) {
+    return lb_odometry_submit(h_, scan, n_pts, point_step, fields.data(), (int)fields.size(), LB_MEM_HOST,
+                              prior ? prior->data() : nullptr, filtered_out, LB_MEM_HOST, ticket) == LB_OK;
+  }
+  // false when nothing is ready (block == false) or nothing is pending
+  bool next(lb_odometry_result* r, bool block = true) { return lb_odometry_next(h_, r, block ? 1 : 0) == LB_OK; }
+  size_t pending() const { size_t n = 0; lb_odometry_pending(h_, &n); return n; }
+  lb_odometry* handle() { return h_; }
+
+ private:
+  lb_odometry* h_ = nullptr;
+  lb_gicp_params p_{};
 };
 
 }  // namespace locus_b200

@@ -7,6 +7,8 @@ import pytest
 
 import conftest
 
+ROOT = conftest.ROOT
+
 
 def test_exports_match_header():
     import locus_b200
@@ -40,3 +42,25 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "lb_oracle" not in txt and "liblocus_oracle" not in txt and "from oracle" not in txt, f
+
+
+def _build_host_example():
+    import subprocess
+    host = os.path.join(ROOT, "locus_b200", "host")
+    out = os.path.join(ROOT, "tests", "_build", "example_odometry")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", host,
+                           os.path.join(host, "example_odometry.cpp"), "-L", os.path.join(ROOT, "locus_b200"),
+                           "-llocus_b200", "-Wl,-rpath," + os.path.join(ROOT, "locus_b200"), "-pthread", "-o", out])
+    return out
+
+
+def test_cpp_host_mirror_compiles_and_links():
+    """locus_b200/host/b200_gicp.hpp (B200Gicp, B200VoxelGrid, B200Odometry) against the C ABI; without a GPU the
+    example reports that there is nothing to run (the library has no CPU path) and exits 0"""
+    import subprocess
+    import locus_b200
+    exe = _build_host_example()
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=120)
+    if locus_b200.device_count() <= 0:
+        assert r.returncode == 0 and "no CUDA device" in r.stdout

@@ -264,3 +264,12 @@ def test_point2plane_information_known_answers(oracle):
     ok = ~(np.isnan(q).any(1) | np.isnan(nr[co]).any(1))
     H = np.concatenate([np.cross(q[ok].astype(np.float64), nr[co][ok]), nr[co][ok]], axis=1)
     assert np.allclose(Ap, H.T @ H, rtol=1e-9, atol=1e-7)
+
+
+def test_cpp_host_mirror_runs():
+    """the PCL-free C++ mirror (B200Gicp align, computeNormals, B200Odometry) end to end on the hollow-cube fixture"""
+    import subprocess
+    from test_cabi_cpu import _build_host_example
+    r = subprocess.run([_build_host_example()], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert "converged=1" in r.stdout and "pipeline:" in r.stdout
