@@ -435,9 +435,9 @@ def main():
     dbg = [gicp.kernelTime("debug%d" % i)[0] for i in range(4)]
     dbg6 = gicp.kernelTime("debug6")[0]
     dbg7 = gicp.kernelTime("debug7")[0]; dbg8 = gicp.kernelTime("debug8")[0]
-    snapP = [gicp.kernelTime("snapP%d" % i)[0] for i in range(64)]
-    snapC = [gicp.kernelTime("snapC%d" % i)[0] for i in range(64)]
-    if os.environ.get("LB_SNAP"):
+    if os.environ.get("LB_SNAP"):     # debugging aid: per-CTA publish / completion times of one collective
+        snapP = [gicp.kernelTime("snapP%d" % i)[0] for i in range(64)]
+        snapC = [gicp.kernelTime("snapC%d" % i)[0] for i in range(64)]
         sys.stderr.write("SNAP publish ns: %s\nSNAP complete ns: %s\n" % (snapP, snapC))
     gicp.resetKernelTimes(False)
     gpu_poses = list(state["poses"])
