@@ -25,6 +25,34 @@ struct HGrid {
 };
 
 extern "C" {
+// CPU model of knn_cov_quadreg_kernel's candidate handling: the candidates of one query are dealt round-robin to
+// four RegLists (the quad's lanes); every `refresh` candidates the shared gate is tightened to the maximum of the
+// lanes' (K/4)-th best keys (quad_row_done); at the end the four lists are merged.  The merged top-k must equal
+// the plain sorted top-k whatever the refresh cadence -- i.e. the gate never rejects a true neighbour.
+int hh_quad_gate_model(const float* d2, const int* orig, int n, int k, int refresh, int* out_orig) {
+  RegList<20> L[4];
+  for (int l = 0; l < 4; l++) L[l].init();
+  for (int i = 0; i < n; i++) {
+    L[i & 3].push(d2[i], orig[i]);
+    if (refresh > 0 && (i % refresh) == refresh - 1) {
+      unsigned long long t = 0;
+      for (int l = 0; l < 4; l++) t = L[l].key[20 / 4 - 1] > t ? L[l].key[20 / 4 - 1] : t;
+      for (int l = 0; l < 4; l++) L[l].gate = t;
+    }
+  }
+  int p[4] = {0, 0, 0, 0}, found = 0;
+  for (int round = 0; round < k; round++) {
+    int best = -1;
+    unsigned long long bk = ~0ull;
+    for (int l = 0; l < 4; l++)
+      if (p[l] < 20 && L[l].key[p[l]] < bk) { bk = L[l].key[p[l]]; best = l; }
+    if (best < 0) break;
+    out_orig[found++] = (int)(uint32_t)bk;
+    p[best]++;
+  }
+  return found;
+}
+
 // RegList (the register-resident candidate list of knn_cov_quadreg_kernel): after n pushes of (d2, orig) it must
 // hold the K best in ascending (d2, orig) order.  gate_d2 >= 0: candidates not better than (gate_d2, gate_orig)
 // are rejected on top of that.  out_*: K entries (-1 when unfilled).

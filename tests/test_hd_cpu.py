@@ -138,3 +138,25 @@ def test_normals_bit_exact_vs_oracle(harness, oracle, name, k):
     ok = np.isfinite(nrm)
     assert np.abs(nrm[ok] - 1).max() < 1e-5
     assert (((vp - pts[ok]).astype(np.float64) * ref[ok, :3]).sum(1) >= -1e-6).all()      # flipped towards the viewpoint
+
+
+@pytest.mark.parametrize("refresh", [0, 1, 3, 17, 64])
+@pytest.mark.parametrize("n", [3, 19, 20, 21, 80, 400])
+def test_quad_gate_never_drops_a_neighbour(harness, n, refresh):
+    """the quad-shared pruning gate of knn_cov_quadreg_kernel (max over lanes of their 5th best key) is exact: merged
+    top-k of four gated lists == sorted top-k, with ties, duplicates and every refresh cadence"""
+    rng = np.random.default_rng(1000 * n + refresh)
+    d2 = np.where(rng.random(n) < 0.4, rng.choice(np.array([0.0, 0.5, 0.5, 2.0], np.float32), n),
+                  rng.random(n).astype(np.float32) * 3).astype(np.float32)
+    if n >= 80:                      # adversarial order: best candidates last, all of them in one lane
+        order = np.argsort(-d2, kind="stable")
+        d2 = d2[order]
+    orig = rng.permutation(4 * n)[:n].astype(np.int32)
+    harness.hh_quad_gate_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    harness.hh_quad_gate_model.restype = C.c_int
+    for k in (1, 7, 20):
+        out = np.full(20, -1, np.int32)
+        found = harness.hh_quad_gate_model(_p(d2), _p(orig), n, k, refresh, _p(out))
+        want = orig[np.lexsort((orig, d2))][:k]
+        assert found == len(want)
+        assert np.array_equal(out[:found], want)
