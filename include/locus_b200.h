@@ -230,6 +230,11 @@ int lb_voxel_set_leaf_size(lb_voxel* h, float lx, float ly, float lz);
 int lb_voxel_get_leaf_size(lb_voxel* h, float* leaf3);
 /* field_name NULL or "" = no filter field.  Defaults: none, [-FLT_MAX, FLT_MAX], not negative. */
 int lb_voxel_set_filter_limits(lb_voxel* h, const char* field_name, double limit_min, double limit_max, int negative);
+/* SURVEY 8f row f4 -- the BodyFilter nodelet that runs right before the voxel grid
+ * (point_cloud_filter/src/body_filter.cc:28-56: pcl::CropBox<PointXYZI>, setMin/setMax from cfg/BodyFilter.cfg,
+ * setRotation((0, 0, rotation)), setNegative(true)) folded into the filter's load predicate: points inside the box
+ * (rotated by rotation_z about z) are removed before voxelisation.  enabled = 0 restores the plain VoxelGrid. */
+int lb_voxel_set_body_filter(lb_voxel* h, int enabled, const float* min3, const float* max3, float rotation_z);
 int lb_voxel_set_min_points_per_voxel(lb_voxel* h, int min_points);
 int lb_voxel_set_downsample_all_data(lb_voxel* h, int all);
 

@@ -70,7 +70,7 @@ SYMBOLS = [
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
-    "lb_voxel_set_downsample_all_data", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
+    "lb_voxel_set_downsample_all_data", "lb_voxel_set_body_filter", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
     "lb_odometry_set_gicp_params", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
     "lb_odometry_launch_count", "lb_odometry_stage_times",
@@ -138,6 +138,8 @@ def lib():
     L.lb_voxel_set_filter_limits.argtypes = [vp, C.c_char_p, C.c_double, C.c_double, i32]
     L.lb_voxel_set_min_points_per_voxel.argtypes = [vp, i32]
     L.lb_voxel_set_downsample_all_data.argtypes = [vp, i32]
+    if hasattr(L, "lb_voxel_set_body_filter"):
+        L.lb_voxel_set_body_filter.argtypes = [vp, i32, vp, vp, C.c_float]
     L.lb_voxel_filter.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, vp, sz, vp, sz,
                                   C.POINTER(sz), vp, i32, i32]
     L.lb_voxel_launch_count.argtypes = [vp, u64p]
@@ -390,6 +392,14 @@ class VoxelGridB200:
 
     def setMinimumPointsNumberPerVoxel(self, m): _check(lib().lb_voxel_set_min_points_per_voxel(self._h, int(m)))
     def setDownsampleAllData(self, a): _check(lib().lb_voxel_set_downsample_all_data(self._h, int(bool(a))))
+
+    def setBodyFilter(self, min3=None, max3=None, rotation_z=0.0, enabled=True):
+        """BodyFilter nodelet (pcl::CropBox, negative) folded into the filter: drop the points inside the rotated box"""
+        if not enabled or min3 is None:
+            _check(lib().lb_voxel_set_body_filter(self._h, 0, None, None, 0.0))
+            return
+        mn = np.ascontiguousarray(min3, dtype=np.float32); mx = np.ascontiguousarray(max3, dtype=np.float32)
+        _check(lib().lb_voxel_set_body_filter(self._h, 1, _ptr(mn), _ptr(mx), np.float32(rotation_z)))
 
     @staticmethod
     def _fields(fields):

@@ -264,6 +264,22 @@ LB_HD void cov_from_normal(float nx, float ny, float nz, double eps, double* out
   out6[SZZ] = 1.0 - s * n[2] * n[2];
 }
 
+// the BodyFilter nodelet (point_cloud_filter/src/body_filter.cc:28-56 = pcl::CropBox<PointXYZI> with
+// setNegative(true) and a rotation about z) folded into the VoxelGrid's load predicate.  ia, ib = cos, sin of the
+// rotation divided by cos^2 + sin^2 (the 3x3 inverse PCL takes of its float32 rotation matrix); a point whose local
+// coordinates lie inside [min, max] is removed.  Parity unpinned in the last bit (PCL absent).
+struct BodyBox {
+  int enabled;
+  float ia, ib;
+  float mn[3], mx[3];
+};
+LB_HD bool body_box_drops(const BodyBox& b, float x, float y, float z) {
+  if (!b.enabled) return false;
+  float lx = b.ia * x + b.ib * y, ly = b.ia * y - b.ib * x, lz = z;
+  bool outside = (lx < b.mn[0] || ly < b.mn[1] || lz < b.mn[2]) || (lx > b.mx[0] || ly > b.mx[1] || lz > b.mx[2]);
+  return !outside;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-point surface normal the way point_cloud_filter::NormalComputation obtains it
 // (normal_computation.cc:26-59 -> pcl::NormalEstimationOMP<PointXYZI, Normal>, k-NN mode).  PCL is not in the

@@ -53,7 +53,7 @@ __global__ void bbox_init_kernel(BBoxAcc* acc) {
 
 __global__ void __launch_bounds__(256)
 bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off,
-            int ff_off, float fmin, float fmax, int negative, BBoxAcc* acc) {
+            int ff_off, float fmin, float fmax, int negative, BodyBox body, BBoxAcc* acc) {
   uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0, mx1 = 0, mx2 = 0, cnt = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint8_t* p = base + (size_t)i * stride;
@@ -65,6 +65,7 @@ bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint3
     const float* q = reinterpret_cast<const float*>(p + xyz_off);
     float x = q[0], y = q[1], z = q[2];
     if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+    if (body_box_drops(body, x, y, z)) continue;
     uint32_t ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
     mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
     mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);

@@ -114,7 +114,7 @@ __device__ __forceinline__ void bbox_reset(BBoxAcc* acc) {
 // Optional limit filter (VoxelGrid getMinMax3D): field value v at ff_off is
 // dropped if  negative ? (v < fmax && v > fmin) : (v > fmax || v < fmin), float compare.
 __global__ void bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off,
-                            int ff_off, float fmin, float fmax, int negative, BBoxAcc* acc);
+                            int ff_off, float fmin, float fmax, int negative, BodyBox body, BBoxAcc* acc);
 
 // ------------------------------------------------------------------ scan
 // Exclusive scan of n uint32 (in may alias out).  total (nullable, device) receives the grand total.

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256)
 vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t x_off, uint32_t y_off,
                uint32_t z_off, int ff_off, double lim_min, double lim_max, int negative, float inv0, float inv1,
                float inv2, int min_b0, int min_b1, int min_b2, int mul1, int mul2, uint32_t sentinel,
-               uint32_t* __restrict__ keys, BBoxAcc* acc_to_reset) {
+               BodyBox body, uint32_t* __restrict__ keys, BBoxAcc* acc_to_reset) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) bbox_reset(acc_to_reset);   // the host has consumed the bounding box: ready for the next call
   if (i >= n) return;
@@ -46,6 +46,7 @@ vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, ui
   float y = *reinterpret_cast<const float*>(p + y_off);
   float z = *reinterpret_cast<const float*>(p + z_off);
   ok = ok && isfinite(x) && isfinite(y) && isfinite(z);
+  ok = ok && !body_box_drops(body, x, y, z);       // BodyFilter folded into the load predicate (row f4)
   uint32_t key = sentinel;
   if (ok) {
     // static_cast<int>(floor(x * inv_leaf) - float(min_b))   (voxel_grid_covariance_omp_impl.hpp:159-161)
@@ -248,6 +249,7 @@ struct lb_voxel {
   int negative = 0;
   int min_points = 0;
   int downsample_all = 1;
+  BodyBox body{0, 1.f, 0.f, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // BodyFilter nodelet folded in (lb_voxel_set_body_filter)
   DBuf<uint8_t> d_in, d_out;
   DBuf<int32_t> d_vidx;
   DBuf<uint32_t> keys, flags, seg_start, keep, slot;
@@ -323,6 +325,18 @@ int lb_voxel_set_filter_limits(lb_voxel* h, const char* field_name, double limit
   h->lim_min = limit_min; h->lim_max = limit_max; h->negative = negative ? 1 : 0;
   return LB_OK;
 }
+int lb_voxel_set_body_filter(lb_voxel* h, int enabled, const float* min3, const float* max3, float rotation_z) {
+  if (!h || (enabled && (!min3 || !max3))) { set_error("lb_voxel_set_body_filter: null argument"); return LB_ERR_INVALID_ARG; }
+  h->body.enabled = enabled ? 1 : 0;
+  if (enabled) {
+    // inverse of PCL's getTransformation(0,0,0, 0,0,rz) taken the way Eigen inverts a 3x3: adjugate / determinant
+    float A = cosf(rotation_z), B = sinf(rotation_z);
+    float det = A * A + B * B;
+    h->body.ia = A / det; h->body.ib = B / det;
+    for (int d = 0; d < 3; d++) { h->body.mn[d] = min3[d]; h->body.mx[d] = max3[d]; }
+  }
+  return LB_OK;
+}
 int lb_voxel_set_min_points_per_voxel(lb_voxel* h, int m) { if (!h) return LB_ERR_INVALID_ARG; h->min_points = m; return LB_OK; }
 int lb_voxel_set_downsample_all_data(lb_voxel* h, int all) { if (!h) return LB_ERR_INVALID_ARG; h->downsample_all = all ? 1 : 0; return LB_OK; }
 int lb_voxel_launch_count(lb_voxel* h, uint64_t* n) { if (!h || !n) return LB_ERR_INVALID_ARG; *n = h->c.launches; return LB_OK; }
@@ -386,7 +400,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   // ---- bounding box of the surviving points (pcl::getMinMax3D with float limits)
   int bb_blocks = min(cdiv(n, 256), c.sm_count * 2);
   bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, ffo, (float)h->lim_min,
-                                                (float)h->lim_max, h->negative, h->d_acc);
+                                                (float)h->lim_max, h->negative, h->body, h->d_acc);
   c.launches += 1;
   LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
@@ -420,7 +434,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   LB_TRY(h->keys.ensure(n)); LB_TRY(h->flags.ensure(n)); LB_TRY(h->seg_start.ensure(n));
   vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, n, point_step, xo, yo, zo, ffo, h->lim_min, h->lim_max,
                                                      h->negative, inv[0], inv[1], inv[2], min_b[0], min_b[1], min_b[2],
-                                                     div_b[0], div_b[0] * div_b[1], sentinel, h->keys.p, h->d_acc);
+                                                     div_b[0], div_b[0] * div_b[1], sentinel, h->body, h->keys.p, h->d_acc);
   c.launches++;
   uint32_t *sk = nullptr, *sv = nullptr;
   LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));

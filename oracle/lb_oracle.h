@@ -165,6 +165,11 @@ typedef struct {
   int filter_limit_negative;
   int min_points_per_voxel;
   int downsample_all_data;   /* 1 (PCL default): average every FLOAT32 field */
+  /* the BodyFilter nodelet ahead of the voxel grid (point_cloud_filter/src/body_filter.cc:28-56 =
+   * pcl::CropBox, negative): points inside the box (rotated by body_rotation about z) are removed first */
+  int body_enabled;
+  float body_min[3], body_max[3];
+  float body_rotation;
 } og_voxel_params;
 
 /* data: n points of point_step bytes; x/y/z FLOAT32 at the given byte offsets.

@@ -50,6 +50,7 @@ class VoxelParams(C.Structure):
         ("filter_limit_min", C.c_double), ("filter_limit_max", C.c_double),
         ("filter_limit_negative", C.c_int), ("min_points_per_voxel", C.c_int),
         ("downsample_all_data", C.c_int),
+        ("body_enabled", C.c_int), ("body_min", C.c_float * 3), ("body_max", C.c_float * 3), ("body_rotation", C.c_float),
     ]
 
 
@@ -204,7 +205,7 @@ def bfgs_quadratic(A, b, x0, max_iters=100, grad_tol=1e-8):
 
 def voxel_filter(blob, point_step, leaf, x_off=0, y_off=4, z_off=8, float_fields=None,
                  filter_field_offset=-1, limit_min=-3.4028234663852886e38, limit_max=3.4028234663852886e38,
-                 negative=False, min_points_per_voxel=0, downsample_all_data=True):
+                 negative=False, min_points_per_voxel=0, downsample_all_data=True, body=None):
     """blob: uint8 array of n*point_step bytes.  Returns dict(out, voxel_idx, first_pt, count, min_b, div_b, rc)."""
     blob = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
     n = blob.size // point_step
@@ -219,6 +220,11 @@ def voxel_filter(blob, point_step, leaf, x_off=0, y_off=4, z_off=8, float_fields
     P.filter_limit_min = limit_min; P.filter_limit_max = limit_max
     P.filter_limit_negative = int(negative); P.min_points_per_voxel = min_points_per_voxel
     P.downsample_all_data = int(downsample_all_data)
+    if body is not None:          # (min3, max3, rotation_z): the BodyFilter nodelet ahead of the voxel grid
+        P.body_enabled = 1
+        for i in range(3):
+            P.body_min[i] = np.float32(body[0][i]); P.body_max[i] = np.float32(body[1][i])
+        P.body_rotation = np.float32(body[2])
     out = np.zeros(max(n, 1) * point_step, dtype=np.uint8)
     vidx = np.zeros(max(n, 1), dtype=np.int32); first = np.zeros(max(n, 1), dtype=np.int32)
     cnt = np.zeros(max(n, 1), dtype=np.int32)

@@ -48,6 +48,21 @@ static inline int dropped_by_limits_f(float v, const og_voxel_params* P) {
   return (v > mx || v < mn);
 }
 
+/* BodyFilter (body_filter.cc:28-56): pcl::CropBox<PointXYZI>, setNegative(true), setRotation((0, 0, rz)).
+ * PCL 1.10 filters/impl/crop_box.hpp: local = inverse(getTransformation(0,0,0, 0,0,rz)) * p in float32; the point
+ * is INSIDE unless a local coordinate lies below min or above max; negative -> inside points are removed.
+ * Parity unpinned (PCL absent): the last bit of the 3x3 inverse only matters for points within 1e-7 of a face. */
+static inline int dropped_by_body(float x, float y, float z, const og_voxel_params* P) {
+  if (!P->body_enabled) return 0;
+  float A = cosf(P->body_rotation), B = sinf(P->body_rotation);
+  float det = A * A + B * B;
+  float ia = A / det, ib = B / det;
+  float lx = ia * x + ib * y, ly = ia * y - ib * x, lz = z;
+  int outside = (lx < P->body_min[0] || ly < P->body_min[1] || lz < P->body_min[2]) ||
+                (lx > P->body_max[0] || ly > P->body_max[1] || lz > P->body_max[2]);
+  return !outside;
+}
+
 int og_voxel_filter(const uint8_t* data, size_t n, uint32_t point_step,
                     uint32_t x_off, uint32_t y_off, uint32_t z_off,
                     const uint32_t* ffo, int n_ff, const og_voxel_params* P,
@@ -71,6 +86,7 @@ int og_voxel_filter(const uint8_t* data, size_t n, uint32_t point_step,
     }
     float x = ldf(p + x_off), y = ldf(p + y_off), z = ldf(p + z_off);
     if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+    if (dropped_by_body(x, y, z, P)) continue;
     if (x < min_p[0]) min_p[0] = x; if (y < min_p[1]) min_p[1] = y; if (z < min_p[2]) min_p[2] = z;
     if (x > max_p[0]) max_p[0] = x; if (y > max_p[1]) max_p[1] = y; if (z > max_p[2]) max_p[2] = z;
     n_valid++;
@@ -102,6 +118,7 @@ int og_voxel_filter(const uint8_t* data, size_t n, uint32_t point_step,
     }
     float x = ldf(p + x_off), y = ldf(p + y_off), z = ldf(p + z_off);
     if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+    if (dropped_by_body(x, y, z, P)) continue;
     int ijk0 = (int)(floorf(x * inv[0]) - (float)min_b[0]);
     int ijk1 = (int)(floorf(y * inv[1]) - (float)min_b[1]);
     int ijk2 = (int)(floorf(z * inv[2]) - (float)min_b[2]);

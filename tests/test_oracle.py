@@ -93,3 +93,28 @@ def test_voxel_oracle_vs_numpy(oracle):
     acc = acc / np.float32(len(members))
     got = r["out"][k].view(np.float32)[:3]
     assert np.array_equal(got, acc)
+
+
+def test_body_filter_in_voxel_oracle_vs_numpy(oracle):
+    """row f4: BodyFilter (pcl::CropBox, negative, rotated about z) ahead of the voxel grid == an independent numpy
+    restatement of the predicate followed by the plain voxel oracle on the surviving points"""
+    from tools import gen_lidar as G
+    scene = G.make_scene(3)
+    blob = G.scan(scene, np.eye(4), 5, beams=16, az=512)
+    mn = np.array([-6.0, -3.0, -1.5], np.float32); mx = np.array([2.5, 5.0, 0.4], np.float32); rot = np.float32(-0.785398)
+    r = oracle.voxel_filter(blob, 32, 0.4, float_fields=G.FLOAT_FIELDS, filter_field_offset=8, limit_min=-100,
+                            limit_max=100, body=(mn, mx, rot))
+    pts = blob.reshape(-1, 32)
+    xyz = G.blob_xyz(blob)
+    c, s = np.cos(rot, dtype=np.float32), np.sin(rot, dtype=np.float32)
+    det = c * c + s * s
+    ia, ib = c / det, s / det
+    lx = ia * xyz[:, 0] + ib * xyz[:, 1]; ly = ia * xyz[:, 1] - ib * xyz[:, 0]; lz = xyz[:, 2]
+    with np.errstate(invalid="ignore"):
+        inside = ~((lx < mn[0]) | (ly < mn[1]) | (lz < mn[2]) | (lx > mx[0]) | (ly > mx[1]) | (lz > mx[2]))
+    fin = np.isfinite(xyz).all(1)
+    assert (inside & fin).sum() > 100 and (~inside & fin).sum() > 100
+    keep = np.ascontiguousarray(pts[~inside | ~fin]).reshape(-1)
+    r2 = oracle.voxel_filter(keep, 32, 0.4, float_fields=G.FLOAT_FIELDS, filter_field_offset=8, limit_min=-100, limit_max=100)
+    assert r["rc"] == 0 and np.array_equal(r["voxel_idx"], r2["voxel_idx"]) and np.array_equal(r["out"], r2["out"])
+    assert int(r["count"].sum()) == int((~inside & fin).sum())

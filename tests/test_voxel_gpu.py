@@ -22,7 +22,7 @@ def _ulp_diff(a, b):
     return np.abs(a - b)
 
 
-def _run(blob, leaf, ff="z", lo=-100.0, hi=100.0, neg=False, min_pts=0, all_data=True):
+def _run(blob, leaf, ff="z", lo=-100.0, hi=100.0, neg=False, min_pts=0, all_data=True, body=None):
     import locus_b200
     from oracle import oracle as O
     vg = locus_b200.VoxelGridB200()
@@ -33,10 +33,12 @@ def _run(blob, leaf, ff="z", lo=-100.0, hi=100.0, neg=False, min_pts=0, all_data
         vg.setFilterFieldName(ff); vg.setFilterLimits(lo, hi); vg.setFilterLimitsNegative(neg)
     vg.setMinimumPointsNumberPerVoxel(min_pts)
     vg.setDownsampleAllData(all_data)
+    if body is not None:
+        vg.setBodyFilter(*body)
     out, vidx = vg.filter(blob, 32, _fields(), want_voxel_idx=True)
     ffo = {"x": 0, "y": 4, "z": 8, "intensity": 16}.get(ff, -1) if ff else -1
     r = O.voxel_filter(blob, 32, leaf, float_fields=G.FLOAT_FIELDS, filter_field_offset=ffo, limit_min=lo,
-                       limit_max=hi, negative=neg, min_points_per_voxel=min_pts, downsample_all_data=all_data)
+                       limit_max=hi, negative=neg, min_points_per_voxel=min_pts, downsample_all_data=all_data, body=body)
     return out, vidx, r, vg
 
 
@@ -130,3 +132,19 @@ def test_voxel_large_inputs_and_long_segments(n_scans, leaf):
     out, vidx, r, _ = _run(blob, leaf)
     _check(out, vidx, r)
     assert int(r["count"].max()) > (2000 if leaf > 1 else 1)
+
+
+def test_voxel_with_body_filter():
+    """row f4: the BodyFilter nodelet (CropBox, negative, rotated about z; cfg/BodyFilter.cfg defaults scaled up so
+    that the synthetic scan has points inside) folded into the voxel filter: bit-exact vs the oracle, and switching
+    it off again restores the plain result"""
+    scene = G.make_scene(3)
+    blob = G.scan(scene, np.eye(4), 5, beams=32, az=1024)
+    body = (np.array([-6.0, -3.0, -1.5], np.float32), np.array([2.5, 5.0, 0.4], np.float32), -0.785398)
+    out, vidx, r, vg = _run(blob, 0.3, body=body)
+    _check(out, vidx, r)
+    plain, pvidx, rp, _ = _run(blob, 0.3)
+    assert int(r["count"].sum()) < int(rp["count"].sum())          # something was cropped
+    vg.setBodyFilter(enabled=False)
+    again = vg.filter(blob, 32, _fields())
+    assert np.array_equal(again, plain)
