@@ -8,6 +8,10 @@ with the odometry settings of SURVEY.md 8d/C2: 50 outer iterations max, 20 inner
 tf_eps 1e-3, k-NN(20) covariances.  Source AND target index + covariances are rebuilt every step,
 exactly like the reference's callers (PointCloudOdometry.cc:265-267).
 
+  step  : one batch of --scans-per-step (16) consecutive scans of the stream handed to the pipeline; K steps are
+          timed between two barrier + device-sync points (pipeline empty on both sides), so a step is long enough
+          for the fill and drain of the pipeline not to dominate a short run.  The reference arm's step is a bounded
+          sample of that batch (one scan).  Every number is reported in scans/s.
   value : scans/s of ONE scan stream through lb_odometry_* (the library's pipelined form of that chain: scan k+1
           is filtered and indexed while scan k is in its align kernel, `depth` aligns in flight; results identical
           to the per-scan calls, checked here against them), inputs already resident in HBM (device pointers),
@@ -48,8 +52,10 @@ GICP_CFG = dict(max_iterations=50, max_inner=20, corr_dist=1.0, tf_eps=1e-3, k=2
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--scans-per-step", type=int, default=int(os.environ.get("LB_BATCH", "16")),
+                    help="one step = one batch of this many consecutive scans of the stream (b200 arm)")
     ap.add_argument("--depth", type=int, default=int(os.environ.get("LB_DEPTH", "6")),
                     help="registration workers of the odometry pipeline (aligns in flight)")
     ap.add_argument("--pipeline-ppc", type=int, default=int(os.environ.get("LB_PIPE_PPC", "1024")),
@@ -192,14 +198,15 @@ def make_stream(rank, n_scans=N_STREAM, beams=64, az=2048):
 
 
 def aggregate(dist, device, times_ms, steps, world):
-    """max over ranks of the per-rank device times; whole-job throughput = all ranks' scans / that time"""
+    """max over ranks of the per-rank device times; whole-job throughput = all ranks' scans / that time.
+    steps: scans per rank behind each time (one number, or one per entry of times_ms)"""
     import torch
     t = torch.tensor(list(times_ms), dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tmax = [float(x) for x in t]
-    total = steps * world
-    return tmax, [total / (x / 1e3) for x in tmax]
+    counts = list(steps) if isinstance(steps, (list, tuple)) else [steps] * len(tmax)
+    return tmax, [c * world / (x / 1e3) for c, x in zip(counts, tmax)]
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -275,7 +282,10 @@ def main():
                       "L2 flushed between steps by a 256 MiB write)",
                 "optimizer": "bfgs (reference-exact)", "execution": "persistent cooperative kernel",
                 "index": "source and target rebuilt every step",
-                "pipeline": "lb_odometry: 1 VoxelGrid stage + %d registration workers, one scan stream" % args.depth}
+                "pipeline": "lb_odometry: 1 VoxelGrid stage + %d registration workers, one scan stream" % args.depth,
+                "scans_per_step": args.scans_per_step,
+                "step": "one batch of %d consecutive scans of the stream submitted to the pipeline (the reference arm's "
+                        "step is a bounded sample of that batch: one scan)" % args.scans_per_step}
 
     if args.impl == "reference":
         if rank != 0:
@@ -425,7 +435,10 @@ def main():
     sampler = ClockSampler(local_rank)
     gicp.resetKernelTimes(True)
     sampler.start()
-    dev_ms, wall = timed_run(lambda i, rec=False: step_device(i, rec), args.steps, args.warmup, record=True)
+    n_scans = args.steps * args.scans_per_step            # scans in the timed region of the pipelined arms
+    n_warm = max(args.warmup, 3) * args.scans_per_step
+    n_seq = min(n_scans, 100)                             # the sequential (latency) arm needs no more than that
+    dev_ms, wall = timed_run(lambda i, rec=False: step_device(i, rec), n_seq, min(n_warm, 10), record=True)
     clocks = sampler.stop()
     launches_timed = int(state["launches"])
     k_ms, k_n = gicp.kernelTime("align_persistent")
@@ -447,7 +460,7 @@ def main():
     # ---- the odometry pipeline (lb_odometry_*): value (device-resident inputs) and e2e (host buffers)
     seq_ms, seq_wall = dev_ms, wall
     if args.profile:
-        return profile_line(args, workload, dev_ms, state, k_ms, k_n, cov_ms, idx_ms, vg)
+        return profile_line(args, workload, dev_ms, state, k_ms, k_n, cov_ms, idx_ms, vg, n_seq)
     props = torch.cuda.get_device_properties(local_rank)
     l2_bytes = int(getattr(props, "L2_cache_size", 126 * 1024 * 1024))
     period = 2 * (N_STREAM - 1)
@@ -514,7 +527,7 @@ def main():
     sampler.start()
     for g in (odo.gicp(i) for i in range(args.depth)):
         g.resetKernelTimes(2)          # only the event pair around the align kernel (the roofline's live duration)
-    dev_ms, p_out, launches_timed = pipelined_run(submit_device, args.steps, args.warmup)
+    dev_ms, p_out, launches_timed = pipelined_run(submit_device, n_scans, n_warm)
     clocks = sampler.stop()
     stages_device = dict(state["stages"])
     kt = [odo.gicp(i).kernelTime("align_persistent") for i in range(args.depth)]
@@ -532,24 +545,24 @@ def main():
         T = np.array(r.gicp.final_transformation, dtype=np.float32).reshape(4, 4)
         if key in seq_T and not np.array_equal(T, seq_T[key]):
             pipe_same = False
-    e2e_ms, e_out, _ = pipelined_run(submit_host, args.steps, args.warmup)
-    state["h2d"] = nraw * POINT_STEP
-    state["d2h"] = int(np.mean([r.n_filtered for r in e_out])) * POINT_STEP + C.sizeof(api.OdometryResult)
+    e2e_ms, e_out, _ = pipelined_run(submit_host, n_scans, n_warm)
+    state["h2d"] = args.scans_per_step * nraw * POINT_STEP
+    state["d2h"] = args.scans_per_step * (int(np.mean([r.n_filtered for r in e_out])) * POINT_STEP + C.sizeof(api.OdometryResult))
 
     # ---- variant (information only, N = 1): north_star's Gauss-Newton inner solve instead of the reference's BFGS
     variants = {}
     if world == 1 and not os.environ.get("LB_OPT"):
         gicp.setOptimizer(locus_b200.LB_OPT_GAUSS_NEWTON)
-        gn_ms, _ = timed_run(lambda i, rec=False: step_device(i, rec), args.steps, args.warmup, record=True)
+        gn_ms, _ = timed_run(lambda i, rec=False: step_device(i, rec), n_seq, min(n_warm, 10), record=True)
         gicp.setOptimizer(locus_b200.LB_OPT_BFGS)
-        variants["gauss_newton"] = {"value": args.steps / (gn_ms * 1e-3), "unit": "scans/s", "mode": "sequential calls",
+        variants["gauss_newton"] = {"value": n_seq / (gn_ms * 1e-3), "unit": "scans/s", "mode": "sequential calls",
                                     "poses": list(state["poses"]),
                                     "note": "6x6 Gauss-Newton inner solve (BASELINE north_star wording); NOT the headline: "
                                             "its pose differs from the reference's BFGS result by more than the 1e-4 bar"}
 
     # max over ranks (device time), whole-job aggregate
     (dev_ms_max, e2e_ms_max, seq_ms_max), (value, e2e_value, seq_value) = aggregate(dist, "cuda", [dev_ms, e2e_ms, seq_ms],
-                                                                                   args.steps, world)
+                                                                                   [n_scans, n_scans, n_seq], world)
 
     if rank != 0:
         if dist is not None:
@@ -565,8 +578,8 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "traffic": ncu_traffic("align_persistent_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms, "launches_timed": int(k_n), "avg_launch_ms_sequential": k_seq_ms,
-                "kernel_share_of_sequential_step": (k_seq_ms / (seq_ms_max / args.steps)) if seq_ms_max else None,
-                "aligns_in_flight_mean": (k_ms / (dev_ms_max / args.steps)) if dev_ms_max else None,
+                "kernel_share_of_sequential_step": (k_seq_ms / (seq_ms_max / n_seq)) if seq_ms_max else None,
+                "aligns_in_flight_mean": (k_ms / (dev_ms_max / n_scans)) if dev_ms_max else None,
                 "note": "working set (<= 5 MB) is L2-resident: this kernel is bound by the latency of its grid-wide "
                         "all-reduces, not by HBM (SURVEY H3); fraction reported for information.  avg_launch_ms is "
                         "measured inside the pipelined timed region (several aligns + the next scans' kernels share the "
@@ -580,9 +593,11 @@ def main():
             "vs_baseline": None, "dtype": "f32 points / f64 accumulation", "data": "synthetic", "config": workload,
             "clocks": clocks, "gpu_launches": launches_timed,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(state.get("h2d", 0)),
-                    "d2h_bytes_per_step": int(state.get("d2h", 0)), "ms_per_step": e2e_ms_max / args.steps},
+                    "d2h_bytes_per_step": int(state.get("d2h", 0)), "ms_per_step": e2e_ms_max / args.steps,
+                    "ms_per_scan": e2e_ms_max / n_scans},
             "roofline": roofline,
-            "sequential": {"value": seq_value, "unit": "scans/s", "ms_per_scan": seq_ms_max / args.steps,
+            "ms_per_scan": dev_ms_max / n_scans,
+            "sequential": {"value": seq_value, "unit": "scans/s", "ms_per_scan": seq_ms_max / n_seq, "scans_timed": n_seq,
                            "note": "per-scan C-ABI calls, one scan at a time (latency view), L2 flushed between scans"},
             "pipeline_equals_sequential": bool(pipe_same),
             "pipeline_stages": dict(stages_device, note="host wall clock per scan inside the timed region (value arm): the "
@@ -626,9 +641,9 @@ def main():
         dist.destroy_process_group()
 
 
-def profile_line(args, workload, dev_ms, state, k_ms, k_n, cov_ms, idx_ms, vg):
+def profile_line(args, workload, dev_ms, state, k_ms, k_n, cov_ms, idx_ms, vg, n_seq):
     """--profile (run under ncu): only the sequential per-scan calls, so that a launch list shows whole steps"""
-    print(json.dumps({"profile_run": True, "metric": "gicp_scans_per_sec", "value": args.steps / (dev_ms * 1e-3),
+    print(json.dumps({"profile_run": True, "metric": "gicp_scans_per_sec", "value": n_seq / (dev_ms * 1e-3),
                       "unit": "scans/s (sequential calls; NOT a bench value when run under a profiler)",
                       "steps": args.steps, "warmup": args.warmup, "config": workload, "gpu_launches": int(state["launches"]),
                       "align_kernel_ms": k_ms, "align_launches": int(k_n), "knn_cov_kernel_ms": cov_ms,
