@@ -549,8 +549,31 @@ def main():
     state["h2d"] = args.scans_per_step * nraw * POINT_STEP
     state["d2h"] = args.scans_per_step * (int(np.mean([r.n_filtered for r in e_out])) * POINT_STEP + C.sizeof(api.OdometryResult))
 
-    # ---- variant (information only, N = 1): north_star's Gauss-Newton inner solve instead of the reference's BFGS
     variants = {}
+    # ---- variant (information only, N = 1): the pipeline with cloud sharing -- every scan's index + covariances are
+    # computed once and adopted as the next registration's target, instead of being rebuilt like the reference does
+    if world == 1 and not os.environ.get("LB_NO_SHARE_VARIANT"):
+        odo_main = odo
+        try:
+            odo = locus_b200.OdometryB200(local_rank, depth=args.depth, max_points=nraw, max_point_step=POINT_STEP)
+            odo.setCloudSharing(True)
+            odo.voxel.setFilterFieldName("z"); odo.voxel.setFilterLimits(-100.0, 100.0); odo.voxel.setLeafSize(leaf)
+            odo.setGicpParams(**dict({k: getattr(gicp._p, k) for k, _ in api.GicpParams._fields_},
+                                     align_points_per_cta=args.pipeline_ppc))
+            sh_ms, sh_out, _ = pipelined_run(submit_device, n_scans, n_warm)
+            same = all(np.array_equal(np.array(r.gicp.final_transformation, dtype=np.float32).reshape(4, 4),
+                                      seq_T[(seq(tick2i[int(r.ticket)] - 1), seq(tick2i[int(r.ticket)]))])
+                       for r in sh_out if (seq(tick2i[int(r.ticket)] - 1), seq(tick2i[int(r.ticket)])) in seq_T)
+            variants["pipeline_shared_clouds"] = {
+                "value": n_scans / (sh_ms * 1e-3), "unit": "scans/s", "equals_sequential": bool(same),
+                "note": "lb_odometry_set_cloud_sharing(1): each filtered scan's index + covariances computed once (by the "
+                        "registration that has it as source) and adopted as the next registration's target; NOT the "
+                        "headline, which rebuilds both clouds per scan like the reference"}
+            odo.close()
+        except Exception as ex:          # the variant must never take the bench line down
+            variants["pipeline_shared_clouds"] = {"error": str(ex)[:200]}
+        odo = odo_main
+    # ---- variant (information only, N = 1): north_star's Gauss-Newton inner solve instead of the reference's BFGS
     if world == 1 and not os.environ.get("LB_OPT"):
         gicp.setOptimizer(locus_b200.LB_OPT_GAUSS_NEWTON)
         gn_ms, _ = timed_run(lambda i, rec=False: step_device(i, rec), n_seq, min(n_warm, 10), record=True)
@@ -628,7 +651,7 @@ def main():
         if dts:
             line["pose_delta_vs_cpu"] = {"max_dt_m": float(max(dts)), "max_dr_rad": float(max(drs)), "pairs": len(dts)}
         for v in variants.values():
-            d = [F.pose_delta(cpu_poses[key], Tg) for key, Tg in v["poses"] if key in cpu_poses]
+            d = [F.pose_delta(cpu_poses[key], Tg) for key, Tg in v.get("poses", []) if key in cpu_poses]
             if d:
                 v["pose_delta_vs_cpu"] = {"max_dt_m": float(max(x[0] for x in d)), "max_dr_rad": float(max(x[1] for x in d)),
                                           "pairs": len(d)}

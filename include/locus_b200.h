@@ -166,6 +166,23 @@ int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
  * target instead of rebuilding them. */
 int lb_gicp_promote_source_to_target(lb_gicp* h);
 
+/* Prepared clouds shared between handles.  In scan-to-scan odometry every filtered scan is the source of one
+ * registration and the target of the next (PointCloudOdometry.cc:243-244: copyPointCloud(*query_, *reference_)).  The
+ * reference recomputes the target's kd-tree and covariances anyway (setInputTarget clears them, gicp.h:196-200);
+ * these entry points let a caller that runs registrations on several handles (lb_odometry's workers) compute each
+ * scan's index + covariances once: the handle that has the scan as its SOURCE prepares it and shares it, the handle
+ * that needs it as TARGET adopts it.  Same bits as rebuilding it (the index is a pure function of the cloud).
+ *   lb_gicp_prepare_source   enqueue index + covariances of the current source now (align would do it lazily)
+ *   lb_gicp_share_source     a new reference to the prepared source (release it with lb_cloud_release)
+ *   lb_gicp_set_target_cloud adopt a shared cloud as target (no copy; this handle's stream waits for its preparation)
+ * A shared cloud is immutable: a handle that still holds it and gets new data switches to another object.  The
+ * handles must sit on the same device and use the same covariance parameters. */
+typedef struct lb_cloud lb_cloud;
+int lb_gicp_prepare_source(lb_gicp* h);
+int lb_gicp_share_source(lb_gicp* h, lb_cloud** out);
+int lb_gicp_set_target_cloud(lb_gicp* h, lb_cloud* cloud);
+int lb_cloud_release(lb_cloud* cloud);
+
 /* guess: row-major 4x4 float, NULL = identity (the callers pass none). */
 int lb_gicp_align(lb_gicp* h, const float* guess, lb_gicp_result* out);
 
@@ -286,6 +303,11 @@ lb_gicp* lb_odometry_gicp(lb_odometry* h, int i);
 int lb_odometry_depth(lb_odometry* h);
 /* applied to every worker's lb_gicp handle (call while the pipeline is idle) */
 int lb_odometry_set_gicp_params(lb_odometry* h, const lb_gicp_params* p);
+/* on != 0: every filtered scan's index + covariances are computed once, by the worker that registers it as source,
+ * and adopted as target by the worker of the next scan (lb_gicp_share_source / lb_gicp_set_target_cloud) instead
+ * of being rebuilt there.  Same poses, bit for bit.  Off by default: the default pipeline does per scan exactly the
+ * work the reference does (both clouds rebuilt).  Call while the pipeline is idle. */
+int lb_odometry_set_cloud_sharing(lb_odometry* h, int on);
 /* scan: n_pts points of point_step bytes described by fields (as lb_voxel_filter); xyz must be FLOAT32 fields.
  * guess: row-major 4x4 prior handed to align() (NULL = identity).  filtered_out (nullable): host (LB_MEM_HOST) or
  * device buffer of at least n_pts * point_step bytes that receives the filtered cloud.  Blocks while 2*depth+2 scans

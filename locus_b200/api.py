@@ -65,14 +65,15 @@ SYMBOLS = [
     "lb_version", "lb_last_error_string", "lb_status_string", "lb_device_count",
     "lb_gicp_default_params", "lb_gicp_create", "lb_gicp_create_on_stream", "lb_gicp_destroy",
     "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
-    "lb_gicp_promote_source_to_target", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
+    "lb_gicp_promote_source_to_target", "lb_gicp_prepare_source", "lb_gicp_share_source", "lb_gicp_set_target_cloud",
+    "lb_cloud_release", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
     "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_compute_normals", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
     "lb_voxel_set_downsample_all_data", "lb_voxel_set_body_filter", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
-    "lb_odometry_set_gicp_params", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
+    "lb_odometry_set_gicp_params", "lb_odometry_set_cloud_sharing", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
     "lb_odometry_launch_count", "lb_odometry_stage_times",
 ]
 
@@ -118,6 +119,11 @@ def lib():
     L.lb_gicp_set_source.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32]
     L.lb_gicp_set_target.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32, u64p]
     L.lb_gicp_promote_source_to_target.argtypes = [vp]
+    if hasattr(L, "lb_gicp_prepare_source"):
+        L.lb_gicp_prepare_source.argtypes = [vp]
+        L.lb_gicp_share_source.argtypes = [vp, C.POINTER(vp)]
+        L.lb_gicp_set_target_cloud.argtypes = [vp, vp]
+        L.lb_cloud_release.argtypes = [vp]
     L.lb_gicp_align.argtypes = [vp, vp, C.POINTER(GicpResult)]
     L.lb_gicp_transform_source.argtypes = [vp, vp, vp, sz, sz, C.c_ssize_t, i32]
     L.lb_gicp_nn_target.argtypes = [vp, vp, sz, sz, vp, vp, i32]
@@ -151,6 +157,8 @@ def lib():
         L.lb_odometry_gicp.argtypes = [vp, i32]; L.lb_odometry_gicp.restype = vp
         L.lb_odometry_depth.argtypes = [vp]
         L.lb_odometry_set_gicp_params.argtypes = [vp, C.POINTER(GicpParams)]
+        if hasattr(L, "lb_odometry_set_cloud_sharing"):
+            L.lb_odometry_set_cloud_sharing.argtypes = [vp, i32]
         L.lb_odometry_submit.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, i32, vp, vp, i32, u64p]
         L.lb_odometry_next.argtypes = [vp, C.POINTER(OdometryResult), i32]
         L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
@@ -263,6 +271,23 @@ class GicpB200:
 
     def promoteSourceToTarget(self):
         _check(lib().lb_gicp_promote_source_to_target(self._h))
+
+    # ---- prepared clouds shared between handles
+    def prepareSource(self):
+        _check(lib().lb_gicp_prepare_source(self._h))
+
+    def shareSource(self):
+        """opaque reference to the prepared source cloud (pass to another handle's setTargetCloud, then releaseCloud)"""
+        c = C.c_void_p()
+        _check(lib().lb_gicp_share_source(self._h, C.byref(c)))
+        return c
+
+    def setTargetCloud(self, cloud):
+        _check(lib().lb_gicp_set_target_cloud(self._h, cloud))
+
+    @staticmethod
+    def releaseCloud(cloud):
+        lib().lb_cloud_release(cloud)
 
     def align(self, guess=None):
         g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
@@ -486,6 +511,10 @@ class OdometryB200:
         _check(lib().lb_odometry_set_gicp_params(self._h, C.byref(p)))
         for g in self._g:
             lib().lb_gicp_get_params(g._h, C.byref(g._p))
+
+    def setCloudSharing(self, on=True):
+        """each scan's index + covariances computed once and adopted as the next registration's target (idle pipeline only)"""
+        _check(lib().lb_odometry_set_cloud_sharing(self._h, int(bool(on))))
 
     def submit(self, scan, n_pts, point_step, fields, mem=LB_MEM_HOST, guess=None, filtered_out=None,
                mem_filtered=LB_MEM_HOST):

@@ -14,6 +14,7 @@
 
 #include <string>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -47,7 +48,17 @@ struct Cloud {
     v.nx = geom.nx; v.ny = geom.ny; v.nz = geom.nz; v.n = (int)n;
     return v;
   }
+  // set by lb_gicp_prepare_source: index + covariances are enqueued up to this event (another handle that adopts the
+  // cloud as its target waits for it on its own stream)
+  cudaEvent_t ready = nullptr;
+  int device = 0;
+  const void* owner = nullptr;   // the handle that created the object (only the owner recycles it)
   void release() { raw.release(); nrm.release(); pts.release(); cell_start.release(); cov.release(); }
+  ~Cloud() {
+    cudaSetDevice(device);
+    release();
+    if (ready) cudaEventDestroy(ready);
+  }
 };
 
 // per-slot scratch so that the source and target pipelines can run concurrently on two streams
@@ -85,7 +96,11 @@ using namespace lb;
 struct lb_gicp {
   Ctx c;
   lb_gicp_params P;
-  Cloud src, tgt;
+  // Clouds are shared objects: a prepared source (index + covariances) can be adopted by another handle as its
+  // target (lb_gicp_share_source / lb_gicp_set_target_cloud).  A handle never writes into a cloud somebody else
+  // still holds: set_source / set_target switch to a fresh (or recycled) object first.
+  std::shared_ptr<Cloud> src, tgt;
+  std::vector<std::shared_ptr<Cloud>> pool;     // objects this handle gave away earlier, recycled once they are unshared
   uint64_t gen_counter = 0;
   // staging / scratch: slot 0 = source pipeline (handle stream), slot 1 = target pipeline (second stream)
   Scratch sc[2];
@@ -200,8 +215,11 @@ float float_gate(double D) {
 int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   if (!out) { set_error("lb_gicp_create: null handle pointer"); return LB_ERR_INVALID_ARG; }
   lb_gicp* h = new lb_gicp;
+  h->src = std::make_shared<Cloud>(); h->tgt = std::make_shared<Cloud>();
   int s = ctx_init(h->c, device, stream, ext);
   if (s != LB_OK) { delete h; return s; }
+  h->src->device = h->tgt->device = device;
+  h->src->owner = h->tgt->owner = h;
   lb_gicp_default_params(&h->P);
   bool ok = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -279,6 +297,25 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   *out = h;
   return LB_OK;
+}
+
+// Before a handle writes into one of its clouds: if another holder still references the object (it was shared with
+// lb_gicp_share_source), switch to an object nobody else holds -- one of the earlier give-aways that has come back,
+// or a new one.  A reference is only dropped after the holder's own GPU work on the cloud has been synchronised.
+void make_private(lb_gicp* h, std::shared_ptr<Cloud>& c) {
+  if (c.use_count() == 1 && c->owner == h) return;
+  if (c->owner == h) h->pool.push_back(c);      // my own give-away: comes back when the other holders drop it
+  // (an adopted cloud of another handle is simply let go)
+  for (size_t i = 0; i < h->pool.size(); i++) {
+    if (h->pool[i].use_count() == 1) {          // only the pool holds it: free to recycle (buffers are kept)
+      c = h->pool[i];
+      h->pool.erase(h->pool.begin() + (long)i);
+      return;
+    }
+  }
+  c = std::make_shared<Cloud>();
+  c->device = h->c.device;
+  c->owner = h;
 }
 
 // Phase 1 (inside set_source / set_target, synchronous because the caller's buffer is only borrowed for the
@@ -476,19 +513,19 @@ int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
 
 int prepare_clouds(lb_gicp* h, bool need_cov, bool src_knn, bool tgt_knn) {
   Ctx& c = h->c;
-  bool tgt_work = h->tgt.valid && (h->tgt.index_dirty || (need_cov && !h->tgt.cov_valid));
-  bool src_work = h->src.valid && (h->src.index_dirty || (need_cov && !h->src.cov_valid));
+  bool tgt_work = h->tgt->valid && (h->tgt->index_dirty || (need_cov && !h->tgt->cov_valid));
+  bool src_work = h->src->valid && (h->src->index_dirty || (need_cov && !h->src->cov_valid));
   if (!tgt_work && !src_work) return LB_OK;
   ScopedKernelTime kt(h, "knn_cov");
   if (tgt_work) {
     LB_CUDA(cudaEventRecord(h->ev_fork, c.stream));
     LB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    LB_TRY(finish_index(h, h->tgt, 1));
-    if (need_cov && !h->tgt.cov_valid) LB_TRY(compute_covariances(h, h->tgt, 1, tgt_knn));   // target first, gicp.hpp:420-432
+    LB_TRY(finish_index(h, *h->tgt, 1));
+    if (need_cov && !h->tgt->cov_valid) LB_TRY(compute_covariances(h, *h->tgt, 1, tgt_knn));   // target first, gicp.hpp:420-432
   }
   if (src_work) {
-    LB_TRY(finish_index(h, h->src, 0));
-    if (need_cov && !h->src.cov_valid) LB_TRY(compute_covariances(h, h->src, 0, src_knn));
+    LB_TRY(finish_index(h, *h->src, 0));
+    if (need_cov && !h->src->cov_valid) LB_TRY(compute_covariances(h, *h->src, 0, src_knn));
   }
   if (tgt_work) {
     LB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
@@ -620,7 +657,7 @@ int lb_gicp_destroy(lb_gicp* h) {
   if (!h) return LB_OK;
   cudaSetDevice(h->c.device);
   cudaStreamSynchronize(h->c.stream);
-  h->src.release(); h->tgt.release();
+  h->src.reset(); h->tgt.reset(); h->pool.clear();
   cudaStreamSynchronize(h->stream2);
   h->sc[0].release(); h->sc[1].release();
   if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -655,7 +692,14 @@ int lb_gicp_set_params(lb_gicp* h, const lb_gicp_params* p) {
                     p->recompute_source_covariance != h->P.recompute_source_covariance ||
                     p->recompute_target_covariance != h->P.recompute_target_covariance;
   h->P = *p;
-  if (cov_change) { h->src.cov_valid = false; h->tgt.cov_valid = false; }
+  if (cov_change) {
+    // covariances of a cloud shared with other handles are theirs too: let go of it instead of invalidating it
+    for (std::shared_ptr<Cloud>* c : {&h->src, &h->tgt}) {
+      const bool shared = c->use_count() > 1 || (*c)->owner != h;
+      if (shared) { make_private(h, *c); (*c)->valid = false; (*c)->n = 0; }
+      (*c)->cov_valid = false;
+    }
+  }
   return LB_OK;
 }
 int lb_gicp_get_params(lb_gicp* h, lb_gicp_params* p) { if (!h || !p) return LB_ERR_INVALID_ARG; *p = h->P; return LB_OK; }
@@ -667,24 +711,78 @@ int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
     set_error("lb_gicp_set_source: invalid or empty point cloud dataset given");
     return LB_ERR_EMPTY_SOURCE;
   }
-  return upload_cloud(h, h->src, 0, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
+  make_private(h, h->src);
+  return upload_cloud(h, *h->src, 0, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
 }
 
 int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem,
                        uint64_t* generation) {
   if (!h) { set_error("lb_gicp_set_target: null handle"); return LB_ERR_INVALID_ARG; }
   if (n == 0) { set_error("lb_gicp_set_target: empty target cloud"); return LB_ERR_NO_TARGET; }
-  int s = upload_cloud(h, h->tgt, 1, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
-  if (s == LB_OK && generation) *generation = h->tgt.generation;
+  make_private(h, h->tgt);
+  int s = upload_cloud(h, *h->tgt, 1, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
+  if (s == LB_OK && generation) *generation = h->tgt->generation;
   return s;
 }
 
 int lb_gicp_promote_source_to_target(lb_gicp* h) {
   if (!h) return LB_ERR_INVALID_ARG;
-  if (!h->src.valid) { set_error("lb_gicp_promote_source_to_target: no source set"); return LB_ERR_EMPTY_SOURCE; }
+  if (!h->src->valid) { set_error("lb_gicp_promote_source_to_target: no source set"); return LB_ERR_EMPTY_SOURCE; }
   std::swap(h->src, h->tgt);
-  h->src.valid = false; h->src.cov_valid = false; h->src.n = 0;
-  h->tgt.generation = ++h->gen_counter;
+  make_private(h, h->src);            // the old target may be a cloud shared with other handles: never write into it
+  h->src->valid = false; h->src->cov_valid = false; h->src->n = 0;
+  h->tgt->generation = ++h->gen_counter;
+  return LB_OK;
+}
+
+// ---- shared, prepared clouds (each scan's index + covariances computed once, used by two registrations)
+struct lb_cloud { std::shared_ptr<Cloud> c; };
+
+int lb_gicp_prepare_source(lb_gicp* h) {
+  if (!h) { set_error("lb_gicp_prepare_source: null handle"); return LB_ERR_INVALID_ARG; }
+  if (!h->src->valid) { set_error("lb_gicp_prepare_source: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
+  if ((size_t)h->P.k_correspondences > h->src->n) {
+    set_error("lb_gicp_prepare_source: number of points in cloud (%zu) is less than k_correspondences (%d)", h->src->n, h->P.k_correspondences);
+    return LB_ERR_TOO_FEW_POINTS;
+  }
+  Ctx& c = h->c;
+  LB_CUDA(cudaSetDevice(c.device));
+  Cloud& cl = *h->src;
+  const bool knn = h->P.recompute_source_covariance || !cl.has_normals;
+  {
+    ScopedKernelTime kt(h, "knn_cov");
+    LB_TRY(finish_index(h, cl, 0));
+    if (!cl.cov_valid) LB_TRY(compute_covariances(h, cl, 0, knn));
+  }
+  if (!cl.ready) LB_CUDA(cudaEventCreateWithFlags(&cl.ready, cudaEventDisableTiming));
+  LB_CUDA(cudaEventRecord(cl.ready, c.stream));
+  return LB_OK;
+}
+
+int lb_gicp_share_source(lb_gicp* h, lb_cloud** out) {
+  if (!h || !out) { set_error("lb_gicp_share_source: null argument"); return LB_ERR_INVALID_ARG; }
+  Cloud& cl = *h->src;
+  if (!cl.valid || cl.index_dirty || !cl.cov_valid || !cl.ready) {
+    set_error("lb_gicp_share_source: the source is not prepared (call lb_gicp_prepare_source or lb_gicp_align first)");
+    return LB_ERR_INVALID_ARG;
+  }
+  *out = new lb_cloud{h->src};
+  return LB_OK;
+}
+
+int lb_cloud_release(lb_cloud* c) {
+  delete c;          // drops one reference; the buffers go back to the owning handle's pool (or are freed with the last one)
+  return LB_OK;
+}
+
+int lb_gicp_set_target_cloud(lb_gicp* h, lb_cloud* c) {
+  if (!h || !c || !c->c) { set_error("lb_gicp_set_target_cloud: null argument"); return LB_ERR_INVALID_ARG; }
+  if (c->c->device != h->c.device) { set_error("lb_gicp_set_target_cloud: cloud lives on device %d, handle on %d", c->c->device, h->c.device); return LB_ERR_INVALID_ARG; }
+  LB_CUDA(cudaSetDevice(h->c.device));
+  if (h->tgt->owner == h && h->tgt.use_count() > 1 && h->tgt != c->c) h->pool.push_back(h->tgt);   // my give-away stays recyclable
+  h->tgt = c->c;
+  // everything this handle launches from now on (on its main stream) comes after the cloud's preparation
+  LB_CUDA(cudaStreamWaitEvent(h->c.stream, h->tgt->ready, 0));
   return LB_OK;
 }
 
@@ -692,14 +790,14 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   if (!h || !out) { set_error("lb_gicp_align: null argument"); return LB_ERR_INVALID_ARG; }
   memset(out, 0, sizeof(*out));
   for (int i = 0; i < 16; i++) out->final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
-  if (!h->src.valid || h->src.n == 0) { set_error("lb_gicp_align: no source cloud"); out->status = LB_ERR_EMPTY_SOURCE; return LB_ERR_EMPTY_SOURCE; }
-  if (!h->tgt.valid || h->tgt.n == 0) { set_error("lb_gicp_align: no target cloud"); out->status = LB_ERR_NO_TARGET; return LB_ERR_NO_TARGET; }
+  if (!h->src->valid || h->src->n == 0) { set_error("lb_gicp_align: no source cloud"); out->status = LB_ERR_EMPTY_SOURCE; return LB_ERR_EMPTY_SOURCE; }
+  if (!h->tgt->valid || h->tgt->n == 0) { set_error("lb_gicp_align: no target cloud"); out->status = LB_ERR_NO_TARGET; return LB_ERR_NO_TARGET; }
   const int k = h->P.k_correspondences;
-  bool src_knn = h->P.recompute_source_covariance || !h->src.has_normals;
-  bool tgt_knn = h->P.recompute_target_covariance || !h->tgt.has_normals;
+  bool src_knn = h->P.recompute_source_covariance || !h->src->has_normals;
+  bool tgt_knn = h->P.recompute_target_covariance || !h->tgt->has_normals;
   // gicp.hpp:72-79 applies the k > size check in both covariance modes
-  if ((size_t)k > h->src.n || (size_t)k > h->tgt.n) {
-    set_error("lb_gicp_align: number of points in cloud (%zu / %zu) is less than k_correspondences (%d)", h->src.n, h->tgt.n, k);
+  if ((size_t)k > h->src->n || (size_t)k > h->tgt->n) {
+    set_error("lb_gicp_align: number of points in cloud (%zu / %zu) is less than k_correspondences (%d)", h->src->n, h->tgt->n, k);
     out->status = LB_ERR_TOO_FEW_POINTS;
     return LB_ERR_TOO_FEW_POINTS;
   }
@@ -712,14 +810,14 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   LB_TRY(prepare_clouds(h, true, src_knn, tgt_knn));
   LB_CUDA(cudaEventRecord(h->ev[1], c.stream));
 
-  const uint32_t N = (uint32_t)h->src.n;
+  const uint32_t N = (uint32_t)h->src->n;
   LB_TRY(h->src_work.ensure(N)); LB_TRY(h->corr.ensure(N)); LB_TRY(h->M.ensure(6 * (size_t)N));
   Mat34 G; mat16_to_34(guess, G);
-  prep_source_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.pts.p, N, G, h->src_work.p);   // gicp.hpp:440
+  prep_source_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src->pts.p, N, G, h->src_work.p);   // gicp.hpp:440
   c.launches++;
 
   CorrArgs ca;
-  ca.tgt = h->tgt.view(); ca.tgt_cov = h->tgt.cov.p; ca.src = h->src_work.p; ca.src_cov = h->src.cov.p;
+  ca.tgt = h->tgt->view(); ca.tgt_cov = h->tgt->cov.p; ca.src = h->src_work.p; ca.src_cov = h->src->cov.p;
   ca.n_src = (int)N; ca.max_d2 = float_gate(h->P.max_correspondence_distance * h->P.max_correspondence_distance);
   ca.corr = h->corr.p; ca.M = h->M.p;
   OuterParams OP;
@@ -810,16 +908,16 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
 
 int lb_gicp_transform_source(lb_gicp* h, const float* T_in, void* out_pts, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem) {
   if (!h || !out_pts) { set_error("lb_gicp_transform_source: null argument"); return LB_ERR_INVALID_ARG; }
-  if (!h->src.valid) { set_error("lb_gicp_transform_source: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
+  if (!h->src->valid) { set_error("lb_gicp_transform_source: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
   if (!T_in && !h->have_result) { set_error("lb_gicp_transform_source: no align() result yet"); return LB_ERR_NO_ALIGN; }
   if ((stride & 3u) || (xyz_off & 3u) || xyz_off + 12 > stride) { set_error("lb_gicp_transform_source: bad stride/offset"); return LB_ERR_INVALID_ARG; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
-  const uint32_t N = (uint32_t)h->src.n;
+  const uint32_t N = (uint32_t)h->src->n;
   Mat34 T; mat16_to_34(T_in ? T_in : h->final_T, T);
-  bool nrm = normal_off >= 0 && h->src.has_normals;
+  bool nrm = normal_off >= 0 && h->src->has_normals;
   if (mem == LB_MEM_DEVICE) {
-    transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.raw.p, nrm ? h->src.nrm.p : nullptr, N, T, (uint8_t*)out_pts,
+    transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src->raw.p, nrm ? h->src->nrm.p : nullptr, N, T, (uint8_t*)out_pts,
                                                          (uint32_t)stride, (uint32_t)xyz_off, nrm ? (int)normal_off : -1);
     c.launches++;
     LB_CUDA(cudaStreamSynchronize(c.stream));
@@ -828,7 +926,7 @@ int lb_gicp_transform_source(lb_gicp* h, const float* T_in, void* out_pts, size_
   // host output: packed (xyz | normal) rows on the device, one D2H, scatter into the caller's layout
   const uint32_t row = nrm ? 24 : 12;
   LB_TRY(h->io.ensure((size_t)N * row));
-  transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src.raw.p, nrm ? h->src.nrm.p : nullptr, N, T, h->io.p, row, 0, nrm ? 12 : -1);
+  transform_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(h->src->raw.p, nrm ? h->src->nrm.p : nullptr, N, T, h->io.p, row, 0, nrm ? 12 : -1);
   c.launches++;
   h->h_io.resize((size_t)N * row);
   LB_CUDA(cudaMemcpyAsync(h->h_io.data(), h->io.p, (size_t)N * row, cudaMemcpyDeviceToHost, c.stream));
@@ -843,7 +941,7 @@ int lb_gicp_transform_source(lb_gicp* h, const float* T_in, void* out_pts, size_
 
 int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int32_t* idx, float* d2, int mem) {
   if (!h || !xyz || !idx || !d2) { set_error("lb_gicp_nn_target: null argument"); return LB_ERR_INVALID_ARG; }
-  if (!h->tgt.valid) { set_error("lb_gicp_nn_target: no target cloud"); return LB_ERR_NO_TARGET; }
+  if (!h->tgt->valid) { set_error("lb_gicp_nn_target: no target cloud"); return LB_ERR_NO_TARGET; }
   if (n == 0) return LB_OK;
   if ((stride & 3u) || stride < 12) { set_error("lb_gicp_nn_target: bad stride"); return LB_ERR_INVALID_ARG; }
   Ctx& c = h->c;
@@ -861,17 +959,17 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
     static int nnv = -1;   // tuning aid: LB_NN=thread selects the thread-per-query kernel
     if (nnv < 0) { const char* e = getenv("LB_NN"); nnv = (e && !strcmp(e, "thread")) ? 0 : 1; }
     if (nnv == 0) {
-      nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+      nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
     } else {
       int blocks = cdiv(N, 8);
       if (blocks > c.sm_count * 8) blocks = c.sm_count * 8;
-      nn_query_warp_kernel<<<blocks, 256, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
+      nn_query_warp_kernel<<<blocks, 256, 0, c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
     }
     c.launches++;
   }
   if (h->timing) {   // profiling aid: mean number of target points visited per query -> h_debug[4], h_debug[5]
     LB_CUDA(cudaMemsetAsync(h->d_debug + 4, 0, sizeof(long long), c.stream));
-    nn_count_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt.view(), dq, N, (uint32_t)stride, 3.0e38f,
+    nn_count_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, 3.0e38f,
                                                         (unsigned long long*)(h->d_debug + 4));
     LB_CUDA(cudaMemcpyAsync(h->h_debug + 4, h->d_debug + 4, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
     h->h_debug[5] = (long long)N;
@@ -887,17 +985,17 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
 
 int lb_gicp_fitness(lb_gicp* h, const float* T_in, double max_range, double* score) {
   if (!h || !score) { set_error("lb_gicp_fitness: null argument"); return LB_ERR_INVALID_ARG; }
-  if (!h->src.valid) { set_error("lb_gicp_fitness: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
-  if (!h->tgt.valid) { set_error("lb_gicp_fitness: no target cloud"); return LB_ERR_NO_TARGET; }
+  if (!h->src->valid) { set_error("lb_gicp_fitness: no source cloud"); return LB_ERR_EMPTY_SOURCE; }
+  if (!h->tgt->valid) { set_error("lb_gicp_fitness: no target cloud"); return LB_ERR_NO_TARGET; }
   if (!T_in && !h->have_result) { set_error("lb_gicp_fitness: no align() result yet"); return LB_ERR_NO_ALIGN; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
   LB_TRY(prepare_clouds(h, false, false, false));
-  const uint32_t N = (uint32_t)h->src.n;
+  const uint32_t N = (uint32_t)h->src->n;
   int nb = cdiv(N, 128);
   LB_TRY(h->io.ensure((size_t)nb * 2 * sizeof(double)));
   Mat34 T; mat16_to_34(T_in ? T_in : h->final_T, T);
-  fitness_kernel<<<nb, 128, 0, c.stream>>>(h->tgt.view(), h->src.raw.p, N, T, max_range, (double*)h->io.p);
+  fitness_kernel<<<nb, 128, 0, c.stream>>>(h->tgt->view(), h->src->raw.p, N, T, max_range, (double*)h->io.p);
   c.launches++;
   std::vector<double> part((size_t)nb * 2);
   LB_CUDA(cudaMemcpyAsync(part.data(), h->io.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -975,7 +1073,7 @@ int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, siz
 // point_cloud_filter::NormalComputation::filter in k-NN mode (normal_computation.cc:26-59).
 int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint, float* out4, int mem) {
   if (!h || !out4 || (which != 0 && which != 1)) { set_error("lb_gicp_compute_normals: bad argument"); return LB_ERR_INVALID_ARG; }
-  Cloud& cl = which == 0 ? h->src : h->tgt;
+  Cloud& cl = which == 0 ? *h->src : *h->tgt;
   if (!cl.valid) { set_error("lb_gicp_compute_normals: no %s cloud", which == 0 ? "source" : "target"); return which == 0 ? LB_ERR_EMPTY_SOURCE : LB_ERR_NO_TARGET; }
   if (k < 3 || k > 20) { set_error("lb_gicp_compute_normals: k must be in [3, 20] (PCL yields NaN normals below 3)"); return LB_ERR_UNSUPPORTED; }
   if ((size_t)k > cl.n) { set_error("lb_gicp_compute_normals: cloud has %zu points, fewer than k = %d", cl.n, k); return LB_ERR_TOO_FEW_POINTS; }
@@ -1006,7 +1104,7 @@ int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint
 
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points) {
   if (!h || !out9) return LB_ERR_INVALID_ARG;
-  Cloud& cl = which ? h->tgt : h->src;
+  Cloud& cl = which ? *h->tgt : *h->src;
   if (!cl.valid || !cl.cov_valid) { set_error("lb_gicp_get_covariances: covariances not computed (run align first)"); return LB_ERR_NO_ALIGN; }
   if (capacity_points < cl.n) { set_error("lb_gicp_get_covariances: capacity too small"); return LB_ERR_CAPACITY; }
   LB_CUDA(cudaSetDevice(h->c.device));
@@ -1028,7 +1126,7 @@ int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity
 
 int lb_gicp_cloud_size(lb_gicp* h, int which, size_t* n) {
   if (!h || !n) return LB_ERR_INVALID_ARG;
-  Cloud& cl = which ? h->tgt : h->src;
+  Cloud& cl = which ? *h->tgt : *h->src;
   *n = cl.valid ? cl.n : 0;
   return LB_OK;
 }
@@ -1048,8 +1146,8 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
     return LB_OK;
   }
   if (!strcmp(name, "probe_rounds")) { *ms_avg = (float)h->probe_rounds; return LB_OK; }
-  if (!strcmp(name, "cell_src")) { *ms_avg = h->src.geom.h; return LB_OK; }      // cell size of the current index (m)
-  if (!strcmp(name, "cell_tgt")) { *ms_avg = h->tgt.geom.h; return LB_OK; }
+  if (!strcmp(name, "cell_src")) { *ms_avg = h->src->geom.h; return LB_OK; }      // cell size of the current index (m)
+  if (!strcmp(name, "cell_tgt")) { *ms_avg = h->tgt->geom.h; return LB_OK; }
   if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100
     int i = atoi(name + 5);
     if (i < 0 || i >= AL_MAXCTA) return LB_ERR_INVALID_ARG;

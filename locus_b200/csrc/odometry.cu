@@ -55,6 +55,12 @@ struct Slot {            // one filtered cloud of the ring
   char error[160] = "";
 };
 
+struct Prepared {        // cloud-sharing mode: scan t's prepared cloud, published by the worker of registration t
+  uint64_t ticket = ~0ull;
+  lb_cloud* cloud = nullptr;     // null when the preparation failed
+  bool ready = false;
+};
+
 struct Entry {           // per in-flight ticket
   Job job;
   lb_odometry_result res;
@@ -72,6 +78,8 @@ struct lb_odometry {
   lb_voxel* vg = nullptr;
   std::vector<lb_gicp*> gicp;
   std::vector<Slot> ring;
+  std::vector<Prepared> prep;          // same indexing as ring (ticket % R); used when share is on
+  bool share = false;                  // lb_odometry_set_cloud_sharing
   cudaStream_t copy_stream = nullptr;
   cudaStream_t voxel_stream = nullptr;
 
@@ -178,7 +186,36 @@ void align_stage(lb_odometry* h, int w) {
     const Slot& cur = h->ring[t % R];
     r.status = cur.status;
     if (cur.status != LB_OK) memcpy(r.error, cur.error, sizeof(r.error));
-    if (t > 0 && cur.status == LB_OK) {
+    if (h->share) {
+      // this scan's cloud is prepared here, once, and published for the worker of the next registration
+      lb_cloud* mine = nullptr;
+      int st = cur.status;
+      if (st == LB_OK && cur.n > 0) {
+        st = lb_gicp_set_source(g, cur.d, cur.n, cur.point_step, (size_t)cur.xyz_off, LB_NO_NORMALS, LB_MEM_DEVICE);
+        if (st == LB_OK) st = lb_gicp_prepare_source(g);
+        if (st == LB_OK) st = lb_gicp_share_source(g, &mine);
+        if (st != LB_OK) { r.status = st; copy_err(r.error, sizeof(r.error)); }
+      }
+      lb_cloud* prev = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(h->mu);
+        Prepared& p = h->prep[t % R];
+        if (p.cloud) lb_cloud_release(p.cloud);       // slot of ticket t-R: both of its users finished long ago
+        p.ticket = t; p.cloud = mine; p.ready = true;
+        h->cv.notify_all();
+        if (t > 0) {
+          Prepared& q = h->prep[(t - 1) % R];
+          h->cv.wait(lk, [&] { return h->stop || (q.ticket == t - 1 && q.ready); });
+          if (!h->stop) prev = q.cloud;
+        }
+      }
+      if (t > 0 && mine && prev) {
+        st = lb_gicp_set_target_cloud(g, prev);
+        if (st == LB_OK) st = lb_gicp_align(g, e->job.has_guess ? e->job.guess : nullptr, &r.gicp);
+        r.status = st;
+        if (st == LB_OK) r.has_pose = 1; else copy_err(r.error, sizeof(r.error));
+      }
+    } else if (t > 0 && cur.status == LB_OK) {
       const Slot& prv = h->ring[(t - 1) % R];
       if (prv.status == LB_OK && prv.n > 0 && cur.n > 0) {
         int st = lb_gicp_set_source(g, cur.d, cur.n, cur.point_step, (size_t)cur.xyz_off, LB_NO_NORMALS, LB_MEM_DEVICE);
@@ -232,6 +269,7 @@ int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_po
   }
   if (st == LB_OK) {
     h->ring.resize((size_t)depth + 3);
+    h->prep.resize((size_t)depth + 3);
     for (auto& s : h->ring) {
       if (cudaMalloc((void**)&s.d, max_points * (size_t)max_point_step) != cudaSuccess) {
         set_error("lb_odometry_create: ring allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -268,6 +306,7 @@ int lb_odometry_destroy(lb_odometry* h) {
   if (h->vthread.joinable()) h->vthread.join();
   for (auto& t : h->gthreads) if (t.joinable()) t.join();
   cudaSetDevice(h->device);
+  for (auto& p : h->prep) if (p.cloud) { lb_cloud_release(p.cloud); p.cloud = nullptr; }
   for (auto g : h->gicp) lb_gicp_destroy(g);
   lb_voxel_destroy(h->vg);
   for (auto& s : h->ring) if (s.d) cudaFree(s.d);
@@ -289,6 +328,19 @@ int lb_odometry_set_gicp_params(lb_odometry* h, const lb_gicp_params* p) {
     if (h->next_return != h->next_ticket) { set_error("lb_odometry_set_gicp_params: pipeline not idle"); return LB_ERR_INVALID_ARG; }
   }
   for (auto g : h->gicp) LB_TRY(lb_gicp_set_params(g, p));
+  return LB_OK;
+}
+
+int lb_odometry_set_cloud_sharing(lb_odometry* h, int on) {
+  if (!h) { set_error("lb_odometry_set_cloud_sharing: null handle"); return LB_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->next_return != h->next_ticket) { set_error("lb_odometry_set_cloud_sharing: pipeline not idle"); return LB_ERR_INVALID_ARG; }
+  if (h->next_ticket != 0 && (on != 0) != h->share) {
+    // the previous scan's cloud exists in one form only (ring slot or prepared cloud): switch before the first scan
+    set_error("lb_odometry_set_cloud_sharing: switch before the first scan is submitted");
+    return LB_ERR_UNSUPPORTED;
+  }
+  h->share = on != 0;
   return LB_OK;
 }
 

@@ -273,3 +273,40 @@ def test_cpp_host_mirror_runs():
     r = subprocess.run([_build_host_example()], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout
     assert "converged=1" in r.stdout and "pipeline:" in r.stdout
+
+
+def test_shared_prepared_cloud_between_handles(oracle):
+    """lb_gicp_prepare_source / share_source / set_target_cloud: handle B registers against the cloud handle A prepared
+    as ITS source -- same bits as B building the target itself -- and the shared cloud stays intact when A moves on"""
+    import locus_b200
+    x = F.random_scene(6000, 21)
+    T = F.se3([0.05, -0.03, 0.02], [0.004, 0.003, -0.006])
+    y = ((x[:4000].astype(np.float64) - T[:3, 3]) @ T[:3, :3]).astype(np.float32)
+    prm = oracle.default_params(transformation_epsilon=1e-4, corr_dist_threshold=0.5, max_iterations=30)
+    ref = _mk(prm, 0)
+    ref.setInputSource(y); ref.setInputTarget(x)
+    Tref = np.array(ref.align().final_transformation, dtype=np.float32)
+    a, b = _mk(prm, 0), _mk(prm, 0)
+    a.setInputSource(x)
+    a.prepareSource()
+    c = a.shareSource()
+    b.setInputSource(y)
+    b.setTargetCloud(c)
+    assert np.array_equal(np.array(b.align().final_transformation, dtype=np.float32), Tref)
+    # A gets new data (and registers it against something else): the cloud B holds must not change
+    z = F.random_scene(3000, 22)
+    a.setInputSource(z); a.setInputTarget(x[:3000]); a.align()
+    b.setInputSource(y)
+    assert np.array_equal(np.array(b.align().final_transformation, dtype=np.float32), Tref)
+    assert np.array_equal(b.covariances(1), ref.covariances(1))
+    # B switches to a target of its own, the reference goes away, A keeps working
+    b.setInputTarget(z); b.align()
+    locus_b200.GicpB200.releaseCloud(c)
+    a.setInputSource(x); a.prepareSource()
+    c2 = a.shareSource()
+    b.setTargetCloud(c2); b.setInputSource(y)
+    assert np.array_equal(np.array(b.align().final_transformation, dtype=np.float32), Tref)
+    locus_b200.GicpB200.releaseCloud(c2)
+    with pytest.raises(locus_b200.LocusB200Error):
+        fresh = _mk(prm, 0)
+        fresh.shareSource()                      # nothing prepared

@@ -49,11 +49,14 @@ def _fields():
     return api.VoxelGridB200._fields([("x", 0, api.LB_FLOAT32, 1), ("y", 4, api.LB_FLOAT32, 1), ("z", 8, api.LB_FLOAT32, 1)])
 
 
+@pytest.mark.parametrize("share", [False, True])
 @pytest.mark.parametrize("depth", [1, 2, 4, 8])
-def test_pipeline_order_pairing_and_ring_safety(oh, depth):
+def test_pipeline_order_pairing_and_ring_safety(oh, depth, share):
     oh.oh_reset(400)
     h = C.c_void_p()
     assert oh.lb_odometry_create(0, depth, 8, STEP, C.byref(h)) == 0
+    oh.lb_odometry_set_cloud_sharing.argtypes = [C.c_void_p, C.c_int]
+    assert oh.lb_odometry_set_cloud_sharing(h, int(share)) == 0
     p = api.GicpParams(); p.max_iterations = 37
     assert oh.lb_odometry_set_gicp_params(h, C.byref(p)) == 0
     fa = _fields()
@@ -94,9 +97,38 @@ def test_pipeline_order_pairing_and_ring_safety(oh, depth):
             assert T[4] == k                                                               # the caller's prior reached align()
     assert 1 <= oh.oh_aligns_peak() <= depth
     cnt = C.c_uint64(0)
-    assert oh.lb_odometry_launch_count(h, C.byref(cnt)) == 0 and cnt.value == 17 * n_scans + 40 * (n_scans - 1)
+    assert oh.lb_odometry_launch_count(h, C.byref(cnt)) == 0
+    assert cnt.value == 17 * n_scans + 40 * (n_scans - 1) + (12 * n_scans if share else 0)   # one preparation per scan when sharing
+    # cloud sharing cannot be switched once scans have gone through
+    assert oh.lb_odometry_set_cloud_sharing(h, int(not share)) == -9
     assert oh.lb_odometry_next(h, C.byref(r), 1) == -10
     assert oh.lb_odometry_destroy(h) == 0
+    assert oh.oh_clouds_alive() == 0           # every shared-cloud reference was released
+
+
+@pytest.mark.parametrize("share", [False, True])
+def test_pipeline_error_propagation(oh, share):
+    """a scan that fails in the VoxelGrid stage: no pose for it nor for the next one, in both modes"""
+    oh.oh_reset(50)
+    h = C.c_void_p()
+    assert oh.lb_odometry_create(0, 3, 8, STEP, C.byref(h)) == 0
+    oh.lb_odometry_set_cloud_sharing.argtypes = [C.c_void_p, C.c_int]
+    assert oh.lb_odometry_set_cloud_sharing(h, int(share)) == 0
+    fa = _fields()
+    t = C.c_uint64(0)
+    flags = [0, 0, 1, 0, 0, 0]
+    scans = [_scan(10 + i, f) for i, f in enumerate(flags)]
+    for s_ in scans:
+        assert oh.lb_odometry_submit(h, s_.ctypes.data_as(C.c_void_p), 8, STEP, fa, 3, 0, None, None, 0, C.byref(t)) == 0
+    r = api.OdometryResult()
+    poses = []
+    for _ in scans:
+        assert oh.lb_odometry_next(h, C.byref(r), 1) == 0
+        poses.append((r.has_pose, r.status))
+    assert [p[0] for p in poses] == [0, 1, 0, 0, 1, 1]
+    assert poses[2][1] != 0 and poses[3][1] == 0
+    assert oh.lb_odometry_destroy(h) == 0
+    assert oh.oh_clouds_alive() == 0
 
 
 def test_pipeline_error_propagation_and_limits(oh):

@@ -43,14 +43,15 @@ def _sequential(blobs, leaf):
     return out
 
 
-@pytest.mark.parametrize("depth", [1, 3])
-def test_pipeline_equals_sequential_calls(depth):
+@pytest.mark.parametrize("depth,share", [(1, False), (3, False), (1, True), (3, True)])
+def test_pipeline_equals_sequential_calls(depth, share):
     import locus_b200
     blobs = _stream(7)
     leaf = 0.35
     ref = _sequential(blobs, leaf)
     n = blobs[0].size // STEP
     odo = locus_b200.OdometryB200(0, depth=depth, max_points=n, max_point_step=STEP)
+    odo.setCloudSharing(share)            # share: every scan's index + covariances computed once, adopted as the next target
     odo.voxel.setLeafSize(leaf); odo.voxel.setFilterFieldName("z"); odo.voxel.setFilterLimits(-100.0, 100.0)
     odo.setGicpParams(**CFG)
     filt = [np.zeros(n * STEP, dtype=np.uint8) for _ in blobs]
