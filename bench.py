@@ -560,12 +560,14 @@ def main():
             odo.voxel.setFilterFieldName("z"); odo.voxel.setFilterLimits(-100.0, 100.0); odo.voxel.setLeafSize(leaf)
             odo.setGicpParams(**dict({k: getattr(gicp._p, k) for k, _ in api.GicpParams._fields_},
                                      align_points_per_cta=args.pipeline_ppc))
+            free0 = torch.cuda.mem_get_info()[0]
             sh_ms, sh_out, _ = pipelined_run(submit_device, n_scans, n_warm)
+            sh_stages = dict(state["stages"], device_memory_taken_mb=(free0 - torch.cuda.mem_get_info()[0]) / 1e6)
             same = all(np.array_equal(np.array(r.gicp.final_transformation, dtype=np.float32).reshape(4, 4),
                                       seq_T[(seq(tick2i[int(r.ticket)] - 1), seq(tick2i[int(r.ticket)]))])
                        for r in sh_out if (seq(tick2i[int(r.ticket)] - 1), seq(tick2i[int(r.ticket)])) in seq_T)
             variants["pipeline_shared_clouds"] = {
-                "value": n_scans / (sh_ms * 1e-3), "unit": "scans/s", "equals_sequential": bool(same),
+                "value": n_scans / (sh_ms * 1e-3), "unit": "scans/s", "equals_sequential": bool(same), "stages": sh_stages,
                 "note": "lb_odometry_set_cloud_sharing(1): each filtered scan's index + covariances computed once (by the "
                         "registration that has it as source) and adopted as the next registration's target; NOT the "
                         "headline, which rebuilds both clouds per scan like the reference"}
