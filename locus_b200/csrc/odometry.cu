@@ -209,8 +209,16 @@ void align_stage(lb_odometry* h, int w) {
           if (!h->stop) prev = q.cloud;
         }
       }
-      if (t > 0 && mine && prev) {
-        st = lb_gicp_set_target_cloud(g, prev);
+      const bool adopt = t > 0 && mine && prev;
+      if (adopt) st = lb_gicp_set_target_cloud(g, prev);       // the handle now holds its own reference
+      if (t > 0) {
+        // this worker is the only consumer of scan t-1's published reference: give it back now, so that the
+        // owner can recycle the object two jobs later instead of R tickets later (no allocation in steady state)
+        std::lock_guard<std::mutex> lk(h->mu);
+        Prepared& q = h->prep[(t - 1) % R];
+        if (q.ticket == t - 1 && q.cloud) { lb_cloud_release(q.cloud); q.cloud = nullptr; }
+      }
+      if (adopt) {
         if (st == LB_OK) st = lb_gicp_align(g, e->job.has_guess ? e->job.guess : nullptr, &r.gicp);
         r.status = st;
         if (st == LB_OK) r.has_pose = 1; else copy_err(r.error, sizeof(r.error));

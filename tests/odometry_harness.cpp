@@ -7,5 +7,6 @@
 extern "C" {
 int oh_aligns_peak(void) { return stub::aligns_peak().load(); }
 int oh_clouds_alive(void) { return clouds_alive().load(); }
-void oh_reset(int max_sleep_us) { stub::aligns_peak().store(0); stub::max_sleep_us().store(max_sleep_us); }
+int oh_clouds_peak(void) { return clouds_peak().load(); }
+void oh_reset(int max_sleep_us) { clouds_peak().store(0); stub::aligns_peak().store(0); stub::max_sleep_us().store(max_sleep_us); }
 }

@@ -94,7 +94,14 @@ inline int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stri
 struct lb_cloud { uint64_t id; size_t n; };
 inline std::atomic<int>& clouds_alive() { static std::atomic<int> v{0}; return v; }
 inline int lb_gicp_prepare_source(lb_gicp* h) { stub::nap(h->src * 11 + 3); h->launches += 12; return LB_OK; }
-inline int lb_gicp_share_source(lb_gicp* h, lb_cloud** out) { *out = new lb_cloud{h->src, h->n_src}; ++clouds_alive(); return LB_OK; }
+inline std::atomic<int>& clouds_peak() { static std::atomic<int> v{0}; return v; }
+inline int lb_gicp_share_source(lb_gicp* h, lb_cloud** out) {
+  *out = new lb_cloud{h->src, h->n_src};
+  int now = ++clouds_alive();
+  int pk = clouds_peak().load();
+  while (now > pk && !clouds_peak().compare_exchange_weak(pk, now)) {}
+  return LB_OK;
+}
 inline int lb_cloud_release(lb_cloud* c) { delete c; --clouds_alive(); return LB_OK; }
 inline int lb_gicp_set_target_cloud(lb_gicp* h, lb_cloud* c) { h->tgt = c->id; h->n_tgt = c->n; return LB_OK; }
 inline int lb_gicp_align(lb_gicp* h, const float* guess, lb_gicp_result* out) {

@@ -104,6 +104,8 @@ def test_pipeline_order_pairing_and_ring_safety(oh, depth, share):
     assert oh.lb_odometry_next(h, C.byref(r), 1) == -10
     assert oh.lb_odometry_destroy(h) == 0
     assert oh.oh_clouds_alive() == 0           # every shared-cloud reference was released
+    if share:                                  # a published reference lives until the next worker has adopted it:
+        assert 1 <= oh.oh_clouds_peak() <= depth + 1     # never more than the scans being worked on, plus one
 
 
 @pytest.mark.parametrize("share", [False, True])
