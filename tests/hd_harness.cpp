@@ -25,6 +25,16 @@ struct HGrid {
 };
 
 extern "C" {
+// Row f4: the product's BodyFilter predicate (hd.h body_box_drops), set up like lb_voxel_set_body_filter does.
+void hh_body_box(const float* xyz, int n, const float* mn, const float* mx, float rot, unsigned char* dropped) {
+  BodyBox b;
+  b.enabled = 1;
+  float A = cosf(rot), B = sinf(rot), det = A * A + B * B;
+  b.ia = A / det; b.ib = B / det;
+  for (int d = 0; d < 3; d++) { b.mn[d] = mn[d]; b.mx[d] = mx[d]; }
+  for (int i = 0; i < n; i++) dropped[i] = body_box_drops(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]) ? 1 : 0;
+}
+
 // CPU model of knn_cov_quadreg_kernel's candidate handling: the candidates of one query are dealt round-robin to
 // four RegLists (the quad's lanes); every `refresh` candidates the shared gate is tightened to the maximum of the
 // lanes' (K/4)-th best keys (quad_row_done); at the end the four lists are merged.  The merged top-k must equal

@@ -160,3 +160,21 @@ def test_quad_gate_never_drops_a_neighbour(harness, n, refresh):
         want = orig[np.lexsort((orig, d2))][:k]
         assert found == len(want)
         assert np.array_equal(out[:found], want)
+
+
+def test_body_box_predicate_matches_oracle(harness, oracle):
+    """row f4: hd.h body_box_drops == the oracle's BodyFilter predicate: filtering with the body box equals plain
+    filtering of exactly the points the product predicate keeps (points on both sides of every face, both rotations)"""
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(-3, 3, (20000, 3)).astype(np.float32)
+    for rot in (np.float32(-0.785398), np.float32(0.0), np.float32(2.1)):
+        mn = np.array([-0.6, -0.3, -0.3], np.float32) * 3; mx = np.array([0.25, 0.5, 0.0], np.float32) * 3
+        dropped = np.zeros(len(xyz), np.uint8)
+        harness.hh_body_box.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        harness.hh_body_box(_p(xyz), len(xyz), _p(mn), _p(mx), rot, _p(dropped))
+        assert 200 < dropped.sum() < len(xyz) - 200
+        blob = np.zeros((len(xyz), 8), np.float32); blob[:, :3] = xyz
+        a = oracle.voxel_filter(blob.view(np.uint8).reshape(-1), 32, 0.25, body=(mn, mx, rot))
+        keep = np.ascontiguousarray(blob[dropped == 0])
+        b = oracle.voxel_filter(keep.view(np.uint8).reshape(-1), 32, 0.25)
+        assert a["rc"] == 0 and np.array_equal(a["voxel_idx"], b["voxel_idx"]) and np.array_equal(a["out"], b["out"])
