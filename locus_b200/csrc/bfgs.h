@@ -355,63 +355,125 @@ struct OuterResult {
   SolveStats st;
 };
 
-// computeTransformation outer loop (gicp.hpp:445-583).  guess: row-major 4x4 float.
-template <class Backend>
-LB_HD void gicp_outer_loop(Backend& be, const OuterParams& P, const float* guess, OuterResult& out) {
-  float T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};     // transformation_ (reset to I by align())
-  float prev[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // previous_transformation_
-  int nr = 0, converged = 0, m_last = 0;
-  double delta = 0.;
-  out.st.n_evals = 0; out.st.n_inner = 0;
-  while (!converged) {
-    // R = rot(double(transformation_) * double(guess))   gicp.hpp:450-460
-    double R[9];
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) {
-        double acc = 0.0;
-        for (int k = 0; k < 3; k++) acc += (double)T[i * 4 + k] * (double)guess[k * 4 + j];
-        acc += (double)T[i * 4 + 3] * (double)guess[12 + j];
-        R[i * 3 + j] = acc;
-      }
-    int m = be.correspond(T, R);
-    m_last = m;
-    for (int i = 0; i < 12; i++) prev[i] = T[i];
-    if (m < 4) break;  // NotEnoughPointsException -> caught -> break (gicp.hpp:225-233,542-547)
-    double x[6];
-    state_from_transform(T, x);
-    int rc = (P.optimizer == 1) ? solve_gn(be, x, P.max_inner_iterations, out.st)
-                                : solve_bfgs(be, x, P.max_inner_iterations, out.st);
-    if (rc != 0) break;  // SolverDidntConvergeException
-    apply_state(x, T);
-    delta = 0.;
-    for (int k = 0; k < 4; k++)
-      for (int l = 0; l < 4; l++) {
-        double ratio = (k < 3 && l < 3) ? 1. / P.rotation_epsilon : 1. / P.transformation_epsilon;
-        double d = (k < 3) ? (double)(prev[k * 4 + l] - T[k * 4 + l]) : 0.0;
-        double c_delta = ratio * fabs(d);
-        if (c_delta > delta) delta = c_delta;
-      }
-    nr++;
-    if (nr >= P.max_iterations || delta < 1) {
-      converged = 1;
-      for (int i = 0; i < 12; i++) prev[i] = T[i];
+// computeTransformation outer loop (gicp.hpp:445-583), split at the correspondence step so that the same code
+// drives (a) the single-kernel / host loops below and (b) the stream-ordered execution, where the correspondence +
+// moment kernel and the solve kernel of one outer iteration are separate launches (gicp_kernels.cuh).
+struct OuterState {
+  float T[12];      // transformation_ (reset to I by align())
+  float prev[12];   // previous_transformation_
+  int nr, converged, m_last, done;   // done: the while loop has been left (converged, or a caught exception)
+  double delta;
+  SolveStats st;
+};
+
+LB_HD void outer_init(OuterState& s) {
+  const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  for (int i = 0; i < 12; i++) { s.T[i] = I[i]; s.prev[i] = I[i]; }
+  s.nr = 0; s.converged = 0; s.m_last = 0; s.done = 0;
+  s.delta = 0.;
+  s.st.n_evals = 0; s.st.n_inner = 0;
+}
+
+// R = rot(double(transformation_) * double(guess))   gicp.hpp:450-460
+LB_HD void outer_rotation(const OuterState& s, const float* guess, double* R) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; k++) acc += (double)s.T[i * 4 + k] * (double)guess[k * 4 + j];
+      acc += (double)s.T[i * 4 + 3] * (double)guess[12 + j];
+      R[i * 3 + j] = acc;
     }
+}
+
+// everything of one outer iteration after the correspondence step returned m pairs (gicp.hpp:509-569)
+template <class Backend>
+LB_HD void outer_step(OuterState& s, Backend& be, const OuterParams& P, int m) {
+  s.m_last = m;
+  for (int i = 0; i < 12; i++) s.prev[i] = s.T[i];
+  if (m < 4) { s.done = 1; return; }  // NotEnoughPointsException -> caught -> break (gicp.hpp:225-233,542-547)
+  double x[6];
+  state_from_transform(s.T, x);
+  int rc = (P.optimizer == 1) ? solve_gn(be, x, P.max_inner_iterations, s.st)
+                              : solve_bfgs(be, x, P.max_inner_iterations, s.st);
+  if (rc != 0) { s.done = 1; return; }  // SolverDidntConvergeException
+  apply_state(x, s.T);
+  double delta = 0.;
+  for (int k = 0; k < 4; k++)
+    for (int l = 0; l < 4; l++) {
+      double ratio = (k < 3 && l < 3) ? 1. / P.rotation_epsilon : 1. / P.transformation_epsilon;
+      double d = (k < 3) ? (double)(s.prev[k * 4 + l] - s.T[k * 4 + l]) : 0.0;
+      double c_delta = ratio * fabs(d);
+      if (c_delta > delta) delta = c_delta;
+    }
+  s.delta = delta;
+  s.nr++;
+  if (s.nr >= P.max_iterations || delta < 1) {
+    s.converged = 1; s.done = 1;
+    for (int i = 0; i < 12; i++) s.prev[i] = s.T[i];
   }
-  // final = previous * guess (float 4x4 product, Eigen coefficient order)
+}
+
+// final = previous * guess (float 4x4 product, Eigen coefficient order)   gicp.hpp:583
+LB_HD void outer_finish(const OuterState& s, const float* guess, OuterResult& out) {
   for (int i = 0; i < 4; i++)
     for (int j = 0; j < 4; j++) {
-      float a0 = (i < 3) ? prev[i * 4 + 0] : 0.f, a1 = (i < 3) ? prev[i * 4 + 1] : 0.f;
-      float a2 = (i < 3) ? prev[i * 4 + 2] : 0.f, a3 = (i < 3) ? prev[i * 4 + 3] : 1.f;
+      float a0 = (i < 3) ? s.prev[i * 4 + 0] : 0.f, a1 = (i < 3) ? s.prev[i * 4 + 1] : 0.f;
+      float a2 = (i < 3) ? s.prev[i * 4 + 2] : 0.f, a3 = (i < 3) ? s.prev[i * 4 + 3] : 1.f;
       float v = a0 * guess[0 * 4 + j];
       v = v + a1 * guess[1 * 4 + j];
       v = v + a2 * guess[2 * 4 + j];
       v = v + a3 * guess[3 * 4 + j];
       out.final_T[i * 4 + j] = v;
     }
-  out.nr_iterations = nr;
-  out.converged = converged;
-  out.n_corr = m_last;
-  out.delta = delta;
+  out.nr_iterations = s.nr;
+  out.converged = s.converged;
+  out.n_corr = s.m_last;
+  out.delta = s.delta;
+  out.st = s.st;
 }
+
+// guess: row-major 4x4 float.
+template <class Backend>
+LB_HD void gicp_outer_loop(Backend& be, const OuterParams& P, const float* guess, OuterResult& out) {
+  OuterState s;
+  outer_init(s);
+  while (!s.done) {
+    double R[9];
+    outer_rotation(s, guess, R);
+    int m = be.correspond(s.T, R);
+    outer_step(s, be, P, m);
+  }
+  outer_finish(s, guess, out);
+}
+
+// The inner solve's objective in moment form (hd.h "moment form of the objective"): the Backend methods fdf / gn of
+// one outer iteration evaluated from the 74 reduced moments, no pass over the points.
+struct MomentObjective {
+  double mom[MOM_N];
+  float A0[12];      // the transform the moments were taken about (= the one the correspondences were searched with)
+  int m;
+  LB_HD void fdf(const double* x, double* f, double* g) const {
+    Trig t;
+    trig_compute(x, t);
+    float A[12];
+    apply_state_trig(x, t, A);
+    double s13[13];
+    moment_sums13(mom, A0, A, s13);
+    objective_finish_trig(s13, m, t, f, g);
+  }
+  LB_HD int gn(const double* x, double* f, double* b, double* H) const {
+    Trig t;
+    trig_compute(x, t);
+    float A[12];
+    apply_state_trig(x, t, A);
+    double dP[9], dT[9], dS[9], s28[28];
+    r_derivatives_trig(t, dP, dT, dS);
+    moment_gn28(mom, A0, A, dP, dT, dS, s28);
+    *f = s28[0] / (double)m;
+    for (int e = 0; e < 6; e++) b[e] = s28[1 + e];
+    for (int e = 0; e < 21; e++) H[e] = s28[7 + e];
+    return 0;
+  }
+};
 
 }  // namespace lb

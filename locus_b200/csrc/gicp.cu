@@ -318,6 +318,22 @@ void make_private(lb_gicp* h, std::shared_ptr<Cloud>& c) {
   c->owner = h;
 }
 
+// A cloud object nobody else holds, for the next upload: one of this handle's earlier objects that has come back
+// (its buffers are kept), or a new one.
+std::shared_ptr<Cloud> spare_cloud(lb_gicp* h) {
+  for (size_t i = 0; i < h->pool.size(); i++) {
+    if (h->pool[i].use_count() == 1) {
+      std::shared_ptr<Cloud> c = h->pool[i];
+      h->pool.erase(h->pool.begin() + (long)i);
+      return c;
+    }
+  }
+  std::shared_ptr<Cloud> c = std::make_shared<Cloud>();
+  c->device = h->c.device;
+  c->owner = h;
+  return c;
+}
+
 // Phase 1 (inside set_source / set_target, synchronous because the caller's buffer is only borrowed for the
 // duration of the call): upload, gather into packed float4 + bounding box in one kernel, choose the grid.
 int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, size_t stride, size_t xyz_off,
@@ -422,6 +438,26 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
   cl.cov_valid = false;
   cl.index_dirty = true;
   cl.generation = ++h->gen_counter;
+  return LB_OK;
+}
+
+// set_source / set_target: the new cloud is uploaded into a SPARE object and only swapped in when the upload
+// succeeded -- on any error (non-finite points, bad stride, out of memory) the handle keeps its previous cloud, which is
+// the header's contract and what the reference does (gicp.h:164-171: "invalid or empty dataset" -> return, input kept).
+int replace_cloud(lb_gicp* h, std::shared_ptr<Cloud>& dst, int slot, const void* pts, size_t n, size_t stride, size_t xyz_off,
+                  ptrdiff_t normal_off, int mem, const char* what) {
+  std::shared_ptr<Cloud> fresh = spare_cloud(h);
+  int s = upload_cloud(h, *fresh, slot, pts, n, stride, xyz_off, normal_off, mem, what);
+  if (dst->keys_slot == slot) dst->keys_slot = -1;     // the slot's scratch (cell keys of the occupancy probe) was reused
+  if (s != LB_OK) {
+    fresh->valid = false;
+    h->pool.push_back(fresh);                           // keeps its buffers for the next upload
+    return s;
+  }
+  // the previous object may still be referenced by other handles (shared prepared cloud), or be an adopted cloud of
+  // another handle: only this handle's own objects are recycled, and only once nobody else holds them
+  if (dst->owner == h) h->pool.push_back(dst);
+  dst = fresh;
   return LB_OK;
 }
 
@@ -711,16 +747,14 @@ int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
     set_error("lb_gicp_set_source: invalid or empty point cloud dataset given");
     return LB_ERR_EMPTY_SOURCE;
   }
-  make_private(h, h->src);
-  return upload_cloud(h, *h->src, 0, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
+  return replace_cloud(h, h->src, 0, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_source");
 }
 
 int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off, ptrdiff_t normal_off, int mem,
                        uint64_t* generation) {
   if (!h) { set_error("lb_gicp_set_target: null handle"); return LB_ERR_INVALID_ARG; }
   if (n == 0) { set_error("lb_gicp_set_target: empty target cloud"); return LB_ERR_NO_TARGET; }
-  make_private(h, h->tgt);
-  int s = upload_cloud(h, *h->tgt, 1, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
+  int s = replace_cloud(h, h->tgt, 1, pts, n, stride, xyz_off, normal_off, mem, "lb_gicp_set_target");
   if (s == LB_OK && generation) *generation = h->tgt->generation;
   return s;
 }
@@ -832,13 +866,26 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
   } else {
     // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
-    if ((h->epoch_base >> 32) != ((h->epoch_base + (1ull << 20)) >> 32) || (h->epoch_base & 0xffffffffull) == 0) {
+    // One launch consumes a range of collective epochs (the slot tags): at most one per correspondence step plus one
+    // per objective evaluation.  The range reserved per launch covers the caller's iteration caps (pcl::BFGS: <= 100
+    // bracketing + 100 sectioning steps of <= 2 evaluations per inner iteration), so a launch can never run into the
+    // tags of the next one.
+    const unsigned long long need = (unsigned long long)h->P.max_iterations * (2ull + (unsigned long long)h->P.max_optimizer_iterations * 402ull) + 16ull;
+    if (need >= (1ull << 31)) {
+      set_error("lb_gicp_align: max_iterations x max_optimizer_iterations too large for the persistent kernel's epoch range; use LB_EXEC_HOST_DRIVEN");
+      out->status = LB_ERR_UNSUPPORTED;
+      return LB_ERR_UNSUPPORTED;
+    }
+    unsigned long long stride = 1ull << 20;
+    while (stride < need) stride <<= 1;
+    // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
+    if ((h->epoch_base >> 32) != ((h->epoch_base + stride) >> 32) || (h->epoch_base & 0xffffffffull) == 0) {
       LB_CUDA(cudaMemsetAsync(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord), c.stream));
       if (h->cslots.p) LB_CUDA(cudaMemsetAsync(h->cslots.p, 0, (CL_MAX_CTAS + CL_CMD_WORDS) * sizeof(SlotWord), c.stream));
       h->epoch_base = ((h->epoch_base >> 32) + 1) << 32 | (1ull << 20);
     }
     const unsigned long long epoch_base = h->epoch_base;
-    h->epoch_base += 1ull << 20;      // > collectives per align
+    h->epoch_base += stride;
     bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT_CLUSTER && N <= (uint32_t)(CL_SIZE * CL_CAP);
     bool launched = false;
     SmLease lease;     // released when this block ends, i.e. after the stream sync below
@@ -1033,30 +1080,20 @@ int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, siz
   int nb = cdiv(N, 256);
   if (nb > c.sm_count * 4) nb = c.sm_count * 4;
   DBuf<double>& scratch = h->M;   // not in use outside align()
-  LB_TRY(scratch.ensure((size_t)nb * 21));
+  LB_TRY(scratch.ensure((size_t)nb * 21 + 4));
   std::vector<double> part((size_t)nb * 21);
+  float* d_norm = reinterpret_cast<float*>(scratch.p + (size_t)nb * 21);
   ApArgs a;
   a.q = dq; a.n = N; a.q_stride = (uint32_t)q_stride; a.q_xyz_off = (uint32_t)q_xyz_off;
   a.ref = dr; a.n_ref = (uint32_t)n_ref; a.r_stride = (uint32_t)r_stride; a.r_normal_off = (uint32_t)r_normal_off;
-  a.corr = dc; a.factor = 1.f; a.tx = a.ty = a.tz = 0.f; a.use_R = T ? 1 : 0;
+  a.corr = dc; a.norm = nullptr; a.use_R = T ? 1 : 0;
   for (int i = 0; i < 9; i++) a.R[i] = T ? (double)T[(i / 3) * 4 + (i % 3)] : ((i % 4 == 0) ? 1.0 : 0.0);
   if (normalize) {
-    // normalizePCloud: centroid, mean distance to it, a = factor * (p - centroid) with factor = n / sum |p - c|
-    ap_sum_kernel<<<nb, 256, 0, c.stream>>>(dq, N, (uint32_t)q_stride, (uint32_t)q_xyz_off, 0.f, 0.f, 0.f, 0, scratch.p);
+    // normalizePCloud's centroid and mean distance, float32 sums in point order like the reference; they stay on the
+    // device (the accumulation kernel derives factor and offset from them): no host round trip
+    ap_normalize_seq_kernel<<<1, 256, 0, c.stream>>>(dq, N, (uint32_t)q_stride, (uint32_t)q_xyz_off, d_norm);
     c.launches++;
-    LB_CUDA(cudaMemcpyAsync(part.data(), scratch.p, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    LB_CUDA(cudaStreamSynchronize(c.stream));
-    double sx = 0, sy = 0, sz = 0;
-    for (int b = 0; b < nb; b++) { sx += part[3 * (size_t)b]; sy += part[3 * (size_t)b + 1]; sz += part[3 * (size_t)b + 2]; }
-    float cx = (float)(sx / (double)n), cy = (float)(sy / (double)n), cz = (float)(sz / (double)n);
-    ap_sum_kernel<<<nb, 256, 0, c.stream>>>(dq, N, (uint32_t)q_stride, (uint32_t)q_xyz_off, cx, cy, cz, 1, scratch.p);
-    c.launches++;
-    LB_CUDA(cudaMemcpyAsync(part.data(), scratch.p, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    LB_CUDA(cudaStreamSynchronize(c.stream));
-    double dist = 0;
-    for (int b = 0; b < nb; b++) dist += part[3 * (size_t)b];
-    float factor = (float)n / (float)dist;
-    a.factor = factor; a.tx = -factor * cx; a.ty = -factor * cy; a.tz = -factor * cz;
+    a.norm = d_norm;
   }
   ap_accumulate_kernel<<<nb, 256, 0, c.stream>>>(a, scratch.p);
   c.launches++;

@@ -459,6 +459,140 @@ LB_HD void objective_finish(const double* sums /*13*/, int m, const double* x, d
   objective_finish_trig(sums, m, t, f, g);
 }
 
+// ---------------------------------------------------------------- moment form of the objective
+// For FIXED correspondences (one inner solve, gicp.hpp:518-524) the residual r_k = A p~_k - q_k, p~ = (p, 1), is
+// linear in the 12 entries of A = [R | t], so f = sum_k r_k' M_k r_k is an exact quadratic form in A.  Expanded
+// about A0 (the transform the correspondences were taken with): r_k = r0_k + D p~_k, D = A - A0, r0_k = A0 p~_k - q_k:
+//     f(A)           = c0 + sum_ia D[i][a] (2 B[a][i] + W[i][a])
+//     sum_k M_k r_k p~_k'   = B' + W                                       (3x4; what the 13 sums of gicp.hpp:373-397 hold)
+//     W[i][a]        = sum_jb S[ab][ij] D[j][b]
+// with the MOM_N = 74 moments, reduced over the correspondences ONCE per outer iteration:
+//     S[ab][ij] = sum_k (p~ p~')_ab (M_k)_ij    10 x 6   (Q = sum p~p~' (x) M has only 60 distinct entries)
+//     B[a][i]   = sum_k p~_a (M_k r0_k)_i       4 x 3
+//     c0        = sum_k r0_k' M_k r0_k,   count = number of correspondences.
+// Every objective / gradient evaluation of the BFGS line search (gicp.hpp:290-402) is then O(1) scalar work: no pass
+// over the points and no grid-wide reduction.  Expanding about A0 keeps every term at its natural size (c0 is the
+// objective at A0 itself, D ~ 1e-2): no cancellation between |p|^2-sized terms.  The only arithmetic difference to
+// the reference: A p~ is evaluated in double here, in float32 there (gicp.hpp:307,341,382: ~1e-6 m per point).
+constexpr int MOM_S = 0, MOM_B = 60, MOM_C = 72, MOM_CNT = 73, MOM_N = 74;
+// index of the pair (a <= b) of p~ components: xx xy xz x1 yy yz y1 zz z1 11
+LB_HD int mom_pair(int a, int b) {
+  const int base[4] = {0, 4, 7, 9};
+  return a <= b ? base[a] + (b - a) : base[b] + (a - b);
+}
+LB_HD int sym6(int i, int j) {
+  const int base[3] = {0, 3, 5};
+  return i <= j ? base[i] + (j - i) : base[j] + (i - j);
+}
+
+// contribution of one correspondence.  A0: row-major 3x4 float; p: source point; q: matched target point.
+LB_HD void moment_terms(const float* A0, float px, float py, float pz, float qx, float qy, float qz, const double* M,
+                        double* acc /*MOM_N*/) {
+  const double p[4] = {(double)px, (double)py, (double)pz, 1.0};
+  double r0[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    r0[i] = (((double)A0[4 * i] * p[0] + (double)A0[4 * i + 1] * p[1]) + (double)A0[4 * i + 2] * p[2]) + (double)A0[4 * i + 3];
+  r0[0] -= (double)qx; r0[1] -= (double)qy; r0[2] -= (double)qz;
+  const double t0 = (M[SXX] * r0[0] + M[SXY] * r0[1]) + M[SXZ] * r0[2];
+  const double t1 = (M[SXY] * r0[0] + M[SYY] * r0[1]) + M[SYZ] * r0[2];
+  const double t2 = (M[SXZ] * r0[0] + M[SYZ] * r0[1]) + M[SZZ] * r0[2];
+  acc[MOM_C] += (r0[0] * t0 + r0[1] * t1) + r0[2] * t2;
+  acc[MOM_CNT] += 1.0;
+  int e = 0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    acc[MOM_B + 3 * a + 0] += p[a] * t0;
+    acc[MOM_B + 3 * a + 1] += p[a] * t1;
+    acc[MOM_B + 3 * a + 2] += p[a] * t2;
+#pragma unroll
+    for (int b = a; b < 4; b++) {
+      const double pab = p[a] * p[b];
+#pragma unroll
+      for (int ij = 0; ij < 6; ij++) acc[MOM_S + 6 * e + ij] += pab * M[ij];
+      e++;
+    }
+  }
+}
+
+// W = Q D for a 3x4 matrix D (row-major), from the S moments.
+LB_HD void moment_apply(const double* mom, const double* D /*12*/, double* W /*12*/) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double w = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) w += mom[MOM_S + 6 * mom_pair(a, b) + sym6(i, j)] * D[4 * j + b];
+      W[4 * i + a] = w;
+    }
+}
+
+// The 13 sums of objective_terms (f, sum M r, sum p (M r)') at transform A, from the moments taken at A0.
+LB_HD void moment_sums13(const double* mom, const float* A0, const float* A, double* sums /*13*/) {
+  double D[12], W[12];
+#pragma unroll
+  for (int e = 0; e < 12; e++) D[e] = (double)A[e] - (double)A0[e];
+  moment_apply(mom, D, W);
+  double f = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double bia = mom[MOM_B + 3 * a + i];
+      f += D[4 * i + a] * (2.0 * bia + W[4 * i + a]);
+      const double g = bia + W[4 * i + a];          // (sum_k M_k r_k p~_k')[i][a]
+      if (a == 3) sums[1 + i] = g;
+      else sums[4 + 3 * a + i] = g;
+    }
+  sums[0] = mom[MOM_C] + f;
+}
+
+// Gauss-Newton normal equations at state x from the moments: J_k = [dA/dx_c p~_k]_c, H = sum J'MJ, b = sum J'Mr.
+// out: f (sum, not divided), b[6], H[21] upper-triangular row-major -- the layout of gn_terms' 28 sums.
+LB_HD void moment_gn28(const double* mom, const float* A0, const float* A, const double* dP, const double* dT,
+                       const double* dS, double* sums /*28*/) {
+  double s13[13];
+  moment_sums13(mom, A0, A, s13);
+  double G[12];                                          // sum_k M_k r_k p~_k' (3x4)
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    G[4 * i + 3] = s13[1 + i];
+#pragma unroll
+    for (int a = 0; a < 3; a++) G[4 * i + a] = s13[4 + 3 * a + i];
+  }
+  double Dc[6][12], QD[6][12];
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+#pragma unroll
+    for (int e = 0; e < 12; e++) Dc[c][e] = 0.0;
+  Dc[0][3] = 1.0; Dc[1][7] = 1.0; Dc[2][11] = 1.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) { Dc[3][4 * i + a] = dP[3 * i + a]; Dc[4][4 * i + a] = dT[3 * i + a]; Dc[5][4 * i + a] = dS[3 * i + a]; }
+#pragma unroll
+  for (int c = 0; c < 6; c++) moment_apply(mom, Dc[c], QD[c]);
+  sums[0] = s13[0];
+  int e = 7;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double bc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) bc += Dc[c][k] * G[k];
+    sums[1 + c] = bc;
+#pragma unroll
+    for (int d = c; d < 6; d++) {
+      double h = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; k++) h += Dc[c][k] * QD[d][k];
+      sums[e++] = h;
+    }
+  }
+}
+
 // Gauss-Newton terms (not in the reference): J = [I | dP p, dT p, dS p],
 // H += J'MJ (21 upper-tri), b += J'Mr (6), f += r'Mr.  acc: 28 doubles [f, b0..5, H00,H01,..H55 upper].
 LB_HD void gn_terms(const float* T, const double* dP, const double* dT, const double* dS,

@@ -458,10 +458,63 @@ static int gn_solve(functor_ctx* c, double x[6], int max_inner, long* n_inner) {
 /* ------------------------------------------------------------ align */
 static double now_s(void) { return omp_get_wtime(); }
 
+/* A target whose kd-tree and covariances are kept between aligns.  The reference keeps both for as long as the
+ * caller does not call setInputTarget again (pcl::Registration rebuilds the tree only when the target changed, and
+ * gicp.hpp:422-426 computes target covariances only "if unset"): that is the scan-to-submap case in which the
+ * submap is unchanged between scans (BASELINE configs[2]). */
+struct og_gicp_target {
+  const float* pts; int n, stride_f;
+  og_kdtree* tree;
+  double* cov;       /* n x 9 */
+};
+
+static int align_impl(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
+                      const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
+                      const og_gicp_params* P, const float* guess_in, og_gicp_result* res,
+                      double* src_cov_out, double* tgt_cov_out, float* aligned_out, const og_gicp_target* prepared);
+
+og_gicp_target* og_gicp_target_prepare(const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
+                                       const og_gicp_params* P) {
+  if (n_tgt <= 0 || P->k_correspondences > n_tgt) return NULL;
+  og_gicp_target* t = (og_gicp_target*)calloc(1, sizeof(*t));
+  t->pts = tgt; t->n = n_tgt; t->stride_f = tgt_stride_f;
+  t->tree = og_kdtree_build(tgt, n_tgt, tgt_stride_f);
+  t->cov = (double*)malloc(sizeof(double) * 9 * (size_t)n_tgt);
+  if (P->target_cov_from_normals && tgt_normal_off_f >= 0)
+    cov_from_normals(tgt, n_tgt, tgt_stride_f, tgt_normal_off_f, P->gicp_epsilon, t->cov);
+  else
+    cov_knn(tgt, n_tgt, tgt_stride_f, t->tree, P->k_correspondences, P->gicp_epsilon,
+            P->num_threads > 0 ? P->num_threads : 1, t->cov);
+  return t;
+}
+
+void og_gicp_target_free(og_gicp_target* t) {
+  if (!t) return;
+  og_kdtree_free(t->tree);
+  free(t->cov);
+  free(t);
+}
+
+int og_gicp_align_prepared(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
+                           const og_gicp_target* target, const og_gicp_params* P, const float* guess,
+                           og_gicp_result* res) {
+  if (!target) { memset(res, 0, sizeof(*res)); res->status = -2; return -2; }
+  return align_impl(src, n_src, src_stride_f, src_normal_off_f, target->pts, target->n, target->stride_f, -1, P, guess,
+                    res, NULL, NULL, NULL, target);
+}
+
 int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
                   const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
                   const og_gicp_params* P, const float* guess_in, og_gicp_result* res,
                   double* src_cov_out, double* tgt_cov_out, float* aligned_out) {
+  return align_impl(src, n_src, src_stride_f, src_normal_off_f, tgt, n_tgt, tgt_stride_f, tgt_normal_off_f, P, guess_in,
+                    res, src_cov_out, tgt_cov_out, aligned_out, NULL);
+}
+
+static int align_impl(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
+                      const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
+                      const og_gicp_params* P, const float* guess_in, og_gicp_result* res,
+                      double* src_cov_out, double* tgt_cov_out, float* aligned_out, const og_gicp_target* prepared) {
   memset(res, 0, sizeof(*res));
   mat4f_identity(res->final_transformation);
   if (n_src <= 0) { res->status = -1; return -1; } /* gicp.h:164-171: empty source -> error, no-op */
@@ -473,13 +526,13 @@ int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_
   if (guess_in) memcpy(guess, guess_in, sizeof(guess)); else mat4f_identity(guess);
 
   /* align(): rebuild target tree; initComputeReciprocal(): source tree (gicp.hpp:412) */
-  og_kdtree* tree = og_kdtree_build(tgt, n_tgt, tgt_stride_f);
+  og_kdtree* tree = prepared ? prepared->tree : og_kdtree_build(tgt, n_tgt, tgt_stride_f);
   og_kdtree* tree_src = og_kdtree_build(src, n_src, src_stride_f);
 
   const size_t N = (size_t)n_src;
   double* mahal = (double*)malloc(sizeof(double) * 9 * N);       /* gicp.hpp:418 */
   double* Csrc = (double*)malloc(sizeof(double) * 9 * N);
-  double* Ctgt = (double*)malloc(sizeof(double) * 9 * (size_t)n_tgt);
+  double* Ctgt = prepared ? prepared->cov : (double*)malloc(sizeof(double) * 9 * (size_t)n_tgt);
   float* output = (float*)malloc(sizeof(float) * 4 * N);         /* copy of input, w=1 */
   int* source_indices = (int*)malloc(sizeof(int) * N);
   int* target_indices = (int*)malloc(sizeof(int) * N);
@@ -498,7 +551,9 @@ int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_
 
   /* covariances: target then source (gicp.hpp:420-432) */
   double t_cov0 = now_s();
-  if (P->target_cov_from_normals && tgt_normal_off_f >= 0) {
+  if (prepared) {
+    /* target covariances already set: gicp.hpp:422 skips them */
+  } else if (P->target_cov_from_normals && tgt_normal_off_f >= 0) {
     if (P->k_correspondences > n_tgt) rc = -3;
     else cov_from_normals(tgt, n_tgt, tgt_stride_f, tgt_normal_off_f, P->gicp_epsilon, Ctgt);
   } else {
@@ -656,8 +711,9 @@ int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_
   res->status = 0;
 
 done:
-  og_kdtree_free(tree); og_kdtree_free(tree_src);
-  free(mahal); free(Csrc); free(Ctgt); free(output); free(source_indices); free(target_indices);
+  if (!prepared) { og_kdtree_free(tree); free(Ctgt); }
+  og_kdtree_free(tree_src);
+  free(mahal); free(Csrc); free(output); free(source_indices); free(target_indices);
   free(csrc4); free(ctgt4); free(cM);
   return res->status;
 }

@@ -100,6 +100,18 @@ int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_
                   og_gicp_result* result,
                   double* src_cov_out, double* tgt_cov_out, float* aligned_out);
 
+/* Scan-to-submap with an UNCHANGED target (BASELINE configs[2]): the reference keeps the target's kd-tree and
+ * covariances until setInputTarget is called again (gicp.h:196-200 clears them only there; gicp.hpp:422-426 computes
+ * them "if unset").  prepare = setInputTarget + the target half of the first align; align_prepared = setInputSource +
+ * align against it.  The target array must outlive the handle. */
+typedef struct og_gicp_target og_gicp_target;
+og_gicp_target* og_gicp_target_prepare(const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
+                                       const og_gicp_params* params);
+void og_gicp_target_free(og_gicp_target* t);
+int og_gicp_align_prepared(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
+                           const og_gicp_target* target, const og_gicp_params* params, const float* guess,
+                           og_gicp_result* result);
+
 /* k-NN covariances only (gicp.hpp:85-154). cov_out: n x 9 doubles. */
 int og_gicp_covariances(const float* pts, int n, int stride_f, int k,
                         double gicp_epsilon, int num_threads, double* cov_out);

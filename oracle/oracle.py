@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "_build", "liblocus_oracle.so")
 
 
 def build(force=False):
-    srcs = ["kdtree.c", "bfgs_oracle.c", "gicp_oracle.c", "voxel_oracle.c", "lb_oracle.h"]
+    srcs = ["kdtree.c", "bfgs_oracle.c", "gicp_oracle.c", "voxel_oracle.c", "normals_oracle.c", "lb_oracle.h"]
     if not force and os.path.exists(_SO):
         mt = os.path.getmtime(_SO)
         if all(os.path.getmtime(os.path.join(_HERE, s)) <= mt for s in srcs):
@@ -67,6 +67,12 @@ def lib():
         L.og_gicp_align.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
             C.POINTER(GicpParams), C.c_void_p, C.POINTER(GicpResult), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_gicp_target_prepare.restype = C.c_void_p
+        L.og_gicp_target_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(GicpParams)]
+        L.og_gicp_target_free.argtypes = [C.c_void_p]
+        L.og_gicp_align_prepared.restype = C.c_int
+        L.og_gicp_align_prepared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(GicpParams),
+                                             C.c_void_p, C.POINTER(GicpResult)]
         L.og_gicp_covariances.restype = C.c_int
         L.og_gicp_covariances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.og_gicp_fitness.restype = C.c_double
@@ -140,6 +146,46 @@ def gicp_align(src, tgt, params=None, guess=None, src_normal_off=-1, tgt_normal_
     if want_aligned:
         out["aligned"] = al
     return out
+
+
+def _result_dict(rc, res):
+    return {
+        "status": rc,
+        "T": np.array(res.final_transformation, dtype=np.float32).reshape(4, 4),
+        "iterations": res.nr_iterations, "converged": bool(res.converged),
+        "n_corr": res.n_correspondences, "delta": res.delta,
+        "n_evals": res.n_fdf_evals, "n_inner": res.n_inner_iterations,
+        "t_cov": res.t_covariances_s, "t_iter": res.t_iterations_s, "t_total": res.t_total_s,
+        "t_lookups": res.t_lookups_s, "t_opt": res.t_optimization_s,
+    }
+
+
+class PreparedTarget:
+    """setInputTarget once, align many sources against it (the reference keeps the target's kd-tree and covariances
+    until the next setInputTarget): the unchanged-submap case of BASELINE configs[2]."""
+
+    def __init__(self, tgt, params, tgt_normal_off=-1):
+        self.tgt = _as_cloud(tgt)
+        self.h = lib().og_gicp_target_prepare(_p(self.tgt), self.tgt.shape[0], self.tgt.shape[1], tgt_normal_off,
+                                              C.byref(params))
+        if not self.h:
+            raise ValueError("og_gicp_target_prepare: empty target or fewer points than k_correspondences")
+
+    def align(self, src, params, guess=None, src_normal_off=-1):
+        src = _as_cloud(src)
+        res = GicpResult()
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        rc = lib().og_gicp_align_prepared(_p(src), src.shape[0], src.shape[1], src_normal_off, self.h, C.byref(params),
+                                          _p(g), C.byref(res))
+        return _result_dict(rc, res)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().og_gicp_target_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 def covariances(pts, k=20, eps=1e-3, num_threads=1):

@@ -165,13 +165,15 @@ int og_voxel_filter(const uint8_t* data, size_t n, uint32_t point_step,
 }
 
 /* ------------------------------------------------------------------ row f1 */
-/* utils.cc:106-128 normalizePCloud: centroid via pcl::compute3DCentroid (double
- * accumulation, cast to float), dist accumulated in float, factor = n/dist,
+/* utils.cc:106-128 normalizePCloud: centroid via pcl::compute3DCentroid (float32
+ * accumulation in point order), dist accumulated in float, factor = n/dist,
  * transform = [factor*I | -factor*centroid] applied by pcl::transformPointCloud. */
 void og_normalize_pcloud(const float* xyz, int n, float* out) {
-  double acc[3] = {0, 0, 0};
-  for (int i = 0; i < n; i++) { acc[0] += xyz[3 * i]; acc[1] += xyz[3 * i + 1]; acc[2] += xyz[3 * i + 2]; }
-  float c[3] = {(float)(acc[0] / n), (float)(acc[1] / n), (float)(acc[2] / n)};
+  /* pcl::compute3DCentroid(cloud, Eigen::Vector4f&) (utils.cc:108): Scalar = float, dense cloud: the three sums are
+   * accumulated in float32 in point order, then divided by the count */
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < n; i++) { acc[0] = acc[0] + xyz[3 * i]; acc[1] = acc[1] + xyz[3 * i + 1]; acc[2] = acc[2] + xyz[3 * i + 2]; }
+  float c[3] = {acc[0] / (float)n, acc[1] / (float)n, acc[2] / (float)n};
   float dist = 0;
   for (int i = 0; i < n; i++) {
     float dx = xyz[3 * i] - c[0], dy = xyz[3 * i + 1] - c[1], dz = xyz[3 * i + 2] - c[2];

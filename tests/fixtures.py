@@ -78,3 +78,25 @@ def random_scene(n, seed, extent=(20.0, 15.0, 3.0)):
     u = rng.uniform(-1, 1, (rest, 2)); pts.append(np.c_[u[:, 0] * ex, np.full(rest, ey), u[:, 1] * ez])
     p = np.concatenate(pts) + rng.normal(0, 0.01, (n, 3))
     return p.astype(np.float32)
+
+
+def c5_case():
+    """BASELINE config 5 shape for the parity tests: 200 k-point scan vs 10 M-point map (dense stress).
+    returns (src, tgt, T_true, cfg); the oracle's pose for exactly these inputs is tests/golden/c5_oracle_pose.npz"""
+    tgt = random_scene(10_000_000, 5, extent=(100.0, 75.0, 15.0))
+    rng = np.random.default_rng(11)
+    sub = tgt[rng.choice(len(tgt), 200_000, replace=False)] + rng.normal(0, 0.005, (200_000, 3)).astype(np.float32)
+    Tg = se3([0.05, 0.03, -0.01], [0.002, 0.003, -0.004])
+    src = ((sub.astype(np.float64) - Tg[:3, 3]) @ Tg[:3, :3]).astype(np.float32)
+    return src, tgt, Tg, dict(tf_eps=1e-5, corr_dist=0.3, max_iterations=50, max_inner=50)
+
+
+def cloud_checksum(*clouds):
+    """order-sensitive 64-bit checksum of the raw float32 bits (golden fixtures verify their regenerated inputs)"""
+    h = np.uint64(1469598103934665603)
+    for c in clouds:
+        b = np.ascontiguousarray(c, dtype=np.float32).view(np.uint32).astype(np.uint64).ravel()
+        w = np.arange(1, b.size + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            h = h * np.uint64(1099511628211) + (b * w).sum(dtype=np.uint64)
+    return int(h)

@@ -239,11 +239,66 @@ struct CpuBackend {
   }
 };
 
+// Moment-form backend (LB_EXEC_MOMENTS): correspond() also reduces the 74 moments (serially, in source order);
+// fdf / gn evaluate them -- the scalar code the solve kernel's leader warp runs.
+struct CpuMomentBackend : CpuBackend {
+  MomentObjective mo;
+  int correspond(const float* T, const double* R) {
+    int mm = CpuBackend::correspond(T, R);
+    for (int e = 0; e < MOM_N; e++) mo.mom[e] = 0.0;
+    for (int e = 0; e < 12; e++) mo.A0[e] = T[e];
+    for (int i = 0; i < n_src; i++) {
+      if (float_to_bits(corr[i].w) < 0) continue;
+      moment_terms(T, src[i].x, src[i].y, src[i].z, corr[i].x, corr[i].y, corr[i].z, &M[6 * (size_t)i], mo.mom);
+    }
+    mo.m = mm;
+    return mm;
+  }
+  void fdf(const double* x, double* f, double* g) { mo.fdf(x, f, g); }
+  int gn(const double* x, double* f, double* b, double* H) { return mo.gn(x, f, b, H); }
+};
+
+static int hh_align_impl(const float* src_xyz, int n_src, const float* tgt_xyz, int n_tgt, float h_src, float h_tgt,
+             int k, double eps, double rot_eps, double tf_eps, double corr_dist, int max_it, int max_inner,
+             int optimizer, const float* guess, float* T_out, int* info, double* delta_out, bool moments);
+
 // src/tgt: n x 3 float.  returns final T (16), iterations etc.  Covariances by k-NN.
 int hh_align(const float* src_xyz, int n_src, const float* tgt_xyz, int n_tgt, float h_src, float h_tgt,
              int k, double eps, double rot_eps, double tf_eps, double corr_dist, int max_it, int max_inner,
+             int optimizer, const float* guess, float* T_out, int* info, double* delta_out) {
+  return hh_align_impl(src_xyz, n_src, tgt_xyz, n_tgt, h_src, h_tgt, k, eps, rot_eps, tf_eps, corr_dist, max_it, max_inner,
+                       optimizer, guess, T_out, info, delta_out, false);
+}
+int hh_align_moments(const float* src_xyz, int n_src, const float* tgt_xyz, int n_tgt, float h_src, float h_tgt,
+             int k, double eps, double rot_eps, double tf_eps, double corr_dist, int max_it, int max_inner,
+             int optimizer, const float* guess, float* T_out, int* info, double* delta_out) {
+  return hh_align_impl(src_xyz, n_src, tgt_xyz, n_tgt, h_src, h_tgt, k, eps, rot_eps, tf_eps, corr_dist, max_it, max_inner,
+                       optimizer, guess, T_out, info, delta_out, true);
+}
+
+// objective + gradient at state x: exact pass over the pairs vs the moment form (moments taken about A0 = T(x0))
+void hh_moment_fdf(const float* src4, const float* tgt4, const double* M6, int m, const double* x0, const double* x,
+                   double* f_exact, double* g_exact, double* f_mom, double* g_mom) {
+  float T[12], A0[12];
+  apply_state(x, T);
+  double acc[13] = {0};
+  for (int i = 0; i < m; i++)
+    objective_terms(T, src4[4 * i], src4[4 * i + 1], src4[4 * i + 2], tgt4[4 * i], tgt4[4 * i + 1], tgt4[4 * i + 2], &M6[6 * (size_t)i], acc);
+  objective_finish(acc, m, x, f_exact, g_exact);
+  MomentObjective mo;
+  apply_state(x0, A0);
+  for (int e = 0; e < MOM_N; e++) mo.mom[e] = 0.0;
+  for (int e = 0; e < 12; e++) mo.A0[e] = A0[e];
+  for (int i = 0; i < m; i++)
+    moment_terms(A0, src4[4 * i], src4[4 * i + 1], src4[4 * i + 2], tgt4[4 * i], tgt4[4 * i + 1], tgt4[4 * i + 2], &M6[6 * (size_t)i], mo.mom);
+  mo.m = m;
+  mo.fdf(x, f_mom, g_mom);
+}
+
+static int hh_align_impl(const float* src_xyz, int n_src, const float* tgt_xyz, int n_tgt, float h_src, float h_tgt,
+             int k, double eps, double rot_eps, double tf_eps, double corr_dist, int max_it, int max_inner,
              int optimizer, const float* guess, float* T_out, int* info /*iters, converged, n_corr, evals, inner*/,
-             double* delta_out) {
+             double* delta_out, bool moments) {
   HGrid* gs = (HGrid*)hh_grid_build(src_xyz, n_src, 3, h_src);
   HGrid* gt = (HGrid*)hh_grid_build(tgt_xyz, n_tgt, 3, h_tgt);
   std::vector<double> cs((size_t)n_src * 6), ct_orig((size_t)n_tgt * 6), ct((size_t)n_tgt * 6);
@@ -261,12 +316,13 @@ int hh_align(const float* src_xyz, int n_src, const float* tgt_xyz, int n_tgt, f
     xform_pcl(G, src_xyz[3 * i], src_xyz[3 * i + 1], src_xyz[3 * i + 2], x, y, z);
     src[i] = f4{x, y, z, 1.0f};
   }
-  CpuBackend be;
+  CpuMomentBackend be;
   be.tg = &gt->v; be.tgt_cov = ct.data(); be.src = src.data(); be.src_cov = cs.data(); be.n_src = n_src;
   be.max_d2 = (float)(corr_dist * corr_dist);
   OuterParams P{rot_eps, tf_eps, max_it, max_inner, optimizer};
   OuterResult R;
-  gicp_outer_loop(be, P, G, R);
+  if (moments) gicp_outer_loop(be, P, G, R);
+  else gicp_outer_loop(static_cast<CpuBackend&>(be), P, G, R);
   memcpy(T_out, R.final_T, sizeof(float) * 16);
   info[0] = R.nr_iterations; info[1] = R.converged; info[2] = R.n_corr; info[3] = R.st.n_evals; info[4] = R.st.n_inner;
   *delta_out = R.delta;

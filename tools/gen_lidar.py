@@ -137,23 +137,40 @@ def blob_xyz(blob, point_step=POINT_STEP):
     return a[:, :12].copy().view(np.float32).reshape(-1, 3)
 
 
+WORKERS = 1      # processes used to ray-cast the scans of a stream (bench.py raises it; the scans do not depend on it)
+
+
+def _scan_job(a):
+    scene, pose, seed, beams, az = a
+    return scan(scene, pose, seed, beams, az)
+
+
+def _world_job(a):
+    scene, T, seed, beams, az = a
+    p = blob_xyz(scan(scene, T, seed, beams, az))
+    p = p[np.isfinite(p).all(axis=1)]
+    return (p.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+
+
+def _map_jobs(fn, jobs):
+    if WORKERS > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(WORKERS, len(jobs))) as pool:      # fork: call before CUDA is initialised
+            return pool.map(fn, jobs)
+    return [fn(j) for j in jobs]
+
+
 def stream(seed, n_scans, beams=64, az=2048):
     """(scene, poses, [blob...]) for a stream of n_scans."""
     scene = make_scene(seed)
     poses = trajectory(seed, n_scans)
-    blobs = [scan(scene, poses[i], seed * 7919 + i, beams, az) for i in range(n_scans)]
+    blobs = _map_jobs(_scan_job, [(scene, poses[i], seed * 7919 + i, beams, az) for i in range(n_scans)])
     return scene, poses, blobs
 
 
 def world_points(scene, poses, seed, beams=64, az=2048):
     """Union of posed scans in the world frame (finite points only), float32 (n,3)."""
-    out = []
-    for i, T in enumerate(poses):
-        b = scan(scene, T, seed * 104729 + i, beams, az)
-        p = blob_xyz(b)
-        p = p[np.isfinite(p).all(axis=1)]
-        out.append((p.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
-    return np.concatenate(out)
+    return np.concatenate(_map_jobs(_world_job, [(scene, T, seed * 104729 + i, beams, az) for i, T in enumerate(poses)]))
 
 
 if __name__ == "__main__":
@@ -169,3 +186,71 @@ if __name__ == "__main__":
     fin = np.isfinite(p).all(axis=1)
     print("scans", len(blobs), "pts/scan", p.shape[0], "finite", int(fin.sum()),
           "bbox", p[fin].min(0), p[fin].max(0), "gen s/scan", (time.time() - t0) / a.scans)
+
+
+# ------------------------------------------------------------------------------------------ C3 / C4 / C5 workloads
+def perturbed_prior(T, seed, t=0.05, r_deg=0.4):
+    """the odometry estimate handed to scan-to-submap registration as its guess: the true pose off by a few
+    centimetres / tenths of a degree (PointCloudLocalization.cc:181-200 pre-transforms the query with it)"""
+    rng = np.random.default_rng(seed)
+    d = pose_matrix(rng.uniform(-t, t, 3), np.deg2rad(rng.uniform(-r_deg, r_deg, 3)))
+    return (T @ d).astype(np.float32)
+
+
+def submap_cloud(scene, seed, n_scans=40, beams=64, az=2048):
+    """raw material of a rolling submap: the union of n_scans posed scans of `scene` in the world
+    frame, float32 (n, 3).  The map poses wander further than the ego-motion of the registered stream so that the
+    submap covers the room from several viewpoints."""
+    poses = trajectory(seed + 50, n_scans, t_step=1.5, r_step_deg=20.0)
+    return world_points(scene, poses, seed + 50, beams, az)
+
+
+def xyz_blob(xyz):
+    """(n, 3) float32 -> the 32-byte point layout of this module (intensity 0)"""
+    b = np.zeros((len(xyz), POINT_STEP // 4), dtype=np.float32)
+    b[:, :3] = xyz
+    b[:, 3] = 1.0
+    return b.view(np.uint8).reshape(-1)
+
+
+def voxel_merge_to(xyz, n_target, voxel_fn, lo=0.005, hi=0.5, rounds=16, seed=0):
+    """voxel-merge a point union down to exactly n_target points: leaf by bisection (voxel_fn(blob, leaf) -> (m, 32)
+    uint8 filtered blob; the GPU filter in bench.py, the oracle's in the tests) so that slightly more than n_target
+    voxels remain, then a seeded random subset of exactly n_target, kept in voxel order.  returns (xyz (n_target, 3), leaf)"""
+    blob = xyz_blob(xyz)
+    best = None
+    for _ in range(rounds):
+        mid = 0.5 * (lo + hi)
+        out = voxel_fn(blob, mid)
+        if out.shape[0] >= n_target:
+            lo, best = mid, (out, mid)
+        else:
+            hi = mid
+    if best is None:
+        raise ValueError("voxel_merge_to: the union holds fewer than %d voxels at leaf %g" % (n_target, lo))
+    out, leaf = best
+    pts = np.ascontiguousarray(out).view(np.float32).reshape(-1, POINT_STEP // 4)[:, :3]
+    keep = np.sort(np.random.default_rng(seed).choice(len(pts), n_target, replace=False))
+    return np.ascontiguousarray(pts[keep]), float(np.float32(leaf))
+
+
+def subsample_to(xyz, n_target, seed=0):
+    """seeded random subset of exactly n_target points, input order kept (the C5 map: the room cannot hold 10 M distinct
+    PCL voxels without overflowing VoxelGrid's int32 leaf index, so the dense map is a subsample, not a voxel merge)"""
+    if len(xyz) < n_target:
+        raise ValueError("subsample_to: the union holds %d points, fewer than %d" % (len(xyz), n_target))
+    keep = np.sort(np.random.default_rng(seed).choice(len(xyz), n_target, replace=False))
+    return np.ascontiguousarray(xyz[keep])
+
+
+def c3_workload(seed, n_scans, voxel_fn, n_map_scans=40, n_submap=500_000, beams=64, az=2048, merge="voxel"):
+    """BASELINE configs[2]: a stream of n_scans raw scans of one scene, the rolling submap of the same
+    scene (voxel-merged union of n_map_scans posed scans, exactly n_submap points, world frame) and the prior each scan
+    is registered with.  voxel_fn(blob, leaf) -> filtered (m, 32) uint8 blob (the GPU filter or the oracle's: they
+    agree bit for bit, so both give the same submap)."""
+    scene, poses, blobs = stream(seed, n_scans, beams, az)
+    world = submap_cloud(scene, seed, n_map_scans, beams, az)
+    sub, leaf = (subsample_to(world, n_submap), 0.0) if merge == "subsample" else voxel_merge_to(world, n_submap, voxel_fn)
+    guesses = [perturbed_prior(poses[i], 100 + i) for i in range(n_scans)]
+    return {"scene": scene, "poses": poses, "blobs": blobs, "submap": sub, "submap_leaf": leaf, "guesses": guesses,
+            "union_points": int(len(world))}
