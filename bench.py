@@ -83,6 +83,7 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--leaf", type=float, default=0.0, help="fixed VoxelGrid leaf (skips the bisection; profiling aid)")
+    ap.add_argument("--stream-scans", type=int, default=0, help="distinct scans of the stream (0 = the config's; profiling aid)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid for ncu: the blocking per-scan calls only (no pipeline, no e2e arm, no CPU baseline)")
     return ap.parse_args()
@@ -424,7 +425,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.stream_scans > 0:
+        cfg["n_stream"] = max(3, args.stream_scans)
     workload = describe(args, world, cfg)
 
     if args.impl == "reference":

@@ -142,6 +142,9 @@ typedef struct lb_gicp_result {
   float t_iterations_ms;
   float t_total_ms;
   int status;
+  /* previous_transformation_ / transformation_ of pcl::Registration after align(): the guess-free increment the loop
+   * converged to (final_transformation = transformation * guess, gicp.hpp:583); getLastIncrementalTransformation() */
+  float transformation[16];
 } lb_gicp_result;
 
 int lb_gicp_default_params(lb_gicp_params* p);

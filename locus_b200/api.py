@@ -47,7 +47,7 @@ class GicpResult(C.Structure):
         ("final_transformation", C.c_float * 16), ("converged", C.c_int), ("iterations", C.c_int),
         ("n_correspondences", C.c_int), ("delta", C.c_double), ("n_objective_evals", C.c_int),
         ("n_inner_iterations", C.c_int), ("t_covariances_ms", C.c_float), ("t_iterations_ms", C.c_float),
-        ("t_total_ms", C.c_float), ("status", C.c_int),
+        ("t_total_ms", C.c_float), ("status", C.c_int), ("transformation", C.c_float * 16),
     ]
 
 
@@ -301,6 +301,12 @@ class GicpB200:
         if self._res is None:
             return np.eye(4, dtype=np.float32)
         return np.array(self._res.final_transformation, dtype=np.float32).reshape(4, 4)
+
+    def getLastIncrementalTransformation(self):
+        """pcl::Registration::getLastIncrementalTransformation(): transformation_, the guess-free increment"""
+        if self._res is None:
+            return np.eye(4, dtype=np.float32)
+        return np.array(self._res.transformation, dtype=np.float32).reshape(4, 4)
 
     def hasConverged(self):
         return bool(self._res.converged) if self._res is not None else False

@@ -350,6 +350,7 @@ struct OuterParams {
 
 struct OuterResult {
   float final_T[16];   // row-major 4x4 = previous * guess (gicp.hpp:583)
+  float prev_T[16];    // previous_transformation_ (= transformation_ once converged): the guess-free increment
   int nr_iterations, converged, n_corr;
   double delta;
   SolveStats st;
@@ -425,6 +426,8 @@ LB_HD void outer_finish(const OuterState& s, const float* guess, OuterResult& ou
       v = v + a3 * guess[3 * 4 + j];
       out.final_T[i * 4 + j] = v;
     }
+  for (int i = 0; i < 12; i++) out.prev_T[i] = s.prev[i];
+  out.prev_T[12] = 0.f; out.prev_T[13] = 0.f; out.prev_T[14] = 0.f; out.prev_T[15] = 1.f;
   out.nr_iterations = s.nr;
   out.converged = s.converged;
   out.n_corr = s.m_last;

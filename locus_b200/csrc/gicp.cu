@@ -823,7 +823,7 @@ int lb_gicp_set_target_cloud(lb_gicp* h, lb_cloud* c) {
 int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   if (!h || !out) { set_error("lb_gicp_align: null argument"); return LB_ERR_INVALID_ARG; }
   memset(out, 0, sizeof(*out));
-  for (int i = 0; i < 16; i++) out->final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
+  for (int i = 0; i < 16; i++) out->final_transformation[i] = out->transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
   if (!h->src->valid || h->src->n == 0) { set_error("lb_gicp_align: no source cloud"); out->status = LB_ERR_EMPTY_SOURCE; return LB_ERR_EMPTY_SOURCE; }
   if (!h->tgt->valid || h->tgt->n == 0) { set_error("lb_gicp_align: no target cloud"); out->status = LB_ERR_NO_TARGET; return LB_ERR_NO_TARGET; }
   const int k = h->P.k_correspondences;
@@ -938,7 +938,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   LB_CUDA(cudaEventRecord(h->ev[2], c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
   timers_collect(h);
-  for (int i = 0; i < 16; i++) { out->final_transformation[i] = R.final_T[i]; h->final_T[i] = R.final_T[i]; }
+  for (int i = 0; i < 16; i++) { out->final_transformation[i] = R.final_T[i]; h->final_T[i] = R.final_T[i]; out->transformation[i] = R.prev_T[i]; }
   h->have_result = true;
   out->converged = R.converged;
   out->iterations = R.nr_iterations;

@@ -103,35 +103,6 @@ bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint3
 // ------------------------------------------------------------------ scan
 constexpr int SC_T = 256, SC_I = 8, SC_TILE = SC_T * SC_I;
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) >= o) v += t;
-  }
-  return v;
-}
-
-// exclusive scan of one value per thread across the block; returns exclusive prefix, total in *total
-template <int T>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* smem /*T/32+1*/) {
-  uint32_t incl = warp_incl_scan(v);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 31) smem[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    uint32_t s = (l < T / 32) ? smem[l] : 0;
-    uint32_t si = warp_incl_scan(s);
-    if (l < T / 32) smem[l] = si - s;
-    if (l == T / 32 - 1) smem[T / 32] = si;
-  }
-  __syncthreads();
-  uint32_t r = smem[w] + incl - v;
-  *total = smem[T / 32];
-  __syncthreads();
-  return r;
-}
-
 __global__ void __launch_bounds__(SC_T) scan_reduce_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* sums) {
   __shared__ uint32_t sm[SC_T / 32 + 1];
   size_t base = (size_t)blockIdx.x * SC_TILE + (size_t)threadIdx.x * SC_I;
@@ -216,8 +187,10 @@ int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, s
 constexpr int RS_WARPS = 8, RS_ITEMS = 8, RS_TILE = RS_WARPS * 32 * RS_ITEMS;
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
-rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist, uint32_t nblocks) {
+rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist, uint32_t nblocks,
+               const int* __restrict__ key_bits_dev) {
   __shared__ uint32_t h[256];
+  if (key_bits_dev && shift >= *key_bits_dev) return;     // pass not needed for this key width (known on the device only)
   h[threadIdx.x] = 0;
   __syncthreads();
   uint32_t base = blockIdx.x * RS_TILE;
@@ -233,8 +206,9 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                  const uint32_t* __restrict__ offsets, uint32_t nblocks) {
+                  const uint32_t* __restrict__ offsets, uint32_t nblocks, const int* __restrict__ key_bits_dev) {
   __shared__ uint32_t whist[RS_WARPS][256];
+  if (key_bits_dev && shift >= *key_bits_dev) return;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_WARPS * 32) (&whist[0][0])[i] = 0;
   __syncthreads();
@@ -292,8 +266,10 @@ static_assert(RS_WARPS * 32 == 256, "digit scan assumes 256 threads per block");
 constexpr uint32_t RS_FUSED_MAX_BLOCKS = 128;
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
-rs_hist_bm_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist) {
+rs_hist_bm_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ block_hist,
+                  const int* __restrict__ key_bits_dev) {
   __shared__ uint32_t h[256];
+  if (key_bits_dev && shift >= *key_bits_dev) return;
   h[threadIdx.x] = 0;
   __syncthreads();
   uint32_t base = blockIdx.x * RS_TILE;
@@ -309,9 +285,11 @@ rs_hist_bm_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rs_scatter_fused_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                         uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                        const uint32_t* __restrict__ block_hist /*[nblocks][256]*/, uint32_t nblocks) {
+                        const uint32_t* __restrict__ block_hist /*[nblocks][256]*/, uint32_t nblocks,
+                        const int* __restrict__ key_bits_dev) {
   __shared__ uint32_t whist[RS_WARPS][256];
   __shared__ uint32_t scan_sm[RS_WARPS + 1];
+  if (key_bits_dev && shift >= *key_bits_dev) return;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_WARPS * 32) (&whist[0][0])[i] = 0;
   // global offset of (digit d = threadIdx.x, this tile): digits below d in all tiles + digit d in the tiles before
@@ -379,8 +357,12 @@ rs_scatter_fused_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __
   }
 }
 
-int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
-                     uint32_t** keys_out, uint32_t** vals_out) {
+// key_bits_dev != nullptr: the key width is only known on the device (lb_voxel_filter: it follows from the bounding box
+// of the call's own input).  `key_bits` is then the host's upper bound: that many bits' worth of passes are LAUNCHED,
+// and the kernels of a pass whose digit lies beyond *key_bits_dev return at once -- the executed passes are a prefix, so
+// the result sits in buffer A (w.ka / w.va) after an odd number of executed passes and in B after an even number (> 0).
+static int radix_sort_impl(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
+                           const int* key_bits_dev, uint32_t** keys_out, uint32_t** vals_out) {
   if (n > 0xfffffff0ull) { set_error("radix_sort_pairs: n too large"); return LB_ERR_INVALID_ARG; }
   LB_TRY(w.ka.ensure(n ? n : 1)); LB_TRY(w.kb.ensure(n ? n : 1));
   LB_TRY(w.va.ensure(n ? n : 1)); LB_TRY(w.vb.ensure(n ? n : 1));
@@ -395,23 +377,32 @@ int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
     if (fused) {
-      rs_hist_bm_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p);
-      rs_scatter_fused_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
+      rs_hist_bm_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, key_bits_dev);
+      rs_scatter_fused_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks, key_bits_dev);
       c.launches += 2;
     } else {
-      rs_hist_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, nblocks);
+      rs_hist_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, (uint32_t)n, shift, w.hist.p, nblocks, key_bits_dev);
       c.launches++;
       LB_TRY(exclusive_scan_u32(c, w.scan, w.hist.p, w.hist.p, (size_t)256 * nblocks, nullptr));
-      rs_scatter_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks);
+      rs_scatter_kernel<<<nblocks, RS_WARPS * 32, 0, c.stream>>>(kin, vin, kout, vout, (uint32_t)n, shift, w.hist.p, nblocks, key_bits_dev);
       c.launches++;
     }
     kin = kout; vin = vout;
     if (kout == w.ka.p) { kout = w.kb.p; vout = w.vb.p; } else { kout = w.ka.p; vout = w.va.p; }
   }
   LB_CUDA(cudaGetLastError());
-  *keys_out = const_cast<uint32_t*>(kin);
-  *vals_out = const_cast<uint32_t*>(vin);
+  if (keys_out) *keys_out = const_cast<uint32_t*>(kin);
+  if (vals_out) *vals_out = const_cast<uint32_t*>(vin);
   return LB_OK;
+}
+
+int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
+                     uint32_t** keys_out, uint32_t** vals_out) {
+  return radix_sort_impl(c, w, keys_in, vals_in, n, key_bits, nullptr, keys_out, vals_out);
+}
+
+int radix_sort_pairs_devbits(Ctx& c, SortWork& w, const uint32_t* keys_in, size_t n, int max_key_bits, const int* key_bits_dev) {
+  return radix_sort_impl(c, w, keys_in, nullptr, n, max_key_bits, key_bits_dev, nullptr, nullptr);
 }
 
 }  // namespace lb

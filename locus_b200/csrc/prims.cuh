@@ -117,6 +117,35 @@ __global__ void bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32
                             int ff_off, float fmin, float fmax, int negative, BodyBox body, BBoxAcc* acc);
 
 // ------------------------------------------------------------------ scan
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across the block; returns exclusive prefix, total in *total
+template <int T>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* smem /*T/32+1*/) {
+  uint32_t incl = warp_incl_scan(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (l < T / 32) ? smem[l] : 0;
+    uint32_t si = warp_incl_scan(s);
+    if (l < T / 32) smem[l] = si - s;
+    if (l == T / 32 - 1) smem[T / 32] = si;
+  }
+  __syncthreads();
+  uint32_t r = smem[w] + incl - v;
+  *total = smem[T / 32];
+  __syncthreads();
+  return r;
+}
+
 // Exclusive scan of n uint32 (in may alias out).  total (nullable, device) receives the grand total.
 struct ScanWork { DBuf<uint32_t> sums; };
 int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);
@@ -131,5 +160,9 @@ struct SortWork {
 };
 int radix_sort_pairs(Ctx& c, SortWork& w, const uint32_t* keys_in, const uint32_t* vals_in, size_t n, int key_bits,
                      uint32_t** keys_out, uint32_t** vals_out);
+// Same sort (val = element index) when the key width is only known on the device: passes for max_key_bits are launched,
+// those beyond *key_bits_dev return at once.  Result: buffers w.ka / w.va after an odd number of executed passes
+// ((*key_bits_dev + 7) / 8), w.kb / w.vb after an even number; consumers pick on the device.
+int radix_sort_pairs_devbits(Ctx& c, SortWork& w, const uint32_t* keys_in, size_t n, int max_key_bits, const int* key_bits_dev);
 
 }  // namespace lb

@@ -4,13 +4,16 @@
 // point_cloud_filter/src/custom_voxel_grid.cc:76-87 (index arithmetic cross-
 // checked with multithreaded_ndt/voxel_grid_covariance_omp_impl.hpp:67-164).
 //
-// Pipeline (all on the handle's stream, data resident in HBM):
-//   bbox_kernel        finite + filter-limit predicate, min/max reduce
-//   vg_keys_kernel     int32 PCL leaf index per point (bit-exact float32 math)
-//   radix_sort_pairs   stable LSD sort of (leaf index, point#)
-//   vg_heads_kernel + exclusive_scan + vg_segstart_kernel    voxel segments
-//   vg_centroid_kernel one thread per voxel: float32 sum in ascending point
-//                      order, divide by count, write the output point
+// One call = one stream-ordered chain of kernels with NO host round trip in between: everything a later kernel needs
+// from an earlier one (bounding box -> min_b / div_b / key width, voxel count) stays in a small device-resident state
+// block; the host synchronises once, at the end, to learn the voxel count and the status.
+//   vg_bbox_kernel     finite + filter-limit + body-box predicate, min/max reduce (two 16-byte loads per 32-byte
+//                      record); the last CTA derives min_b, div_b, the overflow guard and the key width
+//   vg_keys_kernel     int32 PCL leaf index per point (bit-exact float32 math) + a packed float4 record of the four
+//                      averaged fields, so that no later kernel touches the raw cloud's strided layout again
+//   radix sort         stable LSD sort of (leaf index, point#); passes beyond the key width return at once
+//   vg_tile_heads_kernel + vg_segstart_kernel    voxel segments (per-tile head counts, then prefix + local scan)
+//   vg_centroid4_kernel   a warp owns 32 consecutive voxels: float32 sum in ascending point order, / count
 // Algorithmic bytes: N_in*point_step + N_out*point_step.
 #include <float.h>
 #include <math.h>
@@ -27,61 +30,248 @@ struct VoxelFieldsDev {
   uint32_t ff_off[VG_MAX_FIELDS];
 };
 
+// device-resident state of one lb_voxel_filter call (written by the kernels, read back once at the end)
+struct VoxState {
+  BBoxAcc acc;                 // bounding box of the surviving points; reset by the CTA that consumes it
+  unsigned ticket;             // last-CTA detection of vg_bbox_kernel
+  int status;                  // LB_OK or LB_ERR_VOXEL_OVERFLOW
+  int min_b[3], div_b[3];
+  uint32_t sentinel;           // number of cells of the grid = key of a dropped point (sorts last)
+  int key_bits;                // width of the sort key; 0: nothing to do (empty input / overflow)
+  uint32_t count;              // surviving points
+  uint32_t n_seg;              // occupied voxels
+  uint32_t n_final;            // output points (after min_points_per_voxel)
+};
+
+struct VoxLimits {
+  int ff_off;                  // byte offset of the filter field, < 0: none
+  float fmin, fmax;            // getMinMax3D compares in float32
+  double dmin, dmax;           // applyFilter compares the double limits
+  int negative;
+};
+
+// the 8 words of a 32-byte record, fetched with two 16-byte loads
+struct Rec32 { uint4 a, b; };
+__device__ __forceinline__ Rec32 load_rec32(const uint8_t* p) {
+  Rec32 r;
+  r.a = __ldg(reinterpret_cast<const uint4*>(p));
+  r.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  return r;
+}
+__device__ __forceinline__ float rec32_word(const Rec32& r, uint32_t off) {
+  const uint32_t w = off >> 2;
+  uint32_t v = (w == 0) ? r.a.x : (w == 1) ? r.a.y : (w == 2) ? r.a.z : (w == 3) ? r.a.w
+             : (w == 4) ? r.b.x : (w == 5) ? r.b.y : (w == 6) ? r.b.z : r.b.w;
+  return __uint_as_float(v);
+}
+
+__device__ __forceinline__ bool vg_survives(bool lim_drop, float x, float y, float z, const BodyBox& body) {
+  return !lim_drop && isfinite(x) && isfinite(y) && isfinite(z) && !body_box_drops(body, x, y, z);
+}
+
+// pcl::getMinMax3D over the points that pass the (float32) limits, the finite check and the body box; the last CTA to
+// finish turns the box into the grid geometry exactly like applyFilter does on the host side of PCL
+// (voxel_grid_covariance_omp_impl.hpp:75-103): dx*dy*dz overflow guard, min_b = floor(min_p * inv_leaf), div_b.
 __global__ void __launch_bounds__(256)
-vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t x_off, uint32_t y_off,
-               uint32_t z_off, int ff_off, double lim_min, double lim_max, int negative, float inv0, float inv1,
-               float inv2, int min_b0, int min_b1, int min_b2, int mul1, int mul2, uint32_t sentinel,
-               BodyBox body, uint32_t* __restrict__ keys, BBoxAcc* acc_to_reset) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) bbox_reset(acc_to_reset);   // the host has consumed the bounding box: ready for the next call
-  if (i >= n) return;
-  const uint8_t* p = base + (size_t)i * stride;
-  bool ok = true;
-  if (ff_off >= 0) {
-    double v = (double)*reinterpret_cast<const float*>(p + ff_off);
-    bool drop = negative ? (v < lim_max && v > lim_min) : (v > lim_max || v < lim_min);
-    ok = !drop;
+vg_bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
+               float inv0, float inv1, float inv2, int vec32, VoxState* __restrict__ st) {
+  uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0, mx1 = 0, mx2 = 0, cnt = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t* p = base + (size_t)i * stride;
+    float x, y, z, v = 0.f;
+    if (vec32) {
+      const Rec32 r = load_rec32(p);
+      x = rec32_word(r, xyz_off); y = rec32_word(r, xyz_off + 4); z = rec32_word(r, xyz_off + 8);
+      if (lim.ff_off >= 0) v = rec32_word(r, (uint32_t)lim.ff_off);
+    } else {
+      const float* q = reinterpret_cast<const float*>(p + xyz_off);
+      x = q[0]; y = q[1]; z = q[2];
+      if (lim.ff_off >= 0) v = *reinterpret_cast<const float*>(p + lim.ff_off);
+    }
+    bool drop = false;
+    if (lim.ff_off >= 0) drop = lim.negative ? (v < lim.fmax && v > lim.fmin) : (v > lim.fmax || v < lim.fmin);
+    if (!vg_survives(drop, x, y, z, body)) continue;
+    const uint32_t ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+    mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+    mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+    cnt++;
   }
-  float x = *reinterpret_cast<const float*>(p + x_off);
-  float y = *reinterpret_cast<const float*>(p + y_off);
-  float z = *reinterpret_cast<const float*>(p + z_off);
-  ok = ok && isfinite(x) && isfinite(y) && isfinite(z);
-  ok = ok && !body_box_drops(body, x, y, z);       // BodyFilter folded into the load predicate (row f4)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  __shared__ uint32_t sm[8][7];
+  __shared__ bool last;
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[w][0] = mn0; sm[w][1] = mn1; sm[w][2] = mn2; sm[w][3] = mx0; sm[w][4] = mx1; sm[w][5] = mx2; sm[w][6] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) {
+      mn0 = min(mn0, sm[i][0]); mn1 = min(mn1, sm[i][1]); mn2 = min(mn2, sm[i][2]);
+      mx0 = max(mx0, sm[i][3]); mx1 = max(mx1, sm[i][4]); mx2 = max(mx2, sm[i][5]);
+      cnt += sm[i][6];
+    }
+    if (cnt > 0) {       // one set of atomics per CTA (same-address atomics serialise in L2)
+      atomicMin(&st->acc.mn[0], mn0); atomicMin(&st->acc.mn[1], mn1); atomicMin(&st->acc.mn[2], mn2);
+      atomicMax(&st->acc.mx[0], mx0); atomicMax(&st->acc.mx[1], mx1); atomicMax(&st->acc.mx[2], mx2);
+      atomicAdd(&st->acc.count, cnt);
+    }
+    __threadfence();
+    last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  // ---- grid geometry (what pcl::VoxelGrid::applyFilter derives from min_p / max_p)
+  const uint32_t count = atomicAdd(&st->acc.count, 0u);
+  int status = LB_OK, key_bits = 0;
+  uint32_t sentinel = 0;
+  if (count > 0) {
+    float min_p[3], max_p[3];
+    const float inv[3] = {inv0, inv1, inv2};
+    for (int d = 0; d < 3; d++) { min_p[d] = ord2f(atomicAdd(&st->acc.mn[d], 0u)); max_p[d] = ord2f(atomicAdd(&st->acc.mx[d], 0u)); }
+    const long long dx = (long long)((max_p[0] - min_p[0]) * inv[0]) + 1;
+    const long long dy = (long long)((max_p[1] - min_p[1]) * inv[1]) + 1;
+    const long long dz = (long long)((max_p[2] - min_p[2]) * inv[2]) + 1;
+    int min_b[3], div_b[3];
+    for (int d = 0; d < 3; d++) {
+      min_b[d] = (int)floorf(min_p[d] * inv[d]);
+      const int max_b = (int)floorf(max_p[d] * inv[d]);
+      div_b[d] = max_b - min_b[d] + 1;
+      st->min_b[d] = min_b[d]; st->div_b[d] = div_b[d];
+    }
+    const long long ncells = (long long)div_b[0] * div_b[1] * div_b[2];
+    if (dx * dy * dz > 2147483647ll || ncells > 2147483647ll) {
+      status = LB_ERR_VOXEL_OVERFLOW;      // "Leaf size is too small for the input dataset. Integer indices would overflow."
+    } else {
+      sentinel = (uint32_t)ncells;
+      key_bits = 1;
+      while (key_bits < 32 && (1ull << key_bits) <= (unsigned long long)sentinel) key_bits++;
+    }
+  }
+  st->status = status; st->sentinel = sentinel; st->key_bits = key_bits; st->count = count;
+  st->n_seg = 0; st->n_final = 0;
+  bbox_reset(&st->acc);            // consumed: clean for the next call
+  st->ticket = 0;
+}
+
+__global__ void __launch_bounds__(256)
+vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
+               float inv0, float inv1, float inv2, int vec32, VoxelFieldsDev F, const VoxState* __restrict__ st,
+               uint32_t* __restrict__ keys, float4* __restrict__ rec /*nullable: only for 4 averaged fields*/) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int key_bits = st->key_bits;
+  if (key_bits == 0 || i >= n) return;              // empty input or overflow: nothing is sorted
+  const uint32_t sentinel = st->sentinel;
+  const int min_b0 = st->min_b[0], min_b1 = st->min_b[1], min_b2 = st->min_b[2];
+  const int mul1 = st->div_b[0], mul2 = st->div_b[0] * st->div_b[1];
+  const uint8_t* p = base + (size_t)i * stride;
+  float x, y, z, v = 0.f;
+  float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec32) {
+    const Rec32 r = load_rec32(p);
+    x = rec32_word(r, xyz_off); y = rec32_word(r, xyz_off + 4); z = rec32_word(r, xyz_off + 8);
+    if (lim.ff_off >= 0) v = rec32_word(r, (uint32_t)lim.ff_off);
+    if (rec) r4 = make_float4(rec32_word(r, F.ff_off[0]), rec32_word(r, F.ff_off[1]), rec32_word(r, F.ff_off[2]), rec32_word(r, F.ff_off[3]));
+  } else {
+    x = *reinterpret_cast<const float*>(p + xyz_off);
+    y = *reinterpret_cast<const float*>(p + xyz_off + 4);
+    z = *reinterpret_cast<const float*>(p + xyz_off + 8);
+    if (lim.ff_off >= 0) v = *reinterpret_cast<const float*>(p + lim.ff_off);
+    if (rec) r4 = make_float4(*reinterpret_cast<const float*>(p + F.ff_off[0]), *reinterpret_cast<const float*>(p + F.ff_off[1]),
+                              *reinterpret_cast<const float*>(p + F.ff_off[2]), *reinterpret_cast<const float*>(p + F.ff_off[3]));
+  }
+  bool drop = false;
+  if (lim.ff_off >= 0) {
+    const double dv = (double)v;
+    drop = lim.negative ? (dv < lim.dmax && dv > lim.dmin) : (dv > lim.dmax || dv < lim.dmin);
+  }
   uint32_t key = sentinel;
-  if (ok) {
+  if (vg_survives(drop, x, y, z, body)) {          // BodyFilter folded into the load predicate (row f4)
     // static_cast<int>(floor(x * inv_leaf) - float(min_b))   (voxel_grid_covariance_omp_impl.hpp:159-161)
-    int ijk0 = (int)(floorf(x * inv0) - (float)min_b0);
-    int ijk1 = (int)(floorf(y * inv1) - (float)min_b1);
-    int ijk2 = (int)(floorf(z * inv2) - (float)min_b2);
-    int idx = ijk0 + ijk1 * mul1 + ijk2 * mul2;
+    const int ijk0 = (int)(floorf(x * inv0) - (float)min_b0);
+    const int ijk1 = (int)(floorf(y * inv1) - (float)min_b1);
+    const int ijk2 = (int)(floorf(z * inv2) - (float)min_b2);
+    const int idx = ijk0 + ijk1 * mul1 + ijk2 * mul2;
     key = ((uint32_t)idx < sentinel) ? (uint32_t)idx : sentinel;
   }
   keys[i] = key;
+  if (rec) rec[i] = r4;
+}
+
+// which ping-pong buffer holds the sorted pairs: A after an odd number of executed passes, B after an even number
+__device__ __forceinline__ bool vg_sorted_in_a(int key_bits) { return (((key_bits + 7) >> 3) & 1) != 0; }
+
+constexpr int VG_TILE = 2048;      // sorted positions per CTA of the two segment kernels (256 threads x 8)
+
+__device__ __forceinline__ uint32_t vg_head_flags8(const uint32_t* __restrict__ keys, uint32_t base, uint32_t n, uint32_t sentinel,
+                                                   uint32_t* cnt) {
+  // 8 consecutive sorted positions per thread; bit j: position base + j starts a voxel
+  uint32_t bits = 0, c = 0;
+  uint32_t prev = (base > 0 && base <= n) ? keys[base - 1] : 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint32_t i = base + j;
+    if (i < n) {
+      const uint32_t k = keys[i];
+      if (k < sentinel && (i == 0 || k != prev)) { bits |= 1u << j; c++; }
+      prev = k;
+    }
+  }
+  *cnt = c;
+  return bits;
 }
 
 __global__ void __launch_bounds__(256)
-vg_heads_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t sentinel, uint32_t* __restrict__ flags) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t k = keys[i];
-  flags[i] = (k < sentinel && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+vg_tile_heads_kernel(const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb, const VoxState* __restrict__ st, uint32_t n,
+                     uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t sm[256 / 32 + 1];
+  const int key_bits = st->key_bits;
+  if (key_bits == 0) { if (threadIdx.x == 0) tile_cnt[blockIdx.x] = 0; return; }
+  const uint32_t* keys = vg_sorted_in_a(key_bits) ? ka : kb;
+  uint32_t c;
+  vg_head_flags8(keys, blockIdx.x * VG_TILE + threadIdx.x * 8, n, st->sentinel, &c);
+  uint32_t tot;
+  block_excl_scan<256>(c, &tot, sm);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
 }
 
+// seg_start[s] = sorted position where voxel s begins; the last CTA publishes the voxel count
 __global__ void __launch_bounds__(256)
-vg_segstart_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ excl, uint32_t n, uint32_t sentinel,
-                   uint32_t* __restrict__ seg_start) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t k = keys[i];
-  if (k < sentinel && (i == 0 || keys[i - 1] != k)) seg_start[excl[i]] = i;
+vg_segstart_kernel(const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb, VoxState* __restrict__ st, uint32_t n,
+                   const uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ seg_start) {
+  __shared__ uint32_t sm[256 / 32 + 1];
+  __shared__ uint32_t pre_s;
+  const int key_bits = st->key_bits;
+  if (key_bits == 0) return;
+  const uint32_t* keys = vg_sorted_in_a(key_bits) ? ka : kb;
+  // voxels that start in earlier tiles
+  uint32_t part = 0;
+  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 256) part += tile_cnt[b];
+  uint32_t pre;
+  block_excl_scan<256>(part, &pre, sm);
+  if (threadIdx.x == 0) pre_s = pre;
+  uint32_t c;
+  const uint32_t base = blockIdx.x * VG_TILE + threadIdx.x * 8;
+  const uint32_t bits = vg_head_flags8(keys, base, n, st->sentinel, &c);
+  uint32_t tot;
+  uint32_t s = block_excl_scan<256>(c, &tot, sm) + pre_s;
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (bits & (1u << j)) seg_start[s++] = base + j;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { st->n_seg = pre_s + tot; st->n_final = pre_s + tot; }
 }
 
 // keep[s] = 1 iff voxel s holds >= min_points points
 __global__ void __launch_bounds__(256)
-vg_keep_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ seg_start, const uint32_t* n_seg_dev,
-               uint32_t n, int min_points, uint32_t* __restrict__ keep) {
+vg_keep_kernel(const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb, const uint32_t* __restrict__ seg_start,
+               const VoxState* __restrict__ st, uint32_t n, int min_points, uint32_t* __restrict__ keep) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t n_seg = *n_seg_dev;
+  const uint32_t* keys = vg_sorted_in_a(st->key_bits) ? ka : kb;
+  uint32_t n_seg = st->n_seg;
   if (s >= n_seg) { if (s < n) keep[s] = 0; return; }
   uint32_t a = seg_start[s];
   uint32_t k = keys[a];
@@ -90,37 +280,27 @@ vg_keep_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ s
   keep[s] = ((int)(e - a) >= min_points) ? 1u : 0u;
 }
 
-// Gather the averaged FLOAT32 fields of every point into voxel-sorted order (one thread per sorted
-// position: scattered 4-byte reads with full memory-level parallelism, coalesced writes), so that the
-// per-voxel sequential sums below stream over contiguous memory.
-__global__ void __launch_bounds__(256)
-vg_gather_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ vals, uint32_t n,
-                 VoxelFieldsDev F, float* __restrict__ sorted_f) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const uint8_t* p = in + (size_t)vals[s] * stride;
-  float* d = sorted_f + (size_t)s * F.n_ff;
-  for (int f = 0; f < F.n_ff; f++) d[f] = *reinterpret_cast<const float*>(p + F.ff_off[f]);
-}
-
 // The common record layout (x, y, z, intensity averaged: 16-byte records).  A warp owns 32 consecutive voxels, i.e.
-// ONE contiguous range of the voxel-sorted records: the warp copies that range through shared memory with
-// coalesced 16-byte loads, and every lane then adds up its own voxel's records from shared memory in ascending
-// input order (the order defines the float32 rounding) -- no per-lane chains of dependent global loads, which is
-// what made the thread-per-voxel kernel below take 50 us for 30 k voxels.
+// ONE contiguous range of sorted positions: the warp stages the records of that range in shared memory (the packed
+// float4 records written by vg_keys_kernel, fetched through the sorted point numbers: 16-byte gathers from an
+// L2-resident array), and every lane then adds up its own voxel's records from shared memory in ascending input order
+// (the order defines the float32 rounding) -- no per-lane chains of dependent global loads.
 constexpr int VG4_TILE = 256;       // records per warp tile (4 KB)
 __global__ void __launch_bounds__(128)
-vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ keys,
-                    const uint32_t* __restrict__ vals, const float4* __restrict__ rec,
-                    const uint32_t* __restrict__ seg_start, const uint32_t* n_seg_dev,
+vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
+                    const uint32_t* __restrict__ va, const uint32_t* __restrict__ vb, const float4* __restrict__ rec,
+                    const uint32_t* __restrict__ seg_start, const VoxState* __restrict__ st,
                     const uint32_t* __restrict__ slot /*nullable*/, const uint32_t* __restrict__ keep /*nullable*/,
-                    uint32_t n, VoxelFieldsDev F, uint32_t capacity, uint8_t* __restrict__ out,
+                    uint32_t n, VoxelFieldsDev F, uint32_t capacity, int vec32, uint8_t* __restrict__ out,
                     int32_t* __restrict__ out_voxel_idx) {
   __shared__ float4 tile[4][VG4_TILE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t n_seg = *n_seg_dev;
+  const uint32_t n_seg = st->n_seg;
   const uint32_t s0 = (blockIdx.x * 4 + wib) * 32;
   if (s0 >= n_seg) return;                                  // whole warp
+  const bool in_a = vg_sorted_in_a(st->key_bits);
+  const uint32_t* keys = in_a ? ka : kb;
+  const uint32_t* vals = in_a ? va : vb;
   const uint32_t s = s0 + lane;
   const bool seg = s < n_seg;
   uint32_t a = 0, e = 0, k = 0;
@@ -137,7 +317,7 @@ vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint3
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t t0 = r0; t0 < r1; t0 += VG4_TILE) {
     const uint32_t t1 = min(r1, t0 + (uint32_t)VG4_TILE);
-    for (uint32_t i = t0 + lane; i < t1; i += 32) tile[wib][i - t0] = rec[i];
+    for (uint32_t i = t0 + lane; i < t1; i += 32) tile[wib][i - t0] = rec[vals[i]];
     __syncwarp();
     if (seg) {
       uint32_t lo = max(a, t0), hi = min(e, t1);
@@ -164,7 +344,7 @@ vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint3
   const uint8_t* first = in + (size_t)vals[a] * stride;
   uint8_t* dst = out + (size_t)o * stride;
   // bytes not covered by an averaged field come from the voxel's first point
-  if (stride == 32 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+  if (vec32 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     const uint4 w0 = reinterpret_cast<const uint4*>(first)[0], w1 = reinterpret_cast<const uint4*>(first)[1];
     reinterpret_cast<uint4*>(dst)[0] = w0; reinterpret_cast<uint4*>(dst)[1] = w1;
   } else {
@@ -178,21 +358,25 @@ vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint3
   if (out_voxel_idx) out_voxel_idx[o] = (int32_t)k;
 }
 
-// One thread per voxel: float32 sum of its points in ascending input order (the order the stable sort
-// produced), divide by the count (centroid /= float(n), PCL), write the output point.
+// Any other set of averaged fields: one thread per voxel, float32 sum of its points in ascending input order (the order
+// the stable sort produced), read straight from the caller's layout through the sorted point numbers; divide by the
+// count (centroid /= float(n), PCL), write the output point.
 __global__ void __launch_bounds__(128)
-vg_centroid_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ keys,
-                   const uint32_t* __restrict__ vals, const float* __restrict__ sorted_f,
-                   const uint32_t* __restrict__ seg_start, const uint32_t* n_seg_dev,
+vg_centroid_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
+                   const uint32_t* __restrict__ va, const uint32_t* __restrict__ vb,
+                   const uint32_t* __restrict__ seg_start, const VoxState* __restrict__ st,
                    const uint32_t* __restrict__ slot /*nullable*/, const uint32_t* __restrict__ keep /*nullable*/,
                    uint32_t n, VoxelFieldsDev F, uint32_t capacity, uint8_t* __restrict__ out,
                    int32_t* __restrict__ out_voxel_idx) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n_seg = *n_seg_dev;
+  const uint32_t n_seg = st->n_seg;
   if (s >= n_seg) return;
   if (keep && !keep[s]) return;
   uint32_t o = slot ? slot[s] : s;
   if (o >= capacity) return;
+  const bool in_a = vg_sorted_in_a(st->key_bits);
+  const uint32_t* keys = in_a ? ka : kb;
+  const uint32_t* vals = in_a ? va : vb;
   uint32_t a = seg_start[s];
   uint32_t k = keys[a];
   // segment end: next segment's start, or the first sentinel key after the last voxel
@@ -201,32 +385,16 @@ vg_centroid_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32
   else { e = a + 1; while (e < n && keys[e] == k) e++; }
   float acc[VG_MAX_FIELDS];
   const int nf = F.n_ff;
-  const float* src = sorted_f + (size_t)a * nf;
+  const uint8_t* first = in + (size_t)vals[a] * stride;
 #pragma unroll
-  for (int f = 0; f < VG_MAX_FIELDS; f++) acc[f] = (f < nf) ? src[f] : 0.f;
-  if (nf == 4) {
-    // the common case (x, y, z, intensity): 16-byte records, batches of 8 loads in flight, then the adds in
-    // ascending input order (the order defines the float32 rounding; only the LOADS are hoisted)
-    const float4* rec = reinterpret_cast<const float4*>(sorted_f) + a;
-    uint32_t j = 1, len = e - a;
-    for (; j + 8 <= len; j += 8) {
-      float4 v[8];
+  for (int f = 0; f < VG_MAX_FIELDS; f++) acc[f] = (f < nf) ? *reinterpret_cast<const float*>(first + F.ff_off[f]) : 0.f;
+  for (uint32_t j = a + 1; j < e; j++) {
+    const uint8_t* p = in + (size_t)vals[j] * stride;
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = rec[j + u];
-#pragma unroll
-      for (int u = 0; u < 8; u++) { acc[0] = acc[0] + v[u].x; acc[1] = acc[1] + v[u].y; acc[2] = acc[2] + v[u].z; acc[3] = acc[3] + v[u].w; }
-    }
-    for (; j < len; j++) { float4 v = rec[j]; acc[0] = acc[0] + v.x; acc[1] = acc[1] + v.y; acc[2] = acc[2] + v.z; acc[3] = acc[3] + v.w; }
-  } else {
-    for (uint32_t j = a + 1; j < e; j++) {
-      src += nf;
-#pragma unroll
-      for (int f = 0; f < VG_MAX_FIELDS; f++)
-        if (f < nf) acc[f] = acc[f] + src[f];
-    }
+    for (int f = 0; f < VG_MAX_FIELDS; f++)
+      if (f < nf) acc[f] = acc[f] + *reinterpret_cast<const float*>(p + F.ff_off[f]);
   }
   float cnt = (float)(e - a);
-  const uint8_t* first = in + (size_t)vals[a] * stride;
   uint8_t* dst = out + (size_t)o * stride;
   // bytes not covered by an averaged field come from the voxel's first point
   for (uint32_t w = 0; w < stride / 4; w++)
@@ -235,6 +403,14 @@ vg_centroid_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32
   for (int f = 0; f < VG_MAX_FIELDS; f++)
     if (f < nf) *reinterpret_cast<float*>(dst + F.ff_off[f]) = acc[f] / cnt;
   if (out_voxel_idx) out_voxel_idx[o] = (int32_t)k;
+}
+
+__global__ void vg_state_init_kernel(VoxState* st) {
+  if (threadIdx.x == 0) {
+    bbox_reset(&st->acc);
+    st->ticket = 0; st->status = 0; st->sentinel = 0; st->key_bits = 0; st->count = 0; st->n_seg = 0; st->n_final = 0;
+    for (int d = 0; d < 3; d++) { st->min_b[d] = 0; st->div_b[d] = 0; }
+  }
 }
 
 }  // namespace lb
@@ -252,12 +428,11 @@ struct lb_voxel {
   BodyBox body{0, 1.f, 0.f, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // BodyFilter nodelet folded in (lb_voxel_set_body_filter)
   DBuf<uint8_t> d_in, d_out;
   DBuf<int32_t> d_vidx;
-  DBuf<uint32_t> keys, flags, seg_start, keep, slot;
-  DBuf<float> sorted_f;
-  BBoxAcc* d_acc = nullptr;     // device
-  uint32_t* d_tot = nullptr;    // device [2]
-  BBoxAcc* h_acc = nullptr;     // pinned
-  uint32_t* h_tot = nullptr;    // pinned [2]
+  DBuf<uint32_t> keys, tile_cnt, seg_start, keep, slot;
+  DBuf<float4> rec;
+  VoxState* d_st = nullptr;     // device
+  VoxState* h_st = nullptr;     // pinned
+  int bits_hint = 32;           // sort passes to enqueue: the key width of the previous call, rounded up to whole passes
   SortWork sort;
   ScanWork scan;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -269,16 +444,14 @@ static int voxel_create_impl(int device, void* stream, bool ext, lb_voxel** out)
   lb_voxel* h = new lb_voxel;
   int s = ctx_init(h->c, device, stream, ext);
   if (s != LB_OK) { delete h; return s; }
-  if (cudaMalloc((void**)&h->d_acc, sizeof(BBoxAcc)) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_tot, 2 * sizeof(uint32_t)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_acc, sizeof(BBoxAcc)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_tot, 2 * sizeof(uint32_t)) != cudaSuccess ||
+  if (cudaMalloc((void**)&h->d_st, sizeof(VoxState)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_st, sizeof(VoxState)) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     set_error("lb_voxel_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete h;
     return LB_ERR_CUDA;
   }
-  bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_acc);
+  vg_state_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_st);
   cudaStreamSynchronize(h->c.stream);
   *out = h;
   return LB_OK;
@@ -293,14 +466,12 @@ int lb_voxel_destroy(lb_voxel* h) {
   if (!h) return LB_OK;
   cudaSetDevice(h->c.device);
   cudaStreamSynchronize(h->c.stream);
-  h->d_in.release(); h->d_out.release(); h->d_vidx.release(); h->keys.release(); h->flags.release();
-  h->seg_start.release(); h->keep.release(); h->slot.release(); h->sorted_f.release();
+  h->d_in.release(); h->d_out.release(); h->d_vidx.release(); h->keys.release(); h->tile_cnt.release();
+  h->seg_start.release(); h->keep.release(); h->slot.release(); h->rec.release();
   h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
   h->sort.scan.sums.release(); h->scan.sums.release();
-  if (h->d_acc) cudaFree(h->d_acc);
-  if (h->d_tot) cudaFree(h->d_tot);
-  if (h->h_acc) cudaFreeHost(h->h_acc);
-  if (h->h_tot) cudaFreeHost(h->h_tot);
+  if (h->d_st) cudaFree(h->d_st);
+  if (h->h_st) cudaFreeHost(h->h_st);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   ctx_destroy(h->c);
@@ -384,7 +555,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     F.n_ff = 3; F.ff_off[0] = xo; F.ff_off[1] = yo; F.ff_off[2] = zo;
   }
 
-  // x,y,z must be contiguous for bbox_kernel's 3-float read (true for every PCL point type)
+  // x,y,z must be contiguous (true for every PCL point type): the kernels read them as three consecutive floats
   if (yo != xo + 4 || zo != xo + 8) { set_error("lb_voxel_filter: x,y,z must be consecutive FLOAT32 fields"); return LB_ERR_UNSUPPORTED; }
   Ctx& c = h->c;
   LB_CUDA(cudaSetDevice(c.device));
@@ -397,61 +568,6 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     LB_CUDA(cudaMemcpyAsync(h->d_in.p, data, bytes, cudaMemcpyHostToDevice, c.stream));
     d_in = h->d_in.p;
   }
-  // ---- bounding box of the surviving points (pcl::getMinMax3D with float limits)
-  int bb_blocks = min(cdiv(n, 256), c.sm_count * 2);
-  bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, ffo, (float)h->lim_min,
-                                                (float)h->lim_max, h->negative, h->body, h->d_acc);
-  c.launches += 1;
-  LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
-  LB_CUDA(cudaStreamSynchronize(c.stream));
-  if (h->h_acc->count == 0) {
-    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
-    *n_out = 0;
-    return LB_OK;
-  }
-  float min_p[3], max_p[3], inv[3];
-  for (int d = 0; d < 3; d++) { min_p[d] = ord2f(h->h_acc->mn[d]); max_p[d] = ord2f(h->h_acc->mx[d]); inv[d] = 1.0f / h->leaf[d]; }
-  int64_t dx = (int64_t)((max_p[0] - min_p[0]) * inv[0]) + 1;
-  int64_t dy = (int64_t)((max_p[1] - min_p[1]) * inv[1]) + 1;
-  int64_t dz = (int64_t)((max_p[2] - min_p[2]) * inv[2]) + 1;
-  if (dx * dy * dz > (int64_t)INT32_MAX) {
-    bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc);
-    set_error("lb_voxel_filter: leaf size too small for the input dataset, integer indices would overflow");
-    return LB_ERR_VOXEL_OVERFLOW;
-  }
-  int min_b[3], max_b[3], div_b[3];
-  for (int d = 0; d < 3; d++) {
-    min_b[d] = (int)floorf(min_p[d] * inv[d]);
-    max_b[d] = (int)floorf(max_p[d] * inv[d]);
-    div_b[d] = max_b[d] - min_b[d] + 1;
-  }
-  int64_t ncells64 = (int64_t)div_b[0] * div_b[1] * div_b[2];
-  if (ncells64 > (int64_t)INT32_MAX) { bbox_init_kernel<<<1, 32, 0, c.stream>>>(h->d_acc); set_error("lb_voxel_filter: voxel index overflow"); return LB_ERR_VOXEL_OVERFLOW; }
-  uint32_t sentinel = (uint32_t)ncells64;
-  int key_bits = 1;
-  while (key_bits < 32 && (1ull << key_bits) <= (uint64_t)sentinel) key_bits++;
-
-  LB_TRY(h->keys.ensure(n)); LB_TRY(h->flags.ensure(n)); LB_TRY(h->seg_start.ensure(n));
-  vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, n, point_step, xo, yo, zo, ffo, h->lim_min, h->lim_max,
-                                                     h->negative, inv[0], inv[1], inv[2], min_b[0], min_b[1], min_b[2],
-                                                     div_b[0], div_b[0] * div_b[1], sentinel, h->body, h->keys.p, h->d_acc);
-  c.launches++;
-  uint32_t *sk = nullptr, *sv = nullptr;
-  LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &sk, &sv));
-  vg_heads_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(sk, n, sentinel, h->flags.p);
-  c.launches++;
-  LB_TRY(exclusive_scan_u32(c, h->scan, h->flags.p, h->flags.p, n, &h->d_tot[0]));
-  vg_segstart_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(sk, h->flags.p, n, sentinel, h->seg_start.p);
-  c.launches++;
-  const uint32_t* slot = nullptr; const uint32_t* keep = nullptr;
-  const uint32_t* n_final_dev = &h->d_tot[0];
-  if (h->min_points > 1) {
-    LB_TRY(h->keep.ensure(n)); LB_TRY(h->slot.ensure(n));
-    vg_keep_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(sk, h->seg_start.p, &h->d_tot[0], n, h->min_points, h->keep.p);
-    c.launches++;
-    LB_TRY(exclusive_scan_u32(c, h->scan, h->keep.p, h->slot.p, n, &h->d_tot[1]));
-    slot = h->slot.p; keep = h->keep.p; n_final_dev = &h->d_tot[1];
-  }
   uint8_t* d_out = out; int32_t* d_vidx = out_voxel_idx;
   uint32_t capacity = (uint32_t)(out_capacity_pts < n ? out_capacity_pts : n);
   if (mem_out == LB_MEM_HOST) {
@@ -459,29 +575,72 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     d_out = h->d_out.p; capacity = n;
     if (out_voxel_idx) { LB_TRY(h->d_vidx.ensure(n)); d_vidx = h->d_vidx.p; }
   }
-  LB_TRY(h->sorted_f.ensure((size_t)n * F.n_ff));
-  vg_gather_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, point_step, sv, n, F, h->sorted_f.p);
-  if (F.n_ff == 4)
-    vg_centroid4_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, reinterpret_cast<const float4*>(h->sorted_f.p),
-                                                             h->seg_start.p, &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
-  else
-    vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, sk, sv, h->sorted_f.p, h->seg_start.p,
-                                                            &h->d_tot[0], slot, keep, n, F, capacity, d_out, d_vidx);
-  c.launches += 2;
-  LB_CUDA(cudaGetLastError());
-  LB_CUDA(cudaMemcpyAsync(h->h_tot, n_final_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-  LB_CUDA(cudaStreamSynchronize(c.stream));
-  size_t m = h->h_tot[0];
+  const uint32_t ntiles = (uint32_t)cdiv(n, VG_TILE);
+  LB_TRY(h->keys.ensure(n)); LB_TRY(h->seg_start.ensure(n)); LB_TRY(h->tile_cnt.ensure(ntiles));
+  const bool four = F.n_ff == 4;
+  if (four) LB_TRY(h->rec.ensure(n));
+  // 32-byte records on a 16-byte aligned base: two 16-byte loads per point instead of 4-byte strided ones
+  const int vec32 = (point_step == 32 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0) ? 1 : 0;
+  VoxLimits lim;
+  lim.ff_off = ffo; lim.fmin = (float)h->lim_min; lim.fmax = (float)h->lim_max; lim.dmin = h->lim_min; lim.dmax = h->lim_max;
+  lim.negative = h->negative;
+  const float inv0 = 1.0f / h->leaf[0], inv1 = 1.0f / h->leaf[1], inv2 = 1.0f / h->leaf[2];
+  // ---- one stream-ordered chain, no host round trip until the end.  The sort's key width follows from the bounding
+  // box, i.e. it is known on the device only; passes are enqueued for the width the previous call needed (consecutive
+  // scans of a stream have the same extent), passes beyond the actual width return at once, and in the rare case that
+  // this call needs MORE passes than were enqueued the chain is simply run again with all four.
+  const uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const int launched_bits = attempt == 0 ? h->bits_hint : 32;
+    const int bb_blocks = min(cdiv(n, 256), c.sm_count * 4);
+    vg_bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, h->d_st);
+    vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, F,
+                                                       h->d_st, h->keys.p, four ? h->rec.p : nullptr);
+    c.launches += 2;
+    LB_TRY(radix_sort_pairs_devbits(c, h->sort, h->keys.p, n, launched_bits, &h->d_st->key_bits));
+    ka = h->sort.ka.p; kb = h->sort.kb.p; va = h->sort.va.p; vb = h->sort.vb.p;
+    vg_tile_heads_kernel<<<ntiles, 256, 0, c.stream>>>(ka, kb, h->d_st, n, h->tile_cnt.p);
+    vg_segstart_kernel<<<ntiles, 256, 0, c.stream>>>(ka, kb, h->d_st, n, h->tile_cnt.p, h->seg_start.p);
+    c.launches += 2;
+    const uint32_t* slot = nullptr; const uint32_t* keep = nullptr;
+    if (h->min_points > 1) {
+      LB_TRY(h->keep.ensure(n)); LB_TRY(h->slot.ensure(n));
+      vg_keep_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(ka, kb, h->seg_start.p, h->d_st, n, h->min_points, h->keep.p);
+      c.launches++;
+      LB_TRY(exclusive_scan_u32(c, h->scan, h->keep.p, h->slot.p, n, &h->d_st->n_final));
+      slot = h->slot.p; keep = h->keep.p;
+    }
+    if (four)
+      vg_centroid4_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, ka, kb, va, vb, h->rec.p, h->seg_start.p, h->d_st,
+                                                               slot, keep, n, F, capacity, vec32, d_out, d_vidx);
+    else
+      vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, ka, kb, va, vb, h->seg_start.p, h->d_st, slot, keep,
+                                                              n, F, capacity, d_out, d_vidx);
+    c.launches++;
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(VoxState), cudaMemcpyDeviceToHost, c.stream));
+    if (mem_out != LB_MEM_HOST) LB_CUDA(cudaEventRecord(h->ev1, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));        // the one synchronisation of a device-to-device call
+    if (h->h_st->key_bits <= launched_bits) break;   // every pass the key needs was enqueued
+  }
+  if (h->h_st->key_bits > 0) h->bits_hint = ((h->h_st->key_bits + 7) / 8) * 8;
+  if (h->h_st->status != LB_OK) {
+    set_error("lb_voxel_filter: leaf size too small for the input dataset, integer indices would overflow");
+    return LB_ERR_VOXEL_OVERFLOW;
+  }
+  size_t m = h->h_st->key_bits ? h->h_st->n_final : 0;
   if (m > out_capacity_pts) {
     set_error("lb_voxel_filter: output capacity %zu < %zu voxels", out_capacity_pts, m);
     return LB_ERR_CAPACITY;
   }
-  if (mem_out == LB_MEM_HOST && m > 0) {
-    LB_CUDA(cudaMemcpyAsync(out, d_out, m * point_step, cudaMemcpyDeviceToHost, c.stream));
-    if (out_voxel_idx) LB_CUDA(cudaMemcpyAsync(out_voxel_idx, d_vidx, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  if (mem_out == LB_MEM_HOST) {
+    if (m > 0) {
+      LB_CUDA(cudaMemcpyAsync(out, d_out, m * point_step, cudaMemcpyDeviceToHost, c.stream));
+      if (out_voxel_idx) LB_CUDA(cudaMemcpyAsync(out_voxel_idx, d_vidx, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    }
+    LB_CUDA(cudaEventRecord(h->ev1, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
   }
-  LB_CUDA(cudaEventRecord(h->ev1, c.stream));
-  LB_CUDA(cudaStreamSynchronize(c.stream));
   cudaEventElapsedTime(&h->t_last_ms, h->ev0, h->ev1);
   *n_out = m;
   return LB_OK;

@@ -43,3 +43,17 @@ def test_reference_arm_under_torchrun_rank0_only():
     lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
     _check(lines[0], 2)
+
+
+def test_reference_arm_c3_contract_line():
+    """--config c3 (scan-to-submap, BASELINE configs[2]): same contract line; the CPU arm keeps the submap's kd-tree and
+    covariances between scans, like the reference does while setInputTarget is not called again"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "c3", "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--stream-scans", "3"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    _check(lines[0], 1)
+    d = json.loads(lines[0])
+    assert d["config"]["name"] == "c3" and "500000-point submap" in d["config"]["workload"] and "corr 0.2" in d["config"]["workload"]

@@ -309,6 +309,31 @@ def test_cpp_host_mirror_runs():
     assert "converged=1" in r.stdout and "pipeline:" in r.stdout
 
 
+def test_pcl_shim_runs(oracle):
+    """shim/b200_gicp_pcl.hpp -- the pcl::Registration subclass LOCUS's SetupICP() would instantiate -- compiled against
+    the PCL mock and driven like the callers drive icp_: setInputSource / setInputTarget / align() /
+    getFinalTransformation / getSearchMethodTarget()->nearestKSearch, on the reference's hollow-cube fixture"""
+    import subprocess
+    from test_cabi_cpu import _build_shim_harness
+    r = subprocess.run([_build_shim_harness()], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = dict(l.split("=", 1) for l in r.stdout.splitlines() if "=" in l)
+    assert kv["converged"] == "1" and kv["from_normals_converged"] == "1"
+    T = np.array([float(x) for x in kv["T"].split(",")], dtype=np.float32).reshape(4, 4)
+    box = F.hollow_cube(); moved = box.copy(); moved[:, 0] += np.float32(0.05); moved[:, 1] += np.float32(0.05)
+    prm = oracle.default_params(transformation_epsilon=1e-3, corr_dist_threshold=1.0, max_iterations=20)
+    ref = oracle.gicp_align(moved, box, prm)
+    dt, dr = F.pose_delta(ref["T"], T)
+    assert dt <= TOL_T and dr <= TOL_R and int(kv["iterations"]) == ref["iterations"]
+    assert float(kv["output_err"]) < 1e-6
+    # initCompute() built no kd-tree of the target; the first search through getSearchMethodTarget() did
+    assert kv["tree_built_by_align"] == "0" and kv["tree_built_by_search"] == "1" and kv["batched_nn_agrees"] == "1"
+    assert abs(float(kv["fitness"]) - oracle.fitness(moved, box, T)) < 1e-6
+    # a refused target (NaN point) left the previous one in place on both sides of the seam
+    assert kv["target_kept"] == "1" and kv["same_pose_after_refused_target"] == "1"
+    assert "previous input kept" in r.stderr
+
+
 def test_shared_prepared_cloud_between_handles(oracle):
     """lb_gicp_prepare_source / share_source / set_target_cloud: handle B registers against the cloud handle A prepared
     as ITS source -- same bits as B building the target itself -- and the shared cloud stays intact when A moves on"""
