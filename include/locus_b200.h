@@ -271,6 +271,50 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
                     int mem_in, int mem_out);
 int lb_voxel_launch_count(lb_voxel* h, uint64_t* n);
 int lb_voxel_kernel_time(lb_voxel* h, float* ms_total_last_call);
+/* CUDA-event duration per call (first launch .. result available), averaged over the calls since the last reset */
+int lb_voxel_kernel_time_avg(lb_voxel* h, float* ms_avg, uint64_t* calls, int reset);
+
+/* ------------------------------------------------- resident rolling submap
+ * The local map LOCUS keeps in its external point_cloud_mapper object, resident in HBM, in the fixed frame:
+ *   lb_submap_insert      mapper_->InsertPoints(cloud, incremental)   locus/src/Locus.cc:464-465,531-532: a point enters
+ *                         the map iff no map point occupies its voxel (edge = `resolution`) yet; points are taken in
+ *                         input order, so within one call the first point of a voxel wins
+ *   lb_submap_neighbors   mapper_->ApproxNearestNeighbors(scan, neighbors)   Locus.cc:479-483: for every query point
+ *                         the nearest map point (EXACT here; ties -> lowest map index)
+ *   lb_submap_crop_box    mapper_->Refresh(current_pose)   Locus.cc:536-537, lo_settings.yaml:58 box_filter_size: keeps
+ *                         the points with |p - centre| <= half_size on every axis (pcl::CropBox bounds are inclusive)
+ *   lb_gicp_set_target_submap   the map itself as the registration target (BASELINE configs[2]): its voxel-hash index
+ *                         is rebuilt only after the map changed, and the k-NN covariance of a map point is computed
+ *                         once -- by the first registration after its insertion, from the map as it is then -- and
+ *                         cached until the point leaves the window.  (The reference recomputes every target
+ *                         covariance for every scan: setInputTarget clears them, gicp.h:196-200.)
+ * The mapper package is not vendored in the reference tree; its octree anchoring and the "approximate" of its
+ * nearest-neighbour search are therefore unpinned: voxels are world-anchored here (floor(p / resolution)).
+ * oracle/submap_oracle.py restates these semantics for the tests.  Map indices are insertion-order positions; they
+ * shift when a crop removes points.  One handle is used from one thread at a time. */
+typedef struct lb_submap lb_submap;
+int lb_submap_create(int device, float resolution, lb_submap** out);
+int lb_submap_destroy(lb_submap* m);
+int lb_submap_clear(lb_submap* m);
+/* pts: n points (float32 x,y,z at xyz_off, `stride` bytes apart), fixed frame.  n_inserted (nullable): points added.
+ * inserted_xyz (nullable): the added points, n_inserted x 3 float32, input order (capacity n; host or device like pts):
+ * the `incremental_points` output of InsertPoints.  Non-finite points are skipped. */
+int lb_submap_insert(lb_submap* m, const void* pts, size_t n, size_t stride, size_t xyz_off, int mem, size_t* n_inserted,
+                     float* inserted_xyz);
+int lb_submap_crop_box(lb_submap* m, const float* center3, float half_size, size_t* n_removed /* nullable */);
+int lb_submap_size(lb_submap* m, size_t* n);
+/* changes whenever the point set changed (insert that added points, crop that removed points, clear) */
+int lb_submap_generation(lb_submap* m, uint64_t* generation);
+/* the map's points, insertion order, n x 3 float32 */
+int lb_submap_points(lb_submap* m, float* xyz_out, size_t capacity_points, int mem);
+/* neighbors_xyz (nullable): n x 3 float32, the nearest map point of every query; idx / d2 (nullable): its map index and
+ * float32 squared distance.  All buffers host or all device (`mem`). */
+int lb_submap_neighbors(lb_submap* m, const void* query, size_t n, size_t stride, size_t xyz_off, float* neighbors_xyz,
+                        int32_t* idx, float* d2, int mem);
+int lb_submap_launch_count(lb_submap* m, uint64_t* n);
+/* the submap as target of `h` (same device; k_correspondences <= 20).  Call again after the map changed; while it is
+ * unchanged the call only checks the generation.  Uses h's k_correspondences / gicp_epsilon for the covariances. */
+int lb_gicp_set_target_submap(lb_gicp* h, lb_submap* m);
 
 /* ------------------------------------------------- scan-to-scan odometry pipeline
  * One robot's lidar stream, scans submitted in order: VoxelGrid(scan k) -> GICP(source = filtered k, target =

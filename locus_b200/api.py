@@ -72,6 +72,9 @@ SYMBOLS = [
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
     "lb_voxel_set_downsample_all_data", "lb_voxel_set_body_filter", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
+    "lb_voxel_kernel_time_avg",
+    "lb_submap_create", "lb_submap_destroy", "lb_submap_clear", "lb_submap_insert", "lb_submap_crop_box", "lb_submap_size",
+    "lb_submap_generation", "lb_submap_points", "lb_submap_neighbors", "lb_submap_launch_count", "lb_gicp_set_target_submap",
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
     "lb_odometry_set_gicp_params", "lb_odometry_set_cloud_sharing", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
     "lb_odometry_launch_count", "lb_odometry_stage_times",
@@ -150,6 +153,19 @@ def lib():
                                   C.POINTER(sz), vp, i32, i32]
     L.lb_voxel_launch_count.argtypes = [vp, u64p]
     L.lb_voxel_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lb_voxel_kernel_time_avg.argtypes = [vp, C.POINTER(C.c_float), u64p, i32]
+    if hasattr(L, "lb_submap_create"):
+        L.lb_submap_create.argtypes = [i32, C.c_float, C.POINTER(vp)]
+        L.lb_submap_destroy.argtypes = [vp]
+        L.lb_submap_clear.argtypes = [vp]
+        L.lb_submap_insert.argtypes = [vp, vp, sz, sz, sz, i32, C.POINTER(sz), vp]
+        L.lb_submap_crop_box.argtypes = [vp, vp, C.c_float, C.POINTER(sz)]
+        L.lb_submap_size.argtypes = [vp, C.POINTER(sz)]
+        L.lb_submap_generation.argtypes = [vp, u64p]
+        L.lb_submap_points.argtypes = [vp, vp, sz, i32]
+        L.lb_submap_neighbors.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32]
+        L.lb_submap_launch_count.argtypes = [vp, u64p]
+        L.lb_gicp_set_target_submap.argtypes = [vp, vp]
     if hasattr(L, "lb_odometry_create"):     # absent only in older builds loaded through LOCUS_B200_LIB for A/B runs
         L.lb_odometry_create.argtypes = [i32, i32, sz, C.c_uint32, C.POINTER(vp)]
         L.lb_odometry_destroy.argtypes = [vp]
@@ -268,6 +284,11 @@ class GicpB200:
         _check(lib().lb_gicp_set_target(self._h, p, n_, st, xo, no, mem, C.byref(gen)))
         self._keep["tgt"] = keep
         return gen.value
+
+    def setTargetSubmap(self, submap):
+        """the resident rolling submap as registration target (index + cached covariances live with the map)"""
+        _check(lib().lb_gicp_set_target_submap(self._h, submap._h))
+        self._keep["tgt"] = submap
 
     def promoteSourceToTarget(self):
         _check(lib().lb_gicp_promote_source_to_target(self._h))
@@ -471,6 +492,83 @@ class VoxelGridB200:
         ms = C.c_float(0)
         lib().lb_voxel_kernel_time(self._h, C.byref(ms))
         return ms.value
+
+    def avgCallMs(self, reset=True):
+        """mean CUDA-event duration of the filter calls since the last reset"""
+        ms = C.c_float(0); n = C.c_uint64(0)
+        lib().lb_voxel_kernel_time_avg(self._h, C.byref(ms), C.byref(n), int(reset))
+        return ms.value
+
+
+class SubmapB200:
+    """Mirror of the mapper object LOCUS drives (locus/src/Locus.cc:464-465,479-486,522-543): InsertPoints,
+    ApproxNearestNeighbors, Refresh -- resident on the GPU, and usable as a GICP target (GicpB200.setTargetSubmap)."""
+
+    def __init__(self, device=0, resolution=0.05):
+        self._h = C.c_void_p()
+        _check(lib().lb_submap_create(device, np.float32(resolution), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lb_submap_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def Clear(self):
+        _check(lib().lb_submap_clear(self._h))
+
+    def InsertPoints(self, cloud, want_incremental=False):
+        """cloud: (n, >=3) float32, fixed frame.  returns the number of points added [, the added points (m, 3)]"""
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        n_ins = C.c_size_t(0)
+        inc = np.zeros((max(len(a), 1), 3), dtype=np.float32) if want_incremental else None
+        _check(lib().lb_submap_insert(self._h, _ptr(a), a.shape[0], a.shape[1] * 4, 0, LB_MEM_HOST, C.byref(n_ins), _ptr(inc)))
+        return (n_ins.value, inc[: n_ins.value]) if want_incremental else n_ins.value
+
+    def insert_device(self, ptr, n, stride, xyz_off=0):
+        n_ins = C.c_size_t(0)
+        _check(lib().lb_submap_insert(self._h, C.c_void_p(int(ptr)), n, stride, xyz_off, LB_MEM_DEVICE, C.byref(n_ins), None))
+        return n_ins.value
+
+    def Refresh(self, center, half_size):
+        """sliding window: keep the points inside the box centre +- half_size; returns the number removed"""
+        c = np.ascontiguousarray(center, dtype=np.float32).reshape(3)
+        n = C.c_size_t(0)
+        _check(lib().lb_submap_crop_box(self._h, _ptr(c), np.float32(half_size), C.byref(n)))
+        return n.value
+
+    def size(self):
+        n = C.c_size_t(0)
+        _check(lib().lb_submap_size(self._h, C.byref(n)))
+        return n.value
+
+    def generation(self):
+        g = C.c_uint64(0)
+        _check(lib().lb_submap_generation(self._h, C.byref(g)))
+        return g.value
+
+    def points(self):
+        out = np.zeros((self.size(), 3), dtype=np.float32)
+        _check(lib().lb_submap_points(self._h, _ptr(out), out.shape[0], LB_MEM_HOST))
+        return out
+
+    def ApproxNearestNeighbors(self, cloud):
+        """(neighbors (n, 3), idx int32, d2 float32): the nearest map point of every point of `cloud`"""
+        q = np.ascontiguousarray(cloud, dtype=np.float32)
+        nb = np.zeros((q.shape[0], 3), dtype=np.float32)
+        idx = np.zeros(q.shape[0], dtype=np.int32); d2 = np.zeros(q.shape[0], dtype=np.float32)
+        _check(lib().lb_submap_neighbors(self._h, _ptr(q), q.shape[0], q.shape[1] * 4, 0, _ptr(nb), _ptr(idx), _ptr(d2), LB_MEM_HOST))
+        return nb, idx, d2
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        lib().lb_submap_launch_count(self._h, C.byref(n))
+        return n.value
 
 
 class OdometryB200:

@@ -1211,3 +1211,5 @@ int lb_gicp_reset_kernel_times(lb_gicp* h, int enable) {
 }
 
 }  // extern "C"
+
+#include "submap.cuh"

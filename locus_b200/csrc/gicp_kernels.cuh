@@ -286,6 +286,7 @@ struct CovFin {
   double eps;
   double* cov;
   double sum[3], m2[6];
+  __device__ __forceinline__ bool skip(const f4&) const { return false; }
   __device__ __forceinline__ void reset() {
     sum[0] = sum[1] = sum[2] = 0.0;
     m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
@@ -306,10 +307,39 @@ struct CovFin {
   }
 };
 
+// Rolling submap (row f3): covariances only for the points inserted since the last pass (original index >= first_new),
+// written into the submap's per-point cache in ORIGINAL (insertion) order; the other queries leave at once.
+struct CovFinIncr {
+  double eps;
+  double* cache;       // insertion order, 6 per point
+  int first_new;
+  double sum[3], m2[6];
+  __device__ __forceinline__ bool skip(const f4& q) const { return float_to_bits(q.w) < first_new; }
+  __device__ __forceinline__ void reset() {
+    sum[0] = sum[1] = sum[2] = 0.0;
+    m2[0] = m2[1] = m2[2] = m2[3] = m2[4] = m2[5] = 0.0;
+  }
+  __device__ __forceinline__ void add(const f4& pt) {
+    sum[0] += pt.x; sum[1] += pt.y; sum[2] += pt.z;
+    m2[0] += pt.x * pt.x; m2[1] += pt.y * pt.x; m2[2] += pt.y * pt.y;
+    m2[3] += pt.z * pt.x; m2[4] += pt.z * pt.y; m2[5] += pt.z * pt.z;
+  }
+  __device__ __forceinline__ void finish(uint32_t, const f4& q, int k, bool writer) {
+    double out[6];
+    cov_from_moments(sum, m2, k, eps, out);
+    if (writer) {
+      double* d = cache + 6 * (size_t)float_to_bits(q.w);
+#pragma unroll
+      for (int e = 0; e < 6; e++) d[e] = out[e];
+    }
+  }
+};
+
 struct NormalFin {
   float vp[3];
   f4* out;            // original order: (nx, ny, nz, curvature)
   NormalAccum acc;
+  __device__ __forceinline__ bool skip(const f4&) const { return false; }
   __device__ __forceinline__ void reset() { acc.reset(); }
   __device__ __forceinline__ void add(const f4& pt) { acc.add(pt.x, pt.y, pt.z); }
   __device__ __forceinline__ void finish(uint32_t, const f4& q, int k, bool writer) {
@@ -373,6 +403,7 @@ __device__ __forceinline__ void knn_quad_query(const GridView& g, const f4* __re
                                                uint32_t* m_d, uint32_t* m_o) {
   if (s >= (uint32_t)g.n) return;   // whole quads exit together
   f4 q = g.pts[s];
+  if (fin.skip(q)) return;          // (the four lanes of a quad share the query)
   RegList<K> L;
   L.init();
   int cx, cy, cz; float minfrac;
@@ -1350,6 +1381,133 @@ ap_accumulate_kernel(ApArgs a, double* __restrict__ partials /*[grid][21]*/) {
   }
   double tot = block_reduce<21, 8, 0>(acc, red);
   if (threadIdx.x < 21) partials[21 * (size_t)blockIdx.x + threadIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------ row f3: resident rolling submap
+// cell-sorted covariances of a cloud from a per-point cache kept in original (insertion) order
+__global__ void __launch_bounds__(256)
+cov_gather_kernel(const f4* __restrict__ pts, uint32_t n, const double* __restrict__ cache, double* __restrict__ cov) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t s = t / 6, e = t - 6 * s;
+  if (s >= n) return;
+  cov[6 * (size_t)s + e] = cache[6 * (size_t)float_to_bits(pts[s].w) + e];
+}
+
+// Occupancy hash of the submap: one entry per occupied voxel of edge `res` (world-anchored: voxel = floor(p / res)),
+// open addressing, 64-bit key = the three voxel coordinates (21 bits each, offset 2^20), owner = map index of the
+// point that occupies the voxel.  InsertPoints semantics of the reference's mapper (Locus.cc:465,532: a point enters
+// the map iff no map point occupies its voxel yet; points are visited in input order) made parallel: candidates claim
+// their voxel with atomicMin on (0x80000000 | input index) -- a committed owner (< 2^31) always wins, otherwise the
+// lowest input index does, which is what the sequential loop yields.
+constexpr unsigned long long SM_EMPTY = ~0ull;
+__device__ __forceinline__ bool sm_voxel_key(float x, float y, float z, float res, unsigned long long& key) {
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) return false;
+  const float fx = floorf(x / res), fy = floorf(y / res), fz = floorf(z / res);
+  const float LIM = 1048575.0f;      // 2^20 - 1
+  if (fx < -LIM || fx > LIM || fy < -LIM || fy > LIM || fz < -LIM || fz > LIM) return false;
+  const unsigned long long cx = (unsigned long long)((int)fx + 1048576), cy = (unsigned long long)((int)fy + 1048576),
+                           cz = (unsigned long long)((int)fz + 1048576);
+  key = (cx << 42) | (cy << 21) | cz;
+  return true;
+}
+__device__ __forceinline__ uint32_t sm_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+// slot of `key`, claiming an empty one when it is not in the table yet
+__device__ __forceinline__ uint32_t sm_find_or_claim(unsigned long long* __restrict__ keys, uint32_t mask, unsigned long long key) {
+  uint32_t slot = sm_hash(key) & mask;
+  for (;;) {
+    const unsigned long long cur = atomicCAS(&keys[slot], SM_EMPTY, key);
+    if (cur == SM_EMPTY || cur == key) return slot;
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sm_claim_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, float res,
+                unsigned long long* __restrict__ keys, uint32_t* __restrict__ owner, uint32_t mask, uint32_t* __restrict__ slot_of) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(base + (size_t)i * stride + xyz_off);
+  unsigned long long key;
+  uint32_t slot = 0xffffffffu;
+  if (sm_voxel_key(p[0], p[1], p[2], res, key)) {
+    slot = sm_find_or_claim(keys, mask, key);
+    atomicMin(&owner[slot], 0x80000000u | i);
+  }
+  slot_of[i] = slot;
+}
+
+__global__ void __launch_bounds__(256)
+sm_decide_kernel(const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ owner, uint32_t n, uint32_t* __restrict__ flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = slot_of[i];
+  flags[i] = (s != 0xffffffffu && owner[s] == (0x80000000u | i)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+sm_commit_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, const uint32_t* __restrict__ slot_of,
+                 const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t n_old, f4* __restrict__ pts,
+                 uint32_t* __restrict__ owner, float* __restrict__ inserted_xyz /*nullable*/) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  const float* p = reinterpret_cast<const float*>(base + (size_t)i * stride + xyz_off);
+  const uint32_t j = n_old + pos[i];
+  pts[j] = f4{p[0], p[1], p[2], 1.0f};
+  owner[slot_of[i]] = j;
+  if (inserted_xyz) { inserted_xyz[3 * (size_t)pos[i]] = p[0]; inserted_xyz[3 * (size_t)pos[i] + 1] = p[1]; inserted_xyz[3 * (size_t)pos[i] + 2] = p[2]; }
+}
+
+// rebuild of the table from the map's points (after a crop, or when the table grows)
+__global__ void __launch_bounds__(256)
+sm_rehash_kernel(const f4* __restrict__ pts, uint32_t n, float res, unsigned long long* __restrict__ keys,
+                 uint32_t* __restrict__ owner, uint32_t mask) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const f4 p = pts[j];
+  unsigned long long key;
+  if (!sm_voxel_key(p.x, p.y, p.z, res, key)) return;
+  owner[sm_find_or_claim(keys, mask, key)] = j;      // one map point per voxel: no two writers
+}
+
+// Refresh(current_pose) of the sliding-window mapper (Locus.cc:537, lo_settings.yaml:58 box_filter_size): pcl::CropBox
+// keeps min <= p <= max, box = centre +- half
+__global__ void __launch_bounds__(256)
+sm_crop_flags_kernel(const f4* __restrict__ pts, uint32_t n, float cx, float cy, float cz, float half, uint32_t* __restrict__ flags) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const f4 p = pts[j];
+  const float mnx = cx - half, mny = cy - half, mnz = cz - half, mxx = cx + half, mxy = cy + half, mxz = cz + half;
+  const bool out = (p.x < mnx || p.y < mny || p.z < mnz) || (p.x > mxx || p.y > mxy || p.z > mxz);
+  flags[j] = out ? 0u : 1u;
+}
+__global__ void __launch_bounds__(256)
+sm_compact_kernel(const f4* __restrict__ pts, const double* __restrict__ cov, uint32_t n, uint32_t n_cov,
+                  const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, f4* __restrict__ pts_out,
+                  double* __restrict__ cov_out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || !flags[j]) return;
+  const uint32_t d = pos[j];
+  pts_out[d] = pts[j];
+  if (j < n_cov) {
+#pragma unroll
+    for (int e = 0; e < 6; e++) cov_out[6 * (size_t)d + e] = cov[6 * (size_t)j + e];
+  }
+}
+__global__ void __launch_bounds__(256) iota_kernel(int32_t* __restrict__ a, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+// neighbours[i] = xyz of map point idx[i] (ApproxNearestNeighbors output cloud, Locus.cc:479)
+__global__ void __launch_bounds__(256)
+sm_gather_xyz_kernel(const f4* __restrict__ pts, const int32_t* __restrict__ idx, uint32_t n, float* __restrict__ out_xyz) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = idx[i];
+  f4 p = (j >= 0) ? pts[j] : f4{0.f, 0.f, 0.f, 0.f};
+  out_xyz[3 * (size_t)i] = p.x; out_xyz[3 * (size_t)i + 1] = p.y; out_xyz[3 * (size_t)i + 2] = p.z;
 }
 
 // ------------------------------------------------------------------ fitness (a9)

@@ -317,7 +317,21 @@ vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint3
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t t0 = r0; t0 < r1; t0 += VG4_TILE) {
     const uint32_t t1 = min(r1, t0 + (uint32_t)VG4_TILE);
-    for (uint32_t i = t0 + lane; i < t1; i += 32) tile[wib][i - t0] = rec[vals[i]];
+    // a tile is 8 records per lane: all 8 point numbers, then all 8 records, are in flight at once (a loop of
+    // load -> store pairs would expose one memory latency per record)
+    {
+      uint32_t pv[VG4_TILE / 32];
+      float4 rv[VG4_TILE / 32];
+#pragma unroll
+      for (int u = 0; u < VG4_TILE / 32; u++) {
+        const uint32_t i = t0 + lane + 32u * u;
+        pv[u] = (i < t1) ? vals[i] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < VG4_TILE / 32; u++) rv[u] = (pv[u] != 0xffffffffu) ? rec[pv[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < VG4_TILE / 32; u++) tile[wib][lane + 32 * u] = rv[u];
+    }
     __syncwarp();
     if (seg) {
       uint32_t lo = max(a, t0), hi = min(e, t1);
@@ -437,6 +451,8 @@ struct lb_voxel {
   ScanWork scan;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float t_last_ms = 0.f;
+  double t_sum_ms = 0.0;        // since the last lb_voxel_kernel_time_avg(reset)
+  uint64_t t_calls = 0;
 };
 
 static int voxel_create_impl(int device, void* stream, bool ext, lb_voxel** out) {
@@ -512,6 +528,13 @@ int lb_voxel_set_min_points_per_voxel(lb_voxel* h, int m) { if (!h) return LB_ER
 int lb_voxel_set_downsample_all_data(lb_voxel* h, int all) { if (!h) return LB_ERR_INVALID_ARG; h->downsample_all = all ? 1 : 0; return LB_OK; }
 int lb_voxel_launch_count(lb_voxel* h, uint64_t* n) { if (!h || !n) return LB_ERR_INVALID_ARG; *n = h->c.launches; return LB_OK; }
 int lb_voxel_kernel_time(lb_voxel* h, float* ms) { if (!h || !ms) return LB_ERR_INVALID_ARG; *ms = h->t_last_ms; return LB_OK; }
+int lb_voxel_kernel_time_avg(lb_voxel* h, float* ms_avg, uint64_t* calls, int reset) {
+  if (!h || !ms_avg) return LB_ERR_INVALID_ARG;
+  *ms_avg = h->t_calls ? (float)(h->t_sum_ms / (double)h->t_calls) : 0.f;
+  if (calls) *calls = h->t_calls;
+  if (reset) { h->t_sum_ms = 0.0; h->t_calls = 0; }
+  return LB_OK;
+}
 
 int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t point_step, const lb_field* fields,
                     int n_fields, const int32_t* indices, size_t n_indices, uint8_t* out, size_t out_capacity_pts,
@@ -642,6 +665,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
     LB_CUDA(cudaStreamSynchronize(c.stream));
   }
   cudaEventElapsedTime(&h->t_last_ms, h->ev0, h->ev1);
+  h->t_sum_ms += h->t_last_ms; h->t_calls++;
   *n_out = m;
   return LB_OK;
 }

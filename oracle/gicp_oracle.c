@@ -279,6 +279,15 @@ typedef struct {
   long n_evals;
 } functor_ctx;
 
+/* Summation-order probe (tests / studies only; 0 = the reference's order, one serial loop, gicp.hpp:298,331,373).
+ * With chunk = c > 0 the 13 sums are formed as partial sums over blocks of c consecutive correspondences which are
+ * then added in block order: the SAME terms, the SAME arithmetic, only the association of the additions differs (what
+ * any vectorised or parallel build of the reference does).  It exists to measure how far the reference's own result
+ * moves under such a reassociation: where its BFGS line search stalls on the float32 noise floor of the objective,
+ * the last bits of f decide the branch and the final pose moves by up to millimetres (DESIGN.md "Numerics"). */
+static int g_sum_chunk = 0;
+void og_set_sum_chunk(int c) { g_sum_chunk = c > 0 ? c : 0; }
+
 static void functor_core(const functor_ctx* c, const double* x, double* f_out, double* g_out) {
   float T[16];
   og_gicp_apply_state(x, T); /* base_transformation_ = I (gicp.hpp:435) */
@@ -286,6 +295,28 @@ static void functor_core(const functor_ctx* c, const double* x, double* f_out, d
   double gt[3] = {0, 0, 0};
   double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   const int m = c->m;
+  if (g_sum_chunk > 0) {
+    for (int b = 0; b < m; b += g_sum_chunk) {
+      double fb = 0, gb[3] = {0, 0, 0}, Rb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const int e = b + g_sum_chunk < m ? b + g_sum_chunk : m;
+      for (int i = b; i < e; i++) {
+        const float* ps = &c->src4[4 * (size_t)i];
+        const float* pt = &c->tgt4[4 * (size_t)i];
+        const double* M = &c->M[9 * (size_t)i];
+        float pp[3];
+        xform4f(T, ps, pp);
+        double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
+        double temp[3];
+        for (int r = 0; r < 3; r++) temp[r] = (M[r * 3 + 0] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
+        fb += (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
+        gb[0] += temp[0]; gb[1] += temp[1]; gb[2] += temp[2];
+        for (int r = 0; r < 3; r++)
+          for (int cc = 0; cc < 3; cc++) Rb[r * 3 + cc] += (double)ps[r] * temp[cc];
+      }
+      f += fb; gt[0] += gb[0]; gt[1] += gb[1]; gt[2] += gb[2];
+      for (int k = 0; k < 9; k++) R[k] += Rb[k];
+    }
+  } else
   for (int i = 0; i < m; i++) {
     const float* ps = &c->src4[4 * (size_t)i];
     const float* pt = &c->tgt4[4 * (size_t)i];
@@ -486,6 +517,12 @@ og_gicp_target* og_gicp_target_prepare(const float* tgt, int n_tgt, int tgt_stri
     cov_knn(tgt, n_tgt, tgt_stride_f, t->tree, P->k_correspondences, P->gicp_epsilon,
             P->num_threads > 0 ? P->num_threads : 1, t->cov);
   return t;
+}
+
+/* covariances supplied by the caller (n x 9 doubles) instead of computed from the target as it is now: the rolling
+ * submap caches each point's covariance from the time of its insertion (oracle/submap_oracle.py) */
+void og_gicp_target_set_covariances(og_gicp_target* t, const double* cov9) {
+  if (t && cov9) memcpy(t->cov, cov9, sizeof(double) * 9 * (size_t)t->n);
 }
 
 void og_gicp_target_free(og_gicp_target* t) {

@@ -107,10 +107,15 @@ int og_gicp_align(const float* src, int n_src, int src_stride_f, int src_normal_
 typedef struct og_gicp_target og_gicp_target;
 og_gicp_target* og_gicp_target_prepare(const float* tgt, int n_tgt, int tgt_stride_f, int tgt_normal_off_f,
                                        const og_gicp_params* params);
+void og_gicp_target_set_covariances(og_gicp_target* t, const double* cov9 /* n x 9 */);
 void og_gicp_target_free(og_gicp_target* t);
 int og_gicp_align_prepared(const float* src, int n_src, int src_stride_f, int src_normal_off_f,
                            const og_gicp_target* target, const og_gicp_params* params, const float* guess,
                            og_gicp_result* result);
+
+/* Summation-order probe for studies: 0 (default) = the reference's single serial loop; c > 0 = partial sums over blocks of
+ * c correspondences, added in block order (same terms, other association).  Process-global; see gicp_oracle.c. */
+void og_set_sum_chunk(int c);
 
 /* k-NN covariances only (gicp.hpp:85-154). cov_out: n x 9 doubles. */
 int og_gicp_covariances(const float* pts, int n, int stride_f, int k,

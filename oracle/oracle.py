@@ -70,6 +70,7 @@ def lib():
         L.og_gicp_target_prepare.restype = C.c_void_p
         L.og_gicp_target_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(GicpParams)]
         L.og_gicp_target_free.argtypes = [C.c_void_p]
+        L.og_gicp_target_set_covariances.argtypes = [C.c_void_p, C.c_void_p]
         L.og_gicp_align_prepared.restype = C.c_int
         L.og_gicp_align_prepared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(GicpParams),
                                              C.c_void_p, C.POINTER(GicpResult)]
@@ -164,12 +165,17 @@ class PreparedTarget:
     """setInputTarget once, align many sources against it (the reference keeps the target's kd-tree and covariances
     until the next setInputTarget): the unchanged-submap case of BASELINE configs[2]."""
 
-    def __init__(self, tgt, params, tgt_normal_off=-1):
+    def __init__(self, tgt, params, tgt_normal_off=-1, cov=None):
+        """cov (n, 3, 3): use these target covariances instead of computing them from the target as it is now"""
         self.tgt = _as_cloud(tgt)
         self.h = lib().og_gicp_target_prepare(_p(self.tgt), self.tgt.shape[0], self.tgt.shape[1], tgt_normal_off,
                                               C.byref(params))
         if not self.h:
             raise ValueError("og_gicp_target_prepare: empty target or fewer points than k_correspondences")
+        if cov is not None:
+            c = np.ascontiguousarray(cov, dtype=np.float64).reshape(-1, 9)
+            assert c.shape[0] == self.tgt.shape[0]
+            lib().og_gicp_target_set_covariances(self.h, _p(c))
 
     def align(self, src, params, guess=None, src_normal_off=-1):
         src = _as_cloud(src)
@@ -186,6 +192,12 @@ class PreparedTarget:
 
     def __del__(self):
         self.close()
+
+
+def set_sum_chunk(c):
+    """summation-order probe (og_set_sum_chunk): 0 = the reference's serial order"""
+    lib().og_set_sum_chunk.argtypes = [C.c_int]
+    lib().og_set_sum_chunk(int(c))
 
 
 def covariances(pts, k=20, eps=1e-3, num_threads=1):
