@@ -339,8 +339,8 @@ def pick_cpu_threads(O, probe):
     return best
 
 
-PROBE_PAIRS = 40        # scans per config on which the reference's own sensitivity to summation order is measured
-PROBE_CHUNKS = (512, 4096)
+PROBE_PAIRS = 30        # scans per config on which the reference's own sensitivity to summation order is measured
+PROBE_CHUNKS = (64, 256, 1024, 4096, 16384)
 
 
 def run_cpu_arm(args, cfg, data, budget_s=None, max_steps=None, rebuild_target=False, probe=None):

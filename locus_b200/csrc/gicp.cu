@@ -1183,6 +1183,8 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
     return LB_OK;
   }
   if (!strcmp(name, "probe_rounds")) { *ms_avg = (float)h->probe_rounds; return LB_OK; }
+  if (!strcmp(name, "dbuf_allocs")) { *ms_avg = (float)dbuf_alloc_count(); return LB_OK; }   // device allocations so far (process-wide)
+  if (!strcmp(name, "pool_clouds")) { *ms_avg = (float)h->pool.size(); return LB_OK; }
   if (!strcmp(name, "cell_src")) { *ms_avg = h->src->geom.h; return LB_OK; }      // cell size of the current index (m)
   if (!strcmp(name, "cell_tgt")) { *ms_avg = h->tgt->geom.h; return LB_OK; }
   if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100

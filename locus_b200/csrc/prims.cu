@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+unsigned long long& dbuf_alloc_count() { static unsigned long long n = 0; return n; }
 
 int ctx_init(Ctx& c, int device, void* external_stream, bool use_external) {
   int n = 0;

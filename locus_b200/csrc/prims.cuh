@@ -43,12 +43,16 @@ struct Ctx {
 int ctx_init(Ctx& c, int device, void* external_stream, bool use_external);
 void ctx_destroy(Ctx& c);
 
+// device allocations made by DBuf::ensure since the library was loaded (a steady-state call path must not add any)
+unsigned long long& dbuf_alloc_count();
+
 template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t cap = 0;
   int ensure(size_t n) {
     if (n <= cap) return LB_OK;
+    dbuf_alloc_count()++;
     size_t nc = cap ? cap : 1024;
     while (nc < n) nc = nc + nc / 2 + 1024;
     if (p) LB_CUDA(cudaFree(p));

@@ -489,7 +489,7 @@ def test_from_normals_covariances(oracle, execution):
     res = g.align()
     Ti = np.linalg.inv(g.getFinalTransformation().astype(np.float64))
     assert res.converged and g.getFitnessScore() < 0.1
-    assert abs(Ti[0, 3] + 0.05) < 1e-2 and abs(Ti[1, 3] + 0.05) < 1e-2 and abs(Ti[2, 3]) < 1e-2
+    assert abs(Ti[0, 3] - 0.05) < 1e-2 and abs(Ti[1, 3] - 0.05) < 1e-2 and abs(Ti[2, 3]) < 1e-2
     # a cloud WITHOUT normals in from-normals mode falls back to k-NN covariances (documented in locus_b200.h)
     g.setInputSource(src_a[:, :3].copy())
     g.align()
