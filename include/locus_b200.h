@@ -38,6 +38,8 @@
  *                                 point_cloud_localization/src/utils.cc:106-128, PointCloudLocalization.cc:694-750
  *   lb_gicp_compute_normals       NormalComputation::filter, k-NN mode (pcl::NormalEstimationOMP)
  *                                 point_cloud_filter/src/normal_computation.cc:26-59
+ *   lb_gicp_compute_normals_radius   the same nodelet in its radius mode + removeNaNNormalsFromPointCloud
+ *                                 normal_computation.cc:53-57,73-77
  *   lb_voxel_create/destroy       pcl::VoxelGrid<pcl::PCLPointCloud2> impl_
  *                                 point_cloud_filter/include/point_cloud_filter/custom_voxel_grid.h:25
  *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
@@ -213,9 +215,17 @@ int lb_gicp_point2plane_information(lb_gicp* h, const void* query, size_t n, siz
  * as source (which = 0) or target (which = 1): the k nearest neighbours (itself included) -> PCL's float32
  * mean/covariance -> eigenvector of the smallest eigenvalue (PCL eigen33) -> flipped towards `viewpoint` (NULL = the
  * origin, what fromROSMsg leaves in sensor_origin_).  out4: n x (normal_x, normal_y, normal_z, curvature) float32 in
- * the caller's point order, host or device.  3 <= k <= 20.  The radius mode of the nodelet is not implemented
- * (LB_ERR_UNSUPPORTED is never returned silently: there is no such entry point). */
+ * the caller's point order, host or device.  3 <= k <= 20.  (Radius mode: lb_gicp_compute_normals_radius.) */
 int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint, float* out4, int mem);
+/* The nodelet's radius mode (normal_computation.cc:73-77, norm_est_.setRadiusSearch(normal_search_radius)) together
+ * with the NaN-normal removal that follows it (:53-57, pcl::removeNaNNormalsFromPointCloud).  Neighbourhood of a point =
+ * every point with squared distance < float(radius^2) (FLANN's strict compare), itself included, taken in ascending
+ * distance order; fewer than three neighbours -> NaN normal and curvature (pcl::computePointNormal).  out4: n x 4 as
+ * above (NaN rows included); valid_idx (nullable, capacity n): ascending indices of the points whose normal is finite,
+ * i.e. the points of the nodelet's output cloud; n_valid (nullable): their number.  LB_ERR_CAPACITY when a neighbourhood
+ * exceeds 2048 points. */
+int lb_gicp_compute_normals_radius(lb_gicp* h, int which, double radius, const float* viewpoint, float* out4,
+                                   int32_t* valid_idx, size_t* n_valid, int mem);
 /* covariances used by the last align, n x 9 doubles row-major, original point order. which: 0 source, 1 target */
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points);
 /* number of points currently indexed. which: 0 source, 1 target */
@@ -269,6 +279,27 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
                     const lb_field* fields, int n_fields, const int32_t* indices, size_t n_indices,
                     uint8_t* out, size_t out_capacity_pts, size_t* n_out, int32_t* out_voxel_idx,
                     int mem_in, int mem_out);
+/* SURVEY 8f row f4, the rest of the front end folded into the filter's loads.
+ * lb_voxel_set_input_passthrough: what each lidar's pcl/PassThrough nodelet does before everything else
+ *   (locus/launch/locus.launch:90-133: filter_field_name z, limits [-100, 100], output_frame base_link): points that
+ *   are not finite or whose field lies outside [min, max] (inside, when negative) are dropped -- tested on the RAW
+ *   value, in the sensor frame, before the input's transform is applied.  field_name NULL or "" = off (default).
+ * lb_voxel_filter_merged: 1..3 input clouds treated as one, in the order a, b, c -- the concatenation
+ *   point_cloud_merger performs (point_cloud_merger/src/PointCloudMerger.cc:150-178: a + (b + c)); `transform`
+ *   (row-major 4x4 float, NULL = identity) is the sensor -> base_link transform the PassThrough nodelet applies to its
+ *   output (pcl_ros::transformPointCloud: Eigen Matrix4f * Vector4f per point).  Then, on the transformed
+ *   coordinates: the BodyFilter box, the VoxelGrid limits and the grid itself, exactly as lb_voxel_filter.  Needs the
+ *   x, y, z, intensity layout (four averaged FLOAT32 fields) when more than one input or a transform is given.
+ *   The merger's optional random / radius-outlier filters (off in the shipped config) are not part of this call. */
+typedef struct lb_voxel_input {
+  const uint8_t* data;        /* n_pts points of point_step bytes (host or device: mem_in) */
+  size_t n_pts;
+  const float* transform;     /* 16 floats, row-major; NULL = identity */
+} lb_voxel_input;
+int lb_voxel_set_input_passthrough(lb_voxel* h, const char* field_name, double limit_min, double limit_max, int negative);
+int lb_voxel_filter_merged(lb_voxel* h, const lb_voxel_input* inputs, int n_inputs, uint32_t point_step,
+                           const lb_field* fields, int n_fields, uint8_t* out, size_t out_capacity_pts, size_t* n_out,
+                           int32_t* out_voxel_idx, int mem_in, int mem_out);
 int lb_voxel_launch_count(lb_voxel* h, uint64_t* n);
 int lb_voxel_kernel_time(lb_voxel* h, float* ms_total_last_call);
 /* CUDA-event duration per call (first launch .. result available), averaged over the calls since the last reset */

@@ -56,6 +56,10 @@ class OdometryResult(C.Structure):
                 ("gicp", GicpResult), ("error", C.c_char * 160)]
 
 
+class VoxelInput(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n_pts", C.c_size_t), ("transform", C.c_void_p)]
+
+
 class Field(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
 
@@ -67,12 +71,12 @@ SYMBOLS = [
     "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
     "lb_gicp_promote_source_to_target", "lb_gicp_prepare_source", "lb_gicp_share_source", "lb_gicp_set_target_cloud",
     "lb_cloud_release", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
-    "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_compute_normals", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
+    "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_compute_normals", "lb_gicp_compute_normals_radius", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
     "lb_voxel_create", "lb_voxel_create_on_stream", "lb_voxel_destroy", "lb_voxel_set_leaf_size",
     "lb_voxel_get_leaf_size", "lb_voxel_set_filter_limits", "lb_voxel_set_min_points_per_voxel",
     "lb_voxel_set_downsample_all_data", "lb_voxel_set_body_filter", "lb_voxel_filter", "lb_voxel_launch_count", "lb_voxel_kernel_time",
-    "lb_voxel_kernel_time_avg",
+    "lb_voxel_kernel_time_avg", "lb_voxel_set_input_passthrough", "lb_voxel_filter_merged",
     "lb_submap_create", "lb_submap_destroy", "lb_submap_clear", "lb_submap_insert", "lb_submap_crop_box", "lb_submap_size",
     "lb_submap_generation", "lb_submap_points", "lb_submap_neighbors", "lb_submap_launch_count", "lb_gicp_set_target_submap",
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
@@ -135,6 +139,8 @@ def lib():
     L.lb_gicp_get_covariances.argtypes = [vp, i32, vp, sz]
     if hasattr(L, "lb_gicp_compute_normals"):
         L.lb_gicp_compute_normals.argtypes = [vp, i32, i32, vp, vp, i32]
+    if hasattr(L, "lb_gicp_compute_normals_radius"):
+        L.lb_gicp_compute_normals_radius.argtypes = [vp, i32, C.c_double, vp, vp, vp, C.POINTER(sz), i32]
     L.lb_gicp_cloud_size.argtypes = [vp, i32, C.POINTER(sz)]
     L.lb_gicp_launch_count.argtypes = [vp, u64p]
     L.lb_gicp_kernel_time.argtypes = [vp, C.c_char_p, C.POINTER(C.c_float), u64p]
@@ -151,6 +157,10 @@ def lib():
         L.lb_voxel_set_body_filter.argtypes = [vp, i32, vp, vp, C.c_float]
     L.lb_voxel_filter.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(Field), i32, vp, sz, vp, sz,
                                   C.POINTER(sz), vp, i32, i32]
+    if hasattr(L, "lb_voxel_filter_merged"):
+        L.lb_voxel_set_input_passthrough.argtypes = [vp, C.c_char_p, C.c_double, C.c_double, i32]
+        L.lb_voxel_filter_merged.argtypes = [vp, C.POINTER(VoxelInput), i32, C.c_uint32, C.POINTER(Field), i32, vp, sz,
+                                             C.POINTER(sz), vp, i32, i32]
     L.lb_voxel_launch_count.argtypes = [vp, u64p]
     L.lb_voxel_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
     L.lb_voxel_kernel_time_avg.argtypes = [vp, C.POINTER(C.c_float), u64p, i32]
@@ -385,6 +395,17 @@ class GicpB200:
         _check(lib().lb_gicp_compute_normals(self._h, which, int(k), _ptr(vp_), _ptr(out), LB_MEM_HOST))
         return out
 
+    def computeNormalsRadius(self, which=0, radius=0.3, viewpoint=None):
+        """NormalComputation nodelet, radius mode + NaN-normal removal: ((n, 4) float32 normals with NaN rows where a
+        point has fewer than 3 neighbours, int32 indices of the points the nodelet keeps)"""
+        n = self.cloudSize(which)
+        out = np.zeros((n, 4), dtype=np.float32)
+        vi = np.zeros(max(n, 1), dtype=np.int32)
+        m = C.c_size_t(0)
+        vp_ = None if viewpoint is None else np.ascontiguousarray(viewpoint, dtype=np.float32)
+        _check(lib().lb_gicp_compute_normals_radius(self._h, which, float(radius), _ptr(vp_), _ptr(out), _ptr(vi), C.byref(m), LB_MEM_HOST))
+        return out, vi[: m.value]
+
     def launchCount(self):
         n = C.c_uint64(0)
         lib().lb_gicp_launch_count(self._h, C.byref(n))
@@ -470,6 +491,33 @@ class VoxelGridB200:
         fa = self._fields(fields)
         _check(lib().lb_voxel_filter(self._h, _ptr(blob), n, point_step, fa, len(fields), None, 0, _ptr(out), n,
                                      C.byref(n_out), _ptr(vidx), LB_MEM_HOST, LB_MEM_HOST))
+        m = n_out.value
+        o = out[: m * point_step].reshape(m, point_step)
+        return (o, vidx[:m]) if want_voxel_idx else o
+
+    def setInputPassThrough(self, field_name, lo, hi, negative=False):
+        """the per-lidar pcl/PassThrough nodelet (raw field limits in the sensor frame + NaN removal) folded into the loads"""
+        _check(lib().lb_voxel_set_input_passthrough(self._h, field_name.encode() if field_name else None, lo, hi, int(bool(negative))))
+
+    def filterMerged(self, blobs, point_step, fields, transforms=None, want_voxel_idx=False):
+        """1..3 clouds (uint8 host arrays) taken as one in the order given (point_cloud_merger), each optionally
+        transformed by a 4x4 sensor -> base_link matrix; returns like filter()"""
+        blobs = [np.ascontiguousarray(b, dtype=np.uint8).reshape(-1) for b in blobs]
+        transforms = transforms or [None] * len(blobs)
+        Ts = [None if T is None else np.ascontiguousarray(T, dtype=np.float32).reshape(16) for T in transforms]
+        arr = (VoxelInput * len(blobs))()
+        n = 0
+        for i, b in enumerate(blobs):
+            arr[i].data = b.ctypes.data_as(C.c_void_p).value
+            arr[i].n_pts = b.size // point_step
+            arr[i].transform = None if Ts[i] is None else Ts[i].ctypes.data_as(C.c_void_p).value
+            n += b.size // point_step
+        out = np.zeros(max(n, 1) * point_step, dtype=np.uint8)
+        vidx = np.zeros(max(n, 1), dtype=np.int32) if want_voxel_idx else None
+        n_out = C.c_size_t(0)
+        fa = self._fields(fields)
+        _check(lib().lb_voxel_filter_merged(self._h, arr, len(blobs), point_step, fa, len(fields), _ptr(out), n, C.byref(n_out),
+                                            _ptr(vidx), LB_MEM_HOST, LB_MEM_HOST))
         m = n_out.value
         o = out[: m * point_step].reshape(m, point_step)
         return (o, vidx[:m]) if want_voxel_idx else o

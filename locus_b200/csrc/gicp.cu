@@ -1139,6 +1139,64 @@ int lb_gicp_compute_normals(lb_gicp* h, int which, int k, const float* viewpoint
   return LB_OK;
 }
 
+// SURVEY 8f row f2, the nodelet's radius mode + NaN-normal removal (normal_computation.cc:53-57,73-77).
+int lb_gicp_compute_normals_radius(lb_gicp* h, int which, double radius, const float* viewpoint, float* out4, int32_t* valid_idx,
+                                   size_t* n_valid, int mem) {
+  if (!h || !out4 || (which != 0 && which != 1)) { set_error("lb_gicp_compute_normals_radius: bad argument"); return LB_ERR_INVALID_ARG; }
+  if (!(radius > 0.0)) { set_error("lb_gicp_compute_normals_radius: radius must be > 0"); return LB_ERR_INVALID_ARG; }
+  Cloud& cl = which == 0 ? *h->src : *h->tgt;
+  if (!cl.valid) { set_error("lb_gicp_compute_normals_radius: no %s cloud", which == 0 ? "source" : "target"); return which == 0 ? LB_ERR_EMPTY_SOURCE : LB_ERR_NO_TARGET; }
+  if (n_valid) *n_valid = 0;
+  Scratch& S = h->sc[which];
+  Ctx& c = S.c;
+  LB_CUDA(cudaSetDevice(c.device));
+  LB_TRY(finish_index(h, cl, which));
+  const uint32_t N = (uint32_t)cl.n;
+  static const bool attr_ok = [] {
+    return cudaFuncSetAttribute(normals_radius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(NR_WARPS * NR_CAP * sizeof(unsigned long long))) == cudaSuccess;
+  }();
+  if (!attr_ok) { set_error("lb_gicp_compute_normals_radius: cannot reserve shared memory"); return LB_ERR_CUDA; }
+  f4* d_out = reinterpret_cast<f4*>(out4);
+  int32_t* d_vidx = valid_idx;
+  if (mem == LB_MEM_HOST) {
+    LB_TRY(h->io.ensure((size_t)N * sizeof(f4)));
+    d_out = reinterpret_cast<f4*>(h->io.p);
+    if (valid_idx) { LB_TRY(h->io_idx.ensure(N)); d_vidx = h->io_idx.p; }
+  }
+  LB_TRY(S.keys.ensure(N)); LB_TRY(S.worklist.ensure(N));
+  uint32_t* d_flags = S.keys.p; uint32_t* d_pos = S.worklist.p;
+  cl.keys_slot = -1;                               // the slot's key scratch is reused as the flag array
+  uint32_t* d_tot = S.d_u32 + 6;                   // [6] number of valid normals, [7] overflow flag
+  LB_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(uint32_t), c.stream));
+  int blocks = cdiv(N, NR_WARPS);
+  if (blocks > c.sm_count * 8) blocks = c.sm_count * 8;
+  normals_radius_kernel<<<blocks, NR_WARPS * 32, NR_WARPS * NR_CAP * sizeof(unsigned long long), c.stream>>>(
+      cl.view(), cl.raw.p, (float)(radius * radius), viewpoint ? viewpoint[0] : 0.f, viewpoint ? viewpoint[1] : 0.f,
+      viewpoint ? viewpoint[2] : 0.f, d_out, d_flags, reinterpret_cast<int*>(d_tot + 1));
+  c.launches++;
+  LB_TRY(exclusive_scan_u32(c, S.scan, d_flags, d_pos, N, d_tot));
+  if (valid_idx) {
+    compact_indices_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_flags, d_pos, N, d_vidx);
+    c.launches++;
+  }
+  LB_CUDA(cudaGetLastError());
+  LB_CUDA(cudaMemcpyAsync(S.h_u32 + 6, d_tot, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  if (mem == LB_MEM_HOST) LB_CUDA(cudaMemcpyAsync(out4, d_out, (size_t)N * sizeof(f4), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  if (S.h_u32[7]) {
+    set_error("lb_gicp_compute_normals_radius: a neighbourhood holds more than %d points; use a smaller radius or the k-NN mode", NR_CAP);
+    return LB_ERR_CAPACITY;
+  }
+  const size_t m = S.h_u32[6];
+  if (valid_idx && mem == LB_MEM_HOST && m) {
+    LB_CUDA(cudaMemcpyAsync(valid_idx, d_vidx, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  if (n_valid) *n_valid = m;
+  return LB_OK;
+}
+
 int lb_gicp_get_covariances(lb_gicp* h, int which, double* out9, size_t capacity_points) {
   if (!h || !out9) return LB_ERR_INVALID_ARG;
   Cloud& cl = which ? *h->tgt : *h->src;

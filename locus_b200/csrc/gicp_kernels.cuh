@@ -532,6 +532,127 @@ knn_cov_tail_kernel(GridView g, int k, Fin fin, const uint32_t* __restrict__ wor
   }
 }
 
+// Row f2, radius mode of the NormalComputation nodelet (normal_computation.cc:73-77: norm_est_.setRadiusSearch): the
+// neighbourhood of a point is EVERY point closer than the radius (FLANN RadiusResultSet: d2 < float(radius^2), strict),
+// visited in ascending (d2, index) order -- the order PCL's nine float32 accumulators see them in, so it defines the
+// rounding.  One warp per query: the lanes scan the rows of the shells that can reach the radius and append their hits
+// (packed (d2, index) keys) to a list in shared memory; the warp sorts the list (bitonic), then lanes 0-8 each run one
+// of the nine accumulators over the sorted neighbours (staged 32 at a time) and lane 0 finishes the normal.  Fewer than
+// three neighbours -> NaN normal (pcl::computePointNormal), which the nodelet then drops (:53-57): `valid` flags them.
+constexpr int NR_CAP = 2048;          // neighbours per query held in shared memory (16 KB per warp)
+constexpr int NR_WARPS = 4;
+__global__ void __launch_bounds__(NR_WARPS * 32)
+normals_radius_kernel(GridView g, const f4* __restrict__ raw, float r2, float vp0, float vp1, float vp2, f4* __restrict__ out,
+                      uint32_t* __restrict__ valid, int* __restrict__ overflow) {
+  extern __shared__ unsigned long long nr_keys[];       // [NR_WARPS][NR_CAP]
+  __shared__ int cnt[NR_WARPS];
+  __shared__ float ptbuf[NR_WARPS][32][3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long* keys = nr_keys + (size_t)w * NR_CAP;
+  const uint32_t nwarps = gridDim.x * NR_WARPS;
+  const float vp[3] = {vp0, vp1, vp2};
+  for (uint32_t s = blockIdx.x * NR_WARPS + w; s < (uint32_t)g.n; s += nwarps) {
+    const f4 q = g.pts[s];
+    if (lane == 0) cnt[w] = 0;
+    __syncwarp();
+    int cx, cy, cz; float minfrac;
+    query_cell(g, q.x, q.y, q.z, cx, cy, cz, minfrac);
+    int r0, r1;
+    ring_range(g, cx, cy, cz, r0, r1);
+    for (int r = r0; r <= r1; r++) {
+      const int side = 2 * r + 1;
+      for (int j = lane; j < side * side; j += 32) {
+        const int dz = j / side - r, dy = j % side - r;
+        const int z = cz + dz, y = cy + dy;
+        if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+        const bool face = (iabs_(dz) == r) || (iabs_(dy) == r);
+        const int base = (z * g.ny + y) * g.nx;
+        const int nseg = face ? 1 : 2;
+        for (int sgm = 0; sgm < nseg; sgm++) {
+          int xa, xb;
+          if (face) { xa = imax_(cx - r, 0); xb = imin_(cx + r, g.nx - 1); }
+          else { xa = xb = (sgm == 0) ? cx - r : cx + r; if (xa < 0 || xa >= g.nx) continue; }
+          if (xa > xb) continue;
+          const uint32_t a = g.cell_start[base + xa], e = g.cell_start[base + xb + 1];
+          for (uint32_t i = a; i < e; i++) {
+            const f4 p = g.pts[i];
+            const float d2 = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (d2 < r2) {
+              const int pos = atomicAdd(&cnt[w], 1);
+              if (pos < NR_CAP) keys[pos] = RegList<1>::make_key(d2, float_to_bits(p.w));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (ring_bound2(g, r, minfrac) >= r2) break;      // nothing beyond the scanned block can be inside the radius
+    }
+    __syncwarp();
+    int M = cnt[w];
+    if (M > NR_CAP) { if (lane == 0) atomicExch(overflow, 1); M = 0; }      // reported by the host as LB_ERR_CAPACITY
+    // bitonic sort of the M keys (ascending (d2, index)), padded to a power of two with all-ones keys
+    int P = 32;
+    while (P < M) P <<= 1;
+    for (int i = M + lane; i < P; i += 32) keys[i] = ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = keys[i], b = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    // the nine float32 accumulators of computeMeanAndCovarianceMatrix, one per lane, in neighbour order
+    float acc = 0.f;
+    for (int base = 0; base < M; base += 32) {
+      if (base + lane < M) {
+        const f4 p = raw[(uint32_t)keys[base + lane]];
+        ptbuf[w][lane][0] = p.x; ptbuf[w][lane][1] = p.y; ptbuf[w][lane][2] = p.z;
+      }
+      __syncwarp();
+      if (lane < 9) {
+        const int m = min(32, M - base);
+        for (int t = 0; t < m; t++) {
+          const float x = ptbuf[w][t][0], y = ptbuf[w][t][1], z = ptbuf[w][t][2];
+          float term;
+          switch (lane) {
+            case 0: term = x * x; break; case 1: term = x * y; break; case 2: term = x * z; break;
+            case 3: term = y * y; break; case 4: term = y * z; break; case 5: term = z * z; break;
+            case 6: term = x; break; case 7: term = y; break; default: term = z; break;
+          }
+          acc = acc + term;
+        }
+      }
+      __syncwarp();
+    }
+    NormalAccum A;
+#pragma unroll
+    for (int c = 0; c < 9; c++) A.a[c] = __shfl_sync(0xffffffffu, acc, c);
+    if (lane == 0) {
+      float o[4];
+      const float qnan = __int_as_float(0x7fc00000);
+      if (M < 3) { o[0] = o[1] = o[2] = o[3] = qnan; }
+      else pcl_normal_from_accum(A, M, q.x, q.y, q.z, vp, o);
+      const int orig = float_to_bits(q.w);
+      out[orig] = f4{o[0], o[1], o[2], o[3]};
+      valid[orig] = (isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2])) ? 1u : 0u;
+    }
+    __syncwarp();
+  }
+}
+
+// pcl::removeNaNNormalsFromPointCloud: the indices of the points that stay, ascending
+__global__ void __launch_bounds__(256)
+compact_indices_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t n, int32_t* __restrict__ out_idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) out_idx[pos[i]] = (int32_t)i;
+}
+
 // K3': covariance from a stored normal (the reference's default mode when normals are present)
 __global__ void __launch_bounds__(256)
 normal_cov_kernel(const f4* __restrict__ pts, const f4* __restrict__ nrm, uint32_t n, double eps, double* __restrict__ cov) {

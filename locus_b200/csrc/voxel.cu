@@ -50,6 +50,39 @@ struct VoxLimits {
   int negative;
 };
 
+// Up to three input clouds taken as ONE cloud (row f4: the point_cloud_merger node concatenates the 2-3 lidars of a
+// robot, a + (b + c), PointCloudMerger.cc:150-178) with, per cloud, what its pcl/PassThrough nodelet does first
+// (locus.launch:90-133): drop non-finite points and points whose field lies outside the limits -- in the SENSOR frame --
+// then transform into base_link (`output_frame`).  Both are folded into the loads of the voxel kernels.
+constexpr int VG_MAX_INPUTS = 3;
+struct VoxInputs {
+  const uint8_t* base[VG_MAX_INPUTS];
+  uint32_t start[VG_MAX_INPUTS + 1];     // global point number of the first point of every cloud; start[n] = total
+  float T[VG_MAX_INPUTS][12];            // row-major 3x4 sensor -> base_link
+  int has_T[VG_MAX_INPUTS];
+  int n;
+  VoxLimits pass;                        // PassThrough limits on the raw field (ff_off < 0: none)
+};
+__device__ __forceinline__ const uint8_t* vg_point(const VoxInputs& in, uint32_t i, uint32_t stride, int& c) {
+  c = (in.n > 1 && i >= in.start[1]) ? ((in.n > 2 && i >= in.start[2]) ? 2 : 1) : 0;
+  return in.base[c] + (size_t)(i - in.start[c]) * stride;
+}
+// PassThrough predicate (sensor frame) and the transform of one point; returns false when PassThrough drops the point
+__device__ __forceinline__ bool vg_passthrough(const VoxInputs& in, int c, float v, float& x, float& y, float& z) {
+  if (in.pass.ff_off >= 0) {
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z) || !isfinite(v)) return false;     // pcl::PassThrough removes NaNs
+    const double dv = (double)v;
+    const bool drop = in.pass.negative ? (dv < in.pass.dmax && dv > in.pass.dmin) : (dv > in.pass.dmax || dv < in.pass.dmin);
+    if (drop) return false;
+  }
+  if (in.has_T[c]) {
+    float ox, oy, oz;
+    xform(in.T[c], x, y, z, ox, oy, oz);       // Eigen Matrix4f * Vector4f (pcl_ros::transformPointCloud)
+    x = ox; y = oy; z = oz;
+  }
+  return true;
+}
+
 // the 8 words of a 32-byte record, fetched with two 16-byte loads
 struct Rec32 { uint4 a, b; };
 __device__ __forceinline__ Rec32 load_rec32(const uint8_t* p) {
@@ -73,21 +106,27 @@ __device__ __forceinline__ bool vg_survives(bool lim_drop, float x, float y, flo
 // finish turns the box into the grid geometry exactly like applyFilter does on the host side of PCL
 // (voxel_grid_covariance_omp_impl.hpp:75-103): dx*dy*dz overflow guard, min_b = floor(min_p * inv_leaf), div_b.
 __global__ void __launch_bounds__(256)
-vg_bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
+vg_bbox_kernel(const __grid_constant__ VoxInputs in, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
                float inv0, float inv1, float inv2, int vec32, VoxState* __restrict__ st) {
   uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mx0 = 0, mx1 = 0, mx2 = 0, cnt = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint8_t* p = base + (size_t)i * stride;
-    float x, y, z, v = 0.f;
+    int ci;
+    const uint8_t* p = vg_point(in, i, stride, ci);
+    float x, y, z, v = 0.f, pv = 0.f;
     if (vec32) {
       const Rec32 r = load_rec32(p);
       x = rec32_word(r, xyz_off); y = rec32_word(r, xyz_off + 4); z = rec32_word(r, xyz_off + 8);
       if (lim.ff_off >= 0) v = rec32_word(r, (uint32_t)lim.ff_off);
+      if (in.pass.ff_off >= 0) pv = rec32_word(r, (uint32_t)in.pass.ff_off);
     } else {
       const float* q = reinterpret_cast<const float*>(p + xyz_off);
       x = q[0]; y = q[1]; z = q[2];
       if (lim.ff_off >= 0) v = *reinterpret_cast<const float*>(p + lim.ff_off);
+      if (in.pass.ff_off >= 0) pv = *reinterpret_cast<const float*>(p + in.pass.ff_off);
     }
+    if (!vg_passthrough(in, ci, pv, x, y, z)) continue;
+    if (lim.ff_off >= 0 && in.has_T[ci] && (uint32_t)lim.ff_off >= xyz_off && (uint32_t)lim.ff_off < xyz_off + 12)
+      v = ((uint32_t)lim.ff_off == xyz_off) ? x : (((uint32_t)lim.ff_off == xyz_off + 4) ? y : z);   // the grid's own limits see base_link coordinates
     bool drop = false;
     if (lim.ff_off >= 0) drop = lim.negative ? (v < lim.fmax && v > lim.fmin) : (v > lim.fmax || v < lim.fmin);
     if (!vg_survives(drop, x, y, z, body)) continue;
@@ -159,7 +198,7 @@ vg_bbox_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, ui
 }
 
 __global__ void __launch_bounds__(256)
-vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
+vg_keys_kernel(const __grid_constant__ VoxInputs in, uint32_t n, uint32_t stride, uint32_t xyz_off, VoxLimits lim, BodyBox body,
                float inv0, float inv1, float inv2, int vec32, VoxelFieldsDev F, const VoxState* __restrict__ st,
                uint32_t* __restrict__ keys, float4* __restrict__ rec /*nullable: only for 4 averaged fields*/) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,24 +207,36 @@ vg_keys_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, ui
   const uint32_t sentinel = st->sentinel;
   const int min_b0 = st->min_b[0], min_b1 = st->min_b[1], min_b2 = st->min_b[2];
   const int mul1 = st->div_b[0], mul2 = st->div_b[0] * st->div_b[1];
-  const uint8_t* p = base + (size_t)i * stride;
-  float x, y, z, v = 0.f;
+  int ci;
+  const uint8_t* p = vg_point(in, i, stride, ci);
+  float x, y, z, v = 0.f, pv = 0.f;
   float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (vec32) {
     const Rec32 r = load_rec32(p);
     x = rec32_word(r, xyz_off); y = rec32_word(r, xyz_off + 4); z = rec32_word(r, xyz_off + 8);
     if (lim.ff_off >= 0) v = rec32_word(r, (uint32_t)lim.ff_off);
+    if (in.pass.ff_off >= 0) pv = rec32_word(r, (uint32_t)in.pass.ff_off);
     if (rec) r4 = make_float4(rec32_word(r, F.ff_off[0]), rec32_word(r, F.ff_off[1]), rec32_word(r, F.ff_off[2]), rec32_word(r, F.ff_off[3]));
   } else {
     x = *reinterpret_cast<const float*>(p + xyz_off);
     y = *reinterpret_cast<const float*>(p + xyz_off + 4);
     z = *reinterpret_cast<const float*>(p + xyz_off + 8);
     if (lim.ff_off >= 0) v = *reinterpret_cast<const float*>(p + lim.ff_off);
+    if (in.pass.ff_off >= 0) pv = *reinterpret_cast<const float*>(p + in.pass.ff_off);
     if (rec) r4 = make_float4(*reinterpret_cast<const float*>(p + F.ff_off[0]), *reinterpret_cast<const float*>(p + F.ff_off[1]),
                               *reinterpret_cast<const float*>(p + F.ff_off[2]), *reinterpret_cast<const float*>(p + F.ff_off[3]));
   }
-  bool drop = false;
-  if (lim.ff_off >= 0) {
+  const bool passed = vg_passthrough(in, ci, pv, x, y, z);
+  if (in.has_T[ci]) {
+    // the record the centroid sums holds the TRANSFORMED coordinates (the averaged fields are x, y, z, intensity here)
+    if (rec) {
+      if (F.ff_off[0] == xyz_off) r4.x = x; if (F.ff_off[1] == xyz_off + 4) r4.y = y; if (F.ff_off[2] == xyz_off + 8) r4.z = z;
+    }
+    if (lim.ff_off >= 0 && (uint32_t)lim.ff_off >= xyz_off && (uint32_t)lim.ff_off < xyz_off + 12)
+      v = ((uint32_t)lim.ff_off == xyz_off) ? x : (((uint32_t)lim.ff_off == xyz_off + 4) ? y : z);
+  }
+  bool drop = !passed;
+  if (!drop && lim.ff_off >= 0) {
     const double dv = (double)v;
     drop = lim.negative ? (dv < lim.dmax && dv > lim.dmin) : (dv > lim.dmax || dv < lim.dmin);
   }
@@ -287,7 +338,7 @@ vg_keep_kernel(const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
 // (the order defines the float32 rounding) -- no per-lane chains of dependent global loads.
 constexpr int VG4_TILE = 256;       // records per warp tile (4 KB)
 __global__ void __launch_bounds__(128)
-vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
+vg_centroid4_kernel(const __grid_constant__ VoxInputs in, uint32_t stride, const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
                     const uint32_t* __restrict__ va, const uint32_t* __restrict__ vb, const float4* __restrict__ rec,
                     const uint32_t* __restrict__ seg_start, const VoxState* __restrict__ st,
                     const uint32_t* __restrict__ slot /*nullable*/, const uint32_t* __restrict__ keep /*nullable*/,
@@ -355,7 +406,8 @@ vg_centroid4_kernel(const uint8_t* __restrict__ in, uint32_t stride, const uint3
   const uint32_t o = slot ? slot[s] : s;
   if (o >= capacity) return;
   const float cnt = (float)(e - a);
-  const uint8_t* first = in + (size_t)vals[a] * stride;
+  int cfirst;
+  const uint8_t* first = vg_point(in, vals[a], stride, cfirst);
   uint8_t* dst = out + (size_t)o * stride;
   // bytes not covered by an averaged field come from the voxel's first point
   if (vec32 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
@@ -440,6 +492,9 @@ struct lb_voxel {
   int min_points = 0;
   int downsample_all = 1;
   BodyBox body{0, 1.f, 0.f, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // BodyFilter nodelet folded in (lb_voxel_set_body_filter)
+  char pass_field[32] = "";     // pcl/PassThrough nodelet folded in (lb_voxel_set_input_passthrough)
+  double pass_min = -FLT_MAX, pass_max = FLT_MAX;
+  int pass_negative = 0;
   DBuf<uint8_t> d_in, d_out;
   DBuf<int32_t> d_vidx;
   DBuf<uint32_t> keys, tile_cnt, seg_start, keep, slot;
@@ -536,18 +591,52 @@ int lb_voxel_kernel_time_avg(lb_voxel* h, float* ms_avg, uint64_t* calls, int re
   return LB_OK;
 }
 
+int lb_voxel_set_input_passthrough(lb_voxel* h, const char* field_name, double limit_min, double limit_max, int negative) {
+  if (!h) return LB_ERR_INVALID_ARG;
+  h->pass_field[0] = 0;
+  if (field_name) { strncpy(h->pass_field, field_name, sizeof(h->pass_field) - 1); h->pass_field[sizeof(h->pass_field) - 1] = 0; }
+  h->pass_min = limit_min; h->pass_max = limit_max; h->pass_negative = negative ? 1 : 0;
+  return LB_OK;
+}
+
+static int voxel_filter_impl(lb_voxel* h, const lb_voxel_input* inputs, int n_inputs, uint32_t point_step, const lb_field* fields,
+                             int n_fields, uint8_t* out, size_t out_capacity_pts, size_t* n_out, int32_t* out_voxel_idx,
+                             int mem_in, int mem_out);
+
 int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t point_step, const lb_field* fields,
                     int n_fields, const int32_t* indices, size_t n_indices, uint8_t* out, size_t out_capacity_pts,
                     size_t* n_out, int32_t* out_voxel_idx, int mem_in, int mem_out) {
   (void)indices; (void)n_indices;  // pcl::VoxelGrid<PCLPointCloud2> ignores indices_ too
+  lb_voxel_input in;
+  in.data = data; in.n_pts = n_pts; in.transform = nullptr;
+  return voxel_filter_impl(h, &in, 1, point_step, fields, n_fields, out, out_capacity_pts, n_out, out_voxel_idx, mem_in, mem_out);
+}
+
+int lb_voxel_filter_merged(lb_voxel* h, const lb_voxel_input* inputs, int n_inputs, uint32_t point_step, const lb_field* fields,
+                           int n_fields, uint8_t* out, size_t out_capacity_pts, size_t* n_out, int32_t* out_voxel_idx,
+                           int mem_in, int mem_out) {
+  if (!inputs || n_inputs < 1 || n_inputs > VG_MAX_INPUTS) { set_error("lb_voxel_filter_merged: 1 to %d input clouds", VG_MAX_INPUTS); return LB_ERR_INVALID_ARG; }
+  return voxel_filter_impl(h, inputs, n_inputs, point_step, fields, n_fields, out, out_capacity_pts, n_out, out_voxel_idx, mem_in, mem_out);
+}
+
+static int voxel_filter_impl(lb_voxel* h, const lb_voxel_input* inputs, int n_inputs, uint32_t point_step, const lb_field* fields,
+                             int n_fields, uint8_t* out, size_t out_capacity_pts, size_t* n_out, int32_t* out_voxel_idx,
+                             int mem_in, int mem_out) {
   if (!h || !n_out) { set_error("lb_voxel_filter: null handle / n_out"); return LB_ERR_INVALID_ARG; }
   *n_out = 0;
+  size_t n_pts = 0;
+  bool any_T = false;
+  for (int i = 0; i < n_inputs; i++) {
+    if (inputs[i].n_pts && !inputs[i].data) { set_error("lb_voxel_filter: null input cloud %d", i); return LB_ERR_INVALID_ARG; }
+    n_pts += inputs[i].n_pts;
+    any_T = any_T || inputs[i].transform != nullptr;
+  }
   if (n_pts == 0) return LB_OK;
-  if (!data || !out || !fields || n_fields <= 0) { set_error("lb_voxel_filter: null data/out/fields"); return LB_ERR_INVALID_ARG; }
+  if (!out || !fields || n_fields <= 0) { set_error("lb_voxel_filter: null data/out/fields"); return LB_ERR_INVALID_ARG; }
   if (point_step < 12 || (point_step & 3u)) { set_error("lb_voxel_filter: point_step must be a multiple of 4 and >= 12"); return LB_ERR_INVALID_ARG; }
   if (n_pts > 0x7ffffff0ull) { set_error("lb_voxel_filter: too many points"); return LB_ERR_INVALID_ARG; }
   if (!(h->leaf[0] > 0.f)) { set_error("lb_voxel_filter: leaf size not set"); return LB_ERR_INVALID_ARG; }
-  int xo = -1, yo = -1, zo = -1, ffo = -1;
+  int xo = -1, yo = -1, zo = -1, ffo = -1, pfo = -1;
   VoxelFieldsDev F; F.n_ff = 0;
   for (int f = 0; f < n_fields; f++) {
     const lb_field& fd = fields[f];
@@ -559,10 +648,15 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
       if (!is_f32) { set_error("lb_voxel_filter: distance filtering requires a FLOAT32 field"); return LB_ERR_UNSUPPORTED; }
       ffo = (int)fd.offset;
     }
+    if (h->pass_field[0] && !strcmp(fd.name, h->pass_field)) {
+      if (!is_f32) { set_error("lb_voxel_filter: PassThrough requires a FLOAT32 field"); return LB_ERR_UNSUPPORTED; }
+      pfo = (int)fd.offset;
+    }
     if (fd.offset + 4 > point_step || (fd.offset & 3u)) {
       if (is_f32) { set_error("lb_voxel_filter: field '%s' misaligned / out of range", fd.name); return LB_ERR_INVALID_ARG; }
     }
   }
+  if (h->pass_field[0] && pfo < 0) { set_error("lb_voxel_filter: PassThrough field '%s' not found", h->pass_field); return LB_ERR_INVALID_ARG; }
   if (xo < 0 || yo < 0 || zo < 0) { set_error("lb_voxel_filter: x/y/z FLOAT32 fields required"); return LB_ERR_INVALID_ARG; }
   if (h->filter_field[0] && ffo < 0) { set_error("lb_voxel_filter: filter field '%s' not found", h->filter_field); return LB_ERR_INVALID_ARG; }
   if (h->downsample_all) {
@@ -585,11 +679,32 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   const uint32_t n = (uint32_t)n_pts;
   const size_t bytes = (size_t)n * point_step;
   LB_CUDA(cudaEventRecord(h->ev0, c.stream));
-  const uint8_t* d_in = data;
-  if (mem_in == LB_MEM_HOST) {
-    LB_TRY(h->d_in.ensure(bytes));
-    LB_CUDA(cudaMemcpyAsync(h->d_in.p, data, bytes, cudaMemcpyHostToDevice, c.stream));
-    d_in = h->d_in.p;
+  VoxInputs vin;
+  memset(&vin, 0, sizeof(vin));
+  vin.n = n_inputs;
+  vin.pass.ff_off = pfo; vin.pass.fmin = (float)h->pass_min; vin.pass.fmax = (float)h->pass_max;
+  vin.pass.dmin = h->pass_min; vin.pass.dmax = h->pass_max; vin.pass.negative = h->pass_negative;
+  if (mem_in == LB_MEM_HOST) LB_TRY(h->d_in.ensure(bytes));
+  {
+    size_t at = 0;
+    for (int i = 0; i < VG_MAX_INPUTS; i++) {
+      const bool have = i < n_inputs;
+      vin.start[i] = (uint32_t)at;
+      vin.base[i] = nullptr;
+      if (have) {
+        vin.base[i] = inputs[i].data;
+        if (mem_in == LB_MEM_HOST) {          // the clouds are staged back to back: one device cloud
+          if (inputs[i].n_pts)
+            LB_CUDA(cudaMemcpyAsync(h->d_in.p + at * point_step, inputs[i].data, inputs[i].n_pts * point_step, cudaMemcpyHostToDevice, c.stream));
+          vin.base[i] = h->d_in.p + at * point_step;
+        }
+        vin.has_T[i] = inputs[i].transform ? 1 : 0;
+        if (inputs[i].transform) for (int e = 0; e < 12; e++) vin.T[i][e] = inputs[i].transform[e];
+        at += inputs[i].n_pts;
+      }
+    }
+    vin.start[VG_MAX_INPUTS] = (uint32_t)at;
+    for (int i = n_inputs; i < VG_MAX_INPUTS; i++) vin.start[i] = (uint32_t)at;
   }
   uint8_t* d_out = out; int32_t* d_vidx = out_voxel_idx;
   uint32_t capacity = (uint32_t)(out_capacity_pts < n ? out_capacity_pts : n);
@@ -602,8 +717,18 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   LB_TRY(h->keys.ensure(n)); LB_TRY(h->seg_start.ensure(n)); LB_TRY(h->tile_cnt.ensure(ntiles));
   const bool four = F.n_ff == 4;
   if (four) LB_TRY(h->rec.ensure(n));
-  // 32-byte records on a 16-byte aligned base: two 16-byte loads per point instead of 4-byte strided ones
-  const int vec32 = (point_step == 32 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0) ? 1 : 0;
+  if (!four && (n_inputs > 1 || any_T)) {
+    set_error("lb_voxel_filter_merged: merging / transforming inputs needs the x, y, z, intensity layout (4 averaged FLOAT32 fields)");
+    return LB_ERR_UNSUPPORTED;
+  }
+  if (four && any_T && !(F.ff_off[0] == (uint32_t)xo && F.ff_off[1] == (uint32_t)yo && F.ff_off[2] == (uint32_t)zo)) {
+    set_error("lb_voxel_filter_merged: x, y, z must be the first three FLOAT32 fields when inputs are transformed");
+    return LB_ERR_UNSUPPORTED;
+  }
+  // 32-byte records on 16-byte aligned bases: two 16-byte loads per point instead of 4-byte strided ones
+  int vec32 = point_step == 32 ? 1 : 0;
+  for (int i = 0; i < n_inputs; i++) if (reinterpret_cast<uintptr_t>(vin.base[i]) & 15u) vec32 = 0;
+  const uint8_t* d_in = vin.base[0];
   VoxLimits lim;
   lim.ff_off = ffo; lim.fmin = (float)h->lim_min; lim.fmax = (float)h->lim_max; lim.dmin = h->lim_min; lim.dmax = h->lim_max;
   lim.negative = h->negative;
@@ -616,8 +741,8 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
   for (int attempt = 0; attempt < 2; attempt++) {
     const int launched_bits = attempt == 0 ? h->bits_hint : 32;
     const int bb_blocks = min(cdiv(n, 256), c.sm_count * 4);
-    vg_bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, h->d_st);
-    vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(d_in, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, F,
+    vg_bbox_kernel<<<bb_blocks, 256, 0, c.stream>>>(vin, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, h->d_st);
+    vg_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(vin, n, point_step, (uint32_t)xo, lim, h->body, inv0, inv1, inv2, vec32, F,
                                                        h->d_st, h->keys.p, four ? h->rec.p : nullptr);
     c.launches += 2;
     LB_TRY(radix_sort_pairs_devbits(c, h->sort, h->keys.p, n, launched_bits, &h->d_st->key_bits));
@@ -634,7 +759,7 @@ int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint32_t poi
       slot = h->slot.p; keep = h->keep.p;
     }
     if (four)
-      vg_centroid4_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, ka, kb, va, vb, h->rec.p, h->seg_start.p, h->d_st,
+      vg_centroid4_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(vin, point_step, ka, kb, va, vb, h->rec.p, h->seg_start.p, h->d_st,
                                                                slot, keep, n, F, capacity, vec32, d_out, d_vidx);
     else
       vg_centroid_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(d_in, point_step, ka, kb, va, vb, h->seg_start.p, h->d_st, slot, keep,

@@ -181,6 +181,48 @@ int og_kdtree_knn(const og_kdtree* t, const float q[3], int k, int* idx, float* 
   return h.cnt;
 }
 
+/* radius search (pcl::KdTreeFLANN::radiusSearch -> flann radiusSearch with RadiusResultSet: every point with
+ * d2 < radius2, strictly; sorted ascending by (d2, index) like the k-NN results).  Returns the number found; writes at
+ * most cap of them (the nearest ones are kept when the list is longer, callers size cap = n). */
+typedef struct { float r2; int cnt, cap; int* idx; float* d2; } rad_set;
+
+static void radius_rec(const og_kdtree* t, int id, const float q[3], rad_set* h) {
+  const kd_node* nd = &t->nodes[id];
+  if (nd->left < 0) {
+    for (int i = nd->lo; i < nd->hi; i++) {
+      const float* p = &t->xyz[3 * (size_t)i];
+      float dx = q[0] - p[0], dy = q[1] - p[1], dz = q[2] - p[2];
+      float d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      d2 = d2 + dz * dz;
+      if (d2 < h->r2) {
+        if (h->cnt < h->cap) { h->idx[h->cnt] = t->perm[i]; h->d2[h->cnt] = d2; }
+        h->cnt++;
+      }
+    }
+    return;
+  }
+  float qd = q[nd->dim];
+  float dl = qd - nd->split_lo; if (dl < 0.f) dl = 0.f;
+  float dr = nd->split_hi - qd; if (dr < 0.f) dr = 0.f;
+  if (dl * dl <= h->r2) radius_rec(t, nd->left, q, h);
+  if (dr * dr <= h->r2) radius_rec(t, nd->right, q, h);
+}
+
+int og_kdtree_radius(const og_kdtree* t, const float q[3], float radius2, int* idx, float* d2, int cap) {
+  rad_set h; h.r2 = radius2; h.cnt = 0; h.cap = cap; h.idx = idx; h.d2 = d2;
+  if (t->n == 0) return 0;
+  radius_rec(t, 0, q, &h);
+  int m = h.cnt < cap ? h.cnt : cap;
+  /* insertion sort by (d2, index): neighbourhoods are small */
+  for (int i = 1; i < m; i++) {
+    float dd = d2[i]; int ii = idx[i]; int j = i;
+    while (j > 0 && better(dd, ii, d2[j - 1], idx[j - 1])) { d2[j] = d2[j - 1]; idx[j] = idx[j - 1]; j--; }
+    d2[j] = dd; idx[j] = ii;
+  }
+  return h.cnt;
+}
+
 void og_kdtree_nn_batch(const og_kdtree* t, const float* q, int nq, int stride_f,
                         int* idx, float* d2, int num_threads) {
 #pragma omp parallel for schedule(dynamic, 64) num_threads(num_threads)

@@ -54,6 +54,9 @@ void og_kdtree_free(og_kdtree* t);
 /* exact k-NN; results ascending by (d2, index); returns number found (min(k,n)).
  * d2 is float32: ((dx*dx)+(dy*dy))+(dz*dz), no FMA (FLANN L2_Simple<float>). */
 int og_kdtree_knn(const og_kdtree* t, const float q[3], int k, int* idx, float* d2);
+/* radius search: every point with d2 < radius2 (strict, FLANN RadiusResultSet), ascending by (d2, index); returns the
+ * number found and writes min(found, cap) of them */
+int og_kdtree_radius(const og_kdtree* t, const float q[3], float radius2, int* idx, float* d2, int cap);
 /* batch 1-NN helper for tests (OpenMP over queries) */
 void og_kdtree_nn_batch(const og_kdtree* t, const float* q, int nq, int stride_f,
                         int* idx, float* d2, int num_threads);
@@ -216,6 +219,11 @@ void og_compute_ap(const float* query_xyz, int n, const float* ref_normals_xyz,
 /* point_cloud_filter::NormalComputation (k-NN mode) = pcl::NormalEstimationOMP, restated (normals_oracle.c).
  * out4: n x (nx, ny, nz, curvature). */
 int og_normals_knn(const float* pts, int n, int stride_f, int k, const float vp[3], float* out4, int num_threads);
+/* the nodelet's radius mode (normal_computation.cc:73-77) + removeNaNNormalsFromPointCloud (:53-57): neighbours = all
+ * points with d2 < float(radius^2) in ascending distance order; fewer than 3 -> NaN row.  valid_idx (nullable, capacity
+ * n): the points the nodelet keeps.  Returns their number. */
+int og_normals_radius(const float* pts, int n, int stride_f, double radius, const float vp[3], float* out4, int* valid_idx,
+                      int num_threads);
 
 #ifdef __cplusplus
 }

@@ -322,3 +322,18 @@ def normals_knn(pts, k=20, viewpoint=(0.0, 0.0, 0.0), num_threads=8):
     if rc != 0:
         raise ValueError("og_normals_knn: need 3 <= k <= n")
     return out
+
+
+def normals_radius(pts, radius, viewpoint=(0.0, 0.0, 0.0), num_threads=8):
+    """point_cloud_filter::NormalComputation, radius mode + NaN-normal removal (normals_oracle.c).
+    Returns (out4 (n, 4) float32 with NaN rows where a point has fewer than 3 neighbours, valid_idx int32)."""
+    p = _as_cloud(pts)
+    vp = np.ascontiguousarray(viewpoint, dtype=np.float32)
+    out = np.zeros((p.shape[0], 4), dtype=np.float32)
+    vi = np.zeros(max(p.shape[0], 1), dtype=np.int32)
+    lib().og_normals_radius.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib().og_normals_radius.restype = C.c_int
+    m = lib().og_normals_radius(_p(p), p.shape[0], p.shape[1], float(radius), _p(vp), _p(out), _p(vi), int(num_threads))
+    if m < 0:
+        raise ValueError("og_normals_radius failed")
+    return out, vi[:m]

@@ -88,3 +88,36 @@ def test_normals_errors():
         with pytest.raises(api.LocusB200Error) as e:
             g.computeNormals(which=0, k=k)
         assert e.value.status == status
+
+
+@pytest.mark.parametrize("radius", [0.3, 0.6])
+def test_normals_radius_mode_and_nan_removal(radius):
+    """the nodelet's radius mode (normal_computation.cc:73-77) + removeNaNNormalsFromPointCloud (:53-57): the same NaN
+    rows and the same kept indices as the oracle (neighbour sets are exact: d2 < float(radius^2), ascending distance
+    order), normals within 1e-5 where defined"""
+    import locus_b200
+    from oracle import oracle as O
+    pts = F.random_scene(12000, 5)
+    g = locus_b200.GicpB200()
+    g.setInputSource(pts)
+    vp = np.array([0.5, -1.0, 2.0], np.float32)
+    out, keep = g.computeNormalsRadius(which=0, radius=radius, viewpoint=vp)
+    ref, rkeep = O.normals_radius(pts, radius, viewpoint=vp)
+    assert np.array_equal(keep, rkeep)                                   # the nodelet's output cloud: same points, same order
+    assert np.array_equal(np.isnan(out[:, 0]), np.isnan(ref[:, 0])) and 0 < len(keep) < len(pts)
+    n_gpu = out[keep, :3].astype(np.float64); n_ref = ref[keep, :3].astype(np.float64)
+    err = 1.0 - np.abs((n_gpu * n_ref).sum(1))
+    assert (err < 1e-5).mean() >= 0.995 and np.abs(np.linalg.norm(n_gpu, axis=1) - 1).max() < 1e-5
+    assert (np.abs(out[keep, 3] - ref[keep, 3]) < 1e-5).mean() >= 0.995
+    # the filtered lidar scan the nodelet really sees, as target cloud
+    import locus_b200 as lb
+    scene, poses, blobs = G.stream(2, 1)
+    vg = lb.VoxelGridB200()
+    vg.setLeafSize(0.25); vg.setFilterFieldName("z"); vg.setFilterLimits(-100.0, 100.0)
+    f = np.ascontiguousarray(vg.filter(blobs[0], 32, lb.xyzi_fields())).view(np.float32).reshape(-1, 8)[:, :3].copy()
+    g.setInputTarget(f)
+    out, keep = g.computeNormalsRadius(which=1, radius=radius)
+    ref, rkeep = O.normals_radius(f, radius)
+    assert np.array_equal(keep, rkeep)
+    err = 1.0 - np.abs((out[keep, :3].astype(np.float64) * ref[keep, :3].astype(np.float64)).sum(1))
+    assert (err < 1e-5).mean() >= 0.99

@@ -148,3 +148,55 @@ def test_voxel_with_body_filter():
     vg.setBodyFilter(enabled=False)
     again = vg.filter(blob, 32, _fields())
     assert np.array_equal(again, plain)
+
+
+def _front_end_reference(oracle, blobs, transforms, pass_limits, leaf, body=None):
+    """CPU restatement of the chain the fused call replaces (locus.launch:90-186): per lidar pcl/PassThrough (NaN
+    removal, raw z limits, Eigen Matrix4f * Vector4f into base_link), point_cloud_merger's a + (b + c), then BodyFilter
+    and VoxelGrid (the oracle).  numpy float32 arithmetic is IEEE-exact per operation, like the kernels' (no FMA)."""
+    parts = []
+    for b, T in zip(blobs, transforms):
+        a = np.ascontiguousarray(b).view(np.float32).reshape(-1, 8).copy()
+        x, y, z = a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy()
+        keep = np.isfinite(x) & np.isfinite(y) & np.isfinite(z)
+        if pass_limits is not None:
+            keep &= ~((z.astype(np.float64) > pass_limits[1]) | (z.astype(np.float64) < pass_limits[0]))
+        if T is not None:
+            T = np.asarray(T, dtype=np.float32)
+            with np.errstate(invalid="ignore"):
+                for r in range(3):
+                    a[:, r] = ((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3]
+        parts.append(a[keep])
+    merged = np.ascontiguousarray(np.concatenate(parts))
+    return oracle.voxel_filter(merged.view(np.uint8).reshape(-1), 32, leaf, float_fields=G.FLOAT_FIELDS, filter_field_offset=8,
+                               limit_min=-100.0, limit_max=100.0, body=body)
+
+
+def test_merged_inputs_passthrough_and_transform(oracle):
+    """three lidars -> PassThrough (each, sensor frame) -> transform to base_link -> concatenation ->
+    BodyFilter -> VoxelGrid as ONE call, bit-exact vs the chain restated on the CPU"""
+    import locus_b200
+    from tools import gen_lidar as G2
+    scene = G2.make_scene(4)
+    poses = [np.eye(4), G2.pose_matrix([0.4, 0.1, -0.2], np.deg2rad([3.0, -20.0, 45.0])), G2.pose_matrix([-0.5, 0.0, 0.1], np.deg2rad([0.0, 15.0, 180.0]))]
+    blobs = [G2.scan(scene, poses[i], 70 + i, beams=16, az=1024) for i in range(3)]
+    Ts = [None, poses[1].astype(np.float32), poses[2].astype(np.float32)]
+    body = (np.array([-0.8, -0.5, -0.4], np.float32), np.array([0.6, 0.5, 0.3], np.float32), np.float32(0.3))
+    vg = locus_b200.VoxelGridB200()
+    vg.setLeafSize(0.2); vg.setFilterFieldName("z"); vg.setFilterLimits(-100.0, 100.0)
+    vg.setInputPassThrough("z", -1.2, 100.0)
+    vg.setBodyFilter(body[0], body[1], body[2])
+    out, vidx = vg.filterMerged(blobs, 32, locus_b200.xyzi_fields(), transforms=Ts, want_voxel_idx=True)
+    ref = _front_end_reference(oracle, blobs, Ts, (-1.2, 100.0), 0.2, body=body)
+    assert ref["rc"] == 0 and len(ref["out"]) > 1000
+    assert np.array_equal(vidx, ref["voxel_idx"])
+    # x, y, z, intensity (the averaged fields) bit-exact; the padding bytes come from each voxel's first raw point
+    a = np.ascontiguousarray(out).view(np.float32).reshape(-1, 8); b = np.ascontiguousarray(ref["out"]).view(np.float32).reshape(-1, 8)
+    assert np.array_equal(a[:, [0, 1, 2, 4]].view(np.uint32), b[:, [0, 1, 2, 4]].view(np.uint32))
+    # one input, no transform, no PassThrough == the plain call
+    vg2 = locus_b200.VoxelGridB200()
+    vg2.setLeafSize(0.2); vg2.setFilterFieldName("z"); vg2.setFilterLimits(-100.0, 100.0)
+    assert np.array_equal(vg2.filterMerged([blobs[0]], 32, locus_b200.xyzi_fields()), vg2.filter(blobs[0], 32, locus_b200.xyzi_fields()))
+    # two inputs == the concatenated blob
+    cat = np.concatenate([blobs[0], blobs[1]])
+    assert np.array_equal(vg2.filterMerged([blobs[0], blobs[1]], 32, locus_b200.xyzi_fields()), vg2.filter(cat, 32, locus_b200.xyzi_fields()))
