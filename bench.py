@@ -263,7 +263,9 @@ def describe(args, world, cfg):
     if args.config == "c2":
         w["workload"] = ("C2 scan-to-scan odometry: %d-ray synthetic 64-beam scan -> VoxelGrid ~%dk -> %s against the "
                          "previous filtered scan" % (rays, cfg["voxels"] // 1000, gi))
-        w["index"] = "source and target index + covariances rebuilt for every scan (like the reference's callers)"
+        w["index"] = ("blocking-call arms: source and target index + covariances rebuilt for every scan, like the reference's "
+                      "callers; pipeline arms: each filtered scan's index + covariances computed once and adopted as the next "
+                      "registration's target (bit-identical poses; variants.pipeline_rebuild_both_clouds rebuilds them)")
         w["l2"] = ("inputs larger than L2: %d distinct raw scans of %.1f MB cycled; blocking-call arms: L2 flushed "
                    "between scans by a 256 MiB write" % (cfg["n_stream"], rays * POINT_STEP / 1e6))
         w["pipeline"] = "lb_odometry: 1 VoxelGrid stage + %d registration workers, %d source points per align CTA, one scan stream" % (
@@ -794,7 +796,9 @@ def run_c2(ctx):
     sampler.start()
     for g in (odo.gicp(i) for i in range(args.depth)):
         g.resetKernelTimes(2)          # only the event pair around the align kernel (the roofline's live duration)
+    allocs0 = gicp.kernelTime("dbuf_allocs")[0]
     dev_ms, p_out, launches_timed = pipelined_run(odo, submit_device, n_scans, n_warm)
+    allocs_timed = gicp.kernelTime("dbuf_allocs")[0] - allocs0       # includes the untimed warm-up scans of this arm
     clocks = sampler.stop()
     stages_device = dict(state["stages"])
     kt = [odo.gicp(i).kernelTime("align_persistent") for i in range(args.depth)]
@@ -808,29 +812,26 @@ def run_c2(ctx):
     e2e_d2h = args.scans_per_step * (int(np.mean([r.n_filtered for r in e_out])) * POINT_STEP + C.sizeof(api.OdometryResult))
 
     variants = {}
-    # ---- variant (information only, N = 1): the pipeline with cloud sharing -- every scan's index + covariances are
-    # computed once and adopted as the next registration's target, instead of being rebuilt like the reference does
+    # ---- variant (information only, N = 1): the pipeline WITHOUT cloud sharing -- both clouds' index + covariances rebuilt
+    # for every registration, which is what the reference's callers make the reference do
     if ctx.world == 1 and os.environ.get("LB_SHARE_VARIANT", "1") != "0":
         try:
             odo2 = lb.OdometryB200(ctx.local_rank, depth=args.depth, max_points=nraw, max_point_step=POINT_STEP)
-            odo2.setCloudSharing(True)
+            odo2.setCloudSharing(False)
             odo2.voxel.setFilterFieldName("z"); odo2.voxel.setFilterLimits(-100.0, 100.0); odo2.voxel.setLeafSize(ctx.leaf)
             odo2.setGicpParams(**dict({k: getattr(gicp._p, k) for k, _ in api.GicpParams._fields_},
                                       align_points_per_cta=args.pipeline_ppc))
-            free0 = torch.cuda.mem_get_info()[0]
             sub2 = lambda i: odo2.submit(ctx.d_scans[seq(i, n_str)].data_ptr(), nraw, POINT_STEP, fa, mem=lb.LB_MEM_DEVICE)  # noqa: E731
             sh_ms, sh_out, _ = pipelined_run(odo2, sub2, n_scans, n_warm)
-            sh_stages = dict(state["stages"], device_memory_taken_mb=(free0 - torch.cuda.mem_get_info()[0]) / 1e6)
             same, compared = equals_sequential(sh_out)
-            variants["pipeline_shared_clouds"] = {
+            variants["pipeline_rebuild_both_clouds"] = {
                 "value": n_scans / (sh_ms * 1e-3), "unit": "scans/s", "equals_sequential": same, "scans_timed": n_scans,
-                "stages": sh_stages,
-                "note": "lb_odometry_set_cloud_sharing(1): each filtered scan's index + covariances computed once (by the "
-                        "registration that has it as source) and adopted as the next registration's target; NOT the "
-                        "headline, which rebuilds both clouds per scan like the reference"}
+                "stages": dict(state["stages"]),
+                "note": "lb_odometry_set_cloud_sharing(0): source AND target index + covariances rebuilt for every registration, "
+                        "like the reference's callers do; same poses as the default (sharing on), bit for bit"}
             odo2.close()
         except Exception as ex:          # the variant must never take the bench line down
-            variants["pipeline_shared_clouds"] = {"error": str(ex)[:200]}
+            variants["pipeline_rebuild_both_clouds"] = {"error": str(ex)[:200]}
     # ---- variant (information only, N = 1): north_star's Gauss-Newton inner solve instead of the reference's BFGS
     if ctx.world == 1 and not os.environ.get("LB_OPT"):
         keep = list(gpu_poses)
@@ -886,6 +887,7 @@ def run_c2(ctx):
                                "note": "the same blocking calls with HOST (pinned) buffers: raw scan H2D, filtered cloud D2H, "
                                        "source and target clouds H2D, pose D2H, all inside the timed region"},
             "pipeline_equals_sequential": pipe_same, "pipeline_scans_compared": pipe_compared,
+            "pipeline_device_allocations": int(allocs_timed),
             "pipeline_stages": dict(stages_device, note="host wall clock per scan inside the timed region (value arm): the "
                                     "VoxelGrid stage is serial, the registration workers run %d-wide" % args.depth),
             "input_pool": {"distinct_scans": n_str, "bytes": n_str * scan_bytes, "l2_bytes": l2_bytes},

@@ -166,6 +166,11 @@ int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
                        ptrdiff_t normal_off, int mem);
 int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t xyz_off,
                        ptrdiff_t normal_off, int mem, uint64_t* generation /* nullable */);
+/* Optional: pre-size the handle for clouds of up to max_points points (its current clouds, its scratch, and
+ * `spare_clouds` spare cloud objects, which set_source / set_target rotate through), so that a stream in steady state
+ * performs no device allocation -- an allocation synchronises the whole device and stalls every other handle working on
+ * it.  lb_odometry does this for its workers. */
+int lb_gicp_reserve(lb_gicp* h, size_t max_points, int spare_clouds);
 /* scan-to-scan odometry (PointCloudOdometry.cc:243-244 copies the last scan into
  * reference_): re-use the current source's index and covariances as the next
  * target instead of rebuilding them. */
@@ -381,10 +386,12 @@ lb_gicp* lb_odometry_gicp(lb_odometry* h, int i);
 int lb_odometry_depth(lb_odometry* h);
 /* applied to every worker's lb_gicp handle (call while the pipeline is idle) */
 int lb_odometry_set_gicp_params(lb_odometry* h, const lb_gicp_params* p);
-/* on != 0: every filtered scan's index + covariances are computed once, by the worker that registers it as source,
- * and adopted as target by the worker of the next scan (lb_gicp_share_source / lb_gicp_set_target_cloud) instead
- * of being rebuilt there.  Same poses, bit for bit.  Off by default: the default pipeline does per scan exactly the
- * work the reference does (both clouds rebuilt).  Call while the pipeline is idle. */
+/* Cloud sharing (ON by default).  on != 0: every filtered scan's index + covariances are computed once, by the worker
+ * that registers it as source, and adopted as target by the worker of the next scan (lb_gicp_share_source /
+ * lb_gicp_set_target_cloud) instead of being rebuilt there.  Same poses, bit for bit (the index is a pure function of
+ * the cloud).  on == 0: both clouds are rebuilt for every registration, which is what the reference's callers make
+ * the reference do (setInputTarget clears the target's covariances, gicp.h:196-200).  Call while the pipeline is idle,
+ * before the first scan. */
 int lb_odometry_set_cloud_sharing(lb_odometry* h, int on);
 /* scan: n_pts points of point_step bytes described by fields (as lb_voxel_filter); xyz must be FLOAT32 fields.
  * guess: row-major 4x4 prior handed to align() (NULL = identity).  filtered_out (nullable): host (LB_MEM_HOST) or

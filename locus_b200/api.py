@@ -69,7 +69,7 @@ SYMBOLS = [
     "lb_version", "lb_last_error_string", "lb_status_string", "lb_device_count",
     "lb_gicp_default_params", "lb_gicp_create", "lb_gicp_create_on_stream", "lb_gicp_destroy",
     "lb_gicp_set_params", "lb_gicp_get_params", "lb_gicp_set_source", "lb_gicp_set_target",
-    "lb_gicp_promote_source_to_target", "lb_gicp_prepare_source", "lb_gicp_share_source", "lb_gicp_set_target_cloud",
+    "lb_gicp_promote_source_to_target", "lb_gicp_reserve", "lb_gicp_prepare_source", "lb_gicp_share_source", "lb_gicp_set_target_cloud",
     "lb_cloud_release", "lb_gicp_align", "lb_gicp_transform_source", "lb_gicp_nn_target",
     "lb_gicp_fitness", "lb_gicp_point2plane_information", "lb_gicp_compute_normals", "lb_gicp_compute_normals_radius", "lb_gicp_get_covariances", "lb_gicp_cloud_size", "lb_gicp_launch_count",
     "lb_gicp_kernel_time", "lb_gicp_reset_kernel_times",
@@ -126,6 +126,8 @@ def lib():
     L.lb_gicp_set_source.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32]
     L.lb_gicp_set_target.argtypes = [vp, vp, sz, sz, sz, C.c_ssize_t, i32, u64p]
     L.lb_gicp_promote_source_to_target.argtypes = [vp]
+    if hasattr(L, "lb_gicp_reserve"):
+        L.lb_gicp_reserve.argtypes = [vp, sz, i32]
     if hasattr(L, "lb_gicp_prepare_source"):
         L.lb_gicp_prepare_source.argtypes = [vp]
         L.lb_gicp_share_source.argtypes = [vp, C.POINTER(vp)]
@@ -299,6 +301,9 @@ class GicpB200:
         """the resident rolling submap as registration target (index + cached covariances live with the map)"""
         _check(lib().lb_gicp_set_target_submap(self._h, submap._h))
         self._keep["tgt"] = submap
+
+    def reserve(self, max_points, spare_clouds=2):
+        _check(lib().lb_gicp_reserve(self._h, int(max_points), int(spare_clouds)))
 
     def promoteSourceToTarget(self):
         _check(lib().lb_gicp_promote_source_to_target(self._h))

@@ -1,14 +1,15 @@
-// align_cluster.cuh -- persistent align() kernel, thread-block-cluster variant (default for Ns <= 32768).
+// align_cluster.cuh -- persistent align() kernel, thread-block-cluster variant (LB_EXEC_PERSISTENT_CLUSTER).
 //
-// The all-SM persistent kernel (gicp_kernels.cuh) pays ~2.1 us per objective evaluation for the grid-wide
-// exchange through L2 (publish -> visible -> poll round trip, measured with per-CTA globaltimer snapshots).
-// The BFGS inner solve is a chain of ~170 dependent evaluations, so that hop is paid ~170 times per align().
-// Here the inner solve runs inside ONE thread-block cluster of 16 CTAs:
+// The all-SM persistent kernel (gicp_kernels.cuh) pays a grid-wide exchange through L2 per objective evaluation
+// (publish -> visible -> poll, ~8 k cycles including the skew of ~60 CTAs), and the BFGS inner solve is a chain of
+// ~150 dependent evaluations.  Here the inner solve runs inside ONE thread-block cluster of 16 CTAs (one die):
 //   * each solver CTA keeps its 1/16 of the correspondences (source point, matched target point, Mahalanobis
-//     matrix: 72 B per point, <= 2048 points) in shared memory for the whole inner solve;
-//   * the all-reduce of the 13 (BFGS) / 28 (Gauss-Newton) partial sums goes through distributed shared memory:
-//     every CTA writes its partials to its own shared slots, one hardware cluster barrier, every CTA reads the
-//     16 x NV remote words and adds them in rank order -- bitwise identical totals in all 16 leaders;
+//     matrix: 72 B per point, <= CL_CAP points) in shared memory for the whole inner solve;
+//   * the all-reduce of the 13 (BFGS) / 28 (Gauss-Newton) partial sums is a PUSH through distributed shared memory:
+//     the leader warp of every CTA sends its partials to all 16 CTAs with st.async (data + transaction count on the
+//     receiver's mbarrier in one instruction), then sleeps on its own mbarrier until the 16 x NV words have landed and
+//     adds them in rank order -- bitwise identical totals in all 16 leaders, no cluster barrier (which would flush
+//     L1, where the leader keeps its BFGS state), no polling, and the worker warps do not wait for the exchange at all;
 //   * the other clusters of the grid only take part in the correspondence step (K4), which wants every SM:
 //     they wait for a command word published through L2 by the rank-0 leader, search their slice, and report
 //     their hit count; that grid-wide exchange happens once per OUTER iteration, not per evaluation.
@@ -24,13 +25,13 @@ namespace lb {
 namespace cg = cooperative_groups;
 
 constexpr int CL_SIZE = 16;            // CTAs per cluster (non-portable size; checked at handle creation)
-constexpr int CL_CAP = 2048;           // correspondences per solver CTA held in shared memory
+constexpr int CL_CAP = 2816;           // correspondences per solver CTA held in shared memory (16 x 2816 = 45056 source points)
 constexpr int CL_ACC_WARPS = 7;        // warps 1..7 accumulate (warp 0 is the leader)
 constexpr int CL_ACC = CL_ACC_WARPS * 32;
 constexpr int CL_CMD_WORDS = 24;       // op, T[12], R[9] (+pad)
 constexpr int CL_MAX_CTAS = 160;
 
-struct ClusterCache {                  // dynamic shared memory of a solver CTA: 147,456 bytes
+struct ClusterCache {                  // dynamic shared memory of a solver CTA: 202,752 bytes
   float px[CL_CAP], py[CL_CAP], pz[CL_CAP], qx[CL_CAP], qy[CL_CAP], qz[CL_CAP];
   double M[6][CL_CAP];
 };
@@ -45,11 +46,11 @@ struct ClusterShared {                 // static shared memory
   double D[27];
   double red[CL_ACC_WARPS * AL_MAXV];
   double bc[AL_MAXV + 4];
-  double xs[2][AL_MAXV];               // this CTA's published partials (read by the other CTAs through DSMEM)
-  double mat[AL_MAXV * CL_SIZE];
+  double rx[2][CL_SIZE][AL_MAXV];      // partials pushed into this CTA by every rank (double-buffered)
+  unsigned long long mbar[2];          // one mbarrier per buffer: 1 arrival (own leader) + CL_SIZE * NV * 8 bytes
   double cmd[CL_CMD_WORDS];
   double counts[CL_MAX_CTAS];
-  long long t_acc, t_sync, t_gather, n_coll;   // CTA 0 / thread 0 cycle counters (profiling aid)
+  long long t_acc, t_sync, t_gather, n_coll, t_corr, t_scalar, t_mark;   // CTA 0 / thread 0 cycle counters (profiling aid)
 };
 
 struct ClusterArgs {
@@ -68,9 +69,7 @@ __device__ __forceinline__ int cl_nn_slice(const ClusterArgs& a, const float* T,
   int chunk = (a.c.n_src + (int)gridDim.x - 1) / (int)gridDim.x;
   int begin = min(a.c.n_src, (int)blockIdx.x * chunk);
   int end = min(a.c.n_src, begin + chunk);
-  int hits = 0;
-  for (int s = begin + threadIdx.x; s < end; s += blockDim.x) hits += correspond_point(a.c, T, R, s);
-  return hits;
+  return correspond_slice(a.c, T, R, begin, end);
 }
 
 // solver CTA: all threads.  On return sh.m holds the global number of correspondences and the CTA's chunk of
@@ -121,10 +120,36 @@ __device__ __forceinline__ void cl_do_correspond(const ClusterArgs& a, ClusterSh
   __syncthreads();
 }
 
+// ---- distributed-shared-memory push primitives (sm_90+ PTX)
+__device__ __forceinline__ uint32_t cl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cl_map_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cl_mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cl_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cl_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool cl_mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(cl_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// 8 bytes into another CTA's shared memory + 8 bytes of transaction count on that CTA's mbarrier, one instruction
+__device__ __forceinline__ void cl_push_f64(uint32_t remote_data, double v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(remote_data), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+
 // ---- objective evaluation inside the solver cluster ------------------------------------------------------
+// All threads: accumulate + CTA reduce.  Then only the LEADER warp exchanges (push + mbarrier wait); the worker warps
+// return at once and park on the CTA barrier for the next command.  phase: per-buffer mbarrier parity (leader warp).
 template <int NV>
-__device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const ClusterCache& cache, cg::cluster_group& cluster,
-                                                int& flip) {
+__device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const ClusterCache& cache, int rank, int& flip, uint32_t (&phase)[2]) {
   float T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = sh.T[i];
@@ -144,26 +169,30 @@ __device__ __forceinline__ void cl_do_objective(ClusterShared& sh, const Cluster
       else gn_terms(T, sh.D, sh.D + 9, sh.D + 18, cache.px[i], cache.py[i], cache.pz[i], cache.qx[i], cache.qy[i], cache.qz[i], M, acc);
     }
   }
-  double tot = block_reduce<NV, CL_ACC_WARPS, 1>(acc, sh.red);
-  if (threadIdx.x < NV) sh.xs[flip][threadIdx.x] = tot;
+  const double tot = block_reduce<NV, CL_ACC_WARPS, 1>(acc, sh.red);     // lanes < NV of warp 0 hold the CTA's partials
+  if (threadIdx.x >= 32) return;                                         // workers: back to the command loop
   const long long t1 = prof ? clock64() : 0;
-  cluster.sync();                                  // hardware cluster barrier: every CTA's partials are visible
-  const long long t2 = prof ? clock64() : 0;
-  for (int pr = threadIdx.x; pr < CL_SIZE * NV; pr += blockDim.x) {
-    const int r = pr / NV, e = pr - r * NV;
-    const double* remote = cluster.map_shared_rank(&sh.xs[flip][e], r);
-    sh.mat[e * CL_SIZE + r] = *remote;
+  const int lane = threadIdx.x;
+  unsigned long long* bar = &sh.mbar[flip];
+  if (lane == 0) cl_mbar_arrive_expect_tx(bar, (uint32_t)(CL_SIZE * NV * sizeof(double)));
+  if (lane < NV) {
+    const uint32_t l_data = cl_smem_u32(&sh.rx[flip][rank][lane]);
+    const uint32_t l_bar = cl_smem_u32(bar);
+#pragma unroll
+    for (int r = 0; r < CL_SIZE; r++) cl_push_f64(cl_map_rank(l_data, (uint32_t)r), tot, cl_map_rank(l_bar, (uint32_t)r));
   }
-  __syncthreads();
-  if (threadIdx.x < NV) {
+  while (!cl_mbar_try_wait(bar, phase[flip])) {}
+  phase[flip] ^= 1u;
+  const long long t2 = prof ? clock64() : 0;
+  if (lane < NV) {
     double x = 0.0;
 #pragma unroll
-    for (int r = 0; r < CL_SIZE; r++) x += sh.mat[threadIdx.x * CL_SIZE + r];   // rank order: identical in all CTAs
-    sh.bc[threadIdx.x] = x;
+    for (int r = 0; r < CL_SIZE; r++) x += sh.rx[flip][r][lane];         // rank order: identical in all CTAs
+    sh.bc[lane] = x;
   }
   flip ^= 1;
-  __syncthreads();
-  if (prof) { const long long t3 = clock64(); sh.t_acc += t1 - t0; sh.t_sync += t2 - t1; sh.t_gather += t3 - t2; sh.n_coll++; }
+  __syncwarp();
+  if (prof) { const long long t3 = clock64(); sh.t_acc += t1 - t0; sh.t_sync += t2 - t1; sh.t_gather += t3 - t2; sh.n_coll++; sh.t_mark = t3; }
 }
 
 // Backend of bfgs.h for the leader warp of a solver CTA (all 32 lanes call every method together).
@@ -171,15 +200,15 @@ struct ClusterBackend {
   const ClusterArgs& a;
   ClusterShared& sh;
   ClusterCache& cache;
-  cg::cluster_group& cluster;
   unsigned long long& cmd_epoch;
   int& flip;
+  uint32_t (&phase)[2];
   int rank;
   int m;
 
-  __device__ ClusterBackend(const ClusterArgs& a_, ClusterShared& sh_, ClusterCache& cache_, cg::cluster_group& cl_,
-                            unsigned long long& ce_, int& flip_, int rank_)
-      : a(a_), sh(sh_), cache(cache_), cluster(cl_), cmd_epoch(ce_), flip(flip_), rank(rank_), m(0) {}
+  __device__ ClusterBackend(const ClusterArgs& a_, ClusterShared& sh_, ClusterCache& cache_,
+                            unsigned long long& ce_, int& flip_, uint32_t (&phase_)[2], int rank_)
+      : a(a_), sh(sh_), cache(cache_), cmd_epoch(ce_), flip(flip_), phase(phase_), rank(rank_), m(0) {}
 
   __device__ __forceinline__ void warp_trig(const double* x, Trig& t) {
     const int lane = threadIdx.x & 31;
@@ -218,9 +247,11 @@ struct ClusterBackend {
     if (lane < 9) sh.R[lane] = R[lane];
     if (lane == 0) sh.op = OP_CORR;
     publish_cmd(OP_CORR, T, R);
+    const long long tc0 = clock64();
     __syncthreads();
     cl_do_correspond(a, sh, cache, cmd_epoch, rank);
     m = sh.m;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const long long tc1 = clock64(); sh.t_corr += tc1 - tc0; sh.t_mark = tc1; }
     return m;
   }
 
@@ -232,8 +263,9 @@ struct ClusterBackend {
     apply_state_trig(x, t, T);
     if (lane < 12) sh.T[lane] = T[lane];
     if (lane == 0) sh.op = OP_FDF;
+    if (blockIdx.x == 0 && threadIdx.x == 0) sh.t_scalar += clock64() - sh.t_mark;   // leader time since the last collective
     __syncthreads();
-    cl_do_objective<13>(sh, cache, cluster, flip);
+    cl_do_objective<13>(sh, cache, rank, flip, phase);
     double sums[13];
 #pragma unroll
     for (int e = 0; e < 13; e++) sums[e] = sh.bc[e];
@@ -252,7 +284,7 @@ struct ClusterBackend {
     if (lane < 27) sh.D[lane] = D[lane];
     if (lane == 0) sh.op = OP_GN;
     __syncthreads();
-    cl_do_objective<28>(sh, cache, cluster, flip);
+    cl_do_objective<28>(sh, cache, rank, flip, phase);
     *f = sh.bc[0] / (double)m;
 #pragma unroll
     for (int e = 0; e < 6; e++) b[e] = sh.bc[1 + e];
@@ -272,7 +304,13 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
   const bool solver = (blockIdx.x / CL_SIZE) == 0;          // cluster 0 runs the inner solves
   unsigned long long cmd_epoch = a.epoch_base;
   int flip = 0;
+  uint32_t phase[2] = {0u, 0u};
   const long long t_begin = clock64();
+  if (threadIdx.x == 0) {
+    cl_mbar_init(&sh.mbar[0], 1); cl_mbar_init(&sh.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();        // every CTA's mbarriers exist before anybody pushes into them
 
   if (!solver) {
     // ---- helper CTA: correspondence slices only
@@ -306,9 +344,9 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
   }
 
   // ---- solver CTA
-  if (threadIdx.x == 0) { sh.t_acc = 0; sh.t_sync = 0; sh.t_gather = 0; sh.n_coll = 0; }
+  if (threadIdx.x == 0) { sh.t_acc = 0; sh.t_sync = 0; sh.t_gather = 0; sh.n_coll = 0; sh.t_corr = 0; sh.t_scalar = 0; sh.t_mark = clock64(); }
   if (threadIdx.x < 32) {
-    ClusterBackend be(a, sh, cache, cluster, cmd_epoch, flip, rank);
+    ClusterBackend be(a, sh, cache, cmd_epoch, flip, phase, rank);
     OuterResult r;
     gicp_outer_loop(be, a.P, a.guess, r);
     cmd_epoch++;
@@ -319,7 +357,7 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
       *a.result = r;
       if (a.debug) {
         a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_acc; a.debug[2] = sh.t_sync; a.debug[3] = sh.n_coll;
-        a.debug[6] = sh.t_gather;
+        a.debug[6] = sh.t_scalar; a.debug[7] = sh.t_gather; a.debug[8] = sh.t_corr;
       }
     }
   } else {
@@ -328,8 +366,8 @@ align_cluster_kernel(const __grid_constant__ ClusterArgs a) {
       const int op = sh.op;
       if (op == OP_EXIT) break;
       if (op == OP_CORR) { cmd_epoch++; cl_do_correspond(a, sh, cache, cmd_epoch, rank); }
-      else if (op == OP_FDF) cl_do_objective<13>(sh, cache, cluster, flip);
-      else cl_do_objective<28>(sh, cache, cluster, flip);
+      else if (op == OP_FDF) cl_do_objective<13>(sh, cache, rank, flip, phase);
+      else cl_do_objective<28>(sh, cache, rank, flip, phase);
     }
   }
   cluster.sync();     // nobody leaves while its shared memory may still be read by a peer

@@ -759,6 +759,38 @@ int lb_gicp_set_target(lb_gicp* h, const void* pts, size_t n, size_t stride, siz
   return s;
 }
 
+// Pre-size the handle's cloud objects (current source / target and `spare_clouds` spares) for clouds of up to max_points
+// points, so that the steady state of a stream performs no device allocation (cudaMalloc / cudaFree synchronise the
+// whole device: with several handles working concurrently -- lb_odometry's workers -- one allocation stalls all of them).
+int lb_gicp_reserve(lb_gicp* h, size_t max_points, int spare_clouds) {
+  if (!h || max_points == 0 || spare_clouds < 0 || spare_clouds > 64) { set_error("lb_gicp_reserve: bad argument"); return LB_ERR_INVALID_ARG; }
+  LB_CUDA(cudaSetDevice(h->c.device));
+  const size_t cells = 8 * max_points + 1024;          // the automatic cell size keeps 3-12 points per occupied cell
+  auto size_cloud = [&](Cloud& cl) -> int {
+    LB_TRY(cl.raw.ensure(max_points)); LB_TRY(cl.pts.ensure(max_points));
+    LB_TRY(cl.cov.ensure(6 * max_points)); LB_TRY(cl.cell_start.ensure(cells + 1));
+    return LB_OK;
+  };
+  if (h->src.use_count() == 1 && h->src->owner == h) LB_TRY(size_cloud(*h->src));
+  if (h->tgt.use_count() == 1 && h->tgt->owner == h) LB_TRY(size_cloud(*h->tgt));
+  int have = 0;
+  for (auto& c : h->pool) if (c.use_count() == 1) { LB_TRY(size_cloud(*c)); have++; }
+  for (; have < spare_clouds; have++) {
+    std::shared_ptr<Cloud> c = std::make_shared<Cloud>();
+    c->device = h->c.device; c->owner = h;
+    LB_TRY(size_cloud(*c));
+    h->pool.push_back(c);
+  }
+  for (int k = 0; k < 2; k++) {
+    Scratch& S = h->sc[k];
+    LB_TRY(S.keys.ensure(max_points)); LB_TRY(S.cell_cnt.ensure(cells + 1)); LB_TRY(S.worklist.ensure(max_points));
+    LB_TRY(S.sort.ka.ensure(max_points)); LB_TRY(S.sort.kb.ensure(max_points));
+    LB_TRY(S.sort.va.ensure(max_points)); LB_TRY(S.sort.vb.ensure(max_points));
+  }
+  LB_TRY(h->src_work.ensure(max_points)); LB_TRY(h->corr.ensure(max_points)); LB_TRY(h->M.ensure(6 * max_points));
+  return LB_OK;
+}
+
 int lb_gicp_promote_source_to_target(lb_gicp* h) {
   if (!h) return LB_ERR_INVALID_ARG;
   if (!h->src->valid) { set_error("lb_gicp_promote_source_to_target: no source set"); return LB_ERR_EMPTY_SOURCE; }
@@ -905,6 +937,9 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
       cfg.attrs = at; cfg.numAttrs = 2;
+      // the solver cluster and its helpers spin on each other like the all-SM grid does: same per-device SM budget
+      static const int reserve_c = [] { const char* ev = getenv("LB_SM_RESERVE"); return ev ? atoi(ev) : 16; }();
+      lease.acquire(c.device, CL_SIZE * clusters, h->align_blocks - reserve_c);
       ScopedKernelTime kt(h, "align_persistent");
       cudaError_t e = cudaLaunchKernelEx(&cfg, align_cluster_kernel, ka);
       if (e == cudaSuccess) { launched = true; c.launches++; }
@@ -1238,6 +1273,12 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
   timers_collect(h);
   if (!strncmp(name, "debug", 5) && name[5] >= '0' && name[5] <= '9') {   // cycle counters of the last persistent align
     *ms_avg = (float)h->h_debug[name[5] - '0'];
+    return LB_OK;
+  }
+  if (!strncmp(name, "dbg", 3) && name[3] >= '0' && name[3] <= '9') {   // "dbgNN": any of the 16 debug words
+    const int i = atoi(name + 3);
+    if (i < 0 || i >= 16) return LB_ERR_INVALID_ARG;
+    *ms_avg = (float)h->h_debug[i];
     return LB_OK;
   }
   if (!strcmp(name, "probe_rounds")) { *ms_avg = (float)h->probe_rounds; return LB_OK; }

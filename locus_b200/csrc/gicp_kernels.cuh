@@ -1009,12 +1009,9 @@ struct CorrArgs {
   double* M;               // 6 per source point
 };
 
-__device__ __forceinline__ int correspond_point(const CorrArgs& a, const float* T, const double* R, int s) {
-  f4 p = a.src[s];
-  float qx, qy, qz;
-  xform(T, p.x, p.y, p.z, qx, qy, qz);
-  int bo; float bd;
-  int j = nn1(a.tgt, qx, qy, qz, a.max_d2, bo, bd);
+// second half of one correspondence: j = sorted position of the nearest target point (or -1): the matched point and
+// M = (R C1 R' + C2)^-1 are written for source point s.  returns 1 when matched.
+__device__ __forceinline__ int correspond_finish(const CorrArgs& a, const double* R, int s, int j) {
   double M[6] = {0., 0., 0., 0., 0., 0.};
   f4 c = f4{0.f, 0.f, 0.f, bits_to_float(-1)};
   if (j >= 0) {
@@ -1034,13 +1031,37 @@ __device__ __forceinline__ int correspond_point(const CorrArgs& a, const float* 
   return j >= 0 ? 1 : 0;
 }
 
+__device__ __forceinline__ int correspond_point(const CorrArgs& a, const float* T, const double* R, int s, long long* prof = nullptr) {
+  const long long t0 = prof ? clock64() : 0;
+  f4 p = a.src[s];
+  float qx, qy, qz;
+  xform(T, p.x, p.y, p.z, qx, qy, qz);
+  int bo; float bd;
+  int j = nn1_pruned(a.tgt, qx, qy, qz, a.max_d2, bo, bd);
+  const long long t1 = prof ? clock64() : 0;
+  const int r = correspond_finish(a, R, s, j);
+  if (prof) { prof[0] += t1 - t0; prof[1] += clock64() - t1; prof[2] += 1; }
+  return r;
+}
+
+// The correspondence step over the source points [begin, end) by all threads of a CTA; returns this thread's number of
+// matched points.  (A two-phase variant -- 3x3x3 block per thread, then a whole warp per undecided query -- was measured
+// slower on B200: at the first outer iteration a third of the queries are undecided, and 256 threads working on them
+// in parallel beat 8 warps working on them one after the other.)
+__device__ __forceinline__ int correspond_slice(const CorrArgs& a, const float* T, const double* R, int begin, int end,
+                                                long long* prof = nullptr) {
+  int hits = 0;
+  for (int s = begin + (int)threadIdx.x; s < end; s += (int)blockDim.x) hits += correspond_point(a, T, R, s, prof);
+  return hits;
+}
+
 __global__ void __launch_bounds__(128)
 nn_corr_kernel(CorrArgs a, Mat34 T, Mat33d R, int* __restrict__ m_count) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  int hit = 0;
-  if (s < a.n_src) hit = correspond_point(a, T.m, R.m, s);
-  uint32_t b = __ballot_sync(0xffffffffu, hit);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(m_count, __popc(b));
+  const int begin = min(a.n_src, (int)(blockIdx.x * blockDim.x)), end = min(a.n_src, begin + (int)blockDim.x);
+  int hits = correspond_slice(a, T.m, R.m, begin, end);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(m_count, hits);
 }
 
 // ------------------------------------------------------------------ K5 objective
@@ -1195,7 +1216,7 @@ enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4 };
 struct AlignShared {
   int op;
   int m;
-  long long t_reduce, t_wait, n_coll, t_scalar, t_mark;   // CTA 0 / thread 0 cycle counters
+  long long t_reduce, t_wait, n_coll, t_scalar, t_mark, t_corr;   // CTA 0 / thread 0 cycle counters
   long long poll[2];                                       // poll rounds of thread 0, sum of clock at poll completion
   float T[12];
   double R[9];
@@ -1246,8 +1267,11 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
   for (int i = 0; i < 9; i++) R[i] = sh.R[i];
   int begin, end;
   cta_chunk(a.c.n_src, begin, end);
-  int hits = 0;
-  for (int s = begin + threadIdx.x; s < end; s += AL_THREADS) hits += correspond_point(a.c, T, R, s);
+  const bool cprof = a.debug && blockIdx.x == 0 && threadIdx.x == 0;
+  const long long p0 = cprof ? clock64() : 0;
+  const int hits = correspond_slice(a.c, T, R, begin, end, cprof ? a.debug + 11 : nullptr);
+  const long long q0 = cprof ? clock64() : 0;
+  if (cprof) a.debug[10] += q0 - p0;
   // The correspondence arrays written above are only ever re-read by this CTA, after the CTA barrier below.
   __shared__ int s_hits[AL_THREADS];
   s_hits[threadIdx.x] = hits;
@@ -1263,7 +1287,9 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
     ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
     cache_load<PPL>(oa, begin, end, pc);
   }
+  const long long q1 = cprof ? clock64() : 0;
   grid_all_reduce<1>(a, sh, co, cnt);
+  if (cprof) { a.debug[14] += q1 - q0; a.debug[15] += clock64() - q1; }
 }
 
 template <int NV, int PPL>
@@ -1322,9 +1348,11 @@ struct DeviceBackendT {
     if (lane < 12) sh.T[lane] = T[lane];
     if (lane < 9) sh.R[lane] = R[lane];
     if (lane == 0) sh.op = OP_CORR;
+    const long long tc0 = clock64();
     __syncthreads();
     do_correspond<PPL>(a, sh, co, pc);
     m = (int)sh.bc[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const long long tc1 = clock64(); sh.t_corr += tc1 - tc0; sh.t_mark = tc1; }
     return m;
   }
 
@@ -1379,7 +1407,8 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   Collective co;
   co.epoch = a.epoch_base; co.flip = 0;
   const long long t_begin = clock64();
-  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
+  if (a.debug && blockIdx.x == 0 && threadIdx.x == 0) { for (int i = 10; i < 16; i++) a.debug[i] = 0; }
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_corr = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
   if (threadIdx.x < 32) {
     PointCacheT<PPL> pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
     DeviceBackendT<PPL> be(a, sh, co, pc_unused);
@@ -1391,7 +1420,7 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       *a.result = r;
       if (a.debug) {
         a.debug[0] = clock64() - t_begin; a.debug[1] = sh.t_reduce; a.debug[2] = sh.t_wait; a.debug[3] = sh.n_coll;
-        a.debug[6] = sh.t_scalar; a.debug[7] = sh.poll[0]; a.debug[8] = sh.poll[1];
+        a.debug[6] = sh.t_scalar; a.debug[7] = sh.poll[0]; a.debug[8] = sh.poll[1]; a.debug[9] = sh.t_corr;
       }
     }
   } else {
@@ -1644,7 +1673,7 @@ fitness_kernel(GridView g, const f4* __restrict__ raw, uint32_t n, Mat34 T, doub
     float x, y, z;
     xform_pcl(T.m, p.x, p.y, p.z, x, y, z);
     int bo; float bd;
-    int s = nn1(g, x, y, z, 3.0e38f, bo, bd);
+    int s = nn1_pruned(g, x, y, z, 3.0e38f, bo, bd);
     if (s >= 0 && (double)bd <= max_range) { acc[0] = (double)bd; acc[1] = 1.0; }
   }
   double tot = block_reduce<2, 4, 0>(acc, red);

@@ -147,6 +147,171 @@ LB_HD int nn1(const GridView& g, float qx, float qy, float qz, float max_d2, int
   return bs;
 }
 
+// Same result as nn1(), with far fewer candidates: what the correspondence step of align() calls.
+// nn1() scans every cell of a Chebyshev shell.  Here a cell (or a whole x-row of a shell) is only opened when the box it
+// covers can still hold a point closer than the best one found so far: per axis the gap between the query and the cell,
+// in cells, is (|i| - 1 + distance to the facing cell wall), so a lower bound of the distance to anything in the cell is
+// h * sqrt(gx^2 + gy^2 + gz^2), shrunk by the same safety margin as ring_bound2 (it covers the float rounding of the
+// cell assignment).  The centre cell goes first, so when the clouds are nearly aligned -- every outer iteration after
+// the first -- the search ends after a handful of cells instead of 27.  Exactness: a cell is skipped only if its lower
+// bound is strictly greater than the best d2 (or not below the gate), so neither a closer point nor an equidistant one
+// with a lower index can be missed; ties are still broken by (d2, original index).
+LB_HD float nn1_gap(int i, float f) {      // gap in cells along one axis between the query and cell offset i (f = fractional position in its own cell)
+  if (i == 0) return 0.0f;
+  float g = (i > 0) ? ((float)(i - 1) + (1.0f - f)) : ((float)(-i - 1) + f);
+  g = g - 0.01f;
+  return g > 0.0f ? g : 0.0f;
+}
+LB_HD int nn1_pruned(const GridView& g, float qx, float qy, float qz, float max_d2, int& best_orig, float& best_d2) {
+  float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  const float LIM = 1.0e9f;
+  ux = fminf(fmaxf(ux, -LIM), LIM); uy = fminf(fmaxf(uy, -LIM), LIM); uz = fminf(fmaxf(uz, -LIM), LIM);
+  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+  const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+  const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  const float minfrac = fminf(fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy)), fminf(fz, 1.0f - fz));
+  int r0, r1;
+  ring_range(g, cx, cy, cz, r0, r1);
+  const float hs = g.h * 0.9999f;
+  const float hh = hs * hs;
+  float bd2 = max_d2; int bi = -1; int bs = -1;
+  bool found = false;
+  // candidates [s, e) of the cell-sorted cloud: four loads in flight per trip (every lane of a warp reads its own
+  // addresses, and with one CTA per SM nothing else hides the L2 latency of a load -> use -> branch loop)
+  auto scan = [&](uint32_t s, uint32_t e) {
+    for (uint32_t i = s; i < e; i += 4) {
+      f4 pv[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (uint32_t u = 0; u < 4; u++) pv[u] = g.pts[(i + u < e) ? (i + u) : (e - 1)];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (uint32_t u = 0; u < 4; u++) {
+        if (i + u >= e) break;
+        const float d = dist2(qx, qy, qz, pv[u].x, pv[u].y, pv[u].z);
+        const int oi = float_to_bits(pv[u].w);
+        if (!found) {
+          if (d < max_d2) { found = true; bd2 = d; bi = oi; bs = (int)(i + u); }
+        } else if (better(d, oi, bd2, bi)) {
+          bd2 = d; bi = oi; bs = (int)(i + u);
+        }
+      }
+    }
+  };
+  // ---- step 1: the 3x3x3 block, cell by cell, centre first, each cell only while it can still hold a closer point
+  if (r0 <= 1) {
+    const int ORD[3] = {0, -1, 1};
+    for (int a = 0; a < 3; a++) {
+      const int z = cz + ORD[a];
+      if (z < 0 || z >= g.nz) continue;
+      const float gz = nn1_gap(ORD[a], fz);
+      for (int b = 0; b < 3; b++) {
+        const int y = cy + ORD[b];
+        if (y < 0 || y >= g.ny) continue;
+        const float gy = nn1_gap(ORD[b], fy);
+        const float row2 = (gy * gy + gz * gz) * hh;
+        if (row2 > bd2 || row2 >= max_d2) continue;
+        const int base = (z * g.ny + y) * g.nx;
+        // the row's four CSR offsets (cells cx-1, cx, cx+1) are fetched together, then centre, left, right
+        uint32_t cs4[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 4; c++) {
+          const int x = cx - 1 + c;
+          cs4[c] = (x >= 0 && x <= g.nx) ? g.cell_start[base + x] : 0u;
+        }
+        for (int c = 0; c < 3; c++) {
+          const int x = cx + ORD[c];
+          if (x < 0 || x >= g.nx) continue;
+          const float gx = nn1_gap(ORD[c], fx);
+          const float c2 = row2 + (gx * gx) * hh;
+          if (c2 > bd2 || c2 >= max_d2) continue;
+          scan(cs4[ORD[c] + 1], cs4[ORD[c] + 2]);
+        }
+      }
+    }
+    const float lb2 = ring_bound2(g, 1, minfrac);
+    if (r1 <= 1 || lb2 >= max_d2 || (found && bd2 < lb2)) { best_orig = bi; best_d2 = bd2; return bs; }
+    // ---- step 2: the block could not decide (the nearest point is farther than a cell away, or there is none in
+    // the block).  Everything that can still matter lies in the cube of cells whose lower bound is within the current
+    // bound (best so far, else the gate).  Its x-rows are visited ring by ring; a row costs TWO look-ups (the CSR
+    // offsets of the ends of its x-window, which shrinks with the remaining distance budget) and most rows of a
+    // surface-like cloud are empty -- the look-ups of 8 rows are issued together so their latencies overlap.
+    const float bound2 = found ? bd2 : max_d2;
+    const float G = sqrtf(bound2) / hs;
+    if (G < 12.0f) {
+      const int Rc = (int)(G + 1.01f) + 1;
+      for (int ring = 0; ring <= Rc; ring++) {
+        if (ring > 1) {
+          // every row of this ring is at least (ring - 1 + frac - 0.01) cells away in y or z: stop when that exceeds the bound
+          const float gmin = nn1_gap(ring, fmaxf(fmaxf(fy, 1.0f - fy), fmaxf(fz, 1.0f - fz)));   // (ring - 1) + the smallest distance to a y / z cell wall
+          if (gmin * gmin * hh > bd2 || gmin * gmin * hh >= max_d2) break;
+        }
+        const int side = 2 * ring + 1;
+        const int nrows = ring == 0 ? 1 : 8 * ring;             // rows on the perimeter of the (2 ring + 1)^2 square
+        for (int jb = 0; jb < nrows; jb += 8) {
+          uint32_t rs[8], re[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int u = 0; u < 8; u++) {
+            rs[u] = 0; re[u] = 0;
+            const int j = jb + u;
+            if (j >= nrows) continue;
+            // perimeter walk: top edge, bottom edge, then the two sides without their corners
+            int dy, dz;
+            if (ring == 0) { dy = 0; dz = 0; }
+            else if (j < side) { dz = -ring; dy = j - ring; }
+            else if (j < 2 * side) { dz = ring; dy = j - side - ring; }
+            else if (j < 2 * side + (side - 2)) { dy = -ring; dz = j - 2 * side - ring + 1; }
+            else { dy = ring; dz = j - 2 * side - (side - 2) - ring + 1; }
+            const int z = cz + dz, y = cy + dy;
+            if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+            const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
+            const float row2 = (gy * gy + gz * gz) * hh;
+            if (row2 > bd2 || row2 >= max_d2) continue;
+            // x-window: cells whose gap fits into what is left of the bound
+            const float rem = fminf(bd2, max_d2) - row2;
+            const int wx = (int)(sqrtf(rem > 0.f ? rem : 0.f) / hs + 1.01f) + 1;
+            const int xlo = imax_(cx - wx, 0), xhi = imin_(cx + wx, g.nx - 1);
+            if (xlo > xhi) continue;
+            const int base = (z * g.ny + y) * g.nx;
+            rs[u] = g.cell_start[base + xlo];
+            re[u] = g.cell_start[base + xhi + 1];
+          }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int u = 0; u < 8; u++) scan(rs[u], re[u]);
+        }
+      }
+      best_orig = bi; best_d2 = bd2;
+      return bs;
+    }
+  }
+  // ---- far queries (outside the grid, or an unbounded search that found nothing nearby): shell by shell like nn1
+  for (int r = (r0 <= 1 ? 2 : r0); r <= r1; r++) {
+    if (r > r0 || r0 > 0) {
+      const float lb2 = ring_bound2(g, r - 1, minfrac);      // everything not yet scanned is at least this far away
+      if (lb2 >= max_d2) break;
+      if (found && bd2 < lb2) break;
+    }
+    visit_shell(g, cx, cy, cz, r, [&](float x, float y, float z, int oi, int si) {
+      float d = dist2(qx, qy, qz, x, y, z);
+      if (!found) {
+        if (d < max_d2) { found = true; bd2 = d; bi = oi; bs = si; }
+      } else if (better(d, oi, bd2, bi)) {
+        bd2 = d; bi = oi; bs = si;
+      }
+    });
+  }
+  best_orig = bi; best_d2 = bd2;
+  return bs;
+}
+
 // Exact k nearest neighbours (unbounded radius, like FLANN nearestKSearch).
 // Kept ascending by (d2, orig index) in d2s/idx/sidx (arrays of length >= K).
 // Returns the number found (min(K, n)).

@@ -79,7 +79,7 @@ struct lb_odometry {
   std::vector<lb_gicp*> gicp;
   std::vector<Slot> ring;
   std::vector<Prepared> prep;          // same indexing as ring (ticket % R); used when share is on
-  bool share = false;                  // lb_odometry_set_cloud_sharing
+  bool share = true;                   // lb_odometry_set_cloud_sharing (on by default)
   cudaStream_t copy_stream = nullptr;
   cudaStream_t voxel_stream = nullptr;
 
@@ -273,7 +273,10 @@ int lb_odometry_create(int device, int depth, size_t max_points, uint32_t max_po
   for (int i = 0; st == LB_OK && i < depth; i++) {
     lb_gicp* g = nullptr;
     st = lb_gicp_create(device, &g);
+    // no device allocation in steady state: clouds of up to max_points points, and enough spare cloud objects for the
+    // sharing mode (a prepared cloud stays referenced until the next worker has adopted and used it)
     if (st == LB_OK) h->gicp.push_back(g);
+    if (st == LB_OK) st = lb_gicp_reserve(g, max_points, 8);
   }
   if (st == LB_OK) {
     h->ring.resize((size_t)depth + 3);

@@ -134,6 +134,16 @@ void hh_nn1_batch(void* g, const float* q, int nq, int stride_f, float max_d2, i
   }
 }
 
+void hh_nn1_block_batch(void* g, const float* q, int nq, int stride_f, float max_d2, int* idx, float* d2) {
+  HGrid* G = (HGrid*)g;
+  for (int i = 0; i < nq; i++) {
+    int bo; float bd;
+    int s = nn1_pruned(G->v, q[(size_t)i * stride_f], q[(size_t)i * stride_f + 1], q[(size_t)i * stride_f + 2], max_d2, bo, bd);
+    idx[i] = (s >= 0) ? bo : -1;
+    d2[i] = bd;
+  }
+}
+
 void hh_knn_batch(void* g, const float* q, int nq, int stride_f, int k, int* idx, float* d2) {
   HGrid* G = (HGrid*)g;
   for (int i = 0; i < nq; i++) {
@@ -200,7 +210,7 @@ struct CpuBackend {
       float qx, qy, qz;
       xform(T, src[i].x, src[i].y, src[i].z, qx, qy, qz);
       int bo; float bd;
-      int s = nn1(*tg, qx, qy, qz, max_d2, bo, bd);
+      int s = nn1_pruned(*tg, qx, qy, qz, max_d2, bo, bd);
       if (s >= 0) {
         f4 t = tg->pts[s];
         corr[i] = f4{t.x, t.y, t.z, bits_to_float(s)};

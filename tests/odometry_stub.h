@@ -77,6 +77,7 @@ inline int lb_voxel_filter(lb_voxel* h, const uint8_t* data, size_t n_pts, uint3
 }
 inline int lb_gicp_create(int, lb_gicp** h) { *h = new lb_gicp; return LB_OK; }
 inline int lb_gicp_destroy(lb_gicp* h) { delete h; return LB_OK; }
+inline int lb_gicp_reserve(lb_gicp*, size_t, int) { return LB_OK; }
 inline int lb_gicp_set_params(lb_gicp* h, const lb_gicp_params* p) { h->P = *p; return LB_OK; }
 inline int lb_gicp_launch_count(lb_gicp* h, uint64_t* n) { *n = h->launches; return LB_OK; }
 inline int lb_gicp_set_source(lb_gicp* h, const void* pts, size_t n, size_t stride, size_t, ptrdiff_t, int) {

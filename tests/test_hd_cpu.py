@@ -35,6 +35,24 @@ def test_ring_search_exact(harness, oracle, name, h):
     assert np.array_equal(idx, np.where(od < gate, oi, -1))
     harness.hh_nn1_batch(g, _p(q[8:]), len(q) - 8, 3, np.float32(3e38), _p(idx), _p(d2))
     assert np.array_equal(idx[: len(q) - 8], oi[8:]) and np.array_equal(d2[: len(q) - 8], od[8:])
+    # nn1_pruned (cells opened only while they can still hold a closer point; what the correspondence kernels call): same answers
+    harness.hh_nn1_block_batch.argtypes = harness.hh_nn1_batch.argtypes
+    harness.hh_nn1_block_batch(g, _p(q), len(q), 3, gate, _p(idx), _p(d2))
+    assert np.array_equal(idx, np.where(od < gate, oi, -1))
+    harness.hh_nn1_block_batch(g, _p(q[8:]), len(q) - 8, 3, np.float32(3e38), _p(idx), _p(d2))
+    assert np.array_equal(idx[: len(q) - 8], oi[8:]) and np.array_equal(d2[: len(q) - 8], od[8:])
+    # queries up to metres away from the cloud with gates around the cell size: the undecided-block path (x-row windows)
+    qq2 = (pts[rng.integers(0, len(pts), 1500)] + rng.normal(0, 0.7, (1500, 3))).astype(np.float32)
+    oi2, od2 = kt.nn_batch(qq2)
+    for gv in (np.float32(0.25), np.float32(1.0), np.float32(9.0)):
+        i2 = np.zeros(len(qq2), np.int32); dd2 = np.zeros(len(qq2), np.float32)
+        harness.hh_nn1_block_batch(g, _p(qq2), len(qq2), 3, gv, _p(i2), _p(dd2))
+        assert np.array_equal(i2, np.where(od2 < gv, oi2, -1)), (name, h, float(gv))
+        assert np.array_equal(dd2[od2 < gv], od2[od2 < gv])
+    far = (q[:64] * np.float32(3.0) + np.float32(11.0)).astype(np.float32)            # well outside the grid: generic shells
+    fi, fd = kt.nn_batch(far)
+    harness.hh_nn1_block_batch(g, _p(far), len(far), 3, np.float32(3e38), _p(idx), _p(d2))
+    assert np.array_equal(idx[:64], fi) and np.array_equal(d2[:64], fd)
     k = 20
     qq = pts[:300].copy()
     ki = np.zeros((len(qq), k), np.int32); kd = np.zeros((len(qq), k), np.float32)
