@@ -98,7 +98,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_s=0.01):
+    def __init__(self, index, period_s=0.1):     # an NVML query every 10 ms was measured to stall the blocking calls it sampled
         self.index = index
         self.period = period_s
         self.rows = []
@@ -117,6 +117,8 @@ class ClockSampler:
         return self.index
 
     def start(self):
+        if os.environ.get("LB_NO_SAMPLER"):      # diagnostic: is the sampling itself perturbing the arm it watches?
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -161,6 +163,8 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if os.environ.get("LB_NO_SAMPLER"):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "disabled (LB_NO_SAMPLER)"}
         if self.nvml is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
