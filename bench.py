@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scans-per-step", type=int, default=int(os.environ.get("LB_BATCH", "16")),
                     help="c2: one step = one batch of this many consecutive scans of the stream (b200 arm)")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("LB_DEPTH", "6")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("LB_DEPTH", "8")),
                     help="c2: registration workers of the odometry pipeline (aligns in flight)")
     ap.add_argument("--pipeline-ppc", type=int, default=int(os.environ.get("LB_PIPE_PPC", "1024")),
                     help="c2: align_points_per_cta of the pipeline's registration workers (sequential arm: library default 512)")

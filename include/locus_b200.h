@@ -91,7 +91,12 @@ typedef enum lb_optimizer { LB_OPT_BFGS = 0, LB_OPT_GAUSS_NEWTON = 1 } lb_optimi
  * L2); HOST_DRIVEN sequences one launch per objective evaluation from the host; PERSISTENT_CLUSTER runs the inner
  * solve inside one 16-CTA thread-block cluster (all-reduce through distributed shared memory; sources <= 32768
  * points, falls back to PERSISTENT otherwise) -- measured slower than PERSISTENT on B200, kept as an option. */
-typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_CLUSTER = 2 } lb_execution;
+/* STREAM_ORDERED: one outer iteration = two launches on the handle's stream, the correspondence search as a plain
+ * full-occupancy grid and the inner solve as the cooperative grid, the loop state resident in device memory, a few
+ * iterations enqueued ahead of the host (kernels after convergence return at once).  Same device functions and
+ * reduction shape as PERSISTENT: identical bits. */
+typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_CLUSTER = 2,
+                            LB_EXEC_STREAM_ORDERED = 3 } lb_execution;
 
 #define LB_NO_NORMALS ((ptrdiff_t)-1)
 

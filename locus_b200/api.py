@@ -20,7 +20,7 @@ _SO = os.environ.get("LOCUS_B200_LIB") or os.path.join(_HERE, "liblocus_b200.so"
 
 LB_MEM_HOST, LB_MEM_DEVICE = 0, 1
 LB_OPT_BFGS, LB_OPT_GAUSS_NEWTON = 0, 1
-LB_EXEC_PERSISTENT, LB_EXEC_HOST_DRIVEN, LB_EXEC_PERSISTENT_CLUSTER = 0, 1, 2
+LB_EXEC_PERSISTENT, LB_EXEC_HOST_DRIVEN, LB_EXEC_PERSISTENT_CLUSTER, LB_EXEC_STREAM_ORDERED = 0, 1, 2, 3
 LB_FLOAT32 = 7
 
 

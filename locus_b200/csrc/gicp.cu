@@ -120,6 +120,7 @@ struct lb_gicp {
   double* h_sums = nullptr; double* d_sums = nullptr;        // mapped pinned [32]
   int* h_m = nullptr;                                         // pinned
   OuterResult* d_result = nullptr; OuterResult* h_result = nullptr;
+  LoopState* d_loop = nullptr; LoopState* h_loop = nullptr;    // stream-ordered execution: the outer loop's state
   int align_blocks = 0;
   int knn_resident_blocks = 0;    // CTAs of knn_cov_quadreg_kernel that are resident at once on this device
   bool have_result = false;
@@ -239,6 +240,8 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
             cudaHostGetDevicePointer((void**)&h->d_sums, h->h_sums, 0) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_m, sizeof(int)) == cudaSuccess &&
             cudaMalloc((void**)&h->d_result, sizeof(OuterResult)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_loop, sizeof(LoopState)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_loop, sizeof(LoopState)) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_result, sizeof(OuterResult)) == cudaSuccess;
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMemset(h->d_barrier, 0, 2 * sizeof(unsigned)) == cudaSuccess;
@@ -708,6 +711,8 @@ int lb_gicp_destroy(lb_gicp* h) {
   if (h->h_sums) cudaFreeHost(h->h_sums);
   if (h->h_m) cudaFreeHost(h->h_m);
   if (h->d_result) cudaFree(h->d_result);
+  if (h->d_loop) cudaFree(h->d_loop);
+  if (h->h_loop) cudaFreeHost(h->h_loop);
   if (h->h_result) cudaFreeHost(h->h_result);
   for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto& t : h->timers) for (auto e : t.ev) cudaEventDestroy(e);
@@ -896,6 +901,59 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     HostBackend be; be.h = h; be.ca = ca;
     gicp_outer_loop(be, OP, guess, R);
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
+  } else if (h->P.execution == LB_EXEC_STREAM_ORDERED) {
+    // per launch of the solve kernel: one epoch per objective evaluation of ONE inner solve
+    const unsigned long long need = 16ull + (unsigned long long)h->P.max_optimizer_iterations * 402ull;
+    if (need * LOOP_K >= (1ull << 31)) { set_error("lb_gicp_align: max_optimizer_iterations too large"); out->status = LB_ERR_UNSUPPORTED; return LB_ERR_UNSUPPORTED; }
+    unsigned long long stride = 1ull << 12;
+    while (stride < need) stride <<= 1;
+    // loop state: transformation_ = I, R = rot(guess), nothing found yet
+    LoopState& L0 = *h->h_loop;
+    memset(&L0, 0, sizeof(L0));
+    outer_init(L0.s);
+    outer_rotation(L0.s, guess, L0.R);
+    LB_CUDA(cudaMemcpyAsync(h->d_loop, h->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, c.stream));
+    AlignArgs aa;
+    aa.c = ca; aa.slots = h->slots.p; aa.P = OP; aa.result = h->d_result;
+    static int poll_delay_s = -1;
+    if (poll_delay_s < 0) { const char* e = getenv("LB_POLL_DELAY"); poll_delay_s = e ? atoi(e) : (int)AL_POLL_DELAY; }
+    aa.poll_delay = poll_delay_s;
+    aa.debug = nullptr;
+    for (int i = 0; i < 16; i++) aa.guess[i] = guess[i];
+    const int grid = grid_for(h, ca.n_src);
+    static const int reserve_s = [] { const char* e = getenv("LB_SM_RESERVE"); return e ? atoi(e) : 16; }();
+    SmLease lease;
+    lease.acquire(c.device, grid, h->align_blocks - reserve_s);
+    const int chunk = cdiv(ca.n_src, grid);
+    void* kfn = chunk <= AL_PPC ? (void*)loop_solve_kernel<AL_PPL> : (void*)loop_solve_kernel<2 * AL_PPL>;
+    {
+      ScopedKernelTime kt(h, "align_persistent");
+      for (int done = 0; !done;) {
+        for (int k = 0; k < LOOP_K; k++) {
+          // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
+          if ((h->epoch_base >> 32) != ((h->epoch_base + stride) >> 32) || (h->epoch_base & 0xffffffffull) == 0) {
+            LB_CUDA(cudaMemsetAsync(h->slots.p, 0, (size_t)2 * h->c.sm_count * AL_PSTRIDE * sizeof(SlotWord), c.stream));
+            h->epoch_base = ((h->epoch_base >> 32) + 1) << 32 | (1ull << 20);
+          }
+          aa.epoch_base = h->epoch_base;
+          h->epoch_base += stride;
+          {
+            ScopedKernelTime kn(h, "loop_nn");
+            loop_nn_kernel<<<cdiv(ca.n_src, 128), 128, 0, c.stream>>>(ca, h->d_loop, k);
+          }
+          LoopState* dl = h->d_loop;
+          int kk = k;
+          void* args[] = {&aa, &dl, &kk};
+          ScopedKernelTime ks(h, "loop_solve");
+          LB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(AL_THREADS), args, 0, c.stream));
+          c.launches += 2;
+        }
+        LB_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, c.stream));
+        LB_CUDA(cudaStreamSynchronize(c.stream));
+        done = h->h_loop->s.done;
+      }
+    }
+    R = h->h_loop->result;
   } else {
     // the slot tags are the low 32 bits of the epoch: clear the slots whenever the base wraps them
     // One launch consumes a range of collective epochs (the slot tags): at most one per correspondence step plus one

@@ -1211,7 +1211,7 @@ struct AlignArgs {
   OuterResult* result;
 };
 
-enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4 };
+enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4, OP_LOAD = 5 };
 
 struct AlignShared {
   int op;
@@ -1430,6 +1430,92 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
       const int op = sh.op;
       if (op == OP_EXIT) break;
       if (op == OP_CORR) do_correspond<PPL>(a, sh, co, pc);
+      else if (op == OP_FDF) do_objective<13, PPL>(a, sh, co, pc);
+      else do_objective<28, PPL>(a, sh, co, pc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ stream-ordered align (LB_EXEC_STREAM_ORDERED)
+// The correspondence step wants the whole GPU at full occupancy (thousands of independent exact searches, the far ones
+// ~600 candidates each); the inner solve wants a small co-resident grid with everything in registers.  Inside ONE
+// persistent kernel the search runs on the solve's 8 warps per SM and takes ~90 us per outer iteration.  Here one
+// outer iteration is two launches on the handle's stream -- loop_nn_kernel (plain grid, 128-thread CTAs, the search at
+// full occupancy) and loop_solve_kernel (the cooperative grid: BFGS / GN solve, convergence test, next rotation) -- with
+// the state of computeTransformation (gicp.hpp:445-583) kept in device memory between them.  The host enqueues a few
+// iterations ahead; kernels of iterations after convergence return at once.  Same device functions, same reduction
+// shape as the single persistent kernel: identical bits.
+constexpr int LOOP_K = 4;            // outer iterations enqueued per batch
+struct LoopState {
+  OuterState s;
+  double R[9];                       // rotation of the next correspondence step (gicp.hpp:450-460)
+  int m[LOOP_K];                     // correspondences found by the search of iteration k of the batch
+  OuterResult result;
+};
+
+__global__ void __launch_bounds__(128)
+loop_nn_kernel(CorrArgs a, LoopState* __restrict__ st, int k) {
+  if (st->s.done) return;
+  float T[12]; double R[9];
+#pragma unroll
+  for (int i = 0; i < 12; i++) T[i] = st->s.T[i];
+#pragma unroll
+  for (int i = 0; i < 9; i++) R[i] = st->R[i];
+  const int begin = min(a.n_src, (int)(blockIdx.x * blockDim.x)), end = min(a.n_src, begin + (int)blockDim.x);
+  int hits = correspond_slice(a, T, R, begin, end);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&st->m[k], hits);
+}
+
+template <int PPL>
+__global__ void __launch_bounds__(AL_THREADS, AL_MINB)
+loop_solve_kernel(const __grid_constant__ AlignArgs a, LoopState* __restrict__ st, int k) {
+  __shared__ AlignShared sh;
+  if (st->s.done) return;                       // converged in an earlier launch of this batch (uniform for the grid)
+  Collective co;
+  co.epoch = a.epoch_base; co.flip = 0;
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_corr = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
+  if (threadIdx.x < 32) {
+    PointCacheT<PPL> pc_unused;
+    DeviceBackendT<PPL> be(a, sh, co, pc_unused);
+    OuterState s = st->s;
+    const int m = st->m[k];
+    be.m = m;
+    if (threadIdx.x == 0) sh.op = OP_LOAD;      // workers: this CTA's correspondences -> registers
+    __syncthreads();
+    outer_step(s, be, a.P, m);
+    if (threadIdx.x == 0) sh.op = OP_EXIT;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // every leader holds the same state: CTA 0 publishes it
+      if (!s.done) {
+        double R[9];
+        outer_rotation(s, a.guess, R);
+#pragma unroll
+        for (int i = 0; i < 9; i++) st->R[i] = R[i];
+      } else {
+        OuterResult r;
+        outer_finish(s, a.guess, r);
+        st->result = r;
+      }
+      st->m[k] = 0;                              // ready for the next batch
+      st->s = s;
+    }
+  } else {
+    PointCacheT<PPL> pc;
+    for (;;) {
+      __syncthreads();
+      const int op = sh.op;
+      if (op == OP_EXIT) break;
+      if (op == OP_LOAD) {
+        int begin, end;
+        cta_chunk(a.c.n_src, begin, end);
+        const int t = acc_lane();
+        if (end - begin <= PPL * AL_ACC && t >= 0 && t < AL_ACC) {
+          ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
+          cache_load<PPL>(oa, begin, end, pc);
+        }
+      }
       else if (op == OP_FDF) do_objective<13, PPL>(a, sh, co, pc);
       else do_objective<28, PPL>(a, sh, co, pc);
     }

@@ -1,6 +1,6 @@
 // b200_gicp_pcl.hpp -- pcl::Registration subclass backed by liblocus_b200.so.
 // Meant for a LOCUS catkin workspace (PCL + frontend_utils); this repository's image has neither, so here the
-// header is compiled against the minimal PCL mock under tests/pcl_stub/ (tests/test_shim_cpu.py: it parses, links and
+// header is compiled against the minimal PCL mock under tests/pcl_stub/ (tests/test_cabi_cpu.py, tests/test_gicp_gpu.py::test_pcl_shim_runs: it parses, links and
 // -- on a GPU box -- runs through pcl::Registration::align()).  See INTEGRATION.md.
 //
 // Drop-in for pcl::MultithreadedGeneralizedIterativeClosestPoint<PointF, PointF>

@@ -91,7 +91,7 @@ def test_covariances_and_nn_match_oracle(oracle):
     assert np.array_equal(d2, od) and np.array_equal(idx, oi)
 
 
-@pytest.mark.parametrize("execution", [1, 0, 2])   # host-driven, persistent (all-SM kernel), persistent cluster kernel
+@pytest.mark.parametrize("execution", [1, 0, 2, 3])   # host-driven, persistent (all-SM kernel), cluster kernel, stream-ordered
 def test_align_matches_oracle(oracle, execution):
     for name, s, t, prm in _cases(oracle):
         r = oracle.gicp_align(s, t, prm)
@@ -115,16 +115,17 @@ def test_align_with_guess_and_modes_agree(oracle):
     guess = F.se3([0.02, 0.01, 0], [0, 0, 0.005]).astype(np.float32)
     r = oracle.gicp_align(s, t, prm, guess=guess)
     Ts = []
-    for execution in (1, 0, 2):
+    for execution in (1, 0, 2, 3):
         g = _mk(prm, execution)
         g.setInputSource(s); g.setInputTarget(t)
-        g.align(guess)
+        res = g.align(guess)
         Ts.append(g.getFinalTransformation())
         dt, dr = F.pose_delta(r["T"], Ts[-1])
         assert dt <= TOL_T and dr <= TOL_R
-    # same device functions, same chunking, same reduction shape: host-driven and the persistent kernel agree
-    # bit for bit; the cluster kernel sums 16 partials instead of one per 512 points (~1e-16 relative)
-    assert np.array_equal(Ts[0], Ts[1])
+        assert res.iterations == r["iterations"]
+    # same device functions, same chunking, same reduction shape: host-driven, the persistent kernel and the
+    # stream-ordered launches agree bit for bit; the cluster kernel sums 16 partials instead of one per 512 points
+    assert np.array_equal(Ts[0], Ts[1]) and np.array_equal(Ts[0], Ts[3])
     dt, dr = F.pose_delta(Ts[0], Ts[2])
     assert dt <= 1e-6 and dr <= 1e-6
 
@@ -135,7 +136,7 @@ def test_gauss_newton_mode(oracle):
     name, s, t, prm = list(_cases(oracle))[3]
     prm.optimizer = 1
     r = oracle.gicp_align(s, t, prm)
-    for execution in (1, 0, 2):
+    for execution in (1, 0, 2, 3):
         g = _mk(prm, execution, optimizer=1)
         g.setInputSource(s); g.setInputTarget(t)
         g.align()
