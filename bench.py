@@ -529,8 +529,9 @@ class BenchCtx:
         g.setMaximumIterations(gc["max_iterations"]); g.setMaximumOptimizerIterations(gc["max_inner"])
         g.setMaxCorrespondenceDistance(gc["corr_dist"]); g.setTransformationEpsilon(gc["tf_eps"])
         g.setCorrespondenceRandomness(gc["k"]); g.setRANSACIterations(0)
-        g.setOptimizer(locus_b200.LB_OPT_BFGS); g.setExecution(locus_b200.LB_EXEC_PERSISTENT)
-        self.implementation = {"execution": "persistent cooperative kernel, exact (per-point) objective evaluation",
+        g.setOptimizer(locus_b200.LB_OPT_BFGS); g.setExecution(locus_b200.LB_EXEC_STREAM_ORDERED)
+        self.implementation = {"execution": "stream-ordered (search grids with TMA-staged candidates + cooperative solve grid per outer iteration), "
+                                            "exact (per-point) objective evaluation",
                                "optimizer": "bfgs (reference-exact)"}
         if os.environ.get("LB_CELL"):            # tuning aid: fixed voxel-hash cell size instead of the automatic one
             g.setIndexCellSize(float(os.environ["LB_CELL"]))

@@ -87,14 +87,16 @@ typedef enum lb_status {
 
 typedef enum lb_mem { LB_MEM_HOST = 0, LB_MEM_DEVICE = 1 } lb_mem;
 typedef enum lb_optimizer { LB_OPT_BFGS = 0, LB_OPT_GAUSS_NEWTON = 1 } lb_optimizer;
-/* PERSISTENT: one cooperative kernel per align() (leader warp + worker warps per CTA, grid-wide all-reduce through
- * L2); HOST_DRIVEN sequences one launch per objective evaluation from the host; PERSISTENT_CLUSTER runs the inner
- * solve inside one 16-CTA thread-block cluster (all-reduce through distributed shared memory; sources <= 32768
- * points, falls back to PERSISTENT otherwise) -- measured slower than PERSISTENT on B200, kept as an option. */
-/* STREAM_ORDERED: one outer iteration = two launches on the handle's stream, the correspondence search as a plain
- * full-occupancy grid and the inner solve as the cooperative grid, the loop state resident in device memory, a few
- * iterations enqueued ahead of the host (kernels after convergence return at once).  Same device functions and
- * reduction shape as PERSISTENT: identical bits. */
+/* STREAM_ORDERED (default): one outer iteration = three launches on the handle's stream -- the correspondence search as
+ * full-occupancy grids (candidates staged through shared memory with TMA bulk copies, the undecided queries of the
+ * whole cloud queued and finished by a second grid), then the inner solve as a cooperative grid (leader warp + worker
+ * warps per CTA, grid-wide all-reduce through L2) -- with the loop state resident in device memory and a few
+ * iterations enqueued ahead of the host (kernels after convergence return at once).
+ * PERSISTENT: the whole of align() as ONE cooperative kernel (the default of round 1; 10 % slower per align and 16 %
+ * slower in the pipeline on B200).  HOST_DRIVEN sequences one launch per objective evaluation from the host.
+ * PERSISTENT_CLUSTER runs the inner solve inside one 16-CTA thread-block cluster (all-reduce pushed through
+ * distributed shared memory; sources <= 45056 points, falls back to PERSISTENT otherwise).
+ * All four run the same device functions with the same reduction shape: identical bits. */
 typedef enum lb_execution { LB_EXEC_PERSISTENT = 0, LB_EXEC_HOST_DRIVEN = 1, LB_EXEC_PERSISTENT_CLUSTER = 2,
                             LB_EXEC_STREAM_ORDERED = 3 } lb_execution;
 
@@ -122,7 +124,7 @@ typedef struct lb_gicp_params {
   int recompute_source_covariance;      /* reference default 0; here 1 (normals are optional) */
   int recompute_target_covariance;
   int optimizer;                        /* lb_optimizer; LB_OPT_BFGS = reference-exact */
-  int execution;                        /* lb_execution; persistent cooperative kernel by default */
+  int execution;                        /* lb_execution; LB_EXEC_STREAM_ORDERED by default */
   /* accepted for interface compatibility, no effect on the GPU path */
   double euclidean_fitness_epsilon;     /* setEuclideanFitnessEpsilon (unused by gicp.hpp too) */
   int ransac_iterations;                /* setRANSACIterations(0) */

@@ -112,6 +112,9 @@ struct lb_gicp {
   DBuf<SlotWord> slots;
   unsigned long long epoch_base = 1ull << 20;
   long long* d_debug = nullptr; long long* h_debug = nullptr;
+  DBuf<long long> nnprof;          // tuning aid (LB_NNPROF)
+  DBuf<NnsFarItem> far_items;      // staged correspondence search: queue of the undecided queries of a step
+  DBuf<int> far_count;             // its two counters
   DBuf<SlotWord> cslots;           // cluster kernel: [CL_MAX_CTAS] hit-count words + [CL_CMD_WORDS] command words
   bool cluster_ok = false;
   int cluster_count = 0;           // clusters per launch (solver cluster + helpers)
@@ -213,6 +216,22 @@ float float_gate(double D) {
   return g;
 }
 
+// dynamic shared memory of a kernel that runs the staged correspondence search with `threads` threads per CTA
+static inline size_t nn_stage_bytes(const CorrArgs& ca, int threads) {
+  return ca.nn_mode ? (size_t)(threads / 32) * ((size_t)ca.nn_cap * sizeof(f4) + 16) : 0;
+}
+// Search of the correspondence step: 0 = every thread on its own (nn1_pruned), 1 = staged through shared memory with
+// cp.async, 2 = staged with TMA bulk copies (nn_staged.cuh).  Measured on B200 (tools/gpu/exp_nn.py, profiles/): the
+// staged search wins where the step is its own full-occupancy kernels (stream-ordered and host-driven execution) and
+// loses inside the persistent kernels (8 warps per SM and two more grid-wide exchanges per step), so that is the
+// default; LB_NN_MODE forces one mode everywhere (A/B aid).  All modes give identical bits.
+static inline void nn_stage_config(int execution, int& mode, int& cap) {
+  static const int forced = [] { const char* e = getenv("LB_NN_MODE"); return e ? atoi(e) : -1; }();
+  static const int c = [] { const char* e = getenv("LB_NN_CAP"); int v = e ? atoi(e) : 1024; return v < 64 ? 64 : (v > 1536 ? 1536 : v); }();
+  mode = forced >= 0 ? forced : ((execution == LB_EXEC_STREAM_ORDERED || execution == LB_EXEC_HOST_DRIVEN) ? 2 : 0);
+  cap = c;
+}
+
 int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   if (!out) { set_error("lb_gicp_create: null handle pointer"); return LB_ERR_INVALID_ARG; }
   lb_gicp* h = new lb_gicp;
@@ -256,7 +275,20 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   }
   // persistent kernel: one CTA per SM, co-resident (cooperative launch)
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel<AL_PPL>, AL_THREADS, 0);
+  {
+    // the staged correspondence search keeps one candidate stage per warp in dynamic shared memory
+    CorrArgs probe; nn_stage_config(LB_EXEC_STREAM_ORDERED, probe.nn_mode, probe.nn_cap); probe.nn_mode = 2;   // sizes only
+    const int big = (int)nn_stage_bytes(probe, AL_THREADS), small = (int)nn_stage_bytes(probe, 128);
+    if (cudaFuncSetAttribute(align_persistent_kernel<AL_PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+        cudaFuncSetAttribute(align_persistent_kernel<2 * AL_PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+        cudaFuncSetAttribute(nn_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small) != cudaSuccess ||
+        cudaFuncSetAttribute(loop_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small) != cudaSuccess) {
+      set_error("lb_gicp_create: shared-memory configuration refused: %s", cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return LB_ERR_CUDA;
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_persistent_kernel<AL_PPL>, AL_THREADS, big);
+  }
   {
     int knn_per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&knn_per_sm, knn_cov_quadreg_kernel<20, CovFin>, KQ_THREADS, 0);
@@ -592,6 +624,7 @@ struct HostBackend {
   CorrArgs ca;
   int m = 0;
   int status = LB_OK;
+  int corr_calls = 0;        // correspondence steps of this align(): from the second on, ca.corr bounds the search
 
   int correspond(const float* T, const double* R) {
     Ctx& c = h->c;
@@ -601,8 +634,11 @@ struct HostBackend {
     cudaMemsetAsync(h->d_m, 0, sizeof(int), c.stream);
     {
       ScopedKernelTime kt(h, "nn_corr");
-      nn_corr_kernel<<<cdiv(ca.n_src, 128), 128, 0, c.stream>>>(ca, t, r, h->d_m);
+      if (ca.nn_mode) cudaMemsetAsync(ca.far_count, 0, sizeof(int), c.stream);
+      nn_corr_kernel<<<cdiv(ca.n_src, 128), 128, nn_stage_bytes(ca, 128), c.stream>>>(ca, t, r, corr_calls > 0, h->d_m);
+      corr_calls++;
       c.launches++;
+      if (ca.nn_mode) { nn_far_kernel<<<4 * h->c.sm_count, NN_FAR_THREADS, 0, c.stream>>>(ca, t, r, h->d_m); c.launches++; }
     }
     cudaMemcpyAsync(h->h_m, h->d_m, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
     if (cudaStreamSynchronize(c.stream) != cudaSuccess) { status = LB_ERR_CUDA; return 0; }
@@ -679,7 +715,7 @@ int lb_gicp_default_params(lb_gicp_params* p) {
   p->recompute_source_covariance = 1;
   p->recompute_target_covariance = 1;
   p->optimizer = LB_OPT_BFGS;
-  p->execution = LB_EXEC_PERSISTENT;
+  p->execution = LB_EXEC_STREAM_ORDERED;
   p->euclidean_fitness_epsilon = 0.0;
   p->ransac_iterations = 0;
   p->num_threads = 1;
@@ -703,6 +739,7 @@ int lb_gicp_destroy(lb_gicp* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   h->src_work.release(); h->corr.release(); h->M.release(); h->slots.release(); h->cslots.release();
+  h->far_items.release(); h->far_count.release(); h->nnprof.release();
   h->io.release(); h->io_idx.release(); h->io_d2.release();
   if (h->d_barrier) cudaFree(h->d_barrier);
   if (h->d_debug) cudaFree(h->d_debug);
@@ -793,6 +830,7 @@ int lb_gicp_reserve(lb_gicp* h, size_t max_points, int spare_clouds) {
     LB_TRY(S.sort.va.ensure(max_points)); LB_TRY(S.sort.vb.ensure(max_points));
   }
   LB_TRY(h->src_work.ensure(max_points)); LB_TRY(h->corr.ensure(max_points)); LB_TRY(h->M.ensure(6 * max_points));
+  LB_TRY(h->far_items.ensure(max_points)); LB_TRY(h->far_count.ensure(2));
   return LB_OK;
 }
 
@@ -891,17 +929,33 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   ca.tgt = h->tgt->view(); ca.tgt_cov = h->tgt->cov.p; ca.src = h->src_work.p; ca.src_cov = h->src->cov.p;
   ca.n_src = (int)N; ca.max_d2 = float_gate(h->P.max_correspondence_distance * h->P.max_correspondence_distance);
   ca.corr = h->corr.p; ca.M = h->M.p;
+  static const int exec_override = [] { const char* e = getenv("LB_EXEC_OVERRIDE"); return e ? atoi(e) : -1; }();   // tuning aid
+  const int execution = exec_override >= 0 ? exec_override : h->P.execution;
+  nn_stage_config(execution, ca.nn_mode, ca.nn_cap);
+  ca.far_items = nullptr; ca.far_count = nullptr;
+  if (ca.nn_mode) {
+    LB_TRY(h->far_items.ensure(N)); LB_TRY(h->far_count.ensure(2));
+    LB_CUDA(cudaMemsetAsync(h->far_count.p, 0, 2 * sizeof(int), c.stream));
+    ca.far_items = h->far_items.p; ca.far_count = h->far_count.p;
+  }
+  ca.prof = nullptr;
+  static const bool nnprof = getenv("LB_NNPROF") != nullptr;
+  if (nnprof && ca.nn_mode) {
+    LB_TRY(h->nnprof.ensure(8 * (N / 32 + 2)));
+    LB_CUDA(cudaMemsetAsync(h->nnprof.p, 0, 8 * (N / 32 + 2) * sizeof(long long), c.stream));
+    ca.prof = h->nnprof.p;
+  }
   OuterParams OP;
   OP.rotation_epsilon = h->P.rotation_epsilon; OP.transformation_epsilon = h->P.transformation_epsilon;
   OP.max_iterations = h->P.max_iterations; OP.max_inner_iterations = h->P.max_optimizer_iterations;
   OP.optimizer = h->P.optimizer == LB_OPT_GAUSS_NEWTON ? 1 : 0;
 
   OuterResult R;
-  if (h->P.execution == LB_EXEC_HOST_DRIVEN) {
+  if (execution == LB_EXEC_HOST_DRIVEN) {
     HostBackend be; be.h = h; be.ca = ca;
     gicp_outer_loop(be, OP, guess, R);
     if (be.status != LB_OK) { set_error("lb_gicp_align: CUDA failure in host-driven loop: %s", cudaGetErrorString(cudaGetLastError())); out->status = be.status; return be.status; }
-  } else if (h->P.execution == LB_EXEC_STREAM_ORDERED) {
+  } else if (execution == LB_EXEC_STREAM_ORDERED) {
     // per launch of the solve kernel: one epoch per objective evaluation of ONE inner solve
     const unsigned long long need = 16ull + (unsigned long long)h->P.max_optimizer_iterations * 402ull;
     if (need * LOOP_K >= (1ull << 31)) { set_error("lb_gicp_align: max_optimizer_iterations too large"); out->status = LB_ERR_UNSUPPORTED; return LB_ERR_UNSUPPORTED; }
@@ -939,7 +993,8 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
           h->epoch_base += stride;
           {
             ScopedKernelTime kn(h, "loop_nn");
-            loop_nn_kernel<<<cdiv(ca.n_src, 128), 128, 0, c.stream>>>(ca, h->d_loop, k);
+            loop_nn_kernel<<<cdiv(ca.n_src, 128), 128, nn_stage_bytes(ca, 128), c.stream>>>(ca, h->d_loop, k);
+            if (ca.nn_mode) { loop_far_kernel<<<4 * h->c.sm_count, NN_FAR_THREADS, 0, c.stream>>>(ca, h->d_loop, k); c.launches++; }
           }
           LoopState* dl = h->d_loop;
           int kk = k;
@@ -976,7 +1031,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
     }
     const unsigned long long epoch_base = h->epoch_base;
     h->epoch_base += stride;
-    bool use_cluster = h->cluster_ok && h->P.execution == LB_EXEC_PERSISTENT_CLUSTER && N <= (uint32_t)(CL_SIZE * CL_CAP);
+    bool use_cluster = h->cluster_ok && execution == LB_EXEC_PERSISTENT_CLUSTER && N <= (uint32_t)(CL_SIZE * CL_CAP);
     bool launched = false;
     SmLease lease;     // released when this block ends, i.e. after the stream sync below
     if (use_cluster) {
@@ -1020,7 +1075,7 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
       // points per CTA up to 512: 4 per accumulating lane in registers; up to 1024: 8 (beyond: read back from L2)
       const int chunk = cdiv(ca.n_src, grid);
       void* kfn = chunk <= AL_PPC ? (void*)align_persistent_kernel<AL_PPL> : (void*)align_persistent_kernel<2 * AL_PPL>;
-      LB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(AL_THREADS), args, 0, c.stream));
+      LB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(AL_THREADS), args, nn_stage_bytes(ca, AL_THREADS), c.stream));
       c.launches++;
     }
     if (h->timing) LB_CUDA(cudaMemcpyAsync(h->h_debug, h->d_debug, (16 + 2 * AL_MAXCTA) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
@@ -1030,6 +1085,26 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   }
   LB_CUDA(cudaEventRecord(h->ev[2], c.stream));
   LB_CUDA(cudaStreamSynchronize(c.stream));
+  if (ca.prof) {   // tuning aid: what the warps of the LAST correspondence step spent where
+    const size_t nw = (N + 31) / 32;
+    std::vector<long long> hp(8 * nw);
+    cudaMemcpy(hp.data(), ca.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long sum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mx[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int hist[5] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < nw; i++) {
+      const long long chunks = hp[8 * i + 7] >> 40; hp[8 * i + 7] &= (1ll << 40) - 1;
+      sum[8] += chunks; if (chunks > mx[8]) mx[8] = chunks;
+      for (int k = 0; k < 8; k++) { sum[k] += hp[8 * i + k]; if (hp[8 * i + k] > mx[k]) mx[k] = hp[8 * i + k]; }
+      const long long f = hp[8 * i + 2];
+      hist[f == 0 ? 0 : f <= 2 ? 1 : f <= 8 ? 2 : f <= 16 ? 3 : 4]++;
+    }
+    fprintf(stderr, "[nnprof] warps %zu iters %d | staged pass cycles mean %.0f max %lld | far pass mean %.0f max %lld | far lanes mean %.2f max %lld "
+            "hist(0,1-2,3-8,9-16,17+) %d %d %d %d %d | finish mean %.0f max %lld | staged lanes mean %.1f | candidates per warp mean %.0f max %lld\n",
+            nw, R.nr_iterations, (double)sum[0] / nw, mx[0], (double)sum[1] / nw, mx[1], (double)sum[2] / nw, mx[2], hist[0], hist[1], hist[2], hist[3],
+            hist[4], (double)sum[3] / nw, mx[3], (double)sum[4] / nw, (double)sum[5] / nw, mx[5]);
+    fprintf(stderr, "[nnprof]   rows+csr mean %.0f max %lld | copy+wait mean %.0f max %lld | scan mean %.0f max %lld | chunks mean %.2f max %lld\n",
+            (double)sum[4] / nw, mx[4], (double)sum[6] / nw, mx[6], (double)sum[7] / nw, mx[7], (double)sum[8] / nw, mx[8]);
+  }
   timers_collect(h);
   for (int i = 0; i < 16; i++) { out->final_transformation[i] = R.final_T[i]; h->final_T[i] = R.final_T[i]; out->transformation[i] = R.prev_T[i]; }
   h->have_result = true;

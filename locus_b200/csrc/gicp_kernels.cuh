@@ -15,6 +15,7 @@
 
 #include "bfgs.h"
 #include "grid.h"
+#include "nn_staged.cuh"
 #include "prims.cuh"
 
 namespace lb {
@@ -1007,6 +1008,11 @@ struct CorrArgs {
   float max_d2;            // gate, float-exact equivalent of corr_dist^2 (gicp.hpp:438,483)
   f4* corr;                // matched target point, w = sorted target index or -1
   double* M;               // 6 per source point
+  int nn_mode;             // search of the correspondence step: 0 each thread on its own, 1 staged (cp.async), 2 staged (TMA)
+  int nn_cap;              // staged: candidate points per warp stage
+  NnsFarItem* far_items;   // staged: queue of the undecided queries of one correspondence step (n_src entries) ...
+  int* far_count;          // ... and its two counters (steps alternate between them)
+  long long* prof;         // tuning aid (LB_NNPROF): 8 words per group of 32 source points, or null
 };
 
 // second half of one correspondence: j = sorted position of the nearest target point (or -1): the matched point and
@@ -1045,9 +1051,8 @@ __device__ __forceinline__ int correspond_point(const CorrArgs& a, const float* 
 }
 
 // The correspondence step over the source points [begin, end) by all threads of a CTA; returns this thread's number of
-// matched points.  (A two-phase variant -- 3x3x3 block per thread, then a whole warp per undecided query -- was measured
-// slower on B200: at the first outer iteration a third of the queries are undecided, and 256 threads working on them
-// in parallel beat 8 warps working on them one after the other.)
+// matched points.  Serial form: every thread searches on its own (nn1_pruned).  (A two-phase variant -- 3x3x3 block per
+// thread, then a whole warp per undecided query -- was measured slower on B200.)
 __device__ __forceinline__ int correspond_slice(const CorrArgs& a, const float* T, const double* R, int begin, int end,
                                                 long long* prof = nullptr) {
   int hits = 0;
@@ -1055,12 +1060,103 @@ __device__ __forceinline__ int correspond_slice(const CorrArgs& a, const float* 
   return hits;
 }
 
+// Staged form (nn_staged.cuh): the same points go to the same threads, but the 32 searches of a warp run together and
+// fetch their candidates through the warp's shared-memory stage.  have_prev: a.corr still holds the matches of the
+// previous outer iteration of THIS align() (same target), which bound the new search.  All threads of the CTA call it.
+struct NnsCta { unsigned char* base; int cap; };     // dynamic shared memory: per warp cap points + one mbarrier
+__device__ __forceinline__ size_t nns_warp_bytes(int cap) { return (size_t)cap * sizeof(f4) + 16; }
+__device__ __forceinline__ NnsWarp nns_warp_view(const NnsCta& c) {
+  NnsWarp w;
+  w.stage = reinterpret_cast<f4*>(c.base + (size_t)(threadIdx.x >> 5) * nns_warp_bytes(c.cap));
+  w.cap = c.cap;
+  w.mbar = reinterpret_cast<unsigned long long*>(w.stage + c.cap);
+  w.phase = 0;
+  return w;
+}
+// once per kernel, by every warp, before the first staged search
+__device__ __forceinline__ void nns_warp_init(NnsWarp& w) {
+  if ((threadIdx.x & 31) == 0) nns_mbar_init(w.mbar);
+  __syncwarp();
+}
+template <bool TMA>
+__device__ __forceinline__ int correspond_slice_staged(const CorrArgs& a, const float* T, const double* R, int begin, int end,
+                                                       bool have_prev, NnsWarp& w, int step_parity) {
+  int hits = 0;
+  const int lane = threadIdx.x & 31;
+  const NnsFarQueue fq{a.far_items, a.far_count + step_parity};
+  for (int base = begin + (int)(threadIdx.x - lane); base < end; base += (int)blockDim.x) {
+    const int s = base + lane;
+    const bool active = s < end;
+    float qx = 0.f, qy = 0.f, qz = 0.f, ub2 = 0.f;
+    bool have_ub = false;
+    if (active) {
+      const f4 p = a.src[s];
+      xform(T, p.x, p.y, p.z, qx, qy, qz);
+      if (have_prev) {
+        const float4 c = __ldcg(reinterpret_cast<const float4*>(a.corr + s));  // possibly written by another SM (far queue)
+        if (float_to_bits(c.w) >= 0) { have_ub = true; ub2 = dist2(qx, qy, qz, c.x, c.y, c.z); }
+      }
+    }
+    int bo; float bd;
+    long long* wp = a.prof ? a.prof + 8 * (size_t)(base >> 5) : nullptr;     // tuning aid: per-warp cycle counters
+    const int j = nn1_staged<TMA>(a.tgt, active, qx, qy, qz, a.max_d2, have_ub, ub2, w, bo, bd, a.far_items ? &fq : nullptr, s, wp);
+    const long long tf0 = wp ? clock64() : 0;
+    if (active && j != NNS_DEFERRED) hits += correspond_finish(a, R, s, j);
+    if (wp && lane == 0) wp[3] = clock64() - tf0;
+  }
+  return hits;
+}
+
+// The queued (far) queries of one correspondence step, one per warp: warp `gwarp` of `nwarps` takes items gwarp,
+// gwarp + nwarps, ... and searches each one's remaining ball with all its lanes (nn1_far_item).  Returns this thread's
+// number of matched points (lane 0 counts).  (A lane-per-item variant -- the compacted items through the staged pass
+// again, rows in batches of 9 -- was measured slower: 57 vs 42 us per step on the C2 pairs.)
+__device__ __forceinline__ int correspond_far(const CorrArgs& a, const float* T, const double* R, int nfar, int gwarp, int nwarps,
+                                              uint32_t* scratch) {
+  int hits = 0;
+  const int lane = threadIdx.x & 31;
+  for (int i = gwarp; i < nfar; i += nwarps) {
+    const NnsFarItem it = a.far_items[i];
+    const f4 p = a.src[it.s];
+    float qx, qy, qz;
+    xform(T, p.x, p.y, p.z, qx, qy, qz);
+    const int j = nn1_far_item(a.tgt, it, qx, qy, qz, a.max_d2, scratch);
+    if (lane == 0) hits += correspond_finish(a, R, it.s, j);
+    __syncwarp();
+  }
+  return hits;
+}
+
+// nn_mode: 0 = serial, 1 = staged with cp.async, 2 = staged with TMA bulk copies
+__device__ __forceinline__ int correspond_slice_mode(const CorrArgs& a, const float* T, const double* R, int begin, int end,
+                                                     bool have_prev, NnsWarp& w, int step_parity, long long* prof = nullptr) {
+  if (a.nn_mode == 1) return correspond_slice_staged<false>(a, T, R, begin, end, have_prev, w, step_parity);
+  if (a.nn_mode == 2) return correspond_slice_staged<true>(a, T, R, begin, end, have_prev, w, step_parity);
+  return correspond_slice(a, T, R, begin, end, prof);
+}
+
+extern __shared__ __align__(16) unsigned char nns_dyn_smem[];
+
 __global__ void __launch_bounds__(128)
-nn_corr_kernel(CorrArgs a, Mat34 T, Mat33d R, int* __restrict__ m_count) {
+nn_corr_kernel(CorrArgs a, Mat34 T, Mat33d R, int have_prev, int* __restrict__ m_count) {
   const int begin = min(a.n_src, (int)(blockIdx.x * blockDim.x)), end = min(a.n_src, begin + (int)blockDim.x);
-  int hits = correspond_slice(a, T.m, R.m, begin, end);
+  NnsCta nc{nns_dyn_smem, a.nn_cap};
+  NnsWarp w = nns_warp_view(nc);
+  if (a.nn_mode) nns_warp_init(w);
+  int hits = correspond_slice_mode(a, T.m, R.m, begin, end, have_prev != 0, w, 0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(m_count, hits);
+}
+
+// second kernel of a staged correspondence step outside the persistent kernels: the queued queries
+constexpr int NN_FAR_THREADS = 128;
+__global__ void __launch_bounds__(NN_FAR_THREADS)
+nn_far_kernel(CorrArgs a, Mat34 T, Mat33d R, int* __restrict__ m_count) {
+  __shared__ uint32_t scratch[NN_FAR_THREADS / 32][66];
+  const int nfar = a.far_count[0];
+  const int wib = threadIdx.x >> 5;
+  int hits = correspond_far(a, T.m, R.m, nfar, blockIdx.x * (NN_FAR_THREADS / 32) + wib, gridDim.x * (NN_FAR_THREADS / 32), scratch[wib]);
   if ((threadIdx.x & 31) == 0 && hits) atomicAdd(m_count, hits);
 }
 
@@ -1102,13 +1198,15 @@ __device__ __forceinline__ void cache_load(const ObjArgs& a, int begin, int end,
   for (int j = 0; j < PPL; j++) {
     int s = begin + t + AL_ACC * j;
     bool ok = (t >= 0 && t < AL_ACC && s < end);
-    f4 c = ok ? a.corr[s] : f4{0.f, 0.f, 0.f, bits_to_float(-1)};
+    // corr / M may have been written by a warp of another SM (far queue of the staged search): read them from L2
+    f4 c = f4{0.f, 0.f, 0.f, bits_to_float(-1)};
+    if (ok) { const float4 cc = __ldcg(reinterpret_cast<const float4*>(a.corr + s)); c = f4{cc.x, cc.y, cc.z, cc.w}; }
     ok = ok && float_to_bits(c.w) >= 0;
     f4 p = ok ? a.src[s] : f4{0.f, 0.f, 0.f, 0.f};
     pc.px[j] = p.x; pc.py[j] = p.y; pc.pz[j] = p.z;
     pc.qx[j] = c.x; pc.qy[j] = c.y; pc.qz[j] = c.z;
 #pragma unroll
-    for (int e = 0; e < 6; e++) pc.M[j][e] = ok ? a.M[6 * (size_t)s + e] : 0.0;   // M = 0: exact zero contribution
+    for (int e = 0; e < 6; e++) pc.M[j][e] = ok ? __ldcg(a.M + 6 * (size_t)s + e) : 0.0;   // M = 0: exact zero contribution
   }
 }
 
@@ -1130,12 +1228,13 @@ __device__ __forceinline__ void objective_from_global(const ObjArgs& a, const fl
   const int t = acc_lane();
   if (t < 0 || t >= AL_ACC) return;
   for (int s = begin + t; s < end; s += AL_ACC) {
-    f4 c = a.corr[s];
+    const float4 cc = __ldcg(reinterpret_cast<const float4*>(a.corr + s));     // L2: possibly written by another SM
+    f4 c = f4{cc.x, cc.y, cc.z, cc.w};
     f4 p = a.src[s];
     double M[6];
     const double* m = a.M + 6 * (size_t)s;
 #pragma unroll
-    for (int e = 0; e < 6; e++) M[e] = m[e];
+    for (int e = 0; e < 6; e++) M[e] = __ldcg(m + e);
     if (float_to_bits(c.w) < 0) { c = f4{0.f, 0.f, 0.f, 0.f}; p = c; }
     if constexpr (NV == 13) objective_terms(T, p.x, p.y, p.z, c.x, c.y, c.z, M, acc);
     else gn_terms(T, dP, dT, dS, p.x, p.y, p.z, c.x, c.y, c.z, M, acc);
@@ -1216,6 +1315,8 @@ enum { OP_NONE = 0, OP_CORR = 1, OP_FDF = 2, OP_GN = 3, OP_EXIT = 4, OP_LOAD = 5
 struct AlignShared {
   int op;
   int m;
+  int corr_calls;                                          // correspondence steps done by this launch
+  unsigned nn_phase[AL_THREADS / 32];                      // staged search: mbarrier parity of every warp
   long long t_reduce, t_wait, n_coll, t_scalar, t_mark, t_corr;   // CTA 0 / thread 0 cycle counters
   long long poll[2];                                       // poll rounds of thread 0, sum of clock at poll completion
   float T[12];
@@ -1269,13 +1370,32 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
   cta_chunk(a.c.n_src, begin, end);
   const bool cprof = a.debug && blockIdx.x == 0 && threadIdx.x == 0;
   const long long p0 = cprof ? clock64() : 0;
-  const int hits = correspond_slice(a.c, T, R, begin, end, cprof ? a.debug + 11 : nullptr);
+  NnsCta nc{nns_dyn_smem, a.c.nn_cap};
+  NnsWarp w = nns_warp_view(nc);
+  w.phase = sh.nn_phase[threadIdx.x >> 5];
+  const int calls = sh.corr_calls;                 // correspondence steps of this launch before this one
+  const bool have_prev = calls > 0;                // a.c.corr holds the matches of the previous outer iteration
+  int hits = correspond_slice_mode(a.c, T, R, begin, end, have_prev, w, calls & 1, cprof ? a.debug + 11 : nullptr);
+  if ((threadIdx.x & 31) == 0) sh.nn_phase[threadIdx.x >> 5] = w.phase;
+  if (a.c.nn_mode && a.c.far_items) {
+    // the undecided queries of ALL CTAs were queued: once everybody has queued (grid-wide exchange), every warp of the
+    // grid takes its share of them
+    __threadfence();
+    double zero[1] = {0.0};
+    grid_all_reduce<1>(a, sh, co, zero);
+    const int nfar = *(volatile int*)(a.c.far_count + (calls & 1));
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.c.far_count[(calls & 1) ^ 1] = 0;      // the next step's counter
+    hits += correspond_far(a.c, T, R, nfar, (int)blockIdx.x * (AL_THREADS / 32) + (int)(threadIdx.x >> 5),
+                           (int)gridDim.x * (AL_THREADS / 32), reinterpret_cast<uint32_t*>(w.stage));
+    __threadfence();
+  }
   const long long q0 = cprof ? clock64() : 0;
   if (cprof) a.debug[10] += q0 - p0;
-  // The correspondence arrays written above are only ever re-read by this CTA, after the CTA barrier below.
+  // The correspondence arrays may have been written by other CTAs (far queue): they are re-read (L2) after the exchange below.
   __shared__ int s_hits[AL_THREADS];
   s_hits[threadIdx.x] = hits;
   __syncthreads();
+  if (threadIdx.x == 0) sh.corr_calls++;
   double cnt[1] = {0.0};
   const int t = acc_lane();
   if (t >= 0 && t < AL_ACC) {
@@ -1283,12 +1403,12 @@ __device__ __forceinline__ void do_correspond(const AlignArgs& a, AlignShared& s
     for (int k = t; k < AL_THREADS; k += AL_ACC) h += s_hits[k];
     cnt[0] = (double)h;
   }
+  const long long q1 = cprof ? clock64() : 0;
+  grid_all_reduce<1>(a, sh, co, cnt);
   if (end - begin <= PPL * AL_ACC && t >= 0 && t < AL_ACC) {
     ObjArgs oa{a.c.src, a.c.corr, a.c.M, a.c.n_src};
     cache_load<PPL>(oa, begin, end, pc);
   }
-  const long long q1 = cprof ? clock64() : 0;
-  grid_all_reduce<1>(a, sh, co, cnt);
   if (cprof) { a.debug[14] += q1 - q0; a.debug[15] += clock64() - q1; }
 }
 
@@ -1408,7 +1528,9 @@ align_persistent_kernel(const __grid_constant__ AlignArgs a) {
   co.epoch = a.epoch_base; co.flip = 0;
   const long long t_begin = clock64();
   if (a.debug && blockIdx.x == 0 && threadIdx.x == 0) { for (int i = 10; i < 16; i++) a.debug[i] = 0; }
-  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_corr = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; }
+  if (threadIdx.x == 0) { sh.t_reduce = 0; sh.t_wait = 0; sh.n_coll = 0; sh.t_scalar = 0; sh.t_corr = 0; sh.t_mark = clock64(); sh.poll[0] = 0; sh.poll[1] = 0; sh.corr_calls = 0; }
+  if ((threadIdx.x & 31) == 0) sh.nn_phase[threadIdx.x >> 5] = 0;
+  if (a.c.nn_mode) { NnsCta nc{nns_dyn_smem, a.c.nn_cap}; NnsWarp w0 = nns_warp_view(nc); nns_warp_init(w0); }
   if (threadIdx.x < 32) {
     PointCacheT<PPL> pc_unused;   // warp 0 does not accumulate; kept apart from the workers' register-resident cache
     DeviceBackendT<PPL> be(a, sh, co, pc_unused);
@@ -1462,9 +1584,29 @@ loop_nn_kernel(CorrArgs a, LoopState* __restrict__ st, int k) {
 #pragma unroll
   for (int i = 0; i < 9; i++) R[i] = st->R[i];
   const int begin = min(a.n_src, (int)(blockIdx.x * blockDim.x)), end = min(a.n_src, begin + (int)blockDim.x);
-  int hits = correspond_slice(a, T, R, begin, end);
+  NnsCta nc{nns_dyn_smem, a.nn_cap};
+  NnsWarp w = nns_warp_view(nc);
+  if (a.nn_mode) nns_warp_init(w);
+  int hits = correspond_slice_mode(a, T, R, begin, end, st->s.nr > 0, w, k & 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&st->m[k], hits);
+}
+
+// the queued queries of iteration k's search (staged search only), one per warp of a fixed grid
+__global__ void __launch_bounds__(NN_FAR_THREADS)
+loop_far_kernel(CorrArgs a, LoopState* __restrict__ st, int k) {
+  if (st->s.done) return;
+  float T[12]; double R[9];
+#pragma unroll
+  for (int i = 0; i < 12; i++) T[i] = st->s.T[i];
+#pragma unroll
+  for (int i = 0; i < 9; i++) R[i] = st->R[i];
+  const int nfar = a.far_count[k & 1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.far_count[(k & 1) ^ 1] = 0;       // the next iteration's counter
+  __shared__ uint32_t scratch[NN_FAR_THREADS / 32][66];
+  const int wib = threadIdx.x >> 5;
+  int hits = correspond_far(a, T, R, nfar, blockIdx.x * (NN_FAR_THREADS / 32) + wib, gridDim.x * (NN_FAR_THREADS / 32), scratch[wib]);
   if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&st->m[k], hits);
 }
 

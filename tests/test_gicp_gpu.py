@@ -130,6 +130,32 @@ def test_align_with_guess_and_modes_agree(oracle):
     assert dt <= 1e-6 and dr <= 1e-6
 
 
+def test_correspondence_search_modes_agree(tmp_path):
+    """The three searches of the correspondence step -- every thread on its own (nn1_pruned), candidates staged through
+    shared memory with cp.async, staged with TMA bulk copies + the device-wide queue of undecided queries -- are exact:
+    forced one after the other (LB_NN_MODE, read once per process) they give the same bits in every execution mode, on
+    clouds with duplicates, gates from a fifth of a cell to many cells, a poor guess and a half-empty target."""
+    import subprocess
+    import sys
+    child = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nn_modes_child.py")
+    res = []
+    for mode in (0, 1, 2):
+        out = str(tmp_path / ("m%d.npz" % mode))
+        env = dict(os.environ, LB_NN_MODE=str(mode))
+        subprocess.run([sys.executable, child, out], check=True, env=env, timeout=900)
+        res.append(np.load(out))
+    assert len(res[0].files) >= 30
+    for k in res[0].files:
+        for m in (1, 2):
+            assert np.array_equal(res[0][k], res[m][k]), (k, m, res[0][k], res[m][k])
+    # and across execution modes (same reduction shape): persistent == stream-ordered == host-driven
+    for k in res[0].files:
+        if "_e0_" in k:
+            assert np.array_equal(res[0][k], res[0][k.replace("_e0_", "_e3_")]), k
+            k1 = k.replace("_e0_", "_e1_")
+            if k1 in res[0].files: assert np.array_equal(res[0][k], res[0][k1]), k
+
+
 def test_gauss_newton_mode(oracle):
     """GN (north_star's 6x6 solve) vs the oracle's GN restatement, and vs BFGS at a tight tolerance
     where both reach the same fixed point."""
