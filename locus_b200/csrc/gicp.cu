@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <deque>
 #include <vector>
 
 #include "align_cluster.cuh"
@@ -134,7 +135,7 @@ struct lb_gicp {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timing = false;          // event timers of every kernel class + the align kernel's cycle counters
   bool timing_light = false;    // only the CUDA-event pair around the align kernel (what a throughput run can afford)
-  std::vector<KTimer> timers;
+  std::deque<KTimer> timers;       // deque: a ScopedKernelTime keeps a pointer to its timer while nested scopes may add timers
   uint64_t probe_rounds = 0;       // occupancy-probe rounds since creation (diagnostic)
 };
 
