@@ -1149,6 +1149,29 @@ nn_corr_kernel(CorrArgs a, Mat34 T, Mat33d R, int have_prev, int* __restrict__ m
   if ((threadIdx.x & 31) == 0 && hits) atomicAdd(m_count, hits);
 }
 
+// Exact 1-NN of arbitrary query points, 32 queries per warp through the staged search (lb_gicp_nn_target; LB_NN=staged /
+// staged_tma): first look = half a cell around the query, undecided queries finished by the warp itself.
+template <bool TMA>
+__global__ void __launch_bounds__(128)
+nn_query_staged_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, int32_t* __restrict__ idx,
+                       float* __restrict__ d2, float max_d2, int cap, long long* __restrict__ count) {
+  NnsCta nc{nns_dyn_smem, cap};
+  NnsWarp w = nns_warp_view(nc);
+  nns_warp_init(w);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) {
+    const float* p = reinterpret_cast<const float*>(q + (size_t)i * stride);
+    qx = p[0]; qy = p[1]; qz = p[2];
+  }
+  int bo; float bd;
+  long long wp[8];                                // profiling launch only: wp[5] = candidates the warp staged
+  const int j = nn1_staged<TMA>(g, active, qx, qy, qz, max_d2, false, 0.f, w, bo, bd, nullptr, 0, count ? wp : nullptr);
+  if (active) { idx[i] = j >= 0 ? bo : -1; d2[i] = j >= 0 ? bd : max_d2; }
+  if (count && (threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)wp[5]);
+}
+
 // second kernel of a staged correspondence step outside the persistent kernels: the queued queries
 constexpr int NN_FAR_THREADS = 128;
 __global__ void __launch_bounds__(NN_FAR_THREADS)

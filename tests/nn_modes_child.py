@@ -39,4 +39,18 @@ for execution in (0, 3, 1):
         r = g.align(guess)
         out["%s_e%d_T" % (name, execution)] = g.getFinalTransformation()
         out["%s_e%d_s" % (name, execution)] = np.array([r.iterations, r.n_correspondences, r.n_objective_evals, r.converged, g.getFitnessScore()], dtype=np.float64)
+# the same searches behind lb_gicp_nn_target (LB_NN picks the kernel): indices and squared distances of arbitrary queries
+a = F.random_scene(20000, 3)
+rng = np.random.default_rng(11)
+q = np.concatenate([a[rng.integers(0, len(a), 3000)] + rng.normal(0, 0.05, (3000, 3)),       # near the surfaces
+                    rng.uniform(-5, 25, (500, 3)),                                           # anywhere, also outside the grid
+                    a[:200]]).astype(np.float32)                                             # exact hits
+g = locus_b200.GicpB200()
+g.setInputTarget(a)
+idx, d2 = g.nearestTarget(q)
+out["nn_idx"] = idx; out["nn_d2"] = d2
+src, tgt = F.garage()
+g.setInputTarget(tgt)
+idx, d2 = g.nearestTarget(src)
+out["nn_garage_idx"] = idx; out["nn_garage_d2"] = d2
 np.savez(sys.argv[1], **out)

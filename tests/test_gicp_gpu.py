@@ -141,7 +141,7 @@ def test_correspondence_search_modes_agree(tmp_path):
     res = []
     for mode in (0, 1, 2):
         out = str(tmp_path / ("m%d.npz" % mode))
-        env = dict(os.environ, LB_NN_MODE=str(mode))
+        env = dict(os.environ, LB_NN_MODE=str(mode), LB_NN=("warp", "staged", "staged_tma")[mode])   # also the kernel of lb_gicp_nn_target
         subprocess.run([sys.executable, child, out], check=True, env=env, timeout=900)
         res.append(np.load(out))
     assert len(res[0].files) >= 30

@@ -80,7 +80,7 @@ def main():
     best = max(runs, key=lambda r: r["frac"])
     print(json.dumps({"workload": "C5-shaped NN search", "map_points": a.map, "queries": a.queries,
                       "sorted_queries": bool(a.sorted_queries), "peak_gbs": peak, "peak_source": src,
-                      "kernel": "nn_query_warp_kernel", "bytes_model": "B_nn = Nq * (16 + 16*c + 8), c = target points a query visits "
+                      "kernel": os.environ.get("LB_NN", "staged_tma"), "bytes_model": "B_nn = Nq * (16 + 16*c + 8), c = target points a query visits "
                       "(counted on the device): a coarser voxel hash visits more points per query, i.e. moves more bytes "
                       "per query at a higher rate but answers fewer queries per second",
                       "runs": runs, "frac": best["frac"], "achieved_gbs": best["achieved_gbs"], "kernel_ms": best["kernel_ms"],
