@@ -862,9 +862,10 @@ def run_c2(ctx):
     peak, peak_src = measured_peak_hbm()
     bytes_per_launch = float(np.mean(iters * 88.0 * nsrc + evals * 80.0 * ncorr)) if len(iters) else 0.0
     achieved = (bytes_per_launch / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "align_persistent_kernel (K4 NN-correspondence + K5 objective + BFGS, resident)",
+    roofline = {"bound": "hbm", "kernel": ALIGN_KERNELS,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                "traffic": ncu_traffic("align_persistent_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": align_traffic(float(iters.mean()) if len(iters) else 0.0), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms, "launches_timed": int(k_n), "avg_launch_ms_sequential": k_seq_ms,
                 "kernel_share_of_sequential_step": (k_seq_ms / (seq_ms_max / n_seq)) if seq_ms_max else None,
                 "aligns_in_flight_mean": (k_ms / (dev_ms_max / n_scans)) if dev_ms_max else None,
@@ -1025,7 +1026,7 @@ def run_submap(ctx):
     if nn is not None:
         roofline = nn
     else:
-        roofline = {"bound": "hbm", "kernel": "align_persistent_kernel (K4 NN-correspondence in the 500k submap + K5 objective + BFGS, resident)",
+        roofline = {"bound": "hbm", "kernel": ALIGN_KERNELS + " -- target = the 500k submap",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": k_ms,
                     "launches_timed": shares["align_persistent"]["launches"],
@@ -1155,6 +1156,18 @@ def nn_search_roofline(ctx, d_map, n_map):
             "bytes_model": "B_nn = Nq (16 + 16 c + 8) (SURVEY 8d), c = target points THIS kernel fetches per query (its first look is a "
                            "ball of half a cell, not the 3x3x3 block the round-1 kernel scanned: the same answers from ~5x fewer "
                            "bytes, so queries_per_s, not the fraction, is the figure to compare across rounds)"}
+
+
+ALIGN_KERNELS = ("the kernels of one align() -- per outer iteration loop_nn_kernel + loop_far_kernel (K4: exact 1-NN correspondences, "
+                 "Mahalanobis) and loop_solve_kernel (K5 objective + BFGS, cooperative grid); 'launch' below = one align()")
+
+
+def align_traffic(iterations_per_align):
+    """DRAM bytes of one align() from the committed ncu capture: per-launch bytes of its three kernels x outer iterations."""
+    parts = [ncu_traffic(k) for k in ("loop_nn_kernel", "loop_far_kernel", "loop_solve_kernel")]
+    if any(p is None for p in parts) or iterations_per_align <= 0:
+        return None
+    return float(sum(parts) * iterations_per_align)
 
 
 def ncu_traffic(kernel):

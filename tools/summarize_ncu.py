@@ -35,10 +35,11 @@ def launches(path, out):
         v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("lb::", "").replace("void ", "")
         seq.append((name, v))
-    idx = [i for i, s in enumerate(seq) if "align_" in s[0]]
+    # one align() = one prep_source_kernel launch (the stream-ordered execution has no single align kernel)
+    idx = [i for i, s in enumerate(seq) if "prep_source" in s[0]]
     with open(out, "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none): one bench step\n\n")
-        f.write("Source: `%s` (%d launches captured); the step between the last two align kernels.\n" % (path, len(seq)))
+        f.write("Source: `%s` (%d launches captured); the step between the last two align() calls (prep_source_kernel launches).\n" % (path, len(seq)))
         f.write("Durations under ncu are serialised (and cold-cache unless --cache-control none): compare SHARES.\n\n")
         if len(idx) >= 2:
             step = seq[idx[-2] + 1: idx[-1] + 1]
