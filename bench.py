@@ -1143,16 +1143,24 @@ def nn_search_roofline(ctx, d_map, n_map):
     ms, n = gicp.kernelTime("nn_query")
     c = gicp.kernelTime("debug4")[0] / float(nq)
     cell = gicp.kernelTime("cell_tgt")[0]
+    dense = gicp.kernelTime("dense_tgt")[0]
+    first_ms, far_ms, n_second = gicp.kernelTime("nn_query_first")[0], gicp.kernelTime("nn_query_far")[0], gicp.kernelTime("debug6")[0]
     gicp.resetKernelTimes(False)
     peak, peak_src = measured_peak_hbm()
     b = nq * (16.0 + 16.0 * c + 8.0)
     ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    return {"bound": "hbm", "kernel": "nn_query_staged_kernel<TMA> (exact 1-NN of the scan's points in the 10M-point map; 32 queries per warp, "
-                                      "candidates staged through shared memory with cp.async.bulk)",
+    staged = first_ms > 0
+    return {"bound": "hbm", "kernel": ("nn_query_staged_kernel<TMA> + nn_query_far_kernel (exact 1-NN of the scan's points in the 10M-point map; 32 queries "
+                                       "per warp, candidates staged through shared memory with cp.async.bulk)") if staged else
+                                      "nn_query_warp_kernel (exact 1-NN of the scan's points in the 10M-point map; one query per warp)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
-            "traffic": ncu_traffic("nn_query_staged_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": b,
+            "traffic": ncu_traffic("nn_query_staged_kernel" if staged else "nn_query_warp_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": b,
             "avg_launch_ms": ms, "launches_timed": int(n), "queries": nq, "map_points": n_map, "candidates_per_query": c,
             "cell_m": cell, "cell": "automatic", "queries_per_s": nq / (ms * 1e-3) if ms else 0.0,
+            "map_points_in_cells_with_more_than_32_points": dense,
+            "kernel_choice": "points in dense cells > 10 % of the map -> nn_query_warp_kernel (32 lanes share one query's candidates), else the "
+                             "staged kernels (first_look / second kernel times below are 0 when the warp kernel ran)",
+            "first_look_kernel_ms": first_ms, "second_kernel_ms": far_ms, "queries_left_to_second_kernel": n_second,
             "bytes_model": "B_nn = Nq (16 + 16 c + 8) (SURVEY 8d), c = target points THIS kernel fetches per query (its first look is a "
                            "ball of half a cell, not the 3x3x3 block the round-1 kernel scanned: the same answers from ~5x fewer "
                            "bytes, so queries_per_s, not the fraction, is the figure to compare across rounds)"}

@@ -41,6 +41,8 @@ struct Cloud {
   bool index_dirty = false;    // uploaded + geometry chosen, CSR index not built yet (built lazily in align)
   int keys_slot = -1;          // >= 0: that slot's scratch holds this cloud's cell keys and per-cell counts for `geom`
                                // (left there by the accepted round of the occupancy probe)
+  uint64_t dense_generation = 0;   // generation for which dense_fraction was measured (lb_gicp_nn_target picks its kernel by it)
+  double dense_fraction = 0.0;     // share of the points that sit in cells with more than 32 points
 
   GridView view() const {
     GridView v;
@@ -1172,20 +1174,40 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
     LB_CUDA(cudaMemcpyAsync(h->io.p, xyz, n * stride, cudaMemcpyHostToDevice, c.stream));
     dq = h->io.p; di = h->io_idx.p; dd = h->io_d2.p;
   }
+  if (h->tgt->dense_generation != h->tgt->generation) {      // once per target cloud: how uneven it is over its voxel hash
+    Cloud& t = *h->tgt;
+    LB_CUDA(cudaMemsetAsync(h->d_debug + 6, 0, sizeof(long long), c.stream));
+    cell_density_kernel<<<c.sm_count * 4, 256, 0, c.stream>>>(t.cell_start.p, t.ncells, 32u, (unsigned long long*)(h->d_debug + 6));
+    long long dense = 0;
+    LB_CUDA(cudaMemcpyAsync(&dense, h->d_debug + 6, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    LB_CUDA(cudaStreamSynchronize(c.stream));
+    t.dense_fraction = t.n ? (double)dense / (double)t.n : 0.0;
+    t.dense_generation = t.generation;
+    c.launches++;
+  }
   {
     ScopedKernelTime kt(h, "nn_query");
-    // 32 queries per warp through the staged search with TMA bulk copies (nn_staged.cuh): 2.24 G queries/s on the
-    // 10 M-point / 200 k-query shape, against 1.28 for the warp-per-query kernel and 1.84 for the cp.async staging.
-    // LB_NN = warp | thread | staged selects the others (A/B aid).
-    static int nnv = -1;
-    if (nnv < 0) { const char* e = getenv("LB_NN"); nnv = !e ? 3 : !strcmp(e, "thread") ? 0 : !strcmp(e, "warp") ? 1 : !strcmp(e, "staged") ? 2 : 3; }
+    // Default: 32 queries per warp through the staged search with TMA bulk copies, undecided queries queued and finished
+    // one per warp by a second kernel (nn_staged.cuh).  LB_NN = warp | thread | staged selects the warp-per-query kernel,
+    // the thread-per-query kernel, or the cp.async staging (A/B aid; numbers in profiles/README.md).
+    static int nnv_env = -2;
+    if (nnv_env == -2) { const char* e = getenv("LB_NN"); nnv_env = !e ? -1 : !strcmp(e, "thread") ? 0 : !strcmp(e, "warp") ? 1 : !strcmp(e, "staged") ? 2 : 3; }
+    int nnv = nnv_env;
+    if (nnv < 0) nnv = h->tgt->dense_fraction > 0.10 ? 1 : 3;       // locally very dense (raw) maps: the warp-per-query kernel
     CorrArgs probe; nn_stage_config(LB_EXEC_STREAM_ORDERED, probe.nn_mode, probe.nn_cap); probe.nn_mode = 2;
     if (nnv == 0) {
       nn_query_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f);
-    } else if (nnv == 2) {
-      nn_query_staged_kernel<false><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, nullptr);
-    } else if (nnv == 3) {
-      nn_query_staged_kernel<true><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, nullptr);
+    } else if (nnv >= 2) {
+      LB_TRY(h->far_items.ensure(N)); LB_TRY(h->far_count.ensure(2));
+      LB_CUDA(cudaMemsetAsync(h->far_count.p, 0, sizeof(int), c.stream));
+      {
+        ScopedKernelTime k1(h, "nn_query_first");
+        if (nnv == 2) nn_query_staged_kernel<false><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, h->far_items.p, h->far_count.p, nullptr);
+        else nn_query_staged_kernel<true><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, h->far_items.p, h->far_count.p, nullptr);
+      }
+      ScopedKernelTime k2(h, "nn_query_far");
+      nn_query_far_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(h->tgt->view(), dq, (uint32_t)stride, di, dd, 3.0e38f, h->far_items.p, h->far_count.p);
+      c.launches++;
     } else {
       int blocks = cdiv(N, 8);
       if (blocks > c.sm_count * 8) blocks = c.sm_count * 8;
@@ -1194,12 +1216,19 @@ int lb_gicp_nn_target(lb_gicp* h, const void* xyz, size_t n, size_t stride, int3
     c.launches++;
   }
   if (h->timing) {   // profiling aid: mean number of target points a query visits -> h_debug[4], h_debug[5]
-    static int nnv2 = -1;
-    if (nnv2 < 0) { const char* e = getenv("LB_NN"); nnv2 = !e ? 3 : !strcmp(e, "thread") ? 0 : !strcmp(e, "warp") ? 1 : !strcmp(e, "staged") ? 2 : 3; }
-    LB_CUDA(cudaMemsetAsync(h->d_debug + 4, 0, sizeof(long long), c.stream));
-    if (nnv2 >= 2) {      // the staged search: candidates staged by the first look (the few undecided queries' second look is not counted)
+    static int nnv2_env = -2;
+    if (nnv2_env == -2) { const char* e = getenv("LB_NN"); nnv2_env = !e ? -1 : !strcmp(e, "thread") ? 0 : !strcmp(e, "warp") ? 1 : !strcmp(e, "staged") ? 2 : 3; }
+    const int nnv2 = nnv2_env >= 0 ? nnv2_env : (h->tgt->dense_fraction > 0.10 ? 1 : 3);
+    LB_CUDA(cudaMemsetAsync(h->d_debug + 4, 0, 2 * sizeof(long long), c.stream));
+    if (nnv2 >= 2) {      // the staged search: candidates staged by the first look; h_debug[6] = queries left to the second kernel
       CorrArgs probe; nn_stage_config(LB_EXEC_STREAM_ORDERED, probe.nn_mode, probe.nn_cap); probe.nn_mode = 2;
-      nn_query_staged_kernel<true><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, h->d_debug + 4);
+      LB_CUDA(cudaMemsetAsync(h->far_count.p, 0, sizeof(int), c.stream));
+      nn_query_staged_kernel<true><<<cdiv(N, 128), 128, nn_stage_bytes(probe, 128), c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, di, dd, 3.0e38f, probe.nn_cap, h->far_items.p, h->far_count.p, h->d_debug + 4);
+      nn_query_far_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(h->tgt->view(), dq, (uint32_t)stride, di, dd, 3.0e38f, h->far_items.p, h->far_count.p);
+      int nf = 0;
+      LB_CUDA(cudaMemcpyAsync(&nf, h->far_count.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      LB_CUDA(cudaStreamSynchronize(c.stream));
+      h->h_debug[6] = nf;
     } else {
       nn_count_kernel<<<cdiv(N, 128), 128, 0, c.stream>>>(h->tgt->view(), dq, N, (uint32_t)stride, 3.0e38f,
                                                           (unsigned long long*)(h->d_debug + 4));
@@ -1437,6 +1466,7 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
   if (!strcmp(name, "pool_clouds")) { *ms_avg = (float)h->pool.size(); return LB_OK; }
   if (!strcmp(name, "cell_src")) { *ms_avg = h->src->geom.h; return LB_OK; }      // cell size of the current index (m)
   if (!strcmp(name, "cell_tgt")) { *ms_avg = h->tgt->geom.h; return LB_OK; }
+  if (!strcmp(name, "dense_tgt")) { *ms_avg = (float)h->tgt->dense_fraction; return LB_OK; }   // share of target points in cells with > 32 points
   if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100
     int i = atoi(name + 5);
     if (i < 0 || i >= AL_MAXCTA) return LB_ERR_INVALID_ARG;

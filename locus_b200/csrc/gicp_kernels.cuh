@@ -1149,12 +1149,30 @@ nn_corr_kernel(CorrArgs a, Mat34 T, Mat33d R, int have_prev, int* __restrict__ m
   if ((threadIdx.x & 31) == 0 && hits) atomicAdd(m_count, hits);
 }
 
-// Exact 1-NN of arbitrary query points, 32 queries per warp through the staged search (lb_gicp_nn_target; LB_NN=staged /
-// staged_tma): first look = half a cell around the query, undecided queries finished by the warp itself.
+// How uneven the cloud is over its voxel hash: points that sit in cells holding more than `thresh` points.  The staged
+// search scans a lane's candidates sequentially, which is the right shape for voxel-filtered clouds (a handful of
+// points per cell) and the wrong one for raw, locally very dense maps, where the warp-per-query kernel shares a
+// query's candidates among 32 lanes.
+__global__ void cell_density_kernel(const uint32_t* __restrict__ cell_start, size_t ncells, uint32_t thresh, unsigned long long* __restrict__ out) {
+  unsigned long long dense = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = cell_start[i + 1] - cell_start[i];
+    if (c > thresh) dense += c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dense += __shfl_xor_sync(0xffffffffu, dense, o);
+  if ((threadIdx.x & 31) == 0 && dense) atomicAdd(out, dense);
+}
+
+// Exact 1-NN of arbitrary query points (lb_gicp_nn_target), two kernels: 32 queries per warp through the staged search
+// -- first look = half a cell around the query -- with the undecided queries queued; then one warp per queued query:
+// the ball of its best candidate so far (nn1_ball_warp), or, when the first look found nothing, the ring-by-ring search
+// of the warp-per-query kernel (nn1_warp).
 template <bool TMA>
 __global__ void __launch_bounds__(128)
 nn_query_staged_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, uint32_t stride, int32_t* __restrict__ idx,
-                       float* __restrict__ d2, float max_d2, int cap, long long* __restrict__ count) {
+                       float* __restrict__ d2, float max_d2, int cap, NnsFarItem* __restrict__ far_items, int* __restrict__ far_count,
+                       long long* __restrict__ count) {
   NnsCta nc{nns_dyn_smem, cap};
   NnsWarp w = nns_warp_view(nc);
   nns_warp_init(w);
@@ -1167,9 +1185,40 @@ nn_query_staged_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t n, ui
   }
   int bo; float bd;
   long long wp[8];                                // profiling launch only: wp[5] = candidates the warp staged
-  const int j = nn1_staged<TMA>(g, active, qx, qy, qz, max_d2, false, 0.f, w, bo, bd, nullptr, 0, count ? wp : nullptr);
-  if (active) { idx[i] = j >= 0 ? bo : -1; d2[i] = j >= 0 ? bd : max_d2; }
+  const NnsFarQueue fq{far_items, far_count};
+  const int j = nn1_staged<TMA>(g, active, qx, qy, qz, max_d2, false, 0.f, w, bo, bd, &fq, (int)i, count ? wp : nullptr);
+  if (active && j != NNS_DEFERRED) { idx[i] = j >= 0 ? bo : -1; d2[i] = j >= 0 ? bd : max_d2; }
   if (count && (threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)wp[5]);
+}
+
+__global__ void __launch_bounds__(256)
+nn_query_far_kernel(GridView g, const uint8_t* __restrict__ q, uint32_t stride, int32_t* __restrict__ idx, float* __restrict__ d2,
+                    float max_d2, const NnsFarItem* __restrict__ far_items, const int* __restrict__ far_count) {
+  __shared__ NnWarpSmem sm[8];
+  const int nfar = *far_count;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned long long gate_key = (unsigned long long)__float_as_uint(max_d2) << 32;
+  for (int k = blockIdx.x * 8 + wib; k < nfar; k += gridDim.x * 8) {
+    const NnsFarItem it = far_items[k];
+    const float* p = reinterpret_cast<const float*>(q + (size_t)it.s * stride);
+    const float qx = p[0], qy = p[1], qz = p[2];
+    int oi = -1; float od = max_d2;
+    bool done = false;
+    if (it.best < gate_key) {                     // a candidate is known: everything that matters lies within its distance
+      int rbs, rbi; float rbd;
+      done = nn1_ball_warp(g, qx, qy, qz, max_d2, it.ball2, true, __uint_as_float((unsigned)(it.best >> 32)),
+                           (int)(unsigned)(it.best & 0xffffffffull), it.bs, reinterpret_cast<uint32_t*>(&sm[wib]), rbs, rbi, rbd);
+      oi = rbi; od = rbd;
+    }
+    if (!done) {
+      const unsigned long long best = nn1_warp(g, qx, qy, qz, max_d2, sm[wib]);
+      const bool ok = best != 0xffffffffffffffffull;
+      oi = ok ? (int)(unsigned)(best & 0xffffffffull) : -1;
+      od = ok ? __uint_as_float((unsigned)(best >> 32)) : max_d2;
+    }
+    if (lane == 0) { idx[it.s] = oi; d2[it.s] = od; }
+    __syncwarp();
+  }
 }
 
 // second kernel of a staged correspondence step outside the persistent kernels: the queued queries
