@@ -2,17 +2,13 @@
 # ncu launch lists and full captures.  Outputs under gpurun_out/r2f_*.
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2f_test.log 2>&1; tail -2 gpurun_out/r2f_test.log
+for m in 0 1 2; do LB_NN_MODE=$m timeout 300 python tools/gpu/exp_nn.py gpurun_out/r2f_nnmode$m.npz > gpurun_out/r2f_nnmode$m.log 2>&1; done
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/r2f_bench_c2.json 2> gpurun_out/r2f_bench_c2.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2f_bench_c2_reference.json 2>/dev/null
 timeout 900 python bench.py --config c3 > gpurun_out/r2f_bench_c3.json 2> gpurun_out/r2f_bench_c3.err
 timeout 900 python bench.py --config c5 --no-cpu-baseline > gpurun_out/r2f_bench_c5.json 2> gpurun_out/r2f_bench_c5.err
-for v in warp staged staged_tma; do LB_NN=$v timeout 600 python tools/nn_roofline.py --cells 0 --reps 5 > gpurun_out/r2f_nn_$v.json 2>/dev/null; done
-LEAF=$(python -c "import json;print(json.load(open('gpurun_out/r2f_bench_c2.json'))['config']['leaf_m'])")
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r2f_launches_c2.csv python bench.py --profile --leaf $LEAF --stream-scans 8 > gpurun_out/r2f_ncu_l1.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 1500 --csv --log-file gpurun_out/r2f_launches_c2_hot.csv python bench.py --profile --leaf $LEAF --stream-scans 8 > gpurun_out/r2f_ncu_l2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'loop_solve|loop_nn|loop_far|knn_cov_quadreg|vg_centroid4|rs_scatter|vg_keys' --launch-skip 40 -c 24 -o gpurun_out/r2f_prof -f python bench.py --profile --leaf $LEAF --stream-scans 8 > gpurun_out/r2f_ncu_f.log 2>&1
-LB_NN=staged_tma timeout 600 ncu --set full --clock-control none -k regex:nn_query_staged --launch-skip 2 -c 2 -o gpurun_out/r2f_prof_nn -f python tools/nn_roofline.py --cells 0 --reps 3 > gpurun_out/r2f_ncu_nn.log 2>&1
+for v in warp staged staged_tma default; do if [ $v = default ]; then unset LB_NN; else export LB_NN=$v; fi; timeout 600 python tools/nn_roofline.py --cells 0 --reps 5 > gpurun_out/r2f_nn_$v.json 2>/dev/null; done; unset LB_NN
 python - <<'PY'
 import json
 def L(f):
@@ -32,7 +28,8 @@ if d:
     print('  rolling', json.dumps(d['variants'].get('rolling_submap'))[:300])
 d=L('gpurun_out/r2f_bench_c5.json')
 if d: print('C5 value', d['value'], 'e2e', d['e2e']['value'], 'roofline', {k:d['roofline'].get(k) for k in ('frac','achieved','avg_launch_ms','queries_per_s','candidates_per_query')})
-for v in ('warp','staged','staged_tma'):
+for v in ('warp','staged','staged_tma','default'):
     d=L('gpurun_out/r2f_nn_%s.json'%v)
     if d: r=d['runs'][0]; print('NN', v, r['kernel_ms'], r['queries_per_s'], r['candidates_per_query'], r['frac'])
 PY
+du -sh gpurun_out | tail -1
