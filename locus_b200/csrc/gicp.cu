@@ -116,6 +116,9 @@ struct lb_gicp {
   unsigned long long epoch_base = 1ull << 20;
   long long* d_debug = nullptr; long long* h_debug = nullptr;
   DBuf<long long> nnprof;          // tuning aid (LB_NNPROF)
+  std::shared_ptr<Cloud> last_src;  // the source before the current one (a target equal to it adopts it)
+  uint64_t adopted_targets = 0;
+  bool adopt_previous_source = getenv("LB_NO_ADOPT") == nullptr;
   DBuf<NnsFarItem> far_items;      // staged correspondence search: queue of the undecided queries of a step
   DBuf<int> far_count;             // its two counters
   DBuf<SlotWord> cslots;           // cluster kernel: [CL_MAX_CTAS] hit-count words + [CL_CMD_WORDS] command words
@@ -339,12 +342,19 @@ int gicp_create_impl(int device, void* stream, bool ext, lb_gicp** out) {
   return LB_OK;
 }
 
+// hand an object of this handle back for recycling (once): spare_cloud() reuses it when nobody else holds it any more
+void pool_release(lb_gicp* h, const std::shared_ptr<Cloud>& c) {
+  if (!c || c->owner != h) return;
+  for (auto& p : h->pool) if (p.get() == c.get()) return;
+  h->pool.push_back(c);
+}
+
 // Before a handle writes into one of its clouds: if another holder still references the object (it was shared with
 // lb_gicp_share_source), switch to an object nobody else holds -- one of the earlier give-aways that has come back,
 // or a new one.  A reference is only dropped after the holder's own GPU work on the cloud has been synchronised.
 void make_private(lb_gicp* h, std::shared_ptr<Cloud>& c) {
   if (c.use_count() == 1 && c->owner == h) return;
-  if (c->owner == h) h->pool.push_back(c);      // my own give-away: comes back when the other holders drop it
+  pool_release(h, c);                           // my own give-away: comes back when the other holders drop it
   // (an adopted cloud of another handle is simply let go)
   for (size_t i = 0; i < h->pool.size(); i++) {
     if (h->pool[i].use_count() == 1) {          // only the pool holds it: free to recycle (buffers are kept)
@@ -376,8 +386,12 @@ std::shared_ptr<Cloud> spare_cloud(lb_gicp* h) {
 
 // Phase 1 (inside set_source / set_target, synchronous because the caller's buffer is only borrowed for the
 // duration of the call): upload, gather into packed float4 + bounding box in one kernel, choose the grid.
+// same_as (nullable): a prepared cloud of this handle.  When the uploaded points (and normals) equal it bit for bit, the
+// call stops after the gather and returns LB_SAME_CLOUD: the caller adopts that object instead of building another index
+// and another set of covariances for the same data.
+constexpr int LB_SAME_CLOUD = 1;
 int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, size_t stride, size_t xyz_off,
-                 ptrdiff_t normal_off, int mem, const char* what) {
+                 ptrdiff_t normal_off, int mem, const char* what, const Cloud* same_as = nullptr) {
   Scratch& S = h->sc[slot];
   Ctx& c = S.c;
   if (!pts) { set_error("%s: null cloud", what); return LB_ERR_INVALID_ARG; }
@@ -398,10 +412,15 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
   }
   LB_TRY(cl.raw.ensure(n)); LB_TRY(cl.pts.ensure(n));
   if (normal_off >= 0) LB_TRY(cl.nrm.ensure(n));
+  if (same_as && !(same_as->valid && same_as->n == n && same_as->has_normals == (normal_off >= 0))) same_as = nullptr;
+  if (same_as) LB_CUDA(cudaMemsetAsync(S.d_u32 + 2, 0, sizeof(uint32_t), c.stream));
   gather_cloud_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_src, N, (uint32_t)stride, (uint32_t)xyz_off, (int)normal_off,
-                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr, S.d_acc);
+                                                          cl.raw.p, normal_off >= 0 ? cl.nrm.p : nullptr, S.d_acc,
+                                                          same_as ? same_as->raw.p : nullptr,
+                                                          same_as && normal_off >= 0 ? same_as->nrm.p : nullptr, S.d_u32 + 2);
   c.launches += 1;
   LB_CUDA(cudaMemcpyAsync(S.h_acc, S.d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, c.stream));
+  if (same_as) LB_CUDA(cudaMemcpyAsync(S.h_u32 + 2, S.d_u32 + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   bbox_init_kernel<<<1, 32, 0, c.stream>>>(S.d_acc);   // accumulator clean for the next upload
   c.launches += 1;
   LB_CUDA(cudaStreamSynchronize(c.stream));
@@ -409,6 +428,7 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
     set_error("%s: cloud holds %u non-finite points; GICP inputs must be dense (PCL kd-tree precondition)", what, N - S.h_acc->count);
     return LB_ERR_INVALID_ARG;
   }
+  if (same_as && S.h_u32[2] == 0) return LB_SAME_CLOUD;
   float mn[3], mx[3];
   for (int d = 0; d < 3; d++) { mn[d] = ord2f(S.h_acc->mn[d]); mx[d] = ord2f(S.h_acc->mx[d]); }
   float ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
@@ -487,16 +507,31 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
 int replace_cloud(lb_gicp* h, std::shared_ptr<Cloud>& dst, int slot, const void* pts, size_t n, size_t stride, size_t xyz_off,
                   ptrdiff_t normal_off, int mem, const char* what) {
   std::shared_ptr<Cloud> fresh = spare_cloud(h);
-  int s = upload_cloud(h, *fresh, slot, pts, n, stride, xyz_off, normal_off, mem, what);
+  // A new target that IS the previous source (what LOCUS's scan-to-scan odometry passes: reference_ is a copy of the last
+  // query_, PointCloudOdometry.cc:252-262) adopts that cloud with its index and covariances -- when source and target
+  // covariances are computed the same way, which is the reference's only configuration (one recompute_covariances flag).
+  const Cloud* same_as = nullptr;
+  if (slot == 1 && h->last_src && h->last_src.get() != h->src.get() && h->last_src.get() != dst.get() &&
+      h->P.recompute_source_covariance == h->P.recompute_target_covariance && h->adopt_previous_source)
+    same_as = h->last_src.get();
+  int s = upload_cloud(h, *fresh, slot, pts, n, stride, xyz_off, normal_off, mem, what, same_as);
   if (dst->keys_slot == slot) dst->keys_slot = -1;     // the slot's scratch (cell keys of the occupancy probe) was reused
-  if (s != LB_OK) {
+  if (s != LB_OK && s != LB_SAME_CLOUD) {
     fresh->valid = false;
-    h->pool.push_back(fresh);                           // keeps its buffers for the next upload
+    pool_release(h, fresh);                             // keeps its buffers for the next upload
     return s;
   }
   // the previous object may still be referenced by other handles (shared prepared cloud), or be an adopted cloud of
   // another handle: only this handle's own objects are recycled, and only once nobody else holds them
-  if (dst->owner == h) h->pool.push_back(dst);
+  if (slot == 0) h->last_src = dst;                     // stays alive (not recycled) until the next source replaces it
+  pool_release(h, dst);
+  if (s == LB_SAME_CLOUD) {
+    fresh->valid = false;
+    pool_release(h, fresh);
+    dst = h->last_src;
+    h->adopted_targets++;
+    return LB_OK;
+  }
   dst = fresh;
   return LB_OK;
 }
@@ -893,7 +928,7 @@ int lb_gicp_set_target_cloud(lb_gicp* h, lb_cloud* c) {
   if (!h || !c || !c->c) { set_error("lb_gicp_set_target_cloud: null argument"); return LB_ERR_INVALID_ARG; }
   if (c->c->device != h->c.device) { set_error("lb_gicp_set_target_cloud: cloud lives on device %d, handle on %d", c->c->device, h->c.device); return LB_ERR_INVALID_ARG; }
   LB_CUDA(cudaSetDevice(h->c.device));
-  if (h->tgt->owner == h && h->tgt.use_count() > 1 && h->tgt != c->c) h->pool.push_back(h->tgt);   // my give-away stays recyclable
+  if (h->tgt.use_count() > 1 && h->tgt != c->c) pool_release(h, h->tgt);   // my give-away stays recyclable
   h->tgt = c->c;
   // everything this handle launches from now on (on its main stream) comes after the cloud's preparation
   LB_CUDA(cudaStreamWaitEvent(h->c.stream, h->tgt->ready, 0));
@@ -1466,6 +1501,7 @@ int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* l
   if (!strcmp(name, "pool_clouds")) { *ms_avg = (float)h->pool.size(); return LB_OK; }
   if (!strcmp(name, "cell_src")) { *ms_avg = h->src->geom.h; return LB_OK; }      // cell size of the current index (m)
   if (!strcmp(name, "cell_tgt")) { *ms_avg = h->tgt->geom.h; return LB_OK; }
+  if (!strcmp(name, "adopted_targets")) { *ms_avg = (float)h->adopted_targets; return LB_OK; }   // set_target calls that found the previous source
   if (!strcmp(name, "dense_tgt")) { *ms_avg = (float)h->tgt->dense_fraction; return LB_OK; }   // share of target points in cells with > 32 points
   if (!strncmp(name, "snap", 4)) {   // "snapP<i>" / "snapC<i>": publish / completion time (ns, relative) of CTA i at collective 100
     int i = atoi(name + 5);

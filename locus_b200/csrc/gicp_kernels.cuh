@@ -34,7 +34,8 @@ constexpr int AL_MAXB = 8;           // slots per polling lane: supports up to 2
 // ------------------------------------------------------------------ cloud upload
 __global__ void __launch_bounds__(256)
 gather_cloud_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, int normal_off,
-                    f4* __restrict__ raw, f4* __restrict__ nrm, BBoxAcc* __restrict__ acc) {
+                    f4* __restrict__ raw, f4* __restrict__ nrm, BBoxAcc* __restrict__ acc,
+                    const f4* __restrict__ same_raw, const f4* __restrict__ same_nrm, uint32_t* __restrict__ differs) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
   float x = 0.f, y = 0.f, z = 0.f;
@@ -43,10 +44,20 @@ gather_cloud_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t strid
     const float* q = reinterpret_cast<const float*>(p + xyz_off);
     x = q[0]; y = q[1]; z = q[2];
     raw[i] = f4{x, y, z, 1.0f};
+    bool diff = false;
+    if (same_raw) {                       // is this the cloud `same_raw` was gathered from, bit for bit?
+      const f4 o = same_raw[i];
+      diff = __float_as_uint(o.x) != __float_as_uint(x) || __float_as_uint(o.y) != __float_as_uint(y) || __float_as_uint(o.z) != __float_as_uint(z);
+    }
     if (normal_off >= 0) {
       const float* m = reinterpret_cast<const float*>(p + normal_off);
       nrm[i] = f4{m[0], m[1], m[2], 0.0f};
+      if (same_nrm) {
+        const f4 o = same_nrm[i];
+        diff = diff || __float_as_uint(o.x) != __float_as_uint(m[0]) || __float_as_uint(o.y) != __float_as_uint(m[1]) || __float_as_uint(o.z) != __float_as_uint(m[2]);
+      }
     }
+    if (diff) *differs = 1u;
     ok = isfinite(x) && isfinite(y) && isfinite(z);
   }
   bbox_warp_accumulate(ok, x, y, z, acc);   // finite-point bounding box + count (accumulator was reset by the previous build)

@@ -319,7 +319,7 @@ int lb_gicp_set_target_submap(lb_gicp* h, lb_submap* m) {
   // adopt the engine's cloud as this handle's target (shared, immutable: the engine switches to another object when
   // the map changes while somebody still holds this one)
   if (h->tgt != e->src) {
-    if (h->tgt->owner == h && h->tgt.use_count() > 1) h->pool.push_back(h->tgt);
+    if (h->tgt.use_count() > 1) pool_release(h, h->tgt);
     h->tgt = e->src;
   }
   LB_CUDA(cudaSetDevice(h->c.device));

@@ -156,6 +156,40 @@ def test_correspondence_search_modes_agree(tmp_path):
             if k1 in res[0].files: assert np.array_equal(res[0][k], res[0][k1]), k
 
 
+def test_target_equal_to_previous_source_is_adopted():
+    """LOCUS's scan-to-scan odometry passes the previous query as the new target (PointCloudOdometry.cc:252-262).  A
+    target that equals the previous source bit for bit adopts that prepared cloud (index + covariances) instead of
+    building them again: same bits as a handle that rebuilds everything, and it must NOT trigger for a cloud that
+    differs in a single bit."""
+    import locus_b200
+    rng = np.random.default_rng(5)
+    scans = [F.random_scene(6000, 20)]
+    for k in range(1, 5):
+        T = F.se3([0.03 * k, -0.02 * k, 0.0], [0, 0, 0.004 * k])
+        scans.append((scans[0] @ T[:3, :3].T + T[:3, 3] + rng.normal(0, 0.002, scans[0].shape)).astype(np.float32))
+    a = locus_b200.GicpB200(); b = locus_b200.GicpB200()
+    for g in (a, b):
+        g.setMaxCorrespondenceDistance(1.0); g.setTransformationEpsilon(1e-4); g.setMaximumIterations(30)
+    for k in range(1, 5):
+        a.setInputSource(scans[k]); a.setInputTarget(scans[k - 1]); ra = a.align()
+        fresh = locus_b200.GicpB200()                     # a handle without any history
+        fresh.setMaxCorrespondenceDistance(1.0); fresh.setTransformationEpsilon(1e-4); fresh.setMaximumIterations(30)
+        fresh.setInputSource(scans[k]); fresh.setInputTarget(scans[k - 1]); rf = fresh.align()
+        assert np.array_equal(a.getFinalTransformation(), fresh.getFinalTransformation())
+        assert (ra.iterations, ra.n_correspondences) == (rf.iterations, rf.n_correspondences)
+        assert a.getFitnessScore() == fresh.getFitnessScore()
+    assert a.kernelTime("adopted_targets")[0] == 3        # scans 2, 3, 4 found the previous source
+    # one bit flipped: no adoption, and the result is that of the changed cloud
+    almost = scans[3].copy(); almost.view(np.uint32)[100, 1] ^= 1
+    b.setInputSource(scans[3]); b.setInputTarget(scans[2]); b.align()
+    b.setInputSource(scans[4]); b.setInputTarget(almost); b.align()
+    assert b.kernelTime("adopted_targets")[0] == 0
+    fresh = locus_b200.GicpB200()
+    fresh.setMaxCorrespondenceDistance(1.0); fresh.setTransformationEpsilon(1e-4); fresh.setMaximumIterations(30)
+    fresh.setInputSource(scans[4]); fresh.setInputTarget(almost); fresh.align()
+    assert np.array_equal(b.getFinalTransformation(), fresh.getFinalTransformation())
+
+
 def test_gauss_newton_mode(oracle):
     """GN (north_star's 6x6 solve) vs the oracle's GN restatement, and vs BFGS at a tight tolerance
     where both reach the same fixed point."""
