@@ -706,6 +706,7 @@ def run_c2(ctx):
     # first pass with the per-kernel CUDA-event timers on (kernel shares, cycle counters); they cost ~100 event records per
     # scan, so the reported number comes from a second pass without them
     seq_ms, seq_wall, seq_launches, n_seq = blocking_arm(False, n_str - 1)
+    clocks_seq = sampler.stop()        # clocks under this arm's load; the timed pass below runs without the sampling thread
     shares = kernel_shares(gicp, vg.avgCallMs())
     k_seq_ms = shares["align_persistent"]["ms_avg"]
     probe_rounds = gicp.kernelTime("probe_rounds")[0]
@@ -718,7 +719,6 @@ def run_c2(ctx):
     gicp.resetKernelTimes(False)
     if not args.profile:
         seq_ms, seq_wall, seq_launches, n_seq = blocking_arm(False, n_str - 1)
-    clocks_seq = sampler.stop()
     gpu_poses = list(state["poses"])
     iters = np.array(state["iters"], dtype=np.float64); evals = np.array(state["evals"], dtype=np.float64)
     ncorr = np.array(state["ncorr"], dtype=np.float64); nsrc = np.array(state["nsrc"], dtype=np.float64)
