@@ -765,6 +765,7 @@ def run_c2(ctx):
         ctx.barrier()
         st0 = odo.stageTimes()
         l0 = odo.launchCount()
+        a0 = gicp.kernelTime("dbuf_allocs")[0]           # device allocations of the process so far
         ev0.record(ctx.stream)
         out = []
         for k in range(steps):
@@ -778,6 +779,7 @@ def run_c2(ctx):
         ctx.barrier()
         ev1.record(ctx.stream)
         torch.cuda.synchronize()
+        state["allocs_timed_region"] = gicp.kernelTime("dbuf_allocs")[0] - a0
         for r in out:
             if r.status != 0 or not r.has_pose:
                 raise RuntimeError("lb_odometry: ticket %d status %d: %s" % (r.ticket, r.status, r.error.decode(errors="replace")))
@@ -805,9 +807,8 @@ def run_c2(ctx):
     sampler.start()
     for g in (odo.gicp(i) for i in range(args.depth)):
         g.resetKernelTimes(2)          # only the event pair around the align kernel (the roofline's live duration)
-    allocs0 = gicp.kernelTime("dbuf_allocs")[0]
     dev_ms, p_out, launches_timed = pipelined_run(odo, submit_device, n_scans, n_warm)
-    allocs_timed = gicp.kernelTime("dbuf_allocs")[0] - allocs0       # includes the untimed warm-up scans of this arm
+    allocs_timed = state["allocs_timed_region"]       # device allocations inside the timed region (steady state: 0)
     clocks = sampler.stop()
     stages_device = dict(state["stages"])
     kt = [odo.gicp(i).kernelTime("align_persistent") for i in range(args.depth)]
