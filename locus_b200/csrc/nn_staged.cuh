@@ -214,10 +214,9 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
   const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
   const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
   const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
-  const float minfrac = fminf(fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy)), fminf(fz, 1.0f - fz));
   int r0, r1;
   ring_range(g, cx, cy, cz, r0, r1);
-  (void)r1; (void)minfrac;
+  (void)r1;
   const float hs = g.h * 0.9999f;
   const float hh = hs * hs;
   const float inv_hs = 1.0002f / hs;                             // rounded up: windows err on the wide side
@@ -233,7 +232,6 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
   // ---- this lane's ball: what guarantees completeness (the known bound, else the gate); with r0cut > 0 cut to that
   // many cells (half a cell: at most 3 x 3 rows, usually 2 x 2 cells), without a cut up to 9 x 9 rows in batches of 9
   bool inpass = active && !outside;
-  const bool block = false;
   const float need2 = hub ? ub2 : max_d2;
   const float cap2 = r0cut > 0.f ? (r0cut * r0cut) * hh : need2;
   const float b2 = fminf(need2, cap2);
@@ -253,7 +251,7 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
     const int nbatch = __reduce_max_sync(FULL, (nrows + NNS_ROWS - 1) / NNS_ROWS);
     for (int batch = 0; batch < nbatch; batch++) {
       // ---- rows of this batch; a ball shrinks to the best distance found so far
-      const float e2 = block ? 0.f : fminf(b2, __uint_as_float((unsigned)(best >> 32)));   // best >> 32 = the gate while nothing is found
+      const float e2 = fminf(b2, __uint_as_float((unsigned)(best >> 32)));   // best >> 32 = the gate while nothing is found
       int a_lo[NNS_ROWS], a_hi[NNS_ROWS];
       int dy = ylo + (batch * NNS_ROWS) % wy, dz = zlo + (batch * NNS_ROWS) / wy;      // raster walk over the rows
 #pragma unroll
