@@ -17,7 +17,7 @@
 //      (one round trip), and
 //   4. every lane scans its own candidates out of shared memory.
 //
-// Queries the staged pass cannot decide (a block without a decisive best, more than 9 rows, more candidates than the
+// Queries the staged pass cannot decide (a cut ball whose best lies outside it, a huge ball, more candidates than the
 // stage holds) are "far".  They come in clusters -- a part of the scan the target does not cover -- so a warp or a CTA
 // that finished them itself would be the long pole of the step.  Instead they are appended to a device-wide queue
 // (NnsFarQueue) and, after a grid-wide barrier / in the next kernel, taken one per warp by ALL warps of the grid
@@ -262,17 +262,13 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
         if (j < nrows) {
           const int z = cz + dz, y = cy + dy;
           if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-            int xlo = cx - 1, xhi = cx + 1;
-            bool ok = true;
-            if (!block) {
-              const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
-              const float row2 = (gy * gy + gz * gz) * hh;
-              ok = row2 <= e2;
-              const float rem = e2 - row2;
-              const float Sx = nns_sqrt_up(rem) * inv_hs + 1.0e-3f;      // a superset window is all that is needed
-              xlo = cx - (int)(Sx + 1.01f - fx);
-              xhi = cx + (int)(Sx + fx + 0.01f);
-            }
+            const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
+            const float row2 = (gy * gy + gz * gz) * hh;
+            const bool ok = row2 <= e2;
+            const float rem = e2 - row2;
+            const float Sx = nns_sqrt_up(rem) * inv_hs + 1.0e-3f;      // a superset window is all that is needed
+            int xlo = cx - (int)(Sx + 1.01f - fx);
+            int xhi = cx + (int)(Sx + fx + 0.01f);
             xlo = imax_(xlo, 0); xhi = imin_(xhi, g.nx - 1);
             if (ok && xlo <= xhi) {
               const int base = (z * g.ny + y) * g.nx;
