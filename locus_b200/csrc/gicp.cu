@@ -972,6 +972,8 @@ int lb_gicp_align(lb_gicp* h, const float* guess_in, lb_gicp_result* out) {
   static const int exec_override = [] { const char* e = getenv("LB_EXEC_OVERRIDE"); return e ? atoi(e) : -1; }();   // tuning aid
   const int execution = exec_override >= 0 ? exec_override : h->P.execution;
   nn_stage_config(execution, ca.nn_mode, ca.nn_cap);
+  static const float nn_r0 = [] { const char* e = getenv("LB_NN_R0"); float v = e ? (float)atof(e) : NNS_R0; return (v > 0.05f && v <= 1.0f) ? v : NNS_R0; }();
+  ca.nn_r0 = nn_r0;
   ca.far_items = nullptr; ca.far_count = nullptr;
   if (ca.nn_mode) {
     LB_TRY(h->far_items.ensure(N)); LB_TRY(h->far_count.ensure(2));

@@ -1021,6 +1021,7 @@ struct CorrArgs {
   double* M;               // 6 per source point
   int nn_mode;             // search of the correspondence step: 0 each thread on its own, 1 staged (cp.async), 2 staged (TMA)
   int nn_cap;              // staged: candidate points per warp stage
+  float nn_r0;             // staged: radius of the first look in cells (NNS_R0; LB_NN_R0 overrides it for A/B runs)
   NnsFarItem* far_items;   // staged: queue of the undecided queries of one correspondence step (n_src entries) ...
   int* far_count;          // ... and its two counters (steps alternate between them)
   long long* prof;         // tuning aid (LB_NNPROF): 8 words per group of 32 source points, or null
@@ -1110,7 +1111,7 @@ __device__ __forceinline__ int correspond_slice_staged(const CorrArgs& a, const 
     }
     int bo; float bd;
     long long* wp = a.prof ? a.prof + 8 * (size_t)(base >> 5) : nullptr;     // tuning aid: per-warp cycle counters
-    const int j = nn1_staged<TMA>(a.tgt, active, qx, qy, qz, a.max_d2, have_ub, ub2, w, bo, bd, a.far_items ? &fq : nullptr, s, wp);
+    const int j = nn1_staged<TMA>(a.tgt, active, qx, qy, qz, a.max_d2, have_ub, ub2, w, bo, bd, a.far_items ? &fq : nullptr, s, wp, a.nn_r0);
     const long long tf0 = wp ? clock64() : 0;
     if (active && j != NNS_DEFERRED) hits += correspond_finish(a, R, s, j);
     if (wp && lane == 0) wp[3] = clock64() - tf0;
