@@ -717,8 +717,13 @@ def run_c2(ctx):
         snapC = [gicp.kernelTime("snapC%d" % i)[0] for i in range(64)]
         sys.stderr.write("SNAP publish ns: %s\nSNAP complete ns: %s\n" % (snapP, snapC))
     gicp.resetKernelTimes(False)
+    seq_allocs = 0
     if not args.profile:
+        a0 = gicp.kernelTime("dbuf_allocs")[0]
+        if os.environ.get("LB_ALLOC_TRACE"): sys.stderr.write("[bench] seam, timed pass begins\n"); sys.stderr.flush()
         seq_ms, seq_wall, seq_launches, n_seq = blocking_arm(False, n_str - 1)
+        if os.environ.get("LB_ALLOC_TRACE"): sys.stderr.write("[bench] seam, timed pass ends\n"); sys.stderr.flush()
+        seq_allocs = int(gicp.kernelTime("dbuf_allocs")[0] - a0)
     gpu_poses = list(state["poses"])
     iters = np.array(state["iters"], dtype=np.float64); evals = np.array(state["evals"], dtype=np.float64)
     ncorr = np.array(state["ncorr"], dtype=np.float64); nsrc = np.array(state["nsrc"], dtype=np.float64)
@@ -890,7 +895,7 @@ def run_c2(ctx):
             "roofline": roofline,
             "ms_per_scan": dev_ms_max / n_scans,
             "sequential": {"value": seq_value, "unit": "scans/s", "ms_per_scan": seq_ms_max / n_seq, "scans_timed": n_seq,
-                           "gpu_launches": int(seq_launches), "clocks": clocks_seq,
+                           "gpu_launches": int(seq_launches), "clocks": clocks_seq, "device_allocations": seq_allocs,
                            "note": "THE DROP-IN SEAM: blocking per-scan C-ABI calls (what icp_->align() inside LOCUS's "
                                    "queue-depth-1 lidar callback sees), device-resident inputs, L2 flushed between scans"},
             "sequential_e2e": {"value": seqh_value, "unit": "scans/s", "ms_per_scan": seqh_ms_max / n_seqh, "scans_timed": n_seqh,

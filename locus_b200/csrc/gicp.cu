@@ -117,6 +117,7 @@ struct lb_gicp {
   long long* d_debug = nullptr; long long* h_debug = nullptr;
   DBuf<long long> nnprof;          // tuning aid (LB_NNPROF)
   std::shared_ptr<Cloud> last_src;  // the source before the current one (a target equal to it adopts it)
+  size_t max_points_seen[2] = {0, 0}, max_cells_seen[2] = {0, 0};   // per role (source / target): capacity the role's cloud objects are grown to
   uint64_t adopted_targets = 0;
   bool adopt_previous_source = getenv("LB_NO_ADOPT") == nullptr;
   DBuf<NnsFarItem> far_items;      // staged correspondence search: queue of the undecided queries of a step
@@ -410,8 +411,13 @@ int upload_cloud(lb_gicp* h, Cloud& cl, int slot, const void* pts, size_t n, siz
     LB_CUDA(cudaMemcpyAsync(S.stage.p, pts, n * stride, cudaMemcpyHostToDevice, c.stream));
     d_src = S.stage.p;
   }
-  LB_TRY(cl.raw.ensure(n)); LB_TRY(cl.pts.ensure(n));
-  if (normal_off >= 0) LB_TRY(cl.nrm.ensure(n));
+  // A cloud object is sized for the largest cloud (and grid) its role (source / target) has seen on this handle, not just
+  // for the one it receives now: the objects rotate (source, previous source, spares), and an object that had to grow
+  // when it met a bigger cloud would mean a cudaFree + cudaMalloc -- a device-wide synchronisation -- in steady state.
+  size_t& maxn = h->max_points_seen[slot];
+  if (n > maxn) maxn = n;                 // (DBuf::ensure itself grows geometrically)
+  LB_TRY(cl.raw.ensure(maxn)); LB_TRY(cl.pts.ensure(maxn));
+  if (normal_off >= 0) LB_TRY(cl.nrm.ensure(maxn));
   if (same_as && !(same_as->valid && same_as->n == n && same_as->has_normals == (normal_off >= 0))) same_as = nullptr;
   if (same_as) LB_CUDA(cudaMemsetAsync(S.d_u32 + 2, 0, sizeof(uint32_t), c.stream));
   gather_cloud_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(d_src, N, (uint32_t)stride, (uint32_t)xyz_off, (int)normal_off,
@@ -546,7 +552,9 @@ int finish_index(lb_gicp* h, Cloud& cl, int slot) {
   while (key_bits < 32 && (1ull << key_bits) < (uint64_t)cl.ncells) key_bits++;
   const bool have_keys = cl.keys_slot == slot;     // the occupancy probe left keys + per-cell counts in this slot
   cl.keys_slot = -1;
-  LB_TRY(cl.cell_start.ensure(cl.ncells + 1));
+  size_t& maxc = h->max_cells_seen[slot];
+  if (cl.ncells + 1 > maxc) maxc = cl.ncells + 1;
+  LB_TRY(cl.cell_start.ensure(maxc));
   if (!have_keys) {
     LB_TRY(S.keys.ensure(cl.n));
     LB_TRY(S.cell_cnt.ensure(cl.ncells + 1));
@@ -571,7 +579,7 @@ int prepare_clouds(lb_gicp* h, bool need_cov, bool src_knn, bool tgt_knn);
 int compute_covariances(lb_gicp* h, Cloud& cl, int slot, bool recompute) {
   Ctx& c = h->sc[slot].c;
   const uint32_t N = (uint32_t)cl.n;
-  LB_TRY(cl.cov.ensure(6 * cl.n));
+  LB_TRY(cl.cov.ensure(6 * (cl.n > h->max_points_seen[slot] ? cl.n : h->max_points_seen[slot])));
   if (!recompute && cl.has_normals) {
     normal_cov_kernel<<<cdiv(N, 256), 256, 0, c.stream>>>(cl.pts.p, cl.nrm.p, N, h->P.gicp_epsilon, cl.cov.p);
   } else {

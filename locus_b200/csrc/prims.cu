@@ -175,7 +175,7 @@ int exclusive_scan_u32(Ctx& c, ScanWork& w, const uint32_t* in, uint32_t* out, s
     return LB_OK;
   }
   size_t nb = (n + SC_TILE - 1) / SC_TILE;
-  LB_TRY(w.sums.ensure(nb));
+  LB_TRY(w.sums.ensure(nb > 16384 ? nb : 16384));      // never regrown for a slightly larger input (a regrow = cudaFree + cudaMalloc = device-wide sync)
   scan_reduce_kernel<<<(unsigned)nb, SC_T, 0, c.stream>>>(in, n, w.sums.p);
   scan_spine_kernel<<<1, 1024, 0, c.stream>>>(w.sums.p, nb, total_dev);
   scan_down_kernel<<<(unsigned)nb, SC_T, 0, c.stream>>>(in, out, n, w.sums.p);
@@ -369,7 +369,10 @@ static int radix_sort_impl(Ctx& c, SortWork& w, const uint32_t* keys_in, const u
   LB_TRY(w.va.ensure(n ? n : 1)); LB_TRY(w.vb.ensure(n ? n : 1));
   uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   if (nblocks == 0) nblocks = 1;
-  LB_TRY(w.hist.ensure((size_t)256 * nblocks));
+  {   // sized by the CAPACITY of the key buffers, so that it only ever grows together with them
+    const size_t nb_cap = (w.ka.cap + RS_TILE - 1) / RS_TILE;
+    LB_TRY(w.hist.ensure((size_t)256 * (nb_cap > nblocks ? nb_cap : nblocks)));
+  }
   int passes = (key_bits + 7) / 8;
   if (passes < 1) passes = 1;
   const uint32_t* kin = keys_in; const uint32_t* vin = vals_in;

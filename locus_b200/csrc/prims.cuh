@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/locus_b200.h"
@@ -53,6 +54,8 @@ struct DBuf {
   int ensure(size_t n) {
     if (n <= cap) return LB_OK;
     dbuf_alloc_count()++;
+    static const bool trace = getenv("LB_ALLOC_TRACE") != nullptr;      // tuning aid: which buffer still grows in steady state
+    if (trace) fprintf(stderr, "[lb alloc] %zu x %zu bytes requested (capacity was %zu)\n", n, sizeof(T), cap);
     size_t nc = cap ? cap : 1024;
     while (nc < n) nc = nc + nc / 2 + 1024;
     if (p) LB_CUDA(cudaFree(p));
