@@ -156,6 +156,59 @@ def test_correspondence_search_modes_agree(tmp_path):
             if k1 in res[0].files: assert np.array_equal(res[0][k], res[0][k1]), k
 
 
+def test_staged_search_randomized_vs_serial_and_brute_force():
+    """Randomized exactness of the staged (TMA) search against (i) the serial search (the persistent execution uses
+    nn1_pruned, the stream-ordered one nn_staged.cuh: same bits required) over random cloud shapes, densities, cell sizes,
+    gates and guesses, and (ii) a brute-force numpy scan for lb_gicp_nn_target (float32 d2 with the reference's
+    association, ties -> lowest index)."""
+    import locus_b200
+    rng = np.random.default_rng(2024)
+
+    def cloud(kind, n, seed):
+        r = np.random.default_rng(seed)
+        if kind == 0:
+            return F.random_scene(n, seed)
+        if kind == 1:      # blobs of very different density (uneven cells)
+            c = r.uniform(-8, 8, (12, 3)); s = r.uniform(0.05, 1.5, 12)
+            k = r.integers(0, 12, n)
+            return (c[k] + r.normal(0, 1, (n, 3)) * s[k, None]).astype(np.float32)
+        if kind == 2:      # a thin tilted plane + sparse outliers
+            u = r.uniform(-10, 10, (n, 2))
+            p = np.c_[u[:, 0], u[:, 1], 0.1 * u[:, 0] + r.normal(0, 0.005, n)]
+            p[: n // 50] = r.uniform(-10, 10, (n // 50, 3))
+            return p.astype(np.float32)
+        p = F.random_scene(n, seed)                     # with exact duplicates (ties)
+        p[n // 2:] = p[: n - n // 2]
+        return p
+
+    for trial in range(24):
+        kind = trial % 4
+        n = int(rng.integers(3000, 15000))
+        tgt = cloud(kind, n, 100 + trial)
+        T = F.se3(rng.normal(0, 0.15, 3), rng.normal(0, 0.01, 3))
+        src = (tgt[rng.permutation(n)[: n * 3 // 4]] @ T[:3, :3].T + T[:3, 3] + rng.normal(0, 0.003, (n * 3 // 4, 3))).astype(np.float32)
+        corr = float(rng.choice([0.05, 0.2, 0.5, 1.0, 3.0]))
+        cell = float(rng.choice([0.0, 0.0, 0.15, 0.4, 1.0]))
+        guess = F.se3(rng.normal(0, 0.05, 3), [0, 0, 0]).astype(np.float32) if trial % 2 else None
+        out = []
+        for execution in (0, 3):
+            g = locus_b200.GicpB200(); g.setExecution(execution)
+            g.setMaxCorrespondenceDistance(corr); g.setTransformationEpsilon(1e-4); g.setMaximumIterations(12)
+            if cell > 0: g.setIndexCellSize(cell)
+            g.setInputSource(src); g.setInputTarget(tgt)
+            r = g.align(guess)
+            out.append((g.getFinalTransformation(), r.iterations, r.n_correspondences, r.n_objective_evals, g.getFitnessScore()))
+        assert np.array_equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:], (trial, kind, n, corr, cell, out[0][1:], out[1][1:])
+        # lb_gicp_nn_target vs brute force on a sample of queries (near, far and exact hits)
+        q = np.concatenate([src[:400], rng.uniform(-25, 25, (100, 3)).astype(np.float32), tgt[:100]])
+        idx, d2 = g.nearestTarget(q)
+        for i in range(0, len(q), 7):
+            dd = (tgt - q[i]).astype(np.float32)
+            d = ((dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]).astype(np.float32) + dd[:, 2] * dd[:, 2]).astype(np.float32)
+            j = int(np.argmin(d))                       # argmin returns the lowest index among equal distances
+            assert d2[i] == d[j] and idx[i] == j, (trial, i, idx[i], j, d2[i], d[j])
+
+
 def test_target_equal_to_previous_source_is_adopted():
     """LOCUS's scan-to-scan odometry passes the previous query as the new target (PointCloudOdometry.cc:252-262).  A
     target that equals the previous source bit for bit adopts that prepared cloud (index + covariances) instead of
