@@ -111,11 +111,13 @@ __device__ __forceinline__ bool nn1_ball_warp(const GridView& g, float qx, float
   const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
   const float hs = g.h * 0.9999f;
   const float hh = hs * hs;
+  const float inv_hs = 1.0002f / hs;                             // rounded up: windows err on the wide side
   const float S = sqrtf(b2) / hs + 1.0e-4f;
   if (!(S < 24.0f)) return false;
   const int ylo = imax_(-(int)(S + 1.01f - fy), -cy), yhi = imin_((int)(S + fy + 0.01f), g.ny - 1 - cy);
   const int zlo = imax_(-(int)(S + 1.01f - fz), -cz), zhi = imin_((int)(S + fz + 0.01f), g.nz - 1 - cz);
   const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
+  const float inv_wy = 1.0f / (float)(wy > 0 ? wy : 1);
   const int nrows = (wy > 0 && wz > 0) ? wy * wz : 0;
   unsigned long long best = found0 ? (((unsigned long long)__float_as_uint(bd2_0) << 32) | (unsigned)bi0)
                                    : ((unsigned long long)__float_as_uint(max_d2) << 32);      // keys >= the gate key fail d2 < max_d2
@@ -133,12 +135,13 @@ __device__ __forceinline__ bool nn1_ball_warp(const GridView& g, float qx, float
     const int j = jb + lane;
     uint32_t a0 = 0; int n0 = 0;
     if (j < nrows) {
-      const int dz = zlo + j / wy, dy = ylo + j % wy;
+      const int jz = (int)(((float)j + 0.5f) * inv_wy);        // j / wy for 0 <= j < 2401, wy <= 49 (exact: the quotient's
+      const int dz = zlo + jz, dy = ylo + (j - jz * wy);      // fractional part is at least 0.5 / 49 away from an integer)
       const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
       const float row2 = (gy * gy + gz * gz) * hh;
       if (row2 <= e2) {
         const float rem = e2 - row2;
-        const float Sx = sqrtf(rem > 0.f ? rem : 0.f) / hs + 1.0e-4f;
+        const float Sx = nns_sqrt_up(rem) * inv_hs + 1.0e-3f;      // a superset window is all that is needed
         const int xlo = imax_(cx - (int)(Sx + 1.01f - fx), 0), xhi = imin_(cx + (int)(Sx + fx + 0.01f), g.nx - 1);
         if (xlo <= xhi) {
           const int base = ((cz + dz) * g.ny + (cy + dy)) * g.nx;
