@@ -131,7 +131,7 @@ typedef struct lb_gicp_params {
   int num_threads;                      /* setNumThreads */
   int enable_timing_output;             /* enableTimingOutput: spans are always in lb_gicp_result */
   float index_cell_size;                /* voxel-hash cell size in metres; 0 = automatic (a pure function of the cloud) */
-  int align_points_per_cta;             /* source points per CTA of the persistent align kernel; 0 = 512 (lowest latency
+  int align_points_per_cta;             /* source points per CTA of the align solve kernel (any execution); 0 = 512 (lowest latency
                                            of one align: ~60 SMs for a 30k-point scan).  Larger values (1024, 2048) use
                                            fewer SMs per align for longer: more aligns fit on the GPU at once, which is
                                            what lb_odometry's workers want.  Changes the shape of the reduction, i.e. the
@@ -245,7 +245,8 @@ int lb_gicp_cloud_size(lb_gicp* h, int which, size_t* n);
 /* kernels launched by this handle since creation (bench.py reports it) */
 int lb_gicp_launch_count(lb_gicp* h, uint64_t* n);
 /* CUDA-event duration (ms, averaged per launch) of a named kernel class since the last reset:
- * "nn_corr", "objective", "knn_cov", "align_persistent", "index_build". */
+ * "nn_corr", "objective", "knn_cov", "align_persistent" (the iteration part of align() in any execution mode),
+ * "loop_nn" (search grids), "loop_solve", "index_build", "nn_query". */
 int lb_gicp_kernel_time(lb_gicp* h, const char* name, float* ms_avg, uint64_t* launches);
 /* enable_timing: 0 off; 1 event timers of every kernel class plus the align kernel's cycle counters;
  * 2 only the event pair around the align kernel (cheap enough for a throughput run) */
@@ -365,7 +366,7 @@ int lb_gicp_set_target_submap(lb_gicp* h, lb_submap* m);
  * identical to calling lb_voxel_filter / lb_gicp_set_source / lb_gicp_set_target / lb_gicp_align per scan; what
  * the pipeline adds is overlap: a voxel stage (one host thread, one CUDA stream) and `depth` registration workers
  * (one host thread, one lb_gicp handle and stream each).  Scan k+1 is filtered and indexed while scan k is still in
- * its align kernel -- a latency-bound persistent kernel that occupies ~60 of the 148 SMs -- and up to `depth`
+ * its align kernels -- latency-bound cooperative grids that occupy 30-60 of the 148 SMs -- and up to `depth`
  * aligns are in flight at once.  Registration k does not depend on the pose of registration k-1 (the caller's
  * prior, if any, comes from IMU/odometry: PointCloudOdometry.cc:252-262), so the overlap changes no result.
  * In the reference the voxel filter already runs in its own nodelet thread ahead of the odometry thread.

@@ -9,7 +9,7 @@
 //            align -> result k
 //
 // Nothing here touches a point: every byte of device work is done by voxel.cu / gicp.cu kernels.  The pipeline
-// exists because one align() is a latency-bound persistent kernel on ~60 of 148 SMs: the rest of the GPU filters
+// exists because one align() is a chain of latency-bound kernels on 30-60 of 148 SMs: the rest of the GPU filters
 // and indexes the following scans, and several aligns (each on its own CTAs) are in flight at once.  Results are
 // those of the sequential calls: registration k reads only filtered clouds k and k-1 and its caller-given prior.
 #include <chrono>
