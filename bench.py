@@ -267,9 +267,11 @@ def describe(args, world, cfg):
     if args.config == "c2":
         w["workload"] = ("C2 scan-to-scan odometry: %d-ray synthetic 64-beam scan -> VoxelGrid ~%dk -> %s against the "
                          "previous filtered scan" % (rays, cfg["voxels"] // 1000, gi))
-        w["index"] = ("blocking-call arms: source and target index + covariances rebuilt for every scan, like the reference's "
-                      "callers; pipeline arms: each filtered scan's index + covariances computed once and adopted as the next "
-                      "registration's target (bit-identical poses; variants.pipeline_rebuild_both_clouds rebuilds them)")
+        w["index"] = ("blocking-call arms: the caller hands over source AND target for every scan, like the reference's callers; "
+                      "the library recognises a target that equals the previous source bit for bit and adopts its index + "
+                      "covariances (the CPU arm rebuilds both, as the reference does); pipeline arms: each filtered scan's index + "
+                      "covariances computed once and adopted as the next registration's target (bit-identical poses; "
+                      "variants.pipeline_rebuild_both_clouds rebuilds them)")
         w["l2"] = ("inputs larger than L2: %d distinct raw scans of %.1f MB cycled; blocking-call arms: L2 flushed "
                    "between scans by a 256 MiB write" % (cfg["n_stream"], rays * POINT_STEP / 1e6))
         w["pipeline"] = "lb_odometry: 1 VoxelGrid stage + %d registration workers, %d source points per align CTA, one scan stream" % (
