@@ -312,6 +312,105 @@ LB_HD int nn1_pruned(const GridView& g, float qx, float qy, float qz, float max_
   return bs;
 }
 
+// ---- the cells a ball around a query touches (what the staged search of nn_staged.cuh enumerates) -------------------
+// Rows (dy, dz) and, per row, the x-window of the cells whose conservative lower-bound distance (nn1_gap: 0.01 cell
+// safety margin, cell size shrunk by 0.9999) does not exceed the radius.  The windows may be too wide, never too narrow:
+// sqrt is allowed to be an approximation that errs upwards (the device uses rsqrt).  Shared by the device code and by
+// nn1_ball_serial(), the serial restatement the CPU tests run against the kd-tree.
+struct BallGeom {
+  int cx, cy, cz;          // cell of the query (may lie outside the grid)
+  float fx, fy, fz;        // position inside that cell, [0, 1)
+  float hs, hh, inv_hs;    // shrunk cell size, its square, its reciprocal rounded up
+};
+LB_HD float ball_sqrt_up(float x) {
+#if defined(__CUDA_ARCH__)
+  return x > 0.f ? x * rsqrtf(x) * 1.00001f : 0.f;
+#else
+  return x > 0.f ? sqrtf(x) * 1.00001f : 0.f;
+#endif
+}
+LB_HD void ball_geom(const GridView& g, float qx, float qy, float qz, BallGeom& b) {
+  float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  const float LIM = 1.0e9f;
+  ux = fminf(fmaxf(ux, -LIM), LIM); uy = fminf(fmaxf(uy, -LIM), LIM); uz = fminf(fmaxf(uz, -LIM), LIM);
+  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+  b.cx = (int)flx; b.cy = (int)fly; b.cz = (int)flz;
+  b.fx = ux - flx; b.fy = uy - fly; b.fz = uz - flz;
+  b.hs = g.h * 0.9999f;
+  b.hh = b.hs * b.hs;
+  b.inv_hs = 1.0002f / b.hs;
+}
+// radius of the ball in cells (+ margin); rows dy in [ylo, yhi], dz in [zlo, zhi] (not clamped to the grid)
+LB_HD float ball_rows(const BallGeom& b, float b2, int& ylo, int& yhi, int& zlo, int& zhi) {
+  const float S = sqrtf(b2) / b.hs + 1.0e-4f;
+  if (S < 1.0e6f) {
+    ylo = -(int)(S + 1.01f - b.fy); yhi = (int)(S + b.fy + 0.01f);
+    zlo = -(int)(S + 1.01f - b.fz); zhi = (int)(S + b.fz + 0.01f);
+  } else { ylo = yhi = zlo = zhi = 0; }
+  return S;
+}
+// x-window of row (dy, dz) for squared radius e2; false when the row lies outside the ball or the grid
+LB_HD bool ball_window(const GridView& g, const BallGeom& b, int dy, int dz, float e2, int& xlo, int& xhi) {
+  const int z = b.cz + dz, y = b.cy + dy;
+  if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) return false;
+  const float gy = nn1_gap(dy, b.fy), gz = nn1_gap(dz, b.fz);
+  const float row2 = (gy * gy + gz * gz) * b.hh;
+  if (!(row2 <= e2)) return false;
+  const float Sx = ball_sqrt_up(e2 - row2) * b.inv_hs + 1.0e-3f;
+  xlo = imax_(b.cx - (int)(Sx + 1.01f - b.fx), 0);
+  xhi = imin_(b.cx + (int)(Sx + b.fx + 0.01f), g.nx - 1);
+  return xlo <= xhi;
+}
+
+// Serial restatement of the staged search (nn_staged.cuh): first look = the ball that guarantees completeness (the
+// known bound ub2 when have_ub, else the gate) cut to r0cut cells; final when the ball was complete or its best lies
+// inside it; otherwise the remaining ball (best so far / bound / gate), shrinking row by row; huge balls fall back to
+// nn1_pruned.  Same answers as nn1() / nn1_pruned() -- tests/test_hd_cpu.py checks that against the kd-tree.
+LB_HD int nn1_ball_serial(const GridView& g, float qx, float qy, float qz, float max_d2, bool have_ub, float ub2, float r0cut,
+                          int& best_orig, float& best_d2) {
+  BallGeom b;
+  ball_geom(g, qx, qy, qz, b);
+  int r0, r1;
+  ring_range(g, b.cx, b.cy, b.cz, r0, r1);
+  if (r0 > 1 || !(max_d2 > 0.f)) return nn1_pruned(g, qx, qy, qz, max_d2, best_orig, best_d2);
+  float bd2 = max_d2; int bi = -1, bs = -1;
+  bool found = false;
+  auto scan_ball = [&](float b2, bool shrink) {
+    int ylo, yhi, zlo, zhi;
+    ball_rows(b, b2, ylo, yhi, zlo, zhi);
+    for (int dz = zlo; dz <= zhi; dz++)
+      for (int dy = ylo; dy <= yhi; dy++) {
+        const float e2 = (shrink && found) ? fminf(b2, bd2) : b2;
+        int xlo, xhi;
+        if (!ball_window(g, b, dy, dz, e2, xlo, xhi)) continue;
+        const int base = ((b.cz + dz) * g.ny + (b.cy + dy)) * g.nx;
+        for (uint32_t i = g.cell_start[base + xlo]; i < g.cell_start[base + xhi + 1]; i++) {
+          const f4 p = g.pts[i];
+          const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
+          const int oi = float_to_bits(p.w);
+          if (!found) { if (d < max_d2) { found = true; bd2 = d; bi = oi; bs = (int)i; } }
+          else if (better(d, oi, bd2, bi)) { bd2 = d; bi = oi; bs = (int)i; }
+        }
+      }
+  };
+  const bool hub = have_ub && ub2 < max_d2;
+  const float need2 = hub ? ub2 : max_d2;
+  const float cap2 = r0cut > 0.f ? (r0cut * r0cut) * b.hh : need2;
+  const float b2 = fminf(need2, cap2);
+  bool decided = false;
+  if (sqrtf(b2) / b.hs + 1.0e-4f < 4.0f) {
+    scan_ball(b2, true);
+    decided = (need2 <= cap2) || (found && bd2 <= b2);
+  }
+  if (!decided) {
+    const float ball2 = fminf(found ? bd2 : max_d2, need2);
+    if (sqrtf(ball2) / b.hs + 1.0e-4f < 24.0f) scan_ball(ball2, true);
+    else return nn1_pruned(g, qx, qy, qz, max_d2, best_orig, best_d2);
+  }
+  best_orig = bi; best_d2 = bd2;
+  return bs;
+}
+
 // Exact k nearest neighbours (unbounded radius, like FLANN nearestKSearch).
 // Kept ascending by (d2, orig index) in d2s/idx/sidx (arrays of length >= K).
 // Returns the number found (min(K, n)).

@@ -84,9 +84,6 @@ __device__ __forceinline__ void nns_bulk_copy(void* smem_dst, const void* gsrc, 
                "r"(bytes), "r"(b) : "memory");
 }
 
-// sqrt for window sizes: the hardware approximation, nudged up (a window may be too wide, never too narrow)
-__device__ __forceinline__ float nns_sqrt_up(float x) { return x > 0.f ? x * rsqrtf(x) * 1.00001f : 0.f; }
-
 // warp-wide minimum of a packed (d2 bits << 32 | original index) key
 __device__ __forceinline__ unsigned long long nns_warp_min(unsigned long long v) {
 #pragma unroll
@@ -105,17 +102,13 @@ __device__ __forceinline__ bool nn1_ball_warp(const GridView& g, float qx, float
                                               float bd2_0, int bi0, int bs0, uint32_t* scratch, int& out_bs, int& out_bi, float& out_bd2) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
-  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-  const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
-  const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
-  const float hs = g.h * 0.9999f;
-  const float hh = hs * hs;
-  const float inv_hs = 1.0002f / hs;                             // rounded up: windows err on the wide side
-  const float S = sqrtf(b2) / hs + 1.0e-4f;
+  BallGeom b;
+  ball_geom(g, qx, qy, qz, b);
+  int ylo, yhi, zlo, zhi;
+  const float S = ball_rows(b, b2, ylo, yhi, zlo, zhi);
   if (!(S < 24.0f)) return false;
-  const int ylo = imax_(-(int)(S + 1.01f - fy), -cy), yhi = imin_((int)(S + fy + 0.01f), g.ny - 1 - cy);
-  const int zlo = imax_(-(int)(S + 1.01f - fz), -cz), zhi = imin_((int)(S + fz + 0.01f), g.nz - 1 - cz);
+  ylo = imax_(ylo, -b.cy); yhi = imin_(yhi, g.ny - 1 - b.cy);
+  zlo = imax_(zlo, -b.cz); zhi = imin_(zhi, g.nz - 1 - b.cz);
   const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
   const float inv_wy = 1.0f / (float)(wy > 0 ? wy : 1);
   const int nrows = (wy > 0 && wz > 0) ? wy * wz : 0;
@@ -137,17 +130,11 @@ __device__ __forceinline__ bool nn1_ball_warp(const GridView& g, float qx, float
     if (j < nrows) {
       const int jz = (int)(((float)j + 0.5f) * inv_wy);        // j / wy for 0 <= j < 2401, wy <= 49 (exact: the quotient's
       const int dz = zlo + jz, dy = ylo + (j - jz * wy);      // fractional part is at least 0.5 / 49 away from an integer)
-      const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
-      const float row2 = (gy * gy + gz * gz) * hh;
-      if (row2 <= e2) {
-        const float rem = e2 - row2;
-        const float Sx = nns_sqrt_up(rem) * inv_hs + 1.0e-3f;      // a superset window is all that is needed
-        const int xlo = imax_(cx - (int)(Sx + 1.01f - fx), 0), xhi = imin_(cx + (int)(Sx + fx + 0.01f), g.nx - 1);
-        if (xlo <= xhi) {
-          const int base = ((cz + dz) * g.ny + (cy + dy)) * g.nx;
-          a0 = g.cell_start[base + xlo];
-          n0 = (int)(g.cell_start[base + xhi + 1] - a0);
-        }
+      int xlo, xhi;
+      if (ball_window(g, b, dy, dz, e2, xlo, xhi)) {
+        const int base = ((b.cz + dz) * g.ny + (b.cy + dy)) * g.nx;
+        a0 = g.cell_start[base + xlo];
+        n0 = (int)(g.cell_start[base + xhi + 1] - a0);
       }
     }
     int incl = n0;
@@ -211,18 +198,11 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long tp0 = wprof ? clock64() : 0;
-  float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
-  const float LIM = 1.0e9f;
-  ux = fminf(fmaxf(ux, -LIM), LIM); uy = fminf(fmaxf(uy, -LIM), LIM); uz = fminf(fmaxf(uz, -LIM), LIM);
-  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-  const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
-  const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  BallGeom b;
+  ball_geom(g, qx, qy, qz, b);
   int r0, r1;
-  ring_range(g, cx, cy, cz, r0, r1);
+  ring_range(g, b.cx, b.cy, b.cz, r0, r1);
   (void)r1;
-  const float hs = g.h * 0.9999f;
-  const float hh = hs * hs;
-  const float inv_hs = 1.0002f / hs;                             // rounded up: windows err on the wide side
   const unsigned long long gate_key = (unsigned long long)__float_as_uint(max_d2) << 32;   // keys >= this fail d2 < max_d2
   unsigned long long best = gate_key;                            // (d2 bits << 32 | original index) of the best candidate
   int bs = -1;
@@ -236,16 +216,13 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
   // many cells (half a cell: at most 3 x 3 rows, usually 2 x 2 cells), without a cut up to 9 x 9 rows in batches of 9
   bool inpass = active && !outside;
   const float need2 = hub ? ub2 : max_d2;
-  const float cap2 = r0cut > 0.f ? (r0cut * r0cut) * hh : need2;
+  const float cap2 = r0cut > 0.f ? (r0cut * r0cut) * b.hh : need2;
   const float b2 = fminf(need2, cap2);
   const bool complete = need2 <= cap2;
   int ylo = 0, yhi = 0, zlo = 0, zhi = 0;
-  {
-    const float S = sqrtf(b2) / hs + 1.0e-4f;
-    if (S < 4.0f) {
-      ylo = -(int)(S + 1.01f - fy); yhi = (int)(S + fy + 0.01f);
-      zlo = -(int)(S + 1.01f - fz); zhi = (int)(S + fz + 0.01f);
-    } else if (inpass) { far = true; inpass = false; }            // a huge ball: nn1_ball_warp / the serial search
+  if (!(ball_rows(b, b2, ylo, yhi, zlo, zhi) < 4.0f)) {           // a huge ball: nn1_ball_warp / the serial search
+    ylo = yhi = zlo = zhi = 0;
+    if (inpass) { far = true; inpass = false; }
   }
 
   {
@@ -262,22 +239,10 @@ __device__ __forceinline__ int nn1_staged(const GridView& g, bool active, float 
         a_lo[r] = 0; a_hi[r] = 0;
         if (dy > yhi) { dy = ylo; dz++; }
         const int j = batch * NNS_ROWS + r;
-        if (j < nrows) {
-          const int z = cz + dz, y = cy + dy;
-          if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
-            const float gy = nn1_gap(dy, fy), gz = nn1_gap(dz, fz);
-            const float row2 = (gy * gy + gz * gz) * hh;
-            const bool ok = row2 <= e2;
-            const float rem = e2 - row2;
-            const float Sx = nns_sqrt_up(rem) * inv_hs + 1.0e-3f;      // a superset window is all that is needed
-            int xlo = cx - (int)(Sx + 1.01f - fx);
-            int xhi = cx + (int)(Sx + fx + 0.01f);
-            xlo = imax_(xlo, 0); xhi = imin_(xhi, g.nx - 1);
-            if (ok && xlo <= xhi) {
-              const int base = (z * g.ny + y) * g.nx;
-              a_lo[r] = base + xlo; a_hi[r] = base + xhi + 1;
-            }
-          }
+        int xlo, xhi;
+        if (j < nrows && ball_window(g, b, dy, dz, e2, xlo, xhi)) {
+          const int base = ((b.cz + dz) * g.ny + (b.cy + dy)) * g.nx;
+          a_lo[r] = base + xlo; a_hi[r] = base + xhi + 1;
         }
       }
       // ---- CSR offsets of all rows, issued back to back (index 0 for rows that do not exist: both loads hit the same word)

@@ -144,6 +144,19 @@ void hh_nn1_block_batch(void* g, const float* q, int nq, int stride_f, float max
   }
 }
 
+// the serial restatement of the staged search (grid.h nn1_ball_serial): ub2 (nullable) = per-query squared distance to a
+// known target point (the bound the previous outer iteration's match gives), r0cut = first-look radius in cells
+void hh_nn1_ball_batch(void* g, const float* q, int nq, int stride_f, float max_d2, const float* ub2, float r0cut, int* idx, float* d2) {
+  HGrid* G = (HGrid*)g;
+  for (int i = 0; i < nq; i++) {
+    int bo; float bd;
+    int s = nn1_ball_serial(G->v, q[(size_t)i * stride_f], q[(size_t)i * stride_f + 1], q[(size_t)i * stride_f + 2], max_d2,
+                            ub2 != nullptr, ub2 ? ub2[i] : 0.f, r0cut, bo, bd);
+    idx[i] = (s >= 0) ? bo : -1;
+    d2[i] = bd;
+  }
+}
+
 void hh_knn_batch(void* g, const float* q, int nq, int stride_f, int k, int* idx, float* d2) {
   HGrid* G = (HGrid*)g;
   for (int i = 0; i < nq; i++) {

@@ -19,6 +19,41 @@ CLOUDS = {
 }
 
 
+@pytest.mark.parametrize("name,h", [("scene", 0.5), ("scene", 0.15), ("garage", 0.3), ("cube", 0.25)])
+def test_staged_search_restatement_exact(harness, oracle, name, h):
+    """grid.h nn1_ball_serial = the cascade of the staged GPU search (nn_staged.cuh) with the SAME ball / row / window
+    helpers the device code calls: half-cell first look, final only when complete or the best lies inside, remaining ball
+    shrinking as it goes, bounds from a known target point.  Against the kd-tree, for gates from a fifth of a cell to
+    unbounded, first-look radii 0.25 .. 1 cell, and bounds that are exact, loose, or absent."""
+    import ctypes as C
+    pts = np.ascontiguousarray(CLOUDS[name](), dtype=np.float32)
+    g = harness.hh_grid_build(_p(pts), len(pts), 3, h)
+    rng = np.random.default_rng(3)
+    q = np.concatenate([pts[rng.integers(0, len(pts), 1200)] + rng.normal(0, 0.05, (1200, 3)),       # near (decided by the first look)
+                        pts[rng.integers(0, len(pts), 1200)] + rng.normal(0, 0.8, (1200, 3)),        # far: second look
+                        pts[:100]]).astype(np.float32)                                               # exact hits / duplicates
+    kt = oracle.KdTree(pts)
+    oi, od = kt.nn_batch(q)
+    fn = harness.hh_nn1_ball_batch
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    idx = np.zeros(len(q), np.int32); d2 = np.zeros(len(q), np.float32)
+    for gate in (np.float32((0.2 * h) ** 2), np.float32(h * h), np.float32(9.0 * h * h), np.float32(3e38)):
+        want = np.where(od < gate, oi, -1)
+        for r0 in (0.25, 0.5, 1.0):
+            fn(g, _p(q), len(q), 3, gate, None, np.float32(r0), _p(idx), _p(d2))
+            assert np.array_equal(idx, want), (name, h, float(gate), r0, np.flatnonzero(idx != want)[:5])
+            assert np.array_equal(d2[want >= 0], od[want >= 0])
+        # bounds: the exact NN distance, a looser one (the distance to some other target point), a useless one (beyond the gate)
+        other = pts[rng.integers(0, len(pts), len(q))]
+        dd = (other - q).astype(np.float32)
+        loose = ((dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]).astype(np.float32) + dd[:, 2] * dd[:, 2]).astype(np.float32)
+        for ub in (od.copy(), np.minimum(loose, np.float32(3e38)), np.full(len(q), 3e38, np.float32)):
+            fn(g, _p(q), len(q), 3, gate, _p(np.ascontiguousarray(ub)), np.float32(0.5), _p(idx), _p(d2))
+            assert np.array_equal(idx, want), (name, h, float(gate), "bound")
+    harness.hh_grid_free(g)
+
+
 @pytest.mark.parametrize("name", list(CLOUDS))
 @pytest.mark.parametrize("h", [0.07, 0.3, 1.5])
 def test_ring_search_exact(harness, oracle, name, h):
