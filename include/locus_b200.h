@@ -420,6 +420,75 @@ int lb_odometry_launch_count(lb_odometry* h, uint64_t* n);
  *          scans registered, registration workers busy s (summed over workers), their wait s (for a filtered scan) } */
 int lb_odometry_stage_times(lb_odometry* h, double* out6);
 
+/* ------------------------------------------------------------------ NDT
+ * LOCUS's alternative registration method (`registration_method: ndt`, registration_settings.h:3-12): the OpenMP NDT
+ * fork multithreaded_gicp/include/multithreaded_ndt/ndt_omp{.h,_impl.hpp} + voxel_grid_covariance_omp{.h,_impl.hpp},
+ * set up at PointCloudOdometry.cc:182-195 and PointCloudLocalization.cc:267-280 and then driven through the same
+ * icp_->setInputSource / setInputTarget / align / getFinalTransformation calls as GICP.
+ *
+ *   lb_ndt_create/destroy     make_shared<pclomp::NormalDistributionsTransform<PointF, PointF>>
+ *   lb_ndt_set_params         setTransformationEpsilon / setMaximumIterations / setResolution / setStepSize /
+ *                             setOulierRatio / setNeighborhoodSearchMethod (ndt_omp.h:124-196) and the voxel grid's
+ *                             setMinPointPerVoxel / setCovEigValueInflationRatio (voxel_grid_covariance_omp.h:203-236)
+ *   lb_ndt_set_source         icp_->setInputSource()
+ *   lb_ndt_set_target         icp_->setInputTarget() -> init() (ndt_omp.h:116-119,257-262): the target's voxel Gaussians
+ *   lb_ndt_align              icp_->align() + getFinalTransformation() + hasConverged() + getTransformationProbability()
+ *                             (computeTransformation, ndt_omp_impl.hpp:100-208)
+ *   lb_ndt_target_voxels      getTargetCells().getLeaves() restricted to the searchable voxels (voxel_centroids_ order)
+ *   lb_ndt_derivatives        computeDerivatives / computeHessian at a given pose (ndt_omp_impl.hpp:221-343,641-718)
+ *
+ * Semantics kept: non-finite target points are skipped; a source with a non-finite point is refused (previous source
+ * kept); a target whose int32 voxel index would overflow is refused (previous target kept); voxels with fewer than
+ * min_points_per_voxel points are not searchable; a voxel whose covariance fails the eigenvalue / inverse check stays in
+ * the radius search with nr_points = -1 exactly as in the reference (voxel_grid_covariance_omp_impl.hpp:326-355). */
+typedef struct lb_ndt lb_ndt;
+
+typedef struct lb_ndt_params {
+  float resolution;                 /* 1.0   voxel side and neighbour radius (ndt_omp_impl.hpp:50) */
+  double step_size;                 /* 0.1   More-Thuente maximum step (:51) */
+  double outlier_ratio;             /* 0.55  (:52) */
+  double transformation_epsilon;    /* 0.1   (:93); LOCUS passes icp_tf_epsilon / tf_epsilon */
+  int max_iterations;               /* 35    (:94); LOCUS passes icp_iterations / iterations */
+  int min_points_per_voxel;         /* 6     voxel_grid_covariance_omp.h:186 */
+  double min_covar_eigvalue_mult;   /* 0.01  voxel_grid_covariance_omp.h:187 */
+  int search_method;                /* 0 KDTREE (default, :96), 2 DIRECT7, 3 DIRECT1 (pclomp::NeighborSearchMethod values) */
+  /* accepted for interface compatibility (PointCloudOdometry.cc:189,191-193), no effect -- as in the reference's NDT */
+  double max_correspondence_distance;
+  int ransac_iterations;
+  int num_threads;
+  int enable_timing_output;
+} lb_ndt_params;
+
+typedef struct lb_ndt_result {
+  float final_transformation[16];   /* row-major 4x4 */
+  int converged;
+  int nr_iterations;
+  int n_evaluations;                /* computeDerivatives passes */
+  int n_target_voxels;              /* searchable voxels of the target */
+  double trans_probability;         /* score / source points (ndt_omp_impl.hpp:207) */
+  double pose[6];                   /* x y z roll pitch yaw of the last iterate */
+  double t_total_s;
+} lb_ndt_result;
+
+void lb_ndt_default_params(lb_ndt_params* p);
+int lb_ndt_create(int device, lb_ndt** h);
+int lb_ndt_create_on_stream(int device, void* cuda_stream, lb_ndt** h);
+int lb_ndt_destroy(lb_ndt* h);
+int lb_ndt_set_params(lb_ndt* h, const lb_ndt_params* p);
+int lb_ndt_set_source(lb_ndt* h, const void* pts, size_t n, size_t stride_bytes, size_t xyz_offset_bytes, int mem);
+int lb_ndt_set_target(lb_ndt* h, const void* pts, size_t n, size_t stride_bytes, size_t xyz_offset_bytes, int mem);
+/* guess16: row-major 4x4 float, NULL = identity (what LOCUS passes).  Blocking. */
+int lb_ndt_align(lb_ndt* h, const float* guess16, lb_ndt_result* result);
+/* host output buffers of `capacity` voxels each (any may be NULL); *n_voxels = searchable voxels, ascending voxel index */
+int lb_ndt_target_voxels(lb_ndt* h, size_t capacity, size_t* n_voxels, int32_t* leaf_idx, int32_t* nr_points, double* mean3,
+                         double* icov9, float* centroid3);
+/* sums over the source transformed by T16 (row-major 4x4), angle derivatives taken at pose6.  compute_hessian: 0 / 1 = the
+ * float path without / with the Hessian, 2 = the double-precision Hessian pass the line search ends with (score and
+ * gradient come back as 0). */
+int lb_ndt_derivatives(lb_ndt* h, const float* T16, const double* pose6, int compute_hessian, double* score, double* gradient6,
+                       double* hessian36);
+int lb_ndt_launch_count(lb_ndt* h, uint64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,531 @@
+// ndt.cu -- NDT registration on the GPU: the C ABI `lb_ndt_*` replaces
+// pclomp::NormalDistributionsTransform<PointF, PointF> behind LOCUS's `registration_method: ndt`
+// (PointCloudOdometry.cc:182-195, PointCloudLocalization.cc:267-280).
+//
+//   lb_ndt_set_target    setInputTarget -> init() -> VoxelGridCovariance::filter(true)
+//                        (ndt_omp.h:116-119,257-262; voxel_grid_covariance_omp_impl.hpp:48-370):
+//                        ndt_gather -> ndt_keys -> stable radix sort (prims.cu) -> ndt_heads -> scan -> ndt_gaussians
+//                        -> ndt_hash_insert.  One thread per voxel walks its points in input order (the reference's
+//                        accumulation order), so means / inverse covariances / centroids are reproducible bit for bit.
+//   lb_ndt_align         computeTransformation (ndt_omp_impl.hpp:100-208) as a stream-ordered chain
+//                        [ndt_eval_kernel, ndt_ctl_kernel] x evaluations: the evaluation grid computes the score,
+//                        gradient and Hessian terms of every source point against the voxels around it (float per-pair
+//                        terms, double sums: warp shuffle -> CTA -> one partial per CTA), the one-block controller
+//                        kernel adds the partials in CTA order and runs the Newton step / More-Thuente line search
+//                        state machine of ndt.h, then posts the next transform.  The host enqueues a batch of pairs
+//                        and reads the controller back once per batch; pairs after the end return at once.
+//
+// Everything is HBM/L2-bound gather work (96-byte voxel records behind a hash lookup); no contraction, no tensor cores.
+#include <algorithm>
+#include <chrono>
+#include <new>
+#include <vector>
+
+#include "ndt.h"
+#include "prims.cuh"
+
+namespace lb {
+
+constexpr int NDT_EVAL_THREADS = 128;
+constexpr int NDT_BATCH = 8;            // [eval, ctl] pairs enqueued between two looks at the controller
+
+__global__ void __launch_bounds__(256)
+ndt_gather_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, f4* __restrict__ out,
+                  BBoxAcc* __restrict__ acc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (i < n) {
+    const float* q = reinterpret_cast<const float*>(base + (size_t)i * stride + xyz_off);
+    x = q[0]; y = q[1]; z = q[2];
+    out[i] = f4{x, y, z, 1.0f};
+    ok = isfinite(x) && isfinite(y) && isfinite(z);
+  }
+  bbox_warp_accumulate(ok, x, y, z, acc);
+}
+
+__global__ void __launch_bounds__(256)
+ndt_keys_kernel(const f4* __restrict__ pts, uint32_t n, NdtLattice L, uint32_t invalid_key, uint32_t* __restrict__ keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const f4 p = pts[i];
+  const bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);     // non-finite target points are skipped (:196-200)
+  keys[i] = ok ? (uint32_t)ndt_voxel_key(L, p.x, p.y, p.z) : invalid_key;
+}
+
+// flag[i] = 1 when sorted position i opens a voxel with at least min_pts points
+__global__ void __launch_bounds__(256)
+ndt_heads_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t invalid_key, int min_pts, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  uint32_t f = 0;
+  if (k != invalid_key && (i == 0 || keys[i - 1] != k)) {
+    uint32_t j = i + 1;
+    while (j < n && keys[j] == k && (int)(j - i) < min_pts) j++;
+    f = (int)(j - i) >= min_pts ? 1u : 0u;
+  }
+  flag[i] = f;
+}
+
+__global__ void __launch_bounds__(128)
+ndt_gaussians_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, const uint32_t* __restrict__ flag,
+                     const uint32_t* __restrict__ slot_of, const f4* __restrict__ pts, double eig_mult, NdtVoxel* __restrict__ vox,
+                     f4* __restrict__ cen, int32_t* __restrict__ leaf_idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const uint32_t k = keys[i];
+  double sum[3] = {0, 0, 0}, m2[6] = {0, 0, 0, 0, 0, 0};
+  float csum[3] = {0.f, 0.f, 0.f};
+  uint32_t j = i;
+  for (; j < n && keys[j] == k; j++) {          // input order: the sort is stable
+    const f4 p = pts[vals[j]];
+    const double d0 = p.x, d1 = p.y, d2 = p.z;
+    sum[0] += d0; sum[1] += d1; sum[2] += d2;
+    csum[0] += p.x; csum[1] += p.y; csum[2] += p.z;
+    m2[0] += d0 * d0; m2[1] += d0 * d1; m2[2] += d0 * d2; m2[3] += d1 * d1; m2[4] += d1 * d2; m2[5] += d2 * d2;
+  }
+  NdtVoxel v;
+  float c[3];
+  const int nr = ndt_finish_voxel((int)(j - i), sum, m2, csum, eig_mult, v, c);
+  const uint32_t s = slot_of[i];
+  vox[s] = v;
+  cen[s] = f4{c[0], c[1], c[2], __int_as_float(nr)};
+  leaf_idx[s] = (int32_t)k;
+}
+
+__global__ void __launch_bounds__(256)
+ndt_hash_insert_kernel(const int32_t* __restrict__ leaf_idx, uint32_t n_valid, uint32_t* __restrict__ hkey, int32_t* __restrict__ hval,
+                       uint32_t hmask) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_valid) return;
+  const uint32_t key = (uint32_t)leaf_idx[s];
+  uint32_t h = ndt_hash(key) & hmask;
+  for (;;) {
+    const uint32_t prev = atomicCAS(&hkey[h], 0xffffffffu, key);
+    if (prev == 0xffffffffu) { hval[h] = (int32_t)s; return; }
+    h = (h + 1) & hmask;
+  }
+}
+
+// One evaluation: every source point against the voxels around it; one partial (43 doubles) per CTA.
+__global__ void __launch_bounds__(NDT_EVAL_THREADS)
+ndt_eval_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss G, const f4* __restrict__ src, uint32_t n,
+                double* __restrict__ partials) {
+  __shared__ NdtAngles sA;
+  __shared__ float sT[12];
+  __shared__ double sred[NDT_EVAL_THREADS / 32][NDT_NSUM];
+  const int want = ctl->want;
+  if (want == NDT_WANT_NONE) return;                       // the align finished in an earlier pair of this batch
+  {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(&ctl->ang);
+    uint32_t* s = reinterpret_cast<uint32_t*>(&sA);
+    for (uint32_t w = threadIdx.x; w < sizeof(NdtAngles) / 4; w += blockDim.x) s[w] = g[w];
+    if (threadIdx.x < 12) sT[threadIdx.x] = ctl->T[threadIdx.x];
+  }
+  __syncthreads();
+  double acc[NDT_NSUM];
+#pragma unroll
+  for (int k = 0; k < NDT_NSUM; k++) acc[k] = 0.0;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const f4 p = src[i];
+    ndt_point_eval(tv, G, sA, sT, p.x, p.y, p.z, want, acc);
+  }
+  // the sums this request needs: DERIV = score + gradient, DERIV_H = all, HESSIAN = the 6x6 only
+  const int k0 = want == NDT_WANT_HESSIAN ? 7 : 0, k1 = want == NDT_WANT_DERIV ? 7 : NDT_NSUM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NDT_NSUM; k++) {
+    if (k < k0 || k >= k1) continue;
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NDT_NSUM) {
+    const int k = threadIdx.x;
+    double v = 0.0;
+    if (k >= k0 && k < k1) {
+#pragma unroll
+      for (int w = 0; w < NDT_EVAL_THREADS / 32; w++) v += sred[w][k];
+    }
+    partials[(size_t)blockIdx.x * NDT_NSUM + k] = v;
+  }
+}
+
+// Adds the CTA partials in CTA order (fixed shape: run-to-run identical bits) and advances the controller.
+__global__ void __launch_bounds__(64)
+ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, int blocks) {
+  __shared__ double sums[NDT_NSUM];
+  if (ctl->want == NDT_WANT_NONE) return;
+  if (threadIdx.x < NDT_NSUM) {
+    double v = 0.0;
+    for (int b = 0; b < blocks; b++) v += partials[(size_t)b * NDT_NSUM + threadIdx.x];
+    sums[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ndt_ctl_advance(*ctl, sums);
+}
+
+// lb_ndt_derivatives: one evaluation at a caller-given pose, sums to out[43]
+__global__ void __launch_bounds__(64)
+ndt_sum_kernel(const double* __restrict__ partials, int blocks, double* __restrict__ out) {
+  if (threadIdx.x < NDT_NSUM) {
+    double v = 0.0;
+    for (int b = 0; b < blocks; b++) v += partials[(size_t)b * NDT_NSUM + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+struct lb_ndt {
+  Ctx c;
+  lb_ndt_params P;
+  NdtGauss G;
+  // source
+  DBuf<f4> src, src_spare;
+  uint32_t n_src = 0;
+  // target
+  DBuf<f4> tgt, tgt_spare;
+  uint32_t n_tgt = 0;
+  float tgt_mn[3] = {0, 0, 0}, tgt_mx[3] = {0, 0, 0};
+  bool tgt_dirty = false;               // the voxel structure has to be (re)built from tgt
+  bool have_tgt = false;
+  DBuf<uint32_t> keys, flag, slot_of;
+  SortWork sort;
+  ScanWork scan;
+  DBuf<NdtVoxel> vox;
+  DBuf<f4> cen;
+  DBuf<int32_t> leaf_idx, hval;
+  DBuf<uint32_t> hkey;
+  NdtTargetView tv;
+  NdtLattice L;
+  // evaluation
+  DBuf<uint8_t> io;
+  DBuf<double> partials;
+  NdtCtl* d_ctl = nullptr;
+  NdtCtl* h_ctl = nullptr;              // pinned
+  double* d_sums = nullptr;
+  double* h_sums = nullptr;             // pinned
+  BBoxAcc* d_acc = nullptr;
+  BBoxAcc* h_acc = nullptr;             // pinned
+  uint32_t* d_u32 = nullptr;
+  uint32_t* h_u32 = nullptr;            // pinned
+};
+
+extern "C" {
+
+void lb_ndt_default_params(lb_ndt_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->resolution = 1.0f;                  // ndt_omp_impl.hpp:50
+  p->step_size = 0.1;                    // :51
+  p->outlier_ratio = 0.55;               // :52
+  p->transformation_epsilon = 0.1;       // :93
+  p->max_iterations = 35;                // :94
+  p->min_points_per_voxel = 6;           // voxel_grid_covariance_omp.h:186
+  p->min_covar_eigvalue_mult = 0.01;     // :187
+  p->search_method = NDT_KDTREE;         // ndt_omp_impl.hpp:96
+  p->max_correspondence_distance = 0.0;
+  p->ransac_iterations = 0;
+  p->num_threads = 0;
+  p->enable_timing_output = 0;
+}
+
+static int ndt_create_impl(int device, void* stream, bool ext, lb_ndt** out) {
+  if (!out) { set_error("lb_ndt_create: null handle pointer"); return LB_ERR_INVALID_ARG; }
+  lb_ndt* h = new (std::nothrow) lb_ndt;
+  if (!h) { set_error("lb_ndt_create: out of memory"); return LB_ERR_CUDA; }
+  int s = ctx_init(h->c, device, stream, ext);
+  if (s != LB_OK) { delete h; return s; }
+  lb_ndt_default_params(&h->P);
+  ndt_gauss_constants(h->P.outlier_ratio, h->P.resolution, h->G);
+  memset(&h->tv, 0, sizeof(h->tv));
+  bool ok = cudaMalloc((void**)&h->d_ctl, sizeof(NdtCtl)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_ctl, sizeof(NdtCtl)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_sums, NDT_NSUM * sizeof(double)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_sums, NDT_NSUM * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_acc, sizeof(BBoxAcc)) == cudaSuccess &&
+            cudaMalloc((void**)&h->d_u32, 8 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_u32, 8 * sizeof(uint32_t)) == cudaSuccess;
+  if (!ok) {
+    set_error("lb_ndt_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    lb_ndt_destroy(h);
+    return LB_ERR_CUDA;
+  }
+  *out = h;
+  return LB_OK;
+}
+
+int lb_ndt_create(int device, lb_ndt** h) { return ndt_create_impl(device, nullptr, false, h); }
+int lb_ndt_create_on_stream(int device, void* stream, lb_ndt** h) { return ndt_create_impl(device, stream, true, h); }
+
+int lb_ndt_destroy(lb_ndt* h) {
+  if (!h) return LB_OK;
+  cudaSetDevice(h->c.device);
+  if (h->c.stream) cudaStreamSynchronize(h->c.stream);
+  h->src.release(); h->src_spare.release(); h->tgt.release(); h->tgt_spare.release();
+  h->keys.release(); h->flag.release(); h->slot_of.release();
+  h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
+  h->sort.scan.sums.release(); h->scan.sums.release();
+  h->vox.release(); h->cen.release(); h->leaf_idx.release(); h->hval.release(); h->hkey.release();
+  h->io.release(); h->partials.release();
+  if (h->d_ctl) cudaFree(h->d_ctl);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->d_sums) cudaFree(h->d_sums);
+  if (h->h_sums) cudaFreeHost(h->h_sums);
+  if (h->d_acc) cudaFree(h->d_acc);
+  if (h->h_acc) cudaFreeHost(h->h_acc);
+  if (h->d_u32) cudaFree(h->d_u32);
+  if (h->h_u32) cudaFreeHost(h->h_u32);
+  ctx_destroy(h->c);
+  delete h;
+  return LB_OK;
+}
+
+int lb_ndt_set_params(lb_ndt* h, const lb_ndt_params* p) {
+  if (!h || !p) { set_error("lb_ndt_set_params: null argument"); return LB_ERR_INVALID_ARG; }
+  if (!(p->resolution > 0) || !(p->step_size > 0) || !(p->outlier_ratio > 0) || !(p->outlier_ratio < 1) ||
+      !(p->transformation_epsilon > 0) || p->max_iterations < 0 || p->min_points_per_voxel < 3 || !(p->min_covar_eigvalue_mult > 0)) {
+    // setMinPointVoxel refuses fewer than 3 points (voxel_grid_covariance_omp.h:203-214)
+    set_error("lb_ndt_set_params: resolution / step / outlier ratio / epsilon must be positive, min_points_per_voxel >= 3");
+    return LB_ERR_INVALID_ARG;
+  }
+  if (p->search_method != NDT_KDTREE && p->search_method != NDT_DIRECT7 && p->search_method != NDT_DIRECT1) {
+    set_error("lb_ndt_set_params: search_method must be 0 (KDTREE), 2 (DIRECT7) or 3 (DIRECT1)");
+    return LB_ERR_UNSUPPORTED;
+  }
+  // setResolution re-initialises the voxel structure of the current target (ndt_omp.h:124-131); the same holds for the
+  // two voxel parameters
+  if (p->resolution != h->P.resolution || p->min_points_per_voxel != h->P.min_points_per_voxel ||
+      p->min_covar_eigvalue_mult != h->P.min_covar_eigvalue_mult)
+    h->tgt_dirty = h->n_tgt > 0;
+  h->P = *p;
+  ndt_gauss_constants(h->P.outlier_ratio, h->P.resolution, h->G);
+  return LB_OK;
+}
+
+// caller cloud -> packed float4 in `dst` (+ bounding box and count of the finite points in h->h_acc); synchronous
+static int ndt_upload(lb_ndt* h, DBuf<f4>& dst, const void* pts, size_t n, size_t stride, size_t xyz_off, int mem, const char* who) {
+  if (!pts || stride < 12 || xyz_off + 12 > stride || (stride & 3) || (xyz_off & 3) || n > 0x7fffffffull) {
+    set_error("%s: bad cloud description (n %zu, stride %zu, xyz offset %zu)", who, n, stride, xyz_off);
+    return LB_ERR_INVALID_ARG;
+  }
+  LB_CUDA(cudaSetDevice(h->c.device));
+  const uint8_t* dev = (const uint8_t*)pts;
+  if (mem == LB_MEM_HOST) {
+    LB_TRY(h->io.ensure(n * stride));
+    LB_CUDA(cudaMemcpyAsync(h->io.p, pts, n * stride, cudaMemcpyHostToDevice, h->c.stream));
+    dev = h->io.p;
+  } else if (mem != LB_MEM_DEVICE) {
+    set_error("%s: mem must be LB_MEM_HOST or LB_MEM_DEVICE", who);
+    return LB_ERR_INVALID_ARG;
+  }
+  LB_TRY(dst.ensure(n));
+  bbox_init_kernel<<<1, 32, 0, h->c.stream>>>(h->d_acc);
+  ndt_gather_kernel<<<cdiv((long long)n, 256), 256, 0, h->c.stream>>>(dev, (uint32_t)n, (uint32_t)stride, (uint32_t)xyz_off, dst.p, h->d_acc);
+  h->c.launches += 2;
+  LB_CUDA(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaStreamSynchronize(h->c.stream));
+  return LB_OK;
+}
+
+int lb_ndt_set_source(lb_ndt* h, const void* pts, size_t n, size_t stride, size_t xyz_off, int mem) {
+  if (!h) { set_error("lb_ndt_set_source: null handle"); return LB_ERR_INVALID_ARG; }
+  if (n == 0) { set_error("lb_ndt_set_source: invalid or empty point cloud dataset given"); return LB_ERR_EMPTY_SOURCE; }
+  LB_TRY(ndt_upload(h, h->src_spare, pts, n, stride, xyz_off, mem, "lb_ndt_set_source"));
+  if (h->h_acc->count != (uint32_t)n) {
+    set_error("lb_ndt_set_source: %zu of %zu points are not finite; the previous source is kept", n - h->h_acc->count, n);
+    return LB_ERR_INVALID_ARG;
+  }
+  std::swap(h->src, h->src_spare);
+  h->n_src = (uint32_t)n;
+  return LB_OK;
+}
+
+int lb_ndt_set_target(lb_ndt* h, const void* pts, size_t n, size_t stride, size_t xyz_off, int mem) {
+  if (!h) { set_error("lb_ndt_set_target: null handle"); return LB_ERR_INVALID_ARG; }
+  if (n == 0) { set_error("lb_ndt_set_target: empty target cloud"); return LB_ERR_NO_TARGET; }
+  LB_TRY(ndt_upload(h, h->tgt_spare, pts, n, stride, xyz_off, mem, "lb_ndt_set_target"));
+  if (h->h_acc->count == 0) { set_error("lb_ndt_set_target: no finite point; the previous target is kept"); return LB_ERR_NO_TARGET; }
+  // lattice check before the swap: a grid the reference would refuse leaves the previous target in place
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; a++) { mn[a] = ord2f(h->h_acc->mn[a]); mx[a] = ord2f(h->h_acc->mx[a]); }
+  NdtLattice L;
+  if (!ndt_lattice(mn, mx, h->P.resolution, L)) {
+    set_error("lb_ndt_set_target: leaf size is too small for the input dataset, integer indices would overflow");
+    return LB_ERR_VOXEL_OVERFLOW;
+  }
+  std::swap(h->tgt, h->tgt_spare);
+  for (int a = 0; a < 3; a++) { h->tgt_mn[a] = mn[a]; h->tgt_mx[a] = mx[a]; }
+  h->n_tgt = (uint32_t)n;
+  h->tgt_dirty = true;
+  h->have_tgt = false;
+  return LB_OK;
+}
+
+// VoxelGridCovariance::filter(true) on the stored target
+static int ndt_build_target(lb_ndt* h) {
+  Ctx& c = h->c;
+  const uint32_t n = h->n_tgt;
+  const float* mn = h->tgt_mn;
+  const float* mx = h->tgt_mx;      // bounding box of the finite points, kept from the upload (a resolution change rebuilds from it)
+  if (!ndt_lattice(mn, mx, h->P.resolution, h->L)) {
+    set_error("NDT target: leaf size is too small for the input dataset, integer indices would overflow");
+    return LB_ERR_VOXEL_OVERFLOW;
+  }
+  const NdtLattice& L = h->L;
+  const uint64_t cells = (uint64_t)L.div_b[0] * L.div_b[1] * L.div_b[2];
+  const uint32_t invalid_key = (uint32_t)cells;                  // one past the last voxel: non-finite points sort to the end
+  int key_bits = 1;
+  while ((1ull << key_bits) <= cells) key_bits++;
+  LB_TRY(h->keys.ensure(n)); LB_TRY(h->flag.ensure(n)); LB_TRY(h->slot_of.ensure(n));
+  ndt_keys_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(h->tgt.p, n, L, invalid_key, h->keys.p);
+  c.launches++;
+  uint32_t *ks = nullptr, *vs = nullptr;
+  LB_TRY(radix_sort_pairs(c, h->sort, h->keys.p, nullptr, n, key_bits, &ks, &vs));
+  ndt_heads_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(ks, n, invalid_key, h->P.min_points_per_voxel, h->flag.p);
+  c.launches++;
+  LB_TRY(exclusive_scan_u32(c, h->scan, h->flag.p, h->slot_of.p, n, h->d_u32));
+  LB_CUDA(cudaMemcpyAsync(h->h_u32, h->d_u32, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  LB_CUDA(cudaStreamSynchronize(c.stream));
+  const uint32_t nv = h->h_u32[0];
+  uint32_t cap = 16;
+  while (cap < 2u * nv) cap <<= 1;
+  LB_TRY(h->vox.ensure(nv + 1)); LB_TRY(h->cen.ensure(nv + 1)); LB_TRY(h->leaf_idx.ensure(nv + 1));
+  LB_TRY(h->hkey.ensure(cap)); LB_TRY(h->hval.ensure(cap));
+  LB_CUDA(cudaMemsetAsync(h->hkey.p, 0xff, (size_t)cap * sizeof(uint32_t), c.stream));
+  if (nv > 0) {
+    ndt_gaussians_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(ks, vs, n, h->flag.p, h->slot_of.p, h->tgt.p, h->P.min_covar_eigvalue_mult,
+                                                              h->vox.p, h->cen.p, h->leaf_idx.p);
+    ndt_hash_insert_kernel<<<cdiv(nv, 256), 256, 0, c.stream>>>(h->leaf_idx.p, nv, h->hkey.p, h->hval.p, cap - 1);
+    c.launches += 2;
+  }
+  LB_CUDA(cudaGetLastError());
+  NdtTargetView& tv = h->tv;
+  tv.vox = h->vox.p; tv.cen = h->cen.p; tv.hkey = h->hkey.p; tv.hval = h->hval.p; tv.hmask = cap - 1;
+  tv.n_valid = (int)nv;
+  for (int a = 0; a < 3; a++) { tv.min_b[a] = L.min_b[a]; tv.max_b[a] = L.max_b[a]; tv.div_b[a] = L.div_b[a]; }
+  tv.leaf = h->P.resolution; tv.inv_leaf = L.inv_leaf;
+  const double radius = (double)h->P.resolution;
+  tv.r2 = (float)(radius * radius);
+  h->tgt_dirty = false;
+  h->have_tgt = true;
+  return LB_OK;
+}
+
+static int ndt_ready(lb_ndt* h, const char* who) {
+  if (!h) { set_error("%s: null handle", who); return LB_ERR_INVALID_ARG; }
+  LB_CUDA(cudaSetDevice(h->c.device));
+  if (h->n_tgt == 0) { set_error("%s: no target set", who); return LB_ERR_NO_TARGET; }
+  if (h->tgt_dirty || !h->have_tgt) LB_TRY(ndt_build_target(h));
+  h->tv.method = h->P.search_method;
+  h->tv.min_pts = h->P.min_points_per_voxel;
+  return LB_OK;
+}
+
+int lb_ndt_target_voxels(lb_ndt* h, size_t capacity, size_t* n_voxels, int32_t* leaf_idx, int32_t* nr_points, double* mean3,
+                         double* icov9, float* centroid3) {
+  LB_TRY(ndt_ready(h, "lb_ndt_target_voxels"));
+  const size_t nv = (size_t)h->tv.n_valid;
+  if (n_voxels) *n_voxels = nv;
+  if (!leaf_idx && !nr_points && !mean3 && !icov9 && !centroid3) return LB_OK;
+  if (capacity < nv) { set_error("lb_ndt_target_voxels: capacity %zu < %zu voxels", capacity, nv); return LB_ERR_CAPACITY; }
+  std::vector<NdtVoxel> v(nv);
+  std::vector<f4> c(nv);
+  LB_CUDA(cudaMemcpyAsync(v.data(), h->vox.p, nv * sizeof(NdtVoxel), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaMemcpyAsync(c.data(), h->cen.p, nv * sizeof(f4), cudaMemcpyDeviceToHost, h->c.stream));
+  if (leaf_idx) LB_CUDA(cudaMemcpyAsync(leaf_idx, h->leaf_idx.p, nv * sizeof(int32_t), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaStreamSynchronize(h->c.stream));
+  for (size_t i = 0; i < nv; i++) {
+    if (nr_points) nr_points[i] = float_to_bits(c[i].w);
+    if (mean3) memcpy(mean3 + 3 * i, v[i].mean, 3 * sizeof(double));
+    if (icov9) memcpy(icov9 + 9 * i, v[i].icov, 9 * sizeof(double));
+    if (centroid3) { centroid3[3 * i] = c[i].x; centroid3[3 * i + 1] = c[i].y; centroid3[3 * i + 2] = c[i].z; }
+  }
+  return LB_OK;
+}
+
+static int ndt_source_ready(lb_ndt* h, const char* who, int* blocks) {
+  if (h->n_src == 0) { set_error("%s: no source set", who); return LB_ERR_EMPTY_SOURCE; }
+  *blocks = cdiv(h->n_src, NDT_EVAL_THREADS);
+  LB_TRY(h->partials.ensure((size_t)*blocks * NDT_NSUM));
+  return LB_OK;
+}
+
+int lb_ndt_derivatives(lb_ndt* h, const float* T16, const double* pose6, int compute_hessian, double* score, double* gradient6,
+                       double* hessian36) {
+  LB_TRY(ndt_ready(h, "lb_ndt_derivatives"));
+  if (!T16 || !pose6 || compute_hessian < 0 || compute_hessian > 2) { set_error("lb_ndt_derivatives: bad argument"); return LB_ERR_INVALID_ARG; }
+  int blocks = 0;
+  LB_TRY(ndt_source_ready(h, "lb_ndt_derivatives", &blocks));
+  NdtCtl& c = *h->h_ctl;
+  memset(&c, 0, sizeof(c));
+  for (int i = 0; i < 12; i++) c.T[i] = T16[i];
+  ndt_angles(pose6, c.ang);
+  c.want = compute_hessian == 2 ? NDT_WANT_HESSIAN : (compute_hessian ? NDT_WANT_DERIV_H : NDT_WANT_DERIV);
+  LB_CUDA(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(NdtCtl), cudaMemcpyHostToDevice, h->c.stream));
+  ndt_eval_kernel<<<blocks, NDT_EVAL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+  ndt_sum_kernel<<<1, 64, 0, h->c.stream>>>(h->partials.p, blocks, h->d_sums);
+  h->c.launches += 2;
+  LB_CUDA(cudaMemcpyAsync(h->h_sums, h->d_sums, NDT_NSUM * sizeof(double), cudaMemcpyDeviceToHost, h->c.stream));
+  LB_CUDA(cudaStreamSynchronize(h->c.stream));
+  if (score) *score = h->h_sums[0];
+  if (gradient6) memcpy(gradient6, h->h_sums + 1, 6 * sizeof(double));
+  if (hessian36) memcpy(hessian36, h->h_sums + 7, 36 * sizeof(double));
+  return LB_OK;
+}
+
+int lb_ndt_align(lb_ndt* h, const float* guess16, lb_ndt_result* result) {
+  LB_TRY(ndt_ready(h, "lb_ndt_align"));
+  if (!result) { set_error("lb_ndt_align: null result"); return LB_ERR_INVALID_ARG; }
+  int blocks = 0;
+  LB_TRY(ndt_source_ready(h, "lb_ndt_align", &blocks));
+  const auto t0 = std::chrono::steady_clock::now();
+  static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const float* g = guess16 ? guess16 : I16;
+  for (int i = 0; i < 12; i++) if (!isfinite(g[i])) { set_error("lb_ndt_align: the guess is not finite"); return LB_ERR_INVALID_ARG; }
+  NdtCtl& c = *h->h_ctl;
+  ndt_ctl_begin(c, g, h->P.step_size, h->P.transformation_epsilon, h->P.max_iterations);
+  LB_CUDA(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(NdtCtl), cudaMemcpyHostToDevice, h->c.stream));
+  // an align needs at most (max_iterations + 2) Newton steps of 1 + 10 + 1 evaluations each
+  const long max_pairs = 1 + (long)(h->P.max_iterations + 3) * 12;
+  long pairs = 0;
+  for (;;) {
+    for (int b = 0; b < NDT_BATCH; b++) {
+      ndt_eval_kernel<<<blocks, NDT_EVAL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+      ndt_ctl_kernel<<<1, 64, 0, h->c.stream>>>(h->d_ctl, h->partials.p, blocks);
+    }
+    h->c.launches += 2 * NDT_BATCH;
+    pairs += NDT_BATCH;
+    LB_CUDA(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(NdtCtl), cudaMemcpyDeviceToHost, h->c.stream));
+    LB_CUDA(cudaStreamSynchronize(h->c.stream));
+    if (c.want == NDT_WANT_NONE) break;
+    if (pairs > max_pairs) { set_error("lb_ndt_align: the controller did not finish within %ld evaluations", pairs); return LB_ERR_CUDA; }
+  }
+  memset(result, 0, sizeof(*result));
+  for (int i = 0; i < 12; i++) result->final_transformation[i] = c.final_T[i];
+  result->final_transformation[15] = 1.0f;
+  result->converged = c.converged;
+  result->nr_iterations = c.nr_iterations;
+  result->n_evaluations = c.n_evals;
+  result->trans_probability = c.score / (double)h->n_src;          // ndt_omp_impl.hpp:207
+  for (int i = 0; i < 6; i++) result->pose[i] = c.p[i];
+  result->n_target_voxels = h->tv.n_valid;
+  result->t_total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return LB_OK;
+}
+
+int lb_ndt_launch_count(lb_ndt* h, uint64_t* n) {
+  if (!h || !n) { set_error("lb_ndt_launch_count: null argument"); return LB_ERR_INVALID_ARG; }
+  *n = h->c.launches;
+  return LB_OK;
+}
+
+}  // extern "C"

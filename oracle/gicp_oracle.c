@@ -92,6 +92,9 @@ static void sym3_jacobi(double A[3][3], double d[3], double V[3][3]) {
   d[0] = A[0][0]; d[1] = A[1][1]; d[2] = A[2][2];
 }
 
+/* the same decomposition for ndt_oracle.c (SelfAdjointEigenSolver<Matrix3d>) */
+void og_sym3_jacobi(double A[3][3], double d[3], double V[3][3]) { sym3_jacobi(A, d, V); }
+
 /* gicp.hpp:139-153: U from SVD, singular values descending; rebuild with (1,1,eps) */
 static void regularise_cov(double cov[3][3], double eps, double out[9]) {
   double d[3], V[3][3];

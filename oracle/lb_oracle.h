@@ -225,6 +225,47 @@ int og_normals_knn(const float* pts, int n, int stride_f, int k, const float vp[
 int og_normals_radius(const float* pts, int n, int stride_f, double radius, const float vp[3], float* out4, int* valid_idx,
                       int num_threads);
 
+/* ------------------------------------------------- NDT (ndt_oracle.c; PARITY UNPINNED, see there) */
+typedef struct {
+  float resolution;                /* ndt_omp_impl.hpp:50  default 1.0: voxel side AND neighbour radius */
+  double step_size;                /* :51  0.1  More-Thuente maximum step */
+  double outlier_ratio;            /* :52  0.55 */
+  double transformation_epsilon;   /* :93  0.1; LOCUS passes its icp_tf_epsilon (PointCloudOdometry.cc:188) */
+  int max_iterations;              /* :94  35;  LOCUS passes its icp_iterations (PointCloudOdometry.cc:190) */
+  int min_points_per_voxel;        /* voxel_grid_covariance_omp.h:186  6 */
+  double min_covar_eigvalue_mult;  /* voxel_grid_covariance_omp.h:187  0.01 */
+  int search_method;               /* 0 KDTREE (default, ndt_omp_impl.hpp:96), 2 DIRECT7, 3 DIRECT1 */
+  int num_threads;
+} og_ndt_params;
+
+typedef struct {
+  float final_transformation[16];  /* row-major 4x4 */
+  int converged, nr_iterations;
+  double trans_probability;        /* score / number of source points (ndt_omp_impl.hpp:207) */
+  long n_evaluations;              /* computeDerivatives calls */
+  double pose[6];                  /* x y z roll pitch yaw of the last iterate */
+  int status;
+} og_ndt_result;
+
+typedef struct og_ndt_target og_ndt_target;
+void og_ndt_default_params(og_ndt_params* p);
+/* setInputTarget -> init() -> VoxelGridCovariance::filter(true) */
+og_ndt_target* og_ndt_target_build(const float* pts, int n, int stride_f, const og_ndt_params* p);
+void og_ndt_target_free(og_ndt_target* t);
+/* 0 ok, -1 no finite point, -2 voxel index would overflow int32 */
+int og_ndt_target_info(const og_ndt_target* t, int* n_valid, int* n_all, int min_b[3], int div_b[3]);
+/* the voxel_centroids_ list (ascending voxel index): n_valid entries each */
+void og_ndt_target_leaves(const og_ndt_target* t, int* leaf_idx, int* nr_points, double* mean3, double* icov9, float* centroid3);
+/* computeDerivatives on T16 * src with the angle derivatives of p (float path; compute_hessian as the reference's flag) */
+int og_ndt_derivatives(const og_ndt_target* t, const float* src, int n, int stride_f, const float* T16, const double p[6],
+                       int compute_hessian, double* score, double g[6], double H[36]);
+/* computeHessian (double path, what the line search calls after its last trial) */
+int og_ndt_hessian(const og_ndt_target* t, const float* src, int n, int stride_f, const float* T16, const double p[6], double H[36]);
+/* align(output, guess): guess NULL = identity */
+int og_ndt_align(const og_ndt_target* t, const float* src, int n, int stride_f, const float* guess, og_ndt_result* result);
+void og_ndt_pose_to_matrix(const double p[6], float T[16]);
+void og_ndt_euler_xyz(const float T[16], float out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "_build", "liblocus_oracle.so")
 
 
 def build(force=False):
-    srcs = ["kdtree.c", "bfgs_oracle.c", "gicp_oracle.c", "voxel_oracle.c", "normals_oracle.c", "lb_oracle.h"]
+    srcs = ["kdtree.c", "bfgs_oracle.c", "gicp_oracle.c", "voxel_oracle.c", "normals_oracle.c", "ndt_oracle.c", "lb_oracle.h"]
     if not force and os.path.exists(_SO):
         mt = os.path.getmtime(_SO)
         if all(os.path.getmtime(os.path.join(_HERE, s)) <= mt for s in srcs):
@@ -51,6 +51,21 @@ class VoxelParams(C.Structure):
         ("filter_limit_negative", C.c_int), ("min_points_per_voxel", C.c_int),
         ("downsample_all_data", C.c_int),
         ("body_enabled", C.c_int), ("body_min", C.c_float * 3), ("body_max", C.c_float * 3), ("body_rotation", C.c_float),
+    ]
+
+
+class NdtParams(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+        ("transformation_epsilon", C.c_double), ("max_iterations", C.c_int), ("min_points_per_voxel", C.c_int),
+        ("min_covar_eigvalue_mult", C.c_double), ("search_method", C.c_int), ("num_threads", C.c_int),
+    ]
+
+
+class NdtResult(C.Structure):
+    _fields_ = [
+        ("final_transformation", C.c_float * 16), ("converged", C.c_int), ("nr_iterations", C.c_int),
+        ("trans_probability", C.c_double), ("n_evaluations", C.c_long), ("pose", C.c_double * 6), ("status", C.c_int),
     ]
 
 
@@ -96,6 +111,22 @@ def lib():
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.og_normalize_pcloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.og_compute_ap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_ndt_default_params.argtypes = [C.POINTER(NdtParams)]
+        L.og_ndt_target_build.restype = C.c_void_p
+        L.og_ndt_target_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(NdtParams)]
+        L.og_ndt_target_free.argtypes = [C.c_void_p]
+        L.og_ndt_target_info.restype = C.c_int
+        L.og_ndt_target_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_ndt_target_leaves.argtypes = [C.c_void_p] * 6
+        L.og_ndt_derivatives.restype = C.c_int
+        L.og_ndt_derivatives.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_ndt_hessian.restype = C.c_int
+        L.og_ndt_hessian.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.og_ndt_align.restype = C.c_int
+        L.og_ndt_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(NdtResult)]
+        L.og_ndt_pose_to_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.og_ndt_euler_xyz.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -337,3 +368,77 @@ def normals_radius(pts, radius, viewpoint=(0.0, 0.0, 0.0), num_threads=8):
     if m < 0:
         raise ValueError("og_normals_radius failed")
     return out, vi[:m]
+
+
+# ---------------------------------------------------------------- NDT (row f4; ndt_oracle.c -- parity unpinned)
+def ndt_params(**kw):
+    p = NdtParams()
+    lib().og_ndt_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class NdtTarget:
+    """setInputTarget of pclomp::NormalDistributionsTransform: the target's voxel Gaussians + centroid kd-tree."""
+
+    def __init__(self, tgt, params=None):
+        self.tgt = _as_cloud(tgt)
+        self.params = params or ndt_params()
+        self.h = lib().og_ndt_target_build(_p(self.tgt), self.tgt.shape[0], self.tgt.shape[1], C.byref(self.params))
+        nv = C.c_int(); na = C.c_int()
+        self.min_b = np.zeros(3, np.int32); self.div_b = np.zeros(3, np.int32)
+        self.status = lib().og_ndt_target_info(self.h, C.byref(nv), C.byref(na), _p(self.min_b), _p(self.div_b))
+        self.n_valid, self.n_all = nv.value, na.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().og_ndt_target_free(self.h); self.h = None
+
+    def leaves(self):
+        n = self.n_valid
+        out = {"leaf_idx": np.zeros(n, np.int32), "nr_points": np.zeros(n, np.int32), "mean": np.zeros((n, 3)),
+               "icov": np.zeros((n, 9)), "centroid": np.zeros((n, 3), np.float32)}
+        lib().og_ndt_target_leaves(self.h, _p(out["leaf_idx"]), _p(out["nr_points"]), _p(out["mean"]), _p(out["icov"]),
+                                   _p(out["centroid"]))
+        return out
+
+    def derivatives(self, src, T, pose, compute_hessian=True):
+        src = _as_cloud(src)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        score = C.c_double(); g = np.zeros(6); H = np.zeros((6, 6))
+        lib().og_ndt_derivatives(self.h, _p(src), src.shape[0], src.shape[1], _p(T), _p(pose), int(compute_hessian),
+                                 C.byref(score), _p(g), _p(H))
+        return score.value, g, H
+
+    def hessian(self, src, T, pose):
+        src = _as_cloud(src)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        H = np.zeros((6, 6))
+        lib().og_ndt_hessian(self.h, _p(src), src.shape[0], src.shape[1], _p(T), _p(pose), _p(H))
+        return H
+
+    def align(self, src, guess=None):
+        src = _as_cloud(src)
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        r = NdtResult()
+        rc = lib().og_ndt_align(self.h, _p(src), src.shape[0], src.shape[1], _p(g), C.byref(r))
+        return {"status": rc, "T": np.array(r.final_transformation, dtype=np.float32).reshape(4, 4),
+                "converged": bool(r.converged), "iterations": r.nr_iterations, "trans_probability": r.trans_probability,
+                "evaluations": r.n_evaluations, "pose": np.array(r.pose)}
+
+
+def ndt_pose_to_matrix(pose):
+    pose = np.ascontiguousarray(pose, dtype=np.float64); T = np.zeros(16, np.float32)
+    lib().og_ndt_pose_to_matrix(_p(pose), _p(T))
+    return T.reshape(4, 4)
+
+
+def ndt_euler_xyz(T):
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(16); e = np.zeros(3, np.float32)
+    lib().og_ndt_euler_xyz(_p(T), _p(e))
+    return e
