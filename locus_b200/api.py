@@ -51,6 +51,24 @@ class GicpResult(C.Structure):
     ]
 
 
+class NdtParams(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+        ("transformation_epsilon", C.c_double), ("max_iterations", C.c_int), ("min_points_per_voxel", C.c_int),
+        ("min_covar_eigvalue_mult", C.c_double), ("search_method", C.c_int),
+        ("max_correspondence_distance", C.c_double), ("ransac_iterations", C.c_int), ("num_threads", C.c_int),
+        ("enable_timing_output", C.c_int),
+    ]
+
+
+class NdtResult(C.Structure):
+    _fields_ = [
+        ("final_transformation", C.c_float * 16), ("converged", C.c_int), ("nr_iterations", C.c_int),
+        ("n_evaluations", C.c_int), ("n_target_voxels", C.c_int), ("trans_probability", C.c_double),
+        ("pose", C.c_double * 6), ("t_total_s", C.c_double),
+    ]
+
+
 class OdometryResult(C.Structure):
     _fields_ = [("ticket", C.c_uint64), ("status", C.c_int), ("has_pose", C.c_int), ("n_filtered", C.c_size_t),
                 ("gicp", GicpResult), ("error", C.c_char * 160)]
@@ -82,6 +100,8 @@ SYMBOLS = [
     "lb_odometry_create", "lb_odometry_destroy", "lb_odometry_voxel", "lb_odometry_gicp", "lb_odometry_depth",
     "lb_odometry_set_gicp_params", "lb_odometry_set_cloud_sharing", "lb_odometry_submit", "lb_odometry_next", "lb_odometry_pending",
     "lb_odometry_launch_count", "lb_odometry_stage_times",
+    "lb_ndt_default_params", "lb_ndt_create", "lb_ndt_create_on_stream", "lb_ndt_destroy", "lb_ndt_set_params", "lb_ndt_set_source",
+    "lb_ndt_set_target", "lb_ndt_align", "lb_ndt_target_voxels", "lb_ndt_derivatives", "lb_ndt_launch_count",
 ]
 
 
@@ -192,6 +212,19 @@ def lib():
         L.lb_odometry_pending.argtypes = [vp, C.POINTER(sz)]
         L.lb_odometry_launch_count.argtypes = [vp, u64p]
         L.lb_odometry_stage_times.argtypes = [vp, C.POINTER(C.c_double)]
+    if hasattr(L, "lb_ndt_create"):
+        L.lb_ndt_default_params.argtypes = [C.POINTER(NdtParams)]
+        L.lb_ndt_default_params.restype = None
+        L.lb_ndt_create.argtypes = [i32, C.POINTER(vp)]
+        L.lb_ndt_create_on_stream.argtypes = [i32, vp, C.POINTER(vp)]
+        L.lb_ndt_destroy.argtypes = [vp]
+        L.lb_ndt_set_params.argtypes = [vp, C.POINTER(NdtParams)]
+        L.lb_ndt_set_source.argtypes = [vp, vp, sz, sz, sz, i32]
+        L.lb_ndt_set_target.argtypes = [vp, vp, sz, sz, sz, i32]
+        L.lb_ndt_align.argtypes = [vp, vp, C.POINTER(NdtResult)]
+        L.lb_ndt_target_voxels.argtypes = [vp, sz, C.POINTER(sz), vp, vp, vp, vp, vp]
+        L.lb_ndt_derivatives.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_double), vp, vp]
+        L.lb_ndt_launch_count.argtypes = [vp, u64p]
     _lib = L
     return L
 
@@ -710,3 +743,106 @@ class OdometryB200:
         _check(lib().lb_odometry_stage_times(self._h, a))
         return {"filtered": int(a[0]), "voxel_busy_s": a[1], "voxel_wait_s": a[2], "registered": int(a[3]),
                 "workers_busy_s": a[4], "workers_wait_s": a[5]}
+
+
+NDT_KDTREE, NDT_DIRECT7, NDT_DIRECT1 = 0, 2, 3
+
+
+class NdtB200:
+    """Mirror of the pclomp::NormalDistributionsTransform surface LOCUS drives when `registration_method: ndt`
+    (PointCloudOdometry.cc:182-195, PointCloudLocalization.cc:267-280; setters of ndt_omp.h:116-196)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        L = lib()
+        if stream is None:
+            _check(L.lb_ndt_create(device, C.byref(self._h)))
+        else:
+            _check(L.lb_ndt_create_on_stream(device, C.c_void_p(int(stream)), C.byref(self._h)))
+        self._p = NdtParams()
+        L.lb_ndt_default_params(C.byref(self._p))
+        self._res = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lb_ndt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _apply(self):
+        _check(lib().lb_ndt_set_params(self._h, C.byref(self._p)))
+
+    def setTransformationEpsilon(self, v): self._p.transformation_epsilon = v; self._apply()
+    def setMaximumIterations(self, v): self._p.max_iterations = int(v); self._apply()
+    def setMaxCorrespondenceDistance(self, v): self._p.max_correspondence_distance = v; self._apply()
+    def setRANSACIterations(self, v): self._p.ransac_iterations = int(v); self._apply()
+    def setNumThreads(self, v): self._p.num_threads = int(v); self._apply()
+    def enableTimingOutput(self, v): self._p.enable_timing_output = int(bool(v)); self._apply()
+    def setResolution(self, v): self._p.resolution = float(v); self._apply()
+    def setStepSize(self, v): self._p.step_size = float(v); self._apply()
+    def setOulierRatio(self, v): self._p.outlier_ratio = float(v); self._apply()           # the reference's spelling (ndt_omp.h:166)
+    def setNeighborhoodSearchMethod(self, v): self._p.search_method = int(v); self._apply()
+    def setMinPointPerVoxel(self, v): self._p.min_points_per_voxel = int(v); self._apply()
+    def setCovEigValueInflationRatio(self, v): self._p.min_covar_eigvalue_mult = float(v); self._apply()
+    def getResolution(self): return self._p.resolution
+    def getStepSize(self): return self._p.step_size
+    def getOulierRatio(self): return self._p.outlier_ratio
+
+    @staticmethod
+    def _cloud(cloud):
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 3
+        return a
+
+    def setInputSource(self, cloud):
+        a = self._cloud(cloud)
+        _check(lib().lb_ndt_set_source(self._h, _ptr(a), a.shape[0], a.shape[1] * 4, 0, LB_MEM_HOST))
+
+    def setInputTarget(self, cloud):
+        a = self._cloud(cloud)
+        _check(lib().lb_ndt_set_target(self._h, _ptr(a), a.shape[0], a.shape[1] * 4, 0, LB_MEM_HOST))
+
+    def align(self, guess=None):
+        g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float32).reshape(16)
+        r = NdtResult()
+        _check(lib().lb_ndt_align(self._h, _ptr(g), C.byref(r)))
+        self._res = r
+        return r
+
+    def _result(self):
+        if self._res is None:
+            raise LocusB200Error(-10, "no successful align() yet")
+        return self._res
+
+    def getFinalTransformation(self): return np.array(self._result().final_transformation, dtype=np.float32).reshape(4, 4)
+    def hasConverged(self): return bool(self._result().converged)
+    def getTransformationProbability(self): return self._result().trans_probability
+    def getFinalNumIteration(self): return self._result().nr_iterations
+
+    def targetVoxels(self):
+        """The searchable voxels of the target (voxel_centroids_ order = ascending voxel index)."""
+        n = C.c_size_t(0)
+        _check(lib().lb_ndt_target_voxels(self._h, 0, C.byref(n), None, None, None, None, None))
+        n = n.value
+        out = {"leaf_idx": np.zeros(n, np.int32), "nr_points": np.zeros(n, np.int32), "mean": np.zeros((n, 3)),
+               "icov": np.zeros((n, 9)), "centroid": np.zeros((n, 3), np.float32)}
+        _check(lib().lb_ndt_target_voxels(self._h, n, C.byref(C.c_size_t(0)), _ptr(out["leaf_idx"]), _ptr(out["nr_points"]),
+                                          _ptr(out["mean"]), _ptr(out["icov"]), _ptr(out["centroid"])))
+        return out
+
+    def derivatives(self, T, pose, compute_hessian=1):
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        score = C.c_double(0); g = np.zeros(6); H = np.zeros((6, 6))
+        _check(lib().lb_ndt_derivatives(self._h, _ptr(T), _ptr(pose), int(compute_hessian), C.byref(score), _ptr(g), _ptr(H)))
+        return score.value, g, H
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        _check(lib().lb_ndt_launch_count(self._h, C.byref(n)))
+        return n.value

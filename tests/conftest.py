@@ -66,3 +66,27 @@ def oracle():
     from oracle import oracle as O
     O.build()
     return O
+
+
+@pytest.fixture(scope="session")
+def ndt_harness():
+    """TEST-ONLY CPU build of the product's NDT header (locus_b200/csrc/ndt.h) with a serial backend (tests/ndt_harness.cpp)."""
+    import ctypes as C
+    bdir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(bdir, exist_ok=True)
+    so = os.path.join(bdir, "libndt_harness.so")
+    src = os.path.join(ROOT, "tests", "ndt_harness.cpp")
+    hdrs = [os.path.join(ROOT, "locus_b200", "csrc", h) for h in ("hd.h", "ndt.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-o", so, src])
+    H = C.CDLL(so)
+    vp = C.c_void_p
+    H.hn_target_build.restype = vp
+    H.hn_target_build.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, C.c_int, C.c_double]
+    H.hn_target_free.argtypes = [vp]
+    H.hn_target_info.argtypes = [vp] * 4
+    H.hn_target_leaves.argtypes = [vp] * 6
+    H.hn_eval.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]
+    H.hn_align.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_int] + [vp] * 6
+    return H

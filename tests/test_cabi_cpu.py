@@ -32,6 +32,9 @@ def test_no_cpu_fallback():
     assert e.value.status == -3
     with pytest.raises(locus_b200.LocusB200Error):
         locus_b200.VoxelGridB200()
+    with pytest.raises(locus_b200.LocusB200Error) as e:
+        locus_b200.NdtB200()
+    assert e.value.status == -3
 
 
 def test_product_does_not_touch_oracle():
