@@ -68,30 +68,57 @@ ndt_heads_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t invalid
   flag[i] = f;
 }
 
-__global__ void __launch_bounds__(128)
-ndt_gaussians_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, const uint32_t* __restrict__ flag,
-                     const uint32_t* __restrict__ slot_of, const f4* __restrict__ pts, double eig_mult, NdtVoxel* __restrict__ vox,
-                     f4* __restrict__ cen, int32_t* __restrict__ leaf_idx) {
+// head_pos[slot] = sorted position at which the slot-th searchable voxel starts
+__global__ void __launch_bounds__(256)
+ndt_head_pos_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* __restrict__ head_pos) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  const uint32_t k = keys[i];
+  if (i < n && flag[i]) head_pos[slot_of[i]] = i;
+}
+
+// One warp per voxel.  The lanes fetch 32 points of the voxel at a time (the next batch while the current one is being
+// added); the sums themselves run over the points one after the other in input order on every lane alike -- that order
+// is what makes mean / covariance / centroid reproducible bit for bit (the reference adds them in its input loop,
+// voxel_grid_covariance_omp_impl.hpp:218-225).  A thread per voxel instead took 0.8 ms on a 130 k-point scan: two
+// dependent gathers per point, and the voxel under the sensor holds thousands of points.
+__global__ void __launch_bounds__(128)
+ndt_gaussians_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, const uint32_t* __restrict__ head_pos,
+                     uint32_t n_valid, const f4* __restrict__ pts, double eig_mult, NdtVoxel* __restrict__ vox, f4* __restrict__ cen,
+                     int32_t* __restrict__ leaf_idx) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_valid) return;
+  const uint32_t i0 = head_pos[w];
+  const uint32_t k = keys[i0];
   double sum[3] = {0, 0, 0}, m2[6] = {0, 0, 0, 0, 0, 0};
   float csum[3] = {0.f, 0.f, 0.f};
-  uint32_t j = i;
-  for (; j < n && keys[j] == k; j++) {          // input order: the sort is stable
-    const f4 p = pts[vals[j]];
-    const double d0 = p.x, d1 = p.y, d2 = p.z;
-    sum[0] += d0; sum[1] += d1; sum[2] += d2;
-    csum[0] += p.x; csum[1] += p.y; csum[2] += p.z;
-    m2[0] += d0 * d0; m2[1] += d0 * d1; m2[2] += d0 * d2; m2[3] += d1 * d1; m2[4] += d1 * d2; m2[5] += d2 * d2;
+  uint32_t total = 0;
+  uint32_t j = i0 + lane;
+  bool in = j < n && keys[j] == k;
+  f4 p = in ? pts[vals[j]] : f4{0.f, 0.f, 0.f, 0.f};
+  for (;;) {
+    const int cnt = __popc(__ballot_sync(0xffffffffu, in));        // the voxel's points are contiguous: a prefix of the lanes
+    const f4 cur = p;
+    if (cnt == 32) {                                               // fetch the next batch before adding this one
+      j += 32;
+      in = j < n && keys[j] == k;
+      p = in ? pts[vals[j]] : f4{0.f, 0.f, 0.f, 0.f};
+    }
+    for (int t = 0; t < cnt; t++) {
+      const float x = __shfl_sync(0xffffffffu, cur.x, t), y = __shfl_sync(0xffffffffu, cur.y, t), z = __shfl_sync(0xffffffffu, cur.z, t);
+      const double d0 = x, d1 = y, d2 = z;
+      sum[0] += d0; sum[1] += d1; sum[2] += d2;
+      csum[0] += x; csum[1] += y; csum[2] += z;
+      m2[0] += d0 * d0; m2[1] += d0 * d1; m2[2] += d0 * d2; m2[3] += d1 * d1; m2[4] += d1 * d2; m2[5] += d2 * d2;
+    }
+    total += (uint32_t)cnt;
+    if (cnt < 32) break;
   }
+  if (lane != 0) return;
   NdtVoxel v;
   float c[3];
-  const int nr = ndt_finish_voxel((int)(j - i), sum, m2, csum, eig_mult, v, c);
-  const uint32_t s = slot_of[i];
-  vox[s] = v;
-  cen[s] = f4{c[0], c[1], c[2], __int_as_float(nr)};
-  leaf_idx[s] = (int32_t)k;
+  const int nr = ndt_finish_voxel((int)total, sum, m2, csum, eig_mult, v, c);
+  vox[w] = v;
+  cen[w] = f4{c[0], c[1], c[2], __int_as_float(nr)};
+  leaf_idx[w] = (int32_t)k;
 }
 
 __global__ void __launch_bounds__(256)
@@ -108,15 +135,19 @@ ndt_hash_insert_kernel(const int32_t* __restrict__ leaf_idx, uint32_t n_valid, u
   }
 }
 
-// One evaluation: every source point against the voxels around it; one partial (43 doubles) per CTA.
+// One evaluation: every source point against the voxels around it; one partial (43 doubles) per CTA.  Which sums the
+// controller wants (score + gradient / + Hessian / the double-precision Hessian alone) is only known on the device, so
+// one specialisation per request is enqueued and the two that do not match return at once: the line search's trials
+// (score + gradient, 7 sums) then run with a third of the registers of the 43-sum pass.
+template <int WANT>
 __global__ void __launch_bounds__(NDT_EVAL_THREADS)
 ndt_eval_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss G, const f4* __restrict__ src, uint32_t n,
                 double* __restrict__ partials) {
+  constexpr int K0 = WANT == NDT_WANT_HESSIAN ? 7 : 0, K1 = WANT == NDT_WANT_DERIV ? 7 : NDT_NSUM;
   __shared__ NdtAngles sA;
   __shared__ float sT[12];
-  __shared__ double sred[NDT_EVAL_THREADS / 32][NDT_NSUM];
-  const int want = ctl->want;
-  if (want == NDT_WANT_NONE) return;                       // the align finished in an earlier pair of this batch
+  __shared__ double sred[NDT_EVAL_THREADS / 32][K1 - K0];
+  if (ctl->want != WANT) return;                           // another specialisation's turn, or the align has finished
   {
     const uint32_t* g = reinterpret_cast<const uint32_t*>(&ctl->ang);
     uint32_t* s = reinterpret_cast<uint32_t*>(&sA);
@@ -130,53 +161,132 @@ ndt_eval_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss G, co
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const f4 p = src[i];
-    ndt_point_eval(tv, G, sA, sT, p.x, p.y, p.z, want, acc);
+    ndt_point_eval(tv, G, sA, sT, p.x, p.y, p.z, WANT, acc);
   }
-  // the sums this request needs: DERIV = score + gradient, DERIV_H = all, HESSIAN = the 6x6 only
-  const int k0 = want == NDT_WANT_HESSIAN ? 7 : 0, k1 = want == NDT_WANT_DERIV ? 7 : NDT_NSUM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NDT_NSUM; k++) {
-    if (k < k0 || k >= k1) continue;
+  for (int k = K0; k < K1; k++) {
     double v = acc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sred[warp][k] = v;
+    if (lane == 0) sred[warp][k - K0] = v;
   }
   __syncthreads();
   if (threadIdx.x < NDT_NSUM) {
     const int k = threadIdx.x;
     double v = 0.0;
-    if (k >= k0 && k < k1) {
+    if (k >= K0 && k < K1) {
 #pragma unroll
-      for (int w = 0; w < NDT_EVAL_THREADS / 32; w++) v += sred[w][k];
+      for (int w = 0; w < NDT_EVAL_THREADS / 32; w++) v += sred[w][k - K0];
     }
-    partials[(size_t)blockIdx.x * NDT_NSUM + k] = v;
+    partials[(size_t)blockIdx.x * NDT_NSUM + k] = v;       // sums this request does not produce are 0 (hessian.setZero())
   }
 }
 
-// Adds the CTA partials in CTA order (fixed shape: run-to-run identical bits) and advances the controller.
-__global__ void __launch_bounds__(64)
-ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, int blocks) {
-  __shared__ double sums[NDT_NSUM];
-  if (ctl->want == NDT_WANT_NONE) return;
-  if (threadIdx.x < NDT_NSUM) {
+static void ndt_launch_eval(int want, int blocks, cudaStream_t st, const NdtCtl* ctl, const NdtTargetView& tv, const NdtGauss& G,
+                            const f4* src, uint32_t n, double* partials) {
+  if (want == NDT_WANT_DERIV_H) ndt_eval_kernel<NDT_WANT_DERIV_H><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else if (want == NDT_WANT_DERIV) ndt_eval_kernel<NDT_WANT_DERIV><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else ndt_eval_kernel<NDT_WANT_HESSIAN><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+}
+
+// Adds the CTA partials (fixed shape: eight consecutive ranges of CTAs summed in CTA order, then the eight range sums in
+// order -- run-to-run identical bits) and advances the controller.
+constexpr int NDT_CTL_PARTS = 8;
+constexpr int NDT_CTL_THREADS = 352;                       // >= NDT_NSUM * NDT_CTL_PARTS
+__device__ __forceinline__ void ndt_sum_partials(const double* __restrict__ partials, int blocks, double (*part)[NDT_NSUM], double* sums) {
+  const int t = threadIdx.x;
+  if (t < NDT_NSUM * NDT_CTL_PARTS) {
+    const int k = t % NDT_NSUM, r = t / NDT_NSUM;
+    const int per = (blocks + NDT_CTL_PARTS - 1) / NDT_CTL_PARTS;
+    const int b0 = r * per, b1 = min(blocks, b0 + per);
     double v = 0.0;
-    for (int b = 0; b < blocks; b++) v += partials[(size_t)b * NDT_NSUM + threadIdx.x];
-    sums[threadIdx.x] = v;
+#pragma unroll 8
+    for (int b = b0; b < b1; b++) v += partials[(size_t)b * NDT_NSUM + k];
+    part[r][k] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) ndt_ctl_advance(*ctl, sums);
+  if (t < NDT_NSUM) {
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < NDT_CTL_PARTS; r++) v += part[r][t];
+    sums[t] = v;
+  }
+  __syncthreads();
+}
+
+// The Newton solve of the controller on one warp: x = pinv(A) (-g).  The three disjoint column pairs of a round (ndt.h,
+// ndt_svd6_pair) are rotated side by side, lane (grp, k) = (lane >> 3, lane & 7) holding row k of pair grp; the column
+// norms / dot product of a pair are added in row order (as the serial loop does), so the bits equal ndt_svd6_solve's.
+// The serial solve cost 60-70 us of dependent double-precision divisions and square roots per Newton step.
+__device__ __forceinline__ void ndt_svd6_solve_warp(const double* A, const double* g, double (*U)[6], double (*V)[6], double* x) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < 36; e += 32) { U[e / 6][e % 6] = A[e]; V[e / 6][e % 6] = (e / 6 == e % 6) ? 1.0 : 0.0; }
+  __syncwarp();
+  const int grp = lane >> 3, k = lane & 7;
+  const bool active = grp < 3 && k < 6;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool any = false;
+    for (int r = 0; r < 5; r++) {
+      int p = 0, q = 1;
+      if (grp < 3) ndt_svd6_pair(3 * r + grp, p, q);
+      const double up = active ? U[k][p] : 0.0, uq = active ? U[k][q] : 0.0;
+      const double vp = active ? V[k][p] : 0.0, vq = active ? V[k][q] : 0.0;
+      const double a = up * up, bb = uq * uq, gm = up * uq;
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) {
+        const int from = grp * 8 + kk;
+        alpha += __shfl_sync(FULL, a, from); beta += __shfl_sync(FULL, bb, from); gamma += __shfl_sync(FULL, gm, from);
+      }
+      double c = 1.0, s = 0.0;
+      const bool rot = ndt_svd6_angle(alpha, beta, gamma, c, s) && active;
+      if (rot) {
+        U[k][p] = c * up - s * uq; U[k][q] = s * up + c * uq;
+        V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
+      }
+      any = __any_sync(FULL, rot) || any;
+      __syncwarp();
+    }
+    if (!any) break;
+  }
+  if (lane == 0) {
+    double ng[6];
+    for (int i = 0; i < 6; i++) ng[i] = -g[i];
+    ndt_svd6_finish(U, V, ng, x);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(NDT_CTL_THREADS)
+ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, int blocks) {
+  __shared__ double part[NDT_CTL_PARTS][NDT_NSUM];
+  __shared__ double sums[NDT_NSUM];
+  __shared__ double sU[6][6], sV[6][6], sx[6];
+  if (ctl->want == NDT_WANT_NONE) return;
+  ndt_sum_partials(partials, blocks, part, sums);
+  if (threadIdx.x < 32) {
+    // lane 0 runs the scalar controller; whenever it needs a Newton direction the whole warp computes it
+    int need = 0;
+    if (threadIdx.x == 0) need = ndt_ctl_run(*ctl, sums, nullptr) ? 1 : 0;
+    need = __shfl_sync(0xffffffffu, need, 0);
+    while (need) {
+      __syncwarp();                                       // lane 0's writes of ctl->H / ctl->g are visible to the warp
+      ndt_svd6_solve_warp(ctl->H, ctl->g, sU, sV, sx);
+      if (threadIdx.x == 0) need = ndt_ctl_run(*ctl, sums, sx) ? 1 : 0;
+      need = __shfl_sync(0xffffffffu, need, 0);
+    }
+  }
 }
 
 // lb_ndt_derivatives: one evaluation at a caller-given pose, sums to out[43]
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(NDT_CTL_THREADS)
 ndt_sum_kernel(const double* __restrict__ partials, int blocks, double* __restrict__ out) {
-  if (threadIdx.x < NDT_NSUM) {
-    double v = 0.0;
-    for (int b = 0; b < blocks; b++) v += partials[(size_t)b * NDT_NSUM + threadIdx.x];
-    out[threadIdx.x] = v;
-  }
+  __shared__ double part[NDT_CTL_PARTS][NDT_NSUM];
+  __shared__ double sums[NDT_NSUM];
+  ndt_sum_partials(partials, blocks, part, sums);
+  if (threadIdx.x < NDT_NSUM) out[threadIdx.x] = sums[threadIdx.x];
 }
 
 }  // namespace lb
@@ -196,7 +306,7 @@ struct lb_ndt {
   float tgt_mn[3] = {0, 0, 0}, tgt_mx[3] = {0, 0, 0};
   bool tgt_dirty = false;               // the voxel structure has to be (re)built from tgt
   bool have_tgt = false;
-  DBuf<uint32_t> keys, flag, slot_of;
+  DBuf<uint32_t> keys, flag, slot_of, head_pos;
   SortWork sort;
   ScanWork scan;
   DBuf<NdtVoxel> vox;
@@ -271,7 +381,7 @@ int lb_ndt_destroy(lb_ndt* h) {
   cudaSetDevice(h->c.device);
   if (h->c.stream) cudaStreamSynchronize(h->c.stream);
   h->src.release(); h->src_spare.release(); h->tgt.release(); h->tgt_spare.release();
-  h->keys.release(); h->flag.release(); h->slot_of.release();
+  h->keys.release(); h->flag.release(); h->slot_of.release(); h->head_pos.release();
   h->sort.ka.release(); h->sort.kb.release(); h->sort.va.release(); h->sort.vb.release(); h->sort.hist.release();
   h->sort.scan.sums.release(); h->scan.sums.release();
   h->vox.release(); h->cen.release(); h->leaf_idx.release(); h->hval.release(); h->hkey.release();
@@ -398,14 +508,15 @@ static int ndt_build_target(lb_ndt* h) {
   const uint32_t nv = h->h_u32[0];
   uint32_t cap = 16;
   while (cap < 2u * nv) cap <<= 1;
-  LB_TRY(h->vox.ensure(nv + 1)); LB_TRY(h->cen.ensure(nv + 1)); LB_TRY(h->leaf_idx.ensure(nv + 1));
+  LB_TRY(h->vox.ensure(nv + 1)); LB_TRY(h->cen.ensure(nv + 1)); LB_TRY(h->leaf_idx.ensure(nv + 1)); LB_TRY(h->head_pos.ensure(nv + 1));
   LB_TRY(h->hkey.ensure(cap)); LB_TRY(h->hval.ensure(cap));
   LB_CUDA(cudaMemsetAsync(h->hkey.p, 0xff, (size_t)cap * sizeof(uint32_t), c.stream));
   if (nv > 0) {
-    ndt_gaussians_kernel<<<cdiv(n, 128), 128, 0, c.stream>>>(ks, vs, n, h->flag.p, h->slot_of.p, h->tgt.p, h->P.min_covar_eigvalue_mult,
-                                                              h->vox.p, h->cen.p, h->leaf_idx.p);
+    ndt_head_pos_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(h->flag.p, h->slot_of.p, n, h->head_pos.p);
+    ndt_gaussians_kernel<<<cdiv((long long)nv * 32, 128), 128, 0, c.stream>>>(ks, vs, n, h->head_pos.p, nv, h->tgt.p, h->P.min_covar_eigvalue_mult,
+                                                                              h->vox.p, h->cen.p, h->leaf_idx.p);
     ndt_hash_insert_kernel<<<cdiv(nv, 256), 256, 0, c.stream>>>(h->leaf_idx.p, nv, h->hkey.p, h->hval.p, cap - 1);
-    c.launches += 2;
+    c.launches += 3;
   }
   LB_CUDA(cudaGetLastError());
   NdtTargetView& tv = h->tv;
@@ -471,8 +582,8 @@ int lb_ndt_derivatives(lb_ndt* h, const float* T16, const double* pose6, int com
   ndt_angles(pose6, c.ang);
   c.want = compute_hessian == 2 ? NDT_WANT_HESSIAN : (compute_hessian ? NDT_WANT_DERIV_H : NDT_WANT_DERIV);
   LB_CUDA(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(NdtCtl), cudaMemcpyHostToDevice, h->c.stream));
-  ndt_eval_kernel<<<blocks, NDT_EVAL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
-  ndt_sum_kernel<<<1, 64, 0, h->c.stream>>>(h->partials.p, blocks, h->d_sums);
+  ndt_launch_eval(c.want, blocks, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+  ndt_sum_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->partials.p, blocks, h->d_sums);
   h->c.launches += 2;
   LB_CUDA(cudaMemcpyAsync(h->h_sums, h->d_sums, NDT_NSUM * sizeof(double), cudaMemcpyDeviceToHost, h->c.stream));
   LB_CUDA(cudaStreamSynchronize(h->c.stream));
@@ -499,10 +610,11 @@ int lb_ndt_align(lb_ndt* h, const float* guess16, lb_ndt_result* result) {
   long pairs = 0;
   for (;;) {
     for (int b = 0; b < NDT_BATCH; b++) {
-      ndt_eval_kernel<<<blocks, NDT_EVAL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
-      ndt_ctl_kernel<<<1, 64, 0, h->c.stream>>>(h->d_ctl, h->partials.p, blocks);
+      for (int want = NDT_WANT_DERIV_H; want <= NDT_WANT_HESSIAN; want++)
+        ndt_launch_eval(want, blocks, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+      ndt_ctl_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->partials.p, blocks);
     }
-    h->c.launches += 2 * NDT_BATCH;
+    h->c.launches += 4 * NDT_BATCH;
     pairs += NDT_BATCH;
     LB_CUDA(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(NdtCtl), cudaMemcpyDeviceToHost, h->c.stream));
     LB_CUDA(cudaStreamSynchronize(h->c.stream));

@@ -466,32 +466,28 @@ LB_HD void ndt_euler_xyz(const float* T, float* out) {
 }
 
 // ------------------------------------------------------------------ 6x6 solve through a one-sided Jacobi SVD
-// x = pinv(A) b with Eigen's default rank threshold; stands in for JacobiSVD<Matrix6d>(A, FullU | FullV).solve(b)
-LB_HD void ndt_svd6_solve(const double* A, const double* b, double* x) {
-  double U[6][6], V[6][6];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) { U[i][j] = A[6 * i + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
-  for (int sweep = 0; sweep < 60; sweep++) {
-    int rotated = 0;
-    for (int p = 0; p < 5; p++)
-      for (int q = p + 1; q < 6; q++) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int k = 0; k < 6; k++) { alpha += U[k][p] * U[k][p]; beta += U[k][q] * U[k][q]; gamma += U[k][p] * U[k][q]; }
-        if (gamma == 0.0 || fabs(gamma) <= DBL_EPSILON * sqrt(alpha * beta)) continue;
-        rotated = 1;
-        double zeta = (beta - alpha) / (2.0 * gamma);
-        double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        if (zeta < 0.0) t = -t;
-        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int k = 0; k < 6; k++) {
-          double up = U[k][p], uq = U[k][q];
-          U[k][p] = c * up - s * uq; U[k][q] = s * up + c * uq;
-          double vp = V[k][p], vq = V[k][q];
-          V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
-        }
-      }
-    if (!rotated) break;
-  }
+// x = pinv(A) b with Eigen's default rank threshold; stands in for JacobiSVD<Matrix6d>(A, FullU | FullV).solve(b).
+// The column pairs of a sweep are visited in round-robin order: five rounds of three DISJOINT pairs.  Rotations of
+// disjoint pairs touch disjoint columns, so a round's three rotations may run one after the other (here, and in the
+// oracle) or side by side (the controller warp on the device, ndt.cu) with identical bits.
+LB_HD void ndt_svd6_pair(int idx, int& p, int& q) {
+  const int P[15] = {0, 1, 2, 0, 3, 1, 0, 2, 1, 0, 1, 4, 0, 2, 3};
+  const int Q[15] = {5, 4, 3, 4, 5, 2, 3, 4, 5, 2, 3, 5, 1, 5, 4};
+  p = P[idx]; q = Q[idx];
+}
+// One rotation: columns p, q of U (and V) from alpha = |u_p|^2, beta = |u_q|^2, gamma = u_p . u_q.  Returns false when
+// the columns already are orthogonal to working precision (no rotation).
+LB_HD bool ndt_svd6_angle(double alpha, double beta, double gamma, double& c, double& s) {
+  if (gamma == 0.0 || fabs(gamma) <= DBL_EPSILON * sqrt(alpha * beta)) return false;
+  const double zeta = (beta - alpha) / (2.0 * gamma);
+  double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  if (zeta < 0.0) t = -t;
+  c = 1.0 / sqrt(1.0 + t * t);
+  s = c * t;
+  return true;
+}
+// singular values from the rotated columns, Eigen's rank threshold, x = V S^+ U' b
+LB_HD void ndt_svd6_finish(const double (*U)[6], const double (*V)[6], const double* b, double* x) {
   double sig[6];
   int ord[6];
   for (int j = 0; j < 6; j++) {
@@ -516,7 +512,31 @@ LB_HD void ndt_svd6_solve(const double* A, const double* b, double* x) {
     for (int r = 0; r < 6; r++) x[r] += V[r][j] * w;
   }
 }
-
+LB_HD void ndt_svd6_solve(const double* A, const double* b, double* x) {
+  double U[6][6], V[6][6];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) { U[i][j] = A[6 * i + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    int rotated = 0;
+    for (int e = 0; e < 15; e++) {
+      int p, q;
+      ndt_svd6_pair(e, p, q);
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int k = 0; k < 6; k++) { alpha += U[k][p] * U[k][p]; beta += U[k][q] * U[k][q]; gamma += U[k][p] * U[k][q]; }
+      double c, s;
+      if (!ndt_svd6_angle(alpha, beta, gamma, c, s)) continue;
+      rotated = 1;
+      for (int k = 0; k < 6; k++) {
+        double up = U[k][p], uq = U[k][q];
+        U[k][p] = c * up - s * uq; U[k][q] = s * up + c * uq;
+        double vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
+  }
+  ndt_svd6_finish(U, V, b, x);
+}
 // ------------------------------------------------------------------ More-Thuente helpers (ndt_omp_impl.hpp:758-885)
 LB_HD bool ndt_update_interval(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t,
                                double g_t) {
@@ -603,11 +623,16 @@ LB_HD void ndt_ctl_begin(NdtCtl& c, const float* guess16 /*row-major 4x4*/, doub
 }
 
 // Consumes the sums of the evaluation that was requested (sums[43]) and moves on to the next request, or finishes
-// (want = NDT_WANT_NONE, phase = 9).
-LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
+// (want = NDT_WANT_NONE, phase = 9).  The Newton direction is computed OUTSIDE: the function returns true when it needs
+// delta_p = pinv(H) (-g) for the c.H / c.g it holds, and is called again with it (sums are ignored then) -- on the host
+// the serial solve above answers, on the device the controller thread hands the solve to its whole warp (ndt.cu).
+// Returns false once a request is posted or the align has finished.
+LB_HD bool ndt_ctl_run(NdtCtl& c, const double* sums, const double* delta_p) {
   const double mu = 1.e-4, nu = 0.9;
   enum { NEWTON, LS_CHECK, LS_END, POST_LS } at;
-  if (c.phase == 3) {
+  if (delta_p) {
+    at = NEWTON;
+  } else if (c.phase == 3) {
     for (int i = 0; i < 36; i++) c.H[i] = sums[7 + i];
     at = POST_LS;
   } else {
@@ -636,12 +661,12 @@ LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
   }
   for (;;) {
     if (at == NEWTON) {
-      double ng[6], delta_p[6];
-      for (int i = 0; i < 6; i++) ng[i] = -c.g[i];
-      ndt_svd6_solve(c.H, ng, delta_p);
-      double nrm = sqrt(ndt_dot6(delta_p, delta_p));
-      if (nrm == 0 || nrm != nrm) { c.converged = nrm == nrm; c.want = NDT_WANT_NONE; c.phase = 9; return; }
-      for (int i = 0; i < 6; i++) c.dir[i] = delta_p[i] / nrm;
+      if (!delta_p) return true;
+      const double* dp = delta_p;
+      delta_p = nullptr;                 // consumed: a second Newton step within this call asks again
+      double nrm = sqrt(ndt_dot6(dp, dp));
+      if (nrm == 0 || nrm != nrm) { c.converged = nrm == nrm; c.want = NDT_WANT_NONE; c.phase = 9; return false; }
+      for (int i = 0; i < 6; i++) c.dir[i] = dp[i] / nrm;
       // computeStepLengthMT(p, dir, nrm, step_size, tf_eps / 2, ...)
       c.step_max = c.step_size; c.step_min = c.tf_eps / 2;
       c.phi_0 = -c.score;
@@ -662,7 +687,7 @@ LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
       c.a_t = c.a_t > c.step_min ? c.a_t : c.step_min;
       ndt_post_eval(c, NDT_WANT_DERIV_H);
       c.phase = 1;
-      return;
+      return false;
     }
     if (at == LS_CHECK) {
       if (!c.interval_converged && c.step_iterations < 10 && !(c.psi_t <= 0 && c.d_phi_t <= -nu * c.d_phi_0)) {
@@ -672,12 +697,12 @@ LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
         c.a_t = c.a_t > c.step_min ? c.a_t : c.step_min;
         ndt_post_eval(c, NDT_WANT_DERIV);
         c.phase = 2;
-        return;
+        return false;
       }
       at = LS_END;
     }
     if (at == LS_END) {
-      if (c.step_iterations) { c.want = NDT_WANT_HESSIAN; c.phase = 3; return; }   // same transform and angles as the last trial
+      if (c.step_iterations) { c.want = NDT_WANT_HESSIAN; c.phase = 3; return false; }   // same transform and angles as the last trial
       at = POST_LS;
     }
     if (at == POST_LS) {
@@ -685,9 +710,20 @@ LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
       for (int i = 0; i < 6; i++) c.p[i] = c.p[i] + c.dir[i] * delta_p_norm;
       if (c.nr_iterations > c.max_iterations || (c.nr_iterations && (fabs(delta_p_norm) < c.tf_eps))) c.converged = 1;
       c.nr_iterations++;
-      if (c.converged) { c.want = NDT_WANT_NONE; c.phase = 9; return; }
+      if (c.converged) { c.want = NDT_WANT_NONE; c.phase = 9; return false; }
       at = NEWTON;
     }
+  }
+}
+
+LB_HD void ndt_ctl_advance(NdtCtl& c, const double* sums) {
+  double dp[6];
+  const double* have = nullptr;
+  while (ndt_ctl_run(c, sums, have)) {
+    double ng[6];
+    for (int i = 0; i < 6; i++) ng[i] = -c.g[i];
+    ndt_svd6_solve(c.H, ng, dp);
+    have = dp;
   }
 }
 

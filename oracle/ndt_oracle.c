@@ -21,7 +21,7 @@
  * PARITY UNPINNED.  The reference holds no test for NDT at all
  * (test_point_cloud_odometry.cpp:19 "TODO: add tests for ndt") and PCL / Eigen /
  * FLANN are absent here, so nothing can pin this file beyond its own sanity
- * checks (tests/test_ndt_oracle.py: recovers a known offset, derivatives agree
+ * checks (tests/test_ndt_cpu.py: recovers a known offset, derivatives agree
  * with finite differences).  Choices that live in those libraries and are made
  * here: Eigen's fixed-size float products are summed left to right; `exp` of
  * the float argument is expf; SelfAdjointEigenSolver<Matrix3d> is a cyclic
@@ -107,25 +107,29 @@ static void svd6_solve(const double A[36], const double b[6], double x[6]) {
   double U[6][6], V[6][6];
   for (int i = 0; i < 6; i++)
     for (int j = 0; j < 6; j++) { U[i][j] = A[6 * i + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  /* column pairs in round-robin order (five rounds of three disjoint pairs per sweep): any cyclic order converges to the
+   * same decomposition; this one lets an implementation rotate the three pairs of a round side by side */
+  static const int PP[15] = {0, 1, 2, 0, 3, 1, 0, 2, 1, 0, 1, 4, 0, 2, 3};
+  static const int QQ[15] = {5, 4, 3, 4, 5, 2, 3, 4, 5, 2, 3, 5, 1, 5, 4};
   for (int sweep = 0; sweep < 60; sweep++) {
     int rotated = 0;
-    for (int p = 0; p < 5; p++)
-      for (int q = p + 1; q < 6; q++) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int k = 0; k < 6; k++) { alpha += U[k][p] * U[k][p]; beta += U[k][q] * U[k][q]; gamma += U[k][p] * U[k][q]; }
-        if (gamma == 0.0 || fabs(gamma) <= DBL_EPSILON * sqrt(alpha * beta)) continue;
-        rotated = 1;
-        double zeta = (beta - alpha) / (2.0 * gamma);
-        double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        if (zeta < 0.0) t = -t;
-        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int k = 0; k < 6; k++) {
-          double up = U[k][p], uq = U[k][q];
-          U[k][p] = c * up - s * uq; U[k][q] = s * up + c * uq;
-          double vp = V[k][p], vq = V[k][q];
-          V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
-        }
+    for (int e = 0; e < 15; e++) {
+      const int p = PP[e], q = QQ[e];
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int k = 0; k < 6; k++) { alpha += U[k][p] * U[k][p]; beta += U[k][q] * U[k][q]; gamma += U[k][p] * U[k][q]; }
+      if (gamma == 0.0 || fabs(gamma) <= DBL_EPSILON * sqrt(alpha * beta)) continue;
+      rotated = 1;
+      double zeta = (beta - alpha) / (2.0 * gamma);
+      double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      if (zeta < 0.0) t = -t;
+      double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+      for (int k = 0; k < 6; k++) {
+        double up = U[k][p], uq = U[k][q];
+        U[k][p] = c * up - s * uq; U[k][q] = s * up + c * uq;
+        double vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
       }
+    }
     if (!rotated) break;
   }
   double sig[6]; int ord[6];
