@@ -183,17 +183,163 @@ ndt_eval_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss G, co
   }
 }
 
-static void ndt_launch_eval(int want, int blocks, cudaStream_t st, const NdtCtl* ctl, const NdtTargetView& tv, const NdtGauss& G,
-                            const f4* src, uint32_t n, double* partials) {
-  if (want == NDT_WANT_DERIV_H) ndt_eval_kernel<NDT_WANT_DERIV_H><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
-  else if (want == NDT_WANT_DERIV) ndt_eval_kernel<NDT_WANT_DERIV><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
-  else ndt_eval_kernel<NDT_WANT_HESSIAN><<<blocks, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+// The same evaluation with EIGHT lanes per source point (float passes only).  A 30 k-point scan is 918 warps of the
+// kernel above -- six per SM, each a 3-4 k-instruction chain of dependent hash probes and double-precision exps, so the
+// GPU idles on latency.  Here the eight lanes of a point probe its candidate cells side by side (hits appended to a
+// shared-memory list, then ranked by (distance, slot) = the reference's visiting order), compute one (point, voxel) pair
+// each, and add the pairs' float terms IN THAT ORDER into per-point double subtotals (lane s owns sums s, s + 8, ...):
+// the same per-pair arithmetic (ndt.h) and the same per-point association as the kernel above, eight times the warps.
+constexpr int NDT_GRP = 8;                                   // lanes per source point
+constexpr int NDT_GPTS = NDT_EVAL_THREADS / NDT_GRP;         // points per batch of a CTA
+constexpr int NDT_GBATCH = 2;                                // batches per CTA (one partial row per CTA)
+
+template <int WANT>
+__global__ void __launch_bounds__(NDT_EVAL_THREADS)
+ndt_eval_group_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss G, const f4* __restrict__ src, uint32_t n,
+                      double* __restrict__ partials) {
+  constexpr bool HESS = WANT == NDT_WANT_DERIV_H;
+  constexpr int NT = HESS ? NDT_NSUM : 7;                    // sums of this request
+  constexpr int NC = (NT + NDT_GRP - 1) / NDT_GRP;           // of which one lane owns at most this many
+  __shared__ NdtAngles sA;
+  __shared__ float sT[12];
+  __shared__ float sterm[NDT_GPTS][NDT_GRP][NT];
+  __shared__ int shit_slot[NDT_GPTS][NDT_MAX_NB];
+  __shared__ float shit_key[NDT_GPTS][NDT_MAX_NB];
+  __shared__ int ssorted[NDT_GPTS][NDT_MAX_NB];
+  __shared__ int shit_n[NDT_GPTS];
+  __shared__ double sacc[NDT_GPTS][NT];
+  if (ctl->want != WANT) return;
+  {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(&ctl->ang);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(&sA);
+    for (uint32_t w = threadIdx.x; w < sizeof(NdtAngles) / 4; w += blockDim.x) sw[w] = g[w];
+    if (threadIdx.x < 12) sT[threadIdx.x] = ctl->T[threadIdx.x];
+  }
+  __syncthreads();
+  const int pt = threadIdx.x / NDT_GRP, sub = threadIdx.x % NDT_GRP;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);        // the eight lanes of this point
+  double total[NC];
+#pragma unroll
+  for (int ci = 0; ci < NC; ci++) total[ci] = 0.0;
+  for (int b = 0; b < NDT_GBATCH; b++) {
+    const uint32_t i = (blockIdx.x * NDT_GBATCH + b) * NDT_GPTS + pt;
+    const bool valid = i < n;
+    if (sub == 0) shit_n[pt] = 0;
+    __syncwarp(gmask);
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    if (valid) {
+      const f4 p = src[i];
+      x0 = p.x; x1 = p.y; x2 = p.z;
+      xform_pcl(sT, x0, x1, x2, q0, q1, q2);
+      // 1. candidate voxels, eight at a time
+      if (tv.method == NDT_KDTREE) {
+        const float q[3] = {q0, q1, q2};
+        int lo[3], hi[3];
+        ndt_kd_range(tv, q, lo, hi);
+        const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+        if (nx > 0 && ny > 0 && nz > 0) {
+          const int ncell = nx * ny * nz;
+          for (int c = sub; c < ncell; c += NDT_GRP) {
+            const int cx = lo[0] + c % nx, cy = lo[1] + (c / nx) % ny, cz = lo[2] + c / (nx * ny);
+            int sl;
+            float d2;
+            if (ndt_kd_probe(tv, cx, cy, cz, q0, q1, q2, sl, d2)) {
+              const int pos = atomicAdd(&shit_n[pt], 1);
+              if (pos < NDT_MAX_NB) { shit_slot[pt][pos] = sl; shit_key[pt][pos] = d2; }
+            }
+          }
+        }
+      } else {
+        const int nrel = tv.method == NDT_DIRECT1 ? 1 : 7;
+        if (sub < nrel) {
+          const int sl = ndt_direct_probe(tv, sub, q0, q1, q2);
+          if (sl >= 0) {
+            const int pos = atomicAdd(&shit_n[pt], 1);
+            shit_slot[pt][pos] = sl; shit_key[pt][pos] = (float)sub;      // visited in the order of the relative cells
+          }
+        }
+      }
+    }
+    __syncwarp(gmask);
+    const int k = min(shit_n[pt], NDT_MAX_NB);
+    // 2. the reference's visiting order: ascending (distance, slot)
+    for (int h = sub; h < k; h += NDT_GRP) {
+      const float kh = shit_key[pt][h];
+      const int sh = shit_slot[pt][h];
+      int rank = 0;
+      for (int o = 0; o < k; o++) {
+        const float ko = shit_key[pt][o];
+        rank += (ko < kh || (ko == kh && shit_slot[pt][o] < sh)) ? 1 : 0;
+      }
+      ssorted[pt][rank] = sh;
+    }
+    __syncwarp(gmask);
+    // 3. one pair per lane, its terms through shared memory, the owners add them in order
+    double acc[NC];
+#pragma unroll
+    for (int ci = 0; ci < NC; ci++) acc[ci] = 0.0;
+    if (k > 0) {
+      float pg[3][6], ph[6][3];
+      ndt_point_derivs_f(sA, x0, x1, x2, HESS, pg, ph);
+      for (int base = 0; base < k; base += NDT_GRP) {
+        const int j = base + sub;
+        if (j < k) {
+          float t[NT];
+          const bool ok = ndt_pair_terms_f<HESS>(G, pg, ph, q0, q1, q2, tv.vox[ssorted[pt][j]], t);
+#pragma unroll
+          for (int e = 0; e < NT; e++) sterm[pt][sub][e] = ok ? t[e] : 0.0f;      // a dropped pair adds nothing
+        }
+        __syncwarp(gmask);
+        const int m = min(NDT_GRP, k - base);
+        for (int jj = 0; jj < m; jj++) {
+#pragma unroll
+          for (int ci = 0; ci < NC; ci++) {
+            const int c = sub + NDT_GRP * ci;
+            if (c < NT) acc[ci] += (double)sterm[pt][jj][c];
+          }
+        }
+        __syncwarp(gmask);
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < NC; ci++) total[ci] += acc[ci];
+  }
+  // 4. one partial row per CTA: the points' subtotals in point order
+#pragma unroll
+  for (int ci = 0; ci < NC; ci++) {
+    const int c = sub + NDT_GRP * ci;
+    if (c < NT) sacc[pt][c] = total[ci];
+  }
+  __syncthreads();
+  if (threadIdx.x < NDT_NSUM) {
+    const int c = threadIdx.x;
+    double v = 0.0;
+    if (c < NT) {
+#pragma unroll
+      for (int p = 0; p < NDT_GPTS; p++) v += sacc[p][c];
+    }
+    partials[(size_t)blockIdx.x * NDT_NSUM + c] = v;
+  }
 }
 
-// Adds the CTA partials (fixed shape: eight consecutive ranges of CTAs summed in CTA order, then the eight range sums in
-// order -- run-to-run identical bits) and advances the controller.
-constexpr int NDT_CTL_PARTS = 8;
-constexpr int NDT_CTL_THREADS = 352;                       // >= NDT_NSUM * NDT_CTL_PARTS
+struct NdtRows { int thread, group; bool use_group; };        // partial rows (= CTAs) of the two kernel shapes
+static inline int ndt_rows_of(const NdtRows& r, int want) { return (r.use_group && want != NDT_WANT_HESSIAN) ? r.group : r.thread; }
+
+static void ndt_launch_eval(int want, const NdtRows& rows, cudaStream_t st, const NdtCtl* ctl, const NdtTargetView& tv, const NdtGauss& G,
+                            const f4* src, uint32_t n, double* partials) {
+  if (rows.use_group && want == NDT_WANT_DERIV_H)
+    ndt_eval_group_kernel<NDT_WANT_DERIV_H><<<rows.group, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else if (rows.use_group && want == NDT_WANT_DERIV)
+    ndt_eval_group_kernel<NDT_WANT_DERIV><<<rows.group, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else if (want == NDT_WANT_DERIV_H) ndt_eval_kernel<NDT_WANT_DERIV_H><<<rows.thread, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else if (want == NDT_WANT_DERIV) ndt_eval_kernel<NDT_WANT_DERIV><<<rows.thread, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+  else ndt_eval_kernel<NDT_WANT_HESSIAN><<<rows.thread, NDT_EVAL_THREADS, 0, st>>>(ctl, tv, G, src, n, partials);
+}
+
+// Adds the CTA partials (fixed shape: sixteen consecutive ranges of CTAs summed in CTA order, then the sixteen range sums
+// in order -- run-to-run identical bits) and advances the controller.
+constexpr int NDT_CTL_PARTS = 16;
+constexpr int NDT_CTL_THREADS = 704;                       // >= NDT_NSUM * NDT_CTL_PARTS
 __device__ __forceinline__ void ndt_sum_partials(const double* __restrict__ partials, int blocks, double (*part)[NDT_NSUM], double* sums) {
   const int t = threadIdx.x;
   if (t < NDT_NSUM * NDT_CTL_PARTS) {
@@ -260,12 +406,13 @@ __device__ __forceinline__ void ndt_svd6_solve_warp(const double* A, const doubl
 }
 
 __global__ void __launch_bounds__(NDT_CTL_THREADS)
-ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, int blocks) {
+ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, int rows_float, int rows_hessian) {
   __shared__ double part[NDT_CTL_PARTS][NDT_NSUM];
   __shared__ double sums[NDT_NSUM];
   __shared__ double sU[6][6], sV[6][6], sx[6];
-  if (ctl->want == NDT_WANT_NONE) return;
-  ndt_sum_partials(partials, blocks, part, sums);
+  const int want = ctl->want;
+  if (want == NDT_WANT_NONE) return;
+  ndt_sum_partials(partials, want == NDT_WANT_HESSIAN ? rows_hessian : rows_float, part, sums);     // the rows the request's kernel wrote
   if (threadIdx.x < 32) {
     // lane 0 runs the scalar controller; whenever it needs a Newton direction the whole warp computes it
     int need = 0;
@@ -563,10 +710,14 @@ int lb_ndt_target_voxels(lb_ndt* h, size_t capacity, size_t* n_voxels, int32_t* 
   return LB_OK;
 }
 
-static int ndt_source_ready(lb_ndt* h, const char* who, int* blocks) {
+static int ndt_source_ready(lb_ndt* h, const char* who, NdtRows* rows) {
   if (h->n_src == 0) { set_error("%s: no source set", who); return LB_ERR_EMPTY_SOURCE; }
-  *blocks = cdiv(h->n_src, NDT_EVAL_THREADS);
-  LB_TRY(h->partials.ensure((size_t)*blocks * NDT_NSUM));
+  // LB_NDT_EVAL=thread: every pass with one thread per source point (A/B baseline); default: eight lanes per point for the float passes
+  static const bool use_group = !(getenv("LB_NDT_EVAL") && !strcmp(getenv("LB_NDT_EVAL"), "thread"));
+  rows->thread = cdiv(h->n_src, NDT_EVAL_THREADS);
+  rows->group = cdiv(h->n_src, NDT_GPTS * NDT_GBATCH);
+  rows->use_group = use_group;
+  LB_TRY(h->partials.ensure((size_t)std::max(rows->thread, rows->group) * NDT_NSUM));
   return LB_OK;
 }
 
@@ -574,16 +725,16 @@ int lb_ndt_derivatives(lb_ndt* h, const float* T16, const double* pose6, int com
                        double* hessian36) {
   LB_TRY(ndt_ready(h, "lb_ndt_derivatives"));
   if (!T16 || !pose6 || compute_hessian < 0 || compute_hessian > 2) { set_error("lb_ndt_derivatives: bad argument"); return LB_ERR_INVALID_ARG; }
-  int blocks = 0;
-  LB_TRY(ndt_source_ready(h, "lb_ndt_derivatives", &blocks));
+  NdtRows rows;
+  LB_TRY(ndt_source_ready(h, "lb_ndt_derivatives", &rows));
   NdtCtl& c = *h->h_ctl;
   memset(&c, 0, sizeof(c));
   for (int i = 0; i < 12; i++) c.T[i] = T16[i];
   ndt_angles(pose6, c.ang);
   c.want = compute_hessian == 2 ? NDT_WANT_HESSIAN : (compute_hessian ? NDT_WANT_DERIV_H : NDT_WANT_DERIV);
   LB_CUDA(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(NdtCtl), cudaMemcpyHostToDevice, h->c.stream));
-  ndt_launch_eval(c.want, blocks, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
-  ndt_sum_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->partials.p, blocks, h->d_sums);
+  ndt_launch_eval(c.want, rows, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+  ndt_sum_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->partials.p, ndt_rows_of(rows, c.want), h->d_sums);
   h->c.launches += 2;
   LB_CUDA(cudaMemcpyAsync(h->h_sums, h->d_sums, NDT_NSUM * sizeof(double), cudaMemcpyDeviceToHost, h->c.stream));
   LB_CUDA(cudaStreamSynchronize(h->c.stream));
@@ -596,8 +747,8 @@ int lb_ndt_derivatives(lb_ndt* h, const float* T16, const double* pose6, int com
 int lb_ndt_align(lb_ndt* h, const float* guess16, lb_ndt_result* result) {
   LB_TRY(ndt_ready(h, "lb_ndt_align"));
   if (!result) { set_error("lb_ndt_align: null result"); return LB_ERR_INVALID_ARG; }
-  int blocks = 0;
-  LB_TRY(ndt_source_ready(h, "lb_ndt_align", &blocks));
+  NdtRows rows;
+  LB_TRY(ndt_source_ready(h, "lb_ndt_align", &rows));
   const auto t0 = std::chrono::steady_clock::now();
   static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   const float* g = guess16 ? guess16 : I16;
@@ -611,8 +762,8 @@ int lb_ndt_align(lb_ndt* h, const float* guess16, lb_ndt_result* result) {
   for (;;) {
     for (int b = 0; b < NDT_BATCH; b++) {
       for (int want = NDT_WANT_DERIV_H; want <= NDT_WANT_HESSIAN; want++)
-        ndt_launch_eval(want, blocks, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
-      ndt_ctl_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->partials.p, blocks);
+        ndt_launch_eval(want, rows, h->c.stream, h->d_ctl, h->tv, h->G, h->src.p, h->n_src, h->partials.p);
+      ndt_ctl_kernel<<<1, NDT_CTL_THREADS, 0, h->c.stream>>>(h->d_ctl, h->partials.p, ndt_rows_of(rows, NDT_WANT_DERIV), ndt_rows_of(rows, NDT_WANT_HESSIAN));
     }
     h->c.launches += 4 * NDT_BATCH;
     pairs += NDT_BATCH;

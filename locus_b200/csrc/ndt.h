@@ -191,6 +191,46 @@ LB_HD int ndt_hash_find(const NdtTargetView& tv, uint32_t key) {
   }
 }
 
+// KDTREE method, step 1: the lattice range that can hold a voxel whose float centroid lies within one voxel side of q
+// (margin: float rounding of the centroid and of this arithmetic).  lo / hi are relative to min_b, clamped to the grid.
+LB_HD void ndt_kd_range(const NdtTargetView& tv, const float* q, int* lo, int* hi) {
+  const float r = tv.leaf;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    float m = 1e-3f * r + 1e-5f * fabsf(q[a]);
+    lo[a] = (int)floorf((q[a] - r - m) * tv.inv_leaf) - tv.min_b[a];
+    hi[a] = (int)floorf((q[a] + r + m) * tv.inv_leaf) - tv.min_b[a];
+    if (lo[a] < 0) lo[a] = 0;
+    if (hi[a] > tv.div_b[a] - 1) hi[a] = tv.div_b[a] - 1;
+  }
+}
+// step 2: one lattice cell -> its searchable voxel's slot and float d2 when the centroid is within the radius (strict)
+LB_HD bool ndt_kd_probe(const NdtTargetView& tv, int cx, int cy, int cz, float qx, float qy, float qz, int& s, float& d2) {
+  const uint32_t key = (uint32_t)(cx + cy * tv.div_b[0] + cz * tv.div_b[0] * tv.div_b[1]);
+  s = ndt_hash_find(tv, key);
+  if (s < 0) return false;
+  const f4 c = tv.cen[s];
+  const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+  d2 = (dx * dx + dy * dy) + dz * dz;
+  return d2 < tv.r2;
+}
+// DIRECT7 / DIRECT1: the r-th relative cell (own cell, +x, -x, +y, -y, +z, -z) -> slot of a usable voxel, or -1
+LB_HD int ndt_direct_probe(const NdtTargetView& tv, int r, float qx, float qy, float qz) {
+  const int REL[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+  const int ijk[3] = {(int)floorf(qx / tv.leaf), (int)floorf(qy / tv.leaf), (int)floorf(qz / tv.leaf)};
+  int idx = 0, mul = 1;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const int c = ijk[a] + REL[r][a];
+    if (c < tv.min_b[a] || c > tv.max_b[a]) return -1;
+    idx += (c - tv.min_b[a]) * mul;
+    mul *= tv.div_b[a];
+  }
+  const int s = ndt_hash_find(tv, (uint32_t)idx);
+  if (s < 0) return -1;
+  return float_to_bits(tv.cen[s].w) >= tv.min_pts ? s : -1;      // an invalidated voxel carries nr_points = -1
+}
+
 // Neighbourhood of the transformed point q, in the order the reference visits it.  Returns the count; slot[] = index
 // into vox / cen.  KDTREE: every voxel whose float centroid lies within d2 < r2, ascending (d2, slot).
 LB_HD int ndt_neighbours(const NdtTargetView& tv, float qx, float qy, float qz, int* slot) {
@@ -199,49 +239,23 @@ LB_HD int ndt_neighbours(const NdtTargetView& tv, float qx, float qy, float qz, 
     float d2s[NDT_MAX_NB];
     const float q[3] = {qx, qy, qz};
     int lo[3], hi[3];
-    const float r = tv.leaf;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      // a centroid within r of q sits in a voxel of this range (margin: float rounding of the centroid and of this arithmetic)
-      float m = 1e-3f * r + 1e-5f * fabsf(q[a]);
-      lo[a] = (int)floorf((q[a] - r - m) * tv.inv_leaf) - tv.min_b[a];
-      hi[a] = (int)floorf((q[a] + r + m) * tv.inv_leaf) - tv.min_b[a];
-      if (lo[a] < 0) lo[a] = 0;
-      if (hi[a] > tv.div_b[a] - 1) hi[a] = tv.div_b[a] - 1;
-    }
+    ndt_kd_range(tv, q, lo, hi);
     for (int cz = lo[2]; cz <= hi[2]; cz++)
       for (int cy = lo[1]; cy <= hi[1]; cy++)
         for (int cx = lo[0]; cx <= hi[0]; cx++) {
-          uint32_t key = (uint32_t)(cx + cy * tv.div_b[0] + cz * tv.div_b[0] * tv.div_b[1]);
-          int s = ndt_hash_find(tv, key);
-          if (s < 0) continue;
-          const f4 c = tv.cen[s];
-          float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-          float d2 = (dx * dx + dy * dy) + dz * dz;
-          if (!(d2 < tv.r2) || k >= NDT_MAX_NB) continue;
+          int s;
+          float d2;
+          if (!ndt_kd_probe(tv, cx, cy, cz, qx, qy, qz, s, d2) || k >= NDT_MAX_NB) continue;
           int j = k++;                                      // insertion by (d2, slot)
           while (j > 0 && (d2s[j - 1] > d2 || (d2s[j - 1] == d2 && slot[j - 1] > s))) { d2s[j] = d2s[j - 1]; slot[j] = slot[j - 1]; j--; }
           d2s[j] = d2; slot[j] = s;
         }
     return k;
   }
-  const int REL[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
   const int nrel = tv.method == NDT_DIRECT1 ? 1 : 7;
-  const int ijk[3] = {(int)floorf(qx / tv.leaf), (int)floorf(qy / tv.leaf), (int)floorf(qz / tv.leaf)};
   for (int r = 0; r < nrel; r++) {
-    bool ok = true;
-    int idx = 0, mul = 1;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      int c = ijk[a] + REL[r][a];
-      if (c < tv.min_b[a] || c > tv.max_b[a]) ok = false;
-      idx += (c - tv.min_b[a]) * mul;
-      mul *= tv.div_b[a];
-    }
-    if (!ok) continue;
-    int s = ndt_hash_find(tv, (uint32_t)idx);
-    if (s < 0) continue;
-    if (float_to_bits(tv.cen[s].w) >= tv.min_pts) slot[k++] = s;      // an invalidated voxel carries nr_points = -1
+    const int s = ndt_direct_probe(tv, r, qx, qy, qz);
+    if (s >= 0) slot[k++] = s;
   }
   return k;
 }
@@ -291,6 +305,75 @@ LB_HD int ndt_hblk(int i, int j) {
 // a double exp rounded to float gives the same bits on the host and on the device.
 LB_HD float ndt_expf(float x) { return (float)exp((double)x); }
 
+// computePointDerivatives, float (ndt_omp_impl.hpp:478-526): the 3x6 point gradient and (hess) the six second-derivative
+// vectors a..f of one source point
+LB_HD void ndt_point_derivs_f(const NdtAngles& A, float x0, float x1, float x2, bool hess, float (*pg)[6], float (*ph)[3]) {
+  float xj[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) xj[r] = (A.jf[r][0] * x0 + A.jf[r][1] * x1) + A.jf[r][2] * x2;
+  pg[0][0] = 1.f; pg[0][1] = 0.f; pg[0][2] = 0.f; pg[0][3] = 0.f; pg[0][4] = xj[2]; pg[0][5] = xj[5];
+  pg[1][0] = 0.f; pg[1][1] = 1.f; pg[1][2] = 0.f; pg[1][3] = xj[0]; pg[1][4] = xj[3]; pg[1][5] = xj[6];
+  pg[2][0] = 0.f; pg[2][1] = 0.f; pg[2][2] = 1.f; pg[2][3] = xj[1]; pg[2][4] = xj[4]; pg[2][5] = xj[7];
+  if (hess) {
+    float xh[15];
+#pragma unroll
+    for (int r = 0; r < 15; r++) xh[r] = (A.hf[r][0] * x0 + A.hf[r][1] * x1) + A.hf[r][2] * x2;
+    ph[0][0] = 0.f; ph[0][1] = xh[0]; ph[0][2] = xh[1];
+    ph[1][0] = 0.f; ph[1][1] = xh[2]; ph[1][2] = xh[3];
+    ph[2][0] = 0.f; ph[2][1] = xh[4]; ph[2][2] = xh[5];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ph[3][c] = xh[6 + c]; ph[4][c] = xh[9 + c]; ph[5][c] = xh[12 + c]; }
+  }
+}
+
+// updateDerivatives (ndt_omp_impl.hpp:574-638) for one (transformed point q, voxel) pair, float arithmetic:
+// t[0] = score increment, t[1..6] = gradient terms, t[7..42] = Hessian terms (HESS only).  Returns false when the
+// reference's validity check drops the pair (nothing is added then).
+template <bool HESS>
+LB_HD bool ndt_pair_terms_f(const NdtGauss& G, const float (*pg)[6], const float (*ph)[3], float q0, float q1, float q2, const NdtVoxel& vx,
+                            float* t) {
+  const float d2f = (float)G.d2;
+  const float xt[3] = {(float)((double)q0 - vx.mean[0]), (float)((double)q1 - vx.mean[1]), (float)((double)q2 - vx.mean[2])};
+  float cf[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) cf[r][cc] = (float)vx.icov[3 * r + cc];
+  float xc[3];
+#pragma unroll
+  for (int cc = 0; cc < 3; cc++) xc[cc] = (xt[0] * cf[0][cc] + xt[1] * cf[1][cc]) + xt[2] * cf[2][cc];
+  float e = ndt_expf(-d2f * ((xt[0] * xc[0] + xt[1] * xc[1]) + xt[2] * xc[2]) * 0.5f);
+  const float score_inc = (float)(-G.d1 * (double)e);
+  e = d2f * e;
+  if (e > 1 || e < 0 || e != e) return false;
+  e = (float)((double)e * G.d1);
+  float CP[3][6], gq[6];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int cc = 0; cc < 6; cc++) CP[r][cc] = (cf[r][0] * pg[0][cc] + cf[r][1] * pg[1][cc]) + cf[r][2] * pg[2][cc];
+#pragma unroll
+  for (int cc = 0; cc < 6; cc++) gq[cc] = (xt[0] * CP[0][cc] + xt[1] * CP[1][cc]) + xt[2] * CP[2][cc];
+  t[0] = score_inc;
+#pragma unroll
+  for (int cc = 0; cc < 6; cc++) t[1 + cc] = e * gq[cc];
+  if (HESS) {
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        float xH = 0.0f;
+        if (i >= 3 && j >= 3) {
+          const float* v = ph[ndt_hblk(i, j)];
+          xH = (xc[0] * v[0] + xc[1] * v[1]) + xc[2] * v[2];
+        }
+        float JCJ = (pg[0][j] * CP[0][i] + pg[1][j] * CP[1][i]) + pg[2][j] * CP[2][i];
+        t[7 + 6 * i + j] = e * ((-d2f * gq[i] * gq[j] + xH) + JCJ);
+      }
+  }
+  return true;
+}
+
 // One source point against its neighbourhood: adds to acc[43] = {score, gradient, Hessian (row-major)}.
 // want = NDT_WANT_DERIV_H / NDT_WANT_DERIV: computeDerivatives' float path (Hessian only for _H);
 // want = NDT_WANT_HESSIAN: computeHessian's double path (Hessian only).
@@ -302,62 +385,18 @@ LB_HD void ndt_point_eval(const NdtTargetView& tv, const NdtGauss& G, const NdtA
   const int k = ndt_neighbours(tv, q0, q1, q2, slot);
   if (k == 0) return;
   if (want != NDT_WANT_HESSIAN) {
-    // computePointDerivatives, float (ndt_omp_impl.hpp:478-526)
-    float xj[8], ph[6][3];
-#pragma unroll
-    for (int r = 0; r < 8; r++) xj[r] = (A.jf[r][0] * x0 + A.jf[r][1] * x1) + A.jf[r][2] * x2;
-    float pg[3][6] = {{1.f, 0.f, 0.f, 0.f, xj[2], xj[5]}, {0.f, 1.f, 0.f, xj[0], xj[3], xj[6]}, {0.f, 0.f, 1.f, xj[1], xj[4], xj[7]}};
-    if (want == NDT_WANT_DERIV_H) {
-      float xh[15];
-#pragma unroll
-      for (int r = 0; r < 15; r++) xh[r] = (A.hf[r][0] * x0 + A.hf[r][1] * x1) + A.hf[r][2] * x2;
-      ph[0][0] = 0.f; ph[0][1] = xh[0]; ph[0][2] = xh[1];
-      ph[1][0] = 0.f; ph[1][1] = xh[2]; ph[1][2] = xh[3];
-      ph[2][0] = 0.f; ph[2][1] = xh[4]; ph[2][2] = xh[5];
-#pragma unroll
-      for (int c = 0; c < 3; c++) { ph[3][c] = xh[6 + c]; ph[4][c] = xh[9 + c]; ph[5][c] = xh[12 + c]; }
-    }
-    const float d2f = (float)G.d2;
+    float pg[3][6], ph[6][3], t[NDT_NSUM];
+    ndt_point_derivs_f(A, x0, x1, x2, want == NDT_WANT_DERIV_H, pg, ph);
     for (int c = 0; c < k; c++) {
       const NdtVoxel& vx = tv.vox[slot[c]];
-      // updateDerivatives (ndt_omp_impl.hpp:574-638)
-      const float xt[3] = {(float)((double)q0 - vx.mean[0]), (float)((double)q1 - vx.mean[1]), (float)((double)q2 - vx.mean[2])};
-      float cf[3][3];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++) cf[r][cc] = (float)vx.icov[3 * r + cc];
-      float xc[3];
-#pragma unroll
-      for (int cc = 0; cc < 3; cc++) xc[cc] = (xt[0] * cf[0][cc] + xt[1] * cf[1][cc]) + xt[2] * cf[2][cc];
-      float e = ndt_expf(-d2f * ((xt[0] * xc[0] + xt[1] * xc[1]) + xt[2] * xc[2]) * 0.5f);
-      const float score_inc = (float)(-G.d1 * (double)e);
-      e = d2f * e;
-      if (e > 1 || e < 0 || e != e) continue;
-      e = (float)((double)e * G.d1);
-      float CP[3][6], gq[6];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = 0; cc < 6; cc++) CP[r][cc] = (cf[r][0] * pg[0][cc] + cf[r][1] * pg[1][cc]) + cf[r][2] * pg[2][cc];
-#pragma unroll
-      for (int cc = 0; cc < 6; cc++) gq[cc] = (xt[0] * CP[0][cc] + xt[1] * CP[1][cc]) + xt[2] * CP[2][cc];
-      acc[0] += (double)score_inc;
-#pragma unroll
-      for (int cc = 0; cc < 6; cc++) acc[1 + cc] += (double)(e * gq[cc]);
       if (want == NDT_WANT_DERIV_H) {
+        if (!ndt_pair_terms_f<true>(G, pg, ph, q0, q1, q2, vx, t)) continue;
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+        for (int e = 0; e < NDT_NSUM; e++) acc[e] += (double)t[e];
+      } else {
+        if (!ndt_pair_terms_f<false>(G, pg, ph, q0, q1, q2, vx, t)) continue;
 #pragma unroll
-          for (int j = 0; j < 6; j++) {
-            float xH = 0.0f;
-            if (i >= 3 && j >= 3) {
-              const float* v = ph[ndt_hblk(i, j)];
-              xH = (xc[0] * v[0] + xc[1] * v[1]) + xc[2] * v[2];
-            }
-            float JCJ = (pg[0][j] * CP[0][i] + pg[1][j] * CP[1][i]) + pg[2][j] * CP[2][i];
-            acc[7 + 6 * i + j] += (double)(e * ((-d2f * gq[i] * gq[j] + xH) + JCJ));
-          }
+        for (int e = 0; e < 7; e++) acc[e] += (double)t[e];
       }
     }
     return;

@@ -124,6 +124,57 @@ class B200Gicp {
   size_t n_src_ = 0;
 };
 
+// Mirror of pclomp::NormalDistributionsTransform<PointF, PointF> as LOCUS sets it up when `registration_method: ndt`
+// (PointCloudOdometry.cc:182-195, PointCloudLocalization.cc:267-280; setters of multithreaded_ndt/ndt_omp.h:116-196).
+// Same call sequence as B200Gicp: setInputSource / setInputTarget / align / getFinalTransformation.
+class B200Ndt {
+ public:
+  explicit B200Ndt(int device = 0) {
+    lb_ndt_default_params(&p_);
+    if (lb_ndt_create(device, &h_) != LB_OK) throw std::runtime_error(lb_last_error_string());
+  }
+  ~B200Ndt() { lb_ndt_destroy(h_); }
+  B200Ndt(const B200Ndt&) = delete;
+  B200Ndt& operator=(const B200Ndt&) = delete;
+
+  void setTransformationEpsilon(double e) { p_.transformation_epsilon = e; apply(); }
+  void setMaxCorrespondenceDistance(double d) { p_.max_correspondence_distance = d; apply(); }   // accepted; NDT has no gate
+  void setMaximumIterations(int n) { p_.max_iterations = n; apply(); }
+  void setRANSACIterations(int n) { p_.ransac_iterations = n; apply(); }
+  void setNumThreads(int n) { p_.num_threads = n; apply(); }                                      // accepted; the GPU path ignores it
+  void enableTimingOutput(bool e) { p_.enable_timing_output = e; apply(); }
+  void setResolution(float r) { p_.resolution = r; apply(); }          // re-initialises the current target's voxels (ndt_omp.h:124-131)
+  void setStepSize(double s) { p_.step_size = s; apply(); }
+  void setOulierRatio(double r) { p_.outlier_ratio = r; apply(); }     // the reference's spelling (ndt_omp.h:166)
+  void setNeighborhoodSearchMethod(int m) { p_.search_method = m; apply(); }   // 0 KDTREE, 2 DIRECT7, 3 DIRECT1
+  float getResolution() const { return p_.resolution; }
+  double getStepSize() const { return p_.step_size; }
+  double getOulierRatio() const { return p_.outlier_ratio; }
+  std::string getClassName() const { return "B200NormalDistributionsTransform"; }
+
+  bool setInputSource(const PointF* pts, size_t n) { return lb_ndt_set_source(h_, pts, n, sizeof(PointF), 0, LB_MEM_HOST) == LB_OK; }
+  bool setInputTarget(const PointF* pts, size_t n) { return lb_ndt_set_target(h_, pts, n, sizeof(PointF), 0, LB_MEM_HOST) == LB_OK; }
+  bool align(const Matrix4f* guess = nullptr) { return lb_ndt_align(h_, guess ? guess->data() : nullptr, &r_) == LB_OK; }
+  Matrix4f getFinalTransformation() const {
+    Matrix4f m;
+    for (int i = 0; i < 16; i++) m[i] = r_.final_transformation[i];
+    return m;
+  }
+  bool hasConverged() const { return r_.converged != 0; }
+  double getTransformationProbability() const { return r_.trans_probability; }
+  int getFinalNumIteration() const { return r_.nr_iterations; }
+  const lb_ndt_result& result() const { return r_; }
+  lb_ndt* handle() { return h_; }
+
+ private:
+  void apply() {
+    if (lb_ndt_set_params(h_, &p_) != LB_OK) throw std::invalid_argument(lb_last_error_string());
+  }
+  lb_ndt* h_ = nullptr;
+  lb_ndt_params p_{};
+  lb_ndt_result r_{};
+};
+
 // Mirror of the `impl_` object inside point_cloud_filter::CustomVoxelGrid
 // (custom_voxel_grid.h:25): the pcl::VoxelGrid<pcl::PCLPointCloud2> setters that
 // config_callback / ChangeLeafSizeRostopic drive, and filter().

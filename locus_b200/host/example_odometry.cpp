@@ -49,6 +49,19 @@ int main() {
   std::printf("normals: %d interior points of the wall x = 0.9 not facing the origin\n", bad);
   if (bad) return 4;
 
+  // `registration_method: ndt` (row f4): the same pair through the NDT mirror (0.5 m voxels on the 0.9 m cube)
+  B200Ndt ndt;
+  ndt.setTransformationEpsilon(1e-3);
+  ndt.setMaximumIterations(20);
+  ndt.setResolution(0.5f);
+  if (!ndt.setInputSource(query.data(), query.size()) || !ndt.setInputTarget(reference.data(), reference.size()) || !ndt.align()) {
+    std::printf("ndt failed: %s\n", lb_last_error_string());
+    return 8;
+  }
+  Matrix4f Tn = ndt.getFinalTransformation();
+  std::printf("ndt: converged=%d t=(%.4f %.4f %.4f) after %d Newton steps\n", (int)ndt.hasConverged(), Tn[3], Tn[7], Tn[11], ndt.getFinalNumIteration());
+  if (!(ndt.hasConverged() && std::fabs(Tn[3] + 0.05f) < 1e-2f && std::fabs(Tn[7] + 0.05f) < 1e-2f)) return 9;
+
   // the pipelined chain: the same two clouds as PointCloud2 blobs of PointF records
   B200Odometry odo(0, 2, reference.size(), sizeof(PointF));
   odo.setLeafSize(0.01f);                                     // finer than the 0.1 m lattice: every point survives
