@@ -45,6 +45,8 @@
  *   lb_voxel_set_leaf_size        impl_.setLeafSize()      custom_voxel_grid.cc:62-73, 97-101
  *   lb_voxel_set_filter_limits    impl_.setFilterFieldName/Limits/LimitsNegative  custom_voxel_grid.cc:103-134
  *   lb_voxel_filter               impl_.setInputCloud + setIndices + filter()     custom_voxel_grid.cc:76-87
+ *   lb_ndt_*                      pclomp::NormalDistributionsTransform behind `registration_method: ndt`
+ *                                 PointCloudOdometry.cc:182-195, PointCloudLocalization.cc:267-280 (section NDT below)
  *   lb_odometry_submit/next       the per-scan chain of the lidar callback: filtered scan -> odometry_.SetLidar()
  *                                 -> odometry_.UpdateEstimate()   locus/src/Locus.cc:451-453,
  *                                 PointCloudOdometry.cc:221-230 (SetLidar), 237-247 (UpdateEstimate: first scan
