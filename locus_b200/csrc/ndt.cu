@@ -207,6 +207,7 @@ ndt_eval_group_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss
   __shared__ float shit_key[NDT_GPTS][NDT_MAX_NB];
   __shared__ int ssorted[NDT_GPTS][NDT_MAX_NB];
   __shared__ int shit_n[NDT_GPTS];
+  __shared__ float sxj[NDT_GPTS][8], sxh[NDT_GPTS][16];
   __shared__ double sacc[NDT_GPTS][NT];
   if (ctl->want != WANT) return;
   {
@@ -238,9 +239,14 @@ ndt_eval_group_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss
         ndt_kd_range(tv, q, lo, hi);
         const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
         if (nx > 0 && ny > 0 && nz > 0) {
-          const int ncell = nx * ny * nz;
+          const int ncell = nx * ny * nz, nxy = nx * ny;
+          // at most 4 cells per axis: c / nxy and r / nx through float reciprocals (exact for these ranges: the + 0.5 keeps
+          // the quotient away from an integer boundary)
+          const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
           for (int c = sub; c < ncell; c += NDT_GRP) {
-            const int cx = lo[0] + c % nx, cy = lo[1] + (c / nx) % ny, cz = lo[2] + c / (nx * ny);
+            const int iz = (int)(((float)c + 0.5f) * inv_nxy), rem = c - iz * nxy;
+            const int iy = (int)(((float)rem + 0.5f) * inv_nx);
+            const int cx = lo[0] + (rem - iy * nx), cy = lo[1] + iy, cz = lo[2] + iz;
             int sl;
             float d2;
             if (ndt_kd_probe(tv, cx, cy, cz, q0, q1, q2, sl, d2)) {
@@ -279,8 +285,15 @@ ndt_eval_group_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss
 #pragma unroll
     for (int ci = 0; ci < NC; ci++) acc[ci] = 0.0;
     if (k > 0) {
+      // the point's derivative rows: lane s computes row s of the gradient table (and rows s, s + 8 of the Hessian table)
+      sxj[pt][sub] = ndt_row_dot(sA.jf, sub, x0, x1, x2);
+      if (HESS) {
+        sxh[pt][sub] = ndt_row_dot(sA.hf, sub, x0, x1, x2);
+        if (sub + 8 < 15) sxh[pt][sub + 8] = ndt_row_dot(sA.hf, sub + 8, x0, x1, x2);
+      }
+      __syncwarp(gmask);
       float pg[3][6], ph[6][3];
-      ndt_point_derivs_f(sA, x0, x1, x2, HESS, pg, ph);
+      ndt_point_derivs_place(sxj[pt], sxh[pt], HESS, pg, ph);
       for (int base = 0; base < k; base += NDT_GRP) {
         const int j = base + sub;
         if (j < k) {
@@ -410,20 +423,31 @@ ndt_ctl_kernel(NdtCtl* __restrict__ ctl, const double* __restrict__ partials, in
   __shared__ double part[NDT_CTL_PARTS][NDT_NSUM];
   __shared__ double sums[NDT_NSUM];
   __shared__ double sU[6][6], sV[6][6], sx[6];
+  __shared__ NdtCtl sc;                // the controller works on a shared-memory copy: its scalar code is a chain of dependent
+                                       // loads and stores of this state, 30 cycles each here, an L2 round trip each in global memory
   const int want = ctl->want;
   if (want == NDT_WANT_NONE) return;
-  ndt_sum_partials(partials, want == NDT_WANT_HESSIAN ? rows_hessian : rows_float, part, sums);     // the rows the request's kernel wrote
+  {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(ctl);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&sc);
+    for (uint32_t i = threadIdx.x; i < sizeof(NdtCtl) / 4; i += blockDim.x) w[i] = g[i];
+  }
+  ndt_sum_partials(partials, want == NDT_WANT_HESSIAN ? rows_hessian : rows_float, part, sums);     // the rows the request's kernel wrote; syncs the CTA
   if (threadIdx.x < 32) {
     // lane 0 runs the scalar controller; whenever it needs a Newton direction the whole warp computes it
     int need = 0;
-    if (threadIdx.x == 0) need = ndt_ctl_run(*ctl, sums, nullptr) ? 1 : 0;
+    if (threadIdx.x == 0) need = ndt_ctl_run(sc, sums, nullptr) ? 1 : 0;
     need = __shfl_sync(0xffffffffu, need, 0);
     while (need) {
-      __syncwarp();                                       // lane 0's writes of ctl->H / ctl->g are visible to the warp
-      ndt_svd6_solve_warp(ctl->H, ctl->g, sU, sV, sx);
-      if (threadIdx.x == 0) need = ndt_ctl_run(*ctl, sums, sx) ? 1 : 0;
+      __syncwarp();                                       // lane 0's writes of sc.H / sc.g are visible to the warp
+      ndt_svd6_solve_warp(sc.H, sc.g, sU, sV, sx);
+      if (threadIdx.x == 0) need = ndt_ctl_run(sc, sums, sx) ? 1 : 0;
       need = __shfl_sync(0xffffffffu, need, 0);
     }
+    __syncwarp();
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&sc);
+    uint32_t* g = reinterpret_cast<uint32_t*>(ctl);
+    for (uint32_t i = threadIdx.x; i < sizeof(NdtCtl) / 4; i += 32) g[i] = w[i];
   }
 }
 

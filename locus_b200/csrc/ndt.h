@@ -306,24 +306,29 @@ LB_HD int ndt_hblk(int i, int j) {
 LB_HD float ndt_expf(float x) { return (float)exp((double)x); }
 
 // computePointDerivatives, float (ndt_omp_impl.hpp:478-526): the 3x6 point gradient and (hess) the six second-derivative
-// vectors a..f of one source point
-LB_HD void ndt_point_derivs_f(const NdtAngles& A, float x0, float x1, float x2, bool hess, float (*pg)[6], float (*ph)[3]) {
-  float xj[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) xj[r] = (A.jf[r][0] * x0 + A.jf[r][1] * x1) + A.jf[r][2] * x2;
+// vectors a..f of one source point.  Row r of an angle table times the point, then the rows placed as the reference does.
+LB_HD float ndt_row_dot(const float (*M)[3], int r, float x0, float x1, float x2) { return (M[r][0] * x0 + M[r][1] * x1) + M[r][2] * x2; }
+LB_HD void ndt_point_derivs_place(const float* xj /*8*/, const float* xh /*15*/, bool hess, float (*pg)[6], float (*ph)[3]) {
   pg[0][0] = 1.f; pg[0][1] = 0.f; pg[0][2] = 0.f; pg[0][3] = 0.f; pg[0][4] = xj[2]; pg[0][5] = xj[5];
   pg[1][0] = 0.f; pg[1][1] = 1.f; pg[1][2] = 0.f; pg[1][3] = xj[0]; pg[1][4] = xj[3]; pg[1][5] = xj[6];
   pg[2][0] = 0.f; pg[2][1] = 0.f; pg[2][2] = 1.f; pg[2][3] = xj[1]; pg[2][4] = xj[4]; pg[2][5] = xj[7];
   if (hess) {
-    float xh[15];
-#pragma unroll
-    for (int r = 0; r < 15; r++) xh[r] = (A.hf[r][0] * x0 + A.hf[r][1] * x1) + A.hf[r][2] * x2;
     ph[0][0] = 0.f; ph[0][1] = xh[0]; ph[0][2] = xh[1];
     ph[1][0] = 0.f; ph[1][1] = xh[2]; ph[1][2] = xh[3];
     ph[2][0] = 0.f; ph[2][1] = xh[4]; ph[2][2] = xh[5];
 #pragma unroll
     for (int c = 0; c < 3; c++) { ph[3][c] = xh[6 + c]; ph[4][c] = xh[9 + c]; ph[5][c] = xh[12 + c]; }
   }
+}
+LB_HD void ndt_point_derivs_f(const NdtAngles& A, float x0, float x1, float x2, bool hess, float (*pg)[6], float (*ph)[3]) {
+  float xj[8], xh[15];
+#pragma unroll
+  for (int r = 0; r < 8; r++) xj[r] = ndt_row_dot(A.jf, r, x0, x1, x2);
+  if (hess) {
+#pragma unroll
+    for (int r = 0; r < 15; r++) xh[r] = ndt_row_dot(A.hf, r, x0, x1, x2);
+  }
+  ndt_point_derivs_place(xj, xh, hess, pg, ph);
 }
 
 // updateDerivatives (ndt_omp_impl.hpp:574-638) for one (transformed point q, voxel) pair, float arithmetic:
