@@ -7,6 +7,7 @@
 #include <limits>
 
 #include "b200_gicp_pcl.hpp"
+#include "b200_ndt_pcl.hpp"
 
 static PointCloudF::Ptr hollow_cube(float ox, float oy) {
   PointCloudF::Ptr c(new PointCloudF);
@@ -83,5 +84,36 @@ int main() {
   gicp->RecomputeSourceCovariance(false);
   icp->align(out);
   std::printf("from_normals_converged=%d\n", icp->hasConverged() ? 1 : 0);
+
+  // `registration_method: ndt` (SetupICP(), PointCloudOdometry.cc:182-195) through shim/b200_ndt_pcl.hpp
+  boost::shared_ptr<pcl::B200NormalDistributionsTransform> ndt = boost::make_shared<pcl::B200NormalDistributionsTransform>(0);
+  pcl::Registration<PointF, PointF>::Ptr icp2 = ndt;
+  ndt->setTransformationEpsilon(1e-3);
+  ndt->setMaxCorrespondenceDistance(1.0);
+  ndt->setMaximumIterations(20);
+  ndt->setRANSACIterations(0);
+  ndt->setNumThreads(4);
+  ndt->enableTimingOutput(false);
+  ndt->setResolution(0.5f);                                   // the cube is 0.9 m wide
+  icp2->setInputSource(moved);
+  icp2->setInputTarget(box);
+  PointCloudF out2;
+  icp2->align(out2);
+  Eigen::Matrix4f Tn = icp2->getFinalTransformation();
+  std::printf("ndt_converged=%d\n", icp2->hasConverged() ? 1 : 0);
+  std::printf("ndt_T=");
+  for (int i = 0; i < 16; i++) std::printf("%.9g%s", Tn.m[i], i == 15 ? "\n" : ",");
+  std::printf("ndt_iterations=%d\n", ndt->getFinalNumIteration());
+  double err2 = 0;
+  for (size_t i = 0; i < out2.size(); i++) {
+    const PointF& p = (*moved)[i];
+    float x = Tn(0, 0) * p.x + (Tn(0, 1) * p.y + (Tn(0, 2) * p.z + Tn(0, 3)));
+    err2 = std::fmax(err2, std::fabs(x - out2[i].x));
+  }
+  std::printf("ndt_output_err=%g\n", err2);
+  auto lazy2 = boost::static_pointer_cast<pcl::B200LazyKdTree<PointF>>(icp2->getSearchMethodTarget());
+  std::printf("ndt_tree_built_by_align=%d\n", lazy2->built() ? 1 : 0);
+  icp2->setInputSource(bad);                                  // a source with a NaN point is refused, the previous one kept
+  std::printf("ndt_source_kept=%d\n", icp2->getInputSource() == moved ? 1 : 0);
   return 0;
 }

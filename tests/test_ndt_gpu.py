@@ -172,3 +172,22 @@ def test_error_semantics():
     with pytest.raises(locus_b200.LocusB200Error):
         n.align(np.full((4, 4), np.nan, np.float32))
     assert n.launchCount() > 0
+
+
+def test_pcl_ndt_shim_runs(oracle):
+    """shim/b200_ndt_pcl.hpp -- the pcl::Registration subclass a `registration_method: ndt` case would instantiate --
+    compiled against the PCL mock and driven through the base-class pointer like LOCUS drives icp_ (tests/shim_harness.cpp),
+    on the reference's hollow-cube fixture with 0.5 m voxels: pose and Newton steps equal the oracle's"""
+    import subprocess
+    from test_cabi_cpu import _build_shim_harness
+    r = subprocess.run([_build_shim_harness()], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = dict(l.split("=", 1) for l in r.stdout.splitlines() if "=" in l)
+    assert kv["ndt_converged"] == "1"
+    T = np.array([float(x) for x in kv["ndt_T"].split(",")], dtype=np.float32).reshape(4, 4)
+    box = F.hollow_cube(); moved = box.copy(); moved[:, 0] += np.float32(0.05); moved[:, 1] += np.float32(0.05)
+    o = oracle.NdtTarget(box, oracle.ndt_params(resolution=0.5, transformation_epsilon=1e-3, max_iterations=20)).align(moved)
+    dt, dr = F.pose_delta(o["T"], T)
+    assert dt <= TOL_T and dr <= TOL_R and int(kv["ndt_iterations"]) == o["iterations"], (dt, dr, kv["ndt_iterations"], o["iterations"])
+    assert abs(T[0, 3] + 0.05) < 1e-2 and abs(T[1, 3] + 0.05) < 1e-2
+    assert float(kv["ndt_output_err"]) < 1e-6 and kv["ndt_tree_built_by_align"] == "0" and kv["ndt_source_kept"] == "1"
