@@ -101,6 +101,8 @@ def lib():
         L.og_kdtree_free.argtypes = [C.c_void_p]
         L.og_kdtree_knn.restype = C.c_int
         L.og_kdtree_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.og_kdtree_radius.restype = C.c_int
+        L.og_kdtree_radius.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         L.og_kdtree_nn_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.og_bfgs_minimize_quadratic.restype = C.c_int
         L.og_bfgs_minimize_quadratic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double]
@@ -277,6 +279,14 @@ class KdTree:
         idx = np.zeros(k, dtype=np.int32); d2 = np.zeros(k, dtype=np.float32)
         c = lib().og_kdtree_knn(self.h, _p(q), k, _p(idx), _p(d2))
         return idx[:c], d2[:c]
+
+    def radius(self, q, radius2, cap=64):
+        """every point with d2 < radius2 (strict), ascending (d2, index): (indices, d2)"""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        idx = np.zeros(cap, np.int32); d2 = np.zeros(cap, np.float32)
+        n = lib().og_kdtree_radius(self.h, _p(q), np.float32(radius2), _p(idx), _p(d2), cap)
+        n = min(n, cap)
+        return idx[:n].copy(), d2[:n].copy()
 
     def nn_batch(self, q, num_threads=1):
         q = _as_cloud(q)

@@ -102,6 +102,12 @@ void hn_target_leaves(void* hp, int* leaf_idx, int* nr, double* mean, double* ic
   }
 }
 
+// ndt_neighbours for a batch of (already transformed) query points: counts[i] and slots[i * 32 ..]
+void hn_neighbours(void* hp, const float* q, int n, int* counts, int* slots) {
+  HNdt* h = (HNdt*)hp;
+  for (int i = 0; i < n; i++) counts[i] = ndt_neighbours(h->tv, q[3 * i], q[3 * i + 1], q[3 * i + 2], slots + (size_t)i * NDT_MAX_NB);
+}
+
 static void eval_serial(HNdt* h, const float* src, int n, int stride_f, const float* T, const NdtAngles& A, int want, double* sums) {
   for (int k = 0; k < NDT_NSUM; k++) sums[k] = 0;
   for (int i = 0; i < n; i++) {

@@ -197,3 +197,32 @@ def test_product_headers_edge_cases(ndt_harness, oracle):
     r, o = h.align(s1), T.align(s1)
     dt, dr = F.pose_delta(o["T"], r["T"])
     assert r["iterations"] == o["iterations"] and r["evaluations"] == o["evaluations"] and dt < 1e-6 and dr < 1e-6
+
+
+@pytest.mark.parametrize("resolution", [1.0, 0.4, 2.5])
+def test_neighbourhood_search_exact_vs_kdtree(ndt_harness, oracle, resolution):
+    """The reference answers `radiusSearch(x, resolution)` from a kd-tree over the voxel centroids; ndt.h answers it from the
+    lattice cells around x (ndt_kd_range: conservative range, ndt_kd_probe: hash lookup + the same float d2 < r2 test).  Same
+    voxels in the same (d2, index) order for points inside, on the rim of and far outside the target -- incl. queries placed
+    exactly one voxel side away from a centroid and on voxel faces."""
+    s0, s1, _ = _scans()
+    h = _HT(ndt_harness, s0, resolution=resolution)
+    L = h.leaves()
+    cen = np.ascontiguousarray(L["centroid"])
+    kt = oracle.KdTree(cen)
+    rng = np.random.default_rng(4)
+    r = np.float32(resolution)
+    edge = cen[rng.integers(0, len(cen), 400)].copy(); edge[:, 0] += r                     # d = r up to rounding: the strict test decides
+    edge2 = cen[rng.integers(0, len(cen), 400)].copy(); edge2[:, 1] -= r * np.float32(0.99999994)
+    faces = (np.floor(s1[:400] / r) * r).astype(np.float32)                                 # on voxel faces / corners
+    far = (s1[:200] * np.float32(3.0) + np.float32(500.0)).astype(np.float32)               # outside the lattice
+    q = np.ascontiguousarray(np.concatenate([s1[:3000], s0[:1000] + rng.normal(0, 0.3, (1000, 3)).astype(np.float32), edge, edge2, faces, far]), dtype=np.float32)
+    counts = np.zeros(len(q), np.int32); slots = np.zeros((len(q), 32), np.int32)
+    ndt_harness.hn_neighbours(h.h, _p(q), len(q), _p(counts), _p(slots))
+    r2 = np.float32(np.float64(r) * np.float64(r))
+    n_multi = 0
+    for i in range(len(q)):
+        idx, _ = kt.radius(q[i], r2)
+        assert counts[i] == len(idx) and np.array_equal(slots[i, :counts[i]], idx), (i, q[i], counts[i], idx)
+        n_multi += len(idx) > 1
+    assert n_multi > 1000 and counts.max() <= 27
