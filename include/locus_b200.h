@@ -453,7 +453,7 @@ typedef struct lb_ndt_params {
   int max_iterations;               /* 35    (:94); LOCUS passes icp_iterations / iterations */
   int min_points_per_voxel;         /* 6     voxel_grid_covariance_omp.h:186 */
   double min_covar_eigvalue_mult;   /* 0.01  voxel_grid_covariance_omp.h:187 */
-  int search_method;                /* 0 KDTREE (default, :96), 2 DIRECT7, 3 DIRECT1 (pclomp::NeighborSearchMethod values) */
+  int search_method;                /* 0 KDTREE (default, :96), 1 DIRECT26, 2 DIRECT7, 3 DIRECT1 (pclomp::NeighborSearchMethod values) */
   /* accepted for interface compatibility (PointCloudOdometry.cc:189,191-193), no effect -- as in the reference's NDT */
   double max_correspondence_distance;
   int ransac_iterations;

@@ -745,7 +745,7 @@ class OdometryB200:
                 "workers_busy_s": a[4], "workers_wait_s": a[5]}
 
 
-NDT_KDTREE, NDT_DIRECT7, NDT_DIRECT1 = 0, 2, 3
+NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
 
 
 class NdtB200:

@@ -256,12 +256,12 @@ ndt_eval_group_kernel(const NdtCtl* __restrict__ ctl, NdtTargetView tv, NdtGauss
           }
         }
       } else {
-        const int nrel = tv.method == NDT_DIRECT1 ? 1 : 7;
-        if (sub < nrel) {
-          const int sl = ndt_direct_probe(tv, sub, q0, q1, q2);
+        const int nrel = ndt_direct_count(tv.method);
+        for (int r = sub; r < nrel; r += NDT_GRP) {
+          const int sl = ndt_direct_probe(tv, r, q0, q1, q2);
           if (sl >= 0) {
             const int pos = atomicAdd(&shit_n[pt], 1);
-            shit_slot[pt][pos] = sl; shit_key[pt][pos] = (float)sub;      // visited in the order of the relative cells
+            shit_slot[pt][pos] = sl; shit_key[pt][pos] = (float)r;        // visited in the order of the relative cells
           }
         }
       }
@@ -578,8 +578,8 @@ int lb_ndt_set_params(lb_ndt* h, const lb_ndt_params* p) {
     set_error("lb_ndt_set_params: resolution / step / outlier ratio / epsilon must be positive, min_points_per_voxel >= 3");
     return LB_ERR_INVALID_ARG;
   }
-  if (p->search_method != NDT_KDTREE && p->search_method != NDT_DIRECT7 && p->search_method != NDT_DIRECT1) {
-    set_error("lb_ndt_set_params: search_method must be 0 (KDTREE), 2 (DIRECT7) or 3 (DIRECT1)");
+  if (p->search_method < NDT_KDTREE || p->search_method > NDT_DIRECT1) {
+    set_error("lb_ndt_set_params: search_method must be 0 (KDTREE), 1 (DIRECT26), 2 (DIRECT7) or 3 (DIRECT1)");
     return LB_ERR_UNSUPPORTED;
   }
   // setResolution re-initialises the voxel structure of the current target (ndt_omp.h:124-131); the same holds for the

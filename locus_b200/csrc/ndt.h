@@ -26,7 +26,7 @@
 
 namespace lb {
 
-enum { NDT_KDTREE = 0, NDT_DIRECT7 = 2, NDT_DIRECT1 = 3 };          // pclomp::NeighborSearchMethod
+enum { NDT_KDTREE = 0, NDT_DIRECT26 = 1, NDT_DIRECT7 = 2, NDT_DIRECT1 = 3 };   // pclomp::NeighborSearchMethod
 enum { NDT_WANT_NONE = 0, NDT_WANT_DERIV_H = 1, NDT_WANT_DERIV = 2, NDT_WANT_HESSIAN = 3 };
 constexpr int NDT_NSUM = 43;                                        // score, gradient (6), Hessian (36)
 constexpr int NDT_MAX_NB = 32;                                      // a ball of one voxel side meets at most 27 voxels
@@ -214,14 +214,32 @@ LB_HD bool ndt_kd_probe(const NdtTargetView& tv, int cx, int cy, int cz, float q
   d2 = (dx * dx + dy * dy) + dz * dz;
   return d2 < tv.r2;
 }
-// DIRECT7 / DIRECT1: the r-th relative cell (own cell, +x, -x, +y, -y, +z, -z) -> slot of a usable voxel, or -1
+// Relative cells of the DIRECT methods in the order the reference visits them.  DIRECT7 / DIRECT1: own cell, +x, -x, +y, -y,
+// +z, -z (voxel_grid_covariance_omp_impl.hpp:413-440).  DIRECT26: pcl::getAllNeighborCellIndices() -- the 13 "half" offsets
+// ((i, j, -1) for i, j in -1..1; (i, -1, 0) for i in -1..1; (-1, 0, 0)) followed by their negatives; the own cell is NOT among them.
+LB_HD int ndt_direct_count(int method) { return method == NDT_DIRECT1 ? 1 : (method == NDT_DIRECT7 ? 7 : 26); }
+LB_HD void ndt_direct_rel(int method, int r, int* d) {
+  if (method != NDT_DIRECT26) {
+    const int REL[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    d[0] = REL[r][0]; d[1] = REL[r][1]; d[2] = REL[r][2];
+    return;
+  }
+  const int h = r % 13, sgn = r < 13 ? 1 : -1;
+  int i, j, k;
+  if (h < 9) { i = h / 3 - 1; j = h % 3 - 1; k = -1; }
+  else if (h < 12) { i = h - 10; j = -1; k = 0; }
+  else { i = -1; j = 0; k = 0; }
+  d[0] = sgn * i; d[1] = sgn * j; d[2] = sgn * k;
+}
+// the r-th relative cell -> slot of a usable voxel, or -1
 LB_HD int ndt_direct_probe(const NdtTargetView& tv, int r, float qx, float qy, float qz) {
-  const int REL[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+  int rel[3];
+  ndt_direct_rel(tv.method, r, rel);
   const int ijk[3] = {(int)floorf(qx / tv.leaf), (int)floorf(qy / tv.leaf), (int)floorf(qz / tv.leaf)};
   int idx = 0, mul = 1;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    const int c = ijk[a] + REL[r][a];
+    const int c = ijk[a] + rel[a];
     if (c < tv.min_b[a] || c > tv.max_b[a]) return -1;
     idx += (c - tv.min_b[a]) * mul;
     mul *= tv.div_b[a];
@@ -252,7 +270,7 @@ LB_HD int ndt_neighbours(const NdtTargetView& tv, float qx, float qy, float qz, 
         }
     return k;
   }
-  const int nrel = tv.method == NDT_DIRECT1 ? 1 : 7;
+  const int nrel = ndt_direct_count(tv.method);
   for (int r = 0; r < nrel; r++) {
     const int s = ndt_direct_probe(tv, r, qx, qy, qz);
     if (s >= 0) slot[k++] = s;

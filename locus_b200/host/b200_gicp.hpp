@@ -146,7 +146,7 @@ class B200Ndt {
   void setResolution(float r) { p_.resolution = r; apply(); }          // re-initialises the current target's voxels (ndt_omp.h:124-131)
   void setStepSize(double s) { p_.step_size = s; apply(); }
   void setOulierRatio(double r) { p_.outlier_ratio = r; apply(); }     // the reference's spelling (ndt_omp.h:166)
-  void setNeighborhoodSearchMethod(int m) { p_.search_method = m; apply(); }   // 0 KDTREE, 2 DIRECT7, 3 DIRECT1
+  void setNeighborhoodSearchMethod(int m) { p_.search_method = m; apply(); }   // 0 KDTREE, 1 DIRECT26, 2 DIRECT7, 3 DIRECT1
   float getResolution() const { return p_.resolution; }
   double getStepSize() const { return p_.step_size; }
   double getOulierRatio() const { return p_.outlier_ratio; }

@@ -234,7 +234,7 @@ typedef struct {
   int max_iterations;              /* :94  35;  LOCUS passes its icp_iterations (PointCloudOdometry.cc:190) */
   int min_points_per_voxel;        /* voxel_grid_covariance_omp.h:186  6 */
   double min_covar_eigvalue_mult;  /* voxel_grid_covariance_omp.h:187  0.01 */
-  int search_method;               /* 0 KDTREE (default, ndt_omp_impl.hpp:96), 2 DIRECT7, 3 DIRECT1 */
+  int search_method;               /* 0 KDTREE (default, ndt_omp_impl.hpp:96), 1 DIRECT26, 2 DIRECT7, 3 DIRECT1 */
   int num_threads;
 } og_ndt_params;
 

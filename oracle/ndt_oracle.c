@@ -29,7 +29,8 @@
  * threshold; Matrix3d::inverse is the cofactor formula;
  * Transform::rotation() is the linear part itself; eulerAngles(0,1,2) follows
  * Eigen 3.3's published formula; FLANN's radius search is strict (d2 < r2) and
- * ordered by (d2, index); std::map iteration = ascending voxel index.
+ * ordered by (d2, index); std::map iteration = ascending voxel index;
+ * pcl::getAllNeighborCellIndices (DIRECT26) is restated from PCL 1.10.
  */
 #include "lb_oracle.h"
 
@@ -318,13 +319,24 @@ static int neighbourhood(const og_ndt_target* t, const float q[3], const ndt_lea
     return k;
   }
   static const int REL7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
-  const int nrel = t->P.search_method == 3 ? 1 : 7;
+  /* DIRECT26 = pcl::getAllNeighborCellIndices() (pcl/filters/voxel_grid.h, NOT in the reference tree; restated from PCL 1.10):
+   * the 13 "half" offsets -- (i, j, -1) for i, j in -1..1, then (i, -1, 0) for i in -1..1, then (-1, 0, 0) -- followed by
+   * their negatives.  The point's own cell is not among them (voxel_grid_covariance_omp_impl.hpp:403-411). */
+  int rel26[26][3];
+  if (t->P.search_method == 1) {
+    int n = 0;
+    for (int i = -1; i < 2; i++) for (int j = -1; j < 2; j++) { rel26[n][0] = i; rel26[n][1] = j; rel26[n][2] = -1; n++; }
+    for (int i = -1; i < 2; i++) { rel26[n][0] = i; rel26[n][1] = -1; rel26[n][2] = 0; n++; }
+    rel26[n][0] = -1; rel26[n][1] = 0; rel26[n][2] = 0; n++;
+    for (int m = 0; m < 13; m++) for (int a = 0; a < 3; a++) rel26[13 + m][a] = -rel26[m][a];
+  }
+  const int nrel = t->P.search_method == 3 ? 1 : (t->P.search_method == 1 ? 26 : 7);
   int ijk[3];
   for (int a = 0; a < 3; a++) ijk[a] = (int)floorf(q[a] / t->leaf);   /* voxel_grid_covariance_omp_impl.hpp:378-380 */
   for (int r = 0; r < nrel; r++) {
     int ok = 1, idx = 0;
     for (int a = 0; a < 3; a++) {
-      int c = ijk[a] + REL7[r][a];
+      int c = ijk[a] + (t->P.search_method == 1 ? rel26[r][a] : REL7[r][a]);
       if (c < t->min_b[a] || c > t->max_b[a]) ok = 0;
       idx += (c - t->min_b[a]) * t->divb_mul[a];
     }

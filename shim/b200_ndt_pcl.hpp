@@ -43,7 +43,7 @@ class B200NormalDistributionsTransform : public Registration<PointF, PointF> {
   double getStepSize() const { return p_.step_size; }
   void setOulierRatio(double r) { p_.outlier_ratio = r; }
   double getOulierRatio() const { return p_.outlier_ratio; }
-  void setNeighborhoodSearchMethod(int m) { p_.search_method = m; }       // pclomp::KDTREE 0, DIRECT7 2, DIRECT1 3
+  void setNeighborhoodSearchMethod(int m) { p_.search_method = m; }       // pclomp::KDTREE 0, DIRECT26 1, DIRECT7 2, DIRECT1 3
   void setNumThreads(int n) { p_.num_threads = n; }
   void enableTimingOutput(bool e) { p_.enable_timing_output = e; }
   double getTransformationProbability() const { return res_.trans_probability; }

@@ -30,13 +30,16 @@ def test_oracle_recovers_known_offset(oracle):
     M = oracle.ndt_pose_to_matrix(pose).astype(np.float64)
     Mi = np.linalg.inv(M)
     s1 = (s0.astype(np.float64) @ Mi[:3, :3].T + Mi[:3, 3]).astype(np.float32)
-    for method in (0, 2, 3):
+    for method in (0, 1, 2, 3):
         T = oracle.NdtTarget(s0, oracle.ndt_params(num_threads=4, transformation_epsilon=1e-3, search_method=method))
         r = T.align(s1)
         assert r["status"] == 0 and r["converged"]
-        assert np.abs(r["pose"][:3] - pose[:3]).max() < 2e-3 and np.abs(r["pose"][3:] - pose[3:]).max() < 5e-4, (method, r["pose"])
+        # DIRECT26 visits the 26 cells AROUND the point's own cell and not that cell itself (pcl::getAllNeighborCellIndices):
+        # it converges to a slightly biased pose
+        bar = 6e-3 if method == 1 else 2e-3
+        assert np.abs(r["pose"][:3] - pose[:3]).max() < bar and np.abs(r["pose"][3:] - pose[3:]).max() < 5e-4, (method, r["pose"])
         dt, dr = F.pose_delta(r["T"], M.astype(np.float32))
-        assert dt < 2e-3 and dr < 1e-3
+        assert dt < bar and dr < 1e-3
 
 
 def test_oracle_pose_matrix_round_trip(oracle):
@@ -145,7 +148,7 @@ class _HT:
                 "trans_probability": tp.value}
 
 
-@pytest.mark.parametrize("method", [0, 2, 3])
+@pytest.mark.parametrize("method", [0, 1, 2, 3])
 def test_product_headers_match_oracle(ndt_harness, oracle, method):
     """ndt.h (what the CUDA kernels run per voxel / per point / in the controller thread) with a serial backend:
     voxel Gaussians and the double-precision Hessian pass bit-identical to the oracle; the float pass to ~1e-10 (the
