@@ -4,18 +4,22 @@
 //
 //   lb_ndt_set_target    setInputTarget -> init() -> VoxelGridCovariance::filter(true)
 //                        (ndt_omp.h:116-119,257-262; voxel_grid_covariance_omp_impl.hpp:48-370):
-//                        ndt_gather -> ndt_keys -> stable radix sort (prims.cu) -> ndt_heads -> scan -> ndt_gaussians
-//                        -> ndt_hash_insert.  One thread per voxel walks its points in input order (the reference's
-//                        accumulation order), so means / inverse covariances / centroids are reproducible bit for bit.
-//   lb_ndt_align         computeTransformation (ndt_omp_impl.hpp:100-208) as a stream-ordered chain
-//                        [ndt_eval_kernel, ndt_ctl_kernel] x evaluations: the evaluation grid computes the score,
-//                        gradient and Hessian terms of every source point against the voxels around it (float per-pair
-//                        terms, double sums: warp shuffle -> CTA -> one partial per CTA), the one-block controller
-//                        kernel adds the partials in CTA order and runs the Newton step / More-Thuente line search
-//                        state machine of ndt.h, then posts the next transform.  The host enqueues a batch of pairs
-//                        and reads the controller back once per batch; pairs after the end return at once.
+//                        ndt_gather -> ndt_keys -> stable radix sort (prims.cu) -> ndt_heads -> scan -> ndt_head_pos ->
+//                        ndt_gaussians -> ndt_hash_insert.  One warp per voxel fetches its points 32 at a time and adds
+//                        them in input order (the reference's accumulation order), so means / inverse covariances /
+//                        centroids are reproducible bit for bit.
+//   lb_ndt_align         computeTransformation (ndt_omp_impl.hpp:100-208) as a stream-ordered chain of
+//                        [evaluation, ndt_ctl_kernel] steps.  An evaluation computes the score / gradient / Hessian terms
+//                        of every source point against the voxels around it: float per-pair terms and double sums as in
+//                        the reference, eight lanes per point (ndt_eval_group_kernel) for the float passes, one thread per
+//                        point (ndt_eval_kernel) for the closing double-precision Hessian pass; one partial row per CTA.
+//                        The one-CTA controller kernel adds the rows in a fixed shape and runs the Newton step (6x6
+//                        Jacobi SVD on its first warp) / More-Thuente line search state machine of ndt.h, then posts the
+//                        next request.  The host enqueues a batch of steps and reads the controller back once per batch;
+//                        the specialisations a request does not name, and steps after the end, return at once.
 //
-// Everything is HBM/L2-bound gather work (96-byte voxel records behind a hash lookup); no contraction, no tensor cores.
+// Latency-bound gather work over L1 / L2 resident data (96-byte voxel records behind a hash lookup, a few MB per pass); no
+// contraction, no tensor cores.
 #include <algorithm>
 #include <chrono>
 #include <new>
@@ -27,7 +31,7 @@
 namespace lb {
 
 constexpr int NDT_EVAL_THREADS = 128;
-constexpr int NDT_BATCH = 8;            // [eval, ctl] pairs enqueued between two looks at the controller
+constexpr int NDT_BATCH = 8;            // [evaluation, controller] steps enqueued between two looks at the controller
 
 __global__ void __launch_bounds__(256)
 ndt_gather_kernel(const uint8_t* __restrict__ base, uint32_t n, uint32_t stride, uint32_t xyz_off, f4* __restrict__ out,
