@@ -229,3 +229,16 @@ def test_neighbourhood_search_exact_vs_kdtree(ndt_harness, oracle, resolution):
         assert counts[i] == len(idx) and np.array_equal(slots[i, :counts[i]], idx), (i, q[i], counts[i], idx)
         n_multi += len(idx) > 1
     assert n_multi > 1000 and counts.max() <= 27
+
+
+def test_oracle_pose_conventions_vs_scipy(oracle):
+    """Independent cross-check of the pose <-> matrix conventions: Translation * Rx * Ry * Rz = scipy's intrinsic 'XYZ'
+    Euler angles, and eulerAngles(0, 1, 2) returns them (first angle >= 0 here, where Eigen's range folding is the identity)."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        ang = np.array([rng.uniform(0.0, 1.2), rng.uniform(-1.2, 1.2), rng.uniform(-3.0, 3.0)])
+        p = np.concatenate([rng.uniform(-3, 3, 3), ang])
+        M = oracle.ndt_pose_to_matrix(p)
+        assert np.abs(M[:3, :3] - R.from_euler("XYZ", ang).as_matrix()).max() < 2e-6
+        assert np.abs(oracle.ndt_euler_xyz(M) - R.from_matrix(M[:3, :3].astype(np.float64)).as_euler("XYZ")).max() < 2e-6
