@@ -242,3 +242,57 @@ def test_oracle_pose_conventions_vs_scipy(oracle):
         M = oracle.ndt_pose_to_matrix(p)
         assert np.abs(M[:3, :3] - R.from_euler("XYZ", ang).as_matrix()).max() < 2e-6
         assert np.abs(oracle.ndt_euler_xyz(M) - R.from_matrix(M[:3, :3].astype(np.float64)).as_euler("XYZ")).max() < 2e-6
+
+
+def test_oracle_derivatives_vs_independent_score(oracle):
+    """The oracle's gradient and Hessian (the reference's closed-form angle tables, float32 per-pair terms) against finite
+    differences of an INDEPENDENT float64 restatement of the NDT score (Magnusson 2009 eq. 6.9-6.10) with the neighbourhoods
+    frozen at the evaluation pose -- then the score is smooth and the differences are accurate.  Pins the 8 + 15 rows of the
+    angle tables, the placement of the second-derivative blocks and the sign / scale of every term (measured: score 6e-8, gradient
+    4e-7, Hessian 6e-5 relative -- the last one is the finite-difference error)."""
+    from scipy.spatial import cKDTree
+    from scipy.spatial.transform import Rotation as R
+    s0, s1, _ = _scans()
+    src = s1[::3].copy()
+    T = oracle.NdtTarget(s0, oracle.ndt_params(num_threads=4))
+    L = T.leaves()
+    ok = L["nr_points"] > 0
+    cen = L["centroid"].astype(np.float64); mean = L["mean"]; icov = L["icov"].reshape(-1, 3, 3)
+    c1 = 10 * (1 - 0.55); c2 = 0.55 / 1.0 ** 3
+    d3 = -np.log(c2); d1 = -np.log(c1 + c2) - d3; d2 = -2 * np.log((-np.log(c1 * np.exp(-0.5) + c2) - d3) / d1)
+    p0 = np.array([0.03, -0.02, 0.01, 0.006, -0.009, 0.012])
+    x = src.astype(np.float64)
+
+    def transform(p):
+        return x @ R.from_euler("XYZ", p[3:]).as_matrix().T + p[:3]
+
+    q0 = (x @ oracle.ndt_pose_to_matrix(p0)[:3, :3].astype(np.float64).T + oracle.ndt_pose_to_matrix(p0)[:3, 3].astype(np.float64))
+    nb = cKDTree(cen).query_ball_point(q0, 1.0 - 1e-6)
+    pi = np.concatenate([np.full(len(n), i) for i, n in enumerate(nb)]).astype(np.int64)
+    vi = np.concatenate([np.array(n, dtype=np.int64) for n in nb])
+    keep = ok[vi]; pi, vi = pi[keep], vi[keep]
+    assert len(pi) > 3 * len(src)
+
+    def score(p):
+        d = transform(p)[pi] - mean[vi]
+        m = np.einsum("ni,nij,nj->n", d, icov[vi], d)
+        return float(np.sum(-d1 * np.exp(-d2 * m / 2)))
+
+    sc, g, H = T.derivatives(src, oracle.ndt_pose_to_matrix(p0), p0)
+    assert abs(sc - score(p0)) < 1e-6 * abs(sc)
+    e = 1e-5
+    gn = np.array([(score(p0 + e * np.eye(6)[k]) - score(p0 - e * np.eye(6)[k])) / (2 * e) for k in range(6)])
+    assert np.abs(gn - g).max() < 1e-5 * np.abs(g).max(), (g, gn)
+    e = 2e-4
+    Hn = np.zeros((6, 6))
+    f0 = score(p0)
+    for a in range(6):
+        ea = e * np.eye(6)[a]
+        Hn[a, a] = (score(p0 + ea) - 2 * f0 + score(p0 - ea)) / e ** 2
+        for b in range(a + 1, 6):
+            eb = e * np.eye(6)[b]
+            Hn[a, b] = Hn[b, a] = (score(p0 + ea + eb) - score(p0 + ea - eb) - score(p0 - ea + eb) + score(p0 - ea - eb)) / (4 * e ** 2)
+    print("ndt independent check: score rel %.2e, gradient rel %.2e, hessian rel %.2e" % (abs(sc - score(p0)) / abs(sc), np.abs(gn - g).max() / np.abs(g).max(), np.abs(Hn - H).max() / np.abs(H).max()))
+    assert np.abs(Hn - H).max() < 5e-4 * np.abs(H).max(), np.abs(Hn - H).max() / np.abs(H).max()
+    Hd = T.hessian(src, oracle.ndt_pose_to_matrix(p0), p0)
+    assert np.abs(Hn - Hd).max() < 5e-4 * np.abs(Hd).max()
