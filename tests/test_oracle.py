@@ -147,3 +147,57 @@ def test_reference_pose_depends_on_summation_order():
         out[i] = F.pose_delta(a["T"], b["T"])
     assert out[1][0] == 0.0 and out[1][1] == 0.0            # pair 0 -> 1: decisive, bit-identical under re-association
     assert out[13][0] > 3e-4                                  # pair 12 -> 13: 0.6 mm apart
+
+
+def test_gicp_objective_vs_independent(oracle):
+    """og_gicp_fdf (gicp.hpp:290-402: f and its 6 partial derivatives with the closed-form rotation derivative table) against
+    an independent float64 restatement: applyState = Rz(yaw) Ry(pitch) Rx(roll), f = sum r'Mr / m with r = R p + t - q, and
+    central differences of that f.  The oracle rounds T p to float32 (as the reference does): its f carries ~1e-7 relative
+    noise, the gradient is compared at 1e-4."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(7)
+    m = 4000
+    p = rng.uniform(-20, 20, (m, 3)).astype(np.float32)
+    x = np.array([0.11, -0.07, 0.03, 0.012, -0.02, 0.035])
+    A = rng.normal(0, 1, (m, 3, 3)); M = A @ np.transpose(A, (0, 2, 1)) + 0.1 * np.eye(3)
+    Rx = R.from_euler("ZYX", [x[5], x[4], x[3]]).as_matrix()
+    assert np.abs(oracle.apply_state(x)[:3, :3] - Rx).max() < 1e-6 and np.array_equal(oracle.apply_state(x)[:3, 3], x[:3].astype(np.float32))
+    q = (p.astype(np.float64) @ Rx.T + x[:3] + rng.normal(0, 0.05, (m, 3))).astype(np.float32)
+    src4 = np.concatenate([p, np.ones((m, 1), np.float32)], 1); tgt4 = np.concatenate([q, np.ones((m, 1), np.float32)], 1)
+
+    def f64(s):
+        r = p.astype(np.float64) @ R.from_euler("ZYX", [s[5], s[4], s[3]]).as_matrix().T + s[:3] - q.astype(np.float64)
+        return float(np.einsum("ni,nij,nj->", r, M, r) / m)
+
+    f, g = oracle.fdf(src4, tgt4, M.reshape(m, 9), x)
+    assert abs(f - f64(x)) < 1e-5 * abs(f)
+    e = 1e-6
+    gn = np.array([(f64(x + e * np.eye(6)[k]) - f64(x - e * np.eye(6)[k])) / (2 * e) for k in range(6)])
+    assert np.abs(gn - g).max() < 1e-4 * np.abs(g).max(), (g, gn)
+
+
+def test_covariances_and_normals_vs_numpy(oracle):
+    """k-NN(20) covariances (gicp.hpp:85-154) and PCL normals (normals_oracle.c) against numpy: neighbours from scipy's
+    kd-tree, eigen-decomposition of the sample covariance; GICP's regularised covariance is I - (1 - eps) n n' with n the
+    eigenvector of the smallest eigenvalue, PCL's normal is that n turned towards the viewpoint and its curvature
+    l0 / (l0 + l1 + l2).  Points whose two smallest eigenvalues nearly coincide (n ill-defined) are left out."""
+    from scipy.spatial import cKDTree
+    pts = F.random_scene(6000, 3)
+    k, eps = 20, 1e-3
+    cov = oracle.covariances(pts, k, eps, 4)
+    nrm = oracle.normals_knn(pts, k, (0.0, 0.0, 0.0), 4)
+    _, nn = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k)
+    checked = 0
+    for i in range(0, len(pts), 13):
+        nb = pts[nn[i]].astype(np.float64)
+        w, E = np.linalg.eigh(np.cov(nb.T, ddof=0))
+        if w[1] < 4 * w[0] or w[0] < 1e-9:
+            continue
+        n = E[:, 0]
+        ref = np.eye(3) - (1 - eps) * np.outer(n, n)
+        assert np.abs(cov[i] - ref).max() < 2e-4, (i, cov[i], ref)      # the reference's moments are sums of FLOAT products (gicp.hpp:119-126)
+        if np.dot(n, -pts[i].astype(np.float64)) < 0:
+            n = -n
+        assert np.dot(nrm[i, :3], n) > 1 - 1e-5 and abs(nrm[i, 3] - w[0] / w.sum()) < 2e-3, (i, nrm[i], n, w[0] / w.sum())   # PCL: float accumulators
+        checked += 1
+    assert checked > 150
