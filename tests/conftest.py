@@ -87,6 +87,8 @@ def ndt_harness():
     H.hn_target_free.argtypes = [vp]
     H.hn_target_info.argtypes = [vp] * 4
     H.hn_target_leaves.argtypes = [vp] * 6
+    H.hn_svd6_rounds.argtypes = [vp, vp, vp]
+    H.hn_svd6_serial.argtypes = [vp, vp, vp]
     H.hn_neighbours.argtypes = [vp, vp, C.c_int, vp, vp]
     H.hn_eval.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]
     H.hn_align.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_int] + [vp] * 6

@@ -108,6 +108,39 @@ void hn_neighbours(void* hp, const float* q, int n, int* counts, int* slots) {
   for (int i = 0; i < n; i++) counts[i] = ndt_neighbours(h->tv, q[3 * i], q[3 * i + 1], q[3 * i + 2], slots + (size_t)i * NDT_MAX_NB);
 }
 
+// The Newton solve as the controller warp runs it (ndt.cu, ndt_svd6_solve_warp), emulated serially: the three column pairs of a
+// round are rotated from the SAME pre-round state (all alpha / beta / gamma and angles first, then all updates), which is what
+// lanes working side by side do.  Must equal ndt_svd6_solve bit for bit because the pairs of a round are disjoint.
+void hn_svd6_rounds(const double* A, const double* b, double* x) {
+  double U[6][6], V[6][6];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) { U[i][j] = A[6 * i + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool any = false;
+    for (int r = 0; r < 5; r++) {
+      int p[3], q[3]; double c[3], s[3]; bool rot[3];
+      for (int g = 0; g < 3; g++) {
+        ndt_svd6_pair(3 * r + g, p[g], q[g]);
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < 6; k++) { alpha += U[k][p[g]] * U[k][p[g]]; beta += U[k][q[g]] * U[k][q[g]]; gamma += U[k][p[g]] * U[k][q[g]]; }
+        rot[g] = ndt_svd6_angle(alpha, beta, gamma, c[g], s[g]);
+      }
+      for (int g = 0; g < 3; g++) {
+        if (!rot[g]) continue;
+        any = true;
+        for (int k = 0; k < 6; k++) {
+          double up = U[k][p[g]], uq = U[k][q[g]], vp = V[k][p[g]], vq = V[k][q[g]];
+          U[k][p[g]] = c[g] * up - s[g] * uq; U[k][q[g]] = s[g] * up + c[g] * uq;
+          V[k][p[g]] = c[g] * vp - s[g] * vq; V[k][q[g]] = s[g] * vp + c[g] * vq;
+        }
+      }
+    }
+    if (!any) break;
+  }
+  ndt_svd6_finish(U, V, b, x);
+}
+void hn_svd6_serial(const double* A, const double* b, double* x) { ndt_svd6_solve(A, b, x); }
+
 static void eval_serial(HNdt* h, const float* src, int n, int stride_f, const float* T, const NdtAngles& A, int want, double* sums) {
   for (int k = 0; k < NDT_NSUM; k++) sums[k] = 0;
   for (int i = 0; i < n; i++) {

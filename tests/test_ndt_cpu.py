@@ -296,3 +296,25 @@ def test_oracle_derivatives_vs_independent_score(oracle):
     assert np.abs(Hn - H).max() < 5e-4 * np.abs(H).max(), np.abs(Hn - H).max() / np.abs(H).max()
     Hd = T.hessian(src, oracle.ndt_pose_to_matrix(p0), p0)
     assert np.abs(Hn - Hd).max() < 5e-4 * np.abs(Hd).max()
+
+
+def test_newton_solve_rounds_equal_serial(ndt_harness):
+    """The 6x6 Newton solve: (i) rotating the three disjoint column pairs of a round side by side (what the controller warp
+    does on the device) gives the same bits as the serial sweep; (ii) the result is the (pseudo-)inverse solution -- numpy's
+    lstsq -- for well-conditioned, nearly symmetric Hessian-like matrices, for ill-conditioned ones (1e10) and for a
+    rank-deficient one (Eigen's rank threshold drops the null direction)."""
+    rng = np.random.default_rng(9)
+    xs = np.zeros(6); xr = np.zeros(6)
+    for trial in range(200):
+        B = rng.normal(0, 1, (6, 6))
+        A = B @ B.T * 10.0 ** rng.uniform(-2, 6) + rng.normal(0, 1e-7, (6, 6))        # nearly symmetric, like the float Hessian
+        if trial % 4 == 1:
+            Uq, _ = np.linalg.qr(B); A = Uq @ np.diag(10.0 ** np.linspace(0, -10, 6)) @ Uq.T
+        if trial % 4 == 2:
+            A[:, 5] = A[:, 4]; A[5, :] = A[4, :]                                       # rank 5
+        A = np.ascontiguousarray(A); b = np.ascontiguousarray(rng.normal(0, 1, 6))
+        ndt_harness.hn_svd6_serial(_p(A), _p(b), _p(xs)); ndt_harness.hn_svd6_rounds(_p(A), _p(b), _p(xr))
+        assert np.array_equal(xs, xr), trial
+        ref = np.linalg.lstsq(A, b, rcond=6 * np.finfo(float).eps)[0]
+        cond = np.linalg.cond(A) if trial % 4 != 2 else 1e6
+        assert np.abs(xs - ref).max() <= 1e-9 * max(cond, 1e3) * max(np.abs(ref).max(), 1e-300) / 1e3, (trial, xs, ref)
