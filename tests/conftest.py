@@ -91,5 +91,6 @@ def ndt_harness():
     H.hn_svd6_serial.argtypes = [vp, vp, vp]
     H.hn_neighbours.argtypes = [vp, vp, C.c_int, vp, vp]
     H.hn_eval.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]
+    H.hn_eval_grouped.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]
     H.hn_align.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_double, C.c_double, C.c_int] + [vp] * 6
     return H

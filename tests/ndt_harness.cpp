@@ -157,6 +157,78 @@ static void eval_serial(HNdt* h, const float* src, int n, int stride_f, const fl
   }
 }
 
+// The float passes as ndt_eval_group_kernel organises them (ndt.cu), emulated serially: candidate cells probed "eight at a
+// time" in lane order (so hits arrive in an order unrelated to their distance), ranked by (key, slot), pairs computed in
+// rounds of eight, and each sum accumulated over the pairs in rank order; per-point subtotals added in point order.
+// Must equal eval_serial bit for bit: it is the same arithmetic in the same association.
+void hn_eval_grouped(void* hp, const float* src, int n, int stride_f, const float* T, const double* p6, int want, double* sums) {
+  HNdt* h = (HNdt*)hp;
+  const NdtTargetView& tv = h->tv;
+  NdtAngles A;
+  ndt_angles(p6, A);
+  const bool hess = want == NDT_WANT_DERIV_H;
+  const int NT = hess ? NDT_NSUM : 7;
+  for (int k = 0; k < NDT_NSUM; k++) sums[k] = 0;
+  for (int i = 0; i < n; i++) {
+    const float* x = src + (size_t)i * stride_f;
+    float q0, q1, q2;
+    xform_pcl(T, x[0], x[1], x[2], q0, q1, q2);
+    int hit_slot[64]; float hit_key[64]; int nh = 0;
+    if (tv.method == NDT_KDTREE) {
+      const float q[3] = {q0, q1, q2};
+      int lo[3], hi[3];
+      ndt_kd_range(tv, q, lo, hi);
+      const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+      if (nx > 0 && ny > 0 && nz > 0) {
+        const int ncell = nx * ny * nz, nxy = nx * ny;
+        const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
+        for (int sub = 7; sub >= 0; sub--)                         // lanes in some order
+          for (int c = sub; c < ncell; c += 8) {
+            const int iz = (int)(((float)c + 0.5f) * inv_nxy), rem = c - iz * nxy;
+            const int iy = (int)(((float)rem + 0.5f) * inv_nx);
+            if (iz != c / nxy || iy != rem / nx) { sums[0] = NAN; return; }    // the float-reciprocal decode must be exact
+            int sl; float d2;
+            if (ndt_kd_probe(tv, lo[0] + (rem - iy * nx), lo[1] + iy, lo[2] + iz, q0, q1, q2, sl, d2)) { hit_slot[nh] = sl; hit_key[nh] = d2; nh++; }
+          }
+      }
+    } else {
+      const int nrel = ndt_direct_count(tv.method);
+      for (int sub = 7; sub >= 0; sub--)
+        for (int r = sub; r < nrel; r += 8) {
+          const int sl = ndt_direct_probe(tv, r, q0, q1, q2);
+          if (sl >= 0) { hit_slot[nh] = sl; hit_key[nh] = (float)r; nh++; }
+        }
+    }
+    int sorted[64];
+    for (int a = 0; a < nh; a++) {
+      int rank = 0;
+      for (int o = 0; o < nh; o++) rank += (hit_key[o] < hit_key[a] || (hit_key[o] == hit_key[a] && hit_slot[o] < hit_slot[a])) ? 1 : 0;
+      sorted[rank] = hit_slot[a];
+    }
+    double acc[NDT_NSUM];
+    for (int k = 0; k < NDT_NSUM; k++) acc[k] = 0;
+    if (nh > 0) {
+      float xj[8], xh[16], pg[3][6], ph[6][3];
+      for (int r = 0; r < 8; r++) xj[r] = ndt_row_dot(A.jf, r, x[0], x[1], x[2]);
+      if (hess) for (int r = 0; r < 15; r++) xh[r] = ndt_row_dot(A.hf, r, x[0], x[1], x[2]);
+      ndt_point_derivs_place(xj, xh, hess, pg, ph);
+      for (int base = 0; base < nh; base += 8) {
+        float term[8][NDT_NSUM];
+        const int m = std::min(8, nh - base);
+        for (int sub = 0; sub < m; sub++) {
+          float t[NDT_NSUM];
+          const bool ok = hess ? ndt_pair_terms_f<true>(h->G, pg, ph, q0, q1, q2, tv.vox[sorted[base + sub]], t)
+                               : ndt_pair_terms_f<false>(h->G, pg, ph, q0, q1, q2, tv.vox[sorted[base + sub]], t);
+          for (int e = 0; e < NT; e++) term[sub][e] = ok ? t[e] : 0.0f;
+        }
+        for (int c = 0; c < NT; c++)
+          for (int jj = 0; jj < m; jj++) acc[c] += (double)term[jj][c];
+      }
+    }
+    for (int k = 0; k < NDT_NSUM; k++) sums[k] += acc[k];
+  }
+}
+
 void hn_eval(void* hp, const float* src, int n, int stride_f, const float* T16, const double* p6, int want, double* sums43) {
   HNdt* h = (HNdt*)hp;
   NdtAngles A;

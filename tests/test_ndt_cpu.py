@@ -318,3 +318,23 @@ def test_newton_solve_rounds_equal_serial(ndt_harness):
         ref = np.linalg.lstsq(A, b, rcond=6 * np.finfo(float).eps)[0]
         cond = np.linalg.cond(A) if trial % 4 != 2 else 1e6
         assert np.abs(xs - ref).max() <= 1e-9 * max(cond, 1e3) * max(np.abs(ref).max(), 1e-300) / 1e3, (trial, xs, ref)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3])
+def test_grouped_evaluation_equals_per_point(ndt_harness, method):
+    """The organisation of ndt_eval_group_kernel (eight lanes per point: cells probed in lane order, hits ranked by (key, slot),
+    pairs in rounds of eight, every sum accumulated over the pairs in rank order) emulated serially with the helpers the kernel
+    calls: bit-identical sums to the one-thread-per-point form, for both float passes -- the discovery order of the hits does
+    not matter, and the float-reciprocal cell decode is exact."""
+    s0, s1, _ = _scans()
+    h = _HT(ndt_harness, s0, method=method)
+    src = np.ascontiguousarray(s1[:6000], dtype=np.float32)
+    pose = np.array([0.05, -0.02, 0.01, 0.01, -0.02, 0.015])
+    from oracle import oracle as O
+    M = np.ascontiguousarray(O.ndt_pose_to_matrix(pose).reshape(16))
+    for want in (1, 2):
+        a = np.zeros(43); b = np.zeros(43)
+        ndt_harness.hn_eval(h.h, _p(src), len(src), 3, _p(M), _p(pose), want, _p(a))
+        ndt_harness.hn_eval_grouped(h.h, _p(src), len(src), 3, _p(M), _p(pose), want, _p(b))
+        assert np.isfinite(b).all() and np.array_equal(a, b), (method, want, np.abs(a - b).max())
+        assert a[0] != 0
